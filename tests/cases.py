@@ -1,0 +1,151 @@
+"""Shared definitions of the golden cases (must stay in sync with oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from vitta_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TANET_CASES = {
+    "tanet_t8_r64_consis_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=3,
+                                   lr=1e-3, moving_avg=True),
+    "tanet_t8_r64_stats_mse": dict(K=101, T=8, N=2, M=1, res=64, reg_type="mse_loss", consis=False, steps=2,
+                                   lr=1e-3, moving_avg=True),
+    "tanet_t16_r224_stats_l1": dict(K=101, T=16, N=1, M=1, res=224, reg_type="l1_loss", consis=False, steps=1,
+                                    lr=1e-3, moving_avg=True),
+}
+
+SWIN_CASES = {
+    "swin_tiny_t16_r112_consis_l1": dict(K=101, T=16, N=1, M=2, res=112, embed_dim=64, depths=[2, 2], heads=[2, 4],
+                                         window=(8, 7, 7), reg_type="l1_loss", consis=True, steps=2, lr=1e-3,
+                                         chosen=["module.backbone.layers.1", "module.backbone.norm"],
+                                         momentum_mvg=0.05, lambda_consis=0.05),
+    "swin_tiny_t32_r56_stats_l1": dict(K=101, T=32, N=2, M=1, res=56, embed_dim=32, depths=[2, 2, 2], heads=[1, 2, 4],
+                                       window=(8, 7, 7), reg_type="l1_loss", consis=False, steps=2, lr=1e-3,
+                                       chosen=["module.backbone.layers.1", "module.backbone.layers.2",
+                                               "module.backbone.norm"],
+                                       momentum_mvg=0.05, lambda_consis=0.05, sample_views=False),
+}
+
+
+def load_golden(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    return np.load(path, allow_pickle=False)
+
+
+def golden_exists(name):
+    return os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def case_inputs(cfg, arch, tag, n_batches, seed):
+    """List of per-step loader tensors exactly as make_golden feeds the reference."""
+    out = []
+    for b in range(n_batches):
+        v = synth.synth_video(cfg["N"], cfg["M"] if tag == "tta" else 1, cfg["T"], cfg["res"], seed=seed + b,
+                              gauss_sigma=0.38 if tag != "clean" else 0.0, tag=tag)
+        out.append(synth.tanet_loader_tensor(v) if arch == "tanet" else synth.swin_loader_tensor(v))
+    return out
+
+
+def tta_inputs(cfg, arch):
+    return case_inputs(cfg, arch, "tta", cfg["steps"], 200), case_inputs(cfg, arch, "eval", cfg["steps"], 300)
+
+
+def tanet_state_template(num_class, t):
+    """name -> shape of TSN(resnet50, tam=True) without building any module (used for synth weights)."""
+    from oracle.vitta_oracle import RESNET50_STAGES
+    sd = {}
+
+    def bn(p, c):
+        for leaf in ("weight", "bias", "running_mean", "running_var"):
+            sd[p + "." + leaf] = torch.empty(c)
+        sd[p + ".num_batches_tracked"] = torch.empty((), dtype=torch.long)
+    sd["base_model.conv1.weight"] = torch.empty(64, 3, 7, 7)
+    bn("base_model.bn1", 64)
+    cin = 64
+    for li, (wdt, nblk, _) in enumerate(RESNET50_STAGES, 1):
+        for b in range(nblk):
+            p = "base_model.layer%d.%d" % (li, b)
+            sd[p + ".net.conv1.weight"] = torch.empty(wdt, cin, 1, 1)
+            bn(p + ".net.bn1", wdt)
+            sd[p + ".net.conv2.weight"] = torch.empty(wdt, wdt, 3, 3)
+            bn(p + ".net.bn2", wdt)
+            sd[p + ".net.conv3.weight"] = torch.empty(wdt * 4, wdt, 1, 1)
+            bn(p + ".net.bn3", wdt * 4)
+            if b == 0:
+                sd[p + ".net.downsample.0.weight"] = torch.empty(wdt * 4, cin, 1, 1)
+                bn(p + ".net.downsample.1", wdt * 4)
+            sd[p + ".tam.G.0.weight"] = torch.empty(2 * t, t)
+            bn(p + ".tam.G.1", 2 * t)
+            sd[p + ".tam.G.3.weight"] = torch.empty(3, 2 * t)
+            sd[p + ".tam.L.0.weight"] = torch.empty(wdt // 4, wdt, 3)
+            bn(p + ".tam.L.1", wdt // 4)
+            sd[p + ".tam.L.3.weight"] = torch.empty(wdt, wdt // 4, 1)
+            cin = wdt * 4
+    sd["new_fc.weight"] = torch.empty(num_class, 2048)
+    sd["new_fc.bias"] = torch.empty(num_class)
+    return sd
+
+
+def swin_state_template(num_class, embed_dim, depths, heads, window=(8, 7, 7), patch=(2, 4, 4)):
+    from oracle.vitta_oracle import swin_rel_index
+    sd = {}
+    p = "backbone."
+    sd[p + "patch_embed.proj.weight"] = torch.empty(embed_dim, 3, *patch)
+    sd[p + "patch_embed.proj.bias"] = torch.empty(embed_dim)
+    sd[p + "patch_embed.norm.weight"] = torch.empty(embed_dim)
+    sd[p + "patch_embed.norm.bias"] = torch.empty(embed_dim)
+    nbias = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1)
+    for i, dep in enumerate(depths):
+        c = embed_dim * 2 ** i
+        for b in range(dep):
+            q = "%slayers.%d.blocks.%d." % (p, i, b)
+            sd[q + "norm1.weight"] = torch.empty(c)
+            sd[q + "norm1.bias"] = torch.empty(c)
+            sd[q + "attn.relative_position_bias_table"] = torch.empty(nbias, heads[i])
+            sd[q + "attn.relative_position_index"] = swin_rel_index(window)
+            sd[q + "attn.qkv.weight"] = torch.empty(3 * c, c)
+            sd[q + "attn.qkv.bias"] = torch.empty(3 * c)
+            sd[q + "attn.proj.weight"] = torch.empty(c, c)
+            sd[q + "attn.proj.bias"] = torch.empty(c)
+            sd[q + "norm2.weight"] = torch.empty(c)
+            sd[q + "norm2.bias"] = torch.empty(c)
+            sd[q + "mlp.fc1.weight"] = torch.empty(4 * c, c)
+            sd[q + "mlp.fc1.bias"] = torch.empty(4 * c)
+            sd[q + "mlp.fc2.weight"] = torch.empty(c, 4 * c)
+            sd[q + "mlp.fc2.bias"] = torch.empty(c)
+        if i < len(depths) - 1:
+            q = "%slayers.%d.downsample." % (p, i)
+            sd[q + "reduction.weight"] = torch.empty(2 * c, 4 * c)
+            sd[q + "norm.weight"] = torch.empty(4 * c)
+            sd[q + "norm.bias"] = torch.empty(4 * c)
+    cl = embed_dim * 2 ** (len(depths) - 1)
+    sd[p + "norm.weight"] = torch.empty(cl)
+    sd[p + "norm.bias"] = torch.empty(cl)
+    sd["cls_head.fc_cls.weight"] = torch.empty(num_class, cl)
+    sd["cls_head.fc_cls.bias"] = torch.empty(num_class)
+    return sd
+
+
+def src_stats_from_golden(g):
+    i = 0
+    m, v = [], []
+    while "src_mean/%d" % i in g:
+        m.append(g["src_mean/%d" % i])
+        v.append(g["src_var/%d" % i])
+        i += 1
+    return m, v
+
+
+def assert_close(actual, expected, rtol, atol, what=""):
+    a = np.asarray(actual, np.float64)
+    e = np.asarray(expected, np.float64)
+    assert a.shape == e.shape, "%s: shape %s vs %s" % (what, a.shape, e.shape)
+    err = np.abs(a - e)
+    tol = atol + rtol * np.abs(e)
+    if not np.all(err <= tol):
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError("%s: max violation at %s: got %r want %r (|err|=%g tol=%g); max|err|=%g" % (
+            what, i, a[i], e[i], err[i], tol[i], err.max()))
