@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- clips/s per ViTTA adaptation step (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): configs[1] of BASELINE.json -- TANet-R50 ViTTA, synthetic gauss-corrupted
+16x224x224 clips, 8 videos per GPU (weak scaling), one view, statistics-alignment loss only (L1), SGD over all
+parameters.  A step = train-mode forward with the 47 alignment hooks + backward + SGD on one batch.
+
+  value      device-timed throughput with the batch already resident in HBM
+  e2e        the same step through the public API (OnlineAdapter.adapt) from PINNED HOST input, with the H2D copy
+             and a D2H read of the loss inside the timed region
+  roofline   the statistics kernel (K1) over the 29 hooked layer shapes: algorithmic bytes / CUDA-event time
+  cpu_baseline  the oracle port of the reference step timed on the host cores (bounded sample: 1 clip)
+
+`--impl reference` times the CPU port alone (the reference is Python + torch-CPU and cannot travel to the GPU
+box; oracle/vitta_oracle.py is its pinned restatement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_CLASSES, T, RES, N_PER_GPU = 101, 16, 224, 8
+HOOKED_ELEMS_PER_CLIP = 44556288          # SURVEY.md 8a row a2 (29 BN2d outputs of layer3+layer4, T=16)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
+
+
+def cpu_port_clips_per_s(steps=2, warmup=1):
+    """The reference step (fwd with 47 hooks + bwd + SGD over all parameters) on the host cores, via the oracle
+    port, on a bounded sample: 1 video x 1 view x 16 x 224 x 224 per step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    from oracle import vitta_oracle as O
+    from vitta_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(cases.tanet_state_template(K_CLASSES, T), seed=1)
+    names = [n for n, k in O.tanet_norm_layers() if k != "bn1d"]
+    # fabricated source statistics: zeros/ones are enough for timing (sign() of anything is as expensive)
+    import numpy as np
+    src_m = [np.zeros(sd[n + ".weight"].shape[0], np.float32) for n in names]
+    src_v = [np.ones(sd[n + ".weight"].shape[0], np.float32) for n in names]
+    st = O.TTAState(sd, "tanet", T, src_m, src_v, ["layer3", "layer4"], "l1_loss", True, 0.1, lr=5e-5)
+    x = synth.synth_video(1, 1, T, RES, seed=200, tag="tta").view(1, T, 3, RES, RES)
+    for _ in range(warmup):
+        st.adapt_step(x, 1, 1, False, dropout_p=0.8)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.adapt_step(x, 1, 1, False, dropout_p=0.8)
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    v, cores, dt = cpu_port_clips_per_s(steps, warm)
+    sample = "1 video x 1 view x 16x224x224 per step, %d timed steps after %d warm-up (oracle port of the reference " \
+             "step: fwd + 47 hooks + bwd + SGD), torch-CPU fp32, %d threads" % (steps, warm, cores)
+    line = {"impl": "reference", "metric": "clips/sec per TTA step", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, stats-align only (L1), "
+                                   "SGD all params; CPU port on a bounded sample", "clips_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def stats_kernel_roofline(dev, n_clips, iters=20):
+    """K1 over the 29 hooked (layer3 + layer4) BN output shapes of the workload, channels-last as the model
+    stores them.  Buffers total 1.43 GB per pass (> 126 MB L2, and each tensor is read once)."""
+    import torch
+    from vitta_b200 import _lib
+    from vitta_b200._lib import call, ptr, stream_ptr
+    f = n_clips * T
+    shapes = [(256, 784)] + [(256, 196), (1024, 196), (1024, 196)]
+    for _ in range(5):
+        shapes += [(256, 196), (256, 196), (1024, 196)]
+    shapes += [(512, 196), (512, 49), (2048, 49), (2048, 49)]
+    for _ in range(2):
+        shapes += [(512, 49), (512, 49), (2048, 49)]
+    assert len(shapes) == 29
+    elems = sum(c * hw for c, hw in shapes) * f
+    assert elems == HOOKED_ELEMS_PER_CLIP * n_clips, (elems, HOOKED_ELEMS_PER_CLIP * n_clips)
+    bufs = []
+    for c, hw in shapes:
+        x = torch.randn(f * hw, c, device=dev)
+        ch = _lib.chunking(f * hw, c, 1, 1)
+        part = torch.empty(ch.n_entries * c * 2, device=dev)
+        bufs.append((x, part, f * hw, c))
+    st = stream_ptr()
+    def one_pass():
+        for x, part, rows, c in bufs:
+            call("vitta_stats_partial", ptr(x), rows, c, 1, 1, ptr(part), st)
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return elems * 4, ms, len(bufs)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vitta_b200
+    from vitta_b200 import _lib, synth
+    from vitta_b200.corpus.basics import OnlineAdapter, compute_statistics
+    from vitta_b200.models.tanet_models.tanet import TSN
+    from vitta_b200.utils.opts import default_args
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: vitta_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    vitta_b200.set_fp32_exact()
+    torch.backends.cudnn.benchmark = True          # reference corpus/main_eval.py:77
+    _lib.load()
+
+    model = TSN(K_CLASSES, T, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
+                non_local=False, partial_bn=False)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=1))
+    model = model.to(dev)
+    n = N_PER_GPU
+    targs = default_args(arch='tanet', clip_length=T, batch_size=n, n_augmented_views=1, if_pred_consistency=False,
+                         num_classes=K_CLASSES, input_size=RES)
+
+    # source statistics from a clean synthetic batch through our own compute_statistics (untimed set-up)
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, x):
+            self.x = x
+
+        def __len__(self):
+            return self.x.shape[0]
+
+        def __getitem__(self, i):
+            return self.x[i], 0
+    clean = synth.tanet_loader_tensor(synth.synth_video(2, 1, T, RES, seed=100, gauss_sigma=0.0, tag="clean"))
+    sargs = default_args(arch='tanet', clip_length=T, batch_size=2, num_classes=K_CLASSES, input_size=RES,
+                         stat_type='spatiotemp', result_dir=None)
+    sargs.dataset_factory = lambda a, split, dataset_type: DS(clean)
+    stats = compute_statistics(model, sargs)
+    adapter = OnlineAdapter(model, targs, stats, pg)
+
+    host = synth.tanet_loader_tensor(synth.synth_video(n, 1, T, RES, seed=200 + rank, tag="tta")).pin_memory()
+    resident = host.to(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        adapter.adapt(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms_total = timed(lambda: adapter.adapt(resident), args.steps)
+    launches = _lib.launch_count - l0
+    ms_step = ms_total / args.steps
+    value = world * n * 1000.0 / ms_step
+
+    def e2e_step():
+        x = host.to(dev, non_blocking=True)
+        r = adapter.adapt(x)
+        r["loss_reg"].item()
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+
+    def with_eval():
+        adapter.adapt(resident)
+        adapter.hooks_off()
+        adapter.evaluate(resident)
+        adapter.hooks_on()
+    with_eval()
+    ms_eval = timed(with_eval, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, which = _peaks()
+    bytes_pass, ms_k1, n_launch = stats_kernel_roofline(dev, n)
+    achieved = bytes_pass / (ms_k1 * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "stats_cl_kernel (K1, 29 hooked layers/pass)", "achieved": achieved, "peak": peak,
+            "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "bytes_per_launch": bytes_pass / n_launch, "us_per_launch": ms_k1 * 1e3 / n_launch}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, dt = cpu_port_clips_per_s(2, 1)
+        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+               "sample": "1 video x 1 view x 16x224x224 per step, 2 timed steps after 1 warm-up, torch-CPU fp32"}
+    line = {"metric": "clips/sec per TTA step", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, batch 8 per GPU, 1 view, "
+                                   "stats-align only (L1, 47 hooks), SGD all params (BASELINE.json configs[1])",
+                       "clips_per_step": world * n, "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
+                       "conv_backend": "cuDNN fp32 (TF32 off)", "with_eval_fwd_clips_per_s": world * n * 1000.0 / ms_eval},
+            "e2e": {"value": world * n * 1000.0 / ms_e2e, "unit": "clips/s",
+                    "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * vitta_b200 -- C-ABI of the B200 (sm_100a) kernels behind ViTTA's test-time-adaptation inner loop.
+ *
+ * The reference (wlin-at/ViTTA) is pure Python and has no FFI today; every entry point below cites the
+ * reference code whose arithmetic it replaces.  The Python host side (vitta_b200/_lib.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are owned by the caller
+ *     (PyTorch allocations) and only borrowed for the duration of the call;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, a positive cudaError_t value on a CUDA failure, a negative VITTA_E_*
+ *     on bad arguments.  Nothing throws or exits across the ABI.  vitta_last_error() gives a message;
+ *   - all arithmetic is IEEE fp32 ("f32"), statistics are merged with Chan's parallel formula;
+ *   - "rows x C, channels-last" means element (r, c) at r*C + c.  TANet activations are stored NHWC
+ *     (rows = frame*H*W + h*W + w); Video-Swin tokens are (B, D, H, W, C) already.
+ */
+#ifndef VITTA_B200_H
+#define VITTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITTA_E_BADARG (-1)
+#define VITTA_E_ALIGN (-2)
+#define VITTA_E_UNSUPPORTED (-3)
+
+#define VITTA_REG_L1 0  /* reg_type 'l1_loss'  utils/norm_stats_utils.py:538 */
+#define VITTA_REG_MSE 1 /* reg_type 'mse_loss' utils/norm_stats_utils.py:536 */
+#define VITTA_REG_KLD 2 /* reg_type 'kld'      utils/norm_stats_utils.py:8-16,540 */
+
+int vitta_version(void);
+const char* vitta_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int vitta_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  per-channel spatio-temporal statistics (partials)
+ *   replaces: feature.view().permute().contiguous(); output.mean((0,2,3,4));
+ *             output.permute(1,0,2,3,4).contiguous().view(c,-1).var(1, unbiased=False)
+ *             utils/norm_stats_utils.py:188-193, 222-236, 242-243 (and :93-95 in ComputeNormStatsHook)
+ *
+ * A feature is described as (outer O, channels C, inner I): element (o,c,i) at (o*C + c)*I + i.
+ *   BN2d output (N*T, C, H, W) contiguous:      O = N*T, I = H*W
+ *   BN3d output (N, C, T, H, W) contiguous:     O = N,   I = T*H*W
+ *   channels-last / LayerNorm output (rows, C): O = rows, I = 1
+ * The kernel reads the feature exactly once and writes, per chunk e of the reduction domain and per
+ * channel, a (mean, M2) pair: part[(e*C + c)*2 + {0,1}].  vitta_stats_chunking() gives the number of
+ * chunks and the element count of each.  Chunks never straddle a "frame" of
+ * `frame_rows` reduction elements (frame_rows = H*W for per-frame layouts, or O*I for none) so the same
+ * partials can also give per-frame pooled sums.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VittaChunking {
+  int32_t chunk_rows;       /* elements per channel in a full chunk */
+  int32_t chunks_per_frame; /* chunks per frame; the last chunk of every frame may be ragged */
+  int64_t frame_rows;       /* reduction elements per channel per frame */
+  int32_t n_entries;        /* total number of chunks = (mean, M2) entries per channel */
+  int32_t reserved;
+} VittaChunking;
+/* `frames` only matters for I == 1 (must divide O; pass 1 when there is no frame structure). */
+int vitta_stats_chunking(int64_t O, int C, int64_t I, int64_t frames, VittaChunking* out);
+int vitta_stats_partial(const float* x, int64_t O, int C, int64_t I, int64_t frames, float* part, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  merge + EMA + alignment loss + backward coefficients, all hooked layers in ONE launch
+ *   replaces: MovingAverageTensor.update / AverageMeterTensor.update   utils/utils_.py:190-211
+ *             compute_regularization / compute_kld                     utils/norm_stats_utils.py:8-16,531-542
+ *             and prepares the closed-form backward of both (autograd in the reference).
+ *
+ * Layer table entry (host fills it once, uploads it; all offsets are in floats into the arenas).
+ * For entry e of layer l the per-channel pair is  part[part_off + e*entry_stride + c*2 + {0,1}]  with element
+ * count  counts ? counts[cnt_off + e*cnt_stride] : min(chunk_rows, frame_rows - (e % chunks_per_frame)*chunk_rows).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VittaLayerDesc {
+  int32_t C;                /* channels */
+  int32_t n_entries;        /* partial entries to merge (chunks, or ranks after the all-gather) */
+  int32_t chunk_rows;       /* elements per channel in a full chunk */
+  int32_t chunks_per_frame; /* chunks per frame (ragged last chunk of each frame) */
+  int64_t frame_rows;       /* reduction elements per channel per frame */
+  int64_t part_off;         /* offset of this layer's (mean,M2) pairs in `part` */
+  int64_t entry_stride;     /* floats between consecutive entries (2*C locally; 2*sum(C) after an all-gather) */
+  int64_t cnt_off;          /* counts[cnt_off + e*cnt_stride] (only read when counts != NULL) */
+  int64_t cnt_stride;
+  int64_t ch_off;           /* offset of this layer's channel vectors in every per-channel arena */
+  int32_t reg_type;         /* VITTA_REG_* */
+  int32_t has_source;       /* 0: statistics only (ComputeNormStatsHook), no EMA/loss/coefficients */
+  float w_new;              /* meter: avg = w_new*stat + w_old*avg.detach()  (EMA: alpha, 1-alpha;      */
+  float w_old;              /*        AverageMeterTensor: n/count_new, count_old/count_new)              */
+} VittaLayerDesc;
+
+/* Per-channel arenas (length = sum of C over layers): src_mean, src_var (read), ema_mean, ema_var
+ * (read-modify-write), batch_mean, batch_var (write), coef_a, coef_b (write):
+ *     dLoss_l/dy[.., c, ..] = coef_a[c] + coef_b[c] * y          
+ * loss[l] receives r_feature of layer l; loss[n_layers] their sum (summed in layer order by the last CTA
+ * to finish); loss[n_layers+1] is an int32 ticket the caller zero-initialises once (self-resetting).
+ * merge_only != 0: only merge entries and write (mean, M2) pairs to merged[(ch_off + c)*2 + {0,1}] and
+ * the count (as int32) to merged_counts[l] -- the per-rank payload of the multi-GPU all-gather. */
+int vitta_stats_finalize(const VittaLayerDesc* descs, int n_layers, const float* part, const int32_t* counts,
+                         const float* src_mean, const float* src_var, float* ema_mean, float* ema_var,
+                         float* batch_mean, float* batch_var, float* coef_a, float* coef_b, float* loss,
+                         int merge_only, float* merged, int32_t* merged_counts, void* stream);
+
+/* K3  standalone backward of the alignment loss of one layer (used by hooks on stock torch modules):
+ *     gy[o,c,i] = (*gscale) * (coef_a[c] + coef_b[c] * y[o,c,i]),  y = yscale[c]*x + yshift[c] when the
+ *     two affine vectors are given (BatchNorm eval output recomputed from its saved input), else y = x.
+ *   replaces: autograd of var/mean/permute/contiguous, utils/norm_stats_utils.py:242-253 */
+int vitta_stats_inject(const float* x, const float* yscale, const float* yshift, const float* coef_a,
+                       const float* coef_b, const float* gscale, float* gy, int64_t O, int C, int64_t I,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  fused BatchNorm(eval) [+ statistics partials] [+ residual (optionally through a second BN, with its
+ *     own statistics)] [+ ReLU] [+ per-chunk column sums of the result], channels-last.
+ *   replaces: bn -> forward hook -> relu / add -> relu in TemporalBottleneck.forward,
+ *             models/tanet_models/temporal_module.py:88-104; adaptive_avg_pool2d in TAM.forward :50 and
+ *             the ResNet avgpool (tanet.py:145).
+ *   y  = (x - rm) * (w * rsqrt(rv + eps)) + b                      main branch, statistics on y
+ *   r  = res (raw)  or  BN2(res)  (statistics on BN2(res))         optional
+ *   out = relu?(y + r)
+ *   pool_part[(e*C + c)] = sum over the rows of chunk e of out     optional (same chunking as K1), then
+ *   pool_out[f*C + c]    = mean over the frame_rows rows of frame f of out
+ * bn = {weight, bias, running_mean, running_var} each (C,).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VittaBN {
+  const float* weight;
+  const float* bias;
+  const float* running_mean;
+  const float* running_var;
+  float eps;
+} VittaBN;
+
+int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                     float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                     int64_t frame_rows, int C, void* stream);
+
+/* Backward of K4 in one pass.  Reads gout, x (and res if res_bn), recomputes y; writes gx (and gres):
+ *   gpre = gout * (out > 0)           [out recomputed]   (+ gpool[frame, c] / frame_rows: gpool is the gradient of
+ *                                                         pool_out, spread over every row of the frame; applied
+ *                                                         to `out`, i.e. before the ReLU mask)
+ *   gy   = gpre + gs_main * (a[c] + b[c]*y)      gx   = gy * k[c]
+ *   gr   = gpre (+ gs_res*(a2[c] + b2[c]*r) and gres = gr*k2[c] when res_bn)
+ *   gw[c] += sum gy * xhat, gb[c] += sum gy  (and the same for the residual BN), accumulated into the
+ *   given gradient vectors deterministically (per-chunk partials in `ws`, last CTA reduces).
+ * ws: workspace of vitta_bn_act_bwd_ws_floats() floats, zero-initialised ONCE by the caller (self-resetting).
+ *   replaces: autograd of the chain above + of the hook statistics. */
+int64_t vitta_bn_act_bwd_ws_floats(int64_t frames, int64_t frame_rows, int C);
+int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* gs_main,
+                     const float* coef_a2, const float* coef_b2, const float* gs_res, float* gx, float* gres,
+                     float* gw, float* gb, float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows,
+                     int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  TAM temporal stencil, channels-last.  x, out: (N, T, HW, C); kern: (N, 3, C); act: (N, T, C)
+ *   out[n,t,p,c] = sum_k kern[n,k,c] * act[n,t+k-1,c] * x[n,t+k-1,p,c]   (zero padded in t)
+ *   replaces: new_x * local_activation; F.conv2d(groups=N*C) and both permute().contiguous() copies,
+ *             models/tanet_models/temporal_module.py:47-48,56-63
+ * Backward: gx, and per-chunk partial correlations dpart[n, chunk, t, k, c] = sum_p gout[n,t-k+1,p,c]*x[n,t,p,c]
+ *   (chunks = vitta_tam_num_chunks) from which d kern and d act follow on (N,C)-sized data. */
+int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                  void* stream);
+int vitta_tam_num_chunks(int64_t HW, int C);
+int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
+                  int N, int T, int64_t HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10 prediction consistency, forward + gradient in one launch.  preds (B, V, K) logits.
+ *   loss = (1/V) sum_v sum_{b,k} | softmax(preds[b,v]) - mean_v softmax |, mean NOT detached
+ *   replaces: compute_pred_consis, utils/pred_consistency_utils.py:15-31 */
+int vitta_pred_consis(const float* preds, int B, int V, int K, float* loss, float* grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11 multi-tensor SGD with momentum and weight decay (torch.optim.SGD semantics, dampening 0, no nesterov)
+ *   d = g + wd*p;  buf = first ? d : mom*buf + d;  p -= lr*buf
+ *   replaces: torch.optim.SGD(model.parameters(), lr, momentum, weight_decay).step(), corpus/basics.py:559-560,671
+ * Tensor table entries live in device memory.  Every CTA updates one block of vitta_sgd_block_elems()
+ * elements of one tensor: block_start[i] (device, int32, ascending) is the first block of tensor i and
+ * total_blocks the grid size.  first_step != 0 initialises the momentum buffers (buf = d).
+ * grad_scale multiplies g before use (1/world_size after a summed all-reduce). */
+typedef struct VittaSgdTensor {
+  float* p;
+  const float* g;
+  float* buf;
+  int64_t n;
+} VittaSgdTensor;
+int vitta_sgd_block_elems(void);
+int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
+                   float lr, float momentum, float weight_decay, int first_step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITTA_B200_H */

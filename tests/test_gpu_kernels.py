@@ -1,0 +1,306 @@
+"""GPU parity: every kernel of the C-ABI (through the Python operators that bind it) against the CPU oracle and the
+golden vectors produced by the unmodified reference.  fp32; tolerance rtol 1e-4 (BASELINE.json north_star) plus an
+absolute floor scaled to the data."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import cases
+from oracle import vitta_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def units():
+    return cases.load_golden("units")
+
+
+@pytest.fixture(autouse=True)
+def _fp32(cuda_device):
+    import vitta_b200
+    vitta_b200.set_fp32_exact()
+    from vitta_b200.utils import norm_stats_utils as nsu
+    nsu.reset_arenas()
+    nsu.set_process_group(None)
+
+
+def _mod(kind, c):
+    return {"bn2d": nn.BatchNorm2d(c), "bn3d": nn.BatchNorm3d(c), "ln": nn.LayerNorm(c)}[kind]
+
+
+@pytest.mark.parametrize("kind", ["bn2d", "bn3d", "ln"])
+@pytest.mark.parametrize("reg", ["l1_loss", "mse_loss", "kld"])
+@pytest.mark.parametrize("mavg", [1, 0])
+def test_align_hook_vs_reference_golden(units, cuda_device, kind, reg, mavg):
+    """Generic hook path (K1 + K2 + K3) on the exact tensors the reference hook saw; r_feature, EMA and the
+    gradient w.r.t. the feature must match the reference's autograd."""
+    from vitta_b200.utils.norm_stats_utils import CombineNormStatsRegHook_onereg
+    key = "hook/%s/%s/%d" % (kind, reg, mavg)
+    mod = _mod(kind, 6).to(cuda_device).eval()
+    hook = CombineNormStatsRegHook_onereg(
+        mod, clip_len=4, spatiotemp_stats_clean_tuple=(units[key + "/src_mean"], units[key + "/src_var"]),
+        reg_type=reg, moving_avg=bool(mavg), momentum=0.1 if reg != "kld" else 0.9, stat_type_list=["spatiotemp"],
+        reduce_dim=True, before_norm=False, if_sample_tta_aug_views=True, n_augmented_views=2)
+    for s in range(3):
+        feat = torch.from_numpy(units["%s/s%d/feat" % (key, s)]).to(cuda_device).requires_grad_(True)
+        out = feat * 1.0
+        hook.hook_fn(mod, (out,), out)   # same protocol as make_golden: the "layer output" is feat*1
+        r = hook.r_feature
+        r.backward()
+        cases.assert_close(r.detach().cpu(), units["%s/s%d/r" % (key, s)], RTOL, 1e-6, key + "/r")
+        cases.assert_close(hook.ema_mean.cpu(), units["%s/s%d/ema_mean" % (key, s)], RTOL, 1e-6, "ema_mean")
+        cases.assert_close(hook.ema_var.cpu(), units["%s/s%d/ema_var" % (key, s)], RTOL, 1e-6, "ema_var")
+        g = units["%s/s%d/grad" % (key, s)]
+        cases.assert_close(feat.grad.cpu(), g, RTOL, 1e-6 * float(np.abs(g).max()), "grad")
+
+
+@pytest.mark.parametrize("kind", ["bn2d", "bn3d", "ln"])
+@pytest.mark.parametrize("st", ["spatiotemp", "temp", "temp_v2", "spatial"])
+def test_stat_hook_vs_reference_golden(units, cuda_device, kind, st):
+    from vitta_b200.utils.norm_stats_utils import ComputeNormStatsHook
+    key = "stat/%s/%s" % (kind, st)
+    mod = _mod(kind, 6).to(cuda_device).eval()
+    hook = ComputeNormStatsHook(mod, clip_len=4, stat_type=st, before_norm=False, batch_size=2)
+    feat = torch.from_numpy(units[key + "/feat"]).to(cuda_device)
+    with torch.no_grad():
+        hook.hook_fn(mod, (feat,), feat)
+    cases.assert_close(hook.batch_mean.cpu(), units[key + "/mean"], RTOL, 1e-6, key + "/mean")
+    cases.assert_close(hook.batch_var.cpu(), units[key + "/var"], RTOL, 1e-6, key + "/var")
+
+
+@pytest.mark.parametrize("running", [1, 0])
+def test_bns_hook_vs_reference_golden(units, cuda_device, running):
+    from vitta_b200.utils.BNS_utils import BNFeatureHook
+    key = "bns/%d" % running
+    mod = nn.BatchNorm2d(6).to(cuda_device).eval()
+    mod.running_mean.copy_(torch.from_numpy(units[key + "/running_mean"]))
+    mod.running_var.copy_(torch.from_numpy(units[key + "/running_var"]))
+    hook = BNFeatureHook(mod, reg_type="l1_loss", running_manner=bool(running), use_src_stat_in_reg=True, momentum=0.1)
+    for s in range(2):
+        x = torch.from_numpy(units["%s/s%d/x" % (key, s)]).to(cuda_device).requires_grad_(True)
+        xin = x * 1.0
+        hook.hook_fn(mod, (xin,), None)
+        r = hook.r_feature
+        r.backward()
+        cases.assert_close(r.detach().cpu(), units["%s/s%d/r" % (key, s)], RTOL, 1e-6, key)
+        g = units["%s/s%d/grad" % (key, s)]
+        cases.assert_close(x.grad.cpu(), g, RTOL, 1e-6 * float(np.abs(g).max()), key)
+
+
+@pytest.mark.parametrize("shape", ["2_2_101", "3_4_17", "1_2_400"])
+def test_pred_consis_vs_reference_golden(units, cuda_device, shape):
+    from vitta_b200.utils.pred_consistency_utils import compute_pred_consis
+    key = "consis/" + shape
+    p = torch.from_numpy(units[key + "/preds"]).to(cuda_device).requires_grad_(True)
+    loss = compute_pred_consis(p)
+    (loss * 1.0).backward()
+    cases.assert_close(loss.detach().cpu(), units[key + "/loss"], RTOL, 1e-6, key)
+    g = units[key + "/grad"]
+    cases.assert_close(p.grad.cpu(), g, 2e-4, 2e-6 * float(np.abs(g).max()), key)
+
+
+@pytest.mark.parametrize("shape", ["2_8_16_5_7", "1_16_32_7_7"])
+def test_tam_vs_reference_golden(units, cuda_device, shape):
+    """TAM module of ours (K5 stencil + torch G/L) vs the reference module's forward/backward."""
+    from vitta_b200 import synth
+    from vitta_b200.models.tanet_models.temporal_module import TAM
+    key = "tam/" + shape
+    n, t, c, h, w = (int(v) for v in shape.split("_"))
+    tam = TAM(c, t)
+    tam.load_state_dict(synth.synth_state_dict(tam.state_dict(), seed=5))
+    tam = tam.to(cuda_device).train()
+    for m in tam.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            m.eval()
+    x = torch.from_numpy(units[key + "/x"]).to(cuda_device).requires_grad_(True)
+    y = tam(x)
+    cases.assert_close(y.detach().cpu(), units[key + "/y"], RTOL, 1e-6, key + "/y")
+    y.backward(torch.from_numpy(units[key + "/go"]).to(cuda_device))
+    gx = units[key + "/gx"]
+    cases.assert_close(x.grad.cpu(), gx, RTOL, 2e-6 * float(np.abs(gx).max()), key + "/gx")
+    for pn, p in tam.named_parameters():
+        gp = units["%s/gp/%s" % (key, pn)]
+        cases.assert_close(p.grad.cpu(), gp, 3e-4, 1e-5 * float(np.abs(gp).max()) + 1e-7, pn)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1/K2 at real layer shapes, both layouts, against the oracle (torch-CPU restatement)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,layout", [
+    ((16, 256, 14, 14), "nchw"), ((16, 256, 14, 14), "nhwc"), ((16, 2048, 7, 7), "nchw"), ((16, 2048, 7, 7), "nhwc"),
+    ((32, 64, 9, 5), "nhwc"), ((8, 24, 3, 3), "nhwc"), ((8, 6, 3, 3), "nchw"), ((16, 1024, 1, 1), "nchw"),
+])
+def test_stats_kernels_vs_oracle(cuda_device, shape, layout):
+    from vitta_b200.utils.norm_stats_utils import CombineNormStatsRegHook_onereg
+    g = torch.Generator().manual_seed(1)
+    f, c, h, w = shape
+    T = 8
+    mod = nn.BatchNorm2d(c).to(cuda_device).eval()
+    src_m = torch.randn(c, generator=g) * 0.3
+    src_v = torch.rand(c, generator=g) + 0.5
+    hook = CombineNormStatsRegHook_onereg(mod, clip_len=T, spatiotemp_stats_clean_tuple=(src_m.numpy(), src_v.numpy()),
+                                          reg_type="l1_loss", moving_avg=True, momentum=0.1,
+                                          stat_type_list=["spatiotemp"], before_norm=False,
+                                          if_sample_tta_aug_views=True, n_augmented_views=1)
+    tap = O.AlignTap("bn2d", T, src_m, src_v, "l1_loss", True, 0.1)
+    for s in range(2):
+        feat = (torch.randn(shape, generator=g) * (1.0 + s) + 3.0 * torch.randn(1, c, 1, 1, generator=g))
+        fo = feat.clone().requires_grad_(True)
+        tap(None, fo * 1.0)
+        tap.r_feature.backward()
+        fg = feat.to(cuda_device)
+        if layout == "nhwc":
+            fg = fg.contiguous(memory_format=torch.channels_last)
+        fg.requires_grad_(True)
+        out = fg * 1.0
+        hook.hook_fn(mod, (out,), out)
+        r = hook.r_feature
+        r.backward()
+        cases.assert_close(hook.batch_mean.cpu(), tap.batch_mean.detach(), RTOL, 1e-5, "mean")
+        cases.assert_close(hook.batch_var.cpu(), tap.batch_var.detach(), RTOL, 1e-6, "var")
+        cases.assert_close(r.detach().cpu(), tap.r_feature.detach(), RTOL, 1e-6, "r")
+        gmax = float(fo.grad.abs().max())
+        cases.assert_close(fg.grad.cpu(), fo.grad, RTOL, 2e-6 * gmax, "grad")
+
+
+def test_generic_hook_survives_inplace_relu(cuda_device):
+    """torchvision-style Bottleneck: BN output overwritten by ReLU(inplace=True) right after the hook."""
+    from vitta_b200.utils.norm_stats_utils import CombineNormStatsRegHook_onereg
+    g = torch.Generator().manual_seed(3)
+    c, T = 32, 4
+    conv = nn.Conv2d(8, c, 3, padding=1, bias=False)
+    bn = nn.BatchNorm2d(c)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.2, generator=g)
+        bn.running_var.uniform_(0.5, 2.0, generator=g)
+        bn.weight.uniform_(0.5, 1.5, generator=g)
+        bn.bias.normal_(0, 0.2, generator=g)
+    net_cpu = nn.Sequential(conv, bn, nn.ReLU(inplace=True)).eval()
+    import copy
+    net_gpu = copy.deepcopy(net_cpu).to(cuda_device)
+    src_m, src_v = torch.randn(c, generator=g) * 0.2, torch.rand(c, generator=g) + 0.5
+    hook = CombineNormStatsRegHook_onereg(net_gpu[1], clip_len=T, spatiotemp_stats_clean_tuple=(src_m.numpy(), src_v.numpy()),
+                                          reg_type="mse_loss", moving_avg=True, momentum=0.1,
+                                          stat_type_list=["spatiotemp"], before_norm=False)
+    tap = O.AlignTap("bn2d", T, src_m, src_v, "mse_loss", True, 0.1)
+    x = torch.randn(8, 8, 10, 10, generator=g)
+    # oracle
+    y = net_cpu[1](net_cpu[0](x))
+    tap(None, y)
+    z = F.relu(y)
+    (tap.r_feature + z.mean()).backward()
+    # ours
+    zz = net_gpu(x.to(cuda_device))
+    (hook.r_feature + zz.mean()).backward()
+    for (n1, p1), (n2, p2) in zip(net_cpu.named_parameters(), net_gpu.named_parameters()):
+        cases.assert_close(p2.grad.cpu(), p1.grad, 2e-4, 1e-6 * float(p1.grad.abs().max()), n1)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 fused BN/act/stats/pool fwd+bwd vs the oracle ops
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("res_mode", ["none", "raw", "bn"])
+@pytest.mark.parametrize("shape", [(16, 64, 12, 12), (8, 256, 7, 7), (8, 24, 5, 3)])
+@pytest.mark.parametrize("pool", [False, True])
+def test_bn_act_vs_oracle(cuda_device, res_mode, shape, pool):
+    from vitta_b200.nn import StatsBatchNorm2d, norm_act
+    from vitta_b200.utils.norm_stats_utils import CombineNormStatsRegHook_onereg
+    g = torch.Generator().manual_seed(5)
+    f, c, h, w = shape
+    T = 4
+
+    def mkbn():
+        bn = StatsBatchNorm2d(c)
+        with torch.no_grad():
+            bn.running_mean.normal_(0, 0.3, generator=g)
+            bn.running_var.uniform_(0.5, 2.0, generator=g)
+            bn.weight.uniform_(0.5, 1.5, generator=g)
+            bn.bias.normal_(0, 0.3, generator=g)
+        return bn.eval()
+    import copy
+    bn1, bn2 = mkbn(), mkbn()
+    bn1g, bn2g = copy.deepcopy(bn1).to(cuda_device), copy.deepcopy(bn2).to(cuda_device)
+    src = [(torch.randn(c, generator=g) * 0.3, torch.rand(c, generator=g) + 0.5) for _ in range(2)]
+    hooks = [CombineNormStatsRegHook_onereg(m, clip_len=T, spatiotemp_stats_clean_tuple=(s[0].numpy(), s[1].numpy()),
+                                            reg_type="l1_loss", moving_avg=True, momentum=0.1,
+                                            stat_type_list=["spatiotemp"], before_norm=False)
+             for m, s in zip((bn1g, bn2g), src)]
+    taps = [O.AlignTap("bn2d", T, s[0], s[1], "l1_loss", True, 0.1) for s in src]
+    for step in range(2):
+        x = torch.randn(shape, generator=g) * 1.5
+        r = torch.randn(shape, generator=g)
+        go = torch.randn(shape, generator=g)
+        gp = torch.randn(f, c, generator=g)
+        # oracle
+        xo, ro = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+        y = F.batch_norm(xo, bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, False, 0.0, bn1.eps)
+        taps[0](None, y)
+        total = taps[0].r_feature
+        if res_mode == "raw":
+            y = y + ro
+        elif res_mode == "bn":
+            y2 = F.batch_norm(ro, bn2.running_mean, bn2.running_var, bn2.weight, bn2.bias, False, 0.0, bn2.eps)
+            taps[1](None, y2)
+            total = total + 0.5 * taps[1].r_feature
+            y = y + y2
+        out = F.relu(y)
+        po = out.mean((2, 3))
+        for p in list(bn1.parameters()) + list(bn2.parameters()):
+            p.grad = None
+        (total + (out * go).sum() + ((po * gp).sum() if pool else 0.0)).backward()
+        # ours
+        xg = x.to(cuda_device).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        rg = r.to(cuda_device).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        for p in list(bn1g.parameters()) + list(bn2g.parameters()):
+            p.grad = None
+        outg, pg = norm_act(bn1g, xg, True, T, res=None if res_mode == "none" else rg,
+                            res_bn=bn2g if res_mode == "bn" else None, want_pool=pool)
+        tot = hooks[0].r_feature
+        if res_mode == "bn":
+            tot = tot + 0.5 * hooks[1].r_feature
+        (tot + (outg * go.to(cuda_device)).sum() + ((pg * gp.to(cuda_device)).sum() if pool else 0.0)).backward()
+        cases.assert_close(outg.detach().cpu(), out.detach(), RTOL, 1e-5, "out")
+        if pool:
+            cases.assert_close(pg.detach().cpu(), po.detach(), RTOL, 1e-5, "pool")
+        cases.assert_close(tot.detach().cpu(), total.detach(), RTOL, 1e-6, "loss")
+        cases.assert_close(xg.grad.cpu(), xo.grad, RTOL, 2e-6 * float(xo.grad.abs().max()), "gx")
+        if res_mode != "none":
+            cases.assert_close(rg.grad.cpu(), ro.grad, RTOL, 2e-6 * float(ro.grad.abs().max()), "gres")
+        pairs = [(bn1g, bn1)] + ([(bn2g, bn2)] if res_mode == "bn" else [])
+        for mg, mo in pairs:
+            cases.assert_close(mg.weight.grad.cpu(), mo.weight.grad, 2e-4, 2e-5 * float(mo.weight.grad.abs().max()), "gw")
+            cases.assert_close(mg.bias.grad.cpu(), mo.bias.grad, 2e-4, 2e-5 * float(mo.bias.grad.abs().max()), "gb")
+
+
+def test_fused_sgd_vs_torch(cuda_device):
+    from vitta_b200.ops import FusedSGD
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 3, 7, 7), (5,), (1000, 33), (4097,), (3, 3, 3), (256, 64, 1, 1)]
+    ref = [torch.randn(s, generator=g).requires_grad_(True) for s in shapes]
+    ours = [p.detach().clone().to(cuda_device).requires_grad_(True) for p in ref]
+    o1 = torch.optim.SGD(ref, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    o2 = FusedSGD(ours, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(ref, ours)):
+            if i == 1 and step < 2:      # a parameter without gradient for the first steps: must be skipped
+                a.grad = None
+                b.grad = None
+                continue
+            gr = torch.randn(a.shape, generator=g)
+            a.grad = gr.clone()
+            b.grad = gr.to(cuda_device)
+        o1.step()
+        o2.step()
+        for a, b in zip(ref, ours):
+            cases.assert_close(b.detach().cpu(), a.detach(), 1e-6, 1e-7, "param step %d" % step)
+
+
+def test_library_fails_loudly_without_cuda_tensor(cuda_device):
+    from vitta_b200 import _lib
+    from vitta_b200.utils.pred_consistency_utils import compute_pred_consis
+    with pytest.raises(_lib.VittaError):
+        compute_pred_consis(torch.randn(2, 2, 5))

@@ -1,0 +1,100 @@
+"""GPU parity of the whole TANet adaptation step (fused sm_100a path behind the reference's driver API) against
+the golden vectors recorded from the unmodified reference's ``tta_standard``."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(name, dev):
+    import vitta_b200
+    from vitta_b200 import synth
+    from vitta_b200.corpus.basics import OnlineAdapter
+    from vitta_b200.models.tanet_models.tanet import TSN
+    from vitta_b200.utils import norm_stats_utils as nsu
+    from vitta_b200.utils.opts import default_args
+    vitta_b200.set_fp32_exact()
+    nsu.reset_arenas()
+    cfg = cases.TANET_CASES[name]
+    g = cases.load_golden(name)
+    src_m, src_v = cases.src_stats_from_golden(g)
+    model = TSN(cfg["K"], cfg["T"], 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256,
+                tam=True, non_local=False, partial_bn=False)
+    sd0 = synth.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd0, strict=True)
+    model.base_model.fc.p = 0.0
+    model = model.to(dev)
+    args = default_args(arch='tanet', clip_length=cfg["T"], batch_size=cfg["N"], n_augmented_views=cfg["M"],
+                        if_pred_consistency=cfg["consis"], reg_type=cfg["reg_type"], lr=cfg["lr"],
+                        num_classes=cfg["K"], input_size=cfg["res"], moving_avg=cfg["moving_avg"])
+    # the source statistics: our compute_statistics must reproduce the reference's (fused stats kernels, eval fwd)
+    from vitta_b200.corpus.basics import compute_statistics
+    clean = cases.case_inputs(cfg, "tanet", "clean", 2, 100)
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, x):
+            self.x = x
+
+        def __len__(self):
+            return self.x.shape[0]
+
+        def __getitem__(self, i):
+            return self.x[i], 0
+    a2 = default_args(arch='tanet', clip_length=cfg["T"], batch_size=cfg["N"], num_classes=cfg["K"],
+                      input_size=cfg["res"], stat_type='spatiotemp', result_dir=None)
+    a2.dataset_factory = lambda a, split, dataset_type: DS(torch.cat(clean, 0))
+    om, ov = compute_statistics(model, a2)
+    assert len(om) == len(src_m) == 53
+    for i in range(len(om)):
+        cases.assert_close(om[i], src_m[i], 2e-4, 2e-5 * float(np.abs(src_m[i]).max()) + 1e-6, "src_mean/%d" % i)
+        cases.assert_close(ov[i], src_v[i], 2e-4, 2e-5 * float(np.abs(src_v[i]).max()) + 1e-6, "src_var/%d" % i)
+
+    ad = OnlineAdapter(model, args, (src_m, src_v))
+    assert len(ad.stat_reg_hooks) == int(g["n_hooks"]) == 47
+    tta_in, eval_in = cases.tta_inputs(cfg, "tanet")
+    for s in range(cfg["steps"]):
+        r = ad.adapt(tta_in[s].to(dev))
+        cases.assert_close(r["loss_reg"].cpu(), g["step%d/loss_reg" % s], 1e-4, 1e-6, "loss_reg step %d" % s)
+        if cfg["consis"]:
+            cases.assert_close(r["loss_consis"].cpu(), g["step%d/loss_consis" % s], 1e-3, 1e-7, "loss_consis")
+        for h, hook in enumerate(ad.stat_reg_hooks):
+            cases.assert_close(hook.r_feature.detach().cpu(), g["step%d/r_feature/%d" % (s, h)], 1e-4, 1e-6,
+                               "r_feature %d" % h)
+            k = "step%d/ema_mean/%d" % (s, h)
+            if k in g:
+                em, ev = g[k], g["step%d/ema_var/%d" % (s, h)]
+                cases.assert_close(hook.ema_mean.cpu(), em, 1e-4, 1e-5 * float(np.abs(em).max()) + 1e-7, k)
+                cases.assert_close(hook.ema_var.cpu(), ev, 1e-4, 1e-5 * float(np.abs(ev).max()) + 1e-7, "ema_var")
+        ad.hooks_off()
+        ev = ad.evaluate(eval_in[s].to(dev))
+        want = g["step%d/eval_logits" % s]
+        cases.assert_close(ev.cpu(), want, 2e-4, 2e-5 * float(np.abs(want).max()), "eval logits step %d" % s)
+        ad.hooks_on()
+    new_sd = ad.model.state_dict()
+    names = [str(n) for n in g["delta_names"]]
+    ref = g["delta_norm_sum"]
+    for i, n in enumerate(names):
+        d = (new_sd[n].detach().cpu() - sd0[n]).double()
+        cases.assert_close(float(d.norm()), ref[i, 0], 1e-2, 1e-9, "delta norm " + n)
+    for k in g.files:
+        if k.startswith("delta/"):
+            n = k[len("delta/"):]
+            d = (new_sd[n].detach().cpu() - sd0[n]).reshape(-1)[:4096]
+            scale = float(np.abs(g[k]).max()) + 1e-12
+            cases.assert_close(d, g[k], 5e-3, 2e-3 * scale, k)
+
+
+@pytest.mark.parametrize("name", ["tanet_t8_r64_consis_l1", "tanet_t8_r64_stats_mse", "tanet_t16_r224_stats_l1"])
+def test_tanet_tta_vs_reference_golden(cuda_device, name):
+    _run_case(name, cuda_device)
+
+
+def test_state_dict_keys_match_reference_layout():
+    """CPU-safe but cheap: also run on the GPU box so the driver sees the same module tree there."""
+    from vitta_b200.models.tanet_models.tanet import TSN
+    m = TSN(101, 8, 'RGB', base_model='resnet50', tam=True)
+    tmpl = cases.tanet_state_template(101, 8)
+    assert list(m.state_dict().keys()) == list(tmpl.keys())

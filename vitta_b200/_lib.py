@@ -1,0 +1,117 @@
+"""ctypes binding of the C-ABI in include/vitta_b200.h.
+
+There is deliberately no fallback: if ``libvitta_b200.so`` is missing or a call fails, the caller gets
+an exception -- never a silent eager-PyTorch / CPU path.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitta_b200.so")
+
+REG_TYPES = {"l1_loss": 0, "mse_loss": 1, "kld": 2}
+
+
+class VittaChunking(C.Structure):
+    _fields_ = [("chunk_rows", C.c_int32), ("chunks_per_frame", C.c_int32), ("frame_rows", C.c_int64),
+                ("n_entries", C.c_int32), ("reserved", C.c_int32)]
+
+
+class VittaLayerDesc(C.Structure):
+    _fields_ = [("C", C.c_int32), ("n_entries", C.c_int32), ("chunk_rows", C.c_int32), ("chunks_per_frame", C.c_int32),
+                ("frame_rows", C.c_int64), ("part_off", C.c_int64), ("entry_stride", C.c_int64), ("cnt_off", C.c_int64),
+                ("cnt_stride", C.c_int64), ("ch_off", C.c_int64), ("reg_type", C.c_int32), ("has_source", C.c_int32),
+                ("w_new", C.c_float), ("w_old", C.c_float)]
+
+
+class VittaBN(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("eps", C.c_float)]
+
+
+class VittaSgdTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("buf", C.c_void_p), ("n", C.c_int64)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "vitta_version": (C.c_int, []),
+    "vitta_last_error": (C.c_char_p, []),
+    "vitta_sm_count": (C.c_int, []),
+    "vitta_stats_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.POINTER(VittaChunking)]),
+    "vitta_stats_partial": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "vitta_stats_finalize": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "vitta_stats_inject": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, _P]),
+    "vitta_bn_act_fwd": (C.c_int, [_P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, C.c_int64,
+                                   C.c_int64, C.c_int, _P]),
+    "vitta_bn_act_bwd_ws_floats": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
+    "vitta_bn_act_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+                                   _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+    "vitta_tam_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
+    "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "vitta_sgd_block_elems": (C.c_int, []),
+    "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
+}
+
+_lib = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+class VittaError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VittaError("%s not found: build it with `python -m vitta_b200.build` (or __graft_entry__.build()). "
+                         "vitta_b200 has no CPU or eager-PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().vitta_last_error()
+        raise VittaError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    check(rc, name)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def chunking(O, Cc, I, frames=1):
+    out = VittaChunking()
+    check(load().vitta_stats_chunking(O, Cc, I, frames, C.byref(out)), "vitta_stats_chunking")
+    return out
+
+
+def make_bn(weight, bias, running_mean, running_var, eps):
+    return VittaBN(weight.data_ptr(), bias.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), float(eps))

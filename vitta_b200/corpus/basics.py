@@ -1,0 +1,382 @@
+"""Adaptation driver -- mirror of the hot-path parts of the reference's ``corpus/basics.py``:
+``tta_standard`` (:403-747), ``compute_statistics`` (:220-307), ``validate`` (:149-217, source-only evaluation)
+and ``get_model`` (:1447-1493).  The loop body lives in :class:`OnlineAdapter` so that ``bench.py`` and the
+tests can drive single steps; ``tta_standard`` wraps it in the reference's loader loop.
+
+Out of scope: the decord/PIL data pipeline.  ``get_dataset_tanet`` /
+``get_dataset_videoswin`` therefore return synthetic tensor datasets unless ``args.dataset_factory`` is set to
+a callable ``(args, split, dataset_type) -> torch Dataset`` yielding the reference's loader layouts.
+"""
+import copy as cp
+import os.path as osp
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops, synth
+from ..utils.BNS_utils import BNFeatureHook, choose_layers, collect_bn_params, freeze_except_bn
+from ..utils.norm_stats_utils import CombineNormStatsRegHook_onereg, ComputeNormStatsHook
+from ..utils.pred_consistency_utils import compute_pred_consis
+from ..utils.utils_ import AverageMeter, accuracy
+
+CANDIDATE_BN_LAYERS = [nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d]
+
+
+# ----------------------------------------------------------------------------------------------
+# datasets (synthetic stand-ins for the reference's video loaders)
+# ----------------------------------------------------------------------------------------------
+class SyntheticVideoDataset(torch.utils.data.Dataset):
+    """Loader-layout tensors: TANet (M*T*3, H, W) per item, Swin (M, 3, T, H, W) per item."""
+
+    def __init__(self, arch, n_items, n_views, clip_len, size, num_classes, seed, tag):
+        v = synth.synth_video(n_items, n_views, clip_len, size, seed=seed, gauss_sigma=0.38, tag=tag)
+        self.x = synth.tanet_loader_tensor(v) if arch == 'tanet' else synth.swin_loader_tensor(v)
+        self.y = synth.synth_labels(n_items, num_classes, seed)
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i]
+
+
+def _dataset(args, split, dataset_type):
+    factory = getattr(args, 'dataset_factory', None)
+    if factory is not None:
+        return factory(args, split, dataset_type)
+    views = args.n_augmented_views if (dataset_type == 'tta' and args.if_sample_tta_aug_views) else 1
+    return SyntheticVideoDataset(args.arch, getattr(args, 'synthetic_items', 4 * args.batch_size), views,
+                                 args.clip_length, args.input_size, args.num_classes,
+                                 seed=getattr(args, 'synthetic_seed', 0), tag='tta')
+
+
+def get_dataset_tanet(args, split='val', dataset_type=None):
+    return _dataset(args, split, dataset_type)
+
+
+def get_dataset_videoswin(args, split='val', dataset_type=None):
+    return _dataset(args, split, dataset_type)
+
+
+def get_model(args, num_classes, logger=None):
+    """reference :1447-1493 (only the two architectures ``--arch`` can select, utils/opts.py:43)."""
+    if args.arch == 'tanet':
+        from ..models.tanet_models.tanet import TSN
+        return TSN(num_classes, args.clip_length, args.modality, base_model='resnet50', consensus_type='avg',
+                   img_feature_dim=args.img_feature_dim, tam=True, non_local=False, partial_bn=args.partial_bn)
+    if args.arch == 'videoswintransformer':
+        from ..models.videoswintransformer_models.recognizer3d import Recognizer3D
+        return Recognizer3D(num_classes=num_classes, patch_size=args.patch_size, window_size=args.window_size,
+                            drop_path_rate=args.drop_path_rate)
+    raise Exception(f'{args.arch} is not a valid model!')
+
+
+def load_source_statistics(args):
+    """Two pickled object arrays, one (C,) vector per BN2d/3d (TANet) or LN[1:] (Swin) in named_modules()
+    order (reference :482-483).  ``args.source_stats`` = (mean_list, var_list) bypasses the files."""
+    given = getattr(args, 'source_stats', None)
+    if given is not None:
+        return list(given[0]), list(given[1])
+    return (list(np.load(args.spatiotemp_mean_clean_file, allow_pickle=True)),
+            list(np.load(args.spatiotemp_var_clean_file, allow_pickle=True)))
+
+
+def save_stat_list(path, vectors):
+    """The reference np.save()s a ragged python list (:306-307), which numpy>=1.24 refuses; the same file
+    format (1-D object array of float32 vectors) is built explicitly here."""
+    arr = np.empty(len(vectors), dtype=object)
+    for i, v in enumerate(vectors):
+        arr[i] = np.asarray(v, dtype=np.float32)
+    np.save(path, arr, allow_pickle=True)
+
+
+def _reshape_input(args, x, n_views_or_clips):
+    """TANet: (bz, views*T*3, H, W) -> (bz*views, T, 3, H, W) (reference :618-623); Swin: unchanged."""
+    if args.arch == 'tanet':
+        bz = x.shape[0]
+        x = x.view(-1, 3, x.size(2), x.size(3))
+        return x.view(bz * args.test_crops * n_views_or_clips, args.clip_length, 3, x.size(2), x.size(3))
+    if args.arch == 'videoswintransformer':
+        return x
+    raise NotImplementedError(f'Incorrect model type {args.arch}')
+
+
+# ----------------------------------------------------------------------------------------------
+# the loop body
+# ----------------------------------------------------------------------------------------------
+class OnlineAdapter:
+    """One model copy + optimiser + alignment hooks: everything ``tta_standard`` sets up when
+    ``setup_model_optimizer`` is true (reference :525-601), and its per-batch body (:606-728)."""
+
+    def __init__(self, model_origin, args, stats=None, process_group=None):
+        self.args = args
+        self.process_group = process_group
+        if args.arch == 'tanet':
+            self.n_clips = int(args.sample_style.split("-")[-1])
+        else:
+            self.n_clips = args.num_clips
+        if args.if_sample_tta_aug_views:
+            assert self.n_clips == 1
+        self.if_pred_consistency = args.if_pred_consistency if args.if_sample_tta_aug_views else False
+        if not hasattr(args, 'moving_avg'):
+            args.moving_avg = False
+        if not hasattr(args, 'momentum_mvg'):
+            args.momentum_mvg = 0.1
+
+        self.model = cp.deepcopy(model_origin)
+        model = self.model
+        mean_list = var_list = None
+        if args.stat_reg == 'mean_var':
+            assert args.stat_type == ['spatiotemp']
+            mean_list, var_list = stats if stats is not None else load_source_statistics(args)
+            if args.arch == 'tanet':
+                self.chosen_layers = choose_layers(model, CANDIDATE_BN_LAYERS)
+                it = iter(range(len(mean_list)))
+                new_m, new_v = [], []
+                for _, layer in self.chosen_layers:     # None placeholders at BatchNorm1d positions (:488-498)
+                    if isinstance(layer, nn.BatchNorm1d):
+                        new_m.append(None)
+                        new_v.append(None)
+                    else:
+                        i = next(it)
+                        new_m.append(mean_list[i])
+                        new_v.append(var_list[i])
+                mean_list, var_list = new_m, new_v
+            elif args.arch == 'videoswintransformer':
+                self.chosen_layers = choose_layers(model, [nn.LayerNorm])[1:]    # skip patch_embed.norm (:541-543)
+            assert len(mean_list) == len(self.chosen_layers)
+
+        # optimiser (:547-560)
+        if args.update_only_bn_affine:
+            kinds = CANDIDATE_BN_LAYERS if args.arch == 'tanet' else [nn.LayerNorm]
+            self.model = model = freeze_except_bn(model, bn_condidiate_layers=kinds)
+            params, _ = collect_bn_params(model, bn_candidate_layers=kinds)
+            self.optimizer = torch.optim.Adam(params, lr=args.lr, betas=(0.9, 0.999), weight_decay=0.)
+        else:
+            self.optimizer = ops.FusedSGD(model.parameters(), lr=args.lr, momentum=args.momentum,
+                                          weight_decay=args.weight_decay, process_group=process_group)
+
+        # hooks (:564-601)
+        from ..utils import norm_stats_utils as nsu
+        nsu.set_process_group(process_group)
+        self.stat_reg_hooks = []
+        self.hooked_layers = []
+        if args.stat_reg == 'mean_var':
+            if isinstance(args.stat_type, str):
+                raise NotImplementedError('args.stat_type of str  is deprecated, use list instead.')
+            for layer_id, (name, layer) in enumerate(self.chosen_layers):
+                if any(block_name in name for block_name in args.chosen_blocks):
+                    self.stat_reg_hooks.append(CombineNormStatsRegHook_onereg(
+                        layer, clip_len=args.clip_length,
+                        spatiotemp_stats_clean_tuple=(mean_list[layer_id], var_list[layer_id]),
+                        reg_type=args.reg_type, moving_avg=args.moving_avg, momentum=args.momentum_mvg,
+                        stat_type_list=args.stat_type, reduce_dim=args.reduce_dim, before_norm=args.before_norm,
+                        if_sample_tta_aug_views=args.if_sample_tta_aug_views,
+                        n_augmented_views=args.n_augmented_views))
+                    self.hooked_layers.append(layer)
+        elif args.stat_reg == 'BNS':
+            self.chosen_layers = choose_layers(model, CANDIDATE_BN_LAYERS)
+            for name, layer in self.chosen_layers:
+                if any(block_name in name for block_name in args.chosen_blocks):
+                    self.stat_reg_hooks.append(BNFeatureHook(layer, reg_type=args.reg_type,
+                                                             running_manner=args.running_manner,
+                                                             use_src_stat_in_reg=args.use_src_stat_in_reg,
+                                                             momentum=args.momentum_bns))
+                    self.hooked_layers.append(layer)
+        else:
+            raise Exception(f'undefined regularization type {args.stat_reg}')
+        self._hooks_on = True
+
+    # -- :606-677 -------------------------------------------------------------------------------
+    def adapt(self, input, target=None, criterion=None):
+        args, model = self.args, self.model
+        if not self._hooks_on:
+            self.hooks_on()
+        model.train()
+        if args.fix_BNS:
+            for m in model.modules():
+                if isinstance(m, tuple(CANDIDATE_BN_LAYERS)):
+                    m.eval()
+        actual_bz = input.shape[0]
+        n_views = args.n_augmented_views if args.if_sample_tta_aug_views else self.n_clips
+        x = _reshape_input(args, input, n_views)
+        loss_consis = None
+        loss_ce = None
+        for _ in range(args.n_gradient_steps):
+            if args.arch == 'tanet':
+                output = model(x)
+                if args.if_sample_tta_aug_views:
+                    output = output.reshape(actual_bz, args.test_crops * n_views, -1)
+                    if self.if_pred_consistency:
+                        loss_consis = compute_pred_consis(output)
+                    output = output.mean(1)
+                else:
+                    output = output.reshape(actual_bz, args.test_crops * n_views, -1).mean(1)
+            else:
+                output, view_cls_score = model(x)
+                if args.if_sample_tta_aug_views and self.if_pred_consistency:
+                    loss_consis = compute_pred_consis(view_cls_score)
+            if criterion is not None and target is not None:
+                loss_ce = criterion(output.detach(), target)        # logging only (:657)
+            loss_reg = torch.zeros((), dtype=torch.float32, device=x.device)
+            for hook in self.stat_reg_hooks:
+                loss_reg = loss_reg + hook.r_feature
+            if self.if_pred_consistency:
+                loss = args.lambda_feature_reg * loss_reg + args.lambda_pred_consis * loss_consis
+            else:
+                loss = loss_reg                                        # :667: lambda_feature_reg not applied
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.optimizer.step()
+        return {'output': output.detach(), 'loss_reg': loss_reg.detach(), 'loss': loss.detach(),
+                'loss_consis': None if loss_consis is None else loss_consis.detach(), 'loss_ce': loss_ce}
+
+    def hooks_off(self):
+        for h in self.stat_reg_hooks:        # :682-684
+            h.close()
+        self._hooks_on = False
+
+    def hooks_on(self):
+        for h, layer in zip(self.stat_reg_hooks, self.hooked_layers):    # :721-727
+            h.add_hook_back(layer)
+        self._hooks_on = True
+
+    @torch.no_grad()
+    def evaluate(self, input):
+        """:691-713 -- clean forward on the same videos with hooks removed and model.eval()."""
+        args, model = self.args, self.model
+        if self._hooks_on:
+            self.hooks_off()
+        model.eval()
+        x = _reshape_input(args, input, self.n_clips)
+        if args.arch == 'tanet':
+            out = model(x)
+            return out.reshape(input.shape[0], args.test_crops * self.n_clips, -1).mean(1)
+        out, _ = model(x)
+        return out
+
+
+def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
+    """Online test-time adaptation over a loader pair (reference :403-747).  ``tta_online``: one adapter for
+    the whole stream; ``tta_standard``: a fresh model copy, optimiser and hooks per batch."""
+    if args.if_tta_standard == 'tta_standard':
+        assert args.momentum_mvg == 1.0
+        assert args.n_epoch_adapat == 1
+    elif args.if_tta_standard == 'tta_online':
+        assert args.momentum_mvg != 1.0
+        assert args.n_gradient_steps == 1
+        assert args.n_epoch_adapat == 1
+    make = get_dataset_tanet if args.arch == 'tanet' else get_dataset_videoswin
+    tta_loader = torch.utils.data.DataLoader(make(args, split='val', dataset_type='tta'), batch_size=args.batch_size,
+                                             shuffle=False, num_workers=args.workers, pin_memory=True)
+    eval_loader = torch.utils.data.DataLoader(make(args, split='val', dataset_type='eval'),
+                                              batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
+                                              pin_memory=True)
+    stats = load_source_statistics(args) if args.stat_reg == 'mean_var' else None
+    batch_time, losses_ce, losses_reg, losses_consis = AverageMeter(), AverageMeter(), AverageMeter(), AverageMeter()
+    top1, top5 = AverageMeter(), AverageMeter()
+    eval_iter = iter(eval_loader)
+    device = next(model_origin.parameters()).device
+    adapter = None
+    end = time.time()
+    for batch_id, (input, target) in enumerate(tta_loader):
+        if args.if_tta_standard == 'tta_standard' or batch_id == 0:
+            adapter = OnlineAdapter(model_origin, args, stats, getattr(args, 'process_group', None))
+        actual_bz = input.shape[0]
+        input = input.to(device, non_blocking=True)
+        target = target.to(device, non_blocking=True)
+        res = adapter.adapt(input, target, criterion)
+        if res['loss_ce'] is not None:
+            losses_ce.update(res['loss_ce'].item(), actual_bz)
+        losses_reg.update(res['loss_reg'].item(), actual_bz)
+        if res['loss_consis'] is not None:
+            losses_consis.update(res['loss_consis'].item(), actual_bz)
+        adapter.hooks_off()
+        input, target = next(eval_iter)
+        input, target = input.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        output = adapter.evaluate(input)
+        prec1, prec5 = accuracy(output.data, target, topk=(1, 5))
+        top1.update(prec1.item(), actual_bz)
+        top5.update(prec5.item(), actual_bz)
+        batch_time.update(time.time() - end)
+        end = time.time()
+        if args.if_tta_standard == 'tta_online':
+            adapter.hooks_on()
+        if args.verbose and logger is not None:
+            logger.debug(f'TTA Epoch1: [{batch_id}/{len(tta_loader)}]\t'
+                         f'Time {batch_time.val:.3f} ({batch_time.avg:.3f})\t'
+                         f'Loss reg {losses_reg.val:.4f} ({losses_reg.avg:.4f})\t'
+                         f'Loss consis {losses_consis.val:.4f} ({losses_consis.avg:.4f})\t'
+                         f'Prec@1 {top1.val:.3f} ({top1.avg:.3f})\tPrec@5 {top5.val:.3f} ({top5.avg:.3f})')
+    tta_standard.last_adapter = adapter
+    return [top1.avg]
+
+
+def compute_statistics(model=None, args=None, logger=None, log_time=None):
+    """Source-statistics producer (reference :220-307): model.eval(), one ComputeNormStatsHook per BN2d/3d
+    (TANet; BN1d too for the 'temp' types) or LN[1:] (Swin); per-batch mean and per-batch *biased variance*
+    averaged with weight = batch size; written as two .npy object arrays."""
+    if args.arch == 'tanet':
+        kinds = CANDIDATE_BN_LAYERS if args.stat_type in ['temp', 'temp_v2'] else [nn.BatchNorm2d, nn.BatchNorm3d]
+        chosen = choose_layers(model, kinds)
+        n_clips = int(args.sample_style.split("-")[-1])
+        loader_ds = get_dataset_tanet(args, split='val', dataset_type='eval')
+    elif args.arch == 'videoswintransformer':
+        chosen = choose_layers(model, [nn.LayerNorm])[1:]
+        n_clips = args.num_clips
+        loader_ds = get_dataset_videoswin(args, split='val', dataset_type='eval')
+    else:
+        raise Exception(f'{args.arch} is not a valid model!')
+    hooks = [ComputeNormStatsHook(layer, clip_len=args.clip_length, stat_type=args.stat_type,
+                                  before_norm=args.before_norm, batch_size=args.batch_size) for _, layer in chosen]
+    loader = torch.utils.data.DataLoader(loader_ds, batch_size=args.batch_size, shuffle=False,
+                                         num_workers=args.workers, pin_memory=True)
+    device = next(model.parameters()).device
+    sum_mean = [None] * len(hooks)
+    sum_var = [None] * len(hooks)
+    count = 0
+    model.eval()
+    with torch.no_grad():
+        for batch_id, (input, _) in enumerate(loader):
+            bz = input.shape[0]
+            model(_reshape_input(args, input.to(device, non_blocking=True), n_clips))
+            for i, h in enumerate(hooks):
+                m, v = h.batch_mean * bz, h.batch_var * bz
+                sum_mean[i] = m.clone() if sum_mean[i] is None else sum_mean[i] + m
+                sum_var[i] = v.clone() if sum_var[i] is None else sum_var[i] + v
+            count += bz
+    for h in hooks:
+        h.close()
+    list_mean = [(s / count).cpu().numpy() for s in sum_mean]
+    list_var = [(s / count).cpu().numpy() for s in sum_var]
+    if getattr(args, 'result_dir', None):
+        save_stat_list(osp.join(args.result_dir, f'list_{args.stat_type}_mean_{log_time}.npy'), list_mean)
+        save_stat_list(osp.join(args.result_dir, f'list_{args.stat_type}_var_{log_time}.npy'), list_var)
+    return list_mean, list_var
+
+
+@torch.no_grad()
+def validate(val_loader, model, criterion, iter=0, epoch=None, args=None, logger=None, writer=None):
+    """Source-only evaluation: model.eval() forward + accuracy (reference :149-217; config 1 of BASELINE.json)."""
+    top1, top5, losses = AverageMeter(), AverageMeter(), AverageMeter()
+    model.eval()
+    device = next(model.parameters()).device
+    n_clips = int(args.sample_style.split("-")[-1]) if args.arch == 'tanet' else args.num_clips
+    for input, target in val_loader:
+        bz = input.shape[0]
+        input, target = input.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        x = _reshape_input(args, input, n_clips)
+        if args.arch == 'tanet':
+            output = model(x).reshape(bz, args.test_crops * n_clips, -1).mean(1)
+        else:
+            output, _ = model(x)
+        if criterion is not None:
+            losses.update(criterion(output, target).item(), bz)
+        p1, p5 = accuracy(output.data, target, topk=(1, 5))
+        top1.update(p1.item(), bz)
+        top5.update(p5.item(), bz)
+    if logger is not None:
+        logger.debug(f'Testing Results: Prec@1 {top1.avg:.3f} Prec@5 {top5.avg:.3f} Loss {losses.avg:.5f}')
+    return top1.avg

@@ -1,0 +1,371 @@
+// K4: fused BatchNorm(eval) + statistics partials + residual (optionally through a 2nd BN) + ReLU + pooled sums,
+// channels-last, forward and backward.  One pass over HBM each way; 128-bit loads/stores.
+#include "common.cuh"
+
+namespace vitta {
+
+struct BNDev {
+  const float* w;
+  const float* b;
+  const float* rm;
+  const float* rv;
+  float eps;
+};
+
+struct Aff4 {  // per-thread folded BN for 4 channels: y = (x - rm)*k + b ; xhat = (x - rm)*istd
+  float4 rm, k, b, istd;
+};
+
+__device__ __forceinline__ Aff4 load_aff(const BNDev& bn, int c) {
+  Aff4 a;
+  const float4 w = ldg4(bn.w + c), rv = ldg4(bn.rv + c);
+  a.rm = ldg4(bn.rm + c);
+  a.b = ldg4(bn.b + c);
+  a.istd.x = 1.f / sqrtf(rv.x + bn.eps); a.istd.y = 1.f / sqrtf(rv.y + bn.eps);
+  a.istd.z = 1.f / sqrtf(rv.z + bn.eps); a.istd.w = 1.f / sqrtf(rv.w + bn.eps);
+  a.k.x = w.x * a.istd.x; a.k.y = w.y * a.istd.y; a.k.z = w.z * a.istd.z; a.k.w = w.w * a.istd.w;
+  return a;
+}
+__device__ __forceinline__ float4 apply_aff(const Aff4& a, float4 x) {
+  float4 y;
+  y.x = fmaf(x.x - a.rm.x, a.k.x, a.b.x); y.y = fmaf(x.y - a.rm.y, a.k.y, a.b.y);
+  y.z = fmaf(x.z - a.rm.z, a.k.z, a.b.z); y.w = fmaf(x.w - a.rm.w, a.k.w, a.b.w);
+  return y;
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void acc_shift(float4& s1, float4& s2, float4 y, float4 k) {
+  float d;
+  d = y.x - k.x; s1.x += d; s2.x = fmaf(d, d, s2.x);
+  d = y.y - k.y; s1.y += d; s2.y = fmaf(d, d, s2.y);
+  d = y.z - k.z; s1.z += d; s2.z = fmaf(d, d, s2.z);
+  d = y.w - k.w; s1.w += d; s2.w = fmaf(d, d, s2.w);
+}
+
+// sum `v` over the row slots of the CTA; result valid in threads with slot == 0.
+__device__ __forceinline__ float4 slot_reduce(float4 v, float4* sm, int tid, int lpr, int rs) {
+  __syncthreads();
+  sm[tid] = v;
+  __syncthreads();
+  const int slot = tid / lpr;
+  for (int st = rs >> 1; st > 0; st >>= 1) {
+    if (slot < st) {
+      float4 a = sm[tid], b = sm[tid + st * lpr];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      sm[tid] = a;
+    }
+    __syncthreads();
+  }
+  return sm[tid];
+}
+
+__device__ __forceinline__ void write_part(float* part, int64_t e, int C, int col4, float4 k, float4 a, float4 b,
+                                           int nrows) {
+  const float n = (float)nrows, inv = 1.f / n;
+  float* o = part + (e * C + (int64_t)col4 * 4) * 2;
+  float4 o0, o1;
+  o0.x = k.x + a.x * inv; o0.y = fmaxf(b.x - a.x * a.x * inv, 0.f);
+  o0.z = k.y + a.y * inv; o0.w = fmaxf(b.y - a.y * a.y * inv, 0.f);
+  o1.x = k.z + a.z * inv; o1.y = fmaxf(b.z - a.z * a.z * inv, 0.f);
+  o1.z = k.w + a.w * inv; o1.w = fmaxf(b.w - a.w * a.w * inv, 0.f);
+  st4(o, o0);
+  st4(o + 4, o1);
+}
+
+// RES: 0 none, 1 raw residual, 2 residual through its own BN
+template <int RES>
+__global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __restrict__ x, BNDev bn,
+                                                             const float* __restrict__ res, BNDev bn2, int relu,
+                                                             float* __restrict__ out, float* __restrict__ part_main,
+                                                             float* __restrict__ part_res, float* __restrict__ pool_part,
+                                                             int C, int lpr, int rs, int chunk_rows, int cpf,
+                                                             int64_t frame_rows) {
+  __shared__ float4 sm[kThreads];
+  const int tid = threadIdx.x;
+  const int lane = tid % lpr;
+  const int slot = tid / lpr;
+  const int col4 = blockIdx.y * lpr + lane;
+  const bool active = col4 * 4 < C;
+  const int64_t e = blockIdx.x;
+  const int64_t frame = e / cpf;
+  const int j = (int)(e % cpf);
+  const int64_t row0 = frame * frame_rows + (int64_t)j * chunk_rows;
+  const int64_t rem = frame_rows - (int64_t)j * chunk_rows;
+  const int nrows = (int)(rem < chunk_rows ? rem : chunk_rows);
+
+  float4 s1 = f4zero(), s2 = f4zero(), r1 = f4zero(), r2 = f4zero(), pool = f4zero(), ky = f4zero(), kr = f4zero();
+  if (active) {
+    const int c = col4 * 4;
+    const Aff4 a = load_aff(bn, c);
+    Aff4 a2;
+    if (RES == 2) a2 = load_aff(bn2, c);
+    const int64_t off0 = row0 * C + c;
+    ky = apply_aff(a, ldg4(x + off0));
+    if (RES == 2) kr = apply_aff(a2, ldg4(res + off0));
+#pragma unroll 4
+    for (int r = slot; r < nrows; r += rs) {
+      const int64_t off = off0 + (int64_t)r * C;
+      float4 y = apply_aff(a, ld_stream4(x + off));
+      if (part_main) acc_shift(s1, s2, y, ky);
+      if (RES != 0) {
+        float4 rr = ld_stream4(res + off);
+        if (RES == 2) {
+          rr = apply_aff(a2, rr);
+          if (part_res) acc_shift(r1, r2, rr, kr);
+        }
+        y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+      }
+      if (relu) {
+        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+      }
+      st4(out + off, y);
+      pool.x += y.x; pool.y += y.y; pool.z += y.z; pool.w += y.w;
+    }
+  }
+  if (part_main) {
+    float4 a = slot_reduce(s1, sm, tid, lpr, rs);
+    float4 b = slot_reduce(s2, sm, tid, lpr, rs);
+    if (slot == 0 && active) write_part(part_main, e, C, col4, ky, a, b, nrows);
+  }
+  if (RES == 2 && part_res) {
+    float4 a = slot_reduce(r1, sm, tid, lpr, rs);
+    float4 b = slot_reduce(r2, sm, tid, lpr, rs);
+    if (slot == 0 && active) write_part(part_res, e, C, col4, kr, a, b, nrows);
+  }
+  if (pool_part) {
+    float4 p = slot_reduce(pool, sm, tid, lpr, rs);
+    if (slot == 0 && active) st4(pool_part + e * C + (int64_t)col4 * 4, p);
+  }
+}
+
+__global__ void pool_finish_kernel(const float* __restrict__ pool_part, float* __restrict__ pool_out, int64_t frames,
+                                   int cpf, int C, float inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames * C) return;
+  const int64_t f = i / C;
+  const int c = (int)(i % C);
+  float s = 0.f;
+  for (int j = 0; j < cpf; ++j) s += pool_part[(f * cpf + j) * C + c];
+  pool_out[i] = s * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* gout;
+  const float* gpool;  // (frames, C) or null
+  const float* x;
+  const float* res;
+  BNDev bn, bn2;
+  const float *ca, *cb, *gs;     // main-branch alignment coefficients (null: none)
+  const float *ca2, *cb2, *gs2;  // residual-BN alignment coefficients
+  float *gx, *gres, *gw, *gb, *gw2, *gb2;
+  float* ws;
+  int relu, C, lpr, rs, chunk_rows, cpf;
+  int64_t frame_rows, n_chunks;
+  float inv_frame_rows;
+};
+
+__device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+template <int RES>
+__global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
+  __shared__ float4 sm[kThreads];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int lane = tid % p.lpr;
+  const int slot = tid / p.lpr;
+  const int col4 = blockIdx.y * p.lpr + lane;
+  const int C = p.C;
+  const bool active = col4 * 4 < C;
+  const int c = col4 * 4;
+  float4 agw = f4zero(), agb = f4zero(), agw2 = f4zero(), agb2 = f4zero();
+  if (active) {
+    const Aff4 a = load_aff(p.bn, c);
+    Aff4 a2;
+    if (RES == 2) a2 = load_aff(p.bn2, c);
+    float4 ca = f4zero(), cb = f4zero(), ca2 = f4zero(), cb2 = f4zero();
+    if (p.ca) {
+      const float g = __ldg(p.gs);
+      ca = ldg4(p.ca + c); cb = ldg4(p.cb + c);
+      ca.x *= g; ca.y *= g; ca.z *= g; ca.w *= g; cb.x *= g; cb.y *= g; cb.z *= g; cb.w *= g;
+    }
+    if (RES == 2 && p.ca2) {
+      const float g = __ldg(p.gs2);
+      ca2 = ldg4(p.ca2 + c); cb2 = ldg4(p.cb2 + c);
+      ca2.x *= g; ca2.y *= g; ca2.z *= g; ca2.w *= g; cb2.x *= g; cb2.y *= g; cb2.z *= g; cb2.w *= g;
+    }
+    for (int64_t e = blockIdx.x; e < p.n_chunks; e += gridDim.x) {
+      const int64_t frame = e / p.cpf;
+      const int j = (int)(e % p.cpf);
+      const int64_t row0 = frame * p.frame_rows + (int64_t)j * p.chunk_rows;
+      const int64_t rem = p.frame_rows - (int64_t)j * p.chunk_rows;
+      const int nrows = (int)(rem < p.chunk_rows ? rem : p.chunk_rows);
+      float4 gp = f4zero();
+      if (p.gpool) {
+        gp = ldg4(p.gpool + frame * C + c);
+        gp.x *= p.inv_frame_rows; gp.y *= p.inv_frame_rows; gp.z *= p.inv_frame_rows; gp.w *= p.inv_frame_rows;
+      }
+      const int64_t off0 = row0 * C + c;
+#pragma unroll 2
+      for (int r = slot; r < nrows; r += p.rs) {
+        const int64_t off = off0 + (int64_t)r * C;
+        const float4 xv = ld_stream4(p.x + off);
+        float4 g = ld_stream4(p.gout + off);
+        const float4 y = apply_aff(a, xv);
+        float4 rr = f4zero(), rx = f4zero();
+        if (RES != 0) {
+          rx = ld_stream4(p.res + off);
+          rr = (RES == 2) ? apply_aff(a2, rx) : rx;
+        }
+        g.x += gp.x; g.y += gp.y; g.z += gp.z; g.w += gp.w;
+        if (p.relu) {
+          g.x = (y.x + rr.x > 0.f) ? g.x : 0.f; g.y = (y.y + rr.y > 0.f) ? g.y : 0.f;
+          g.z = (y.z + rr.z > 0.f) ? g.z : 0.f; g.w = (y.w + rr.w > 0.f) ? g.w : 0.f;
+        }
+        // main branch
+        float4 gy = f4fma(cb, y, ca);
+        gy.x += g.x; gy.y += g.y; gy.z += g.z; gy.w += g.w;
+        st4(p.gx + off, make_float4(gy.x * a.k.x, gy.y * a.k.y, gy.z * a.k.z, gy.w * a.k.w));
+        agb.x += gy.x; agb.y += gy.y; agb.z += gy.z; agb.w += gy.w;
+        agw.x = fmaf(gy.x, (xv.x - a.rm.x) * a.istd.x, agw.x); agw.y = fmaf(gy.y, (xv.y - a.rm.y) * a.istd.y, agw.y);
+        agw.z = fmaf(gy.z, (xv.z - a.rm.z) * a.istd.z, agw.z); agw.w = fmaf(gy.w, (xv.w - a.rm.w) * a.istd.w, agw.w);
+        if (RES == 1) {
+          st4(p.gres + off, g);
+        } else if (RES == 2) {
+          float4 gr = f4fma(cb2, rr, ca2);
+          gr.x += g.x; gr.y += g.y; gr.z += g.z; gr.w += g.w;
+          st4(p.gres + off, make_float4(gr.x * a2.k.x, gr.y * a2.k.y, gr.z * a2.k.z, gr.w * a2.k.w));
+          agb2.x += gr.x; agb2.y += gr.y; agb2.z += gr.z; agb2.w += gr.w;
+          agw2.x = fmaf(gr.x, (rx.x - a2.rm.x) * a2.istd.x, agw2.x); agw2.y = fmaf(gr.y, (rx.y - a2.rm.y) * a2.istd.y, agw2.y);
+          agw2.z = fmaf(gr.z, (rx.z - a2.rm.z) * a2.istd.z, agw2.z); agw2.w = fmaf(gr.w, (rx.w - a2.rm.w) * a2.istd.w, agw2.w);
+        }
+      }
+    }
+  }
+  // per-CTA partial parameter gradients -> ws[blockIdx.x][k][C], k in {gw, gb, gw2, gb2}
+  const int nk = (RES == 2) ? 4 : 2;
+  float4 red[4];
+  red[0] = slot_reduce(agw, sm, tid, p.lpr, p.rs);
+  red[1] = slot_reduce(agb, sm, tid, p.lpr, p.rs);
+  if (RES == 2) {
+    red[2] = slot_reduce(agw2, sm, tid, p.lpr, p.rs);
+    red[3] = slot_reduce(agb2, sm, tid, p.lpr, p.rs);
+  }
+  float* wsb = p.ws + (int64_t)blockIdx.x * 4 * C;
+  if (slot == 0 && active) {
+    for (int k = 0; k < nk; ++k) st4(wsb + (int64_t)k * C + c, red[k]);
+  }
+  __threadfence();
+  __syncthreads();
+  int* tickets = reinterpret_cast<int*>(p.ws + (int64_t)gridDim.x * 4 * C);
+  if (tid == 0) s_last = (atomicAdd(tickets + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA of this channel tile: sum the partials in CTA order (deterministic) and accumulate into the grads
+  const int nch = p.lpr * 4;
+  for (int i = tid; i < nch * nk; i += kThreads) {
+    const int k = i / nch;
+    const int cc = blockIdx.y * nch + (i % nch);
+    if (cc >= C) continue;
+    float s = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(p.ws + ((int64_t)b * 4 + k) * C + cc);
+    float* dst = (k == 0) ? p.gw : (k == 1) ? p.gb : (k == 2) ? p.gw2 : p.gb2;
+    if (dst) dst[cc] += s;
+  }
+  if (tid == 0) tickets[blockIdx.y] = 0;
+}
+
+static inline int bwd_grid_x(const ClGeom& g) {
+  int64_t cap = (148 * 4 + g.ctiles - 1) / g.ctiles;
+  if (cap < 1) cap = 1;
+  int64_t n = g.n_chunks();
+  return (int)(n < cap ? n : cap);
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+static BNDev to_dev(const VittaBN& b) { return BNDev{b.weight, b.bias, b.running_mean, b.running_var, b.eps}; }
+
+extern "C" {
+
+int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                     float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                     int64_t frame_rows, int C, void* stream) {
+  VITTA_CHECK_ARG(x && out && bn.weight && bn.bias && bn.running_mean && bn.running_var, VITTA_E_BADARG,
+                  "bn_act_fwd: null pointer");
+  VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && frames > 0 && frame_rows > 0, VITTA_E_BADARG, "bn_act_fwd: bad shape");
+  VITTA_CHECK_ARG(aligned16(x) && aligned16(out) && (!res || aligned16(res)), VITTA_E_ALIGN,
+                  "bn_act_fwd: tensors must be 16-byte aligned");
+  VITTA_CHECK_ARG(!(res_bn && !res), VITTA_E_BADARG, "bn_act_fwd: res_bn without res");
+  VITTA_CHECK_ARG((pool_part == nullptr) == (pool_out == nullptr), VITTA_E_BADARG, "bn_act_fwd: pool buffers");
+  ClGeom g = cl_geom(frames, frame_rows, C);
+  dim3 grid((unsigned)g.n_chunks(), (unsigned)g.ctiles);
+  cudaStream_t st = (cudaStream_t)stream;
+  BNDev b1 = to_dev(bn), b2 = res_bn ? to_dev(*res_bn) : b1;
+  if (!res)
+    bn_act_fwd_kernel<0><<<grid, kThreads, 0, st>>>(x, b1, nullptr, b2, relu, out, part_main, nullptr, pool_part, C,
+                                                   g.lpr, g.rs, g.chunk_rows, g.cpf, g.frame_rows);
+  else if (!res_bn)
+    bn_act_fwd_kernel<1><<<grid, kThreads, 0, st>>>(x, b1, res, b2, relu, out, part_main, nullptr, pool_part, C, g.lpr,
+                                                   g.rs, g.chunk_rows, g.cpf, g.frame_rows);
+  else
+    bn_act_fwd_kernel<2><<<grid, kThreads, 0, st>>>(x, b1, res, b2, relu, out, part_main, part_res, pool_part, C, g.lpr,
+                                                   g.rs, g.chunk_rows, g.cpf, g.frame_rows);
+  VITTA_CHECK_LAUNCH();
+  if (pool_part) {
+    int64_t n = frames * C;
+    pool_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pool_part, pool_out, frames, g.cpf, C,
+                                                                   1.f / (float)frame_rows);
+    VITTA_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int64_t vitta_bn_act_bwd_ws_floats(int64_t frames, int64_t frame_rows, int C) {
+  if (C <= 0 || C % 4 || frames <= 0 || frame_rows <= 0) return -1;
+  ClGeom g = cl_geom(frames, frame_rows, C);
+  return (int64_t)bwd_grid_x(g) * 4 * C + g.ctiles + 4;
+}
+
+int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* gs_main,
+                     const float* coef_a2, const float* coef_b2, const float* gs_res, float* gx, float* gres,
+                     float* gw, float* gb, float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows,
+                     int C, void* stream) {
+  VITTA_CHECK_ARG(gout && x && gx && ws, VITTA_E_BADARG, "bn_act_bwd: null pointer");
+  VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && frames > 0 && frame_rows > 0, VITTA_E_BADARG, "bn_act_bwd: bad shape");
+  VITTA_CHECK_ARG(aligned16(gout) && aligned16(x) && aligned16(gx) && (!res || aligned16(res)) &&
+                      (!gres || aligned16(gres)) && aligned16(ws),
+                  VITTA_E_ALIGN, "bn_act_bwd: tensors must be 16-byte aligned");
+  VITTA_CHECK_ARG(!(res && !gres), VITTA_E_BADARG, "bn_act_bwd: residual without gres");
+  VITTA_CHECK_ARG((coef_a == nullptr) == (coef_b == nullptr) && (coef_a == nullptr) == (gs_main == nullptr),
+                  VITTA_E_BADARG, "bn_act_bwd: main coefficients must come as (a, b, gscale)");
+  VITTA_CHECK_ARG((coef_a2 == nullptr) == (coef_b2 == nullptr) && (coef_a2 == nullptr) == (gs_res == nullptr),
+                  VITTA_E_BADARG, "bn_act_bwd: residual coefficients must come as (a, b, gscale)");
+  ClGeom g = cl_geom(frames, frame_rows, C);
+  BwdArgs p;
+  p.gout = gout; p.gpool = gpool; p.x = x; p.res = res;
+  p.bn = to_dev(bn); p.bn2 = res_bn ? to_dev(*res_bn) : p.bn;
+  p.ca = coef_a; p.cb = coef_b; p.gs = gs_main; p.ca2 = coef_a2; p.cb2 = coef_b2; p.gs2 = gs_res;
+  p.gx = gx; p.gres = gres; p.gw = gw; p.gb = gb; p.gw2 = gw2; p.gb2 = gb2; p.ws = ws;
+  p.relu = relu; p.C = C; p.lpr = g.lpr; p.rs = g.rs; p.chunk_rows = g.chunk_rows; p.cpf = g.cpf;
+  p.frame_rows = g.frame_rows; p.n_chunks = g.n_chunks(); p.inv_frame_rows = 1.f / (float)frame_rows;
+  dim3 grid((unsigned)bwd_grid_x(g), (unsigned)g.ctiles);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!res)
+    bn_act_bwd_kernel<0><<<grid, kThreads, 0, st>>>(p);
+  else if (!res_bn)
+    bn_act_bwd_kernel<1><<<grid, kThreads, 0, st>>>(p);
+  else
+    bn_act_bwd_kernel<2><<<grid, kThreads, 0, st>>>(p);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

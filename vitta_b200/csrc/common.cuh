@@ -1,0 +1,117 @@
+// Shared device/host helpers for the vitta_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vitta_b200.h"
+
+namespace vitta {
+
+void set_error(const char* fmt, ...);
+
+#define VITTA_CHECK_ARG(cond, code, ...)  \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::vitta::set_error(__VA_ARGS__);    \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define VITTA_CHECK_LAUNCH()                                                        \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ::vitta::set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kThreads = 256;     // CTA size of the streaming kernels
+constexpr int kMaxRowsPerThread = 16;
+
+// Chunking of a channels-last (rows x C) tensor: lanes run along C (float4 each), the remaining threads
+// of the CTA take different rows.  See include/vitta_b200.h (K1) for the contract.
+struct ClGeom {
+  int lpr;         // lanes (float4) per row handled by one CTA
+  int rs;          // row slots per CTA = kThreads / lpr
+  int ctiles;      // channel tiles = C / (4*lpr)
+  int rpt;         // rows per thread
+  int chunk_rows;  // rs * rpt
+  int cpf;         // chunks per frame
+  int64_t frames, frame_rows;
+  int64_t n_chunks() const { return frames * cpf; }
+};
+
+static inline ClGeom cl_geom(int64_t frames, int64_t frame_rows, int C) {
+  ClGeom g;
+  int c4 = C / 4;
+  g.lpr = c4 < 32 ? c4 : 32;
+  // largest power of two <= lpr keeps kThreads % lpr == 0
+  int l = 1;
+  while (l * 2 <= g.lpr) l *= 2;
+  g.lpr = l;
+  g.rs = kThreads / g.lpr;
+  g.ctiles = (c4 + g.lpr - 1) / g.lpr;
+  int64_t cap = (int64_t)g.rs * kMaxRowsPerThread;
+  g.cpf = (int)((frame_rows + cap - 1) / cap);
+  if (g.cpf < 1) g.cpf = 1;
+  g.rpt = (int)((frame_rows + (int64_t)g.cpf * g.rs - 1) / ((int64_t)g.cpf * g.rs));
+  if (g.rpt < 1) g.rpt = 1;
+  g.chunk_rows = g.rs * g.rpt;
+  // rounding rpt up can make the last chunks empty: recompute cpf for the final chunk size
+  g.cpf = (int)((frame_rows + g.chunk_rows - 1) / g.chunk_rows);
+  if (g.cpf < 1) g.cpf = 1;
+  g.frames = frames;
+  g.frame_rows = frame_rows;
+  return g;
+}
+
+// Chunking of an (O, C, I) tensor with I > 1: one warp reduces `og` consecutive o-slices of one channel.
+struct OciGeom {
+  int og;
+  int n_entries;
+};
+static inline OciGeom oci_geom(int64_t O, int64_t I) {
+  OciGeom g;
+  int64_t og = (4096 + I - 1) / I;
+  if (og < 1) og = 1;
+  if (og > O) og = O;
+  g.og = (int)og;
+  g.n_entries = (int)((O + og - 1) / og);
+  return g;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming load: read-once data, do not allocate in L1
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Chan et al. pairwise merge of (n, mean, M2)
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
+  if (nb == 0.f) return;
+  float nt = n + nb;
+  float d = meanb - mean;
+  float f = nb / nt;
+  mean = fmaf(d, f, mean);
+  m2 = m2 + m2b + d * d * n * f;
+  n = nt;
+}
+#endif
+
+}  // namespace vitta

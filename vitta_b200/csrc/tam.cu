@@ -1,0 +1,139 @@
+// K5: TAM gated 3-tap temporal stencil in the native channels-last (N, T, HW, C) layout, forward and backward.
+// The reference materialises two transposed copies, the gated tensor and a grouped conv (temporal_module.py:47-63);
+// here x is read once and out written once.
+#include "common.cuh"
+
+namespace vitta {
+
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+// thread = one (n, p, 4 channels) column, marching through t with a 3-frame register window
+__global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kern,
+                                                          const float* __restrict__ act, float* __restrict__ out, int N,
+                                                          int T, int64_t HW, int C4) {
+  const int64_t per_n = HW * C4;
+  const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= (int64_t)N * per_n) return;
+  const int n = (int)(idx / per_n);
+  const int64_t pc = idx % per_n;          // p*C4 + c4
+  const int c = (int)(pc % C4) * 4;
+  const int C = C4 * 4;
+  const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c);
+  const float4 k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c);
+  const float4 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
+  const float* xb = x + (int64_t)n * T * per_n * 4 + pc * 4;
+  float* ob = out + (int64_t)n * T * per_n * 4 + pc * 4;
+  const float* ab = act + (int64_t)n * T * C + c;
+  const int64_t ts = per_n * 4;
+  float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cur = mul4(ldg4(ab), ld_stream4(xb));
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t + 1 < T) nxt = mul4(ldg4(ab + (int64_t)(t + 1) * C), ld_stream4(xb + (int64_t)(t + 1) * ts));
+    float4 o = mul4(k0, prev);
+    o = fma4(k1, cur, o);
+    o = fma4(k2, nxt, o);
+    st4(ob + (int64_t)t * ts, o);
+    prev = cur;
+    cur = nxt;
+  }
+}
+
+constexpr int kTamChunkRows = 64;
+
+// CTA = (n, row chunk, channel tile).  Thread = (float4 of channels, frame slot): owns frames t = slot, slot+rs, ...
+//   gx[t]    = act[t] * (k0*g[t+1] + k1*g[t] + k2*g[t-1])
+//   D[t][k]  = sum_p g[t-k+1][p] * x[t][p]                 (partial over the chunk's rows)
+__global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
+                                                          const float* __restrict__ kern, const float* __restrict__ act,
+                                                          float* __restrict__ gx, float* __restrict__ dpart, int N, int T,
+                                                          int64_t HW, int C, int lpr, int rs, int nchunks) {
+  const int tid = threadIdx.x;
+  const int lane = tid % lpr;
+  const int slot = tid / lpr;
+  const int col4 = blockIdx.y * lpr + lane;
+  if (col4 * 4 >= C) return;
+  const int c = col4 * 4;
+  const int n = blockIdx.x / nchunks;
+  const int ch = blockIdx.x % nchunks;
+  const int64_t p0 = (int64_t)ch * kTamChunkRows;
+  const int64_t left = HW - p0;
+  const int np = (int)(left < kTamChunkRows ? left : kTamChunkRows);
+  const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c);
+  const float4 k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c);
+  const float4 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
+  const int64_t ts = HW * C;
+  const int64_t nb = (int64_t)n * T * ts;
+  for (int t = slot; t < T; t += rs) {
+    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
+    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+    const int64_t base = nb + (int64_t)t * ts + p0 * C + c;
+    const bool hp = t + 1 < T, hm = t > 0;
+#pragma unroll 2
+    for (int p = 0; p < np; ++p) {
+      const int64_t off = base + (int64_t)p * C;
+      const float4 g1 = ldg4(gout + off);
+      const float4 gp = hp ? ldg4(gout + off + ts) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gm = hm ? ldg4(gout + off - ts) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = ld_stream4(x + off);
+      float4 s = mul4(k0, gp);
+      s = fma4(k1, g1, s);
+      s = fma4(k2, gm, s);
+      st4(gx + off, mul4(a, s));
+      d0 = fma4(gp, xv, d0);
+      d1 = fma4(g1, xv, d1);
+      d2 = fma4(gm, xv, d2);
+    }
+    float* dp = dpart + ((((int64_t)n * nchunks + ch) * T + t) * 3) * C + c;
+    st4(dp, d0);
+    st4(dp + C, d1);
+    st4(dp + 2 * (int64_t)C, d2);
+  }
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+extern "C" {
+
+int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                  void* stream) {
+  VITTA_CHECK_ARG(x && kern && act && out, VITTA_E_BADARG, "tam_fwd: null pointer");
+  VITTA_CHECK_ARG(N > 0 && T > 0 && HW > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_fwd: bad shape (C %% 4 != 0?)");
+  VITTA_CHECK_ARG(aligned16(x) && aligned16(kern) && aligned16(act) && aligned16(out), VITTA_E_ALIGN,
+                  "tam_fwd: tensors must be 16-byte aligned");
+  const int64_t total = (int64_t)N * HW * (C / 4);
+  const int64_t blocks = (total + kThreads - 1) / kThreads;
+  VITTA_CHECK_ARG(blocks < (1ll << 31), VITTA_E_UNSUPPORTED, "tam_fwd: grid too large");
+  tam_fwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, kern, act, out, N, T, HW, C / 4);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_tam_num_chunks(int64_t HW, int C) {
+  (void)C;
+  return (int)((HW + kTamChunkRows - 1) / kTamChunkRows);
+}
+
+int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
+                  int N, int T, int64_t HW, int C, void* stream) {
+  VITTA_CHECK_ARG(gout && x && kern && act && gx && dpart, VITTA_E_BADARG, "tam_bwd: null pointer");
+  VITTA_CHECK_ARG(N > 0 && T > 0 && HW > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_bwd: bad shape");
+  VITTA_CHECK_ARG(aligned16(gout) && aligned16(x) && aligned16(gx) && aligned16(dpart) && aligned16(kern) &&
+                      aligned16(act),
+                  VITTA_E_ALIGN, "tam_bwd: tensors must be 16-byte aligned");
+  ClGeom g = cl_geom(1, 1, C);  // only lpr / rs / ctiles are used
+  const int nchunks = vitta_tam_num_chunks(HW, C);
+  dim3 grid((unsigned)(N * nchunks), (unsigned)g.ctiles);
+  tam_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(gout, x, kern, act, gx, dpart, N, T, HW, C, g.lpr, g.rs,
+                                                             nchunks);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""TAM and TemporalBottleneck -- mirror of the reference's ``models/tanet_models/temporal_module.py`` with the
+heavy tensor work moved into sm_100a kernels (K4 fused norm/act/stats/pool, K5 temporal stencil).
+
+Module / parameter names are the reference's (``net.conv1 .. net.bn3``, ``net.downsample.{0,1}``, ``tam.G.{0,1,3}``,
+``tam.L.{0,1,3}``) so reference checkpoints load unchanged and ``choose_layers`` enumerates the norm layers in
+the same order."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ...nn import StatsBatchNorm2d, norm_act
+
+
+class TAM(nn.Module):
+    """Temporal Adaptive Module (reference :12-65).
+
+    G (global branch): per (video, channel) a softmax-normalised 3-tap temporal kernel from the spatially
+    pooled T-vector.  L (local branch): a sigmoid gate per (video, channel, frame).  Output:
+        out[n,t,c,:] = sum_k K[n,c,k] * L[n,c,t+k-1] * x[n,t+k-1,c,:]      (zero padded in t)
+    The pooled input normally arrives from the preceding fused norm kernel (``pooled``); the tiny G/L networks
+    run as ordinary torch modules; the stencil over the (N, T, HW, C) activation is kernel K5."""
+
+    def __init__(self, in_channels, n_segment, kernel_size=3, stride=1, padding=1):
+        super().__init__()
+        if kernel_size != 3 or stride != 1 or padding != 1:
+            raise NotImplementedError("the sm_100a stencil implements the reference's only configuration "
+                                      "(kernel 3, stride 1, padding 1; temporal_module.py:134-139)")
+        self.in_channels = in_channels
+        self.n_segment = n_segment
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.G = nn.Sequential(
+            nn.Linear(n_segment, n_segment * 2, bias=False),
+            nn.BatchNorm1d(n_segment * 2), nn.ReLU(inplace=True),
+            nn.Linear(n_segment * 2, kernel_size, bias=False), nn.Softmax(-1))
+        self.L = nn.Sequential(
+            nn.Conv1d(in_channels, in_channels // 4, kernel_size, stride=1, padding=kernel_size // 2, bias=False),
+            nn.BatchNorm1d(in_channels // 4), nn.ReLU(inplace=True),
+            nn.Conv1d(in_channels // 4, in_channels, 1, bias=False), nn.Sigmoid())
+
+    def forward(self, x, pooled=None):
+        nt, c, h, w = x.shape
+        t = self.n_segment
+        n = nt // t
+        if pooled is None:
+            pooled = F.adaptive_avg_pool2d(x, 1).flatten(1)          # (N*T, C)
+        p_nct = pooled.view(n, t, c).permute(0, 2, 1)                # (N, C, T)
+        kern = self.G(p_nct.reshape(n * c, t)).view(n, c, self.kernel_size).permute(0, 2, 1).contiguous()   # (N, 3, C)
+        act = self.L(p_nct.contiguous()).permute(0, 2, 1).contiguous()                                       # (N, T, C)
+        x = x.contiguous(memory_format=torch.channels_last)
+        return ops.TamStencilFn.apply(x, kern, act, t)
+
+
+class Bottleneck(nn.Module):
+    """torchvision ResNet v1.5 bottleneck container (stride on the 3x3 conv); only holds the layers."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = StatsBatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = StatsBatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
+        self.bn3 = StatsBatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class TemporalBottleneck(nn.Module):
+    """conv1-bn1-relu-TAM-conv2-bn2-relu-conv3-bn3 (+downsample) -add-relu (reference :68-106)."""
+
+    def __init__(self, net, n_segment=8, t_kernel_size=3, t_stride=1, t_padding=1):
+        super().__init__()
+        self.net = net
+        assert isinstance(net, Bottleneck)
+        self.n_segment = n_segment
+        self.tam = TAM(in_channels=net.conv1.out_channels, n_segment=n_segment, kernel_size=t_kernel_size,
+                       stride=t_stride, padding=t_padding)
+
+    def forward(self, x, want_pool=False):
+        net, t = self.net, self.n_segment
+        out = net.conv1(x)
+        out, pooled = norm_act(net.bn1, out, True, t, want_pool=True)       # BN + stats + ReLU + HW-pool: 1 pass
+        out = self.tam(out, pooled)
+        out = net.conv2(out)
+        out, _ = norm_act(net.bn2, out, True, t)
+        out = net.conv3(out)
+        if net.downsample is not None:
+            idt = net.downsample[0](x)
+            return norm_act(net.bn3, out, True, t, res=idt, res_bn=net.downsample[1], want_pool=want_pool)
+        return norm_act(net.bn3, out, True, t, res=x, want_pool=want_pool)
+
+
+def make_temporal_modeling(net, n_segment=8, t_kernel_size=3, t_stride=1, t_padding=1):
+    """Wrap every Bottleneck of layer1..layer4 in a TemporalBottleneck (reference :109-140)."""
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        stage = getattr(net, name)
+        setattr(net, name, nn.Sequential(*[TemporalBottleneck(b, n_segment, t_kernel_size, t_stride, t_padding)
+                                           for b in stage.children()]))

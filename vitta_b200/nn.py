@@ -1,0 +1,52 @@
+"""Norm modules that can host a statistics *tap* (see utils/norm_stats_utils.py) and the fused call path."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class StatsBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters / buffers / state-dict keys).  Called as a module it behaves exactly
+    like its base class, so foreign forward hooks keep working; the vitta_b200 models call
+    :func:`norm_act` instead, which runs the fused sm_100a kernel when that is legal."""
+    _vitta_fused = True
+    _vitta_tap = None
+
+
+def _fusable(bn):
+    return (bn is not None and isinstance(bn, StatsBatchNorm2d) and not bn.training and not bn._forward_hooks
+            and not bn._forward_pre_hooks)
+
+
+def norm_act(bn, x, relu, clip_len, res=None, res_bn=None, want_pool=False):
+    """out = relu?(bn(x) + [res | res_bn(res)]); returns (out, per-frame mean of out or None).
+
+    Fused path (K4): eval-mode BatchNorm without foreign hooks -- one kernel reads x (and res) once, writes
+    out once, and emits the statistics partials of whatever taps are attached to ``bn`` / ``res_bn``.
+    Otherwise (BatchNorm in training mode, i.e. ``fix_BNS=False``, or third-party forward hooks present) the
+    modules are called one by one so that every hook observes the reference's tensors."""
+    if _fusable(bn) and (res_bn is None or _fusable(res_bn)) and x.is_cuda:
+        arena = ly_main = ly_res = None
+        tap = bn._vitta_tap
+        n_clips = x.shape[0] // clip_len if clip_len else x.shape[0]
+        if tap is not None:
+            arena, ly_main = tap.tap_target()
+            tap.note_batch(n_clips)
+        if res_bn is not None and res_bn._vitta_tap is not None:
+            a2, ly_res = res_bn._vitta_tap.tap_target()
+            res_bn._vitta_tap.note_batch(n_clips)
+            if arena is not None and a2 is not arena:
+                raise RuntimeError("taps of one block belong to different arenas")
+            arena = a2
+        x = x.contiguous(memory_format=torch.channels_last)
+        if res is not None:
+            res = res.contiguous(memory_format=torch.channels_last)
+        return ops.bn_act(x, bn, relu, res, res_bn, arena, ly_main, ly_res, want_pool)
+    y = bn(x)
+    if res is not None:
+        y = y + (res_bn(res) if res_bn is not None else res)
+    if relu:
+        y = F.relu(y)
+    pool = F.adaptive_avg_pool2d(y, 1).flatten(1) if want_pool else None
+    return y, pool

@@ -1,0 +1,535 @@
+"""Autograd operators over the C-ABI kernels (include/vitta_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every byte of the
+hot-path arithmetic below runs in libvitta_b200.so.  Nothing in this file falls back to eager torch
+math when the library is missing -- ``_lib.load()`` raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+CL = torch.channels_last
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.VittaError("%s: vitta_b200 kernels need CUDA tensors (got %s); there is no CPU path" % (what, t.device))
+    if t.dtype != torch.float32:
+        raise _lib.VittaError("%s: fp32 only (got %s)" % (what, t.dtype))
+
+
+def as_rows_cl(x):
+    """4-D logical (F, C, H, W) tensor in channels_last memory -> (frames, frame_rows, C) geometry."""
+    f, c, h, w = x.shape
+    return f, h * w, c
+
+
+def to_cl(x):
+    return x.contiguous(memory_format=CL)
+
+
+# ----------------------------------------------------------------------------------------------
+# Statistics arena: one finalize launch (merge + EMA + loss + backward coefficients) for all layers
+# ----------------------------------------------------------------------------------------------
+class _Layer:
+    __slots__ = ("idx", "C", "reg_type", "moving_avg", "momentum", "has_source", "ch_off", "geom_key", "chunking",
+                 "part", "count", "meter_count", "fired", "token", "name", "n_batch")
+
+
+class StatsArena:
+    """State shared by all alignment hooks attached to one model.
+
+    Forward: each hooked layer writes per-chunk (mean, M2) partials (K1, fused into the norm kernel where
+    the model is ours).  ``finalize()`` -- triggered lazily by the first ``r_feature`` read after the
+    forward -- merges them (and, with ``process_group`` set, all-gathers per-rank merges: collective C1),
+    applies the EMA / average meter, evaluates the L1/MSE/KLD alignment loss per layer and emits the
+    per-channel coefficients (a_c, b_c) of dLoss/dy = a_c + b_c*y consumed by the backward kernels.
+    """
+
+    def __init__(self, device=None, process_group=None):
+        self.device = device
+        self.layers = []
+        self.frozen = False
+        self.finalized = True      # nothing pending
+        self.desc_dirty = True
+        self.process_group = process_group
+        self._desc_dev = None
+        self._desc_active = None
+        self._base = None
+        self.total_C = 0
+        self.finalize_calls = 0
+
+    # -- registration ---------------------------------------------------------------------------
+    def add_layer(self, C_, src_mean, src_var, reg_type, moving_avg, momentum, name=""):
+        ly = _Layer()
+        ly.idx = len(self.layers)
+        ly.C = int(C_)
+        ly.reg_type = _lib.REG_TYPES[reg_type] if src_mean is not None else 0
+        ly.moving_avg = bool(moving_avg)
+        ly.momentum = float(momentum)
+        ly.has_source = src_mean is not None
+        ly.ch_off = self.total_C
+        ly.geom_key = None
+        ly.chunking = None
+        ly.part = None
+        ly.count = 0
+        ly.meter_count = 0
+        ly.fired = False
+        ly.token = None
+        ly.name = name
+        ly.n_batch = 1
+        self.total_C += ly.C
+        self.layers.append(ly)
+        self._pending_src = getattr(self, "_pending_src", [])
+        self._pending_src.append((src_mean, src_var))
+        if self.frozen:
+            self._grow()
+        return ly
+
+    def _alloc(self, dev):
+        n = self.total_C
+        z = lambda: torch.zeros(n, dtype=torch.float32, device=dev)
+        self.src_mean, self.src_var = z(), torch.ones(n, dtype=torch.float32, device=dev)
+        self.ema_mean, self.ema_var = z(), z()
+        self.batch_mean, self.batch_var = z(), z()
+        self.coef_a, self.coef_b = z(), z()
+        for ly, (m, v) in zip(self.layers, self._pending_src):
+            if m is not None:
+                sl = slice(ly.ch_off, ly.ch_off + ly.C)
+                self.src_mean[sl] = torch.as_tensor(m, dtype=torch.float32).to(dev).reshape(-1)
+                self.src_var[sl] = torch.as_tensor(v, dtype=torch.float32).to(dev).reshape(-1)
+        self.loss = torch.zeros(len(self.layers) + 2, dtype=torch.float32, device=dev)
+        self._base = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def _freeze(self, dev):
+        if self.frozen:
+            return
+        self.device = dev
+        self._alloc(dev)
+        self.frozen = True
+        self.desc_dirty = True
+
+    def _grow(self):
+        old = (self.ema_mean, self.ema_var, self.batch_mean, self.batch_var)
+        self._alloc(self.device)
+        for dst, src in zip((self.ema_mean, self.ema_var, self.batch_mean, self.batch_var), old):
+            dst[:src.numel()] = src
+        self.desc_dirty = True
+
+    # -- forward side ---------------------------------------------------------------------------
+    def partial_buffer(self, ly, O, Cc, I, frames, dev):
+        """Return the (mean, M2) partial buffer of a layer for this forward, starting a new step if needed."""
+        self._freeze(dev)
+        if self.finalized:
+            self.finalized = False
+            for l2 in self.layers:
+                l2.fired = False
+        key = (O, Cc, I, frames)
+        if ly.geom_key != key:
+            ch = _lib.chunking(O, Cc, I, frames)
+            ly.chunking = ch
+            ly.geom_key = key
+            ly.part = torch.empty(ch.n_entries * Cc * 2, dtype=torch.float32, device=dev)
+            ly.count = O * I
+            self.desc_dirty = True
+        ly.fired = True
+        return ly.part
+
+    def record(self, ly, feat, O, Cc, I, frames=1):
+        """Standalone K1 launch on a feature tensor (hooks on stock torch modules)."""
+        part = self.partial_buffer(ly, O, Cc, I, frames, feat.device)
+        call("vitta_stats_partial", ptr(feat), O, Cc, I, frames, ptr(part), stream_ptr())
+
+    # -- finalize -------------------------------------------------------------------------------
+    def _build_descs(self, active, gathered=None):
+        arr = (_lib.VittaLayerDesc * len(active))()
+        base = self._base.data_ptr()
+        for i, ly in enumerate(active):
+            d = arr[i]
+            d.C = ly.C
+            d.ch_off = ly.ch_off
+            d.reg_type = ly.reg_type
+            d.has_source = 1 if ly.has_source else 0
+            if ly.moving_avg:
+                d.w_new, d.w_old = ly.momentum, 1.0 - ly.momentum
+            else:
+                n = ly.n_batch
+                d.w_new = n / float(ly.meter_count + n)
+                d.w_old = ly.meter_count / float(ly.meter_count + n)
+            if gathered is None:
+                ch = ly.chunking
+                d.n_entries, d.chunk_rows, d.chunks_per_frame = ch.n_entries, ch.chunk_rows, ch.chunks_per_frame
+                d.frame_rows = ch.frame_rows
+                off = ly.part.data_ptr() - base
+                assert off % 4 == 0
+                d.part_off, d.entry_stride = off // 4, 2 * ly.C
+                d.cnt_off = d.cnt_stride = 0
+            else:
+                world, n_active = gathered
+                d.n_entries, d.chunk_rows, d.chunks_per_frame, d.frame_rows = world, 0, 1, 0
+                d.part_off, d.entry_stride = 2 * ly.ch_off, 2 * self.total_C
+                d.cnt_off, d.cnt_stride = i, n_active
+        return arr
+
+    @staticmethod
+    def _upload(arr):
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host
+
+    def finalize(self):
+        if self.finalized:
+            return
+        active = [ly for ly in self.layers if ly.fired]
+        if not active:
+            self.finalized = True
+            return
+        dev = self.device
+        any_mean_meter = any(not ly.moving_avg for ly in active)
+        ids = tuple(ly.idx for ly in active)
+        if self.desc_dirty or ids != self._desc_active or any_mean_meter:
+            self._desc_dev = self._upload(self._build_descs(active)).to(dev)
+            if self.process_group is not None:
+                ws = torch.distributed.get_world_size(self.process_group)
+                self._desc_gath = self._upload(self._build_descs(active, (ws, len(active)))).to(dev)
+            if ids != self._desc_active:
+                self.loss.zero_()       # the ticket slot moves with the number of active layers
+            self._desc_active = ids
+            self.desc_dirty = False
+        st = stream_ptr()
+        n = len(active)
+        if self.process_group is None:
+            call("vitta_stats_finalize", ptr(self._desc_dev), n, ptr(self._base), None, ptr(self.src_mean),
+                 ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
+                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, st)
+        else:
+            import torch.distributed as dist
+            ws = dist.get_world_size(self.process_group)
+            # payload per rank: [2*total_C floats (mean, M2)] + [n int32 counts bit-cast to float]
+            pay = torch.empty(2 * self.total_C + n, dtype=torch.float32, device=dev)
+            merged = pay[:2 * self.total_C]
+            cnts = pay[2 * self.total_C:].view(torch.int32)
+            call("vitta_stats_finalize", ptr(self._desc_dev), n, ptr(self._base), None, None, None, None, None, None,
+                 None, None, None, None, 1, ptr(merged), ptr(cnts), st)
+            gath = torch.empty(ws * pay.numel(), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gath, pay, group=self.process_group)   # collective C1 (NCCL over NVLink)
+            g2 = gath.view(ws, -1)
+            means = g2[:, :2 * self.total_C].contiguous()
+            counts = g2[:, 2 * self.total_C:].contiguous().view(torch.int32)
+            self._gath_keep = (means, counts)
+            call("vitta_stats_finalize", ptr(self._desc_gath), n, ptr(means), ptr(counts), ptr(self.src_mean),
+                 ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
+                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, st)
+        for ly in active:
+            if not ly.moving_avg:
+                ly.meter_count += ly.n_batch
+        self._loss_index = {ly.idx: i for i, ly in enumerate(active)}
+        self._n_active = n
+        self.finalized = True
+        self.finalize_calls += 1
+
+    def layer_loss(self, ly):
+        """r_feature of one layer: differentiable w.r.t. the layer's token (see _RFeature)."""
+        self.finalize()
+        i = self._loss_index[ly.idx]
+        if ly.token is None or not ly.token.requires_grad:
+            return self.loss[i].clone()
+        return _RFeature.apply(ly.token, self.loss, i)
+
+    def vec(self, t, ly):
+        return t[ly.ch_off:ly.ch_off + ly.C]
+
+    def coef_ptrs(self, ly):
+        off = ly.ch_off * 4
+        return C.c_void_p(self.coef_a.data_ptr() + off), C.c_void_p(self.coef_b.data_ptr() + off)
+
+
+class _RFeature(torch.autograd.Function):
+    """Ties the scalar loss of a layer (written by the finalize kernel) to that layer's autograd token."""
+
+    @staticmethod
+    def forward(ctx, token, loss, i):
+        return loss[i].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+def new_token(ref):
+    """0-dim placeholder returned by the forward operators; its gradient is d(total loss)/d(r_feature)."""
+    return torch.empty((), dtype=torch.float32, device=ref.device)
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 + K3 on stock modules: statistics tap with closed-form backward
+# ----------------------------------------------------------------------------------------------
+class StatsTapFn(torch.autograd.Function):
+    """feature described as (O, C, I) -> token.  backward: dL/dfeature = g * (a_c + b_c * y).
+
+    ``y`` is ``feature`` itself, or -- for an eval-mode BatchNorm whose output a following in-place ReLU
+    overwrites (torchvision Bottleneck) -- recomputed as yscale[c]*saved + yshift[c] from the BatchNorm
+    *input* ``saved``.  The gradient is always returned for ``feature`` (the norm output), so autograd's own
+    norm backward distributes it to the norm input and affine parameters exactly as in the reference."""
+
+    @staticmethod
+    def forward(ctx, feature, saved, arena, ly, O, Cc, I, frames, yscale, yshift):
+        arena.record(ly, feature, O, Cc, I, frames)
+        ctx.arena, ctx.ly, ctx.geom = arena, ly, (O, Cc, I)
+        ctx.save_for_backward(saved, yscale, yshift)
+        return new_token(feature)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved, yscale, yshift = ctx.saved_tensors
+        O, Cc, I = ctx.geom
+        ca, cb = ctx.arena.coef_ptrs(ctx.ly)
+        g = g.contiguous()
+        gy = torch.empty_like(saved)
+        call("vitta_stats_inject", ptr(saved), ptr(yscale), ptr(yshift), ca, cb, ptr(g), ptr(gy), O, Cc, I, stream_ptr())
+        return gy, None, None, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# K4: fused BN(eval) + stats + residual + ReLU + pooling
+# ----------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _bwd_ws(frames, frame_rows, Cc, dev):
+    key = (frames, frame_rows, Cc, dev)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = _lib.load().vitta_bn_act_bwd_ws_floats(frames, frame_rows, Cc)
+        ws = torch.zeros(n, dtype=torch.float32, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+class BNActFn(torch.autograd.Function):
+    """out = relu?( BN(x) + [res | BN2(res)] ), statistics partials of BN(x) / BN2(res) into the arena,
+    optional per-frame mean of out.  x, res: logical (F, C, H, W), channels_last memory."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rm, rv, eps, res, w2, b2, rm2, rv2, eps2, relu, arena, ly_main, ly_res, want_pool,
+                stat_frames):
+        _require_cuda(x, "bn_act")
+        if not x.is_contiguous(memory_format=CL):
+            raise _lib.VittaError("bn_act: x must be channels_last contiguous")
+        frames, frame_rows, Cc = as_rows_cl(x)
+        dev = x.device
+        out = torch.empty_like(x)          # preserves channels_last
+        has_res_bn = w2 is not None
+        if res is not None and not res.is_contiguous(memory_format=CL):
+            raise _lib.VittaError("bn_act: residual must be channels_last contiguous")
+        # the kernel's chunking: per-frame when pooling is requested, else one flat frame
+        kf, kr = (frames, frame_rows) if want_pool else (1, frames * frame_rows)
+        part_main = part_res = None
+        if ly_main is not None:
+            part_main = arena.partial_buffer(ly_main, frames * frame_rows, Cc, 1, kf, dev)
+        if ly_res is not None:
+            part_res = arena.partial_buffer(ly_res, frames * frame_rows, Cc, 1, kf, dev)
+        pool_part = pool_out = None
+        if want_pool:
+            ch = _lib.chunking(frames * frame_rows, Cc, 1, kf)
+            pool_part = torch.empty(ch.n_entries * Cc, dtype=torch.float32, device=dev)
+            pool_out = torch.empty(frames, Cc, dtype=torch.float32, device=dev)
+        bn = _lib.make_bn(w, b, rm, rv, eps)
+        bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
+        call("vitta_bn_act_fwd", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu), ptr(out),
+             ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, stream_ptr())
+        ctx.save_for_backward(x, w, b, rm, rv, res, w2, b2, rm2, rv2)
+        ctx.meta = (eps, eps2, bool(relu), arena, ly_main, ly_res, want_pool, kf, kr, Cc)
+        tok_main = new_token(x) if ly_main is not None else None
+        tok_res = new_token(x) if ly_res is not None else None
+        return out, pool_out, tok_main, tok_res
+
+    @staticmethod
+    def backward(ctx, gout, gpool, gtok_main, gtok_res):
+        x, w, b, rm, rv, res, w2, b2, rm2, rv2 = ctx.saved_tensors
+        eps, eps2, relu, arena, ly_main, ly_res, want_pool, kf, kr, Cc = ctx.meta
+        dev = x.device
+        if gout is None:
+            gout = torch.zeros_like(x)
+        gout = gout.contiguous(memory_format=CL)
+        has_res, has_res_bn = res is not None, w2 is not None
+        gx = torch.empty_like(x)
+        gres = torch.empty_like(res) if has_res else None
+        gw = torch.zeros(Cc, dtype=torch.float32, device=dev)
+        gb = torch.zeros(Cc, dtype=torch.float32, device=dev)
+        gw2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
+        gb2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
+        ca = cb = gs = ca2 = cb2 = gs2 = None
+        if ly_main is not None and gtok_main is not None:
+            ca, cb = arena.coef_ptrs(ly_main)
+            gs = ptr(gtok_main.contiguous())
+        if ly_res is not None and gtok_res is not None:
+            ca2, cb2 = arena.coef_ptrs(ly_res)
+            gs2 = ptr(gtok_res.contiguous())
+        if gpool is not None:
+            gpool = gpool.contiguous()
+        ws = _bwd_ws(kf, kr, Cc, dev)
+        bn = _lib.make_bn(w, b, rm, rv, eps)
+        bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
+        call("vitta_bn_act_bwd", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
+             C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, gs, ca2, cb2, gs2, ptr(gx), ptr(gres),
+             ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, stream_ptr())
+        return (gx, gw, gb, None, None, None, gres, gw2, gb2, None, None, None, None, None, None, None, None, None)
+
+
+def bn_act(x, bn, relu, res=None, res_bn=None, arena=None, ly_main=None, ly_res=None, want_pool=False):
+    """Functional wrapper.  ``bn`` / ``res_bn`` are nn.BatchNorm2d modules in eval mode."""
+    w2 = b2 = rm2 = rv2 = None
+    eps2 = 0.0
+    if res_bn is not None:
+        w2, b2, rm2, rv2, eps2 = res_bn.weight, res_bn.bias, res_bn.running_mean, res_bn.running_var, res_bn.eps
+    out, pool, tok_main, tok_res = BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, res,
+                                                 w2, b2, rm2, rv2, eps2, relu, arena, ly_main, ly_res, want_pool, None)
+    if ly_main is not None:
+        ly_main.token = tok_main
+    if ly_res is not None:
+        ly_res.token = tok_res
+    return out, pool
+
+
+# ----------------------------------------------------------------------------------------------
+# K5: TAM stencil
+# ----------------------------------------------------------------------------------------------
+class TamStencilFn(torch.autograd.Function):
+    """x (N*T, C, H, W) channels_last; kern (N, 3, C); act (N, T, C) -> out like x."""
+
+    @staticmethod
+    def forward(ctx, x, kern, act, T):
+        _require_cuda(x, "tam")
+        if not x.is_contiguous(memory_format=CL):
+            raise _lib.VittaError("tam: x must be channels_last contiguous")
+        nt, Cc, h, w = x.shape
+        n = nt // T
+        kern, act = kern.contiguous(), act.contiguous()
+        out = torch.empty_like(x)
+        call("vitta_tam_fwd", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, stream_ptr())
+        ctx.save_for_backward(x, kern, act)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, kern, act = ctx.saved_tensors
+        T = ctx.T
+        nt, Cc, h, w = x.shape
+        n = nt // T
+        gout = gout.contiguous(memory_format=CL)
+        gx = torch.empty_like(x)
+        nch = _lib.load().vitta_tam_num_chunks(h * w, Cc)
+        dpart = torch.empty(n, nch, T, 3, Cc, dtype=torch.float32, device=x.device)
+        call("vitta_tam_bwd", ptr(gout), ptr(x), ptr(kern), ptr(act), ptr(gx), ptr(dpart), n, T, h * w, Cc, stream_ptr())
+        D = dpart.sum(1)                                   # (N, T, 3, C): tiny
+        gkern = (act.unsqueeze(2) * D).sum(1)              # (N, 3, C)
+        gact = (kern.unsqueeze(1) * D).sum(2)              # (N, T, C)
+        return gx, gkern, gact, None
+
+
+# ----------------------------------------------------------------------------------------------
+# K10: prediction consistency
+# ----------------------------------------------------------------------------------------------
+class PredConsisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds):
+        _require_cuda(preds, "pred_consis")
+        p = preds.contiguous()
+        b, v, k = p.shape
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        grad = torch.empty_like(p)
+        call("vitta_pred_consis", ptr(p), b, v, k, ptr(loss), ptr(grad), stream_ptr())
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, = ctx.saved_tensors
+        return grad * g
+
+
+# ----------------------------------------------------------------------------------------------
+# K11: fused SGD
+# ----------------------------------------------------------------------------------------------
+class FusedSGD:
+    """torch.optim.SGD(params, lr, momentum, weight_decay) semantics (dampening 0, no nesterov) in one
+    kernel launch over a device-resident tensor table (corpus/basics.py:559-560,669-671).  Parameters
+    whose ``.grad`` is None are skipped exactly like torch does (no decay, no momentum update)."""
+
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, process_group=None):
+        self.params = [p for p in params]
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        self.bufs = {}
+        self._key = None
+        self._tables = None
+        self.process_group = process_group
+        self.param_groups = [{"params": self.params, "lr": self.lr, "momentum": self.momentum,
+                              "weight_decay": self.weight_decay}]
+        self._block = None
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
+
+    def _table(self, items, dev):
+        n = len(items)
+        arr = (_lib.VittaSgdTensor * n)()
+        starts = []
+        blk = 0
+        for i, (p, g, buf) in enumerate(items):
+            arr[i].p, arr[i].g, arr[i].buf, arr[i].n = p.data_ptr(), g.data_ptr(), buf.data_ptr(), p.numel()
+            starts.append(blk)
+            blk += (p.numel() + self._block - 1) // self._block
+        tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        st = torch.tensor(starts, dtype=torch.int32).to(dev)
+        return tab, st, n, blk
+
+    @torch.no_grad()
+    def step(self):
+        if self._block is None:
+            self._block = _lib.load().vitta_sgd_block_elems()
+        lr = float(self.param_groups[0]["lr"])
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        dev = live[0].device
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in live]
+        if self.process_group is not None:
+            import torch.distributed as dist
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, group=self.process_group)            # collective C2: gradient sum over ranks
+            outs, o = [], 0
+            for g in grads:
+                outs.append(flat[o:o + g.numel()])
+                o += g.numel()
+            grads = outs
+            self._flat_keep = flat
+        first, rest = [], []
+        for p, g in zip(live, grads):
+            if not p.is_contiguous():
+                raise _lib.VittaError("FusedSGD: parameters must be contiguous")
+            buf = self.bufs.get(p)
+            if buf is None:
+                buf = torch.empty_like(p, memory_format=torch.contiguous_format)
+                self.bufs[p] = buf
+                first.append((p, g, buf))
+            else:
+                rest.append((p, g, buf))
+        key = (tuple((p.data_ptr(), g.data_ptr()) for p, g, _ in first), tuple((p.data_ptr(), g.data_ptr()) for p, g, _ in rest))
+        if key != self._key:
+            self._tables = (self._table(first, dev) if first else None, self._table(rest, dev) if rest else None)
+            self._key = key
+        st = stream_ptr()
+        for tab, is_first in ((self._tables[0], 1), (self._tables[1], 0)):
+            if tab is None:
+                continue
+            t, starts, n, blocks = tab
+            call("vitta_sgd_step", ptr(t), ptr(starts), n, blocks, lr, self.momentum, self.weight_decay, is_first, 1.0, st)
