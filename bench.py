@@ -227,6 +227,14 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         adapter.adapt(resident)
+    if args.ncu_step:
+        # profiling aid: `ncu --profile-from-start off ... bench.py --ncu-step` captures exactly one warm step
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        adapter.adapt(resident)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -290,6 +298,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--ncu-step", dest="ncu_step", action="store_true",
+                    help="run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,7 +93,8 @@ typedef struct VittaLayerDesc {
 
 /* Per-channel arenas (length = sum of C over layers): src_mean, src_var (read), ema_mean, ema_var
  * (read-modify-write), batch_mean, batch_var (write), coef_a, coef_b (write):
- *     dLoss_l/dy[.., c, ..] = coef_a[c] + coef_b[c] * y          
+ *     dLoss_l/dy[.., c, ..] = coef_a[c] + coef_b[c] * (y - batch_mean[c])     (SURVEY.md section 8a row a5;
+ *     the centred form keeps fp32 accuracy when |mean| >> std)
  * loss[l] receives r_feature of layer l; loss[n_layers] their sum (summed in layer order by the last CTA
  * to finish); loss[n_layers+1] is an int32 ticket the caller zero-initialises once (self-resetting).
  * merge_only != 0: only merge entries and write (mean, M2) pairs to merged[(ch_off + c)*2 + {0,1}] and
@@ -104,12 +105,13 @@ int vitta_stats_finalize(const VittaLayerDesc* descs, int n_layers, const float*
                          int merge_only, float* merged, int32_t* merged_counts, void* stream);
 
 /* K3  standalone backward of the alignment loss of one layer (used by hooks on stock torch modules):
- *     gy[o,c,i] = (*gscale) * (coef_a[c] + coef_b[c] * y[o,c,i]),  y = yscale[c]*x + yshift[c] when the
- *     two affine vectors are given (BatchNorm eval output recomputed from its saved input), else y = x.
+ *     gy[o,c,i] = (*gscale) * (coef_a[c] + coef_b[c] * (y[o,c,i] - mean[c])),  y = yscale[c]*x + yshift[c] when
+ *     the two affine vectors are given (BatchNorm eval output recomputed from its saved input), else y = x.
+ *     mean = the layer's slice of batch_mean.
  *   replaces: autograd of var/mean/permute/contiguous, utils/norm_stats_utils.py:242-253 */
 int vitta_stats_inject(const float* x, const float* yscale, const float* yshift, const float* coef_a,
-                       const float* coef_b, const float* gscale, float* gy, int64_t O, int C, int64_t I,
-                       void* stream);
+                       const float* coef_b, const float* mean, const float* gscale, float* gy, int64_t O, int C,
+                       int64_t I, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  fused BatchNorm(eval) [+ statistics partials] [+ residual (optionally through a second BN, with its
@@ -140,18 +142,18 @@ int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN
  *   gpre = gout * (out > 0)           [out recomputed]   (+ gpool[frame, c] / frame_rows: gpool is the gradient of
  *                                                         pool_out, spread over every row of the frame; applied
  *                                                         to `out`, i.e. before the ReLU mask)
- *   gy   = gpre + gs_main * (a[c] + b[c]*y)      gx   = gy * k[c]
- *   gr   = gpre (+ gs_res*(a2[c] + b2[c]*r) and gres = gr*k2[c] when res_bn)
+ *   gy   = gpre + gs_main * (a[c] + b[c]*(y - mean[c]))      gx   = gy * k[c]
+ *   gr   = gpre (+ gs_res*(a2[c] + b2[c]*(r - mean2[c])) and gres = gr*k2[c] when res_bn)
  *   gw[c] += sum gy * xhat, gb[c] += sum gy  (and the same for the residual BN), accumulated into the
  *   given gradient vectors deterministically (per-chunk partials in `ws`, last CTA reduces).
  * ws: workspace of vitta_bn_act_bwd_ws_floats() floats, zero-initialised ONCE by the caller (self-resetting).
  *   replaces: autograd of the chain above + of the hook statistics. */
 int64_t vitta_bn_act_bwd_ws_floats(int64_t frames, int64_t frame_rows, int C);
 int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
-                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* gs_main,
-                     const float* coef_a2, const float* coef_b2, const float* gs_res, float* gx, float* gres,
-                     float* gw, float* gb, float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows,
-                     int C, void* stream);
+                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* mean_main,
+                     const float* gs_main, const float* coef_a2, const float* coef_b2, const float* mean_res,
+                     const float* gs_res, float* gx, float* gres, float* gw, float* gb, float* gw2, float* gb2,
+                     float* ws, int64_t frames, int64_t frame_rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  TAM temporal stencil, channels-last.  x, out: (N, T, HW, C); kern: (N, 3, C); act: (N, T, C)

@@ -28,8 +28,18 @@ def _fp32(cuda_device):
     nsu.set_process_group(None)
 
 
+def _identity_bn(mod):
+    """The unit protocols below hand the hook `output == input`.  For an eval-mode BatchNorm the hook recomputes the
+    output from the module input in backward (in-place-ReLU safety), so the module must really be the identity:
+    running_var = 1 - eps makes weight * rsqrt(running_var + eps) == 1 (a default BN scales by 1/sqrt(1 + 1e-5))."""
+    if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm3d)):
+        with torch.no_grad():
+            mod.running_var.fill_(1.0 - mod.eps)
+    return mod
+
+
 def _mod(kind, c):
-    return {"bn2d": nn.BatchNorm2d(c), "bn3d": nn.BatchNorm3d(c), "ln": nn.LayerNorm(c)}[kind]
+    return _identity_bn({"bn2d": nn.BatchNorm2d(c), "bn3d": nn.BatchNorm3d(c), "ln": nn.LayerNorm(c)}[kind])
 
 
 @pytest.mark.parametrize("kind", ["bn2d", "bn3d", "ln"])
@@ -139,7 +149,7 @@ def test_stats_kernels_vs_oracle(cuda_device, shape, layout):
     g = torch.Generator().manual_seed(1)
     f, c, h, w = shape
     T = 8
-    mod = nn.BatchNorm2d(c).to(cuda_device).eval()
+    mod = _identity_bn(nn.BatchNorm2d(c)).to(cuda_device).eval()
     src_m = torch.randn(c, generator=g) * 0.3
     src_v = torch.rand(c, generator=g) + 0.5
     hook = CombineNormStatsRegHook_onereg(mod, clip_len=T, spatiotemp_stats_clean_tuple=(src_m.numpy(), src_v.numpy()),

@@ -41,12 +41,12 @@ _SIGNATURES = {
     "vitta_stats_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.POINTER(VittaChunking)]),
     "vitta_stats_partial": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int64, _P, _P]),
     "vitta_stats_finalize": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
-    "vitta_stats_inject": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, _P]),
+    "vitta_stats_inject": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, _P]),
     "vitta_bn_act_fwd": (C.c_int, [_P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, C.c_int64,
                                    C.c_int64, C.c_int, _P]),
     "vitta_bn_act_bwd_ws_floats": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
     "vitta_bn_act_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P,
-                                   _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+                                   _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "vitta_tam_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),

@@ -157,8 +157,8 @@ struct BwdArgs {
   const float* x;
   const float* res;
   BNDev bn, bn2;
-  const float *ca, *cb, *gs;     // main-branch alignment coefficients (null: none)
-  const float *ca2, *cb2, *gs2;  // residual-BN alignment coefficients
+  const float *ca, *cb, *cm, *gs;     // main-branch alignment coefficients + batch mean (null: none)
+  const float *ca2, *cb2, *cm2, *gs2; // residual-BN alignment coefficients
   float *gx, *gres, *gw, *gb, *gw2, *gb2;
   float* ws;
   int relu, C, lpr, rs, chunk_rows, cpf;
@@ -169,6 +169,8 @@ struct BwdArgs {
 __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
   return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
 }
+
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
 template <int RES>
 __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
@@ -186,15 +188,15 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
     const Aff4 a = load_aff(p.bn, c);
     Aff4 a2;
     if (RES == 2) a2 = load_aff(p.bn2, c);
-    float4 ca = f4zero(), cb = f4zero(), ca2 = f4zero(), cb2 = f4zero();
+    float4 ca = f4zero(), cb = f4zero(), ca2 = f4zero(), cb2 = f4zero(), cm = f4zero(), cm2 = f4zero();
     if (p.ca) {
       const float g = __ldg(p.gs);
-      ca = ldg4(p.ca + c); cb = ldg4(p.cb + c);
+      ca = ldg4(p.ca + c); cb = ldg4(p.cb + c); cm = ldg4(p.cm + c);
       ca.x *= g; ca.y *= g; ca.z *= g; ca.w *= g; cb.x *= g; cb.y *= g; cb.z *= g; cb.w *= g;
     }
     if (RES == 2 && p.ca2) {
       const float g = __ldg(p.gs2);
-      ca2 = ldg4(p.ca2 + c); cb2 = ldg4(p.cb2 + c);
+      ca2 = ldg4(p.ca2 + c); cb2 = ldg4(p.cb2 + c); cm2 = ldg4(p.cm2 + c);
       ca2.x *= g; ca2.y *= g; ca2.z *= g; ca2.w *= g; cb2.x *= g; cb2.y *= g; cb2.z *= g; cb2.w *= g;
     }
     for (int64_t e = blockIdx.x; e < p.n_chunks; e += gridDim.x) {
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
           g.z = (y.z + rr.z > 0.f) ? g.z : 0.f; g.w = (y.w + rr.w > 0.f) ? g.w : 0.f;
         }
         // main branch
-        float4 gy = f4fma(cb, y, ca);
+        float4 gy = f4fma(cb, f4sub(y, cm), ca);
         gy.x += g.x; gy.y += g.y; gy.z += g.z; gy.w += g.w;
         st4(p.gx + off, make_float4(gy.x * a.k.x, gy.y * a.k.y, gy.z * a.k.z, gy.w * a.k.w));
         agb.x += gy.x; agb.y += gy.y; agb.z += gy.z; agb.w += gy.w;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
         if (RES == 1) {
           st4(p.gres + off, g);
         } else if (RES == 2) {
-          float4 gr = f4fma(cb2, rr, ca2);
+          float4 gr = f4fma(cb2, f4sub(rr, cm2), ca2);
           gr.x += g.x; gr.y += g.y; gr.z += g.z; gr.w += g.w;
           st4(p.gres + off, make_float4(gr.x * a2.k.x, gr.y * a2.k.y, gr.z * a2.k.z, gr.w * a2.k.w));
           agb2.x += gr.x; agb2.y += gr.y; agb2.z += gr.z; agb2.w += gr.w;
@@ -334,25 +336,28 @@ int64_t vitta_bn_act_bwd_ws_floats(int64_t frames, int64_t frame_rows, int C) {
 }
 
 int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
-                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* gs_main,
-                     const float* coef_a2, const float* coef_b2, const float* gs_res, float* gx, float* gres,
-                     float* gw, float* gb, float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows,
-                     int C, void* stream) {
+                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* mean_main,
+                     const float* gs_main, const float* coef_a2, const float* coef_b2, const float* mean_res,
+                     const float* gs_res, float* gx, float* gres, float* gw, float* gb, float* gw2, float* gb2,
+                     float* ws, int64_t frames, int64_t frame_rows, int C, void* stream) {
   VITTA_CHECK_ARG(gout && x && gx && ws, VITTA_E_BADARG, "bn_act_bwd: null pointer");
   VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && frames > 0 && frame_rows > 0, VITTA_E_BADARG, "bn_act_bwd: bad shape");
   VITTA_CHECK_ARG(aligned16(gout) && aligned16(x) && aligned16(gx) && (!res || aligned16(res)) &&
                       (!gres || aligned16(gres)) && aligned16(ws),
                   VITTA_E_ALIGN, "bn_act_bwd: tensors must be 16-byte aligned");
   VITTA_CHECK_ARG(!(res && !gres), VITTA_E_BADARG, "bn_act_bwd: residual without gres");
-  VITTA_CHECK_ARG((coef_a == nullptr) == (coef_b == nullptr) && (coef_a == nullptr) == (gs_main == nullptr),
-                  VITTA_E_BADARG, "bn_act_bwd: main coefficients must come as (a, b, gscale)");
-  VITTA_CHECK_ARG((coef_a2 == nullptr) == (coef_b2 == nullptr) && (coef_a2 == nullptr) == (gs_res == nullptr),
-                  VITTA_E_BADARG, "bn_act_bwd: residual coefficients must come as (a, b, gscale)");
+  VITTA_CHECK_ARG((coef_a == nullptr) == (coef_b == nullptr) && (coef_a == nullptr) == (gs_main == nullptr) &&
+                      (coef_a == nullptr) == (mean_main == nullptr),
+                  VITTA_E_BADARG, "bn_act_bwd: main coefficients must come as (a, b, mean, gscale)");
+  VITTA_CHECK_ARG((coef_a2 == nullptr) == (coef_b2 == nullptr) && (coef_a2 == nullptr) == (gs_res == nullptr) &&
+                      (coef_a2 == nullptr) == (mean_res == nullptr),
+                  VITTA_E_BADARG, "bn_act_bwd: residual coefficients must come as (a, b, mean, gscale)");
   ClGeom g = cl_geom(frames, frame_rows, C);
   BwdArgs p;
   p.gout = gout; p.gpool = gpool; p.x = x; p.res = res;
   p.bn = to_dev(bn); p.bn2 = res_bn ? to_dev(*res_bn) : p.bn;
-  p.ca = coef_a; p.cb = coef_b; p.gs = gs_main; p.ca2 = coef_a2; p.cb2 = coef_b2; p.gs2 = gs_res;
+  p.ca = coef_a; p.cb = coef_b; p.cm = mean_main; p.gs = gs_main;
+  p.ca2 = coef_a2; p.cb2 = coef_b2; p.cm2 = mean_res; p.gs2 = gs_res;
   p.gx = gx; p.gres = gres; p.gw = gw; p.gb = gb; p.gw2 = gw2; p.gb2 = gb2; p.ws = ws;
   p.relu = relu; p.C = C; p.lpr = g.lpr; p.rs = g.rs; p.chunk_rows = g.chunk_rows; p.cpf = g.cpf;
   p.frame_rows = g.frame_rows; p.n_chunks = g.n_chunks(); p.inv_frame_rows = 1.f / (float)frame_rows;

@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(kFinThreads) stats_finalize_kernel(
       gv = 0.5f / ev - q / (2.f * ev * ev);
     }
     lsum += l;
-    const float b = d.w_new * gv * 2.f / n;
-    coef_b[ci] = b;
-    coef_a[ci] = d.w_new * gm / n - b * mean;
+    // dLoss/dy = coef_a + coef_b * (y - batch_mean): the centred form avoids the cancellation of a' + b*y
+    coef_b[ci] = d.w_new * gv * 2.f / n;
+    coef_a[ci] = d.w_new * gm / n;
   }
   if (merge_only) {
     if (threadIdx.x == 0) merged_counts[blockIdx.x] = (int32_t)ntot_d;
@@ -209,12 +209,13 @@ __global__ void __launch_bounds__(kFinThreads) stats_finalize_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: gy = gscale * (a[c] + b[c]*y), y = x or yscale[c]*x + yshift[c]
+// K3: gy = gscale * (a[c] + b[c]*(y - mean[c])), y = x or yscale[c]*x + yshift[c]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) inject_cl_kernel(const float* __restrict__ x, const float* __restrict__ ys,
                                                             const float* __restrict__ yt, const float* __restrict__ ca,
-                                                            const float* __restrict__ cb, const float* __restrict__ gscale,
-                                                            float* __restrict__ gy, int64_t n4, int C4) {
+                                                            const float* __restrict__ cb, const float* __restrict__ cm,
+                                                            const float* __restrict__ gscale, float* __restrict__ gy,
+                                                            int64_t n4, int C4) {
   const float g = __ldg(gscale);
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
     const int c = (int)(i % C4) * 4;
@@ -223,24 +224,25 @@ __global__ void __launch_bounds__(kThreads) inject_cl_kernel(const float* __rest
       const float4 s = ldg4(ys + c), t = ldg4(yt + c);
       v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
     }
-    const float4 a = ldg4(ca + c), b = ldg4(cb + c);
+    const float4 a = ldg4(ca + c), b = ldg4(cb + c), m = ldg4(cm + c);
     float4 o;
-    o.x = g * fmaf(b.x, v.x, a.x); o.y = g * fmaf(b.y, v.y, a.y);
-    o.z = g * fmaf(b.z, v.z, a.z); o.w = g * fmaf(b.w, v.w, a.w);
+    o.x = g * fmaf(b.x, v.x - m.x, a.x); o.y = g * fmaf(b.y, v.y - m.y, a.y);
+    o.z = g * fmaf(b.z, v.z - m.z, a.z); o.w = g * fmaf(b.w, v.w - m.w, a.w);
     st4(gy + i * 4, o);
   }
 }
 
 __global__ void __launch_bounds__(kThreads) inject_oci_kernel(const float* __restrict__ x, const float* __restrict__ ys,
                                                              const float* __restrict__ yt, const float* __restrict__ ca,
-                                                             const float* __restrict__ cb, const float* __restrict__ gscale,
-                                                             float* __restrict__ gy, int64_t n, int C, int64_t I) {
+                                                             const float* __restrict__ cb, const float* __restrict__ cm,
+                                                             const float* __restrict__ gscale, float* __restrict__ gy,
+                                                             int64_t n, int C, int64_t I) {
   const float g = __ldg(gscale);
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const int c = (int)((i / I) % C);
     float v = __ldg(x + i);
     if (ys) v = fmaf(v, __ldg(ys + c), __ldg(yt + c));
-    gy[i] = g * fmaf(__ldg(cb + c), v, __ldg(ca + c));
+    gy[i] = g * fmaf(__ldg(cb + c), v - __ldg(cm + c), __ldg(ca + c));
   }
 }
 
@@ -325,9 +327,9 @@ int vitta_stats_finalize(const VittaLayerDesc* descs, int n_layers, const float*
 }
 
 int vitta_stats_inject(const float* x, const float* yscale, const float* yshift, const float* coef_a,
-                       const float* coef_b, const float* gscale, float* gy, int64_t O, int C, int64_t I,
-                       void* stream) {
-  VITTA_CHECK_ARG(x && coef_a && coef_b && gscale && gy, VITTA_E_BADARG, "stats_inject: null pointer");
+                       const float* coef_b, const float* mean, const float* gscale, float* gy, int64_t O, int C,
+                       int64_t I, void* stream) {
+  VITTA_CHECK_ARG(x && coef_a && coef_b && mean && gscale && gy, VITTA_E_BADARG, "stats_inject: null pointer");
   VITTA_CHECK_ARG((yscale == nullptr) == (yshift == nullptr), VITTA_E_BADARG, "stats_inject: scale/shift mismatch");
   const int64_t n = O * C * I;
   const int sms = 148;
@@ -335,13 +337,13 @@ int vitta_stats_inject(const float* x, const float* yscale, const float* yshift,
     int64_t n4 = n / 4;
     int64_t blocks = (n4 + kThreads - 1) / kThreads;
     if (blocks > sms * 16) blocks = sms * 16;
-    inject_cl_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, yscale, yshift, coef_a, coef_b, gscale,
-                                                                             gy, n4, C / 4);
+    inject_cl_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, yscale, yshift, coef_a, coef_b, mean,
+                                                                             gscale, gy, n4, C / 4);
   } else {
     int64_t blocks = (n + kThreads - 1) / kThreads;
     if (blocks > sms * 16) blocks = sms * 16;
     inject_oci_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, yscale, yshift, coef_a, coef_b,
-                                                                              gscale, gy, n, C, I);
+                                                                              mean, gscale, gy, n, C, I);
   }
   VITTA_CHECK_LAUNCH();
   return 0;

@@ -242,8 +242,10 @@ class StatsArena:
         return t[ly.ch_off:ly.ch_off + ly.C]
 
     def coef_ptrs(self, ly):
+        """(coef_a, coef_b, batch_mean) of a layer: dLoss/dy = a + b * (y - mean)."""
         off = ly.ch_off * 4
-        return C.c_void_p(self.coef_a.data_ptr() + off), C.c_void_p(self.coef_b.data_ptr() + off)
+        return (C.c_void_p(self.coef_a.data_ptr() + off), C.c_void_p(self.coef_b.data_ptr() + off),
+                C.c_void_p(self.batch_mean.data_ptr() + off))
 
 
 class _RFeature(torch.autograd.Function):
@@ -285,10 +287,11 @@ class StatsTapFn(torch.autograd.Function):
     def backward(ctx, g):
         saved, yscale, yshift = ctx.saved_tensors
         O, Cc, I = ctx.geom
-        ca, cb = ctx.arena.coef_ptrs(ctx.ly)
+        ca, cb, cm = ctx.arena.coef_ptrs(ctx.ly)
         g = g.contiguous()
         gy = torch.empty_like(saved)
-        call("vitta_stats_inject", ptr(saved), ptr(yscale), ptr(yshift), ca, cb, ptr(g), ptr(gy), O, Cc, I, stream_ptr())
+        call("vitta_stats_inject", ptr(saved), ptr(yscale), ptr(yshift), ca, cb, cm, ptr(g), ptr(gy), O, Cc, I,
+             stream_ptr())
         return gy, None, None, None, None, None, None, None, None, None
 
 
@@ -361,12 +364,12 @@ class BNActFn(torch.autograd.Function):
         gb = torch.zeros(Cc, dtype=torch.float32, device=dev)
         gw2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
         gb2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
-        ca = cb = gs = ca2 = cb2 = gs2 = None
+        ca = cb = cm = gs = ca2 = cb2 = cm2 = gs2 = None
         if ly_main is not None and gtok_main is not None:
-            ca, cb = arena.coef_ptrs(ly_main)
+            ca, cb, cm = arena.coef_ptrs(ly_main)
             gs = ptr(gtok_main.contiguous())
         if ly_res is not None and gtok_res is not None:
-            ca2, cb2 = arena.coef_ptrs(ly_res)
+            ca2, cb2, cm2 = arena.coef_ptrs(ly_res)
             gs2 = ptr(gtok_res.contiguous())
         if gpool is not None:
             gpool = gpool.contiguous()
@@ -374,7 +377,7 @@ class BNActFn(torch.autograd.Function):
         bn = _lib.make_bn(w, b, rm, rv, eps)
         bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
         call("vitta_bn_act_bwd", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
-             C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, gs, ca2, cb2, gs2, ptr(gx), ptr(gres),
+             C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx), ptr(gres),
              ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, stream_ptr())
         return (gx, gw, gb, None, None, None, gres, gw2, gb2, None, None, None, None, None, None, None, None, None)
 
