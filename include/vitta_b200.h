@@ -192,6 +192,29 @@ int vitta_sgd_block_elems(void);
 int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
                    float lr, float momentum, float weight_decay, int first_step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6/K8  fp32-accurate GEMM and implicit-GEMM convolution on the tcgen05 tensor cores (3xTF32 split, fp32
+ *        accumulation in TMEM, TMA-fed, persistent).  See csrc/gemm_tf32.cu.
+ *   replaces: cuDNN / cuBLAS fp32 calls behind nn.Conv2d (torchvision Bottleneck convs inside TemporalBottleneck,
+ *             models/tanet_models/temporal_module.py:85-106) and nn.Linear (qkv / proj / fc1+GELU / fc2 / reduction,
+ *             models/videoswintransformer_models/swin_transformer.py:24-35,130-132,160-167,287,311).
+ *
+ * vitta_split_tf32: weight preparation, once per optimizer step.  src is [R][T][Cc] (R output channels, T filter
+ *   taps, Cc input channels -- i.e. a conv weight in channels_last memory, or a Linear weight with T = 1).
+ *   mode 0: hi/lo in the same order (forward operand).  mode 1: hi/lo[c][T-1-t][r] = split(src[r][t][c]) (the operand
+ *   of the data-gradient pass: transposed, filter rotated by 180 degrees).   hi = rna_tf32(x), lo = x - hi.
+ * vitta_gemm_tf32x3: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) then act (0 none, 1 exact GELU) then (+ residual[M,N]).
+ *   Row-major, leading dimensions in floats; lda, ldb multiples of 4; K tail and ragged M/N handled (TMA zero fill).
+ *   force_bn: 0 = choose the N tile automatically, else 64 / 128 / 256.
+ * vitta_conv2d_tf32x3: Y[F,Ho,Wo,Cout] = conv2d(X[F,H,W,Cin], W[Cout][KH][KW][Cin], stride, pad) (+ bias), NHWC,
+ *   Cin multiple of 4.  Padding comes from the TMA out-of-bounds zero fill; no im2col buffer exists. */
+int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int Cc, int mode, void* stream);
+int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
+                      int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                      int act, int force_bn, void* stream);
+int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
+                        int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

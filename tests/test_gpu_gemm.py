@@ -1,0 +1,97 @@
+"""GPU: the tcgen05 3xTF32 GEMM / implicit-GEMM convolution (K6/K8) against float64 references.
+
+Tolerance: the split keeps ~21 mantissa bits per product, so |err| <= 2e-6 * sum_k |a||b| (the same error class as an
+fp32 FFMA dot product); a plain single-pass TF32 GEMM misses this bound by three orders of magnitude."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _err_ok(got, ref64, absprod64, tol=2e-6):
+    err = (got.double() - ref64).abs()
+    bound = tol * absprod64 + 1e-30
+    worst = float((err / bound).max())
+    assert worst <= 1.0, "max err/bound = %.3f (max |err| %.3e)" % (worst, float(err.max()))
+    return float((err / (absprod64 + 1e-30)).max())
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 32), (128, 128, 64), (256, 256, 128), (200, 96, 100), (1000, 320, 256),
+                                   (6272, 2048, 512), (25088, 64, 256), (392, 384, 128), (37, 5, 36)])
+@pytest.mark.parametrize("force_bn", [0, 64, 128, 256])
+def test_gemm_tf32x3_vs_float64(cuda_device, m, n, k, force_bn):
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(m, k, generator=g).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).to(cuda_device)
+    bh, bl = ops.split_tf32(b)
+    out = ops.gemm_tf32x3(a, bh, bl, n, force_bn=force_bn)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    absprod = a.double().abs() @ b.double().abs().t()
+    rel = _err_ok(out, ref, absprod)
+    # and it is an fp32-grade result, not a TF32 one
+    assert rel < 2e-6
+
+
+def test_gemm_epilogues(cuda_device):
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    m, n, k = 777, 512, 128
+    a = torch.randn(m, k, generator=g).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).to(cuda_device)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    res = torch.randn(m, n, generator=g).to(cuda_device)
+    bh, bl = ops.split_tf32(b)
+    ref = a.double() @ b.double().t() + bias.double()
+    out = ops.gemm_tf32x3(a, bh, bl, n, bias=bias)
+    assert float((out.double() - ref).abs().max()) < 2e-5
+    out = ops.gemm_tf32x3(a, bh, bl, n, bias=bias, act=1)
+    assert float((out.double() - F.gelu(ref)).abs().max()) < 2e-5
+    out = ops.gemm_tf32x3(a, bh, bl, n, bias=bias, residual=res)
+    assert float((out.double() - (ref + res.double())).abs().max()) < 2e-5
+    # strided A (a column slice of a wider matrix) and output into a strided view
+    wide = torch.randn(m, 3 * k, generator=g).to(cuda_device)
+    a2 = wide[:, k:2 * k]
+    big = torch.zeros(m, 2 * n, device=cuda_device)
+    ops.gemm_tf32x3(a2, bh, bl, n, out=big[:, n:])
+    ref2 = a2.double() @ b.double().t()
+    assert float((big[:, n:].double() - ref2).abs().max()) < 2e-5
+    assert float(big[:, :n].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("f,h,w,cin,cout,kh,stride,pad", [
+    (4, 14, 14, 64, 128, 3, 1, 1), (3, 7, 7, 32, 64, 3, 1, 1), (2, 56, 56, 64, 64, 3, 1, 1), (5, 28, 28, 128, 128, 3, 1, 1),
+    (2, 56, 56, 64, 256, 1, 1, 0), (3, 28, 28, 128, 128, 3, 2, 1), (3, 14, 14, 256, 512, 1, 2, 0), (2, 9, 5, 8, 24, 3, 1, 1),
+    (2, 30, 30, 4, 64, 7, 2, 3), (16, 7, 7, 512, 512, 3, 1, 1),
+])
+def test_conv2d_tf32x3_vs_float64(cuda_device, f, h, w, cin, cout, kh, stride, pad):
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(f + h * 3 + cin)
+    x = torch.randn(f, cin, h, w, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, kh, kh, generator=g) / (cin * kh * kh) ** 0.5).to(cuda_device)
+    wh, wl = ops.split_tf32(wt)
+    y = ops.conv2d_tf32x3(x, wh, wl, cout, kh, kh, stride, pad)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.double(), None, stride, pad)
+    absprod = F.conv2d(x.double().abs(), wt.double().abs(), None, stride, pad)
+    assert y.shape == ref.shape
+    _err_ok(y, ref, absprod)
+
+
+@pytest.mark.parametrize("cin,cout,kh", [(64, 128, 3), (128, 64, 1)])
+def test_split_mode1_gives_data_gradient(cuda_device, cin, cout, kh):
+    """dgrad of a stride-1 conv = the same implicit GEMM on grad_out with the mode-1 (transposed, rotated) operand."""
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    f, h, w = 3, 14, 14
+    pad = kh // 2
+    x = torch.randn(f, cin, h, w, generator=g, dtype=torch.float64).to(cuda_device).requires_grad_(True)
+    wt = (torch.randn(cout, cin, kh, kh, generator=g) / (cin * kh * kh) ** 0.5).to(cuda_device)
+    go = torch.randn(f, cout, h, w, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    F.conv2d(x, wt.double(), None, 1, pad).backward(go.double())
+    wh, wl = ops.split_tf32(wt, mode=1)
+    gx = ops.conv2d_tf32x3(go, wh, wl, cin, kh, kh, 1, pad)
+    scale = float(x.grad.abs().max())
+    assert float((gx.double() - x.grad).abs().max()) < 3e-6 * scale * (cout * kh * kh) ** 0.5

@@ -51,6 +51,11 @@ _SIGNATURES = {
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "vitta_split_tf32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_gemm_tf32x3": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
+                                    C.c_int64, C.c_int, C.c_int, _P]),
+    "vitta_conv2d_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, _P, _P, C.c_int, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }

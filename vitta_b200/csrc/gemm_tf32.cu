@@ -1,0 +1,608 @@
+// K6/K8: fp32-accurate GEMM / implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, kind::tf32) with the
+// 3xTF32 operand split:   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   x_hi = rna_tf32(x), x_lo = x - x_hi
+// (error ~2^-21 relative per product, fp32 accumulation in TMEM), i.e. fp32-grade results at tensor-core speed.
+//
+//   D[m, n] = sum_{tap, k} A[row(m) shifted by tap, k] * B[n, tap*Kc + k]   (+ bias[n]) (+ residual) (GELU)
+//
+// * A (activations, channels-last) arrives RAW through TMA (4-D tiled map {C, W, H, F}, 128B swizzle, OOB = 0
+//   gives the convolution padding for free); four "split" warps rewrite each landed stage in place as a_hi and emit
+//   a_lo into a second buffer -- an elementwise pass, so the swizzled layout never has to be decoded.
+// * B (weights) is pre-split in global memory (vitta_split_tf32, once per optimizer step) and arrives as two TMA tiles.
+// * One elected thread issues 3 x (BK/8) tcgen05.mma per stage into a double-buffered TMEM accumulator; four
+//   epilogue warps drain the other buffer (tcgen05.ld 32x32b) with the fused bias / GELU / residual epilogue.
+// * Persistent: grid = min(#tiles, #SMs); tiles are walked n-fastest so CTAs running together share an A panel in L2.
+//
+// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = operand split, 6-9 = epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vitta {
+
+constexpr int kBM = 128;         // UMMA M (one TMEM lane per accumulator row)
+constexpr int kBK = 32;          // fp32 elements per stage row = 128 B = one swizzle atom row
+constexpr int kGemmThreads = 320;
+constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
+constexpr uint32_t kSpinLimit = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
+
+struct GemmParams {
+  float* C;
+  const float* bias;       // [N] or null
+  const float* residual;   // same indexing as C (row stride ldr) or null
+  int64_t ldc, ldr;
+  int M_total;             // rows of C (plain GEMM) -- unused for conv (validity from the box geometry)
+  int N;
+  int k_chunks;            // ceil(Kc / 32) per tap
+  int Kc;                  // channels (K extent per tap)
+  int taps_h, taps_w;      // filter extent (1,1 for a plain GEMM)
+  int stride, pad;
+  int Ho, Wo, F;           // output geometry: rows of C = (f, ho, wo); plain GEMM: F = 1, Ho = 1, Wo = M
+  int BW, BH, BF;          // output pixels covered by one M tile: BF frames x BH rows x BW cols  (BW*BH*BF <= 128)
+  int tiles_w, tiles_h, tiles_f, tiles_n;
+  int act;                 // 0 none, 1 exact GELU
+  int vec_ok;              // C / bias / residual allow 128-bit accesses
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address   bits [0,14)
+  d |= (uint64_t)1 << 16;                         // LBO (ignored for swizzled K-major) bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;               // SBO             bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------------------------
+// shared memory plan
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN <= 128) ? 3 : 2;
+  static constexpr int kABytes = kBM * kBK * 4;   // 16 KB
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // + alignment slack
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bars_mem = smem + kStages * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bars_mem);        // TMA landed          [kStages]
+  uint64_t* split_bar = full_bar + kStages;                          // a_hi / a_lo written [kStages]
+  uint64_t* empty_bar = split_bar + kStages;                         // MMAs retired        [kStages]
+  uint64_t* acc_full = empty_bar + kStages;                          // accumulator ready   [2]
+  uint64_t* acc_empty = acc_full + 2;                                // accumulator drained [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_f;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int taps = p.taps_h * p.taps_w;
+  const int k_iters = taps * p.k_chunks;
+  const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BF) * kBK * 4;
+  const uint32_t stage_tx = a_box_bytes + 2u * S::kBBytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 4);    // one elected arrive per split warp
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);    // one elected arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBhi);
+    tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(S::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+        const int hb = mt % p.tiles_h;
+        const int fb = mt / p.tiles_h;
+        const int w_in0 = wb * p.BW * p.stride - p.pad;
+        const int h_in0 = hb * p.BH * p.stride - p.pad;
+        const int f0 = fb * p.BF;
+        const int n0 = nt * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.k_chunks;
+          const int kc = (it - tap * p.k_chunks) * kBK;
+          const int th = tap / p.taps_w, tw = tap - th * p.taps_w;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_4d(&tmA, &full_bar[stage], st, kc, w_in0 + tw, h_in0 + th, f0);
+          tma_load_2d(&tmBhi, &full_bar[stage], st + 2 * S::kABytes, tap * p.Kc + kc, n0);
+          tma_load_2d(&tmBlo, &full_bar[stage], st + 2 * S::kABytes + S::kBBytes, tap * p.Kc + kc, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);    // B tiles (and raw A) landed
+        mbar_wait(&split_bar[stage], phase);   // a_hi / a_lo written
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t a_hi = umma_desc_sw128(st);
+          const uint64_t a_lo = umma_desc_sw128(st + S::kABytes);
+          const uint64_t b_hi = umma_desc_sw128(st + 2 * S::kABytes);
+          const uint64_t b_lo = umma_desc_sw128(st + 2 * S::kABytes + S::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);   // 8 tf32 = 32 B = 2 x 16 B inside the swizzle atom row
+            // small terms first, the dominant hi*hi product last
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem stage reusable once these MMAs retire
+          if (it == k_iters - 1) umma_commit(&acc_full[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp < kEpiWarp0) {
+    // ===================== operand split: raw A -> a_hi (in place) + a_lo =====================
+    const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* a = reinterpret_cast<float4*>(smem + stage * S::kStageBytes);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * S::kStageBytes + S::kABytes);
+#pragma unroll
+        for (int j = 0; j < (kBM * kBK / 4) / 128; ++j) {
+          const int i = j * 128 + t;
+          const float4 v = a[i];
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          a[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;                // accumulator row == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int wb = mt % p.tiles_w; mt /= p.tiles_w;
+      const int hb = mt % p.tiles_h;
+      const int fb = mt / p.tiles_h;
+      // row -> (frame, ho, wo) inside the box
+      const int bw = row % p.BW;
+      const int bh = (row / p.BW) % p.BH;
+      const int bf = row / (p.BW * p.BH);
+      const int wo = wb * p.BW + bw, ho = hb * p.BH + bh, f = fb * p.BF + bf;
+      const bool row_ok = (bf < p.BF) && (wo < p.Wo) && (ho < p.Ho) && (f < p.F);
+      const int64_t out_row = ((int64_t)f * p.Ho + ho) * p.Wo + wo;
+      float* crow = p.C + out_row * p.ldc;
+      const float* rrow = p.residual ? p.residual + out_row * p.ldr : nullptr;
+      const int n0 = nt * BN;
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int nbase = n0 + c0;
+          if (nbase + 32 <= p.N && p.vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                const float4 b = ldg4(p.bias + nbase + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
+              if (rrow) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              st4(crow + nbase + j, v);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nbase + j;
+              if (n < p.N) {
+                float v = __uint_as_float(r[j]);
+                if (p.bias) v += __ldg(p.bias + n);
+                if (p.act == 1) v = gelu_exact(v);
+                if (rrow) v += rrow[n];
+                crow[n] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::kTmemCols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: hi/lo split, optional transposition / filter rotation (for the data-gradient pass)
+// ------------------------------------------------------------------------------------------------
+// src: [R][T][Cc] (R = out channels, T = taps, Cc = in channels).  mode 0: dst[r][t][c] = src[r][t][c];
+// mode 1 (dgrad operand): dst[c][T-1-t][r] = src[r][t][c].
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                                                        float* __restrict__ lo, int R, int T, int Cc, int mode) {
+  const int64_t n = (int64_t)R * T * Cc;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t s = i;
+    if (mode == 1) {   // i indexes dst [c][t'][r]
+      const int r = (int)(i % R);
+      const int64_t q = i / R;
+      const int tp = (int)(q % T);
+      const int c = (int)(q / T);
+      s = ((int64_t)r * T + (T - 1 - tp)) * Cc + c;
+    }
+    const float v = __ldg(src + s);
+    const float h = tf32_rna(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* estr) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return VITTA_E_UNSUPPORTED;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                   reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu %llu box %u %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return VITTA_E_BADARG;
+  }
+  return 0;
+}
+
+static int g_sms = 0;
+static int sm_count() {
+  if (g_sms <= 0) g_sms = vitta_sm_count();
+  return g_sms > 0 ? g_sms : 148;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, GemmParams p,
+                       cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * p.tiles_f * p.tiles_n;
+  if (tiles <= 0 || tiles >= (1ll << 31)) {
+    set_error("gemm_tf32x3: bad tile count");
+    return VITTA_E_BADARG;
+  }
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tf32x3_kernel<BN><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("gemm_tf32x3 launch: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+static int pick_bn(int N, int forced) {
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  if (N <= 64) return 64;
+  if (N <= 128 || N % 256 != 0) return 128;
+  return 256;
+}
+
+static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, const GemmParams& p, int bn,
+                    cudaStream_t st) {
+  if (bn == 64) return launch_gemm<64>(a, bh, bl, p, st);
+  if (bn == 128) return launch_gemm<128>(a, bh, bl, p, st);
+  return launch_gemm<256>(a, bh, bl, p, st);
+}
+
+static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const float* Bhi, const float* Blo, int64_t ldb, int N,
+                       int Ktot, int bn) {
+  const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
+  const uint64_t str[1] = {(uint64_t)ldb * 4};
+  const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
+  const uint32_t es[2] = {1, 1};
+  int rc = make_map(bh, Bhi, 2, dims, str, box, es);
+  if (rc) return rc;
+  return make_map(bl, Blo, 2, dims, str, box, es);
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+extern "C" {
+
+int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int Cc, int mode, void* stream) {
+  VITTA_CHECK_ARG(src && hi && lo && R > 0 && T > 0 && Cc > 0 && (mode == 0 || mode == 1), VITTA_E_BADARG,
+                  "split_tf32: bad arguments");
+  const int64_t n = (int64_t)R * T * Cc;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, R, T, Cc, mode);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
+                      int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                      int act, int force_bn, void* stream) {
+  VITTA_CHECK_ARG(A && Bhi && Blo && C && M > 0 && N > 0 && K > 0, VITTA_E_BADARG, "gemm_tf32x3: bad arguments");
+  VITTA_CHECK_ARG(M < (1ll << 31), VITTA_E_UNSUPPORTED, "gemm_tf32x3: M too large");
+  VITTA_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(Bhi) && aligned16(Blo), VITTA_E_ALIGN,
+                  "gemm_tf32x3: operands need 16-byte aligned rows (lda, ldb multiples of 4 floats)");
+  VITTA_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, VITTA_E_BADARG, "gemm_tf32x3: leading dimension too small");
+  const int bn = pick_bn(N, force_bn);
+  CUtensorMap ta, tbh, tbl;
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+    const uint64_t str[3] = {(uint64_t)lda * 4, (uint64_t)lda * 4 * (uint64_t)M, (uint64_t)lda * 4 * (uint64_t)M};
+    const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)kBM, 1, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = make_map(&ta, A, 4, dims, str, box, es);
+    if (rc) return rc;
+  }
+  int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn);
+  if (rc) return rc;
+  GemmParams p{};
+  p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
+  p.M_total = (int)M; p.N = N; p.Kc = K; p.k_chunks = (K + kBK - 1) / kBK;
+  p.taps_h = p.taps_w = 1; p.stride = 1; p.pad = 0;
+  p.Ho = 1; p.Wo = (int)M; p.F = 1;
+  p.BW = kBM; p.BH = 1; p.BF = 1;
+  p.tiles_w = (int)((M + kBM - 1) / kBM); p.tiles_h = 1; p.tiles_f = 1;
+  p.act = act;
+  p.vec_ok = aligned16(C) && (ldc % 4 == 0) && (!bias || aligned16(bias)) &&
+             (!residual || (aligned16(residual) && ldr % 4 == 0));
+  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
+}
+
+int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
+                        int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream) {
+  VITTA_CHECK_ARG(X && Whi && Wlo && Y && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
+                  "conv2d_tf32x3: bad arguments");
+  VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_tf32x3: bad filter");
+  VITTA_CHECK_ARG(Cin % 4 == 0 && aligned16(X) && aligned16(Whi) && aligned16(Wlo), VITTA_E_ALIGN,
+                  "conv2d_tf32x3: Cin must be a multiple of 4 and tensors 16-byte aligned");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  VITTA_CHECK_ARG(Ho > 0 && Wo > 0, VITTA_E_BADARG, "conv2d_tf32x3: empty output");
+  // M tile = BF frames x BH rows x BW cols of output pixels, at most 128
+  const int BW = Wo < kBM ? Wo : kBM;
+  int BH = 1, BF = 1;
+  if (BW == Wo) {
+    int bh_max = kBM / BW;
+    if (bh_max > Ho) bh_max = Ho;
+    BH = bh_max;
+    for (int d = bh_max; d >= 1; --d) {   // largest divisor of Ho that fits; keep it unless it halves the tile
+      if (Ho % d == 0) {
+        if (2 * d > bh_max) BH = d;
+        break;
+      }
+    }
+    if (BH == Ho) {
+      BF = kBM / (BW * BH);
+      if (BF > F) BF = F;
+      if (BF < 1) BF = 1;
+    }
+  }
+  VITTA_CHECK_ARG((int64_t)BW * stride <= 256 && (int64_t)BH * stride <= 256, VITTA_E_UNSUPPORTED,
+                  "conv2d_tf32x3: box exceeds the TMA limit");
+  const int bn = pick_bn(Cout, force_bn);
+  CUtensorMap ta, tbh, tbl;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)F};
+    const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * 4 * W, (uint64_t)Cin * 4 * W * H};
+    const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(BW * stride), (uint32_t)(BH * stride), (uint32_t)BF};
+    const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = make_map(&ta, X, 4, dims, str, box, es);
+    if (rc) return rc;
+  }
+  const int Ktot = KH * KW * Cin;
+  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn);
+  if (rc) return rc;
+  GemmParams p{};
+  p.C = Y; p.bias = bias; p.residual = nullptr; p.ldc = Cout; p.ldr = 0;
+  p.M_total = 0; p.N = Cout; p.Kc = Cin; p.k_chunks = (Cin + kBK - 1) / kBK;
+  p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
+  p.Ho = Ho; p.Wo = Wo; p.F = F;
+  p.BW = BW; p.BH = BH; p.BF = BF;
+  p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
+  p.act = 0;
+  p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias));
+  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
+}
+
+}  // extern "C"

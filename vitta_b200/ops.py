@@ -536,3 +536,52 @@ class FusedSGD:
                 continue
             t, starts, n, blocks = tab
             call("vitta_sgd_step", ptr(t), ptr(starts), n, blocks, lr, self.momentum, self.weight_decay, is_first, 1.0, st)
+
+
+# ----------------------------------------------------------------------------------------------
+# K6/K8: tcgen05 3xTF32 GEMM / implicit-GEMM convolution
+# ----------------------------------------------------------------------------------------------
+def split_tf32(w, mode=0):
+    """Weight preparation (vitta_split_tf32).  ``w``: Linear weight (N, K) or conv weight (Cout, Cin, KH, KW) in
+    channels_last memory.  mode 0 -> forward operand [Cout][tap][Cin]; mode 1 -> data-gradient operand
+    [Cin][rotated tap][Cout].  Returns (hi, lo) flat fp32 tensors."""
+    _require_cuda(w, "split_tf32")
+    if w.dim() == 2:
+        r, t, c = w.shape[0], 1, w.shape[1]
+        src = w.contiguous()
+    else:
+        r, c, kh, kw = w.shape
+        t = kh * kw
+        src = w.contiguous(memory_format=CL) if t > 1 else w.reshape(r, c).contiguous()
+    hi = torch.empty(r * t * c, dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    call("vitta_split_tf32", ptr(src), ptr(hi), ptr(lo), r, t, c, int(mode), stream_ptr())
+    return hi, lo
+
+
+def gemm_tf32x3(a, b_hi, b_lo, n, bias=None, residual=None, act=0, out=None, force_bn=0):
+    """out[M, n] = a[M, K] @ B[n, K]^T (+bias) (GELU if act=1) (+residual); B given pre-split (split_tf32)."""
+    _require_cuda(a, "gemm_tf32x3")
+    if a.dim() != 2 or a.stride(1) != 1:
+        raise _lib.VittaError("gemm_tf32x3: A must be (M, K) with unit inner stride")
+    m, k = a.shape
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    call("vitta_gemm_tf32x3", ptr(a), a.stride(0), ptr(b_hi), ptr(b_lo), k, ptr(out), out.stride(0), m, n, k,
+         ptr(bias), ptr(residual), ldr, int(act), int(force_bn), stream_ptr())
+    return out
+
+
+def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=0):
+    """x: logical (F, Cin, H, W) in channels_last memory -> logical (F, cout, Ho, Wo) channels_last."""
+    _require_cuda(x, "conv2d_tf32x3")
+    if not x.is_contiguous(memory_format=CL):
+        raise _lib.VittaError("conv2d_tf32x3: x must be channels_last contiguous")
+    f, cin, h, w = x.shape
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    y = torch.empty((f, cout, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
+    call("vitta_conv2d_tf32x3", ptr(x), f, h, w, cin, ptr(w_hi), ptr(w_lo), cout, kh, kw, stride, pad, ptr(y), ptr(bias),
+         int(force_bn), stream_ptr())
+    return y
