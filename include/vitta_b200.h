@@ -215,6 +215,15 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
                         int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream);
 
+/* Weight gradient of the same convolution: dW[Cout][Cin][KH][KW] (contiguous NCHW, the layout of nn.Conv2d.weight)
+ *   (+)= sum over output pixels of dY[F,Ho,Wo,Cout] (x) X[F,H,W,Cin] shifted by the filter tap.
+ * Split-K over pixel ranges on the tcgen05 tensor cores (both operands MN-major, split hi/lo in-kernel); the K splits
+ * are summed in a fixed order (deterministic).  ws: vitta_conv2d_wgrad_ws_floats() floats of scratch (no init needed).
+ *   replaces: autograd's convolution_backward weight branch (cuDNN wgrad) for the layers above. */
+int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
+                              int stride, int pad, float* dW, int accumulate, float* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

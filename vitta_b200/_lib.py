@@ -56,6 +56,8 @@ _SIGNATURES = {
                                     C.c_int64, C.c_int, C.c_int, _P]),
     "vitta_conv2d_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _P, _P, C.c_int, _P]),
+    "vitta_conv2d_wgrad_ws_floats": (C.c_int64, [C.c_int] * 9),
+    "vitta_conv2d_wgrad_tf32x3": (C.c_int, [_P, _P] + [C.c_int] * 9 + [_P, C.c_int, _P, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }

@@ -13,9 +13,7 @@
 // * Persistent: grid = min(#tiles, #SMs); tiles are walked n-fastest so CTAs running together share an A panel in L2.
 //
 // Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = operand split, 6-9 = epilogue.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc05.cuh"
 
 namespace vitta {
 
@@ -23,7 +21,6 @@ constexpr int kBM = 128;         // UMMA M (one TMEM lane per accumulator row)
 constexpr int kBK = 32;          // fp32 elements per stage row = 128 B = one swizzle atom row
 constexpr int kGemmThreads = 320;
 constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
-constexpr uint32_t kSpinLimit = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 struct GemmParams {
   float* C;
@@ -42,104 +39,6 @@ struct GemmParams {
   int act;                 // 0 none, 1 exact GELU
   int vec_ok;              // C / bias / residual allow 128-bit accesses
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address   bits [0,14)
-  d |= (uint64_t)1 << 16;                         // LBO (ignored for swizzled K-major) bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;               // SBO             bits [32,46)
-  d |= (uint64_t)1 << 46;                         // descriptor version
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------------------------
 // shared memory plan
@@ -420,8 +319,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* estr) {
+int make_tensor_map_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, const uint32_t* estr, bool swizzle_atom_32b) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -430,7 +329,9 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                    reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu %llu box %u %u", (int)r, rank,
@@ -441,7 +342,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 }
 
 static int g_sms = 0;
-static int sm_count() {
+int cached_sm_count() {
   if (g_sms <= 0) g_sms = vitta_sm_count();
   return g_sms > 0 ? g_sms : 148;
 }
@@ -465,7 +366,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
     set_error("gemm_tf32x3: bad tile count");
     return VITTA_E_BADARG;
   }
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const int grid = (int)(tiles < cached_sm_count() ? tiles : cached_sm_count());
   gemm_tf32x3_kernel<BN><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -495,9 +396,9 @@ static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const float* Bhi, const
   const uint64_t str[1] = {(uint64_t)ldb * 4};
   const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
   const uint32_t es[2] = {1, 1};
-  int rc = make_map(bh, Bhi, 2, dims, str, box, es);
+  int rc = make_tensor_map_f32(bh, Bhi, 2, dims, str, box, es);
   if (rc) return rc;
-  return make_map(bl, Blo, 2, dims, str, box, es);
+  return make_tensor_map_f32(bl, Blo, 2, dims, str, box, es);
 }
 
 }  // namespace vitta
@@ -532,7 +433,7 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
     const uint64_t str[3] = {(uint64_t)lda * 4, (uint64_t)lda * 4 * (uint64_t)M, (uint64_t)lda * 4 * (uint64_t)M};
     const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)kBM, 1, 1};
     const uint32_t es[4] = {1, 1, 1, 1};
-    int rc = make_map(&ta, A, 4, dims, str, box, es);
+    int rc = make_tensor_map_f32(&ta, A, 4, dims, str, box, es);
     if (rc) return rc;
   }
   int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn);
@@ -587,7 +488,7 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
     const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * 4 * W, (uint64_t)Cin * 4 * W * H};
     const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(BW * stride), (uint32_t)(BH * stride), (uint32_t)BF};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-    int rc = make_map(&ta, X, 4, dims, str, box, es);
+    int rc = make_tensor_map_f32(&ta, X, 4, dims, str, box, es);
     if (rc) return rc;
   }
   const int Ktot = KH * KW * Cin;

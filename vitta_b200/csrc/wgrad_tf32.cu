@@ -1,0 +1,399 @@
+// K6 (weight gradient): dW[co][tap][ci] = sum over output pixels p of dY[p, co] * X[p shifted by tap, ci]
+// as a split-K GEMM on the tcgen05 tensor cores with the 3xTF32 split (see gemm_tf32.cu for the numerics).
+//
+// The reduction dimension is the pixel index, so BOTH operands are "MN-major" in UMMA terms: a smem row is one pixel
+// (K index) holding 32 consecutive channels (128 B), exactly what a TMA box {32 channels, BW, BH, BF pixels} of the
+// channels-last activation delivers (swizzle mode 128B_ATOM_32B, the one layout tf32 MN-major operands accept).  A stage = 32 pixels; the A tile (128 output channels) is 4 such boxes, the B
+// tile (BN input channels) BN/32 boxes, the filter tap only shifts the X box (OOB zero fill = padding).  Both
+// operands are activations, so both are split in-kernel (hi in place, lo beside it) by four warps.
+// Work item = (Cout tile, tap, Cin tile, K split); every item writes its fp32 partial [128 x BN] to a workspace and
+// wgrad_reduce_kernel sums the K splits in a fixed order (deterministic) straight into the NCHW weight gradient.
+#include "tc05.cuh"
+
+namespace vitta {
+
+constexpr int kWgThreads = 320;
+constexpr int kWgRows = 32;                       // pixels per stage
+constexpr int kWgBoxBytes = kWgRows * 128;        // one {32 ch x 32 px} box = 4 KB
+constexpr int kWgBM = 128;
+
+struct WgradParams {
+  float* ws;               // [splits][Cout][taps*Cin]
+  int Cout, Cin;
+  int taps_h, taps_w, stride, pad;
+  int BW, BH, BF;          // pixel box (product = 32)
+  int boxes_w, boxes_h, boxes_f;
+  int m_tiles, n_ctiles;   // Cout tiles, Cin tiles (per tap)
+  int splits;
+};
+
+template <int BN>
+struct WgSmem {
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = 4 * kWgBoxBytes;            // 16 KB raw/hi, + same for lo
+  static constexpr int kBBytes = (BN / 32) * kWgBoxBytes;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                    const WgradParams p) {
+  using S = WgSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bars_mem = smem + kStages * S::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bars_mem);
+  uint64_t* split_bar = full_bar + kStages;
+  uint64_t* empty_bar = split_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.taps_h * p.taps_w;
+  const int n_tiles = taps * p.n_ctiles;
+  const int total_items = p.m_tiles * n_tiles * p.splits;
+  const int total_boxes = p.boxes_w * p.boxes_h * p.boxes_f;
+  constexpr uint32_t stage_tx = (uint32_t)(S::kABytes + S::kBBytes);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(S::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (m tile, split, tap, cin tile), (tap, cin tile) fastest: CTAs running together work on the SAME pixel
+  // range for different taps / channel tiles, so dY and the (overlapping) shifted X boxes are shared through L2 and
+  // every pixel range streams from HBM once.
+  auto decode = [&](int item, int& mt, int& tap, int& ct, int& sp, int& b0, int& b1) {
+    const int nt = item % n_tiles;
+    const int r = item / n_tiles;
+    sp = r % p.splits;
+    mt = r / p.splits;
+    tap = nt / p.n_ctiles;
+    ct = nt - tap * p.n_ctiles;
+    b0 = (int)(((int64_t)total_boxes * sp) / p.splits);
+    b1 = (int)(((int64_t)total_boxes * (sp + 1)) / p.splits);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int mt, tap, ct, sp, b0, b1;
+        decode(item, mt, tap, ct, sp, b0, b1);
+        const int th = tap / p.taps_w, tw = tap - th * p.taps_w;
+        for (int b = b0; b < b1; ++b) {
+          const int wb = b % p.boxes_w;
+          const int r = b / p.boxes_w;
+          const int hb = r % p.boxes_h;
+          const int fb = r / p.boxes_h;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            tma_load_4d(&tmDY, &full_bar[stage], st + g * kWgBoxBytes, mt * kWgBM + g * 32, wb * p.BW, hb * p.BH,
+                        fb * p.BF);
+          uint8_t* sb = st + 2 * S::kABytes;
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g)
+            tma_load_4d(&tmX, &full_bar[stage], sb + g * kWgBoxBytes, ct * BN + g * 32,
+                        wb * p.BW * p.stride - p.pad + tw, hb * p.BH * p.stride - p.pad + th, fb * p.BF);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_tf32_mn(kWgBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mt, tap, ct, sp, b0, b1;
+      decode(item, mt, tap, ct, sp, b0, b1);
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int b = b0; b < b1; ++b) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t a_hi = umma_desc_mn_sw128(st, kWgBoxBytes);
+          const uint64_t a_lo = umma_desc_mn_sw128(st + S::kABytes, kWgBoxBytes);
+          const uint64_t b_hi = umma_desc_mn_sw128(st + 2 * S::kABytes, kWgBoxBytes);
+          const uint64_t b_lo = umma_desc_mn_sw128(st + 2 * S::kABytes + S::kBBytes, kWgBoxBytes);
+#pragma unroll
+          for (int k = 0; k < kWgRows / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * (1024 >> 4));   // 8 pixels = 8 rows of 128 B (two 4-row swizzle atoms)
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (b != b0 || k != 0));
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (b == b1 - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (b1 > b0) {
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    const int t = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mt, tap, ct, sp, b0, b1;
+      decode(item, mt, tap, ct, sp, b0, b1);
+      for (int b = b0; b < b1; ++b) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* st = smem + stage * S::kStageBytes;
+        {
+          float4* a = reinterpret_cast<float4*>(st);
+          float4* lo = reinterpret_cast<float4*>(st + S::kABytes);
+#pragma unroll
+          for (int j = 0; j < (S::kABytes / 16) / 128; ++j) {
+            const int i = j * 128 + t;
+            const float4 v = a[i];
+            float4 h, l;
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            a[i] = h;
+            lo[i] = l;
+          }
+        }
+        {
+          float4* a = reinterpret_cast<float4*>(st + 2 * S::kABytes);
+          float4* lo = reinterpret_cast<float4*>(st + 2 * S::kABytes + S::kBBytes);
+#pragma unroll
+          for (int j = 0; j < (S::kBBytes / 16) / 128; ++j) {
+            const int i = j * 128 + t;
+            const float4 v = a[i];
+            float4 h, l;
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            a[i] = h;
+            lo[i] = l;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int64_t ktot = (int64_t)taps * p.Cin;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mt, tap, ct, sp, b0, b1;
+      decode(item, mt, tap, ct, sp, b0, b1);
+      const int co = mt * kWgBM + row;
+      float* dst = p.ws + ((int64_t)sp * p.Cout + co) * ktot + (int64_t)tap * p.Cin + ct * BN;
+      if (b1 <= b0) {   // empty K range (more splits than boxes): the partial is zero
+        if (co < p.Cout)
+          for (int j = 0; j < BN; ++j)
+            if (ct * BN + j < p.Cin) dst[j] = 0.f;
+        continue;
+      }
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          if (ct * BN + c0 + 32 <= p.Cin && (p.Cin & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              st4(dst + c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                            __uint_as_float(r[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ct * BN + c0 + j < p.Cin) dst[c0 + j] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::kTmemCols));
+  }
+}
+
+// dW (NCHW: [co][ci][tap]) (+)= sum_s ws[s][co][tap][ci], splits summed in order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout,
+                                                          int Cin, int taps, int splits, int accumulate) {
+  const int64_t n = (int64_t)Cout * taps * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += __ldg(ws + (int64_t)k * n + i);
+    const int ci = (int)(i % Cin);
+    const int64_t r = i / Cin;
+    const int tap = (int)(r % taps);
+    const int64_t co = r / taps;
+    float* d = dw + (co * Cin + ci) * taps + tap;
+    *d = accumulate ? *d + s : s;
+  }
+}
+
+static void wgrad_box(int Wo, int Ho, int& BW, int& BH, int& BF) {
+  BW = 1;
+  for (int c = 8; c >= 1; c >>= 1)
+    if (Wo % c == 0) { BW = c; break; }
+  BH = 1;
+  for (int c = kWgRows / BW; c >= 1; c >>= 1)
+    if (Ho % c == 0) { BH = c; break; }
+  BF = kWgRows / (BW * BH);
+}
+
+struct WgPlan {
+  WgradParams p;
+  int bn;
+};
+
+static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, WgPlan* out) {
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return VITTA_E_BADARG;
+  WgradParams& p = out->p;
+  p = WgradParams{};
+  p.Cout = Cout; p.Cin = Cin; p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
+  wgrad_box(Wo, Ho, p.BW, p.BH, p.BF);
+  p.boxes_w = (Wo + p.BW - 1) / p.BW; p.boxes_h = (Ho + p.BH - 1) / p.BH; p.boxes_f = (F + p.BF - 1) / p.BF;
+  out->bn = (Cin <= 64) ? 64 : 128;
+  p.m_tiles = (Cout + kWgBM - 1) / kWgBM;
+  p.n_ctiles = (Cin + out->bn - 1) / out->bn;
+  const int64_t base_items = (int64_t)p.m_tiles * KH * KW * p.n_ctiles;
+  const int64_t boxes = (int64_t)p.boxes_w * p.boxes_h * p.boxes_f;
+  int64_t splits = (2 * (int64_t)cached_sm_count() + base_items - 1) / base_items;
+  const int64_t max_by_k = boxes / 8 > 0 ? boxes / 8 : 1;   // at least 8 stages of work per item
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits < 1) splits = 1;
+  if (splits > 1024) splits = 1024;
+  p.splits = (int)splits;
+  return 0;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t st) {
+  using S = WgSmem<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  const int64_t items = (int64_t)p.m_tiles * p.taps_h * p.taps_w * p.n_ctiles * p.splits;
+  const int grid = (int)(items < cached_sm_count() ? items : cached_sm_count());
+  wgrad_tf32x3_kernel<BN><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("wgrad_tf32x3 launch: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+extern "C" {
+
+int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  WgPlan pl;
+  if (F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride < 1) return -1;
+  if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl)) return -1;
+  return (int64_t)pl.p.splits * Cout * KH * KW * Cin;
+}
+
+int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
+                              int stride, int pad, float* dW, int accumulate, float* ws, void* stream) {
+  VITTA_CHECK_ARG(X && dY && dW && ws && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
+                  "conv2d_wgrad: bad arguments");
+  VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_wgrad: bad filter");
+  VITTA_CHECK_ARG(Cin % 4 == 0 && Cout % 4 == 0 && aligned16(X) && aligned16(dY) && aligned16(ws), VITTA_E_ALIGN,
+                  "conv2d_wgrad: channel counts must be multiples of 4 and tensors 16-byte aligned");
+  WgPlan pl;
+  int rc = wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl);
+  VITTA_CHECK_ARG(rc == 0, VITTA_E_BADARG, "conv2d_wgrad: empty output");
+  WgradParams& p = pl.p;
+  p.ws = ws;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  VITTA_CHECK_ARG(p.BW * stride <= 256 && p.BH * stride <= 256, VITTA_E_UNSUPPORTED, "conv2d_wgrad: box too large");
+  CUtensorMap tdy, tx;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)F};
+    const uint64_t str[3] = {(uint64_t)Cout * 4, (uint64_t)Cout * 4 * Wo, (uint64_t)Cout * 4 * Wo * Ho};
+    const uint32_t box[4] = {32, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BF};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    rc = make_tensor_map_f32(&tdy, dY, 4, dims, str, box, es, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)F};
+    const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * 4 * W, (uint64_t)Cin * 4 * W * H};
+    const uint32_t box[4] = {32, (uint32_t)(p.BW * stride), (uint32_t)(p.BH * stride), (uint32_t)p.BF};
+    const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    rc = make_tensor_map_f32(&tx, X, 4, dims, str, box, es, true);
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = (pl.bn == 64) ? launch_wgrad<64>(tdy, tx, p, st) : launch_wgrad<128>(tdy, tx, p, st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)Cout * KH * KW * Cin;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -8,7 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.init import constant_, normal_
 
-from ...nn import StatsBatchNorm2d, norm_act
+from ...nn import StatsBatchNorm2d, conv2d, norm_act
 from .basic_ops import ConsensusModule
 from .temporal_module import Bottleneck, TemporalBottleneck, make_temporal_modeling
 
@@ -47,7 +47,7 @@ class ResNet50Trunk(nn.Module):
     def forward(self, x):
         t = self.n_segment
         x = x.contiguous(memory_format=torch.channels_last)
-        x = self.conv1(x)
+        x = conv2d(self.conv1, x)
         x, _ = norm_act(self.bn1, x, True, t)
         x = self.maxpool(x)
         pooled = None

@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import ops
-from ...nn import StatsBatchNorm2d, norm_act
+from ...nn import StatsBatchNorm2d, conv2d, norm_act
 
 
 class TAM(nn.Module):
@@ -83,14 +83,14 @@ class TemporalBottleneck(nn.Module):
 
     def forward(self, x, want_pool=False):
         net, t = self.net, self.n_segment
-        out = net.conv1(x)
+        out = conv2d(net.conv1, x)
         out, pooled = norm_act(net.bn1, out, True, t, want_pool=True)       # BN + stats + ReLU + HW-pool: 1 pass
         out = self.tam(out, pooled)
-        out = net.conv2(out)
+        out = conv2d(net.conv2, out)
         out, _ = norm_act(net.bn2, out, True, t)
-        out = net.conv3(out)
+        out = conv2d(net.conv3, out)
         if net.downsample is not None:
-            idt = net.downsample[0](x)
+            idt = conv2d(net.downsample[0], x)
             return norm_act(net.bn3, out, True, t, res=idt, res_bn=net.downsample[1], want_pool=want_pool)
         return norm_act(net.bn3, out, True, t, res=x, want_pool=want_pool)
 

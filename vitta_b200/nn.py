@@ -50,3 +50,18 @@ def norm_act(bn, x, relu, clip_len, res=None, res_bn=None, want_pool=False):
         y = F.relu(y)
     pool = F.adaptive_avg_pool2d(y, 1).flatten(1) if want_pool else None
     return y, pool
+
+
+def conv2d(conv, x):
+    """nn.Conv2d call path of the vitta_b200 models: bias-free, ungrouped, undilated convolutions whose input has a
+    multiple of 4 channels run on the tcgen05 3xTF32 implicit-GEMM kernel (K6); the 3-channel stem convolution is
+    the one layer left to the library (its rows are not 16-byte aligned for TMA)."""
+    if not x.is_cuda:
+        raise ops._lib.VittaError("vitta_b200 models need CUDA tensors; there is no CPU path")
+    kh, kw = conv.kernel_size
+    if (conv.bias is None and conv.groups == 1 and conv.dilation == (1, 1) and conv.in_channels % 4 == 0
+            and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and kh == kw
+            and conv.padding_mode == 'zeros' and not conv._forward_hooks and not conv._forward_pre_hooks):
+        x = x.contiguous(memory_format=torch.channels_last)
+        return ops.conv2d(x, conv.weight, conv.stride[0], conv.padding[0])
+    return conv(x)

@@ -536,6 +536,7 @@ class FusedSGD:
                 continue
             t, starts, n, blocks = tab
             call("vitta_sgd_step", ptr(t), ptr(starts), n, blocks, lr, self.momentum, self.weight_decay, is_first, 1.0, st)
+        bump_weight_epoch()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -585,3 +586,91 @@ def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=
     call("vitta_conv2d_tf32x3", ptr(x), f, h, w, cin, ptr(w_hi), ptr(w_lo), cout, kh, kw, stride, pad, ptr(y), ptr(bias),
          int(force_bn), stream_ptr())
     return y
+
+
+# weight-split cache: the hi/lo operands of a weight are rebuilt only when the weight changed.  Keyed by the
+# storage address (autograd hands backward() re-wrapped tensor objects); validated by the autograd version counter
+# and emptied by every FusedSGD step (it updates parameters through raw pointers, invisible to the version counter).
+_split_cache = {}
+
+
+def bump_weight_epoch():
+    _split_cache.clear()
+
+
+def weight_split(w, mode):
+    key = (w.data_ptr(), mode)
+    ent = _split_cache.get(key)
+    if ent is None or ent[0] != (w._version, tuple(w.shape)):
+        with torch.no_grad():
+            ent = ((w._version, tuple(w.shape)), split_tf32(w.detach(), mode))
+        _split_cache[key] = ent
+    return ent[1]
+
+
+_wgrad_ws = {}
+
+
+def conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad):
+    """Weight gradient (Cout, Cin, KH, KW), contiguous, of conv2d(x, w, stride, pad) given dL/dy = gy.
+    x, gy: channels_last."""
+    _require_cuda(x, "conv2d_wgrad")
+    if not (x.is_contiguous(memory_format=CL) and gy.is_contiguous(memory_format=CL)):
+        raise _lib.VittaError("conv2d_wgrad: x and gy must be channels_last contiguous")
+    f, cin, h, w = x.shape
+    n = _lib.load().vitta_conv2d_wgrad_ws_floats(f, h, w, cin, cout, kh, kw, stride, pad)
+    if n <= 0:
+        raise _lib.VittaError("conv2d_wgrad: bad geometry")
+    ws = _wgrad_ws.get(x.device)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(n, dtype=torch.float32, device=x.device)
+        _wgrad_ws[x.device] = ws
+    gw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+    call("vitta_conv2d_wgrad_tf32x3", ptr(x), ptr(gy), f, h, w, cin, cout, kh, kw, stride, pad, ptr(gw), 0, ptr(ws),
+         stream_ptr())
+    return gw
+
+
+class Conv2dFn(torch.autograd.Function):
+    """Bias-free 2-D convolution, channels-last, forward and data gradient on the tcgen05 3xTF32 kernel.
+
+    Stride-1 data gradients reuse the forward kernel with the transposed / 180-degree-rotated operand (split mode 1);
+    weight gradients run on the split-K tcgen05 wgrad kernel.  Only the data gradient of the six stride-2 layers
+    still goes through ``aten::convolution_backward`` (see DESIGN.md)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        cout, cin, kh, kw = w.shape
+        whi, wlo = weight_split(w, 0)
+        y = conv2d_tf32x3(x, whi, wlo, cout, kh, kw, stride, pad)
+        ctx.save_for_backward(x, w)
+        ctx.geom = (stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.geom
+        cout, cin, kh, kw = w.shape
+        gy = gy.contiguous(memory_format=CL)
+        gx = gw = None
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
+            whi, wlo = weight_split(w, 1)
+            gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad)
+            need_x = False
+        if need_w and cout % 4 == 0:
+            gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)
+            need_w = False
+        if need_x or need_w:
+            r = torch.ops.aten.convolution_backward(gy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0],
+                                                    1, [need_x, need_w, False])
+            if need_x:
+                gx = r[0]
+            if need_w:
+                gw = r[1]
+        return gx, gw, None, None
+
+
+def conv2d(x, w, stride, pad):
+    return Conv2dFn.apply(x, w, stride, pad)
