@@ -96,13 +96,16 @@ typedef struct VittaLayerDesc {
  *     dLoss_l/dy[.., c, ..] = coef_a[c] + coef_b[c] * (y - batch_mean[c])     (SURVEY.md section 8a row a5;
  *     the centred form keeps fp32 accuracy when |mean| >> std)
  * loss[l] receives r_feature of layer l; loss[n_layers] their sum (summed in layer order by the last CTA
- * to finish); loss[n_layers+1] is an int32 ticket the caller zero-initialises once (self-resetting).
+ * to finish); loss[n_layers+1] is an int32 ticket the caller zero-initialises once (self-resetting); the rest of the
+ * buffer (vitta_stats_finalize_loss_floats(n_layers, max_channels) floats in total) holds per-CTA loss partials.
+ * max_channels = the largest C in the table (sizes the grid: one CTA per 32 channels per layer).
  * merge_only != 0: only merge entries and write (mean, M2) pairs to merged[(ch_off + c)*2 + {0,1}] and
  * the count (as int32) to merged_counts[l] -- the per-rank payload of the multi-GPU all-gather. */
 int vitta_stats_finalize(const VittaLayerDesc* descs, int n_layers, const float* part, const int32_t* counts,
                          const float* src_mean, const float* src_var, float* ema_mean, float* ema_var,
                          float* batch_mean, float* batch_var, float* coef_a, float* coef_b, float* loss,
-                         int merge_only, float* merged, int32_t* merged_counts, void* stream);
+                         int merge_only, float* merged, int32_t* merged_counts, int max_channels, void* stream);
+int64_t vitta_stats_finalize_loss_floats(int n_layers, int max_channels);
 
 /* K3  standalone backward of the alignment loss of one layer (used by hooks on stock torch modules):
  *     gy[o,c,i] = (*gscale) * (coef_a[c] + coef_b[c] * (y[o,c,i] - mean[c])),  y = yscale[c]*x + yshift[c] when

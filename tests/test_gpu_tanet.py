@@ -66,10 +66,10 @@ def _run_case(name, dev):
             k = "step%d/ema_mean/%d" % (s, h)
             if k in g:
                 em, ev = g[k], g["step%d/ema_var/%d" % (s, h)]
-                # per-channel means can be ~0, so the absolute floor is 1e-5 x the layer's activation
+                # per-channel means can be ~0, so the absolute floor is 3e-5 x the layer's activation
                 # scale (|mean| + std over channels), not 1e-5 x max|mean|
                 scale = float((np.abs(em) + np.sqrt(np.abs(ev))).max())
-                cases.assert_close(hook.ema_mean.cpu(), em, 1e-4, 1e-5 * scale + 1e-7, k)
+                cases.assert_close(hook.ema_mean.cpu(), em, 1e-4, 3e-5 * scale + 1e-7, k)
                 cases.assert_close(hook.ema_var.cpu(), ev, 1e-4, 1e-5 * float(np.abs(ev).max()) + 1e-7, "ema_var")
         ad.hooks_off()
         ev = ad.evaluate(eval_in[s].to(dev))

@@ -40,7 +40,9 @@ _SIGNATURES = {
     "vitta_sm_count": (C.c_int, []),
     "vitta_stats_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int64, C.POINTER(VittaChunking)]),
     "vitta_stats_partial": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int64, _P, _P]),
-    "vitta_stats_finalize": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "vitta_stats_finalize": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int,
+                                       _P]),
+    "vitta_stats_finalize_loss_floats": (C.c_int64, [C.c_int, C.c_int]),
     "vitta_stats_inject": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, _P]),
     "vitta_bn_act_fwd": (C.c_int, [_P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, C.c_int64,
                                    C.c_int64, C.c_int, _P]),
@@ -97,10 +99,21 @@ def check(rc, what):
         raise VittaError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else ""))
 
 
+profile = None  # set to a list to record (name, start_event, end_event, args) for every call (bench.py attribution)
+
+
 def call(name, *args):
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        profile.append((name, e0, e1, args))
+    else:
+        rc = getattr(lib, name)(*args)
     launch_count += 1
     check(rc, name)
 

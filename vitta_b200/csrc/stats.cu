@@ -110,10 +110,14 @@ __global__ void __launch_bounds__(kThreads) stats_oci_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: one CTA per layer.  Thread = channel (strided); serial Chan merge over the layer's entries,
-// EMA, loss term, backward coefficients; deterministic block reduction of the loss.
+// K2: grid = (layers, channel groups of 32).  Thread = (channel, entry slice): the layer's entries are merged
+// with Chan's formula by 8 slices in parallel (coalesced float2 loads across the 32 channels), then tree-merged in
+// shared memory; 32 threads apply the meter, the loss term and the backward coefficients.  Per-CTA loss partials
+// are summed in a fixed order by the last CTA to finish (deterministic).
 // ------------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 512;
+constexpr int kFinThreads = 256;
+constexpr int kFinCh = 32;
+constexpr int kFinSlices = kFinThreads / kFinCh;
 
 __device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
@@ -123,86 +127,107 @@ __global__ void __launch_bounds__(kFinThreads) stats_finalize_kernel(
     float* __restrict__ ema_mean, float* __restrict__ ema_var, float* __restrict__ batch_mean,
     float* __restrict__ batch_var, float* __restrict__ coef_a, float* __restrict__ coef_b, float* __restrict__ loss,
     int merge_only, float* __restrict__ merged, int32_t* __restrict__ merged_counts) {
-  __shared__ float red[kFinThreads / 32];
+  __shared__ float s_n[kFinThreads], s_mean[kFinThreads], s_m2[kFinThreads];
   __shared__ int s_last;
   const VittaLayerDesc d = descs[blockIdx.x];
   const int C = d.C;
-  float lsum = 0.f;
-  double ntot_d = 0.0;
-  for (int c = threadIdx.x; c < C; c += kFinThreads) {
+  const int cs = threadIdx.x % kFinCh, es = threadIdx.x / kFinCh;
+  const int c = blockIdx.y * kFinCh + cs;
+  const int max_groups = gridDim.y;
+  float* loss_part = loss + n_layers + 2;
+  float l = 0.f;
+  if (blockIdx.y * kFinCh < C) {
     float n = 0.f, mean = 0.f, m2 = 0.f;
-    const float* p = part + d.part_off + (int64_t)c * 2;
-    for (int e = 0; e < d.n_entries; ++e) {
-      float cnt;
-      if (counts) {
-        cnt = (float)counts[d.cnt_off + (int64_t)e * d.cnt_stride];
-      } else {
-        int64_t rem = d.frame_rows - (int64_t)(e % d.chunks_per_frame) * d.chunk_rows;
-        cnt = (float)(rem < d.chunk_rows ? rem : (int64_t)d.chunk_rows);
+    if (c < C) {
+      const float* p = part + d.part_off + (int64_t)c * 2;
+#pragma unroll 4
+      for (int e = es; e < d.n_entries; e += kFinSlices) {
+        float cnt;
+        if (counts) {
+          cnt = (float)counts[d.cnt_off + (int64_t)e * d.cnt_stride];
+        } else {
+          int64_t rem = d.frame_rows - (int64_t)(e % d.chunks_per_frame) * d.chunk_rows;
+          cnt = (float)(rem < d.chunk_rows ? rem : (int64_t)d.chunk_rows);
+        }
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p + (int64_t)e * d.entry_stride));
+        chan_merge(n, mean, m2, cnt, v.x, v.y);
       }
-      const float2 v = __ldg(reinterpret_cast<const float2*>(p + (int64_t)e * d.entry_stride));
-      chan_merge(n, mean, m2, cnt, v.x, v.y);
     }
-    const int64_t ci = d.ch_off + c;
-    if (merge_only) {
-      merged[ci * 2 + 0] = mean;
-      merged[ci * 2 + 1] = m2;
-      ntot_d = (double)n;
-      continue;
+    s_n[threadIdx.x] = n; s_mean[threadIdx.x] = mean; s_m2[threadIdx.x] = m2;
+    __syncthreads();
+    for (int st = kFinSlices >> 1; st > 0; st >>= 1) {
+      if (es < st) {
+        const int o = threadIdx.x + st * kFinCh;
+        chan_merge(n, mean, m2, s_n[o], s_mean[o], s_m2[o]);
+        s_n[threadIdx.x] = n; s_mean[threadIdx.x] = mean; s_m2[threadIdx.x] = m2;
+      }
+      __syncthreads();
     }
-    const float var = m2 / n;
-    batch_mean[ci] = mean;
-    batch_var[ci] = var;
-    if (!d.has_source) continue;
-    const float em = fmaf(d.w_new, mean, d.w_old * ema_mean[ci]);
-    const float ev = fmaf(d.w_new, var, d.w_old * ema_var[ci]);
-    ema_mean[ci] = em;
-    ema_var[ci] = ev;
-    const float sm = src_mean[ci], sv = src_var[ci];
-    const float dm = em - sm, dv = ev - sv;
-    float gm, gv, l;
-    if (d.reg_type == VITTA_REG_L1) {
-      const float invC = 1.f / (float)C;
-      l = (fabsf(dv) + fabsf(dm)) * invC;
-      gm = sgnf(dm) * invC;
-      gv = sgnf(dv) * invC;
-    } else if (d.reg_type == VITTA_REG_MSE) {
-      const float invC = 1.f / (float)C;
-      l = (dv * dv + dm * dm) * invC;
-      gm = 2.f * dm * invC;
-      gv = 2.f * dv * invC;
-    } else {  // KLD: true = source, pred = ema (norm_stats_utils.py:8-16); summed over channels
-      const float q = sv + dm * dm;
-      l = 0.5f * logf(ev / sv) + q / (2.f * ev) - 0.5f;
-      gm = dm / ev;
-      gv = 0.5f / ev - q / (2.f * ev * ev);
+    if (es == 0 && c < C) {
+      const int64_t ci = d.ch_off + c;
+      if (merge_only) {
+        merged[ci * 2 + 0] = mean;
+        merged[ci * 2 + 1] = m2;
+        if (c == 0) merged_counts[blockIdx.x] = (int32_t)n;
+      } else {
+        const float var = m2 / n;
+        batch_mean[ci] = mean;
+        batch_var[ci] = var;
+        if (d.has_source) {
+          const float em = fmaf(d.w_new, mean, d.w_old * ema_mean[ci]);
+          const float ev = fmaf(d.w_new, var, d.w_old * ema_var[ci]);
+          ema_mean[ci] = em;
+          ema_var[ci] = ev;
+          const float sm = src_mean[ci], sv = src_var[ci];
+          const float dm = em - sm, dv = ev - sv;
+          float gm, gv;
+          if (d.reg_type == VITTA_REG_L1) {
+            const float invC = 1.f / (float)C;
+            l = (fabsf(dv) + fabsf(dm)) * invC;
+            gm = sgnf(dm) * invC;
+            gv = sgnf(dv) * invC;
+          } else if (d.reg_type == VITTA_REG_MSE) {
+            const float invC = 1.f / (float)C;
+            l = (dv * dv + dm * dm) * invC;
+            gm = 2.f * dm * invC;
+            gv = 2.f * dv * invC;
+          } else {  // KLD: true = source, pred = ema (norm_stats_utils.py:8-16); summed over channels
+            const float q = sv + dm * dm;
+            l = 0.5f * logf(ev / sv) + q / (2.f * ev) - 0.5f;
+            gm = dm / ev;
+            gv = 0.5f / ev - q / (2.f * ev * ev);
+          }
+          // dLoss/dy = coef_a + coef_b * (y - batch_mean): the centred form avoids the cancellation of a' + b*y
+          coef_b[ci] = d.w_new * gv * 2.f / n;
+          coef_a[ci] = d.w_new * gm / n;
+        }
+      }
     }
-    lsum += l;
-    // dLoss/dy = coef_a + coef_b * (y - batch_mean): the centred form avoids the cancellation of a' + b*y
-    coef_b[ci] = d.w_new * gv * 2.f / n;
-    coef_a[ci] = d.w_new * gm / n;
   }
-  if (merge_only) {
-    if (threadIdx.x == 0) merged_counts[blockIdx.x] = (int32_t)ntot_d;
-    return;
+  if (merge_only) return;
+  // loss partial of this CTA: fixed shuffle tree over its 32 channels (warp 0 holds them: es == 0)
+  if (threadIdx.x < 32) {
+    l = warp_sum(l);
+    if (threadIdx.x == 0) {
+      loss_part[(int64_t)blockIdx.x * max_groups + blockIdx.y] = l;
+      __threadfence();
+      int* ticket = reinterpret_cast<int*>(loss + n_layers + 1);
+      s_last = (atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+    }
   }
-  // deterministic block reduction (fixed shuffle tree, then warp 0 sums the warp partials in order)
-  lsum = warp_sum(lsum);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int ly = threadIdx.x; ly < n_layers; ly += kFinThreads) {
+    const int groups = (descs[ly].C + kFinCh - 1) / kFinCh;
+    float t = 0.f;
+    for (int g = 0; g < groups; ++g) t += __ldcg(loss_part + (int64_t)ly * max_groups + g);
+    loss[ly] = t;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int w = 0; w < kFinThreads / 32; ++w) t += red[w];
-    loss[blockIdx.x] = t;
-    __threadfence();
-    int* ticket = reinterpret_cast<int*>(loss + n_layers + 1);
-    s_last = (atomicAdd(ticket, 1) == n_layers - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    float t = 0.f;
-    for (int l = 0; l < n_layers; ++l) t += *(volatile float*)(loss + l);
+    for (int ly = 0; ly < n_layers; ++ly) t += loss[ly];
     loss[n_layers] = t;
     *reinterpret_cast<int*>(loss + n_layers + 1) = 0;
   }
@@ -309,17 +334,23 @@ int vitta_stats_partial(const float* x, int64_t O, int C, int64_t I, int64_t fra
   return 0;
 }
 
+int64_t vitta_stats_finalize_loss_floats(int n_layers, int max_channels) {
+  if (n_layers <= 0 || max_channels <= 0) return -1;
+  return (int64_t)n_layers + 2 + (int64_t)n_layers * ((max_channels + kFinCh - 1) / kFinCh);
+}
+
 int vitta_stats_finalize(const VittaLayerDesc* descs, int n_layers, const float* part, const int32_t* counts,
                          const float* src_mean, const float* src_var, float* ema_mean, float* ema_var,
                          float* batch_mean, float* batch_var, float* coef_a, float* coef_b, float* loss,
-                         int merge_only, float* merged, int32_t* merged_counts, void* stream) {
-  VITTA_CHECK_ARG(descs && part && n_layers > 0, VITTA_E_BADARG, "stats_finalize: bad arguments");
+                         int merge_only, float* merged, int32_t* merged_counts, int max_channels, void* stream) {
+  VITTA_CHECK_ARG(descs && part && n_layers > 0 && max_channels > 0, VITTA_E_BADARG, "stats_finalize: bad arguments");
   if (merge_only) {
     VITTA_CHECK_ARG(merged && merged_counts, VITTA_E_BADARG, "stats_finalize: merge_only needs merged buffers");
   } else {
     VITTA_CHECK_ARG(batch_mean && batch_var && loss, VITTA_E_BADARG, "stats_finalize: null output");
   }
-  stats_finalize_kernel<<<n_layers, kFinThreads, 0, (cudaStream_t)stream>>>(
+  dim3 grid((unsigned)n_layers, (unsigned)((max_channels + kFinCh - 1) / kFinCh));
+  stats_finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(
       descs, n_layers, part, counts, src_mean, src_var, ema_mean, ema_var, batch_mean, batch_var, coef_a, coef_b, loss,
       merge_only, merged, merged_counts);
   VITTA_CHECK_LAUNCH();

@@ -101,7 +101,9 @@ class StatsArena:
                 sl = slice(ly.ch_off, ly.ch_off + ly.C)
                 self.src_mean[sl] = torch.as_tensor(m, dtype=torch.float32).to(dev).reshape(-1)
                 self.src_var[sl] = torch.as_tensor(v, dtype=torch.float32).to(dev).reshape(-1)
-        self.loss = torch.zeros(len(self.layers) + 2, dtype=torch.float32, device=dev)
+        self.max_C = max(ly.C for ly in self.layers)
+        self.loss = torch.zeros(_lib.load().vitta_stats_finalize_loss_floats(len(self.layers), self.max_C),
+                                dtype=torch.float32, device=dev)
         self._base = torch.zeros(4, dtype=torch.float32, device=dev)
 
     def _freeze(self, dev):
@@ -203,7 +205,7 @@ class StatsArena:
         if self.process_group is None:
             call("vitta_stats_finalize", ptr(self._desc_dev), n, ptr(self._base), None, ptr(self.src_mean),
                  ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
-                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, st)
+                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, self.max_C, st)
         else:
             import torch.distributed as dist
             ws = dist.get_world_size(self.process_group)
@@ -212,7 +214,7 @@ class StatsArena:
             merged = pay[:2 * self.total_C]
             cnts = pay[2 * self.total_C:].view(torch.int32)
             call("vitta_stats_finalize", ptr(self._desc_dev), n, ptr(self._base), None, None, None, None, None, None,
-                 None, None, None, None, 1, ptr(merged), ptr(cnts), st)
+                 None, None, None, None, 1, ptr(merged), ptr(cnts), self.max_C, st)
             gath = torch.empty(ws * pay.numel(), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(gath, pay, group=self.process_group)   # collective C1 (NCCL over NVLink)
             g2 = gath.view(ws, -1)
@@ -221,7 +223,7 @@ class StatsArena:
             self._gath_keep = (means, counts)
             call("vitta_stats_finalize", ptr(self._desc_gath), n, ptr(means), ptr(counts), ptr(self.src_mean),
                  ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
-                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, st)
+                 ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, self.max_C, st)
         for ly in active:
             if not ly.moving_avg:
                 ly.meter_count += ly.n_batch
