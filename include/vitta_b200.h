@@ -215,6 +215,15 @@ int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int C
 int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                       int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
                       int act, int force_bn, void* stream);
+/* Extended epilogue (Swin MLP / attention projections):
+ *   v = acc + bias;  aux_out[m,n] = v (optional: the pre-activation, leading dimension ldc);
+ *   act 1: v = GELU(v);  act 2: v = v * GELU'(residual[m,n]) (residual = saved pre-activation; backward of fc1's GELU);
+ *   v *= row_scale[m / rows_per_group] (optional: DropPath's per-sample factor, swin_transformer.py:210,246,252);
+ *   act != 2: v += residual[m,n] (the block's shortcut, swin_transformer.py:266,272). */
+int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
+                         int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                         int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
+                         void* stream);
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
                         int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream);
 
@@ -226,6 +235,74 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
 int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
                               int stride, int pad, float* dW, int accumulate, float* ws, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  LayerNorm over the channel axis of a (rows, C) token matrix with the statistics hook fused in.
+ *   replaces: nn.LayerNorm (norm1 / norm2 / downsample.norm / backbone.norm,
+ *             models/videoswintransformer_models/swin_transformer.py:204,212,288,545) followed by the forward hook
+ *             (utils/norm_stats_utils.py:222-243), and in "merge" mode the PatchMerging gather that feeds
+ *             downsample.norm (swin_transformer.py:293-310).
+ * Forward: y = (x - mean_r) * rstd_r * gamma + beta, mean/rstd saved per row; when `part` is given every chunk of
+ *   vitta_ln_chunking(rows, C, 1) consecutive rows writes the per-channel (mean, M2) of y to part[(e*C + c)*2 + {0,1}]
+ *   (same format as K1, consumed by vitta_stats_finalize).
+ * gather != NULL: the logical row (b, d, h2, w2) of 4*Cin channels is read from x = (B, D, H, W, Cin) as
+ *   [x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1), x(2h2+1,2w2+1)] (zeros outside H x W); rows = B*D*ceil(H/2)*ceil(W/2).
+ * Backward: gy' = gy + gscale*(coef_a + coef_b*(y - coef_mean))   [hook term, optional, y recomputed]
+ *   gx = rstd*(gy'*gamma - mean_C(gy'*gamma) - xhat*mean_C(gy'*gamma*xhat)) (+ gadd), dgamma += sum_r gy'*xhat,
+ *   dbeta += sum_r gy'.  In merge mode gx is scattered back into the (B, D, H, W, Cin) layout.
+ * ws: vitta_ln_bwd_ws_floats() floats, zero-initialised ONCE by the caller (self-resetting tickets).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VittaLnGather {
+  int32_t B, D, H, W, Cin;
+} VittaLnGather;
+int vitta_ln_chunking(int64_t rows, int C, int want_stats, VittaChunking* out);
+int vitta_ln_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
+                 float* part, int64_t rows, int C, const VittaLnGather* gather, void* stream);
+int64_t vitta_ln_bwd_ws_floats(int64_t rows, int C);
+int vitta_ln_bwd(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                 const float* rstd, const float* gadd, const float* coef_a, const float* coef_b, const float* coef_mean,
+                 const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws, int64_t rows, int C,
+                 const VittaLnGather* gather, void* stream);
+
+/* Small token-matrix helpers of the Swin path.
+ *   vitta_colsum:      out[c] (+)= sum_r x[r, c]   (bias gradients of nn.Linear; deterministic two-stage sum;
+ *                      ws: vitta_colsum_ws_floats() floats zero-initialised once)
+ *   vitta_frame_mean:  out[f, c] = mean over the `rows` rows of frame f   (AdaptiveAvgPool3d of I3DHead,
+ *                      models/videoswintransformer_models/i3d_head.py:66-67) and its backward
+ *   vitta_patchify3d:  video (B, 3, T, H, W) -> (B*D*Hp*Wp, 3*pt*ph*pw) patch rows in nn.Conv3d weight order, so that
+ *                      PatchEmbed3D.proj (swin_transformer.py:432,446) becomes one GEMM */
+int64_t vitta_colsum_ws_floats(int64_t rows, int C);
+int vitta_colsum(const float* x, int64_t rows, int C, float* out, int accumulate, float* ws, void* stream);
+int vitta_frame_mean(const float* x, int64_t frames, int rows, int C, float* out, void* stream);
+int vitta_frame_mean_bwd(const float* g, int64_t frames, int rows, int C, float* gx, void* stream);
+int vitta_patchify3d(const float* video, int B, int T, int H, int W, int pt, int ph, int pw, float* out, void* stream);
+/* out[r, :] = x[r, :] * scale[r / rows_per_group]: DropPath's per-sample factor applied to a gradient before the
+ * weight-gradient GEMM (timm DropPath, call site swin_transformer.py:210). */
+int vitta_row_scale(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  Video-Swin 3-D (shifted-)window multi-head self-attention, head_dim 32.
+ *   replaces: WindowAttention3D.forward (q*scale, q@k^T, + relative_position_bias_table[relative_position_index[:N,:N]],
+ *             + shift mask (0 / -100), softmax, attn@v; models/videoswintransformer_models/swin_transformer.py:145-166)
+ *             and the roll / window_partition / window_reverse / roll-back copies around it (:229-248), and
+ *             compute_mask (:316-329) -- the mask is evaluated from region ids inside the kernel.
+ *   qkv: (B, D, H, W, 3, heads, 32) = the output of nn.Linear(dim, 3*dim) on the normalised tokens, natural token order;
+ *   bias_table: (prod(2*window-1), heads);  out: (B, D, H, W, heads*32) = the proj input, natural token order;
+ *   lse: (B*windows, heads, N) log-sum-exp per query row (saved for the backward);
+ *   window / shift: the CONFIGURED 3-vectors (e.g. {8,7,7}, {4,3,3} or {0,0,0}); they are clamped per dimension exactly
+ *   as get_window_size (:71-84) does, and the bias index uses the configured window (relative_position_index[:N,:N]).
+ *   D, H, W must be multiples of the clamped window (true for every 224x224 configuration; the zero-padding branch
+ *   :222-227 returns VITTA_E_UNSUPPORTED).
+ * Forward: tcgen05 (3xTF32) -- S = QK^T accumulates in TMEM, softmax in place, O += P V.
+ * Backward: dqkv has the layout of qkv (every element written once); dbias_table is ACCUMULATED into (zero it first).
+ * ---------------------------------------------------------------------------------------------- */
+int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                     int heads, int head_dim, const int* window_host, const int* shift_host, float scale, void* stream);
+int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
+                     float* dqkv, float* dbias_table, int B, int D, int H, int W, int heads, int head_dim,
+                     const int* window_host, const int* shift_host, float scale, void* stream);
 
 #ifdef __cplusplus
 }

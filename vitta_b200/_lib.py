@@ -29,6 +29,10 @@ class VittaBN(C.Structure):
                 ("running_var", C.c_void_p), ("eps", C.c_float)]
 
 
+class VittaLnGather(C.Structure):
+    _fields_ = [("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32)]
+
+
 class VittaSgdTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("buf", C.c_void_p), ("n", C.c_int64)]
 
@@ -60,6 +64,22 @@ _SIGNATURES = {
                                       C.c_int, _P, _P, C.c_int, _P]),
     "vitta_conv2d_wgrad_ws_floats": (C.c_int64, [C.c_int] * 9),
     "vitta_conv2d_wgrad_tf32x3": (C.c_int, [_P, _P] + [C.c_int] * 9 + [_P, C.c_int, _P, _P]),
+    "vitta_gemm_tf32x3_ex": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
+                                       C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int, _P]),
+    "vitta_ln_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(VittaChunking)]),
+    "vitta_ln_fwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P]),
+    "vitta_ln_bwd_ws_floats": (C.c_int64, [C.c_int64, C.c_int]),
+    "vitta_ln_bwd": (C.c_int, [_P] * 15 + [C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P]),
+    "vitta_colsum_ws_floats": (C.c_int64, [C.c_int64, C.c_int]),
+    "vitta_colsum": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P]),
+    "vitta_frame_mean": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "vitta_frame_mean_bwd": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "vitta_patchify3d": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vitta_row_scale": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "vitta_wmsa3d_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P]),
+    "vitta_wmsa3d_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }
@@ -130,6 +150,12 @@ def stream_ptr():
 def chunking(O, Cc, I, frames=1):
     out = VittaChunking()
     check(load().vitta_stats_chunking(O, Cc, I, frames, C.byref(out)), "vitta_stats_chunking")
+    return out
+
+
+def ln_chunking(rows, Cc, want_stats=True):
+    out = VittaChunking()
+    check(load().vitta_ln_chunking(rows, Cc, 1 if want_stats else 0, C.byref(out)), "vitta_ln_chunking")
     return out
 
 

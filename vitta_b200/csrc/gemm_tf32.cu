@@ -36,8 +36,11 @@ struct GemmParams {
   int Ho, Wo, F;           // output geometry: rows of C = (f, ho, wo); plain GEMM: F = 1, Ho = 1, Wo = M
   int BW, BH, BF;          // output pixels covered by one M tile: BF frames x BH rows x BW cols  (BW*BH*BF <= 128)
   int tiles_w, tiles_h, tiles_f, tiles_n;
-  int act;                 // 0 none, 1 exact GELU
+  int act;                 // 0 none, 1 exact GELU, 2 multiply by GELU'(residual[m, n]) (residual = saved pre-activation)
   int vec_ok;              // C / bias / residual allow 128-bit accesses
+  float* aux_out;          // optional second output: the pre-activation acc + bias (same indexing as C)
+  const float* row_scale;  // optional per-row-group factor (DropPath): v *= row_scale[row / rows_per_group]
+  int rows_per_group;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -221,6 +224,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int64_t out_row = ((int64_t)f * p.Ho + ho) * p.Wo + wo;
       float* crow = p.C + out_row * p.ldc;
       const float* rrow = p.residual ? p.residual + out_row * p.ldr : nullptr;
+      float* arow = p.aux_out ? p.aux_out + out_row * p.ldc : nullptr;
+      const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + out_row / p.rows_per_group) : 1.f;
       const int n0 = nt * BN;
 
       mbar_wait(&acc_full[acc], acc_phase);
@@ -242,10 +247,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float4 b = ldg4(p.bias + nbase + j);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
               }
+              if (arow) st4(arow + nbase + j, v);
               if (p.act == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
               if (rrow) {
                 const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                if (p.act == 2) {
+                  v.x *= gelu_grad(rr.x); v.y *= gelu_grad(rr.y); v.z *= gelu_grad(rr.z); v.w *= gelu_grad(rr.w);
+                  v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
+                } else {
+                  v.x = fmaf(v.x, rscale, rr.x); v.y = fmaf(v.y, rscale, rr.y);
+                  v.z = fmaf(v.z, rscale, rr.z); v.w = fmaf(v.w, rscale, rr.w);
+                }
+              } else {
+                v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
               }
               st4(crow + nbase + j, v);
             }
@@ -256,8 +270,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (n < p.N) {
                 float v = __uint_as_float(r[j]);
                 if (p.bias) v += __ldg(p.bias + n);
+                if (arow) arow[n] = v;
                 if (p.act == 1) v = gelu_exact(v);
-                if (rrow) v += rrow[n];
+                if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale : fmaf(v, rscale, rrow[n]);
+                else v *= rscale;
                 crow[n] = v;
               }
             }
@@ -421,7 +437,19 @@ int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int C
 int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                       int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
                       int act, int force_bn, void* stream) {
+  return vitta_gemm_tf32x3_ex(A, lda, Bhi, Blo, ldb, C, ldc, M, N, K, bias, residual, ldr, act, nullptr, nullptr, 1,
+                              force_bn, stream);
+}
+
+int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
+                         int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                         int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
+                         void* stream) {
   VITTA_CHECK_ARG(A && Bhi && Blo && C && M > 0 && N > 0 && K > 0, VITTA_E_BADARG, "gemm_tf32x3: bad arguments");
+  VITTA_CHECK_ARG(act >= 0 && act <= 2 && !(act == 2 && !residual), VITTA_E_BADARG,
+                  "gemm_tf32x3: act must be 0/1/2 and act 2 needs the pre-activation in `residual`");
+  VITTA_CHECK_ARG(!row_scale || (rows_per_group > 0 && rows_per_group < (1ll << 31)), VITTA_E_BADARG,
+                  "gemm_tf32x3: rows_per_group");
   VITTA_CHECK_ARG(M < (1ll << 31), VITTA_E_UNSUPPORTED, "gemm_tf32x3: M too large");
   VITTA_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(Bhi) && aligned16(Blo), VITTA_E_ALIGN,
                   "gemm_tf32x3: operands need 16-byte aligned rows (lda, ldb multiples of 4 floats)");
@@ -446,8 +474,9 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
   p.BW = kBM; p.BH = 1; p.BF = 1;
   p.tiles_w = (int)((M + kBM - 1) / kBM); p.tiles_h = 1; p.tiles_f = 1;
   p.act = act;
+  p.aux_out = aux_out; p.row_scale = row_scale; p.rows_per_group = row_scale ? (int)rows_per_group : 1;
   p.vec_ok = aligned16(C) && (ldc % 4 == 0) && (!bias || aligned16(bias)) &&
-             (!residual || (aligned16(residual) && ldr % 4 == 0));
+             (!residual || (aligned16(residual) && ldr % 4 == 0)) && (!aux_out || aligned16(aux_out));
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
 }
 

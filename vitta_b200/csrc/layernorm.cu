@@ -1,0 +1,608 @@
+// K9: LayerNorm over the channel axis of a (rows, C) token matrix, forward and backward, with the statistics hook
+// fused in: the forward emits per-chunk per-channel (mean, M2) partials of its OUTPUT (Welford per warp, merged later by
+// vitta_stats_finalize), the backward adds the closed-form hook gradient a_c + b_c (y - mu_c) while it already holds the
+// row, adds the residual-branch gradient and accumulates d(gamma), d(beta).
+// "merge" mode folds Video-Swin's PatchMerging gather (swin_transformer.py:293-310) into the load / scatter:
+//   row (b, d, h2, w2), channel q*Cin + c  <-  x[b, d, 2*h2 + (q & 1), 2*w2 + (q >> 1), c]   (zero outside H x W).
+// One warp per row, lanes along C with 128-bit accesses; a warp owns a chunk of consecutive rows (= one statistics entry).
+#include "common.cuh"
+
+namespace vitta {
+
+constexpr int kLnThreads = 256;
+constexpr int kLnWarps = kLnThreads / 32;
+constexpr int kWsHeader = 64;   // floats reserved at the front of a workspace for the self-resetting tickets
+
+struct LnGather {   // PatchMerging gather (merge != 0)
+  int merge;
+  int D, H, W, Cin;   // source tensor (B, D, H, W, Cin); rows index (b, d, ceil(H/2), ceil(W/2))
+  int H2, W2;
+};
+
+struct LnFwdArgs {
+  const float* x;
+  float* y;
+  const float* gamma;
+  const float* beta;
+  float* mean;    // [rows]
+  float* rstd;    // [rows]
+  float* part;    // [(entry*C + c)*2] or null
+  int64_t rows;
+  int C;
+  int rows_per_warp;
+  float eps;
+  LnGather g;
+};
+
+__device__ __forceinline__ const float* ln_src_row(const float* x, int64_t r, int C, const LnGather& g, int64_t& base,
+                                                   int& h0, int& w0) {
+  if (!g.merge) {
+    base = r * C;
+    return x;
+  }
+  const int w2 = (int)(r % g.W2);
+  int64_t t = r / g.W2;
+  const int h2 = (int)(t % g.H2);
+  t /= g.H2;   // = b*D + d
+  h0 = 2 * h2;
+  w0 = 2 * w2;
+  base = ((t * g.H + h0) * g.W + w0) * (int64_t)g.Cin;
+  return x;
+}
+
+template <int VPL, bool STATS>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int64_t r0 = chunk * p.rows_per_warp;
+  if (r0 >= p.rows) return;
+  const int64_t r1 = (r0 + p.rows_per_warp < p.rows) ? r0 + p.rows_per_warp : p.rows;
+  const int C4 = p.C >> 2;
+  const float invC = 1.f / (float)p.C;
+  // merge mode: per-lane source offsets of each vector (row independent)
+  int goff[VPL];
+  int gdh[VPL], gdw[VPL];
+  if (p.g.merge) {
+    const int cin4 = p.g.Cin >> 2;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      const int q = i / cin4, ci = i - q * cin4;
+      gdh[j] = q & 1;
+      gdw[j] = q >> 1;
+      goff[j] = (gdh[j] * p.g.W + gdw[j]) * p.g.Cin + ci * 4;
+    }
+  }
+  float4 wm[VPL], w2[VPL];   // Welford mean / M2 of y over this warp's rows
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) wm[j] = w2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float nrow = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    int64_t base;
+    int h0 = 0, w0 = 0;
+    const float* src = ln_src_row(p.x, r, p.C, p.g, base, h0, w0);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C4) {
+        if (!p.g.merge) {
+          v[j] = ld_stream4(src + base + (int64_t)i * 4);
+        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
+          v[j] = ld_stream4(src + base + goff[j]);
+        }
+      }
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mu = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      if (i < C4) {
+        const float a = v[j].x - mu, b = v[j].y - mu, c = v[j].z - mu, d = v[j].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rs = 1.f / sqrtf(warp_sum(q) * invC + p.eps);
+    if (lane == 0) {
+      p.mean[r] = mu;
+      p.rstd[r] = rs;
+    }
+    nrow += 1.f;
+    const float inv_n = 1.f / nrow;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      if (i < C4) {
+        const float4 ga = ldg4(p.gamma + i * 4), be = ldg4(p.beta + i * 4);
+        float4 y;
+        y.x = fmaf((v[j].x - mu) * rs, ga.x, be.x);
+        y.y = fmaf((v[j].y - mu) * rs, ga.y, be.y);
+        y.z = fmaf((v[j].z - mu) * rs, ga.z, be.z);
+        y.w = fmaf((v[j].w - mu) * rs, ga.w, be.w);
+        st4(p.y + r * p.C + (int64_t)i * 4, y);
+        if (STATS) {
+          float d;
+          d = y.x - wm[j].x; wm[j].x = fmaf(d, inv_n, wm[j].x); w2[j].x = fmaf(d, y.x - wm[j].x, w2[j].x);
+          d = y.y - wm[j].y; wm[j].y = fmaf(d, inv_n, wm[j].y); w2[j].y = fmaf(d, y.y - wm[j].y, w2[j].y);
+          d = y.z - wm[j].z; wm[j].z = fmaf(d, inv_n, wm[j].z); w2[j].z = fmaf(d, y.z - wm[j].z, w2[j].z);
+          d = y.w - wm[j].w; wm[j].w = fmaf(d, inv_n, wm[j].w); w2[j].w = fmaf(d, y.w - wm[j].w, w2[j].w);
+        }
+      }
+    }
+  }
+  if (STATS) {
+    float* o = p.part + chunk * p.C * 2;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      if (i < C4) {
+        st4(o + (int64_t)i * 8, make_float4(wm[j].x, w2[j].x, wm[j].y, w2[j].y));
+        st4(o + (int64_t)i * 8 + 4, make_float4(wm[j].z, w2[j].z, wm[j].w, w2[j].w));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  const float* gy;      // gradient w.r.t. the LayerNorm output (rows, C)
+  const float* x;       // forward input (plain: (rows, C); merge: source tensor)
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* rstd;
+  const float* gadd;    // optional gradient added to gx (residual branch), plain mode only
+  const float *ca, *cb, *cm, *gs;   // hook coefficients (per channel) + gradient of the layer's r_feature; null: none
+  float* gx;            // plain: (rows, C); merge: scattered into the source layout (B, D, H, W, Cin)
+  float* dgamma;        // accumulated (+=)
+  float* dbeta;
+  float* ws;            // [grid][2][C] partials + 1 int ticket, zero-initialised once (self-resetting)
+  int64_t rows;
+  int C;
+  LnGather g;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
+  __shared__ float4 s_red[2 * 512];   // [2][C/4], C <= 2048
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int C4 = p.C >> 2;
+  const float invC = 1.f / (float)p.C;
+  int goff[VPL];
+  int gdh[VPL], gdw[VPL];
+  if (p.g.merge) {
+    const int cin4 = p.g.Cin >> 2;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      const int q = i / cin4, ci = i - q * cin4;
+      gdh[j] = q & 1;
+      gdw[j] = q >> 1;
+      goff[j] = (gdh[j] * p.g.W + gdw[j]) * p.g.Cin + ci * 4;
+    }
+  }
+  const float gsc = p.ca ? __ldg(p.gs) : 0.f;
+  float4 dg[VPL], db[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t r = (int64_t)blockIdx.x * kLnWarps + warp; r < p.rows; r += (int64_t)gridDim.x * kLnWarps) {
+    int64_t base;
+    int h0 = 0, w0 = 0;
+    const float* src = ln_src_row(p.x, r, p.C, p.g, base, h0, w0);
+    const float mu = __ldg(p.mean + r), rs = __ldg(p.rstd + r);
+    float4 xh[VPL], g[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.g.merge) {
+          v = ld_stream4(src + base + (int64_t)i * 4);
+        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
+          v = ld_stream4(src + base + goff[j]);
+        }
+        float4 gy = ld_stream4(p.gy + r * p.C + (int64_t)i * 4);
+        const float4 ga = ldg4(p.gamma + i * 4);
+        xh[j] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+        if (p.ca) {
+          const float4 be = ldg4(p.beta + i * 4);
+          const float4 a = ldg4(p.ca + i * 4), b = ldg4(p.cb + i * 4), m = ldg4(p.cm + i * 4);
+          gy.x = fmaf(gsc, fmaf(b.x, fmaf(xh[j].x, ga.x, be.x) - m.x, a.x), gy.x);
+          gy.y = fmaf(gsc, fmaf(b.y, fmaf(xh[j].y, ga.y, be.y) - m.y, a.y), gy.y);
+          gy.z = fmaf(gsc, fmaf(b.z, fmaf(xh[j].z, ga.z, be.z) - m.z, a.z), gy.z);
+          gy.w = fmaf(gsc, fmaf(b.w, fmaf(xh[j].w, ga.w, be.w) - m.w, a.w), gy.w);
+        }
+        db[j].x += gy.x; db[j].y += gy.y; db[j].z += gy.z; db[j].w += gy.w;
+        dg[j].x = fmaf(gy.x, xh[j].x, dg[j].x); dg[j].y = fmaf(gy.y, xh[j].y, dg[j].y);
+        dg[j].z = fmaf(gy.z, xh[j].z, dg[j].z); dg[j].w = fmaf(gy.w, xh[j].w, dg[j].w);
+        g[j] = make_float4(gy.x * ga.x, gy.y * ga.y, gy.z * ga.z, gy.w * ga.w);
+        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+      }
+    }
+    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      if (i < C4) {
+        float4 o;
+        o.x = rs * (g[j].x - c1 - xh[j].x * c2);
+        o.y = rs * (g[j].y - c1 - xh[j].y * c2);
+        o.z = rs * (g[j].z - c1 - xh[j].z * c2);
+        o.w = rs * (g[j].w - c1 - xh[j].w * c2);
+        if (!p.g.merge) {
+          if (p.gadd) {
+            const float4 a = ld_stream4(p.gadd + r * p.C + (int64_t)i * 4);
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          st4(p.gx + r * p.C + (int64_t)i * 4, o);
+        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
+          st4(p.gx + base + goff[j], o);
+        }
+      }
+    }
+  }
+  // CTA reduction of d(gamma), d(beta): warps add in turn (fixed order), then one partial per CTA
+  for (int w = 0; w < kLnWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        if (i < C4) {
+          if (w == 0) {
+            s_red[i] = dg[j];
+            s_red[512 + i] = db[j];
+          } else {
+            float4 a = s_red[i], b = s_red[512 + i];
+            a.x += dg[j].x; a.y += dg[j].y; a.z += dg[j].z; a.w += dg[j].w;
+            b.x += db[j].x; b.y += db[j].y; b.z += db[j].z; b.w += db[j].w;
+            s_red[i] = a;
+            s_red[512 + i] = b;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* wsp = p.ws + kWsHeader;   // ws = [ticket ints | per-CTA partials]
+  float* wsb = wsp + (int64_t)blockIdx.x * 2 * p.C;
+  for (int i = threadIdx.x; i < C4; i += kLnThreads) {
+    st4(wsb + (int64_t)i * 4, s_red[i]);
+    st4(wsb + p.C + (int64_t)i * 4, s_red[512 + i]);
+  }
+  __threadfence();
+  __syncthreads();
+  int* ticket = reinterpret_cast<int*>(p.ws);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
+    float s = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(wsp + (int64_t)b * 2 * p.C + i);
+    if (i < p.C) {
+      if (p.dgamma) p.dgamma[i] += s;
+    } else {
+      if (p.dbeta) p.dbeta[i - p.C] += s;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+static int ln_vpl(int C) {
+  const int v = (C / 4 + 31) / 32;
+  return v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : 16;
+}
+static int ln_bwd_grid(int64_t rows) {
+  int64_t g = (rows + kLnWarps - 1) / kLnWarps;
+  const int64_t cap = 148 * 4;
+  return (int)(g < cap ? g : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums / per-frame column means
+// ------------------------------------------------------------------------------------------------
+// out[c] (+)= sum_r x[r, c]; two-stage, fixed order.  grid = (row chunks, channel tiles of 128)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                    float* __restrict__ ws, int64_t rows, int C, int accumulate) {
+  __shared__ float4 sm[256];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int c4 = blockIdx.y * 32 + lane;
+  const bool active = c4 * 4 < C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    for (int64_t r = (int64_t)blockIdx.x * 8 + slot; r < rows; r += (int64_t)gridDim.x * 8) {
+      const float4 v = ld_stream4(x + r * C + (int64_t)c4 * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 4; st > 0; st >>= 1) {
+    if (slot < st) {
+      float4 a = sm[threadIdx.x], b = sm[threadIdx.x + st * 32];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  float* wsp = ws + kWsHeader;
+  if (slot == 0 && active) st4(wsp + (int64_t)blockIdx.x * C + (int64_t)c4 * 4, sm[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  int* tickets = reinterpret_cast<int*>(ws);
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < 128; i += 256) {
+    const int c = blockIdx.y * 128 + i;
+    if (c >= C) continue;
+    float t = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(wsp + (int64_t)b * C + c);
+    out[c] = accumulate ? out[c] + t : t;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.y] = 0;
+}
+
+// out[f, c] = mean over the `rows` rows of frame f.  grid = (frames, channel tiles of 128)
+__global__ void __launch_bounds__(256) frame_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int rows,
+                                                        int C) {
+  __shared__ float4 sm[256];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int c4 = blockIdx.y * 32 + lane;
+  const bool active = c4 * 4 < C;
+  const float* base = x + (int64_t)blockIdx.x * rows * C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    for (int r = slot; r < rows; r += 8) {
+      const float4 v = ld_stream4(base + (int64_t)r * C + (int64_t)c4 * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 4; st > 0; st >>= 1) {
+    if (slot < st) {
+      float4 a = sm[threadIdx.x], b = sm[threadIdx.x + st * 32];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (slot == 0 && active) {
+    const float inv = 1.f / (float)rows;
+    float4 a = sm[threadIdx.x];
+    st4(out + (int64_t)blockIdx.x * C + (int64_t)c4 * 4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+  }
+}
+
+// gx[f, r, c] = g[f, c] / rows
+__global__ void __launch_bounds__(256) frame_mean_bwd_kernel(const float* __restrict__ g, float* __restrict__ gx,
+                                                            int64_t n4, int rows, int C4) {
+  const float inv = 1.f / (float)rows;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const int c4 = (int)(i % C4);
+    const int64_t f = i / ((int64_t)C4 * rows);
+    const float4 v = ldg4(g + (f * C4 + c4) * 4);
+    st4(gx + i * 4, make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv));
+  }
+}
+
+// out[r, :] = x[r, :] * scale[r / rows_per_group]   (DropPath applied to a gradient before the weight-gradient GEMM)
+__global__ void __launch_bounds__(256) row_scale_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                       float* __restrict__ out, int64_t n4, int C4, int64_t rpg) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float s = __ldg(scale + (i / C4) / rpg);
+    const float4 v = ld_stream4(x + i * 4);
+    st4(out + i * 4, make_float4(v.x * s, v.y * s, v.z * s, v.w * s));
+  }
+}
+
+// PatchEmbed3D gather (swin_transformer.py:432,446): video (B, 3, T, H, W) -> patches (B*D*Hp*Wp, 3*pt*ph*pw) with the
+// column order of nn.Conv3d.weight.view(embed, -1): (c, i, j, k).  pw must be 4 (128-bit loads along W).
+__global__ void __launch_bounds__(256) patchify3d_kernel(const float* __restrict__ v, float* __restrict__ out, int B,
+                                                        int T, int H, int W, int pt, int ph) {
+  const int D = T / pt, Hp = H / ph, Wp = W / 4;
+  const int K4 = 3 * pt * ph;   // float4 per patch row
+  const int64_t n4 = (int64_t)B * D * Hp * Wp * K4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const int k4 = (int)(i % K4);
+    int64_t tok = i / K4;
+    const int j = k4 % ph;
+    int t2 = k4 / ph;
+    const int ii = t2 % pt;
+    const int c = t2 / pt;
+    const int wp = (int)(tok % Wp); tok /= Wp;
+    const int hp = (int)(tok % Hp); tok /= Hp;
+    const int d = (int)(tok % D);
+    const int64_t b = tok / D;
+    const float* src = v + ((((b * 3 + c) * T + d * pt + ii) * H + hp * ph + j) * (int64_t)W + wp * 4);
+    st4(out + i * 4, ld_stream4(src));
+  }
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+extern "C" {
+
+int vitta_ln_chunking(int64_t rows, int C, int want_stats, VittaChunking* out) {
+  VITTA_CHECK_ARG(out && rows > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "ln_chunking: bad shape");
+  // a chunk = the rows one warp normalises = one statistics entry
+  int rpw = want_stats ? 64 : 8;
+  while (rpw > 4 && (rows + rpw - 1) / rpw < 148 * 16) rpw >>= 1;
+  out->chunk_rows = rpw;
+  out->frame_rows = rows;
+  const int64_t n = (rows + rpw - 1) / rpw;
+  VITTA_CHECK_ARG(n < (1ll << 31), VITTA_E_UNSUPPORTED, "ln_chunking: too many chunks");
+  out->n_entries = (int32_t)n;
+  out->chunks_per_frame = (int32_t)n;
+  out->reserved = 0;
+  return 0;
+}
+
+static int ln_check_gather(const VittaLnGather* g, int C, int64_t rows, LnGather* o) {
+  o->merge = 0;
+  if (!g) return 0;
+  VITTA_CHECK_ARG(g->B > 0 && g->D > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Cin % 4 == 0 && C == 4 * g->Cin,
+                  VITTA_E_BADARG, "ln: bad PatchMerging geometry");
+  o->merge = 1; o->D = g->D; o->H = g->H; o->W = g->W; o->Cin = g->Cin;
+  o->H2 = (g->H + 1) / 2; o->W2 = (g->W + 1) / 2;
+  VITTA_CHECK_ARG(rows == (int64_t)g->B * g->D * o->H2 * o->W2, VITTA_E_BADARG, "ln: rows do not match the merge geometry");
+  return 0;
+}
+
+int vitta_ln_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
+                 float* part, int64_t rows, int C, const VittaLnGather* gather, void* stream) {
+  VITTA_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows > 0, VITTA_E_BADARG, "ln_fwd: null pointer");
+  VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 2048, VITTA_E_UNSUPPORTED, "ln_fwd: C must be a multiple of 4, <= 2048");
+  VITTA_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!part || aligned16(part)),
+                  VITTA_E_ALIGN, "ln_fwd: tensors must be 16-byte aligned");
+  LnFwdArgs p;
+  int rc = ln_check_gather(gather, C, rows, &p.g);
+  if (rc) return rc;
+  VittaChunking ch;
+  rc = vitta_ln_chunking(rows, C, part != nullptr, &ch);
+  if (rc) return rc;
+  p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.part = part;
+  p.rows = rows; p.C = C; p.rows_per_warp = ch.chunk_rows; p.eps = eps;
+  const unsigned grid = (unsigned)((ch.n_entries + kLnWarps - 1) / kLnWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vpl = ln_vpl(C);
+#define VITTA_LN_FWD(V)                                                        \
+  if (part) ln_fwd_kernel<V, true><<<grid, kLnThreads, 0, st>>>(p);            \
+  else ln_fwd_kernel<V, false><<<grid, kLnThreads, 0, st>>>(p)
+  switch (vpl) {
+    case 1: VITTA_LN_FWD(1); break;
+    case 2: VITTA_LN_FWD(2); break;
+    case 4: VITTA_LN_FWD(4); break;
+    case 8: VITTA_LN_FWD(8); break;
+    default: VITTA_LN_FWD(16); break;
+  }
+#undef VITTA_LN_FWD
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int64_t vitta_ln_bwd_ws_floats(int64_t rows, int C) {
+  if (rows <= 0 || C <= 0) return -1;
+  return (int64_t)148 * 4 * 2 * C + kWsHeader;   // independent of rows: one buffer per C serves every call
+}
+
+int vitta_ln_bwd(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                 const float* rstd, const float* gadd, const float* coef_a, const float* coef_b, const float* coef_mean,
+                 const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws, int64_t rows, int C,
+                 const VittaLnGather* gather, void* stream) {
+  VITTA_CHECK_ARG(gy && x && gamma && beta && mean && rstd && gx && ws && rows > 0, VITTA_E_BADARG, "ln_bwd: null pointer");
+  VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 2048, VITTA_E_UNSUPPORTED, "ln_bwd: C must be a multiple of 4, <= 2048");
+  VITTA_CHECK_ARG((coef_a == nullptr) == (coef_b == nullptr) && (coef_a == nullptr) == (coef_mean == nullptr) &&
+                      (coef_a == nullptr) == (gscale == nullptr),
+                  VITTA_E_BADARG, "ln_bwd: hook coefficients must come as (a, b, mean, gscale)");
+  VITTA_CHECK_ARG(aligned16(gy) && aligned16(x) && aligned16(gx) && aligned16(ws) && (!gadd || aligned16(gadd)),
+                  VITTA_E_ALIGN, "ln_bwd: tensors must be 16-byte aligned");
+  LnBwdArgs p;
+  int rc = ln_check_gather(gather, C, rows, &p.g);
+  if (rc) return rc;
+  VITTA_CHECK_ARG(!(p.g.merge && gadd), VITTA_E_BADARG, "ln_bwd: gadd is not available in merge mode");
+  p.gy = gy; p.x = x; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.gadd = gadd;
+  p.ca = coef_a; p.cb = coef_b; p.cm = coef_mean; p.gs = gscale;
+  p.gx = gx; p.dgamma = dgamma; p.dbeta = dbeta; p.ws = ws; p.rows = rows; p.C = C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.g.merge && ((p.g.H & 1) || (p.g.W & 1))) {
+    // odd extents: every source element is still written exactly once (the padded ones do not exist)
+  }
+  const unsigned grid = (unsigned)ln_bwd_grid(rows);
+  switch (ln_vpl(C)) {
+    case 1: ln_bwd_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 2: ln_bwd_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 4: ln_bwd_kernel<4><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 8: ln_bwd_kernel<8><<<grid, kLnThreads, 0, st>>>(p); break;
+    default: ln_bwd_kernel<16><<<grid, kLnThreads, 0, st>>>(p); break;
+  }
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int64_t vitta_colsum_ws_floats(int64_t rows, int C) {
+  if (rows <= 0 || C <= 0) return -1;
+  return (int64_t)(148 * 2 + 1) * C + kWsHeader;
+}
+
+int vitta_colsum(const float* x, int64_t rows, int C, float* out, int accumulate, float* ws, void* stream) {
+  VITTA_CHECK_ARG(x && out && ws && rows > 0 && C > 0 && C % 4 == 0 && C <= 128 * kWsHeader, VITTA_E_BADARG,
+                  "colsum: bad arguments");
+  VITTA_CHECK_ARG(aligned16(x) && aligned16(ws), VITTA_E_ALIGN, "colsum: tensors must be 16-byte aligned");
+  const int ctiles = (C + 127) / 128;
+  int64_t gx = (rows + 63) / 64;
+  int64_t cap = (148 * 2 + ctiles - 1) / ctiles;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)ctiles);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, ws, rows, C, accumulate);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_frame_mean(const float* x, int64_t frames, int rows, int C, float* out, void* stream) {
+  VITTA_CHECK_ARG(x && out && frames > 0 && rows > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "frame_mean: bad arguments");
+  VITTA_CHECK_ARG(aligned16(x) && aligned16(out), VITTA_E_ALIGN, "frame_mean: tensors must be 16-byte aligned");
+  dim3 grid((unsigned)frames, (unsigned)((C + 127) / 128));
+  frame_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, rows, C);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_frame_mean_bwd(const float* g, int64_t frames, int rows, int C, float* gx, void* stream) {
+  VITTA_CHECK_ARG(g && gx && frames > 0 && rows > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "frame_mean_bwd: bad arguments");
+  const int64_t n4 = frames * rows * (C / 4);
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  frame_mean_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, gx, n4, rows, C / 4);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_row_scale(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
+                    void* stream) {
+  VITTA_CHECK_ARG(x && scale && out && rows > 0 && rows_per_group > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG,
+                  "row_scale: bad arguments");
+  const int64_t n4 = rows * (C / 4);
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  row_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, scale, out, n4, C / 4, rows_per_group);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_patchify3d(const float* video, int B, int T, int H, int W, int pt, int ph, int pw, float* out, void* stream) {
+  VITTA_CHECK_ARG(video && out && B > 0 && T > 0 && H > 0 && W > 0 && pt > 0 && ph > 0, VITTA_E_BADARG,
+                  "patchify3d: bad arguments");
+  VITTA_CHECK_ARG(pw == 4 && W % 4 == 0 && T % pt == 0 && H % ph == 0, VITTA_E_UNSUPPORTED,
+                  "patchify3d: patch width must be 4 and the clip a multiple of the patch (swin_transformer.py:440-446 pads "
+                  "otherwise; pad on the host)");
+  VITTA_CHECK_ARG(aligned16(video) && aligned16(out), VITTA_E_ALIGN, "patchify3d: tensors must be 16-byte aligned");
+  const int64_t n4 = (int64_t)B * (T / pt) * (H / ph) * (W / 4) * 3 * pt * ph;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  patchify3d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, out, B, T, H, W, pt, ph);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,719 @@
+// K7: Video-Swin 3-D (shifted-)window multi-head self-attention, head_dim 32, fp32-grade (3xTF32) on tcgen05.
+//
+//   replaces WindowAttention3D.forward's core (swin_transformer.py:145-166) AND the data movement around it in
+//   SwinTransformerBlock3D.forward_part1 (:229-248): torch.roll, window_partition, the qkv permute, the relative-position
+//   bias gather, the (0 / -100) shift mask tensor, softmax, attn @ v, window_reverse and the roll back.  All of those are
+//   index maps here: a work item = (batch, window, head); its N = Wd*Wh*Ww tokens are gathered straight from the
+//   (B, D, H, W, 3, heads, 32) qkv tensor with the cyclic shift folded into the addresses, and the output rows are
+//   scattered back to their un-shifted token positions.
+//
+// Forward kernel (288 threads, 1 CTA / SM, persistent over a contiguous item range, head-major so the bias table of a
+// head is loaded once):
+//   warps 4-7  loaders: gather K (whole window), per 128-row tile Q (pre-scaled), per 32-key chunk V; split every value
+//              into tf32 hi / lo and store both in the UMMA shared-memory layouts (K-major SWIZZLE_128B for Q, K, P;
+//              MN-major SWIZZLE_128B_BASE32B for V)
+//   warp  8    one thread issues tcgen05.mma.kind::tf32:  S[128 x N] = Q K^T  (3 MMAs per k-step: lo*hi, hi*lo, hi*hi)
+//              into TMEM columns [0, 400), then per key chunk  O[128 x 32] += P_chunk V_chunk  into columns [400, 432)
+//   warps 0-3  softmax: thread = query row = TMEM lane.  pass 1 adds bias[rel(i, j)] and the shift mask to S in place
+//              (tcgen05.ld / tcgen05.st) and finds the row maximum; pass 2 exponentiates, accumulates the row sum and
+//              writes P (hi / lo) chunk by chunk for the PV MMAs; finally O / rowsum is written out with log-sum-exp.
+//   The whole score row lives in TMEM, so there is no online-softmax rescaling and the N x N matrix never touches HBM.
+// Backward (v0): fp32 FFMA2 kernel, one CTA per item with Q, K, V, dO resident in shared memory (see wmsa3d_bwd_kernel).
+#include "tc05.cuh"
+
+namespace vitta {
+
+constexpr int kAtThreads = 288;
+constexpr int kAtMaxKeys = 400;     // 392 padded to a multiple of 16 (UMMA N granularity)
+constexpr int kAtMaxRel = 2560;     // (2*8-1)*(2*7-1)*(2*7-1) = 2535 table rows
+
+struct WmsaGeom {
+  int B, D, H, W, heads;
+  int ws0, ws1, ws2;   // window, clamped to the volume (get_window_size, swin_transformer.py:71-84)
+  int ss0, ss1, ss2;   // cyclic shift, clamped the same way (0 where the window covers the dimension)
+  int fw0, fw1, fw2;   // configured window: geometry of relative_position_index[:N, :N] (:113-125, :148-149)
+  int nw0, nw1, nw2;   // windows per dimension
+  int N;               // tokens per window
+  int NP;              // N rounded up to 16
+  int nrel;            // rows of the bias table
+};
+
+// per-token bookkeeping of one window: source token offset and packed (relative-index base | region id << 16)
+__device__ __forceinline__ void window_token(const WmsaGeom& g, int b, int wd, int wh, int ww, int i, int& tok, int& info) {
+  if (i >= g.N) {
+    tok = -1;
+    info = (int)0x80000000;
+    return;
+  }
+  const int hw = g.ws1 * g.ws2;
+  const int a = i / hw, rem = i - a * hw;
+  const int bb = rem / g.ws2, cc = rem - bb * g.ws2;
+  const int p0 = wd * g.ws0 + a, p1 = wh * g.ws1 + bb, p2 = ww * g.ws2 + cc;   // position in the rolled volume
+  // region ids of compute_mask (swin_transformer.py:316-329)
+  const int r0 = g.ss0 ? (p0 < g.D - g.ws0 ? 0 : (p0 < g.D - g.ss0 ? 1 : 2)) : 0;
+  const int r1 = g.ss1 ? (p1 < g.H - g.ws1 ? 0 : (p1 < g.H - g.ss1 ? 1 : 2)) : 0;
+  const int r2 = g.ss2 ? (p2 < g.W - g.ws2 ? 0 : (p2 < g.W - g.ss2 ? 1 : 2)) : 0;
+  int s0 = p0 + g.ss0, s1 = p1 + g.ss1, s2 = p2 + g.ss2;                       // torch.roll(x, -shift): source index
+  if (s0 >= g.D) s0 -= g.D;
+  if (s1 >= g.H) s1 -= g.H;
+  if (s2 >= g.W) s2 -= g.W;
+  tok = ((b * g.D + s0) * g.H + s1) * g.W + s2;
+  const int fhw = g.fw1 * g.fw2;
+  const int fd = i / fhw, fr = i - fd * fhw;
+  const int fh = fr / g.fw2, fw = fr - fh * g.fw2;
+  const int bj = (fd * (2 * g.fw1 - 1) + fh) * (2 * g.fw2 - 1) + fw;
+  info = bj | ((r0 * 9 + r1 * 3 + r2) << 16);
+}
+__device__ __forceinline__ int rel_row_base(const WmsaGeom& g) {
+  return ((g.fw0 - 1) * (2 * g.fw1 - 1) + (g.fw1 - 1)) * (2 * g.fw2 - 1) + (g.fw2 - 1);
+}
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int q) {   // K-major SWIZZLE_128B, 128-B rows, q = float4 index
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((q ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t mn32_off(int row, int q) {    // MN-major SWIZZLE_128B_BASE32B, 128-B rows
+  return (uint32_t)(row * 128 + (((((q >> 1) ^ (row & 3)) << 1) | (q & 1)) << 4));
+}
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// shared memory plan of the forward kernel (bytes from the 1024-aligned base)
+// ------------------------------------------------------------------------------------------------
+constexpr int kOffKhi = 0;
+constexpr int kOffKlo = kOffKhi + kAtMaxKeys * 128;      //  51200
+constexpr int kOffQhi = kOffKlo + kAtMaxKeys * 128;      // 102400
+constexpr int kOffQlo = kOffQhi + 128 * 128;             // 118784
+constexpr int kOffP = kOffQlo + 128 * 128;               // 135168: 2 stages x (hi 16 KB, lo 16 KB)
+constexpr int kOffV = kOffP + 2 * 32768;                 // 200704: 2 stages x (hi 4 KB, lo 4 KB)
+constexpr int kOffTab = kOffV + 2 * 8192;                // 217088: bias table of the current head
+constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;        // 227328
+constexpr int kOffTok = kOffInfo + kAtMaxKeys * 4;       // 228928
+constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;        // 230528
+constexpr int kAtSmemBytes = kOffBar + 256 + 1024;       // + alignment slack = 231808 <= 232448
+
+struct WmsaFwdParams {
+  const float* qkv;     // (B, D, H, W, 3, heads, 32)
+  const float* table;   // (nrel, heads)
+  float* out;           // (B, D, H, W, heads*32)
+  float* lse;           // ((b*nW + w)*heads + head)*N + i
+  float scale;
+  int items, items_per_cta;
+  WmsaGeom g;
+};
+
+enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_READY1, B_V_FREE0, B_V_FREE1, B_S_FULL,
+       B_S_FREE, B_P_READY0, B_P_READY1, B_P_FREE0, B_P_FREE1, B_O_FULL, B_O_FREE, B_COUNT };
+
+__global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+  float* tab = reinterpret_cast<float*>(smem + kOffTab);
+  int* info = reinterpret_cast<int*>(smem + kOffInfo);
+  int* tok = reinterpret_cast<int*>(smem + kOffTok);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const WmsaGeom& g = p.g;
+  const int C = g.heads * 32;
+  const int nwin = g.nw0 * g.nw1 * g.nw2;
+  const int nwin_total = g.B * nwin;
+  const int n_tiles = (g.N + 127) >> 7;
+  const int n_chunks = (g.N + 31) >> 5;
+  const int item0 = blockIdx.x * p.items_per_cta;
+  const int item1 = min(p.items, item0 + p.items_per_cta);
+
+  if (threadIdx.x == 0) {
+    const int counts[B_COUNT] = {4, 1, 4, 4, 1, 4, 4, 1, 1, 1, 4, 4, 4, 1, 1, 1, 4};
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================== loaders ===========================
+    const int lt = threadIdx.x - 128;
+    const int rslot = lt >> 3, q4 = lt & 7;
+    int cur_head = -1;
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      const int wg = item - head * nwin_total;
+      const int b = wg / nwin;
+      int w = wg - b * nwin;
+      const int ww = w % g.nw2; w /= g.nw2;
+      const int wh = w % g.nw1;
+      const int wd = w / g.nw1;
+      mbar_wait(&bar[B_KV_FREE], (it & 1) ^ 1);
+      mbar_wait(&bar[B_TAB_FREE], (it & 1) ^ 1);
+      for (int i = lt; i < g.NP; i += 128) {
+        int t, f;
+        window_token(g, b, wd, wh, ww, i, t, f);
+        tok[i] = t;
+        info[i] = f;
+      }
+      if (head != cur_head) {
+        for (int i = lt; i < g.nrel; i += 128) tab[i] = __ldg(p.table + (int64_t)i * g.heads + head);
+        cur_head = head;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // tok[] complete (loader warps only)
+      const float* qkv_h = p.qkv + head * 32 + q4 * 4;
+      // ---- K: all keys of the window
+      for (int r = rslot; r < g.NP; r += 16) {
+        const int t = tok[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0) v = ldg4(qkv_h + ((int64_t)t * 3 + 1) * C);
+        float4 h, l;
+        split4(v, h, l);
+        const uint32_t o = sw128_off(r, q4);
+        *reinterpret_cast<float4*>(smem + kOffKhi + o) = h;
+        *reinterpret_cast<float4*>(smem + kOffKlo + o) = l;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_KV_READY]);
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        mbar_wait(&bar[B_Q_FREE], (tile_ctr & 1) ^ 1);
+        for (int r = rslot; r < 128; r += 16) {
+          const int i = tile * 128 + r;
+          const int t = (i < g.N) ? tok[i] : -1;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0) {
+            v = ldg4(qkv_h + (int64_t)t * 3 * C);
+            v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;   // q = q * scale (:146)
+          }
+          float4 h, l;
+          split4(v, h, l);
+          const uint32_t o = sw128_off(r, q4);
+          *reinterpret_cast<float4*>(smem + kOffQhi + o) = h;
+          *reinterpret_cast<float4*>(smem + kOffQlo + o) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_Q_READY]);
+        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          const int st = chunk_ctr & 1;
+          mbar_wait(&bar[B_V_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          uint8_t* vb = smem + kOffV + st * 8192;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = rslot + rr * 16;
+            const int j = c * 32 + r;
+            const int t = (j < g.N) ? tok[j] : -1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0) v = ldg4(qkv_h + ((int64_t)t * 3 + 2) * C);
+            float4 h, l;
+            split4(v, h, l);
+            const uint32_t o = mn32_off(r, q4);
+            *reinterpret_cast<float4*>(vb + o) = h;
+            *reinterpret_cast<float4*>(vb + 4096 + o) = l;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_V_READY0 + st]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    const int part0 = g.NP < 256 ? g.NP : 256;
+    const int part1 = g.NP - part0;
+    const uint32_t idesc_s0 = umma_idesc_tf32(128, part0);
+    const uint32_t idesc_s1 = part1 ? umma_idesc_tf32(128, part1) : 0;
+    const uint32_t idesc_o = umma_idesc_tf32(128, 32) | (1u << 16);   // B (= V) is MN-major
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        if (tile == 0) mbar_wait(&bar[B_KV_READY], it & 1);
+        mbar_wait(&bar[B_Q_READY], tile_ctr & 1);
+        mbar_wait(&bar[B_S_FREE], (tile_ctr & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t q_hi = umma_desc_sw128(sbase + kOffQhi), q_lo = umma_desc_sw128(sbase + kOffQlo);
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            if (part == 1 && part1 == 0) break;
+            const uint32_t koff = part ? 256 * 128 : 0;
+            const uint64_t k_hi = umma_desc_sw128(sbase + kOffKhi + koff), k_lo = umma_desc_sw128(sbase + kOffKlo + koff);
+            const uint32_t d = tmem_base + (part ? 256u : 0u);
+            const uint32_t idesc = part ? idesc_s1 : idesc_s0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_tf32(d, q_lo + adv, k_hi + adv, idesc, k != 0);
+              umma_tf32(d, q_hi + adv, k_lo + adv, idesc, 1);
+              umma_tf32(d, q_hi + adv, k_hi + adv, idesc, 1);
+            }
+          }
+          umma_commit(&bar[B_Q_FREE]);
+          if (tile == n_tiles - 1) umma_commit(&bar[B_KV_FREE]);
+          umma_commit(&bar[B_S_FULL]);
+        }
+        __syncwarp();
+        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          const int st = chunk_ctr & 1;
+          const uint32_t par = (chunk_ctr >> 1) & 1;
+          mbar_wait(&bar[B_P_READY0 + st], par);
+          mbar_wait(&bar[B_V_READY0 + st], par);
+          if (c == 0) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t pb = sbase + kOffP + st * 32768, vb = sbase + kOffV + st * 8192;
+            const uint64_t p_hi = umma_desc_sw128(pb), p_lo = umma_desc_sw128(pb + 16384);
+            const uint64_t v_hi = umma_desc_mn_sw128(vb, 4096), v_lo = umma_desc_mn_sw128(vb + 4096, 4096);
+            const int left = g.N - c * 32;
+            const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
+            const uint32_t d = tmem_base + 400u;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
+              umma_tf32(d, p_lo + adva, v_hi + advb, idesc_o, (c | k) != 0);
+              umma_tf32(d, p_hi + adva, v_lo + advb, idesc_o, 1);
+              umma_tf32(d, p_hi + adva, v_hi + advb, idesc_o, 1);
+            }
+            umma_commit(&bar[B_P_FREE0 + st]);
+            umma_commit(&bar[B_V_FREE0 + st]);
+            if (c == n_chunks - 1) umma_commit(&bar[B_O_FULL]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =========================== softmax / epilogue (thread = query row = TMEM lane) ===========================
+    const int row = threadIdx.x;   // 0..127
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int rel0 = rel_row_base(g);
+    constexpr float kLog2e = 1.4426950408889634f;
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      const int wg = item - head * nwin_total;
+      mbar_wait(&bar[B_KV_READY], it & 1);   // tab / info / tok of this item are in place
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        const int i = tile * 128 + row;
+        const bool valid = i < g.N;
+        const int fi = info[valid ? i : 0];
+        const int a_i = (fi & 0xffff) + rel0;
+        const int r_i = (fi >> 16) & 0x1f;
+        const int my_tok = tok[valid ? i : 0];   // read before TAB_FREE is released (the loaders reuse tok[] / info[])
+        mbar_wait(&bar[B_S_FULL], tile_ctr & 1);
+        tc_fence_after();
+        // ---- pass 1: s += bias + mask (in place), row maximum
+        float m = -INFINITY;
+        for (int c0 = 0; c0 < g.NP; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_lane + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int fj = info[c0 + jj];
+            float s = __uint_as_float(r[jj]) + tab[a_i - (fj & 0xffff)];
+            s += (((fj >> 16) & 0x1f) != r_i) ? -100.f : 0.f;
+            s = (fj < 0) ? -INFINITY : s;
+            m = fmaxf(m, s);
+            r[jj] = __float_as_uint(s);
+          }
+          tmem_st16(t_lane + (uint32_t)c0, r);
+        }
+        tmem_st_wait();
+        if (tile == n_tiles - 1) {   // last use of tab / info by this warp for this item
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_TAB_FREE]);
+        }
+        // ---- pass 2: p = exp(s - m), row sum, P chunks for the PV MMAs
+        float l = 0.f;
+        const float mb = m * kLog2e;
+        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          const int st = chunk_ctr & 1;
+          uint32_t r[32];
+          const int cols = min(32, g.NP - c * 32);
+          tmem_ld16(t_lane + (uint32_t)(c * 32), r);
+          if (cols > 16) tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
+          tmem_ld_wait();
+          mbar_wait(&bar[B_P_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          uint8_t* pb = smem + kOffP + st * 32768;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v;
+            v.x = (q * 4 + 0 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 0]), kLog2e, -mb)) : 0.f;
+            v.y = (q * 4 + 1 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 1]), kLog2e, -mb)) : 0.f;
+            v.z = (q * 4 + 2 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 2]), kLog2e, -mb)) : 0.f;
+            v.w = (q * 4 + 3 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 3]), kLog2e, -mb)) : 0.f;
+            l += (v.x + v.y) + (v.z + v.w);
+            float4 h, lo;
+            split4(v, h, lo);
+            const uint32_t o = sw128_off(row, q);
+            *reinterpret_cast<float4*>(pb + o) = h;
+            *reinterpret_cast<float4*>(pb + 16384 + o) = lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_P_READY0 + st]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_S_FREE]);
+        // ---- O / l -> global
+        mbar_wait(&bar[B_O_FULL], tile_ctr & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32(t_lane + 400u, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_O_FREE]);
+        if (valid) {
+          const float inv = 1.f / l;
+          float* dst = p.out + (int64_t)my_tok * C + head * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            st4(dst + q * 4, make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
+                                         __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv));
+          p.lse[((int64_t)wg * g.heads + head) * g.N + i] = m + logf(l);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (v0): exact fp32 on the FFMA2 pipe.  One CTA (416 threads) per item; Qs = scale*Q, K, V, dO of the window live
+// in shared memory (broadcast reads), the bias table and its gradient too.
+//   pass A (thread = query i):  dQ_i = scale * sum_j dS_ij K_j,   dTable[rel(i,j)] += dS_ij
+//   pass B (thread = key j):    dK_j = sum_i dS_ij Qs_i,          dV_j = sum_i P_ij dO_i
+//   with P_ij = exp(S_ij - lse_i), dS_ij = P_ij (dO_i . V_j - dO_i . O_i)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAtBwdThreads = 416;
+
+struct WmsaBwdParams {
+  const float* qkv;
+  const float* table;
+  const float* out;     // forward output (B, D, H, W, C)
+  const float* dout;    // gradient of it
+  const float* lse;
+  float* dqkv;          // (B, D, H, W, 3, heads, 32), every element written exactly once
+  float* dtable;        // (nrel, heads), accumulated with red.global.add
+  float scale;
+  int items, items_per_cta;
+  WmsaGeom g;
+};
+
+constexpr int kBwRows = 392;
+constexpr int kBwOffQ = 0;
+constexpr int kBwOffK = kBwOffQ + kBwRows * 128;
+constexpr int kBwOffV = kBwOffK + kBwRows * 128;
+constexpr int kBwOffDO = kBwOffV + kBwRows * 128;
+constexpr int kBwOffTab = kBwOffDO + kBwRows * 128;        // 200704
+constexpr int kBwOffDTab = kBwOffTab + kAtMaxRel * 4;
+constexpr int kBwOffLse = kBwOffDTab + kAtMaxRel * 4;
+constexpr int kBwOffDsum = kBwOffLse + kAtMaxKeys * 4;
+constexpr int kBwOffInfo = kBwOffDsum + kAtMaxKeys * 4;
+constexpr int kBwOffTok = kBwOffInfo + kAtMaxKeys * 4;
+constexpr int kBwSmemBytes = kBwOffTok + kAtMaxKeys * 4 + 16;   // 227600
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__global__ void __maxnreg__(152) wmsa3d_bwd_kernel(const WmsaBwdParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* sQ = reinterpret_cast<float*>(smem + kBwOffQ);
+  float* sK = reinterpret_cast<float*>(smem + kBwOffK);
+  float* sV = reinterpret_cast<float*>(smem + kBwOffV);
+  float* sDO = reinterpret_cast<float*>(smem + kBwOffDO);
+  float* tab = reinterpret_cast<float*>(smem + kBwOffTab);
+  float* dtab = reinterpret_cast<float*>(smem + kBwOffDTab);
+  float* sLse = reinterpret_cast<float*>(smem + kBwOffLse);
+  float* sDs = reinterpret_cast<float*>(smem + kBwOffDsum);
+  int* info = reinterpret_cast<int*>(smem + kBwOffInfo);
+  int* tok = reinterpret_cast<int*>(smem + kBwOffTok);
+  const WmsaGeom& g = p.g;
+  const int tid = threadIdx.x;
+  const int C = g.heads * 32;
+  const int nwin = g.nw0 * g.nw1 * g.nw2;
+  const int nwin_total = g.B * nwin;
+  const int rel0 = rel_row_base(g);
+  const int item0 = blockIdx.x * p.items_per_cta;
+  const int item1 = min(p.items, item0 + p.items_per_cta);
+  int cur_head = -1;
+
+  auto flush_dtab = [&](int head) {
+    for (int i = tid; i < g.nrel; i += kAtBwdThreads) {
+      const float v = dtab[i];
+      if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + head, v);
+    }
+  };
+
+  for (int item = item0; item < item1; ++item) {
+    const int head = item / nwin_total;
+    const int wg = item - head * nwin_total;
+    const int b = wg / nwin;
+    int w = wg - b * nwin;
+    const int ww = w % g.nw2; w /= g.nw2;
+    const int wh = w % g.nw1;
+    const int wd = w / g.nw1;
+    __syncthreads();   // previous item fully consumed
+    if (head != cur_head) {
+      if (cur_head >= 0) flush_dtab(cur_head);
+      __syncthreads();
+      for (int i = tid; i < g.nrel; i += kAtBwdThreads) {
+        tab[i] = __ldg(p.table + (int64_t)i * g.heads + head);
+        dtab[i] = 0.f;
+      }
+      cur_head = head;
+    }
+    for (int i = tid; i < g.N; i += kAtBwdThreads) {
+      int t, f;
+      window_token(g, b, wd, wh, ww, i, t, f);
+      tok[i] = t;
+      info[i] = f;
+      sLse[i] = __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i);
+    }
+    __syncthreads();
+    // cooperative gather: 8 lanes per row
+    {
+      const int rslot = tid >> 3, q4 = tid & 7;   // 52 row slots
+      for (int r0 = 0; r0 < g.N; r0 += kAtBwdThreads / 8) {   // uniform trip count: the shuffles below need full warps
+        const int r = (r0 + rslot < g.N) ? r0 + rslot : g.N - 1;
+        const bool own = r0 + rslot < g.N;
+        const int64_t t = tok[r];
+        const float* base = p.qkv + t * 3 * C + head * 32 + q4 * 4;
+        float4 q = ldg4(base);
+        q.x *= p.scale; q.y *= p.scale; q.z *= p.scale; q.w *= p.scale;
+        const float4 dO = ldg4(p.dout + t * C + head * 32 + q4 * 4);
+        const float4 O = ldg4(p.out + t * C + head * 32 + q4 * 4);
+        if (own) {
+          *reinterpret_cast<float4*>(sQ + r * 32 + q4 * 4) = q;
+          *reinterpret_cast<float4*>(sK + r * 32 + q4 * 4) = ldg4(base + C);
+          *reinterpret_cast<float4*>(sV + r * 32 + q4 * 4) = ldg4(base + 2 * C);
+          *reinterpret_cast<float4*>(sDO + r * 32 + q4 * 4) = dO;
+        }
+        float d = (dO.x * O.x + dO.y * O.y) + (dO.z * O.z + dO.w * O.w);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (q4 == 0 && own) sDs[r] = d;
+      }
+    }
+    __syncthreads();
+    const bool act = tid < g.N;
+    const int me = act ? tid : 0;
+    const int f_me = info[me];
+    const int b_me = f_me & 0xffff;
+    const int r_me = (f_me >> 16) & 0x1f;
+    // ---------------- pass A: thread = query row ----------------
+    {
+      float2 q[16], d_o[16], dq[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        q[k] = *reinterpret_cast<const float2*>(sQ + me * 32 + k * 2);
+        d_o[k] = *reinterpret_cast<const float2*>(sDO + me * 32 + k * 2);
+        dq[k] = make_float2(0.f, 0.f);
+      }
+      const float lse_i = sLse[me], dsum_i = sDs[me];
+      const int a_i = b_me + rel0;
+      for (int j = 0; j < g.N; ++j) {
+        const float2* kj = reinterpret_cast<const float2*>(sK + j * 32);
+        const float2* vj = reinterpret_cast<const float2*>(sV + j * 32);
+        float2 kr[16];
+        float2 s2 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          kr[k] = kj[k];
+          s2 = ffma2(q[k], kr[k], s2);
+          p2 = ffma2(d_o[k], vj[k], p2);
+        }
+        const int fj = info[j];
+        const int idx = a_i - (fj & 0xffff);
+        float s = (s2.x + s2.y) + tab[idx];
+        s += (((fj >> 16) & 0x1f) != r_me) ? -100.f : 0.f;
+        const float pij = expf(s - lse_i);
+        const float ds = pij * ((p2.x + p2.y) - dsum_i);
+        const float2 ds2 = make_float2(ds, ds);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dq[k] = ffma2(ds2, kr[k], dq[k]);
+        if (act) atomicAdd(&dtab[idx], ds);
+      }
+      if (act) {
+        float* dst = p.dqkv + (int64_t)tok[me] * 3 * C + head * 32;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          st4(dst + k * 4, make_float4(dq[2 * k].x * p.scale, dq[2 * k].y * p.scale, dq[2 * k + 1].x * p.scale,
+                                       dq[2 * k + 1].y * p.scale));
+      }
+    }
+    // ---------------- pass B: thread = key row ----------------
+    {
+      float2 kk[16], vv[16], dk[16], dv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        kk[k] = *reinterpret_cast<const float2*>(sK + me * 32 + k * 2);
+        vv[k] = *reinterpret_cast<const float2*>(sV + me * 32 + k * 2);
+        dk[k] = dv[k] = make_float2(0.f, 0.f);
+      }
+      for (int i = 0; i < g.N; ++i) {
+        const float2* qi = reinterpret_cast<const float2*>(sQ + i * 32);
+        const float2* doi = reinterpret_cast<const float2*>(sDO + i * 32);
+        float2 s2 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          s2 = ffma2(qi[k], kk[k], s2);
+          p2 = ffma2(doi[k], vv[k], p2);
+        }
+        const int fi = info[i];
+        float s = (s2.x + s2.y) + tab[(fi & 0xffff) + rel0 - b_me];
+        s += (((fi >> 16) & 0x1f) != r_me) ? -100.f : 0.f;
+        const float pij = expf(s - sLse[i]);
+        const float ds = pij * ((p2.x + p2.y) - sDs[i]);
+        const float2 ds2 = make_float2(ds, ds), pp2 = make_float2(pij, pij);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {   // rows re-read from shared memory (broadcast) instead of held in registers
+          dk[k] = ffma2(ds2, qi[k], dk[k]);
+          dv[k] = ffma2(pp2, doi[k], dv[k]);
+        }
+      }
+      if (act) {
+        float* dst = p.dqkv + ((int64_t)tok[me] * 3 + 1) * C + head * 32;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          st4(dst + k * 4, make_float4(dk[2 * k].x, dk[2 * k].y, dk[2 * k + 1].x, dk[2 * k + 1].y));
+          st4(dst + C + k * 4, make_float4(dv[2 * k].x, dv[2 * k].y, dv[2 * k + 1].x, dv[2 * k + 1].y));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (cur_head >= 0) flush_dtab(cur_head);
+}
+
+static int wmsa_geom(int B, int D, int H, int W, int heads, const int* window, const int* shift, WmsaGeom* g) {
+  VITTA_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && heads > 0 && window && shift, VITTA_E_BADARG, "wmsa3d: bad shape");
+  const int dims[3] = {D, H, W};
+  int ws[3], ss[3];
+  for (int i = 0; i < 3; ++i) {
+    VITTA_CHECK_ARG(window[i] > 0 && shift[i] >= 0 && shift[i] < window[i], VITTA_E_BADARG, "wmsa3d: bad window / shift");
+    ws[i] = window[i];
+    ss[i] = shift[i];
+    if (dims[i] <= window[i]) {   // get_window_size (swin_transformer.py:71-84)
+      ws[i] = dims[i];
+      ss[i] = 0;
+    }
+    VITTA_CHECK_ARG(dims[i] % ws[i] == 0, VITTA_E_UNSUPPORTED,
+                    "wmsa3d: the token volume must be a multiple of the window (the zero-padding branch of "
+                    "swin_transformer.py:222-227 is not implemented)");
+  }
+  g->B = B; g->D = D; g->H = H; g->W = W; g->heads = heads;
+  g->ws0 = ws[0]; g->ws1 = ws[1]; g->ws2 = ws[2];
+  g->ss0 = ss[0]; g->ss1 = ss[1]; g->ss2 = ss[2];
+  g->fw0 = window[0]; g->fw1 = window[1]; g->fw2 = window[2];
+  g->nw0 = D / ws[0]; g->nw1 = H / ws[1]; g->nw2 = W / ws[2];
+  g->N = ws[0] * ws[1] * ws[2];
+  g->NP = (g->N + 15) / 16 * 16;
+  g->nrel = (2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1);
+  VITTA_CHECK_ARG(g->N <= 392 && g->NP <= kAtMaxKeys && g->nrel <= kAtMaxRel, VITTA_E_UNSUPPORTED,
+                  "wmsa3d: windows of at most 392 tokens / 2560 relative positions");
+  VITTA_CHECK_ARG((int64_t)B * D * H * W < (1ll << 31) / 4, VITTA_E_UNSUPPORTED, "wmsa3d: too many tokens");
+  return 0;
+}
+
+}  // namespace vitta
+
+using namespace vitta;
+
+extern "C" {
+
+int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                     int heads, int head_dim, const int* window, const int* shift, float scale, void* stream) {
+  VITTA_CHECK_ARG(qkv && bias_table && out && lse, VITTA_E_BADARG, "wmsa3d_fwd: null pointer");
+  VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
+  VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out), VITTA_E_ALIGN, "wmsa3d_fwd: tensors must be 16-byte aligned");
+  WmsaFwdParams p;
+  int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
+  if (rc) return rc;
+  p.qkv = qkv; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale;
+  p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("wmsa3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  const int sms = cached_sm_count();
+  int grid = p.items < sms ? p.items : sms;
+  p.items_per_cta = (p.items + grid - 1) / grid;
+  grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
+  wmsa3d_fwd_kernel<<<grid, kAtThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
+                     float* dqkv, float* dbias_table, int B, int D, int H, int W, int heads, int head_dim,
+                     const int* window, const int* shift, float scale, void* stream) {
+  VITTA_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, VITTA_E_BADARG, "wmsa3d_bwd: null pointer");
+  VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
+  VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), VITTA_E_ALIGN,
+                  "wmsa3d_bwd: tensors must be 16-byte aligned");
+  WmsaBwdParams p;
+  int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
+  if (rc) return rc;
+  p.qkv = qkv; p.table = bias_table; p.out = out; p.dout = dout; p.lse = lse; p.dqkv = dqkv; p.dtable = dbias_table;
+  p.scale = scale;
+  p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("wmsa3d_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  const int sms = cached_sm_count();
+  int grid = p.items < sms ? p.items : sms;
+  p.items_per_cta = (p.items + grid - 1) / grid;
+  grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
+  wmsa3d_bwd_kernel<<<grid, kAtBwdThreads, kBwSmemBytes, (cudaStream_t)stream>>>(p);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

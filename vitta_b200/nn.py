@@ -14,6 +14,35 @@ class StatsBatchNorm2d(nn.BatchNorm2d):
     _vitta_tap = None
 
 
+class StatsLayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state-dict keys) that can host a statistics tap.  The vitta_b200 Swin modules
+    call :func:`layer_norm` instead of the module, which runs the fused sm_100a kernel (K9) when that is legal."""
+    _vitta_fused = True
+    _vitta_tap = None
+
+
+def layer_norm(ln, x, want_alias=True):
+    """x: (..., C) contiguous tokens -> (normalised rows (rows, C), alias of x as rows for the shortcut).
+    Fused path: LayerNorm + the statistics partials of an attached tap in one pass; its backward adds the hook
+    gradient and the shortcut gradient.  With foreign forward hooks on the module the module itself is called so that
+    every hook observes the reference's tensors (``(B, D, H, W, C)`` output)."""
+    from . import ops_swin
+    c = x.shape[-1]
+    if (isinstance(ln, StatsLayerNorm) and not ln._forward_hooks and not ln._forward_pre_hooks and x.is_cuda
+            and ln.elementwise_affine):
+        arena = ly = None
+        tap = ln._vitta_tap
+        if tap is not None:
+            arena, ly = tap.tap_target()
+            tap.note_batch(x.shape[0])
+        rows = x.reshape(-1, c)
+        if not rows.is_contiguous():
+            rows = rows.contiguous()
+        return ops_swin.layer_norm_rows(rows, ln.weight, ln.bias, ln.eps, arena, ly, want_alias)
+    y = ln(x)
+    return y.reshape(-1, c), (x.reshape(-1, c) if want_alias else None)
+
+
 def _fusable(bn):
     return (bn is not None and isinstance(bn, StatsBatchNorm2d) and not bn.training and not bn._forward_hooks
             and not bn._forward_pre_hooks)

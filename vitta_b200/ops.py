@@ -122,16 +122,17 @@ class StatsArena:
         self.desc_dirty = True
 
     # -- forward side ---------------------------------------------------------------------------
-    def partial_buffer(self, ly, O, Cc, I, frames, dev):
-        """Return the (mean, M2) partial buffer of a layer for this forward, starting a new step if needed."""
+    def partial_buffer(self, ly, O, Cc, I, frames, dev, ln=False):
+        """Return the (mean, M2) partial buffer of a layer for this forward, starting a new step if needed.
+        ``ln``: the partials come from the LayerNorm kernel (K9), whose chunks are vitta_ln_chunking's."""
         self._freeze(dev)
         if self.finalized:
             self.finalized = False
             for l2 in self.layers:
                 l2.fired = False
-        key = (O, Cc, I, frames)
+        key = (O, Cc, I, frames, ln)
         if ly.geom_key != key:
-            ch = _lib.chunking(O, Cc, I, frames)
+            ch = _lib.ln_chunking(O, Cc, True) if ln else _lib.chunking(O, Cc, I, frames)
             ly.chunking = ch
             ly.geom_key = key
             ly.part = torch.empty(ch.n_entries * Cc * 2, dtype=torch.float32, device=dev)

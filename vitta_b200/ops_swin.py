@@ -1,0 +1,347 @@
+"""Autograd operators of the Video-Swin path over the C-ABI kernels (include/vitta_b200.h: K7, K8, K9).
+
+Every operator works on the token matrix ``(rows, C)`` of a ``(B, D, H, W, C)`` activation, fp32, CUDA.  The
+composite Functions (attention half-block, MLP half-block, PatchMerging, PatchEmbed3D) keep their intermediate
+tensors inside one autograd node so that epilogues can be fused (bias / GELU / shortcut / DropPath in the GEMM
+store, GELU' in the data-gradient GEMM, the hook gradient and the shortcut gradient in the LayerNorm backward).
+No eager-torch arithmetic fallback exists: a missing library raises in ``_lib.load()``.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import call, ptr, stream_ptr
+
+
+def _chk(t, what):
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise _lib.VittaError("%s: vitta_b200 kernels need fp32 CUDA tensors (got %s %s); there is no CPU path"
+                              % (what, t.dtype, t.device))
+
+
+_ws = {}
+
+
+def _workspace(kind, n, dev, zero):
+    key = (kind, dev)
+    w = _ws.get(key)
+    if w is None or w.numel() < n:
+        w = (torch.zeros if zero else torch.empty)(int(n), dtype=torch.float32, device=dev)
+        _ws[key] = w
+    return w
+
+
+# ----------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ----------------------------------------------------------------------------------------------
+def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=None, rows_per_group=1, out=None):
+    """out[M, N] = a[M, K] @ op(w)  with the fused epilogue of vitta_gemm_tf32x3_ex.
+    mode 0: w is (N, K) (forward of nn.Linear);  mode 1: w is (K, N) and its transpose is used (data gradient)."""
+    m, k = a.shape
+    n = w.shape[0] if mode == 0 else w.shape[1]
+    hi, lo = ops.weight_split(w, mode)
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    call("vitta_gemm_tf32x3_ex", ptr(a), a.stride(0), ptr(hi), ptr(lo), k, ptr(out), out.stride(0), m, n, k, ptr(bias),
+         ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale), int(rows_per_group), 0, stream_ptr())
+    return out
+
+
+def linear_wgrad(x, gy):
+    """dW (N, K) = gy[M, N]^T @ x[M, K] on the split-K tcgen05 weight-gradient kernel (a 1x1 'convolution' over M pixels)."""
+    m, k = x.shape
+    n = gy.shape[1]
+    wdt = 8 if m % 8 == 0 else 4 if m % 4 == 0 else 2 if m % 2 == 0 else 1
+    f = m // wdt
+    nws = _lib.load().vitta_conv2d_wgrad_ws_floats(f, 1, wdt, k, n, 1, 1, 1, 0)
+    if nws <= 0:
+        raise _lib.VittaError("linear_wgrad: bad geometry")
+    ws = _workspace("wgrad", nws, x.device, False)
+    gw = torch.empty(n, k, dtype=torch.float32, device=x.device)
+    call("vitta_conv2d_wgrad_tf32x3", ptr(x), ptr(gy), f, 1, wdt, k, n, 1, 1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
+    return gw
+
+
+def colsum(g):
+    rows, c = g.shape
+    n = _lib.load().vitta_colsum_ws_floats(rows, c)
+    ws = _workspace(("colsum", c), n, g.device, True)
+    out = torch.empty(c, dtype=torch.float32, device=g.device)
+    call("vitta_colsum", ptr(g), rows, c, ptr(out), 0, ptr(ws), stream_ptr())
+    return out
+
+
+def row_scale(x, scale, rows_per_group):
+    out = torch.empty_like(x)
+    call("vitta_row_scale", ptr(x), ptr(scale), x.shape[0], int(rows_per_group), x.shape[1], ptr(out), stream_ptr())
+    return out
+
+
+def _gather_struct(gather):
+    if gather is None:
+        return None, None
+    g = _lib.VittaLnGather(*[int(v) for v in gather])
+    return g, C.byref(g)
+
+
+def ln_fwd(x, weight, bias, eps, rows, c, part=None, gather=None):
+    y = torch.empty(rows, c, dtype=torch.float32, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    keep, gp = _gather_struct(gather)
+    call("vitta_ln_fwd", ptr(x), ptr(weight), ptr(bias), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(part), rows, c, gp,
+         stream_ptr())
+    return y, mean, rstd
+
+
+def ln_bwd(gy, x, weight, bias, mean, rstd, rows, c, gadd=None, coef=None, gscale=None, gather=None, gx_shape=None):
+    dev = gy.device
+    n = _lib.load().vitta_ln_bwd_ws_floats(rows, c)
+    ws = _workspace(("ln_bwd", c), n, dev, True)
+    gx = torch.empty(gx_shape if gx_shape is not None else (rows, c), dtype=torch.float32, device=dev)
+    dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
+    ca = cb = cm = gs = None
+    if coef is not None:
+        ca, cb, cm = coef
+        gs = ptr(gscale)
+    keep, gp = _gather_struct(gather)
+    call("vitta_ln_bwd", ptr(gy), ptr(x), ptr(weight), ptr(bias), ptr(mean), ptr(rstd), ptr(gadd), ca, cb, cm, gs, ptr(gx),
+         ptr(dgamma), ptr(dbeta), ptr(ws), rows, c, gp, stream_ptr())
+    return gx, dgamma, dbeta
+
+
+def _int3(v):
+    return (C.c_int * 3)(int(v[0]), int(v[1]), int(v[2]))
+
+
+def wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale):
+    b, d, h, w = dims
+    c = heads * 32
+    out = torch.empty(b * d * h * w, c, dtype=torch.float32, device=qkv.device)
+    lse = torch.empty(b * d * h * w * heads, dtype=torch.float32, device=qkv.device)
+    call("vitta_wmsa3d_fwd", ptr(qkv), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window), _int3(shift),
+         float(scale), stream_ptr())
+    return out, lse
+
+
+def wmsa3d_bwd(qkv, table, out, dout, lse, dims, heads, window, shift, scale):
+    b, d, h, w = dims
+    dqkv = torch.empty_like(qkv)
+    dtable = torch.zeros_like(table)
+    call("vitta_wmsa3d_bwd", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), b, d, h, w, heads,
+         32, _int3(window), _int3(shift), float(scale), stream_ptr())
+    return dqkv, dtable
+
+
+# ----------------------------------------------------------------------------------------------
+# K9: LayerNorm (+ statistics tap) returning the normalised rows AND an alias of the input for the shortcut, so
+# that the backward kernel adds the shortcut gradient itself
+# ----------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, arena, ly, want_alias):
+        _chk(x, "layer_norm")
+        rows, c = x.shape
+        part = None
+        if ly is not None:
+            part = arena.partial_buffer(ly, rows, c, 1, 1, x.device, ln=True)
+        y, mean, rstd = ln_fwd(x, weight, bias, eps, rows, c, part)
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        ctx.meta = (arena, ly, want_alias)
+        tok = ops.new_token(x) if ly is not None else None
+        alias = x.view_as(x) if want_alias else None
+        return y, alias, tok
+
+    @staticmethod
+    def backward(ctx, gy, galias, gtok):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        arena, ly, want_alias = ctx.meta
+        rows, c = x.shape
+        if gy is None:
+            gy = torch.zeros_like(x)
+        gy = gy.contiguous()
+        coef = gs = None
+        if ly is not None and gtok is not None:
+            coef = arena.coef_ptrs(ly)
+            gs = gtok.contiguous()
+        gadd = galias.contiguous() if galias is not None else None
+        gx, dg, db = ln_bwd(gy, x, weight, bias, mean, rstd, rows, c, gadd, coef, gs)
+        return gx, dg, db, None, None, None, None
+
+
+def layer_norm_rows(x, weight, bias, eps, arena=None, ly=None, want_alias=True):
+    y, alias, tok = LayerNormFn.apply(x, weight, bias, eps, arena, ly, want_alias)
+    if ly is not None:
+        ly.token = tok
+    return y, alias
+
+
+# ----------------------------------------------------------------------------------------------
+# K8 + K7: attention half-block   x + DropPath(proj(W-MSA(qkv(y))))
+# ----------------------------------------------------------------------------------------------
+class SwinAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, shortcut, wqkv, bqkv, table, wproj, bproj, dims, heads, window, shift, scale, rscale):
+        _chk(y, "swin_attention")
+        b, d, h, w = dims
+        rows = b * d * h * w
+        qkv = gemm(y, wqkv, 0, bias=bqkv)
+        ao, lse = wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale)
+        out = gemm(ao, wproj, 0, bias=bproj, residual=shortcut, row_scale=rscale, rows_per_group=rows // b)
+        ctx.save_for_backward(y, wqkv, table, wproj, qkv, ao, lse, rscale)
+        ctx.meta = (dims, heads, window, shift, scale, bqkv is not None, bproj is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, wqkv, table, wproj, qkv, ao, lse, rscale = ctx.saved_tensors
+        dims, heads, window, shift, scale, has_bqkv, has_bproj = ctx.meta
+        b = dims[0]
+        g = g.contiguous()
+        rpg = g.shape[0] // b
+        gs = row_scale(g, rscale, rpg) if rscale is not None else g      # gradient of the branch output
+        dao = gemm(gs, wproj, 1)
+        dwproj = linear_wgrad(ao, gs)
+        dbproj = colsum(gs) if has_bproj else None
+        dqkv, dtable = wmsa3d_bwd(qkv, table, ao, dao, lse, dims, heads, window, shift, scale)
+        dy = gemm(dqkv, wqkv, 1)
+        dwqkv = linear_wgrad(y, dqkv)
+        dbqkv = colsum(dqkv) if has_bqkv else None
+        return dy, g, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# K8: MLP half-block   x + DropPath(fc2(GELU(fc1(y))))
+# ----------------------------------------------------------------------------------------------
+class SwinMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, shortcut, w1, b1, w2, b2, n_samples, rscale):
+        _chk(y, "swin_mlp")
+        rows = y.shape[0]
+        pre = torch.empty(rows, w1.shape[0], dtype=torch.float32, device=y.device)
+        act = gemm(y, w1, 0, bias=b1, act=1, aux_out=pre)
+        out = gemm(act, w2, 0, bias=b2, residual=shortcut, row_scale=rscale, rows_per_group=rows // n_samples)
+        ctx.save_for_backward(y, w1, w2, pre, act, rscale)
+        ctx.meta = (n_samples, b1 is not None, b2 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, w1, w2, pre, act, rscale = ctx.saved_tensors
+        n_samples, has_b1, has_b2 = ctx.meta
+        g = g.contiguous()
+        rpg = g.shape[0] // n_samples
+        gs = row_scale(g, rscale, rpg) if rscale is not None else g
+        dpre = gemm(gs, w2, 1, residual=pre, act=2)                      # (g @ W2) * GELU'(pre) in the epilogue
+        dw2 = linear_wgrad(act, gs)
+        db2 = colsum(gs) if has_b2 else None
+        dy = gemm(dpre, w1, 1)
+        dw1 = linear_wgrad(y, dpre)
+        db1 = colsum(dpre) if has_b1 else None
+        return dy, g, dw1, db1, dw2, db2, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# PatchMerging: gather 2x2 neighbours -> LayerNorm(4C) (+ tap) -> Linear(4C -> 2C, no bias)
+# ----------------------------------------------------------------------------------------------
+class PatchMergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, nw, nb, wred, eps, dims, arena, ly):
+        _chk(x, "patch_merging")
+        b, d, h, w = dims
+        cin = x.shape[1]
+        rows = b * d * ((h + 1) // 2) * ((w + 1) // 2)
+        gather = (b, d, h, w, cin)
+        part = None
+        if ly is not None:
+            part = arena.partial_buffer(ly, rows, 4 * cin, 1, 1, x.device, ln=True)
+        yn, mean, rstd = ln_fwd(x, nw, nb, eps, rows, 4 * cin, part, gather)
+        out = gemm(yn, wred, 0)
+        ctx.save_for_backward(x, nw, nb, wred, yn, mean, rstd)
+        ctx.meta = (gather, rows, arena, ly)
+        tok = ops.new_token(x) if ly is not None else None
+        return out, tok
+
+    @staticmethod
+    def backward(ctx, g, gtok):
+        x, nw, nb, wred, yn, mean, rstd = ctx.saved_tensors
+        gather, rows, arena, ly = ctx.meta
+        g = g.contiguous()
+        dyn = gemm(g, wred, 1)
+        dwred = linear_wgrad(yn, g)
+        coef = gs = None
+        if ly is not None and gtok is not None:
+            coef = arena.coef_ptrs(ly)
+            gs = gtok.contiguous()
+        gx, dg, db = ln_bwd(dyn, x, nw, nb, mean, rstd, rows, 4 * x.shape[1], None, coef, gs, gather, tuple(x.shape))
+        return gx, dg, db, dwred, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# PatchEmbed3D: Conv3d(kernel = stride = patch) as patchify + GEMM, then LayerNorm
+# ----------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, video, wconv, bconv, nw, nb, eps, patch):
+        _chk(video, "patch_embed")
+        b, cin, t, h, w = video.shape
+        pt, ph, pw = patch
+        if cin != 3 or pw != 4 or t % pt or h % ph or w % pw:
+            raise _lib.VittaError("patch_embed: needs 3-channel clips that are multiples of the (pt, ph, 4) patch")
+        video = video.contiguous()
+        rows = b * (t // pt) * (h // ph) * (w // pw)
+        kdim = 3 * pt * ph * pw
+        patches = torch.empty(rows, kdim, dtype=torch.float32, device=video.device)
+        call("vitta_patchify3d", ptr(video), b, t, h, w, pt, ph, pw, ptr(patches), stream_ptr())
+        w2d = wconv.view(wconv.shape[0], kdim)
+        tok = gemm(patches, w2d, 0, bias=bconv)
+        if nw is None:
+            ctx.save_for_backward(patches, w2d)
+            ctx.meta = (False, bconv is not None, tuple(wconv.shape))
+            return tok
+        y, mean, rstd = ln_fwd(tok, nw, nb, eps, rows, tok.shape[1])
+        ctx.save_for_backward(patches, w2d, tok, nw, nb, mean, rstd)
+        ctx.meta = (True, bconv is not None, tuple(wconv.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        has_norm, has_bias, wshape = ctx.meta
+        g = g.contiguous()
+        dg = db = None
+        if has_norm:
+            patches, w2d, tok, nw, nb, mean, rstd = ctx.saved_tensors
+            g, dg, db = ln_bwd(g, tok, nw, nb, mean, rstd, tok.shape[0], tok.shape[1])
+        else:
+            patches, w2d = ctx.saved_tensors
+        dw = linear_wgrad(patches, g).view(wshape)
+        dbias = colsum(g) if has_bias else None
+        return None, dw, dbias, dg, db, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# token pooling of the head
+# ----------------------------------------------------------------------------------------------
+class FrameMeanFn(torch.autograd.Function):
+    """(frames*rows, C) -> (frames, C) mean over the rows of each frame (AdaptiveAvgPool3d((1,1,1)) of I3DHead)."""
+
+    @staticmethod
+    def forward(ctx, x, frames):
+        _chk(x, "frame_mean")
+        n, c = x.shape
+        rows = n // frames
+        out = torch.empty(frames, c, dtype=torch.float32, device=x.device)
+        call("vitta_frame_mean", ptr(x), frames, rows, c, ptr(out), stream_ptr())
+        ctx.meta = (frames, rows, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        frames, rows, c = ctx.meta
+        g = g.contiguous()
+        gx = torch.empty(frames * rows, c, dtype=torch.float32, device=g.device)
+        call("vitta_frame_mean_bwd", ptr(g), frames, rows, c, ptr(gx), stream_ptr())
+        return gx, None
