@@ -1,0 +1,108 @@
+"""World-size-2 CPU (gloo) tests of the multi-GPU host logic: the C1 statistics payload / all-gather
+/ exact Chan merge, the C2 flat gradient all-reduce, and the sharding identity the design rests on -- per-rank backward of
+the GLOBAL alignment loss restricted to the rank's samples, summed over ranks, equals the single-process full-batch
+gradient of the reference formulation."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _chan_merge(n_a, m_a, M2_a, n_b, m_b, M2_b):
+    n = n_a + n_b
+    d = m_b - m_a
+    return n, m_a + d * (n_b / n), M2_a + M2_b + d * d * (n_a * n_b / n)
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vitta_b200 import ops
+    from oracle import vitta_oracle as O
+    torch.manual_seed(0)
+    # the full batch is generated identically on every rank; rank r owns a ragged shard of the samples
+    layers = [(6, 40, 8), (6, 40, 16)]           # (samples, tokens per sample, channels)
+    full = [torch.randn(n, t, c) * (1.0 + i) + 0.3 * i for i, (n, t, c) in enumerate(layers)]
+    split = [0, 4, 6]                             # rank 0: samples 0-3, rank 1: samples 4-5
+    mine = [x[split[rank]:split[rank + 1]] for x in full]
+    total_C = sum(c for _, _, c in layers)
+    # ---- C1: per-rank (mean, M2, n) -> payload -> all-gather -> exact merge
+    pay, merged, cnts = ops.stats_payload(total_C, len(layers), "cpu")
+    off = 0
+    for li, x in enumerate(mine):
+        f = x.reshape(-1, x.shape[-1])
+        merged[2 * off:2 * (off + f.shape[1]):2] = f.mean(0)
+        merged[2 * off + 1:2 * (off + f.shape[1]):2] = ((f - f.mean(0)) ** 2).sum(0)
+        cnts[li] = f.shape[0]
+        off += f.shape[1]
+    means, counts = ops.gather_stats_payload(pay, total_C, dist.group.WORLD)
+    assert means.shape == (world, 2 * total_C) and counts.shape == (world, len(layers))
+    assert counts.dtype == torch.int32 and counts[:, 0].tolist() == [4 * 40, 2 * 40]
+    off = 0
+    for li, x in enumerate(full):
+        c = x.shape[-1]
+        n, m, M2 = 0.0, torch.zeros(c), torch.zeros(c)
+        for r in range(world):
+            blk = means[r, 2 * off:2 * (off + c)]
+            n, m, M2 = _chan_merge(n, m, M2, float(counts[r, li]), blk[0::2], blk[1::2])
+        f = x.reshape(-1, c)
+        torch.testing.assert_close(m, f.mean(0), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(M2 / n, f.var(0, unbiased=False), rtol=1e-5, atol=1e-6)
+        off += c
+    # ---- C2: flat gradient all-reduce
+    grads = [torch.full((3, 2), float(rank + 1)), torch.arange(5.0) * (rank + 1)]
+    outs, flat = ops.allreduce_grads(grads, dist.group.WORLD)
+    assert flat.numel() == 11
+    torch.testing.assert_close(outs[0], torch.full((3, 2), 3.0))
+    torch.testing.assert_close(outs[1], torch.arange(5.0) * 3)
+    # ---- sharding identity: sum over ranks of d(global loss)/d(theta) on the local samples == full-batch gradient
+    w = torch.randn(8, 8, requires_grad=True)
+    src_m, src_v = torch.randn(8) * 0.1, torch.rand(8) + 0.5
+
+    def feature(x):          # a toy "layer": y = x @ w, channels-last tokens (n, t, c) -> the hook's (N, C, T, 1, 1)
+        return (x @ w).permute(0, 2, 1)[..., None, None]
+    yf = feature(full[0])
+    mean, var = O.spatiotemp_stats(yf)
+    loss = O.regularization(src_m, 0.1 * mean, src_v, 0.1 * var, "l1_loss")
+    g_full, = torch.autograd.grad(loss, w)
+    # rank-local: global statistics from the gathered moments, closed-form coefficients
+    yl = feature(mine[0])
+    with torch.no_grad():
+        fl = yl.permute(0, 2, 3, 4, 1).reshape(-1, 8)
+        p2, m2, c2 = ops.stats_payload(8, 1, "cpu")
+        m2[0::2] = fl.mean(0)
+        m2[1::2] = ((fl - fl.mean(0)) ** 2).sum(0)
+        c2[0] = fl.shape[0]
+        mm, cc = ops.gather_stats_payload(p2, 8, dist.group.WORLD)
+        n, gm, gM2 = 0.0, torch.zeros(8), torch.zeros(8)
+        for r in range(world):
+            n, gm, gM2 = _chan_merge(n, gm, gM2, float(cc[r, 0]), mm[r, 0::2], mm[r, 1::2])
+        gvar = gM2 / n
+        a = 0.1 * torch.sign(0.1 * gm - src_m) / 8 / n
+        b = 0.1 * 2 * torch.sign(0.1 * gvar - src_v) / 8 / n
+        gy = (a + b * (fl - gm)).reshape(yl.shape[0], -1, 8).permute(0, 2, 1)[..., None, None]
+    g_local, = torch.autograd.grad(yl, w, gy)
+    (g_sum,), _ = ops.allreduce_grads([g_local], dist.group.WORLD)
+    torch.testing.assert_close(g_sum, g_full, rtol=1e-4, atol=1e-7)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_statistics_and_gradients(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()

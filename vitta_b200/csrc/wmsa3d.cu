@@ -18,7 +18,7 @@
 //              (tcgen05.ld / tcgen05.st) and finds the row maximum; pass 2 exponentiates, accumulates the row sum and
 //              writes P (hi / lo) chunk by chunk for the PV MMAs; finally O / rowsum is written out with log-sum-exp.
 //   The whole score row lives in TMEM, so there is no online-softmax rescaling and the N x N matrix never touches HBM.
-// Backward (v0): fp32 FFMA2 kernel, one CTA per item with Q, K, V, dO resident in shared memory (see wmsa3d_bwd_kernel).
+// Backward (v0): fp32 FFMA2 kernel, one CTA (384 threads) per item with Q, K, V, dO resident in shared memory (see wmsa3d_bwd_kernel).
 #include "tc05.cuh"
 
 namespace vitta {
@@ -414,13 +414,13 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward (v0): exact fp32 on the FFMA2 pipe.  One CTA (416 threads) per item; Qs = scale*Q, K, V, dO of the window live
+// backward (v0): exact fp32 on the FFMA2 pipe.  One CTA (384 threads) per item; Qs = scale*Q, K, V, dO of the window live
 // in shared memory (broadcast reads), the bias table and its gradient too.
 //   pass A (thread = query i):  dQ_i = scale * sum_j dS_ij K_j,   dTable[rel(i,j)] += dS_ij
 //   pass B (thread = key j):    dK_j = sum_i dS_ij Qs_i,          dV_j = sum_i P_ij dO_i
 //   with P_ij = exp(S_ij - lse_i), dS_ij = P_ij (dO_i . V_j - dO_i . O_i)
 // ------------------------------------------------------------------------------------------------
-constexpr int kAtBwdThreads = 416;
+constexpr int kAtBwdThreads = 384;   // 12 warps = 3 per SM sub-partition -> 168 registers / thread
 
 struct WmsaBwdParams {
   const float* qkv;
@@ -450,7 +450,7 @@ constexpr int kBwSmemBytes = kBwOffTok + kAtMaxKeys * 4 + 16;   // 227600
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-__global__ void __maxnreg__(152) wmsa3d_bwd_kernel(const WmsaBwdParams p) {
+__global__ void __launch_bounds__(kAtBwdThreads, 1) wmsa3d_bwd_kernel(const WmsaBwdParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* sQ = reinterpret_cast<float*>(smem + kBwOffQ);
   float* sK = reinterpret_cast<float*>(smem + kBwOffK);
@@ -531,8 +531,9 @@ __global__ void __maxnreg__(152) wmsa3d_bwd_kernel(const WmsaBwdParams p) {
       }
     }
     __syncthreads();
-    const bool act = tid < g.N;
-    const int me = act ? tid : 0;
+    for (int base = 0; base < g.N; base += kAtBwdThreads) {   // 392 rows = one full sweep + one 8-row sweep
+    const bool act = base + tid < g.N;
+    const int me = act ? base + tid : 0;
     const int f_me = info[me];
     const int b_me = f_me & 0xffff;
     const int r_me = (f_me >> 16) & 0x1f;
@@ -616,6 +617,7 @@ __global__ void __maxnreg__(152) wmsa3d_bwd_kernel(const WmsaBwdParams p) {
         }
       }
     }
+    }   // row sweeps
   }
   __syncthreads();
   if (cur_head >= 0) flush_dtab(cur_head);

@@ -39,6 +39,38 @@ class _Layer:
                  "part", "count", "meter_count", "fired", "token", "name", "n_batch")
 
 
+# ----------------------------------------------------------------------------------------------
+# multi-GPU host plumbing (device agnostic: exercised on CPU with the gloo backend by tests/test_dist_gloo.py)
+# ----------------------------------------------------------------------------------------------
+def stats_payload(total_C, n_layers, device):
+    """Per-rank payload of collective C1: [2*total_C floats (mean, M2 per channel)] + [n_layers int32 element counts,
+    bit-cast to float32 so that ONE all-gather moves both].  Returns (payload, merged view, counts view)."""
+    pay = torch.empty(2 * total_C + n_layers, dtype=torch.float32, device=device)
+    return pay, pay[:2 * total_C], pay[2 * total_C:].view(torch.int32)
+
+
+def gather_stats_payload(pay, total_C, group):
+    """all-gather the payloads of every rank; returns ((world, 2*total_C) float32 means/M2, (world, n) int32 counts)."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    gath = torch.empty(ws * pay.numel(), dtype=torch.float32, device=pay.device)
+    dist.all_gather_into_tensor(gath, pay, group=group)           # collective C1 (NCCL over NVLink on the GPU box)
+    g2 = gath.view(ws, -1)
+    return g2[:, :2 * total_C].contiguous(), g2[:, 2 * total_C:].contiguous().view(torch.int32)
+
+
+def allreduce_grads(grads, group):
+    """Collective C2: sum the gradients of all ranks through one flat buffer; returns views into it (same order)."""
+    import torch.distributed as dist
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    outs, o = [], 0
+    for g in grads:
+        outs.append(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+    return outs, flat
+
+
 class StatsArena:
     """State shared by all alignment hooks attached to one model.
 
@@ -208,19 +240,10 @@ class StatsArena:
                  ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
                  ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, self.max_C, st)
         else:
-            import torch.distributed as dist
-            ws = dist.get_world_size(self.process_group)
-            # payload per rank: [2*total_C floats (mean, M2)] + [n int32 counts bit-cast to float]
-            pay = torch.empty(2 * self.total_C + n, dtype=torch.float32, device=dev)
-            merged = pay[:2 * self.total_C]
-            cnts = pay[2 * self.total_C:].view(torch.int32)
+            pay, merged, cnts = stats_payload(self.total_C, n, dev)
             call("vitta_stats_finalize", ptr(self._desc_dev), n, ptr(self._base), None, None, None, None, None, None,
                  None, None, None, None, 1, ptr(merged), ptr(cnts), self.max_C, st)
-            gath = torch.empty(ws * pay.numel(), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gath, pay, group=self.process_group)   # collective C1 (NCCL over NVLink)
-            g2 = gath.view(ws, -1)
-            means = g2[:, :2 * self.total_C].contiguous()
-            counts = g2[:, 2 * self.total_C:].contiguous().view(torch.int32)
+            means, counts = gather_stats_payload(pay, self.total_C, self.process_group)
             self._gath_keep = (means, counts)
             call("vitta_stats_finalize", ptr(self._desc_gath), n, ptr(means), ptr(counts), ptr(self.src_mean),
                  ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
@@ -509,15 +532,7 @@ class FusedSGD:
         dev = live[0].device
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in live]
         if self.process_group is not None:
-            import torch.distributed as dist
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat, group=self.process_group)            # collective C2: gradient sum over ranks
-            outs, o = [], 0
-            for g in grads:
-                outs.append(flat[o:o + g.numel()])
-                o += g.numel()
-            grads = outs
-            self._flat_keep = flat
+            grads, self._flat_keep = allreduce_grads(grads, self.process_group)   # collective C2
         first, rest = [], []
         for p, g in zip(live, grads):
             if not p.is_contiguous():
