@@ -45,14 +45,14 @@ def _arg(v):
     return v.value if hasattr(v, "value") else v
 
 
-def attribute_step(adapter, resident):
+def attribute_step(adapter, resident, step=None):
     """One extra, instrumented adaptation step: CUDA events around every launch of our library on the launching
     stream (torch's current stream).  Returns {kernel family: {"ms", "launches", "flops", "bytes"}} with ALGORITHMIC
     flops (2*M*N*K of the fp32 product, not the 3 tf32 MMAs issued per product) and bytes."""
     import torch
     from vitta_b200 import _lib
     _lib.profile = []
-    adapter.adapt(resident)
+    (step or (lambda: adapter.adapt(resident)))()
     torch.cuda.synchronize()
     recs, _lib.profile = _lib.profile, None
     fam = {}
@@ -60,10 +60,28 @@ def attribute_step(adapter, resident):
         ms = e0.elapsed_time(e1)
         flops = nbytes = 0.0
         key = name
-        if name == "vitta_gemm_tf32x3":
+        if name in ("vitta_gemm_tf32x3", "vitta_gemm_tf32x3_ex"):
             m, n, k = _arg(a[7]), _arg(a[8]), _arg(a[9])
             flops = 2.0 * m * n * k
             key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
+        elif name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd"):
+            fwd = name == "vitta_wmsa3d_fwd"
+            i0 = 4 if fwd else 7
+            b_, d_, h_, w_, heads = (_arg(a[i0 + j]) for j in range(5))
+            win = a[i0 + 6]
+            nwin = 1
+            ntok = 1
+            for dim, wsz in zip((d_, h_, w_), win):
+                wsz = min(int(wsz), dim)
+                nwin *= dim // wsz
+                ntok *= wsz
+            flops = (4.0 if fwd else 10.0) * ntok * ntok * 32 * b_ * nwin * heads
+            key = "wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (FFMA2 window attention backward)"
+        elif name in ("vitta_ln_fwd", "vitta_ln_bwd"):
+            fwd = name == "vitta_ln_fwd"
+            rows, c = (_arg(a[8]), _arg(a[9])) if fwd else (_arg(a[15]), _arg(a[16]))
+            nbytes = 4.0 * rows * c * (2 if fwd else 3)
+            key = "ln_fwd (LayerNorm + stats, K9)" if fwd else "ln_bwd (K9 backward + hook gradient)"
         elif name in ("vitta_conv2d_tf32x3", "vitta_conv2d_wgrad_tf32x3"):
             if name == "vitta_conv2d_tf32x3":
                 f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in (1, 2, 3, 4, 7, 8, 9, 10, 11))

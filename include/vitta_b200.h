@@ -227,6 +227,15 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
                         int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream);
 
+/* Data gradient of a STRIDED convolution: dX[F,H,W,Cin] = conv2d_backward_input(dY[F,Ho,Wo,Cout], W), stride >= 1.
+ * Wthi / Wtlo: the weight split with mode 1 ([Cin][rotated tap][Cout]).  Input pixels are processed per residue class
+ * modulo the stride: each class is a small dense stride-1 convolution over dY with only the filter taps that reach it
+ * (no zero-insertion, no wasted MMAs), stored straight to its strided positions of dX; classes no tap reaches are zeroed.
+ *   replaces: autograd's convolution_backward input branch (cuDNN dgrad) for the stride-2 3x3 / 1x1 convolutions of
+ *             layer2-4.0 (torchvision Bottleneck v1.5 inside TemporalBottleneck, temporal_module.py:85-106). */
+int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
+                              int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream);
+
 /* Weight gradient of the same convolution: dW[Cout][Cin][KH][KW] (contiguous NCHW, the layout of nn.Conv2d.weight)
  *   (+)= sum over output pixels of dY[F,Ho,Wo,Cout] (x) X[F,H,W,Cin] shifted by the filter tap.
  * Split-K over pixel ranges on the tcgen05 tensor cores (both operands MN-major, split hi/lo in-kernel); the K splits

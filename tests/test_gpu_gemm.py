@@ -124,9 +124,12 @@ def test_conv2d_autograd_matches_torch(cuda_device):
     """Conv2dFn (forward + dgrad + wgrad on tcgen05) against torch's float64 autograd, stride 1 and 2."""
     import vitta_b200
     from vitta_b200 import ops
-    vitta_b200.set_fp32_exact()      # the stride-2 data gradient still goes through cuDNN: keep it out of TF32
+    vitta_b200.set_fp32_exact()
     g = torch.Generator().manual_seed(21)
-    for (f, h, cin, cout, kh, stride, pad) in [(4, 14, 64, 128, 3, 1, 1), (4, 28, 128, 128, 3, 2, 1), (8, 14, 256, 64, 1, 1, 0)]:
+    for (f, h, cin, cout, kh, stride, pad) in [(4, 14, 64, 128, 3, 1, 1), (4, 28, 128, 128, 3, 2, 1), (8, 14, 256, 64, 1, 1, 0),
+                                                (3, 28, 256, 512, 1, 2, 0),    # downsample conv: 3 of 4 pixel classes get 0
+                                                (2, 15, 64, 64, 3, 2, 1),      # odd extent: ragged residue classes
+                                                (5, 14, 512, 512, 3, 2, 1)]:
         x = torch.randn(f, cin, h, h, generator=g).to(cuda_device)
         wt = (torch.randn(cout, cin, kh, kh, generator=g) / (cin * kh * kh) ** 0.5).to(cuda_device)
         x1 = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)

@@ -38,6 +38,12 @@ struct GemmParams {
   int tiles_w, tiles_h, tiles_f, tiles_n;
   int act;                 // 0 none, 1 exact GELU, 2 multiply by GELU'(residual[m, n]) (residual = saved pre-activation)
   int vec_ok;              // C / bias / residual allow 128-bit accesses
+  // optional tap table (strided data gradient): tap t reads the A box shifted by (tap_dh, tap_dw) and the B columns of
+  // weight tap tap_wt; 0 taps = the plain taps_h x taps_w raster
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_wt[9];
+  // output pixel (f, ho, wo) -> row ((f*out_H + ho*out_sy + out_oy)*out_W + wo*out_sx + out_ox); out_sy == 0: dense
+  int out_sy, out_sx, out_oy, out_ox, out_H, out_W;
   float* aux_out;          // optional second output: the pre-activation acc + bias (same indexing as C)
   const float* row_scale;  // optional per-row-group factor (DropPath): v *= row_scale[row / rows_per_group]
   int rows_per_group;
@@ -79,7 +85,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_f;
   const int total_tiles = tiles_m * p.tiles_n;
-  const int taps = p.taps_h * p.taps_w;
+  const int taps = p.ntaps ? p.ntaps : p.taps_h * p.taps_w;
   const int k_iters = taps * p.k_chunks;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BF) * kBK * 4;
   const uint32_t stage_tx = a_box_bytes + 2u * S::kBBytes;
@@ -129,13 +135,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_chunks;
           const int kc = (it - tap * p.k_chunks) * kBK;
-          const int th = tap / p.taps_w, tw = tap - th * p.taps_w;
+          int th = tap / p.taps_w, tw = tap - th * p.taps_w, wt = tap;
+          if (p.ntaps) { th = p.tap_dh[tap]; tw = p.tap_dw[tap]; wt = p.tap_wt[tap]; }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           tma_load_4d(&tmA, &full_bar[stage], st, kc, w_in0 + tw, h_in0 + th, f0);
-          tma_load_2d(&tmBhi, &full_bar[stage], st + 2 * S::kABytes, tap * p.Kc + kc, n0);
-          tma_load_2d(&tmBlo, &full_bar[stage], st + 2 * S::kABytes + S::kBBytes, tap * p.Kc + kc, n0);
+          tma_load_2d(&tmBhi, &full_bar[stage], st + 2 * S::kABytes, wt * p.Kc + kc, n0);
+          tma_load_2d(&tmBlo, &full_bar[stage], st + 2 * S::kABytes + S::kBBytes, wt * p.Kc + kc, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -220,8 +227,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int bh = (row / p.BW) % p.BH;
       const int bf = row / (p.BW * p.BH);
       const int wo = wb * p.BW + bw, ho = hb * p.BH + bh, f = fb * p.BF + bf;
-      const bool row_ok = (bf < p.BF) && (wo < p.Wo) && (ho < p.Ho) && (f < p.F);
-      const int64_t out_row = ((int64_t)f * p.Ho + ho) * p.Wo + wo;
+      bool row_ok = (bf < p.BF) && (wo < p.Wo) && (ho < p.Ho) && (f < p.F);
+      int64_t out_row = ((int64_t)f * p.Ho + ho) * p.Wo + wo;
+      if (p.out_sy) {
+        const int oy = ho * p.out_sy + p.out_oy, ox = wo * p.out_sx + p.out_ox;
+        row_ok = row_ok && oy < p.out_H && ox < p.out_W;
+        out_row = ((int64_t)f * p.out_H + oy) * p.out_W + ox;
+      }
       float* crow = p.C + out_row * p.ldc;
       const float* rrow = p.residual ? p.residual + out_row * p.ldr : nullptr;
       float* arow = p.aux_out ? p.aux_out + out_row * p.ldc : nullptr;
@@ -417,6 +429,29 @@ static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const float* Bhi, const
   return make_tensor_map_f32(bl, Blo, 2, dims, str, box, es);
 }
 
+// M tile = BF frames x BH rows x BW cols of output pixels, at most 128
+static void pick_boxes(int Wo, int Ho, int F, int* pBW, int* pBH, int* pBF) {
+  const int BW = Wo < kBM ? Wo : kBM;
+  int BH = 1, BF = 1;
+  if (BW == Wo) {
+    int bh_max = kBM / BW;
+    if (bh_max > Ho) bh_max = Ho;
+    BH = bh_max;
+    for (int d = bh_max; d >= 1; --d) {   // largest divisor of Ho that fits; keep it unless it halves the tile
+      if (Ho % d == 0) {
+        if (2 * d > bh_max) BH = d;
+        break;
+      }
+    }
+    if (BH == Ho) {
+      BF = kBM / (BW * BH);
+      if (BF > F) BF = F;
+      if (BF < 1) BF = 1;
+    }
+  }
+  *pBW = BW; *pBH = BH; *pBF = BF;
+}
+
 }  // namespace vitta
 
 using namespace vitta;
@@ -489,25 +524,8 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
                   "conv2d_tf32x3: Cin must be a multiple of 4 and tensors 16-byte aligned");
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   VITTA_CHECK_ARG(Ho > 0 && Wo > 0, VITTA_E_BADARG, "conv2d_tf32x3: empty output");
-  // M tile = BF frames x BH rows x BW cols of output pixels, at most 128
-  const int BW = Wo < kBM ? Wo : kBM;
-  int BH = 1, BF = 1;
-  if (BW == Wo) {
-    int bh_max = kBM / BW;
-    if (bh_max > Ho) bh_max = Ho;
-    BH = bh_max;
-    for (int d = bh_max; d >= 1; --d) {   // largest divisor of Ho that fits; keep it unless it halves the tile
-      if (Ho % d == 0) {
-        if (2 * d > bh_max) BH = d;
-        break;
-      }
-    }
-    if (BH == Ho) {
-      BF = kBM / (BW * BH);
-      if (BF > F) BF = F;
-      if (BF < 1) BF = 1;
-    }
-  }
+  int BW, BH, BF;
+  pick_boxes(Wo, Ho, F, &BW, &BH, &BF);
   VITTA_CHECK_ARG((int64_t)BW * stride <= 256 && (int64_t)BH * stride <= 256, VITTA_E_UNSUPPORTED,
                   "conv2d_tf32x3: box exceeds the TMA limit");
   const int bn = pick_bn(Cout, force_bn);
@@ -533,6 +551,84 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
   p.act = 0;
   p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias));
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
+}
+
+int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
+                              int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream) {
+  VITTA_CHECK_ARG(dY && Wthi && Wtlo && dX && F > 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0,
+                  VITTA_E_BADARG, "conv2d_dgrad: bad arguments");
+  VITTA_CHECK_ARG(KH > 0 && KW > 0 && KH * KW <= 9 && stride >= 1 && stride <= 4 && pad >= 0, VITTA_E_UNSUPPORTED,
+                  "conv2d_dgrad: filters up to 3x3, stride up to 4");
+  VITTA_CHECK_ARG(Ho == (H + 2 * pad - KH) / stride + 1 && Wo == (W + 2 * pad - KW) / stride + 1, VITTA_E_BADARG,
+                  "conv2d_dgrad: output geometry does not match");
+  VITTA_CHECK_ARG(Cout % 4 == 0 && aligned16(dY) && aligned16(Wthi) && aligned16(Wtlo), VITTA_E_ALIGN,
+                  "conv2d_dgrad: Cout must be a multiple of 4 and tensors 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ktot = KH * KW * Cout;
+  const int bn = pick_bn(Cin, 0);
+  CUtensorMap tbh, tbl;
+  int rc = make_b_maps(&tbh, &tbl, Wthi, Wtlo, Ktot, Cin, Ktot, bn);
+  if (rc) return rc;
+  // residue classes no filter tap reaches (e.g. 1x1 stride 2) have zero gradient: clear dX first if there are any
+  bool any_empty = false;
+  for (int a = 0; a < stride; ++a) {
+    bool hit = false;
+    for (int kh = 0; kh < KH; ++kh) hit = hit || ((a + pad - kh) % stride == 0);
+    any_empty = any_empty || !hit;
+  }
+  for (int b = 0; b < stride; ++b) {
+    bool hit = false;
+    for (int kw = 0; kw < KW; ++kw) hit = hit || ((b + pad - kw) % stride == 0);
+    any_empty = any_empty || !hit;
+  }
+  if (any_empty) {
+    cudaError_t e = cudaMemsetAsync(dX, 0, (size_t)F * H * W * Cin * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("conv2d_dgrad: memset: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  // one launch per residue class (a, b) of the input-pixel coordinates modulo the stride
+  for (int a = 0; a < stride && a < H; ++a) {
+    for (int b = 0; b < stride && b < W; ++b) {
+      GemmParams p{};
+      int nt = 0;
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((a + pad - kh) % stride != 0) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          if ((b + pad - kw) % stride != 0) continue;
+          // floor division is exact here; negative offsets fall into the TMA zero fill
+          p.tap_dh[nt] = (a + pad - kh) / stride;
+          p.tap_dw[nt] = (b + pad - kw) / stride;
+          p.tap_wt[nt] = (KH - 1 - kh) * KW + (KW - 1 - kw);   // split mode 1 stores the filter rotated by 180 degrees
+          ++nt;
+        }
+      }
+      if (nt == 0) continue;   // no filter tap reaches this class: already zeroed
+      const int Hc = (H - a + stride - 1) / stride, Wc = (W - b + stride - 1) / stride;
+      int BW, BH, BF;
+      pick_boxes(Wc, Hc, F, &BW, &BH, &BF);
+      CUtensorMap ta;
+      {
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)F};
+        const uint64_t str[3] = {(uint64_t)Cout * 4, (uint64_t)Cout * 4 * Wo, (uint64_t)Cout * 4 * Wo * Ho};
+        const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)BH, (uint32_t)BF};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        rc = make_tensor_map_f32(&ta, dY, 4, dims, str, box, es);
+        if (rc) return rc;
+      }
+      p.C = dX; p.ldc = Cin; p.N = Cin; p.Kc = Cout; p.k_chunks = (Cout + kBK - 1) / kBK;
+      p.taps_h = p.taps_w = 1; p.stride = 1; p.pad = 0; p.ntaps = nt;
+      p.Ho = Hc; p.Wo = Wc; p.F = F;
+      p.BW = BW; p.BH = BH; p.BF = BF;
+      p.tiles_w = (Wc + BW - 1) / BW; p.tiles_h = (Hc + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
+      p.out_sy = stride; p.out_sx = stride; p.out_oy = a; p.out_ox = b; p.out_H = H; p.out_W = W;
+      p.vec_ok = aligned16(dX) && (Cin % 4 == 0);
+      rc = dispatch(ta, tbh, tbl, p, bn, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

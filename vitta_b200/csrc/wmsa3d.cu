@@ -188,30 +188,84 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");   // tok[] complete (loader warps only)
       const float* qkv_h = p.qkv + head * 32 + q4 * 4;
-      // ---- K: all keys of the window
-      for (int r = rslot; r < g.NP; r += 16) {
-        const int t = tok[r];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0) v = ldg4(qkv_h + ((int64_t)t * 3 + 1) * C);
-        float4 h, l;
-        split4(v, h, l);
-        const uint32_t o = sw128_off(r, q4);
-        *reinterpret_cast<float4*>(smem + kOffKhi + o) = h;
-        *reinterpret_cast<float4*>(smem + kOffKlo + o) = l;
+      // Every loop below issues a BATCH of independent global loads into registers before touching shared memory, so a
+      // thread pays the HBM/L2 latency once per batch instead of once per row.
+      // ---- K: all keys of the window (8 rows per thread and batch)
+      for (int r0 = rslot; r0 < g.NP; r0 += 128) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + u * 16;
+          const int t = (r < g.NP) ? tok[r] : -1;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0) v[u] = ldg4(qkv_h + ((int64_t)t * 3 + 1) * C);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + u * 16;
+          if (r < g.NP) {
+            float4 h, l;
+            split4(v[u], h, l);
+            const uint32_t o = sw128_off(r, q4);
+            *reinterpret_cast<float4*>(smem + kOffKhi + o) = h;
+            *reinterpret_cast<float4*>(smem + kOffKlo + o) = l;
+          }
+        }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[B_KV_READY]);
-      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        mbar_wait(&bar[B_Q_FREE], (tile_ctr & 1) ^ 1);
-        for (int r = rslot; r < 128; r += 16) {
-          const int i = tile * 128 + r;
-          const int t = (i < g.N) ? tok[i] : -1;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (t >= 0) {
-            v = ldg4(qkv_h + (int64_t)t * 3 * C);
-            v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;   // q = q * scale (:146)
+      // V chunks: groups of 4 chunks (8 float4 per thread), the next group in flight while the current one is stored
+      auto v_issue = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = grp * 128 + (u >> 1) * 32 + rslot + (u & 1) * 16;
+          const int t = (grp * 4 + (u >> 1) < n_chunks && j < g.N) ? tok[j] : -1;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0) v[u] = ldg4(qkv_h + ((int64_t)t * 3 + 2) * C);
+        }
+      };
+      auto v_drain = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (grp * 4 + cc >= n_chunks) break;
+          const int st = chunk_ctr & 1;
+          mbar_wait(&bar[B_V_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          uint8_t* vb = smem + kOffV + st * 8192;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = rslot + rr * 16;
+            float4 h, l;
+            split4(v[cc * 2 + rr], h, l);
+            const uint32_t o = mn32_off(r, q4);
+            *reinterpret_cast<float4*>(vb + o) = h;
+            *reinterpret_cast<float4*>(vb + 4096 + o) = l;
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_V_READY0 + st]);
+          ++chunk_ctr;
+        }
+      };
+      const int n_groups = (n_chunks + 3) >> 2;
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        // Q tile: loads go to registers BEFORE the wait for the previous tile's S MMAs to release the buffer
+        float4 qv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = tile * 128 + rslot + u * 16;
+          const int t = (i < g.N) ? tok[i] : -1;
+          qv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0) qv[u] = ldg4(qkv_h + (int64_t)t * 3 * C);
+        }
+        float4 va[8], vb8[8];
+        v_issue(va, 0);
+        mbar_wait(&bar[B_Q_FREE], (tile_ctr & 1) ^ 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = rslot + u * 16;
+          float4 v = qv[u];
+          v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;   // q = q * scale (:146)
           float4 h, l;
           split4(v, h, l);
           const uint32_t o = sw128_off(r, q4);
@@ -221,26 +275,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_Q_READY]);
-        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = chunk_ctr & 1;
-          mbar_wait(&bar[B_V_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
-          uint8_t* vb = smem + kOffV + st * 8192;
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int r = rslot + rr * 16;
-            const int j = c * 32 + r;
-            const int t = (j < g.N) ? tok[j] : -1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t >= 0) v = ldg4(qkv_h + ((int64_t)t * 3 + 2) * C);
-            float4 h, l;
-            split4(v, h, l);
-            const uint32_t o = mn32_off(r, q4);
-            *reinterpret_cast<float4*>(vb + o) = h;
-            *reinterpret_cast<float4*>(vb + 4096 + o) = l;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_V_READY0 + st]);
+        for (int grp = 0; grp < n_groups; grp += 2) {
+          if (grp + 1 < n_groups) v_issue(vb8, grp + 1);
+          v_drain(va, grp);
+          if (grp + 2 < n_groups) v_issue(va, grp + 2);
+          if (grp + 1 < n_groups) v_drain(vb8, grp + 1);
         }
       }
     }

@@ -653,8 +653,8 @@ class Conv2dFn(torch.autograd.Function):
     """Bias-free 2-D convolution, channels-last, forward and data gradient on the tcgen05 3xTF32 kernel.
 
     Stride-1 data gradients reuse the forward kernel with the transposed / 180-degree-rotated operand (split mode 1);
-    weight gradients run on the split-K tcgen05 wgrad kernel.  Only the data gradient of the six stride-2 layers
-    still goes through ``aten::convolution_backward`` (see DESIGN.md)."""
+    strided data gradients run the same kernel once per residue class of the input pixels (vitta_conv2d_dgrad_tf32x3);
+    weight gradients run on the split-K tcgen05 wgrad kernel."""
 
     @staticmethod
     def forward(ctx, x, w, stride, pad):
@@ -676,6 +676,13 @@ class Conv2dFn(torch.autograd.Function):
         if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
             whi, wlo = weight_split(w, 1)
             gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad)
+            need_x = False
+        elif need_x and stride > 1 and kh * kw <= 9 and cout % 4 == 0:
+            whi, wlo = weight_split(w, 1)
+            f, _, h, wd = x.shape
+            gx = torch.empty_like(x)             # channels_last like x
+            call("vitta_conv2d_dgrad_tf32x3", ptr(gy), f, gy.shape[2], gy.shape[3], cout, ptr(whi), ptr(wlo), cin, kh, kw,
+                 stride, pad, h, wd, ptr(gx), stream_ptr())
             need_x = False
         if need_w and cout % 4 == 0:
             gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)
