@@ -66,7 +66,7 @@ def attribute_step(adapter, resident, step=None):
             key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
         elif name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd"):
             fwd = name == "vitta_wmsa3d_fwd"
-            i0 = 4 if fwd else 7
+            i0 = 4 if fwd else 8
             b_, d_, h_, w_, heads = (_arg(a[i0 + j]) for j in range(5))
             win = a[i0 + 6]
             nwin = 1
@@ -76,7 +76,7 @@ def attribute_step(adapter, resident, step=None):
                 nwin *= dim // wsz
                 ntok *= wsz
             flops = (4.0 if fwd else 10.0) * ntok * ntok * 32 * b_ * nwin * heads
-            key = "wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (FFMA2 window attention backward)"
+            key = "wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (tcgen05 window attention backward, 2 launches + dsum)"
         elif name in ("vitta_ln_fwd", "vitta_ln_bwd"):
             fwd = name == "vitta_ln_fwd"
             rows, c = (_arg(a[8]), _arg(a[9])) if fwd else (_arg(a[15]), _arg(a[16]))

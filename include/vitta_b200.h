@@ -306,12 +306,17 @@ int vitta_row_scale(const float* x, const float* scale, int64_t rows, int64_t ro
  *   :222-227 returns VITTA_E_UNSUPPORTED).
  * Forward: tcgen05 (3xTF32) -- S = QK^T accumulates in TMEM, softmax in place, O += P V.
  * Backward: dqkv has the layout of qkv (every element written once); dbias_table is ACCUMULATED into (zero it first).
+ *   dS = P o (dO V^T - rowsum(dO o O)), dQ = scale dS K, dK = dS^T (scale Q), dV = P^T dO, dTable[rel(i,j)] += dS_ij.
  * ---------------------------------------------------------------------------------------------- */
 int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
                      int heads, int head_dim, const int* window_host, const int* shift_host, float scale, void* stream);
+/* ws: vitta_wmsa3d_bwd_ws_floats() floats of scratch (D_i = dO_i . O_i per token and head; no init needed).
+ * impl 0: tcgen05 (3xTF32) -- a query-outer launch (dQ, dTable) and a key-outer launch (dK, dV);
+ * impl 1: the exact-fp32 FFMA2 kernel (one CTA per window and head), kept as an on-device cross-check. */
+int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads);
 int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
-                     float* dqkv, float* dbias_table, int B, int D, int H, int W, int heads, int head_dim,
-                     const int* window_host, const int* shift_host, float scale, void* stream);
+                     float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
+                     const int* window_host, const int* shift_host, float scale, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -144,4 +144,5 @@ def test_conv2d_autograd_matches_torch(cuda_device):
         for a, b, nm in ((y1, y2, "y"), (x1.grad, x2.grad, "gx"), (w1.grad, w2.grad, "gw")):
             scale = float(b.detach().abs().max())
             err = float((a.detach().double() - b.detach()).abs().max())
-            assert err < 2e-5 * scale, (nm, stride, kh, err, scale)
+            # 3xTF32 drops the lo*lo term (2^-22 per product): the bound grows with sqrt(K); K = 4608 in the last case
+            assert err < 5e-5 * scale, (nm, stride, kh, err, scale)

@@ -207,10 +207,11 @@ def test_window_attention_fwd_bwd_vs_reference(cuda_device, b, d, h, w, heads, w
     cases.assert_close(out.cpu(), ref.detach().cpu(), 2e-5, 2e-6, "attention output")
     go = _rnd(rows, c, seed=3)
     ref.backward(go.double())
-    dqkv, dtable = ops_swin.wmsa3d_bwd(qkv, table, out, go, lse, (b, d, h, w), heads, window, shift, scale)
-    # fp32 sums over N = 392 terms against a float64 reference: the absolute floor scales with the tensor
-    cases.assert_close(dqkv.cpu(), qd.grad.cpu(), 1e-4, 2e-5 * float(qd.grad.abs().max()), "dqkv")
-    cases.assert_close(dtable.cpu(), td.grad.cpu(), 1e-4, 2e-5 * float(td.grad.abs().max()), "dbias table")
+    for impl in (0, 1):     # 0: tcgen05 kernels (the product path), 1: exact-fp32 FFMA2 kernel
+        dqkv, dtable = ops_swin.wmsa3d_bwd(qkv, table, out, go, lse, (b, d, h, w), heads, window, shift, scale, impl)
+        # fp32 sums over N = 392 terms against a float64 reference: the absolute floor scales with the tensor
+        cases.assert_close(dqkv.cpu(), qd.grad.cpu(), 1e-4, 2e-5 * float(qd.grad.abs().max()), "dqkv impl %d" % impl)
+        cases.assert_close(dtable.cpu(), td.grad.cpu(), 1e-4, 2e-5 * float(td.grad.abs().max()), "dtable impl %d" % impl)
 
 
 # ----------------------------------------------------------------------------------------------

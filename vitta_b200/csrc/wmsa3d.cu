@@ -662,6 +662,453 @@ __global__ void __launch_bounds__(kAtBwdThreads, 1) wmsa3d_bwd_kernel(const Wmsa
   if (cur_head >= 0) flush_dtab(cur_head);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward (v1): tcgen05, 3xTF32.  Two launches of one skeleton (template MODE):
+//   MODE 0 "query-outer": thread = query row i.  Row operands (resident per 128-row tile, K-major A):  Qs_t, dO_t.
+//           per 32-key chunk c:  S = Qs_t K_c^T,  dP = dO_t V_c^T  (TMEM, double-buffered)
+//           dS = P o (dP - D_i), P = exp(S + bias + mask - lse_i);  dQ_t += dS K_c ;  dTable[rel(i,j)] += dS
+//   MODE 1 "key-outer":   thread = key row j.    Row operands: K_t, V_t.
+//           per 32-query chunk c:  S^T = K_t Qs_c^T,  dP^T = V_t dO_c^T
+//           P^T, dS^T with the per-column lse_i, D_i;  dV_t += P^T dO_c ;  dK_t += dS^T Qs_c
+// D_i = dO_i . O_i comes from wmsa3d_dsum_kernel.  Column chunks are stored twice: K-major (B operand of the score
+// MMAs) and MN-major (B operand of the accumulating MMAs); dS / P chunks are written by the row threads as K-major A
+// operands, exactly like P in the forward kernel.
+// ------------------------------------------------------------------------------------------------
+struct WmsaBwd2Params {
+  const float* qkv;
+  const float* table;
+  const float* dout;
+  const float* lse;
+  const float* dsum;    // (tokens, heads)
+  float* dqkv;
+  float* dtable;
+  float scale;
+  int items, items_per_cta;
+  WmsaGeom g;
+};
+
+// dsum[token, head] = sum_d dout[token, head*32 + d] * out[token, head*32 + d]; one 8-lane group per (token, head)
+__global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restrict__ out, const float* __restrict__ dout,
+                                                         float* __restrict__ dsum, int64_t n_pairs) {
+  const int q4 = threadIdx.x & 7;
+  for (int64_t pr0 = (int64_t)blockIdx.x * 32; pr0 < n_pairs; pr0 += (int64_t)gridDim.x * 32) {
+    const int64_t pr = pr0 + (threadIdx.x >> 3);
+    float d = 0.f;
+    if (pr < n_pairs) {
+      const float4 a = ldg4(out + pr * 32 + q4 * 4), b = ldg4(dout + pr * 32 + q4 * 4);
+      d = (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (q4 == 0 && pr < n_pairs) dsum[pr] = d;
+  }
+}
+
+constexpr int kB2OffR = 0;                         // R1 hi, R1 lo, R2 hi, R2 lo: 4 x 16 KB
+constexpr int kB2OffC = kB2OffR + 4 * 16384;       // 2 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
+constexpr int kB2OffE = kB2OffC + 2 * 32768;       // 64 KB: MODE 0: 2 stages x (E1 hi, lo); MODE 1: E1 hi, lo, E2 hi, lo
+constexpr int kB2OffTab = kB2OffE + 65536;         // bias table of the head
+constexpr int kB2OffDTab = kB2OffTab + kAtMaxRel * 4;
+constexpr int kB2OffLse = kB2OffDTab + kAtMaxRel * 4;
+constexpr int kB2OffDs = kB2OffLse + kAtMaxKeys * 4;
+constexpr int kB2OffInfo = kB2OffDs + kAtMaxKeys * 4;
+constexpr int kB2OffTok = kB2OffInfo + kAtMaxKeys * 4;
+constexpr int kB2OffBar = kB2OffTok + kAtMaxKeys * 4;
+constexpr int kB2SmemBytes = kB2OffBar + 256 + 1024;   // 224768
+
+enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C_COL_READY1, C_COL_FREE0, C_COL_FREE1,
+       C_SC_FULL0, C_SC_FULL1, C_SC_FREE0, C_SC_FREE1, C_E_READY0, C_E_READY1, C_E_FREE0, C_E_FREE1, C_ACC_FULL,
+       C_ACC_FREE, C_COUNT };
+
+template <int MODE>
+__global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kB2OffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + C_COUNT);
+  float* tab = reinterpret_cast<float*>(smem + kB2OffTab);
+  float* dtab = reinterpret_cast<float*>(smem + kB2OffDTab);
+  float* sLse = reinterpret_cast<float*>(smem + kB2OffLse);
+  float* sDs = reinterpret_cast<float*>(smem + kB2OffDs);
+  int* info = reinterpret_cast<int*>(smem + kB2OffInfo);
+  int* tok = reinterpret_cast<int*>(smem + kB2OffTok);
+  constexpr int kEStages = MODE == 0 ? 2 : 1;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const WmsaGeom& g = p.g;
+  const int C = g.heads * 32;
+  const int nwin = g.nw0 * g.nw1 * g.nw2;
+  const int nwin_total = g.B * nwin;
+  const int n_tiles = (g.N + 127) >> 7;
+  const int n_chunks = (g.N + 31) >> 5;
+  const int item0 = blockIdx.x * p.items_per_cta;
+  const int item1 = min(p.items, item0 + p.items_per_cta);
+
+  if (threadIdx.x == 0) {
+    const int counts[C_COUNT] = {4, 4, 4, 1, 4, 4, 1, 1, 1, 1, 4, 4, 4, 4, 1, 1, 1, 4};
+    for (int i = 0; i < C_COUNT; ++i) mbar_init(&bar[i], counts[i]);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: scores buffer b: SC1 at 64*b, SC2 at 64*b + 32; accumulators: ACC1 at 128, ACC2 at 160
+
+  if (warp >= 4 && warp < 8) {
+    // =========================== loaders ===========================
+    const int lt = threadIdx.x - 128;
+    const int rslot = lt >> 3, q4 = lt & 7;
+    int cur_head = -1;
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      const int wg = item - head * nwin_total;
+      const int b = wg / nwin;
+      int w = wg - b * nwin;
+      const int ww = w % g.nw2; w /= g.nw2;
+      const int wh = w % g.nw1;
+      const int wd = w / g.nw1;
+      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
+      if (head != cur_head) {
+        if (MODE == 0 && cur_head >= 0) {   // flush the table gradient of the previous head
+          for (int i = lt; i < g.nrel; i += 128) {
+            const float v = dtab[i];
+            if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
+          }
+        }
+        for (int i = lt; i < g.nrel; i += 128) {
+          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head);
+          if (MODE == 0) dtab[i] = 0.f;
+        }
+        cur_head = head;
+      }
+      for (int i = lt; i < g.NP; i += 128) {
+        int t, f;
+        window_token(g, b, wd, wh, ww, i, t, f);
+        tok[i] = t;
+        info[i] = f;
+        sLse[i] = (t >= 0) ? __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) : 0.f;
+        sDs[i] = (t >= 0) ? __ldg(p.dsum + (int64_t)t * g.heads + head) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[C_ITEM_READY]);
+      const float* qkv_h = p.qkv + head * 32 + q4 * 4;
+      const float* do_h = p.dout + head * 32 + q4 * 4;
+      // row operand r (0: R1, 1: R2) / column operand of a token
+      auto load_row = [&](int which, int t) -> float4 {
+        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 0) {
+          if (which == 0) {
+            float4 v = ldg4(qkv_h + (int64_t)t * 3 * C);
+            v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+            return v;
+          }
+          return ldg4(do_h + (int64_t)t * C);
+        }
+        return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C);
+      };
+      auto load_col = [&](int which, int t) -> float4 {
+        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 0) return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C);
+        if (which == 0) {
+          float4 v = ldg4(qkv_h + (int64_t)t * 3 * C);
+          v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+          return v;
+        }
+        return ldg4(do_h + (int64_t)t * C);
+      };
+      // column chunks: 2 chunks per group (2 tensors x 2 rows x 2 chunks = 8 float4 per thread)
+      auto c_issue = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cc = u >> 2, which = (u >> 1) & 1, rr = u & 1;
+          const int j = (grp * 2 + cc) * 32 + rslot + rr * 16;
+          const int t = (grp * 2 + cc < n_chunks && j < g.N) ? tok[j] : -1;
+          v[u] = load_col(which, t);
+        }
+      };
+      auto c_drain = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (grp * 2 + cc >= n_chunks) break;
+          const int st = chunk_ctr & 1;
+          mbar_wait(&bar[C_COL_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          uint8_t* cb = smem + kB2OffC + st * 32768;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int r = rslot + rr * 16;
+              float4 h, l;
+              split4(v[cc * 4 + which * 2 + rr], h, l);
+              const uint32_t ok = sw128_off(r, q4), om = mn32_off(r, q4);
+              uint8_t* base = cb + which * 16384;
+              *reinterpret_cast<float4*>(base + ok) = h;
+              *reinterpret_cast<float4*>(base + 4096 + ok) = l;
+              if (MODE == 1 || which == 0) {
+                *reinterpret_cast<float4*>(base + 8192 + om) = h;
+                *reinterpret_cast<float4*>(base + 12288 + om) = l;
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[C_COL_READY0 + st]);
+          ++chunk_ctr;
+        }
+      };
+      const int n_groups = (n_chunks + 1) >> 1;
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        float4 ra[8], rb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = tile * 128 + rslot + u * 16;
+          const int t = (i < g.N) ? tok[i] : -1;
+          ra[u] = load_row(0, t);
+          rb[u] = load_row(1, t);
+        }
+        float4 va[8], vb8[8];
+        c_issue(va, 0);
+        mbar_wait(&bar[C_ROWS_FREE], (tile_ctr & 1) ^ 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = rslot + u * 16;
+          const uint32_t o = sw128_off(r, q4);
+          float4 h, l;
+          split4(ra[u], h, l);
+          *reinterpret_cast<float4*>(smem + kB2OffR + o) = h;
+          *reinterpret_cast<float4*>(smem + kB2OffR + 16384 + o) = l;
+          split4(rb[u], h, l);
+          *reinterpret_cast<float4*>(smem + kB2OffR + 32768 + o) = h;
+          *reinterpret_cast<float4*>(smem + kB2OffR + 49152 + o) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[C_ROWS_READY]);
+        for (int grp = 0; grp < n_groups; grp += 2) {
+          if (grp + 1 < n_groups) c_issue(vb8, grp + 1);
+          c_drain(va, grp);
+          if (grp + 2 < n_groups) c_issue(va, grp + 2);
+          if (grp + 1 < n_groups) c_drain(vb8, grp + 1);
+        }
+      }
+    }
+    if (MODE == 0 && cur_head >= 0) {
+      // the row threads of the last item are done once ITEM_FREE completes its phase
+      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
+      for (int i = lt; i < g.nrel; i += 128) {
+        const float v = dtab[i];
+        if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc_sc = umma_idesc_tf32(128, 32);
+    const uint32_t idesc_ac = umma_idesc_tf32(128, 32) | (1u << 16);   // B MN-major
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t tile_ctr = 0, chunk_ctr = 0;   // chunk_ctr counts score issues; acc_ctr accumulate issues
+    uint32_t acc_ctr = 0;
+    for (int item = item0; item < item1; ++item) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        mbar_wait(&bar[C_ROWS_READY], tile_ctr & 1);
+        const uint64_t r1_hi = umma_desc_sw128(sbase + kB2OffR), r1_lo = umma_desc_sw128(sbase + kB2OffR + 16384);
+        const uint64_t r2_hi = umma_desc_sw128(sbase + kB2OffR + 32768), r2_lo = umma_desc_sw128(sbase + kB2OffR + 49152);
+        auto issue_scores = [&](uint32_t cc) {   // cc = global chunk counter of the chunk whose scores are issued
+          const int st = cc & 1;
+          const uint32_t par = (cc >> 1) & 1;
+          mbar_wait(&bar[C_COL_READY0 + st], par);
+          mbar_wait(&bar[C_SC_FREE0 + st], par ^ 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t cb = sbase + kB2OffC + st * 32768;
+            const uint64_t c1_hi = umma_desc_sw128(cb), c1_lo = umma_desc_sw128(cb + 4096);
+            const uint64_t c2_hi = umma_desc_sw128(cb + 16384), c2_lo = umma_desc_sw128(cb + 16384 + 4096);
+            const uint32_t d1 = tmem_base + (uint32_t)(st * 64), d2 = d1 + 32u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_tf32(d1, r1_lo + adv, c1_hi + adv, idesc_sc, k != 0);
+              umma_tf32(d1, r1_hi + adv, c1_lo + adv, idesc_sc, 1);
+              umma_tf32(d1, r1_hi + adv, c1_hi + adv, idesc_sc, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_tf32(d2, r2_lo + adv, c2_hi + adv, idesc_sc, k != 0);
+              umma_tf32(d2, r2_hi + adv, c2_lo + adv, idesc_sc, 1);
+              umma_tf32(d2, r2_hi + adv, c2_hi + adv, idesc_sc, 1);
+            }
+            umma_commit(&bar[C_SC_FULL0 + st]);
+          }
+          __syncwarp();
+        };
+        issue_scores(chunk_ctr);
+        for (int c = 0; c < n_chunks; ++c) {
+          if (c + 1 < n_chunks) {
+            issue_scores(chunk_ctr + 1);
+          } else if (lane == 0) {
+            umma_commit(&bar[C_ROWS_FREE]);   // last score MMAs of the tile issued: rows reusable when they retire
+          }
+          __syncwarp();
+          // accumulate chunk c
+          const int st = chunk_ctr & 1;
+          const int es = (kEStages == 2) ? (int)(acc_ctr & 1) : 0;
+          const uint32_t epar = (kEStages == 2) ? ((acc_ctr >> 1) & 1) : (acc_ctr & 1);
+          mbar_wait(&bar[C_E_READY0 + es], epar);
+          if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t cb = sbase + kB2OffC + st * 32768;
+            const uint32_t eb = sbase + kB2OffE + (kEStages == 2 ? es * 32768 : 0);
+            const uint64_t e1_hi = umma_desc_sw128(eb), e1_lo = umma_desc_sw128(eb + 16384);
+            const uint64_t m1_hi = umma_desc_mn_sw128(cb + 8192, 4096), m1_lo = umma_desc_mn_sw128(cb + 12288, 4096);
+            const int left = g.N - c * 32;
+            const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
+            const uint32_t a1 = tmem_base + 128u, a2 = tmem_base + 160u;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
+              umma_tf32(a1, e1_lo + adva, m1_hi + advb, idesc_ac, (c | k) != 0);
+              umma_tf32(a1, e1_hi + adva, m1_lo + advb, idesc_ac, 1);
+              umma_tf32(a1, e1_hi + adva, m1_hi + advb, idesc_ac, 1);
+            }
+            if (MODE == 1) {
+              const uint64_t e2_hi = umma_desc_sw128(eb + 32768), e2_lo = umma_desc_sw128(eb + 49152);
+              const uint64_t m2_hi = umma_desc_mn_sw128(cb + 16384 + 8192, 4096);
+              const uint64_t m2_lo = umma_desc_mn_sw128(cb + 16384 + 12288, 4096);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
+                umma_tf32(a2, e2_lo + adva, m2_hi + advb, idesc_ac, (c | k) != 0);
+                umma_tf32(a2, e2_hi + adva, m2_lo + advb, idesc_ac, 1);
+                umma_tf32(a2, e2_hi + adva, m2_hi + advb, idesc_ac, 1);
+              }
+            }
+            umma_commit(&bar[C_E_FREE0 + es]);
+            umma_commit(&bar[C_COL_FREE0 + st]);
+            if (c == n_chunks - 1) umma_commit(&bar[C_ACC_FULL]);
+          }
+          __syncwarp();
+          ++chunk_ctr;
+          ++acc_ctr;
+        }
+      }
+    }
+  } else {
+    // =========================== row threads (thread = TMEM lane = row of the tile) ===========================
+    const int row = threadIdx.x;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int rel0 = rel_row_base(g);
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      mbar_wait(&bar[C_ITEM_READY], it & 1);
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        const int i = tile * 128 + row;
+        const bool valid = i < g.N;
+        const int ii = valid ? i : 0;
+        const int f_row = info[ii];
+        const int b_row = f_row & 0xffff;
+        const int r_row = (f_row >> 16) & 0x1f;
+        const int my_tok = tok[ii];
+        const float lse_row = sLse[ii], ds_row = sDs[ii];
+        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          const int st = chunk_ctr & 1;
+          mbar_wait(&bar[C_SC_FULL0 + st], (chunk_ctr >> 1) & 1);
+          tc_fence_after();
+          uint32_t s[32], d[32];
+          tmem_ld32(t_lane + (uint32_t)(st * 64), s);
+          tmem_ld32(t_lane + (uint32_t)(st * 64 + 32), d);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[C_SC_FREE0 + st]);
+          const int es = (kEStages == 2) ? (int)(chunk_ctr & 1) : 0;
+          const uint32_t epar = (kEStages == 2) ? ((chunk_ctr >> 1) & 1) : (chunk_ctr & 1);
+          float pv[32], dv[32];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int col = c * 32 + jj;
+            const int fc = info[col < g.NP ? col : 0];
+            const bool cvalid = col < g.N;
+            const int idx = (MODE == 0) ? (b_row + rel0 - (fc & 0xffff)) : ((fc & 0xffff) + rel0 - b_row);
+            float sv = __uint_as_float(s[jj]) + tab[(valid && cvalid) ? idx : 0];
+            sv += (((fc >> 16) & 0x1f) != r_row) ? -100.f : 0.f;
+            const float lse = (MODE == 0) ? lse_row : sLse[cvalid ? col : 0];
+            const float dsum = (MODE == 0) ? ds_row : sDs[cvalid ? col : 0];
+            float pij = (valid && cvalid) ? __expf(sv - lse) : 0.f;
+            const float dsv = pij * (__uint_as_float(d[jj]) - dsum);
+            pv[jj] = pij;
+            dv[jj] = dsv;
+            if (MODE == 0 && valid && cvalid) atomicAdd(&dtab[idx], dsv);
+          }
+          mbar_wait(&bar[C_E_FREE0 + es], epar ^ 1);
+          uint8_t* eb = smem + kB2OffE + (kEStages == 2 ? es * 32768 : 0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t o = sw128_off(row, q);
+            float4 h, l;
+            split4(make_float4(dv[q * 4], dv[q * 4 + 1], dv[q * 4 + 2], dv[q * 4 + 3]), h, l);
+            *reinterpret_cast<float4*>(eb + o) = h;
+            *reinterpret_cast<float4*>(eb + 16384 + o) = l;
+            if (MODE == 1) {
+              split4(make_float4(pv[q * 4], pv[q * 4 + 1], pv[q * 4 + 2], pv[q * 4 + 3]), h, l);
+              *reinterpret_cast<float4*>(eb + 32768 + o) = h;
+              *reinterpret_cast<float4*>(eb + 49152 + o) = l;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[C_E_READY0 + es]);
+        }
+        // ---- accumulators -> global
+        mbar_wait(&bar[C_ACC_FULL], tile_ctr & 1);
+        tc_fence_after();
+        uint32_t a1[32], a2[32];
+        tmem_ld32(t_lane + 128u, a1);
+        if (MODE == 1) tmem_ld32(t_lane + 160u, a2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[C_ACC_FREE]);
+        if (valid) {
+          if (MODE == 0) {
+            float* dst = p.dqkv + (int64_t)my_tok * 3 * C + head * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]) * p.scale, __uint_as_float(a1[q * 4 + 1]) * p.scale,
+                                           __uint_as_float(a1[q * 4 + 2]) * p.scale, __uint_as_float(a1[q * 4 + 3]) * p.scale));
+          } else {
+            float* dst = p.dqkv + ((int64_t)my_tok * 3 + 1) * C + head * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]), __uint_as_float(a1[q * 4 + 1]),
+                                           __uint_as_float(a1[q * 4 + 2]), __uint_as_float(a1[q * 4 + 3])));
+              st4(dst + C + q * 4, make_float4(__uint_as_float(a2[q * 4]), __uint_as_float(a2[q * 4 + 1]),
+                                               __uint_as_float(a2[q * 4 + 2]), __uint_as_float(a2[q * 4 + 3])));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[C_ITEM_FREE]);   // tab / dtab / info / tok / lse of this item no longer needed
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
 static int wmsa_geom(int B, int D, int H, int W, int heads, const int* window, const int* shift, WmsaGeom* g) {
   VITTA_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && heads > 0 && window && shift, VITTA_E_BADARG, "wmsa3d: bad shape");
   const int dims[3] = {D, H, W};
@@ -726,19 +1173,14 @@ int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, floa
   return 0;
 }
 
-int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
-                     float* dqkv, float* dbias_table, int B, int D, int H, int W, int heads, int head_dim,
-                     const int* window, const int* shift, float scale, void* stream) {
-  VITTA_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, VITTA_E_BADARG, "wmsa3d_bwd: null pointer");
-  VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
-  VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), VITTA_E_ALIGN,
-                  "wmsa3d_bwd: tensors must be 16-byte aligned");
+static int wmsa3d_bwd_v0(const WmsaGeom& g, const float* qkv, const float* bias_table, const float* out,
+                         const float* dout, const float* lse, float* dqkv, float* dbias_table, float scale,
+                         cudaStream_t st) {
   WmsaBwdParams p;
-  int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
-  if (rc) return rc;
+  p.g = g;
   p.qkv = qkv; p.table = bias_table; p.out = out; p.dout = dout; p.lse = lse; p.dqkv = dqkv; p.dtable = dbias_table;
   p.scale = scale;
-  p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
+  p.items = g.B * g.nw0 * g.nw1 * g.nw2 * g.heads;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes);
@@ -752,7 +1194,59 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_bwd_kernel<<<grid, kAtBwdThreads, kBwSmemBytes, (cudaStream_t)stream>>>(p);
+  wmsa3d_bwd_kernel<<<grid, kAtBwdThreads, kBwSmemBytes, st>>>(p);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || heads <= 0) return -1;
+  return (int64_t)B * D * H * W * heads;
+}
+
+int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
+                     float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
+                     const int* window, const int* shift, float scale, int impl, void* stream) {
+  VITTA_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, VITTA_E_BADARG, "wmsa3d_bwd: null pointer");
+  VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
+  VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), VITTA_E_ALIGN,
+                  "wmsa3d_bwd: tensors must be 16-byte aligned");
+  WmsaGeom g;
+  int rc = wmsa_geom(B, D, H, W, heads, window, shift, &g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1) return wmsa3d_bwd_v0(g, qkv, bias_table, out, dout, lse, dqkv, dbias_table, scale, st);
+  VITTA_CHECK_ARG(ws, VITTA_E_BADARG, "wmsa3d_bwd: workspace of vitta_wmsa3d_bwd_ws_floats() floats required");
+  const int64_t n_pairs = (int64_t)B * D * H * W * heads;
+  {
+    int64_t blocks = (n_pairs + 31) / 32;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wmsa3d_dsum_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, dout, ws, n_pairs);
+    VITTA_CHECK_LAUNCH();
+  }
+  WmsaBwd2Params p;
+  p.g = g;
+  p.qkv = qkv; p.table = bias_table; p.dout = dout; p.lse = lse; p.dsum = ws; p.dqkv = dqkv; p.dtable = dbias_table;
+  p.scale = scale;
+  p.items = B * g.nw0 * g.nw1 * g.nw2 * heads;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wmsa3d_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+    if (e != cudaSuccess) {
+      set_error("wmsa3d_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  const int sms = cached_sm_count();
+  int grid = p.items < sms ? p.items : sms;
+  p.items_per_cta = (p.items + grid - 1) / grid;
+  grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
+  wmsa3d_bwd2_kernel<0><<<grid, kAtThreads, kB2SmemBytes, st>>>(p);
+  VITTA_CHECK_LAUNCH();
+  wmsa3d_bwd2_kernel<1><<<grid, kAtThreads, kB2SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

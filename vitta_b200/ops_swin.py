@@ -127,12 +127,14 @@ def wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale):
     return out, lse
 
 
-def wmsa3d_bwd(qkv, table, out, dout, lse, dims, heads, window, shift, scale):
+def wmsa3d_bwd(qkv, table, out, dout, lse, dims, heads, window, shift, scale, impl=0):
+    """impl 0: tcgen05 kernels; impl 1: the exact-fp32 FFMA2 kernel (cross-check)."""
     b, d, h, w = dims
     dqkv = torch.empty_like(qkv)
     dtable = torch.zeros_like(table)
-    call("vitta_wmsa3d_bwd", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), b, d, h, w, heads,
-         32, _int3(window), _int3(shift), float(scale), stream_ptr())
+    ws = _workspace("wmsa_bwd", b * d * h * w * heads, qkv.device, False)
+    call("vitta_wmsa3d_bwd", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b, d, h, w,
+         heads, 32, _int3(window), _int3(shift), float(scale), int(impl), stream_ptr())
     return dqkv, dtable
 
 
