@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
     const int64_t off0 = row0 * C + c;
     ky = apply_aff(a, ldg4(x + off0));
     if (RES == 2) kr = apply_aff(a2, ldg4(res + off0));
-#pragma unroll 4
+#pragma unroll 8
     for (int r = slot; r < nrows; r += rs) {
       const int64_t off = off0 + (int64_t)r * C;
       float4 y = apply_aff(a, ld_stream4(x + off));

@@ -30,7 +30,7 @@ void set_error(const char* fmt, ...);
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kThreads = 256;     // CTA size of the streaming kernels
-constexpr int kMaxRowsPerThread = 16;
+constexpr int kMaxRowsPerThread = 32;
 
 // Chunking of a channels-last (rows x C) tensor: lanes run along C (float4 each), the remaining threads
 // of the CTA take different rows.  See include/vitta_b200.h (K1) for the contract.
@@ -89,7 +89,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // streaming load: read-once data, do not allocate in L1
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  // not volatile: a pure read-only load the compiler is free to hoist and batch (several in flight per thread)
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kThreads) stats_cl_kernel(const float* __restr
   if (active) {
     const float* base = x + row0 * C + (int64_t)col4 * 4;
     k = ldg4(base);
-#pragma unroll 4
+#pragma unroll 8
     for (int r = slot; r < nrows; r += rs) {
       float4 v = ld_stream4(base + (int64_t)r * C);
       float d;

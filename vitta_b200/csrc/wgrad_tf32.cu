@@ -44,7 +44,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   using S = WgSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bars_mem = smem + kStages * S::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bars_mem);
   uint64_t* split_bar = full_bar + kStages;

@@ -128,7 +128,8 @@ enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B
 
 __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
   float* tab = reinterpret_cast<float*>(smem + kOffTab);
@@ -708,13 +709,14 @@ __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restric
 
 constexpr int kB2OffR = 0;                         // R1 hi, R1 lo, R2 hi, R2 lo: 4 x 16 KB
 constexpr int kB2OffC = kB2OffR + 4 * 16384;       // 2 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
-constexpr int kB2OffE = kB2OffC + 2 * 32768;       // 64 KB: MODE 0: 2 stages x (E1 hi, lo); MODE 1: E1 hi, lo, E2 hi, lo
-constexpr int kB2OffTab = kB2OffE + 65536;         // bias table of the head
-constexpr int kB2OffDTab = kB2OffTab + kAtMaxRel * 4;
-constexpr int kB2OffLse = kB2OffDTab + kAtMaxRel * 4;
-constexpr int kB2OffDs = kB2OffLse + kAtMaxKeys * 4;
-constexpr int kB2OffInfo = kB2OffDs + kAtMaxKeys * 4;
-constexpr int kB2OffTok = kB2OffInfo + kAtMaxKeys * 4;
+constexpr int kB2OffE = kB2OffC + 2 * 32768;       // 64 KB: E1 hi, lo (32 KB); MODE 1: E2 hi, lo in the second half
+constexpr int kB2OffDTab = kB2OffE + 32768;        // MODE 0: 4 per-warp private table gradients (40 KB) over E's second
+                                                   // half and the 10 KB after it
+constexpr int kB2OffTab = kB2OffE + 65536 + kAtMaxRel * 4;   // bias table of the head
+constexpr int kAtColPad = 416;                     // per-token arrays padded to a multiple of the 32-column chunk
+constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;       // float2 (lse * log2e, dsum) per token
+constexpr int kB2OffInfo = kB2OffLse + kAtColPad * 8;
+constexpr int kB2OffTok = kB2OffInfo + kAtColPad * 4;
 constexpr int kB2OffBar = kB2OffTok + kAtMaxKeys * 4;
 constexpr int kB2SmemBytes = kB2OffBar + 256 + 1024;   // 224768
 
@@ -725,16 +727,15 @@ enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C
 template <int MODE>
 __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kB2OffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + C_COUNT);
   float* tab = reinterpret_cast<float*>(smem + kB2OffTab);
   float* dtab = reinterpret_cast<float*>(smem + kB2OffDTab);
   float* sLse = reinterpret_cast<float*>(smem + kB2OffLse);
-  float* sDs = reinterpret_cast<float*>(smem + kB2OffDs);
   int* info = reinterpret_cast<int*>(smem + kB2OffInfo);
   int* tok = reinterpret_cast<int*>(smem + kB2OffTok);
-  constexpr int kEStages = MODE == 0 ? 2 : 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -778,25 +779,29 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       const int wd = w / g.nw1;
       mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
       if (head != cur_head) {
-        if (MODE == 0 && cur_head >= 0) {   // flush the table gradient of the previous head
+        if (MODE == 0 && cur_head >= 0) {   // flush the table gradient of the previous head (4 private copies)
           for (int i = lt; i < g.nrel; i += 128) {
-            const float v = dtab[i];
+            const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
             if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
           }
         }
         for (int i = lt; i < g.nrel; i += 128) {
-          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head);
-          if (MODE == 0) dtab[i] = 0.f;
+          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
+          if (MODE == 0) dtab[i] = dtab[kAtMaxRel + i] = dtab[2 * kAtMaxRel + i] = dtab[3 * kAtMaxRel + i] = 0.f;
         }
         cur_head = head;
       }
-      for (int i = lt; i < g.NP; i += 128) {
-        int t, f;
-        window_token(g, b, wd, wh, ww, i, t, f);
-        tok[i] = t;
+      for (int i = lt; i < kAtColPad; i += 128) {
+        int t = -1, f = 31 << 16;                 // padding columns: region id 31 = always masked
+        float2 q = make_float2(INFINITY, 0.f);    // ... and lse = +inf: p = 0 exactly when they are queries
+        if (i < g.N) {
+          window_token(g, b, wd, wh, ww, i, t, f);
+          q.x = __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) * 1.4426950408889634f;
+          q.y = __ldg(p.dsum + (int64_t)t * g.heads + head);
+        }
+        if (i < kAtMaxKeys) tok[i] = t;
         info[i] = f;
-        sLse[i] = (t >= 0) ? __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) : 0.f;
-        sDs[i] = (t >= 0) ? __ldg(p.dsum + (int64_t)t * g.heads + head) : 0.f;
+        reinterpret_cast<float2*>(sLse)[i] = q;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       __syncwarp();
@@ -906,7 +911,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       // the row threads of the last item are done once ITEM_FREE completes its phase
       mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
       for (int i = lt; i < g.nrel; i += 128) {
-        const float v = dtab[i];
+        const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
         if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
       }
     }
@@ -961,14 +966,14 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           __syncwarp();
           // accumulate chunk c
           const int st = chunk_ctr & 1;
-          const int es = (kEStages == 2) ? (int)(acc_ctr & 1) : 0;
-          const uint32_t epar = (kEStages == 2) ? ((acc_ctr >> 1) & 1) : (acc_ctr & 1);
+          const int es = 0;
+          const uint32_t epar = acc_ctr & 1;
           mbar_wait(&bar[C_E_READY0 + es], epar);
           if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t cb = sbase + kB2OffC + st * 32768;
-            const uint32_t eb = sbase + kB2OffE + (kEStages == 2 ? es * 32768 : 0);
+            const uint32_t eb = sbase + kB2OffE;
             const uint64_t e1_hi = umma_desc_sw128(eb), e1_lo = umma_desc_sw128(eb + 16384);
             const uint64_t m1_hi = umma_desc_mn_sw128(cb + 8192, 4096), m1_lo = umma_desc_mn_sw128(cb + 12288, 4096);
             const int left = g.N - c * 32;
@@ -1006,6 +1011,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
     const int row = threadIdx.x;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int rel0 = rel_row_base(g);
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kMask2 = -100.f * kLog2e;
+    const float* __restrict__ tab2 = tab;                        // bias table, pre-multiplied by log2(e) by the loaders
+    float* __restrict__ mytab = dtab + warp * kAtMaxRel;         // this warp's private table gradient (no atomics)
+    const float2* __restrict__ sLD = reinterpret_cast<const float2*>(sLse);   // (lse * log2e, dsum) per window token
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
@@ -1016,9 +1026,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         const int ii = valid ? i : 0;
         const int f_row = info[ii];
         const int b_row = f_row & 0xffff;
-        const int r_row = (f_row >> 16) & 0x1f;
+        const int r_row = f_row & 0x1f0000;
         const int my_tok = tok[ii];
-        const float lse_row = sLse[ii], ds_row = sDs[ii];
+        const float2 ld_row = sLD[ii];
+        const int kidx = (MODE == 0) ? (b_row + rel0) : (rel0 - b_row);
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
           const int st = chunk_ctr & 1;
           mbar_wait(&bar[C_SC_FULL0 + st], (chunk_ctr >> 1) & 1);
@@ -1030,27 +1041,47 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[C_SC_FREE0 + st]);
-          const int es = (kEStages == 2) ? (int)(chunk_ctr & 1) : 0;
-          const uint32_t epar = (kEStages == 2) ? ((chunk_ctr >> 1) & 1) : (chunk_ctr & 1);
+          const uint32_t epar = chunk_ctr & 1;
+          // per element: p = 2^(s*log2e + bias2 + mask2 - lse2), ds = p * (dp - dsum).  The per-token arrays are padded to
+          // a multiple of 32 columns: padding columns carry region id 31 (always masked: p flushes to 0) and, as
+          // queries (MODE 1), lse = +inf (p = 0 exactly), so no bounds selects are needed here.
           float pv[32], dv[32];
+          const int* ic = info + c * 32;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const int col = c * 32 + jj;
-            const int fc = info[col < g.NP ? col : 0];
-            const bool cvalid = col < g.N;
-            const int idx = (MODE == 0) ? (b_row + rel0 - (fc & 0xffff)) : ((fc & 0xffff) + rel0 - b_row);
-            float sv = __uint_as_float(s[jj]) + tab[(valid && cvalid) ? idx : 0];
-            sv += (((fc >> 16) & 0x1f) != r_row) ? -100.f : 0.f;
-            const float lse = (MODE == 0) ? lse_row : sLse[cvalid ? col : 0];
-            const float dsum = (MODE == 0) ? ds_row : sDs[cvalid ? col : 0];
-            float pij = (valid && cvalid) ? __expf(sv - lse) : 0.f;
-            const float dsv = pij * (__uint_as_float(d[jj]) - dsum);
+            const int fc = ic[jj];
+            const int idx = (MODE == 0) ? (kidx - (fc & 0xffff)) : (kidx + (fc & 0xffff));
+            float t = fmaf(__uint_as_float(s[jj]), kLog2e, tab2[idx]);
+            t += ((fc & 0x1f0000) != r_row) ? kMask2 : 0.f;
+            float lse2, dsum;
+            if (MODE == 0) {
+              lse2 = ld_row.x;
+              dsum = ld_row.y;
+            } else {
+              const float2 q = sLD[c * 32 + jj];
+              lse2 = q.x;
+              dsum = q.y;
+            }
+            float pij;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(t - lse2));
             pv[jj] = pij;
-            dv[jj] = dsv;
-            if (MODE == 0 && valid && cvalid) atomicAdd(&dtab[idx], dsv);
+            dv[jj] = pij * (__uint_as_float(d[jj]) - dsum);
           }
-          mbar_wait(&bar[C_E_FREE0 + es], epar ^ 1);
-          uint8_t* eb = smem + kB2OffE + (kEStages == 2 ? es * 32768 : 0);
+          if (MODE == 0) {
+            // dTable[rel(i, j)] += dS_ij.  Lanes of a warp are distinct rows => distinct entries for one column, so a
+            // predicated straight-line LDS / FADD / STS on the warp-private copy is race free; program order keeps the
+            // successive columns of a thread coherent.
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int fc = ic[jj];
+              const int idx = kidx - (fc & 0xffff);
+              const bool ok = valid && (c * 32 + jj < g.N);
+              const float o = mytab[ok ? idx : 0];
+              if (ok) mytab[idx] = o + dv[jj];
+            }
+          }
+          mbar_wait(&bar[C_E_FREE0], epar ^ 1);
+          uint8_t* eb = smem + kB2OffE;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t o = sw128_off(row, q);
@@ -1066,7 +1097,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_E_READY0 + es]);
+          if (lane == 0) mbar_arrive(&bar[C_E_READY0]);
         }
         // ---- accumulators -> global
         mbar_wait(&bar[C_ACC_FULL], tile_ctr & 1);
