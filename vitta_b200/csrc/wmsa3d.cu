@@ -707,33 +707,82 @@ __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restric
   }
 }
 
-constexpr int kB2OffR = 0;                         // R1 hi, R1 lo, R2 hi, R2 lo: 4 x 16 KB
-constexpr int kB2OffC = kB2OffR + 4 * 16384;       // 2 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
-constexpr int kB2OffE = kB2OffC + 2 * 32768;       // 64 KB: E1 hi, lo (32 KB); MODE 1: E2 hi, lo in the second half
-constexpr int kB2OffDTab = kB2OffE + 32768;        // MODE 0: 4 per-warp private table gradients (40 KB) over E's second
-                                                   // half and the 10 KB after it
-constexpr int kB2OffTab = kB2OffE + 65536 + kAtMaxRel * 4;   // bias table of the head
-constexpr int kAtColPad = 416;                     // per-token arrays padded to a multiple of the 32-column chunk
-constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;       // float2 (lse * log2e, dsum) per token
+// TMEM-operand variants: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Issue-side helpers for warps in which EVERY lane runs the (warp-uniform) control flow and only the instruction
+// itself is predicated on one lane: operands then stay in uniform registers (no per-MMA R2UR round trips).
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum,
+                                               uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(pe)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// Shared memory holds only the B operands (column chunks) and the tables: every A operand lives in TENSOR MEMORY --
+// the row tiles (written once per tile by the loader warps with tcgen05.st, thread = row) and the dS / P chunks (written
+// by the row threads, thread = row = TMEM lane, no swizzle / proxy fence needed).  With N = 32 per MMA an A operand in
+// shared memory would cost 4 KB of smem reads per 16 tensor cycles; from TMEM it is free.
+constexpr int kB2Stages = 4;
+constexpr int kB2OffC = 0;                          // 4 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
+constexpr int kB2OffDTab = kB2OffC + kB2Stages * 32768;     // MODE 0: 4 warp-private table gradients
+constexpr int kB2OffTab = kB2OffDTab + 4 * kAtMaxRel * 4;   // bias table of the head (* log2 e)
+constexpr int kAtColPad = 416;                      // per-token arrays padded to a multiple of the 32-column chunk
+constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;        // float2 (lse * log2e, dsum) per token
 constexpr int kB2OffInfo = kB2OffLse + kAtColPad * 8;
 constexpr int kB2OffTok = kB2OffInfo + kAtColPad * 4;
-constexpr int kB2OffBar = kB2OffTok + kAtMaxKeys * 4;
-constexpr int kB2SmemBytes = kB2OffBar + 256 + 1024;   // 224768
+constexpr int kB2OffBar = kB2OffTok + kAtColPad * 4;
+constexpr int kB2SmemBytes = kB2OffBar + 512 + 1024;        // ~186 KB
+// TMEM columns
+constexpr uint32_t kTR1hi = 0, kTR1lo = 32, kTR2hi = 64, kTR2lo = 96;   // row tiles (A of the score MMAs)
+constexpr uint32_t kTSC = 128;                                          // scores: buffer b at 128 + 64 b: SC1, SC2
+constexpr uint32_t kTE1hi = 256, kTE1lo = 288, kTE2hi = 320, kTE2lo = 352;   // dS / P chunks (A of the accumulating MMAs)
+constexpr uint32_t kTACC1 = 384, kTACC2 = 416;
 
-enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C_COL_READY1, C_COL_FREE0, C_COL_FREE1,
-       C_SC_FULL0, C_SC_FULL1, C_SC_FREE0, C_SC_FREE1, C_E_READY0, C_E_READY1, C_E_FREE0, C_E_FREE1, C_ACC_FULL,
-       C_ACC_FREE, C_COUNT };
+enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C_COL_FREE0 = C_COL_READY0 + kB2Stages,
+       C_SC_FULL0 = C_COL_FREE0 + kB2Stages, C_SC_FULL1, C_SC_FREE0, C_SC_FREE1, C_E_READY, C_E_FREE, C_ACC_FULL, C_ACC_FREE,
+       C_COUNT };
+
+constexpr int kB2Threads = 384;   // warps 0-3 row threads, 4-7 loaders, 8-11 MMA issuers (SC1, SC2, ACC1, ACC2)
 
 template <int MODE>
-__global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
+__global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kB2OffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + C_COUNT);
   float* tab = reinterpret_cast<float*>(smem + kB2OffTab);
   float* dtab = reinterpret_cast<float*>(smem + kB2OffDTab);
-  float* sLse = reinterpret_cast<float*>(smem + kB2OffLse);
+  float2* sLD = reinterpret_cast<float2*>(smem + kB2OffLse);
   int* info = reinterpret_cast<int*>(smem + kB2OffInfo);
   int* tok = reinterpret_cast<int*>(smem + kB2OffTok);
 
@@ -749,26 +798,39 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
   const int item1 = min(p.items, item0 + p.items_per_cta);
 
   if (threadIdx.x == 0) {
-    const int counts[C_COUNT] = {4, 4, 4, 1, 4, 4, 1, 1, 1, 1, 4, 4, 4, 4, 1, 1, 1, 4};
-    for (int i = 0; i < C_COUNT; ++i) mbar_init(&bar[i], counts[i]);
+    constexpr int kAccIssuers = MODE == 1 ? 2 : 1;
+    for (int i = 0; i < C_COUNT; ++i) {
+      int cnt = kAccIssuers;   // E_FREE, COL_FREE, ACC_FULL: one tcgen05.commit per accumulate issuer
+      if (i == C_SC_FULL0 || i == C_SC_FULL1 || i == C_ROWS_FREE) cnt = 2;   // one commit per score issuer
+      if (i == C_ITEM_READY || i == C_ITEM_FREE || i == C_ROWS_READY || (i >= C_COL_READY0 && i < C_COL_FREE0) ||
+          i == C_SC_FREE0 || i == C_SC_FREE1 || i == C_E_READY || i == C_ACC_FREE)
+        cnt = 4;     // one elected arrive per warp of a 4-warp role
+      mbar_init(&bar[i], cnt);
+    }
     fence_barrier_init();
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: scores buffer b: SC1 at 64*b, SC2 at 64*b + 32; accumulators: ACC1 at 128, ACC2 at 160
 
   if (warp >= 4 && warp < 8) {
     // =========================== loaders ===========================
     const int lt = threadIdx.x - 128;
     const int rslot = lt >> 3, q4 = lt & 7;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);   // this warp's TMEM lane quadrant
     int cur_head = -1;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    auto flush_dtab = [&](int head) {
+      for (int i = lt; i < g.nrel; i += 128) {
+        const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
+        if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + head, v);
+      }
+    };
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
@@ -779,12 +841,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       const int wd = w / g.nw1;
       mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
       if (head != cur_head) {
-        if (MODE == 0 && cur_head >= 0) {   // flush the table gradient of the previous head (4 private copies)
-          for (int i = lt; i < g.nrel; i += 128) {
-            const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
-            if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
-          }
-        }
+        if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
         for (int i = lt; i < g.nrel; i += 128) {
           tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
           if (MODE == 0) dtab[i] = dtab[kAtMaxRel + i] = dtab[2 * kAtMaxRel + i] = dtab[3 * kAtMaxRel + i] = 0.f;
@@ -799,37 +856,37 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           q.x = __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) * 1.4426950408889634f;
           q.y = __ldg(p.dsum + (int64_t)t * g.heads + head);
         }
-        if (i < kAtMaxKeys) tok[i] = t;
+        tok[i] = t;
         info[i] = f;
-        reinterpret_cast<float2*>(sLse)[i] = q;
+        sLD[i] = q;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[C_ITEM_READY]);
-      const float* qkv_h = p.qkv + head * 32 + q4 * 4;
-      const float* do_h = p.dout + head * 32 + q4 * 4;
-      // row operand r (0: R1, 1: R2) / column operand of a token
-      auto load_row = [&](int which, int t) -> float4 {
+      const float* qkv_h = p.qkv + head * 32;
+      const float* do_h = p.dout + head * 32;
+      // row operand (which 0: R1, 1: R2) / column operand of token t; q = float4 index inside the 32-float head slice
+      auto load_row = [&](int which, int t, int q) -> float4 {
         if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == 0) {
           if (which == 0) {
-            float4 v = ldg4(qkv_h + (int64_t)t * 3 * C);
+            float4 v = ldg4(qkv_h + (int64_t)t * 3 * C + q * 4);
             v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
             return v;
           }
-          return ldg4(do_h + (int64_t)t * C);
+          return ldg4(do_h + (int64_t)t * C + q * 4);
         }
-        return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C);
+        return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q * 4);
       };
       auto load_col = [&](int which, int t) -> float4 {
         if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 0) return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C);
+        if (MODE == 0) return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q4 * 4);
         if (which == 0) {
-          float4 v = ldg4(qkv_h + (int64_t)t * 3 * C);
+          float4 v = ldg4(qkv_h + (int64_t)t * 3 * C + q4 * 4);
           v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
           return v;
         }
-        return ldg4(do_h + (int64_t)t * C);
+        return ldg4(do_h + (int64_t)t * C + q4 * 4);
       };
       // column chunks: 2 chunks per group (2 tensors x 2 rows x 2 chunks = 8 float4 per thread)
       auto c_issue = [&](float4 (&v)[8], int grp) {
@@ -837,7 +894,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         for (int u = 0; u < 8; ++u) {
           const int cc = u >> 2, which = (u >> 1) & 1, rr = u & 1;
           const int j = (grp * 2 + cc) * 32 + rslot + rr * 16;
-          const int t = (grp * 2 + cc < n_chunks && j < g.N) ? tok[j] : -1;
+          const int t = (grp * 2 + cc < n_chunks) ? tok[j] : -1;
           v[u] = load_col(which, t);
         }
       };
@@ -845,8 +902,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           if (grp * 2 + cc >= n_chunks) break;
-          const int st = chunk_ctr & 1;
-          mbar_wait(&bar[C_COL_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          const int st = chunk_ctr & (kB2Stages - 1);
+          mbar_wait(&bar[C_COL_FREE0 + st], ((chunk_ctr / kB2Stages) & 1) ^ 1);
           uint8_t* cb = smem + kB2OffC + st * 32768;
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
@@ -873,30 +930,46 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       };
       const int n_groups = (n_chunks + 1) >> 1;
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        // row tile: thread = row (TMEM lane); both rows' global loads are in flight before the wait
+        const int i = tile * 128 + (warp - 4) * 32 + lane;
+        const int trow = (i < g.N) ? tok[i] : -1;
         float4 ra[8], rb[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int i = tile * 128 + rslot + u * 16;
-          const int t = (i < g.N) ? tok[i] : -1;
-          ra[u] = load_row(0, t);
-          rb[u] = load_row(1, t);
+          ra[u] = load_row(0, trow, u);
+          rb[u] = load_row(1, trow, u);
         }
         float4 va[8], vb8[8];
         c_issue(va, 0);
         mbar_wait(&bar[C_ROWS_FREE], (tile_ctr & 1) ^ 1);
+        tc_fence_after();
+        {
+          uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = rslot + u * 16;
-          const uint32_t o = sw128_off(r, q4);
-          float4 h, l;
-          split4(ra[u], h, l);
-          *reinterpret_cast<float4*>(smem + kB2OffR + o) = h;
-          *reinterpret_cast<float4*>(smem + kB2OffR + 16384 + o) = l;
-          split4(rb[u], h, l);
-          *reinterpret_cast<float4*>(smem + kB2OffR + 32768 + o) = h;
-          *reinterpret_cast<float4*>(smem + kB2OffR + 49152 + o) = l;
+          for (int u = 0; u < 8; ++u) {
+            float4 h, l;
+            split4(ra[u], h, l);
+            hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
+            hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
+            lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
+            lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
+          }
+          tmem_st32(t_lane + kTR1hi, hi);
+          tmem_st32(t_lane + kTR1lo, lo);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 h, l;
+            split4(rb[u], h, l);
+            hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
+            hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
+            lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
+            lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
+          }
+          tmem_st32(t_lane + kTR2hi, hi);
+          tmem_st32(t_lane + kTR2lo, lo);
         }
-        fence_proxy_async();
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[C_ROWS_READY]);
         for (int grp = 0; grp < n_groups; grp += 2) {
@@ -908,101 +981,76 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       }
     }
     if (MODE == 0 && cur_head >= 0) {
-      // the row threads of the last item are done once ITEM_FREE completes its phase
-      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
-      for (int i = lt; i < g.nrel; i += 128) {
-        const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
-        if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + cur_head, v);
-      }
+      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);   // the row threads finished the last item
+      flush_dtab(cur_head);
     }
-  } else if (warp == 8) {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc_sc = umma_idesc_tf32(128, 32);
-    const uint32_t idesc_ac = umma_idesc_tf32(128, 32) | (1u << 16);   // B MN-major
+  } else if (warp >= 8) {
+    // =========================== MMA issuers ===========================
+    // Four independent issue streams (each MMA is only 128 x 32 x 8, so the serial issue chain of ONE thread would be
+    // the bottleneck): warp 8: S / S^T, warp 9: dP / dP^T, warp 10: ACC1 (dQ | dK), warp 11: ACC2 (dV, MODE 1 only).
+    // They touch disjoint accumulators; ordering against the other roles goes through the mbarriers.
+    const int which = warp & 1;
+    const bool is_score = warp < 10;
+    const uint32_t pe = (lane == 0) ? 1u : 0u;
     const uint32_t sbase = smem_u32(smem);
-    uint32_t tile_ctr = 0, chunk_ctr = 0;   // chunk_ctr counts score issues; acc_ctr accumulate issues
-    uint32_t acc_ctr = 0;
-    for (int item = item0; item < item1; ++item) {
-      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        mbar_wait(&bar[C_ROWS_READY], tile_ctr & 1);
-        const uint64_t r1_hi = umma_desc_sw128(sbase + kB2OffR), r1_lo = umma_desc_sw128(sbase + kB2OffR + 16384);
-        const uint64_t r2_hi = umma_desc_sw128(sbase + kB2OffR + 32768), r2_lo = umma_desc_sw128(sbase + kB2OffR + 49152);
-        auto issue_scores = [&](uint32_t cc) {   // cc = global chunk counter of the chunk whose scores are issued
-          const int st = cc & 1;
-          const uint32_t par = (cc >> 1) & 1;
-          mbar_wait(&bar[C_COL_READY0 + st], par);
-          mbar_wait(&bar[C_SC_FREE0 + st], par ^ 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t cb = sbase + kB2OffC + st * 32768;
-            const uint64_t c1_hi = umma_desc_sw128(cb), c1_lo = umma_desc_sw128(cb + 4096);
-            const uint64_t c2_hi = umma_desc_sw128(cb + 16384), c2_lo = umma_desc_sw128(cb + 16384 + 4096);
-            const uint32_t d1 = tmem_base + (uint32_t)(st * 64), d2 = d1 + 32u;
+    uint32_t tile_ctr = 0, chunk_ctr = 0;
+    if (is_score) {
+      const uint32_t idesc_sc = umma_idesc_tf32(128, 32);
+      const uint32_t a_hi = tmem_base + (which ? kTR2hi : kTR1hi), a_lo = tmem_base + (which ? kTR2lo : kTR1lo);
+      for (int item = item0; item < item1; ++item) {
+        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+          mbar_wait(&bar[C_ROWS_READY], tile_ctr & 1);
+          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+            const int st = chunk_ctr & (kB2Stages - 1);
+            const int sb = chunk_ctr & 1;
+            mbar_wait(&bar[C_COL_READY0 + st], (chunk_ctr / kB2Stages) & 1);
+            mbar_wait(&bar[C_SC_FREE0 + sb], ((chunk_ctr >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t cb = sbase + kB2OffC + st * 32768 + which * 16384;
+            const uint64_t c_hi = umma_desc_sw128(cb), c_lo = umma_desc_sw128(cb + 4096);
+            const uint32_t d = tmem_base + kTSC + (uint32_t)(sb * 64 + which * 32);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);
-              umma_tf32(d1, r1_lo + adv, c1_hi + adv, idesc_sc, k != 0);
-              umma_tf32(d1, r1_hi + adv, c1_lo + adv, idesc_sc, 1);
-              umma_tf32(d1, r1_hi + adv, c1_hi + adv, idesc_sc, 1);
+              const uint32_t ka = (uint32_t)(k * 8);
+              umma_tf32_ts_p(d, a_lo + ka, c_hi + adv, idesc_sc, k != 0, pe);
+              umma_tf32_ts_p(d, a_hi + ka, c_lo + adv, idesc_sc, 1, pe);
+              umma_tf32_ts_p(d, a_hi + ka, c_hi + adv, idesc_sc, 1, pe);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              umma_tf32(d2, r2_lo + adv, c2_hi + adv, idesc_sc, k != 0);
-              umma_tf32(d2, r2_hi + adv, c2_lo + adv, idesc_sc, 1);
-              umma_tf32(d2, r2_hi + adv, c2_hi + adv, idesc_sc, 1);
-            }
-            umma_commit(&bar[C_SC_FULL0 + st]);
+            umma_commit_p(&bar[C_SC_FULL0 + sb], pe);
+            if (c == n_chunks - 1) umma_commit_p(&bar[C_ROWS_FREE], pe);   // the row tile is reusable when these retire
           }
-          __syncwarp();
-        };
-        issue_scores(chunk_ctr);
-        for (int c = 0; c < n_chunks; ++c) {
-          if (c + 1 < n_chunks) {
-            issue_scores(chunk_ctr + 1);
-          } else if (lane == 0) {
-            umma_commit(&bar[C_ROWS_FREE]);   // last score MMAs of the tile issued: rows reusable when they retire
-          }
-          __syncwarp();
-          // accumulate chunk c
-          const int st = chunk_ctr & 1;
-          const int es = 0;
-          const uint32_t epar = acc_ctr & 1;
-          mbar_wait(&bar[C_E_READY0 + es], epar);
-          if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t cb = sbase + kB2OffC + st * 32768;
-            const uint32_t eb = sbase + kB2OffE;
-            const uint64_t e1_hi = umma_desc_sw128(eb), e1_lo = umma_desc_sw128(eb + 16384);
-            const uint64_t m1_hi = umma_desc_mn_sw128(cb + 8192, 4096), m1_lo = umma_desc_mn_sw128(cb + 12288, 4096);
+        }
+      }
+    } else if (which == 0 || MODE == 1) {
+      const uint32_t idesc_ac = umma_idesc_tf32(128, 32) | (1u << 16);   // B MN-major
+      const uint32_t e_hi = tmem_base + (which ? kTE2hi : kTE1hi), e_lo = tmem_base + (which ? kTE2lo : kTE1lo);
+      const uint32_t acc = tmem_base + (which ? kTACC2 : kTACC1);
+      for (int item = item0; item < item1; ++item) {
+        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+            const int st = chunk_ctr & (kB2Stages - 1);
+            mbar_wait(&bar[C_E_READY], chunk_ctr & 1);
+            if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t cb = sbase + kB2OffC + st * 32768 + which * 16384;
+            const uint64_t m_hi = umma_desc_mn_sw128(cb + 8192, 4096), m_lo = umma_desc_mn_sw128(cb + 12288, 4096);
             const int left = g.N - c * 32;
             const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
-            const uint32_t a1 = tmem_base + 128u, a2 = tmem_base + 160u;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
-              umma_tf32(a1, e1_lo + adva, m1_hi + advb, idesc_ac, (c | k) != 0);
-              umma_tf32(a1, e1_hi + adva, m1_lo + advb, idesc_ac, 1);
-              umma_tf32(a1, e1_hi + adva, m1_hi + advb, idesc_ac, 1);
-            }
-            if (MODE == 1) {
-              const uint64_t e2_hi = umma_desc_sw128(eb + 32768), e2_lo = umma_desc_sw128(eb + 49152);
-              const uint64_t m2_hi = umma_desc_mn_sw128(cb + 16384 + 8192, 4096);
-              const uint64_t m2_lo = umma_desc_mn_sw128(cb + 16384 + 12288, 4096);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
-                umma_tf32(a2, e2_lo + adva, m2_hi + advb, idesc_ac, (c | k) != 0);
-                umma_tf32(a2, e2_hi + adva, m2_lo + advb, idesc_ac, 1);
-                umma_tf32(a2, e2_hi + adva, m2_hi + advb, idesc_ac, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                const uint64_t advb = (uint64_t)(k * (1024 >> 4));
+                const uint32_t ka = (uint32_t)(k * 8);
+                umma_tf32_ts_p(acc, e_lo + ka, m_hi + advb, idesc_ac, (c | k) != 0, pe);
+                umma_tf32_ts_p(acc, e_hi + ka, m_lo + advb, idesc_ac, 1, pe);
+                umma_tf32_ts_p(acc, e_hi + ka, m_hi + advb, idesc_ac, 1, pe);
               }
             }
-            umma_commit(&bar[C_E_FREE0 + es]);
-            umma_commit(&bar[C_COL_FREE0 + st]);
-            if (c == n_chunks - 1) umma_commit(&bar[C_ACC_FULL]);
+            umma_commit_p(&bar[C_E_FREE], pe);
+            umma_commit_p(&bar[C_COL_FREE0 + st], pe);
+            if (c == n_chunks - 1) umma_commit_p(&bar[C_ACC_FULL], pe);
           }
-          __syncwarp();
-          ++chunk_ctr;
-          ++acc_ctr;
         }
       }
     }
@@ -1015,7 +1063,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
     constexpr float kMask2 = -100.f * kLog2e;
     const float* __restrict__ tab2 = tab;                        // bias table, pre-multiplied by log2(e) by the loaders
     float* __restrict__ mytab = dtab + warp * kAtMaxRel;         // this warp's private table gradient (no atomics)
-    const float2* __restrict__ sLD = reinterpret_cast<const float2*>(sLse);   // (lse * log2e, dsum) per window token
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
@@ -1031,21 +1078,19 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         const float2 ld_row = sLD[ii];
         const int kidx = (MODE == 0) ? (b_row + rel0) : (rel0 - b_row);
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = chunk_ctr & 1;
-          mbar_wait(&bar[C_SC_FULL0 + st], (chunk_ctr >> 1) & 1);
+          const int sb = chunk_ctr & 1;
+          mbar_wait(&bar[C_SC_FULL0 + sb], (chunk_ctr >> 1) & 1);
           tc_fence_after();
           uint32_t s[32], d[32];
-          tmem_ld32(t_lane + (uint32_t)(st * 64), s);
-          tmem_ld32(t_lane + (uint32_t)(st * 64 + 32), d);
+          tmem_ld32(t_lane + kTSC + (uint32_t)(sb * 64), s);
+          tmem_ld32(t_lane + kTSC + (uint32_t)(sb * 64 + 32), d);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_SC_FREE0 + st]);
-          const uint32_t epar = chunk_ctr & 1;
+          if (lane == 0) mbar_arrive(&bar[C_SC_FREE0 + sb]);
           // per element: p = 2^(s*log2e + bias2 + mask2 - lse2), ds = p * (dp - dsum).  The per-token arrays are padded to
           // a multiple of 32 columns: padding columns carry region id 31 (always masked: p flushes to 0) and, as
           // queries (MODE 1), lse = +inf (p = 0 exactly), so no bounds selects are needed here.
-          float pv[32], dv[32];
           const int* ic = info + c * 32;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
@@ -1064,8 +1109,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
             }
             float pij;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(t - lse2));
-            pv[jj] = pij;
-            dv[jj] = pij * (__uint_as_float(d[jj]) - dsum);
+            s[jj] = __float_as_uint(pij);                                          // P
+            d[jj] = __float_as_uint(pij * (__uint_as_float(d[jj]) - dsum));        // dS
           }
           if (MODE == 0) {
             // dTable[rel(i, j)] += dS_ij.  Lanes of a warp are distinct rows => distinct entries for one column, so a
@@ -1077,34 +1122,44 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
               const int idx = kidx - (fc & 0xffff);
               const bool ok = valid && (c * 32 + jj < g.N);
               const float o = mytab[ok ? idx : 0];
-              if (ok) mytab[idx] = o + dv[jj];
+              if (ok) mytab[idx] = o + __uint_as_float(d[jj]);
             }
           }
-          mbar_wait(&bar[C_E_FREE0], epar ^ 1);
-          uint8_t* eb = smem + kB2OffE;
+          // hi / lo split, then straight into tensor memory as the A operand of the accumulating MMAs
+          uint32_t lo[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t o = sw128_off(row, q);
-            float4 h, l;
-            split4(make_float4(dv[q * 4], dv[q * 4 + 1], dv[q * 4 + 2], dv[q * 4 + 3]), h, l);
-            *reinterpret_cast<float4*>(eb + o) = h;
-            *reinterpret_cast<float4*>(eb + 16384 + o) = l;
-            if (MODE == 1) {
-              split4(make_float4(pv[q * 4], pv[q * 4 + 1], pv[q * 4 + 2], pv[q * 4 + 3]), h, l);
-              *reinterpret_cast<float4*>(eb + 32768 + o) = h;
-              *reinterpret_cast<float4*>(eb + 49152 + o) = l;
-            }
+          for (int jj = 0; jj < 32; ++jj) {
+            const float x = __uint_as_float(d[jj]);
+            const float h = tf32_rna(x);
+            d[jj] = __float_as_uint(h);
+            lo[jj] = __float_as_uint(x - h);
           }
-          fence_proxy_async();
+          mbar_wait(&bar[C_E_FREE], (chunk_ctr & 1) ^ 1);
+          tc_fence_after();
+          tmem_st32(t_lane + kTE1hi, d);
+          tmem_st32(t_lane + kTE1lo, lo);
+          if (MODE == 1) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const float x = __uint_as_float(s[jj]);
+              const float h = tf32_rna(x);
+              s[jj] = __float_as_uint(h);
+              lo[jj] = __float_as_uint(x - h);
+            }
+            tmem_st32(t_lane + kTE2hi, s);
+            tmem_st32(t_lane + kTE2lo, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_E_READY0]);
+          if (lane == 0) mbar_arrive(&bar[C_E_READY]);
         }
         // ---- accumulators -> global
         mbar_wait(&bar[C_ACC_FULL], tile_ctr & 1);
         tc_fence_after();
         uint32_t a1[32], a2[32];
-        tmem_ld32(t_lane + 128u, a1);
-        if (MODE == 1) tmem_ld32(t_lane + 160u, a2);
+        tmem_ld32(t_lane + kTACC1, a1);
+        if (MODE == 1) tmem_ld32(t_lane + kTACC2, a2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -1136,7 +1191,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_bwd2_kernel(const WmsaBw
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -1275,9 +1330,9 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_bwd2_kernel<0><<<grid, kAtThreads, kB2SmemBytes, st>>>(p);
+  wmsa3d_bwd2_kernel<0><<<grid, kB2Threads, kB2SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
-  wmsa3d_bwd2_kernel<1><<<grid, kAtThreads, kB2SmemBytes, st>>>(p);
+  wmsa3d_bwd2_kernel<1><<<grid, kB2Threads, kB2SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
