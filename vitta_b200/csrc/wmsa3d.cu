@@ -23,7 +23,7 @@
 
 namespace vitta {
 
-constexpr int kAtThreads = 288;
+constexpr int kAtThreads = 288;   // (historic role layout: 4 softmax + 4 loader + 1 issuer warps)
 constexpr int kAtMaxKeys = 400;     // 392 padded to a multiple of 16 (UMMA N granularity)
 constexpr int kAtMaxRel = 2560;     // (2*8-1)*(2*7-1)*(2*7-1) = 2535 table rows
 
@@ -98,20 +98,65 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// TMEM-operand variants: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Issue-side helpers for warps in which EVERY lane runs the (warp-uniform) control flow and only the instruction
+// itself is predicated on one lane: operands then stay in uniform registers (no per-MMA R2UR round trips).
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum,
+                                               uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(pe)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // shared memory plan of the forward kernel (bytes from the 1024-aligned base)
 // ------------------------------------------------------------------------------------------------
+constexpr int kAtColPad = 416;                           // per-token arrays padded to a multiple of the 32-column chunk
+constexpr int kFwdVStages = 4;
 constexpr int kOffKhi = 0;
 constexpr int kOffKlo = kOffKhi + kAtMaxKeys * 128;      //  51200
 constexpr int kOffQhi = kOffKlo + kAtMaxKeys * 128;      // 102400
 constexpr int kOffQlo = kOffQhi + 128 * 128;             // 118784
-constexpr int kOffP = kOffQlo + 128 * 128;               // 135168: 2 stages x (hi 16 KB, lo 16 KB)
-constexpr int kOffV = kOffP + 2 * 32768;                 // 200704: 2 stages x (hi 4 KB, lo 4 KB)
-constexpr int kOffTab = kOffV + 2 * 8192;                // 217088: bias table of the current head
-constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;        // 227328
-constexpr int kOffTok = kOffInfo + kAtMaxKeys * 4;       // 228928
-constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;        // 230528
-constexpr int kAtSmemBytes = kOffBar + 256 + 1024;       // + alignment slack = 231808 <= 232448
+constexpr int kOffV = kOffQlo + 128 * 128;               // 135168: 4 stages x (hi 4 KB, lo 4 KB)
+constexpr int kOffTab = kOffV + kFwdVStages * 8192;      // bias table of the current head (* log2 e)
+constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;
+constexpr int kOffTok = kOffInfo + kAtColPad * 4;
+constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;
+constexpr int kAtSmemBytes = kOffBar + 256 + 1024;       // ~183 KB
+// TMEM columns of the forward kernel: S [0, 400), O [400, 432), P chunk hi [432, 464), lo [464, 496)
+constexpr uint32_t kFT_O = 400, kFT_Phi = 432, kFT_Plo = 464;
 
 struct WmsaFwdParams {
   const float* qkv;     // (B, D, H, W, 3, heads, 32)
@@ -123,10 +168,23 @@ struct WmsaFwdParams {
   WmsaGeom g;
 };
 
-enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_READY1, B_V_FREE0, B_V_FREE1, B_S_FULL,
-       B_S_FREE, B_P_READY0, B_P_READY1, B_P_FREE0, B_P_FREE1, B_O_FULL, B_O_FREE, B_COUNT };
+enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages,
+       B_S_FULL = B_V_FREE0 + kFwdVStages, B_S_FREE, B_P_READY, B_P_FREE, B_O_FULL, B_O_FREE, B_COUNT };
 
-__global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
+constexpr int kFwdThreads = 320;   // warps 0-3 softmax, 4-7 loaders, 8 S issuer (+ TMEM owner), 9 PV issuer
+
+__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum,
+                                            uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -148,8 +206,13 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
   const int item1 = min(p.items, item0 + p.items_per_cta);
 
   if (threadIdx.x == 0) {
-    const int counts[B_COUNT] = {4, 1, 4, 4, 1, 4, 4, 1, 1, 1, 4, 4, 4, 1, 1, 1, 4};
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bar[i], counts[i]);
+    for (int i = 0; i < B_COUNT; ++i) {
+      int cnt = 1;   // tcgen05.commit barriers
+      if (i == B_KV_READY || i == B_TAB_FREE || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i == B_S_FREE ||
+          i == B_P_READY || i == B_O_FREE)
+        cnt = 4;     // one elected arrive per warp of a 4-warp role
+      mbar_init(&bar[i], cnt);
+    }
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -177,14 +240,15 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
       const int wd = w / g.nw1;
       mbar_wait(&bar[B_KV_FREE], (it & 1) ^ 1);
       mbar_wait(&bar[B_TAB_FREE], (it & 1) ^ 1);
-      for (int i = lt; i < g.NP; i += 128) {
-        int t, f;
-        window_token(g, b, wd, wh, ww, i, t, f);
-        tok[i] = t;
+      for (int i = lt; i < kAtColPad; i += 128) {
+        int t = -1, f = 31 << 16;   // padding columns: region id 31 = always masked (and their V rows are zero)
+        if (i < g.N) window_token(g, b, wd, wh, ww, i, t, f);
+        if (i < kAtMaxKeys) tok[i] = t;
         info[i] = f;
       }
       if (head != cur_head) {
-        for (int i = lt; i < g.nrel; i += 128) tab[i] = __ldg(p.table + (int64_t)i * g.heads + head);
+        for (int i = lt; i < g.nrel; i += 128)
+          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
         cur_head = head;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");   // tok[] complete (loader warps only)
@@ -230,8 +294,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           if (grp * 4 + cc >= n_chunks) break;
-          const int st = chunk_ctr & 1;
-          mbar_wait(&bar[B_V_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
+          const int st = chunk_ctr & (kFwdVStages - 1);
+          mbar_wait(&bar[B_V_FREE0 + st], ((chunk_ctr / kFwdVStages) & 1) ^ 1);
           uint8_t* vb = smem + kOffV + st * 8192;
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
@@ -285,92 +349,100 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
       }
     }
   } else if (warp == 8) {
-    // =========================== MMA issuer ===========================
+    // =========================== S issuer: S[128 x NP] = Q K^T ===========================
+    // every lane runs the warp-uniform control flow, only the instruction is predicated on lane 0 (uniform operands)
+    const uint32_t pe = (lane == 0) ? 1u : 0u;
     const int part0 = g.NP < 256 ? g.NP : 256;
     const int part1 = g.NP - part0;
     const uint32_t idesc_s0 = umma_idesc_tf32(128, part0);
     const uint32_t idesc_s1 = part1 ? umma_idesc_tf32(128, part1) : 0;
-    const uint32_t idesc_o = umma_idesc_tf32(128, 32) | (1u << 16);   // B (= V) is MN-major
     const uint32_t sbase = smem_u32(smem);
-    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    const uint64_t q_hi = umma_desc_sw128(sbase + kOffQhi), q_lo = umma_desc_sw128(sbase + kOffQlo);
+    uint32_t it = 0, tile_ctr = 0;
     for (int item = item0; item < item1; ++item, ++it) {
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         if (tile == 0) mbar_wait(&bar[B_KV_READY], it & 1);
         mbar_wait(&bar[B_Q_READY], tile_ctr & 1);
         mbar_wait(&bar[B_S_FREE], (tile_ctr & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t q_hi = umma_desc_sw128(sbase + kOffQhi), q_lo = umma_desc_sw128(sbase + kOffQlo);
 #pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            if (part == 1 && part1 == 0) break;
-            const uint32_t koff = part ? 256 * 128 : 0;
-            const uint64_t k_hi = umma_desc_sw128(sbase + kOffKhi + koff), k_lo = umma_desc_sw128(sbase + kOffKlo + koff);
-            const uint32_t d = tmem_base + (part ? 256u : 0u);
-            const uint32_t idesc = part ? idesc_s1 : idesc_s0;
+        for (int part = 0; part < 2; ++part) {
+          if (part == 1 && part1 == 0) break;
+          const uint32_t koff = part ? 256 * 128 : 0;
+          const uint64_t k_hi = umma_desc_sw128(sbase + kOffKhi + koff), k_lo = umma_desc_sw128(sbase + kOffKlo + koff);
+          const uint32_t d = tmem_base + (part ? 256u : 0u);
+          const uint32_t idesc = part ? idesc_s1 : idesc_s0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              umma_tf32(d, q_lo + adv, k_hi + adv, idesc, k != 0);
-              umma_tf32(d, q_hi + adv, k_lo + adv, idesc, 1);
-              umma_tf32(d, q_hi + adv, k_hi + adv, idesc, 1);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_tf32_p(d, q_lo + adv, k_hi + adv, idesc, k != 0, pe);
+            umma_tf32_p(d, q_hi + adv, k_lo + adv, idesc, 1, pe);
+            umma_tf32_p(d, q_hi + adv, k_hi + adv, idesc, 1, pe);
           }
-          umma_commit(&bar[B_Q_FREE]);
-          if (tile == n_tiles - 1) umma_commit(&bar[B_KV_FREE]);
-          umma_commit(&bar[B_S_FULL]);
         }
-        __syncwarp();
+        umma_commit_p(&bar[B_Q_FREE], pe);
+        if (tile == n_tiles - 1) umma_commit_p(&bar[B_KV_FREE], pe);
+        umma_commit_p(&bar[B_S_FULL], pe);
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== PV issuer: O[128 x 32] += P_chunk V_chunk, P read from tensor memory ===============
+    const uint32_t pe = (lane == 0) ? 1u : 0u;
+    const uint32_t idesc_o = umma_idesc_tf32(128, 32) | (1u << 16);   // B (= V) is MN-major
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t tile_ctr = 0, chunk_ctr = 0;
+    for (int item = item0; item < item1; ++item) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = chunk_ctr & 1;
-          const uint32_t par = (chunk_ctr >> 1) & 1;
-          mbar_wait(&bar[B_P_READY0 + st], par);
-          mbar_wait(&bar[B_V_READY0 + st], par);
+          const int st = chunk_ctr & (kFwdVStages - 1);
+          mbar_wait(&bar[B_P_READY], chunk_ctr & 1);
+          mbar_wait(&bar[B_V_READY0 + st], (chunk_ctr / kFwdVStages) & 1);
           if (c == 0) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t pb = sbase + kOffP + st * 32768, vb = sbase + kOffV + st * 8192;
-            const uint64_t p_hi = umma_desc_sw128(pb), p_lo = umma_desc_sw128(pb + 16384);
-            const uint64_t v_hi = umma_desc_mn_sw128(vb, 4096), v_lo = umma_desc_mn_sw128(vb + 4096, 4096);
-            const int left = g.N - c * 32;
-            const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
-            const uint32_t d = tmem_base + 400u;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adva = (uint64_t)(k * 2), advb = (uint64_t)(k * (1024 >> 4));
-              umma_tf32(d, p_lo + adva, v_hi + advb, idesc_o, (c | k) != 0);
-              umma_tf32(d, p_hi + adva, v_lo + advb, idesc_o, 1);
-              umma_tf32(d, p_hi + adva, v_hi + advb, idesc_o, 1);
+          const uint32_t vb = sbase + kOffV + st * 8192;
+          const uint64_t v_hi = umma_desc_mn_sw128(vb, 4096), v_lo = umma_desc_mn_sw128(vb + 4096, 4096);
+          const int left = g.N - c * 32;
+          const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
+          const uint32_t d = tmem_base + kFT_O;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              const uint64_t advb = (uint64_t)(k * (1024 >> 4));
+              const uint32_t ka = (uint32_t)(k * 8);
+              umma_tf32_ts_p(d, tmem_base + kFT_Plo + ka, v_hi + advb, idesc_o, (c | k) != 0, pe);
+              umma_tf32_ts_p(d, tmem_base + kFT_Phi + ka, v_lo + advb, idesc_o, 1, pe);
+              umma_tf32_ts_p(d, tmem_base + kFT_Phi + ka, v_hi + advb, idesc_o, 1, pe);
             }
-            umma_commit(&bar[B_P_FREE0 + st]);
-            umma_commit(&bar[B_V_FREE0 + st]);
-            if (c == n_chunks - 1) umma_commit(&bar[B_O_FULL]);
           }
-          __syncwarp();
+          umma_commit_p(&bar[B_P_FREE], pe);
+          umma_commit_p(&bar[B_V_FREE0 + st], pe);
+          if (c == n_chunks - 1) umma_commit_p(&bar[B_O_FULL], pe);
         }
       }
     }
   } else {
     // =========================== softmax / epilogue (thread = query row = TMEM lane) ===========================
-    const int row = threadIdx.x;   // 0..127
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int rel0 = rel_row_base(g);
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kMask2 = -100.f * kLog2e;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
       mbar_wait(&bar[B_KV_READY], it & 1);   // tab / info / tok of this item are in place
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        const int i = tile * 128 + row;
+        const int i = tile * 128 + threadIdx.x;
         const bool valid = i < g.N;
         const int fi = info[valid ? i : 0];
         const int a_i = (fi & 0xffff) + rel0;
-        const int r_i = (fi >> 16) & 0x1f;
+        const int r_i = fi & 0x1f0000;
         const int my_tok = tok[valid ? i : 0];   // read before TAB_FREE is released (the loaders reuse tok[] / info[])
         mbar_wait(&bar[B_S_FULL], tile_ctr & 1);
         tc_fence_after();
-        // ---- pass 1: s += bias + mask (in place), row maximum
-        float m = -INFINITY;
+        // ---- pass 1 (log2 domain): t = s*log2e + bias2 + mask2, in place; row maximum.  Padding columns carry region
+        //      id 31 and are therefore always masked (their P is ~2^-144 and multiplies zero V rows).
+        float m2 = -INFINITY;
         for (int c0 = 0; c0 < g.NP; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(t_lane + (uint32_t)c0, r);
@@ -378,11 +450,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             const int fj = info[c0 + jj];
-            float s = __uint_as_float(r[jj]) + tab[a_i - (fj & 0xffff)];
-            s += (((fj >> 16) & 0x1f) != r_i) ? -100.f : 0.f;
-            s = (fj < 0) ? -INFINITY : s;
-            m = fmaxf(m, s);
-            r[jj] = __float_as_uint(s);
+            float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
+            t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
+            m2 = fmaxf(m2, t);
+            r[jj] = __float_as_uint(t);
           }
           tmem_st16(t_lane + (uint32_t)c0, r);
         }
@@ -391,35 +462,31 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[B_TAB_FREE]);
         }
-        // ---- pass 2: p = exp(s - m), row sum, P chunks for the PV MMAs
+        // ---- pass 2: p = 2^(t - m2), row sum; P chunks (tf32 hi / lo) go to tensor memory as the A operand of PV
         float l = 0.f;
-        const float mb = m * kLog2e;
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = chunk_ctr & 1;
-          uint32_t r[32];
+          uint32_t r[32], lo[32];
           const int cols = min(32, g.NP - c * 32);
           tmem_ld16(t_lane + (uint32_t)(c * 32), r);
           if (cols > 16) tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
           tmem_ld_wait();
-          mbar_wait(&bar[B_P_FREE0 + st], ((chunk_ctr >> 1) & 1) ^ 1);
-          uint8_t* pb = smem + kOffP + st * 32768;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 v;
-            v.x = (q * 4 + 0 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 0]), kLog2e, -mb)) : 0.f;
-            v.y = (q * 4 + 1 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 1]), kLog2e, -mb)) : 0.f;
-            v.z = (q * 4 + 2 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 2]), kLog2e, -mb)) : 0.f;
-            v.w = (q * 4 + 3 < cols) ? exp2f(fmaf(__uint_as_float(r[q * 4 + 3]), kLog2e, -mb)) : 0.f;
-            l += (v.x + v.y) + (v.z + v.w);
-            float4 h, lo;
-            split4(v, h, lo);
-            const uint32_t o = sw128_off(row, q);
-            *reinterpret_cast<float4*>(pb + o) = h;
-            *reinterpret_cast<float4*>(pb + 16384 + o) = lo;
+          for (int jj = 0; jj < 32; ++jj) {
+            float pij = 0.f;
+            if (jj < 16 || cols > 16) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(__uint_as_float(r[jj]) - m2));
+            l += pij;
+            const uint32_t h = (__float_as_uint(pij) + 0x1000u) & 0xffffe000u;   // tf32 round-to-nearest of a finite value
+            r[jj] = h;
+            lo[jj] = __float_as_uint(pij - __uint_as_float(h));
           }
-          fence_proxy_async();
+          mbar_wait(&bar[B_P_FREE], (chunk_ctr & 1) ^ 1);
+          tc_fence_after();
+          tmem_st32(t_lane + kFT_Phi, r);
+          tmem_st32(t_lane + kFT_Plo, lo);
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_P_READY0 + st]);
+          if (lane == 0) mbar_arrive(&bar[B_P_READY]);
         }
         tc_fence_before();
         __syncwarp();
@@ -428,7 +495,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
         mbar_wait(&bar[B_O_FULL], tile_ctr & 1);
         tc_fence_after();
         uint32_t o[32];
-        tmem_ld32(t_lane + 400u, o);
+        tmem_ld32(t_lane + kFT_O, o);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -440,7 +507,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) wmsa3d_fwd_kernel(const WmsaFwd
           for (int q = 0; q < 8; ++q)
             st4(dst + q * 4, make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
                                          __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv));
-          p.lse[((int64_t)wg * g.heads + head) * g.N + i] = m + logf(l);
+          p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2 + log2f(l)) * 0.6931471805599453f;
         }
       }
     }
@@ -707,47 +774,6 @@ __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restric
   }
 }
 
-// TMEM-operand variants: D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// Issue-side helpers for warps in which EVERY lane runs the (warp-uniform) control flow and only the instruction
-// itself is predicated on one lane: operands then stay in uniform registers (no per-MMA R2UR round trips).
-__device__ __forceinline__ void umma_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum,
-                                               uint32_t pe) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t pe) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(pe)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-
 // Shared memory holds only the B operands (column chunks) and the tables: every A operand lives in TENSOR MEMORY --
 // the row tiles (written once per tile by the loader warps with tcgen05.st, thread = row) and the dS / P chunks (written
 // by the row threads, thread = row = TMEM lane, no swizzle / proxy fence needed).  With N = 32 per MMA an A operand in
@@ -756,7 +782,6 @@ constexpr int kB2Stages = 4;
 constexpr int kB2OffC = 0;                          // 4 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
 constexpr int kB2OffDTab = kB2OffC + kB2Stages * 32768;     // MODE 0: 4 warp-private table gradients
 constexpr int kB2OffTab = kB2OffDTab + 4 * kAtMaxRel * 4;   // bias table of the head (* log2 e)
-constexpr int kAtColPad = 416;                      // per-token arrays padded to a multiple of the 32-column chunk
 constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;        // float2 (lse * log2e, dsum) per token
 constexpr int kB2OffInfo = kB2OffLse + kAtColPad * 8;
 constexpr int kB2OffTok = kB2OffInfo + kAtColPad * 4;
@@ -1254,7 +1279,7 @@ int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, floa
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_fwd_kernel<<<grid, kAtThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
+  wmsa3d_fwd_kernel<<<grid, kFwdThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
