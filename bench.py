@@ -336,12 +336,13 @@ def run_ours(args):
     ms_eval = timed(with_eval, max(2, args.steps // 2)) / max(2, args.steps // 2)
     sampler.stop_flag = True
 
+    # the instrumented step contains the step's collectives: every rank has to run it
+    fam = attribute_step(adapter, resident)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_tf32, which = _peaks()
-    fam = attribute_step(adapter, resident)
     gk = "gemm_tf32x3 (fwd+dgrad conv / linear)"
     g = fam[gk]
     tf = g["flops"] / (g["ms"] * 1e-3) / 1e12

@@ -28,6 +28,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 constexpr int kThreads = 256;     // CTA size of the streaming kernels
 constexpr int kMaxRowsPerThread = 32;
@@ -96,6 +97,17 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   return r;
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st8(float* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+               "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

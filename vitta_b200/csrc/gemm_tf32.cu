@@ -251,7 +251,45 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_wait();
         if (row_ok) {
           const int nbase = n0 + c0;
-          if (nbase + 32 <= p.N && p.vec_ok) {
+          if (nbase + 32 <= p.N && p.vec_ok == 2) {
+            // 256-bit path: every store / load instruction moves one full 32-byte sector per thread
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float4 v0 = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                      __uint_as_float(r[j + 3]));
+              float4 v1 = make_float4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]),
+                                      __uint_as_float(r[j + 7]));
+              if (p.bias) {
+                const float4 b0 = ldg4(p.bias + nbase + j), b1 = ldg4(p.bias + nbase + j + 4);
+                v0.x += b0.x; v0.y += b0.y; v0.z += b0.z; v0.w += b0.w;
+                v1.x += b1.x; v1.y += b1.y; v1.z += b1.z; v1.w += b1.w;
+              }
+              if (arow) st8(arow + nbase + j, v0, v1);
+              if (p.act == 1) {
+                v0.x = gelu_exact(v0.x); v0.y = gelu_exact(v0.y); v0.z = gelu_exact(v0.z); v0.w = gelu_exact(v0.w);
+                v1.x = gelu_exact(v1.x); v1.y = gelu_exact(v1.y); v1.z = gelu_exact(v1.z); v1.w = gelu_exact(v1.w);
+              }
+              if (rrow) {
+                float4 r0, r1;
+                ld8(rrow + nbase + j, r0, r1);
+                if (p.act == 2) {
+                  v0.x *= gelu_grad(r0.x) * rscale; v0.y *= gelu_grad(r0.y) * rscale;
+                  v0.z *= gelu_grad(r0.z) * rscale; v0.w *= gelu_grad(r0.w) * rscale;
+                  v1.x *= gelu_grad(r1.x) * rscale; v1.y *= gelu_grad(r1.y) * rscale;
+                  v1.z *= gelu_grad(r1.z) * rscale; v1.w *= gelu_grad(r1.w) * rscale;
+                } else {
+                  v0.x = fmaf(v0.x, rscale, r0.x); v0.y = fmaf(v0.y, rscale, r0.y);
+                  v0.z = fmaf(v0.z, rscale, r0.z); v0.w = fmaf(v0.w, rscale, r0.w);
+                  v1.x = fmaf(v1.x, rscale, r1.x); v1.y = fmaf(v1.y, rscale, r1.y);
+                  v1.z = fmaf(v1.z, rscale, r1.z); v1.w = fmaf(v1.w, rscale, r1.w);
+                }
+              } else {
+                v0.x *= rscale; v0.y *= rscale; v0.z *= rscale; v0.w *= rscale;
+                v1.x *= rscale; v1.y *= rscale; v1.z *= rscale; v1.w *= rscale;
+              }
+              st8(crow + nbase + j, v0, v1);
+            }
+          } else if (nbase + 32 <= p.N && p.vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -405,10 +443,20 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
   return 0;
 }
 
-static int pick_bn(int N, int forced) {
+static int pick_bn(int N, int forced, int64_t tiles_m = 0) {
   if (forced == 64 || forced == 128 || forced == 256) return forced;
   if (N <= 64) return 64;
   if (N <= 128 || N % 256 != 0) return 128;
+  if (tiles_m > 0) {
+    // wave quantisation: the persistent grid has one CTA per SM, so a tile count just above a multiple of the SM count
+    // wastes most of the last wave.  Compare the 256-wide tile with the 128-wide one (more, smaller tiles; its MMAs and
+    // epilogues are somewhat less efficient per flop).
+    const int sms = cached_sm_count();
+    auto wave_eff = [&](int64_t tiles) { return (double)tiles / (double)(((tiles + sms - 1) / sms) * sms); };
+    const double e256 = wave_eff(tiles_m * (N / 256));
+    const double e128 = wave_eff(tiles_m * (N / 128)) * 0.88;
+    if (e128 > e256) return 128;
+  }
   return 256;
 }
 
@@ -490,7 +538,7 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
   VITTA_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0 && aligned16(A) && aligned16(Bhi) && aligned16(Blo), VITTA_E_ALIGN,
                   "gemm_tf32x3: operands need 16-byte aligned rows (lda, ldb multiples of 4 floats)");
   VITTA_CHECK_ARG(lda >= K && ldb >= K && ldc >= N, VITTA_E_BADARG, "gemm_tf32x3: leading dimension too small");
-  const int bn = pick_bn(N, force_bn);
+  const int bn = pick_bn(N, force_bn, (M + kBM - 1) / kBM);
   CUtensorMap ta, tbh, tbl;
   {
     const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
@@ -513,6 +561,9 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
   p.aux_out = aux_out; p.row_scale = row_scale; p.rows_per_group = row_scale ? (int)rows_per_group : 1;
   p.vec_ok = aligned16(C) && (ldc % 4 == 0) && (!bias || aligned16(bias)) &&
              (!residual || (aligned16(residual) && ldr % 4 == 0)) && (!aux_out || aligned16(aux_out));
+  if (p.vec_ok && aligned32(C) && (ldc % 8 == 0) && (!residual || (aligned32(residual) && ldr % 8 == 0)) &&
+      (!aux_out || aligned32(aux_out)))
+    p.vec_ok = 2;
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
 }
 
@@ -529,7 +580,8 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
   pick_boxes(Wo, Ho, F, &BW, &BH, &BF);
   VITTA_CHECK_ARG((int64_t)BW * stride <= 256 && (int64_t)BH * stride <= 256, VITTA_E_UNSUPPORTED,
                   "conv2d_tf32x3: box exceeds the TMA limit");
-  const int bn = pick_bn(Cout, force_bn);
+  const int bn = pick_bn(Cout, force_bn,
+                         (int64_t)((Wo + BW - 1) / BW) * ((Ho + BH - 1) / BH) * ((F + BF - 1) / BF));
   CUtensorMap ta, tbh, tbl;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)F};
@@ -551,6 +603,7 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
   p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
   p.act = 0;
   p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias));
+  if (p.vec_ok && aligned32(Y) && (Cout % 8 == 0)) p.vec_ok = 2;
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
 }
 
@@ -625,6 +678,7 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
       p.tiles_w = (Wc + BW - 1) / BW; p.tiles_h = (Hc + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
       p.out_sy = stride; p.out_sx = stride; p.out_oy = a; p.out_ox = b; p.out_H = H; p.out_W = W;
       p.vec_ok = aligned16(dX) && (Cin % 4 == 0);
+      if (p.vec_ok && aligned32(dX) && (Cin % 8 == 0)) p.vec_ok = 2;
       rc = dispatch(ta, tbh, tbl, p, bn, st);
       if (rc) return rc;
     }

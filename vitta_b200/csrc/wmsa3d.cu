@@ -780,13 +780,13 @@ __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restric
 // shared memory would cost 4 KB of smem reads per 16 tensor cycles; from TMEM it is free.
 constexpr int kB2Stages = 4;
 constexpr int kB2OffC = 0;                          // 4 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
-constexpr int kB2OffDTab = kB2OffC + kB2Stages * 32768;     // MODE 0: 4 warp-private table gradients
-constexpr int kB2OffTab = kB2OffDTab + 4 * kAtMaxRel * 4;   // bias table of the head (* log2 e)
+constexpr int kB2OffDTab = kB2OffC + kB2Stages * 32768;     // MODE 0: 8 warp-private table gradients
+constexpr int kB2OffTab = kB2OffDTab + 8 * kAtMaxRel * 4;   // bias table of the head (* log2 e)
 constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;        // float2 (lse * log2e, dsum) per token
 constexpr int kB2OffInfo = kB2OffLse + kAtColPad * 8;
 constexpr int kB2OffTok = kB2OffInfo + kAtColPad * 4;
 constexpr int kB2OffBar = kB2OffTok + kAtColPad * 4;
-constexpr int kB2SmemBytes = kB2OffBar + 512 + 1024;        // ~186 KB
+constexpr int kB2SmemBytes = kB2OffBar + 256 + 1024;        // 231168 <= 232448
 // TMEM columns
 constexpr uint32_t kTR1hi = 0, kTR1lo = 32, kTR2hi = 64, kTR2lo = 96;   // row tiles (A of the score MMAs)
 constexpr uint32_t kTSC = 128;                                          // scores: buffer b at 128 + 64 b: SC1, SC2
@@ -797,7 +797,8 @@ enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C
        C_SC_FULL0 = C_COL_FREE0 + kB2Stages, C_SC_FULL1, C_SC_FREE0, C_SC_FREE1, C_E_READY, C_E_FREE, C_ACC_FULL, C_ACC_FREE,
        C_COUNT };
 
-constexpr int kB2Threads = 384;   // warps 0-3 row threads, 4-7 loaders, 8-11 MMA issuers (SC1, SC2, ACC1, ACC2)
+constexpr int kB2Threads = 512;   // warps 0-7 row threads (TMEM lane quadrant = w & 3, column half = w >> 2), 8-11 loaders,
+                                  // 12-15 MMA issuers (SC1, SC2, ACC1, ACC2); 128 registers / thread
 
 template <int MODE>
 __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
@@ -827,14 +828,15 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
     for (int i = 0; i < C_COUNT; ++i) {
       int cnt = kAccIssuers;   // E_FREE, COL_FREE, ACC_FULL: one tcgen05.commit per accumulate issuer
       if (i == C_SC_FULL0 || i == C_SC_FULL1 || i == C_ROWS_FREE) cnt = 2;   // one commit per score issuer
-      if (i == C_ITEM_READY || i == C_ITEM_FREE || i == C_ROWS_READY || (i >= C_COL_READY0 && i < C_COL_FREE0) ||
-          i == C_SC_FREE0 || i == C_SC_FREE1 || i == C_E_READY || i == C_ACC_FREE)
-        cnt = 4;     // one elected arrive per warp of a 4-warp role
+      if (i == C_ITEM_READY || i == C_ROWS_READY || (i >= C_COL_READY0 && i < C_COL_FREE0))
+        cnt = 4;     // one elected arrive per loader warp
+      if (i == C_ITEM_FREE || i == C_SC_FREE0 || i == C_SC_FREE1 || i == C_E_READY || i == C_ACC_FREE)
+        cnt = 8;     // one elected arrive per row warp
       mbar_init(&bar[i], cnt);
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -843,16 +845,18 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 12) {
     // =========================== loaders ===========================
-    const int lt = threadIdx.x - 128;
+    const int lt = threadIdx.x - 256;
     const int rslot = lt >> 3, q4 = lt & 7;
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);   // this warp's TMEM lane quadrant
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 8) * 32) << 16);   // this warp's TMEM lane quadrant
     int cur_head = -1;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     auto flush_dtab = [&](int head) {
       for (int i = lt; i < g.nrel; i += 128) {
-        const float v = (dtab[i] + dtab[kAtMaxRel + i]) + (dtab[2 * kAtMaxRel + i] + dtab[3 * kAtMaxRel + i]);
+        float v = 0.f;
+#pragma unroll
+        for (int cpy = 0; cpy < 8; ++cpy) v += dtab[cpy * kAtMaxRel + i];
         if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + head, v);
       }
     };
@@ -869,7 +873,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
         for (int i = lt; i < g.nrel; i += 128) {
           tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
-          if (MODE == 0) dtab[i] = dtab[kAtMaxRel + i] = dtab[2 * kAtMaxRel + i] = dtab[3 * kAtMaxRel + i] = 0.f;
+          if (MODE == 0) {
+#pragma unroll
+            for (int cpy = 0; cpy < 8; ++cpy) dtab[cpy * kAtMaxRel + i] = 0.f;
+          }
         }
         cur_head = head;
       }
@@ -956,7 +963,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       const int n_groups = (n_chunks + 1) >> 1;
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         // row tile: thread = row (TMEM lane); both rows' global loads are in flight before the wait
-        const int i = tile * 128 + (warp - 4) * 32 + lane;
+        const int i = tile * 128 + (warp - 8) * 32 + lane;
         const int trow = (i < g.N) ? tok[i] : -1;
         float4 ra[8], rb[8];
 #pragma unroll
@@ -964,35 +971,36 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           ra[u] = load_row(0, trow, u);
           rb[u] = load_row(1, trow, u);
         }
-        float4 va[8], vb8[8];
-        c_issue(va, 0);
         mbar_wait(&bar[C_ROWS_FREE], (tile_ctr & 1) ^ 1);
         tc_fence_after();
-        {
-          uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
             float4 h, l;
-            split4(ra[u], h, l);
+            split4(ra[half * 4 + u], h, l);
             hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
             hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
             lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
             lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
           }
-          tmem_st32(t_lane + kTR1hi, hi);
-          tmem_st32(t_lane + kTR1lo, lo);
+          tmem_st16(t_lane + kTR1hi + half * 16, hi);
+          tmem_st16(t_lane + kTR1lo + half * 16, lo);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             float4 h, l;
-            split4(rb[u], h, l);
+            split4(rb[half * 4 + u], h, l);
             hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
             hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
             lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
             lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
           }
-          tmem_st32(t_lane + kTR2hi, hi);
-          tmem_st32(t_lane + kTR2lo, lo);
+          tmem_st16(t_lane + kTR2hi + half * 16, hi);
+          tmem_st16(t_lane + kTR2lo + half * 16, lo);
         }
+        float4 va[8], vb8[8];
+        c_issue(va, 0);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -1009,13 +1017,13 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);   // the row threads finished the last item
       flush_dtab(cur_head);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // =========================== MMA issuers ===========================
     // Four independent issue streams (each MMA is only 128 x 32 x 8, so the serial issue chain of ONE thread would be
-    // the bottleneck): warp 8: S / S^T, warp 9: dP / dP^T, warp 10: ACC1 (dQ | dK), warp 11: ACC2 (dV, MODE 1 only).
+    // the bottleneck): warp 12: S / S^T, warp 13: dP / dP^T, warp 14: ACC1 (dQ | dK), warp 15: ACC2 (dV, MODE 1 only).
     // They touch disjoint accumulators; ordering against the other roles goes through the mbarriers.
     const int which = warp & 1;
-    const bool is_score = warp < 10;
+    const bool is_score = warp < 14;
     const uint32_t pe = (lane == 0) ? 1u : 0u;
     const uint32_t sbase = smem_u32(smem);
     uint32_t tile_ctr = 0, chunk_ctr = 0;
@@ -1080,9 +1088,12 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       }
     }
   } else {
-    // =========================== row threads (thread = TMEM lane = row of the tile) ===========================
-    const int row = threadIdx.x;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // =========================== row threads ===========================
+    // thread = (row of the tile = TMEM lane, column half): warps w and w + 4 share a lane quadrant and split the 32 columns
+    // of every chunk, which doubles the warps available to hide the latency of the per-element chain.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
     const int rel0 = rel_row_base(g);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kMask2 = -100.f * kLog2e;
@@ -1106,9 +1117,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           const int sb = chunk_ctr & 1;
           mbar_wait(&bar[C_SC_FULL0 + sb], (chunk_ctr >> 1) & 1);
           tc_fence_after();
-          uint32_t s[32], d[32];
-          tmem_ld32(t_lane + kTSC + (uint32_t)(sb * 64), s);
-          tmem_ld32(t_lane + kTSC + (uint32_t)(sb * 64 + 32), d);
+          uint32_t s[16], d[16];
+          tmem_ld16(t_lane + kTSC + (uint32_t)(sb * 64), s);
+          tmem_ld16(t_lane + kTSC + (uint32_t)(sb * 64 + 32), d);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -1116,9 +1127,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
           // per element: p = 2^(s*log2e + bias2 + mask2 - lse2), ds = p * (dp - dsum).  The per-token arrays are padded to
           // a multiple of 32 columns: padding columns carry region id 31 (always masked: p flushes to 0) and, as
           // queries (MODE 1), lse = +inf (p = 0 exactly), so no bounds selects are needed here.
-          const int* ic = info + c * 32;
+          const int col0 = c * 32 + half * 16;
+          const int* ic = info + col0;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
+          for (int jj = 0; jj < 16; ++jj) {
             const int fc = ic[jj];
             const int idx = (MODE == 0) ? (kidx - (fc & 0xffff)) : (kidx + (fc & 0xffff));
             float t = fmaf(__uint_as_float(s[jj]), kLog2e, tab2[idx]);
@@ -1128,7 +1140,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
               lse2 = ld_row.x;
               dsum = ld_row.y;
             } else {
-              const float2 q = sLD[c * 32 + jj];
+              const float2 q = sLD[col0 + jj];
               lse2 = q.x;
               dsum = q.y;
             }
@@ -1142,64 +1154,64 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
             // predicated straight-line LDS / FADD / STS on the warp-private copy is race free; program order keeps the
             // successive columns of a thread coherent.
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
+            for (int jj = 0; jj < 16; ++jj) {
               const int fc = ic[jj];
               const int idx = kidx - (fc & 0xffff);
-              const bool ok = valid && (c * 32 + jj < g.N);
+              const bool ok = valid && (col0 + jj < g.N);
               const float o = mytab[ok ? idx : 0];
               if (ok) mytab[idx] = o + __uint_as_float(d[jj]);
             }
           }
-          // hi / lo split, then straight into tensor memory as the A operand of the accumulating MMAs
-          uint32_t lo[32];
+          // hi / lo split (round-to-nearest tf32 of finite values), then straight into tensor memory as the A operand
+          uint32_t lo[16];
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
+          for (int jj = 0; jj < 16; ++jj) {
             const float x = __uint_as_float(d[jj]);
-            const float h = tf32_rna(x);
-            d[jj] = __float_as_uint(h);
-            lo[jj] = __float_as_uint(x - h);
+            const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+            d[jj] = h;
+            lo[jj] = __float_as_uint(x - __uint_as_float(h));
           }
           mbar_wait(&bar[C_E_FREE], (chunk_ctr & 1) ^ 1);
           tc_fence_after();
-          tmem_st32(t_lane + kTE1hi, d);
-          tmem_st32(t_lane + kTE1lo, lo);
+          tmem_st16(t_lane + kTE1hi, d);
+          tmem_st16(t_lane + kTE1lo, lo);
           if (MODE == 1) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
+            for (int jj = 0; jj < 16; ++jj) {
               const float x = __uint_as_float(s[jj]);
-              const float h = tf32_rna(x);
-              s[jj] = __float_as_uint(h);
-              lo[jj] = __float_as_uint(x - h);
+              const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+              s[jj] = h;
+              lo[jj] = __float_as_uint(x - __uint_as_float(h));
             }
-            tmem_st32(t_lane + kTE2hi, s);
-            tmem_st32(t_lane + kTE2lo, lo);
+            tmem_st16(t_lane + kTE2hi, s);
+            tmem_st16(t_lane + kTE2lo, lo);
           }
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[C_E_READY]);
         }
-        // ---- accumulators -> global
+        // ---- accumulators -> global (this thread's 16 of the 32 head channels)
         mbar_wait(&bar[C_ACC_FULL], tile_ctr & 1);
         tc_fence_after();
-        uint32_t a1[32], a2[32];
-        tmem_ld32(t_lane + kTACC1, a1);
-        if (MODE == 1) tmem_ld32(t_lane + kTACC2, a2);
+        uint32_t a1[16], a2[16];
+        tmem_ld16(t_lane + kTACC1, a1);
+        if (MODE == 1) tmem_ld16(t_lane + kTACC2, a2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[C_ACC_FREE]);
         if (valid) {
           if (MODE == 0) {
-            float* dst = p.dqkv + (int64_t)my_tok * 3 * C + head * 32;
+            float* dst = p.dqkv + (int64_t)my_tok * 3 * C + head * 32 + half * 16;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
+            for (int q = 0; q < 4; ++q)
               st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]) * p.scale, __uint_as_float(a1[q * 4 + 1]) * p.scale,
                                            __uint_as_float(a1[q * 4 + 2]) * p.scale, __uint_as_float(a1[q * 4 + 3]) * p.scale));
           } else {
-            float* dst = p.dqkv + ((int64_t)my_tok * 3 + 1) * C + head * 32;
+            float* dst = p.dqkv + ((int64_t)my_tok * 3 + 1) * C + head * 32 + half * 16;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
               st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]), __uint_as_float(a1[q * 4 + 1]),
                                            __uint_as_float(a1[q * 4 + 2]), __uint_as_float(a1[q * 4 + 3])));
               st4(dst + C + q * 4, make_float4(__uint_as_float(a2[q * 4]), __uint_as_float(a2[q * 4 + 1]),
@@ -1215,7 +1227,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
