@@ -82,8 +82,12 @@ def attribute_step(adapter, resident, step=None):
             rows, c = (_arg(a[8]), _arg(a[9])) if fwd else (_arg(a[15]), _arg(a[16]))
             nbytes = 4.0 * rows * c * (2 if fwd else 3)
             key = "ln_fwd (LayerNorm + stats, K9)" if fwd else "ln_bwd (K9 backward + hook gradient)"
-        elif name in ("vitta_conv2d_tf32x3", "vitta_conv2d_wgrad_tf32x3"):
-            if name == "vitta_conv2d_tf32x3":
+        elif name == "vitta_conv2d_dgrad_tf32x3":
+            f, ho, wo, cout, cin, kh, kw = (_arg(a[i]) for i in (1, 2, 3, 4, 7, 8, 9))
+            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
+            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
+        elif name in ("vitta_conv2d_tf32x3", "vitta_conv2d_tf32x3_ex", "vitta_conv2d_wgrad_tf32x3"):
+            if name != "vitta_conv2d_wgrad_tf32x3":
                 f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in (1, 2, 3, 4, 7, 8, 9, 10, 11))
                 key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
             else:

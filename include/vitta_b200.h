@@ -226,6 +226,12 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
                          void* stream);
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
                         int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream);
+/* Same, plus `residual` (shape of Y) added in the epilogue.  Used by the data-gradient pass of a convolution whose input
+ * also feeds the block's shortcut: dX = dgrad(dY) + dShortcut in one store instead of a separate accumulation pass
+ * (autograd's gradient sum of the residual split in TemporalBottleneck.forward, temporal_module.py:85-104). */
+int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
+                           int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
+                           int force_bn, void* stream);
 
 /* Data gradient of a STRIDED convolution: dX[F,H,W,Cin] = conv2d_backward_input(dY[F,Ho,Wo,Cout], W), stride >= 1.
  * Wthi / Wtlo: the weight split with mode 1 ([Cin][rotated tap][Cout]).  Input pixels are processed per residue class

@@ -62,6 +62,8 @@ _SIGNATURES = {
                                     C.c_int64, C.c_int, C.c_int, _P]),
     "vitta_conv2d_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _P, _P, C.c_int, _P]),
+    "vitta_conv2d_tf32x3_ex": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, _P, _P, _P, C.c_int, _P]),
     "vitta_conv2d_dgrad_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_conv2d_wgrad_ws_floats": (C.c_int64, [C.c_int] * 9),

@@ -569,6 +569,12 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
 
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
                         int KH, int KW, int stride, int pad, float* Y, const float* bias, int force_bn, void* stream) {
+  return vitta_conv2d_tf32x3_ex(X, F, H, W, Cin, Whi, Wlo, Cout, KH, KW, stride, pad, Y, bias, nullptr, force_bn, stream);
+}
+
+int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
+                           int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
+                           int force_bn, void* stream) {
   VITTA_CHECK_ARG(X && Whi && Wlo && Y && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
                   "conv2d_tf32x3: bad arguments");
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_tf32x3: bad filter");
@@ -595,15 +601,15 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
   int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn);
   if (rc) return rc;
   GemmParams p{};
-  p.C = Y; p.bias = bias; p.residual = nullptr; p.ldc = Cout; p.ldr = 0;
+  p.C = Y; p.bias = bias; p.residual = residual; p.ldc = Cout; p.ldr = Cout;
   p.M_total = 0; p.N = Cout; p.Kc = Cin; p.k_chunks = (Cin + kBK - 1) / kBK;
   p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
   p.Ho = Ho; p.Wo = Wo; p.F = F;
   p.BW = BW; p.BH = BH; p.BF = BF;
   p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
   p.act = 0;
-  p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias));
-  if (p.vec_ok && aligned32(Y) && (Cout % 8 == 0)) p.vec_ok = 2;
+  p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias)) && (!residual || aligned16(residual));
+  if (p.vec_ok && aligned32(Y) && (Cout % 8 == 0) && (!residual || aligned32(residual))) p.vec_ok = 2;
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
 }
 

@@ -12,7 +12,8 @@
 
 namespace vitta {
 
-constexpr int kWgThreads = 320;
+constexpr int kWgThreads = 448;   // warp 0 TMA, 1 MMA, 2-9 operand split (8 warps: both operands are split in-kernel), 10-13 epilogue
+constexpr int kWgSplitThreads = 256;
 constexpr int kWgRows = 32;                       // pixels per stage
 constexpr int kWgBoxBytes = kWgRows * 128;        // one {32 ch x 32 px} box = 4 KB
 constexpr int kWgBM = 128;
@@ -65,7 +66,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);
+      mbar_init(&split_bar[s], kWgSplitThreads / 32);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -170,7 +171,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kWgSplitThreads / 32) {
     const int t = threadIdx.x - 64;
     int stage = 0;
     uint32_t phase = 0;
@@ -184,8 +185,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           float4* a = reinterpret_cast<float4*>(st);
           float4* lo = reinterpret_cast<float4*>(st + S::kABytes);
 #pragma unroll
-          for (int j = 0; j < (S::kABytes / 16) / 128; ++j) {
-            const int i = j * 128 + t;
+          for (int j = 0; j < (S::kABytes / 16) / kWgSplitThreads; ++j) {
+            const int i = j * kWgSplitThreads + t;
             const float4 v = a[i];
             float4 h, l;
             h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -198,8 +199,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           float4* a = reinterpret_cast<float4*>(st + 2 * S::kABytes);
           float4* lo = reinterpret_cast<float4*>(st + 2 * S::kABytes + S::kBBytes);
 #pragma unroll
-          for (int j = 0; j < (S::kBBytes / 16) / 128; ++j) {
-            const int i = j * 128 + t;
+          for (int j = 0; j < (S::kBBytes / 16) / kWgSplitThreads; ++j) {
+            const int i = j * kWgSplitThreads + t;
             const float4 v = a[i];
             float4 h, l;
             h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);

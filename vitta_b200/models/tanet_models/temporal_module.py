@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import ops
-from ...nn import StatsBatchNorm2d, conv2d, norm_act
+from ...nn import StatsBatchNorm2d, conv2d, conv2d_shortcut, norm_act
 
 
 class TAM(nn.Module):
@@ -46,11 +46,28 @@ class TAM(nn.Module):
         n = nt // t
         if pooled is None:
             pooled = F.adaptive_avg_pool2d(x, 1).flatten(1)          # (N*T, C)
-        p_nct = pooled.view(n, t, c).permute(0, 2, 1)                # (N, C, T)
-        kern = self.G(p_nct.reshape(n * c, t)).view(n, c, self.kernel_size).permute(0, 2, 1).contiguous()   # (N, 3, C)
-        act = self.L(p_nct.contiguous()).permute(0, 2, 1).contiguous()                                       # (N, T, C)
+        p_ntc = pooled.view(n, t, c)
+        # G: per (video, channel) a softmax-normalised 3-tap kernel from the pooled T-vector
+        kern = self.G(p_ntc.permute(0, 2, 1).reshape(n * c, t)).view(n, c, self.kernel_size)
+        kern = kern.permute(0, 2, 1).contiguous()                                                    # (N, 3, C)
+        act = self._local_gate(p_ntc, n, t, c)                                                       # (N, T, C)
         x = x.contiguous(memory_format=torch.channels_last)
         return ops.TamStencilFn.apply(x, kern, act, t)
+
+    def _local_gate(self, p_ntc, n, t, c):
+        """L branch (reference :35-41,52-55) on the (N, T, C) pooled tensor.  The k=3 temporal Conv1d is evaluated as ONE
+        linear map over the three time-shifted copies (rows = (video, frame)), the k=1 Conv1d as a plain linear map:
+        identical arithmetic, but small GEMMs instead of cuDNN's conv1d paths with their NCHW<->NHWC conversions.  The
+        modules (and therefore parameter names, BatchNorm1d hooks and train/eval behaviour) are the reference's."""
+        conv_a, bn, relu, conv_b, gate = self.L
+        if (conv_a._forward_hooks or conv_b._forward_hooks or conv_a._forward_pre_hooks or conv_b._forward_pre_hooks):
+            return self.L(p_ntc.permute(0, 2, 1).contiguous()).permute(0, 2, 1).contiguous()
+        z = F.pad(p_ntc, (0, 0, 1, 1))                                                   # zero padding in t
+        x3 = torch.cat([z[:, :-2], z[:, 1:-1], z[:, 2:]], dim=2).reshape(n * t, 3 * c)    # taps t-1, t, t+1
+        w_a = conv_a.weight.permute(0, 2, 1).reshape(conv_a.out_channels, 3 * c)          # [out][tap][in]
+        hdn = relu(bn(F.linear(x3, w_a)))                                                # BatchNorm1d on (rows, C/4)
+        out = gate(F.linear(hdn, conv_b.weight.view(c, conv_b.in_channels)))
+        return out.view(n, t, c)
 
 
 class Bottleneck(nn.Module):
@@ -83,7 +100,7 @@ class TemporalBottleneck(nn.Module):
 
     def forward(self, x, want_pool=False):
         net, t = self.net, self.n_segment
-        out = conv2d(net.conv1, x)
+        out, x = conv2d_shortcut(net.conv1, x)                              # x: alias for the shortcut path
         out, pooled = norm_act(net.bn1, out, True, t, want_pool=True)       # BN + stats + ReLU + HW-pool: 1 pass
         out = self.tam(out, pooled)
         out = conv2d(net.conv2, out)

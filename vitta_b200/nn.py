@@ -81,6 +81,21 @@ def norm_act(bn, x, relu, clip_len, res=None, res_bn=None, want_pool=False):
     return y, pool
 
 
+def conv2d_shortcut(conv, x):
+    """(conv(x), alias of x): for the first convolution of a residual block whose input also feeds the shortcut.  The
+    alias' gradient is added inside the data-gradient kernel of ``conv`` (no separate accumulation pass)."""
+    if not x.is_cuda:
+        raise ops._lib.VittaError("vitta_b200 models need CUDA tensors; there is no CPU path")
+    kh, kw = conv.kernel_size
+    if (conv.bias is None and conv.groups == 1 and conv.dilation == (1, 1) and conv.in_channels % 4 == 0
+            and conv.stride == (1, 1) and conv.padding[0] == conv.padding[1] and kh == kw
+            and conv.padding_mode == 'zeros' and not conv._forward_hooks and not conv._forward_pre_hooks
+            and torch.is_grad_enabled() and x.requires_grad):
+        x = x.contiguous(memory_format=torch.channels_last)
+        return ops.conv2d_shortcut(x, conv.weight, 1, conv.padding[0])
+    return conv2d(conv, x), x
+
+
 def conv2d(conv, x):
     """nn.Conv2d call path of the vitta_b200 models: bias-free, ungrouped, undilated convolutions whose input has a
     multiple of 4 channels run on the tcgen05 3xTF32 implicit-GEMM kernel (K6); the 3-channel stem convolution is

@@ -592,8 +592,9 @@ def gemm_tf32x3(a, b_hi, b_lo, n, bias=None, residual=None, act=0, out=None, for
     return out
 
 
-def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=0):
-    """x: logical (F, Cin, H, W) in channels_last memory -> logical (F, cout, Ho, Wo) channels_last."""
+def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=0, residual=None):
+    """x: logical (F, Cin, H, W) in channels_last memory -> logical (F, cout, Ho, Wo) channels_last.
+    ``residual`` (shape of the result, channels_last) is added in the epilogue."""
     _require_cuda(x, "conv2d_tf32x3")
     if not x.is_contiguous(memory_format=CL):
         raise _lib.VittaError("conv2d_tf32x3: x must be channels_last contiguous")
@@ -601,8 +602,10 @@ def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=
     ho = (h + 2 * pad - kh) // stride + 1
     wo = (w + 2 * pad - kw) // stride + 1
     y = torch.empty((f, cout, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
-    call("vitta_conv2d_tf32x3", ptr(x), f, h, w, cin, ptr(w_hi), ptr(w_lo), cout, kh, kw, stride, pad, ptr(y), ptr(bias),
-         int(force_bn), stream_ptr())
+    if residual is not None and not (residual.shape == y.shape and residual.is_contiguous(memory_format=CL)):
+        raise _lib.VittaError("conv2d_tf32x3: residual must be channels_last with the shape of the result")
+    call("vitta_conv2d_tf32x3_ex", ptr(x), f, h, w, cin, ptr(w_hi), ptr(w_lo), cout, kh, kw, stride, pad, ptr(y), ptr(bias),
+         ptr(residual), int(force_bn), stream_ptr())
     return y
 
 
@@ -657,25 +660,32 @@ class Conv2dFn(torch.autograd.Function):
     weight gradients run on the split-K tcgen05 wgrad kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, pad):
+    def forward(ctx, x, w, stride, pad, want_alias=False):
         cout, cin, kh, kw = w.shape
         whi, wlo = weight_split(w, 0)
         y = conv2d_tf32x3(x, whi, wlo, cout, kh, kw, stride, pad)
         ctx.save_for_backward(x, w)
         ctx.geom = (stride, pad)
+        if want_alias:
+            # the input also feeds the block's shortcut: hand out an alias whose gradient is added inside the
+            # data-gradient kernel's epilogue instead of by a separate autograd accumulation pass
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, galias=None):
         x, w = ctx.saved_tensors
         stride, pad = ctx.geom
+        if galias is not None:
+            galias = galias.contiguous(memory_format=CL)
         cout, cin, kh, kw = w.shape
         gy = gy.contiguous(memory_format=CL)
         gx = gw = None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
             whi, wlo = weight_split(w, 1)
-            gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad)
+            gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
+            galias = None
             need_x = False
         elif need_x and stride > 1 and kh * kw <= 9 and cout % 4 == 0:
             whi, wlo = weight_split(w, 1)
@@ -694,8 +704,15 @@ class Conv2dFn(torch.autograd.Function):
                 gx = r[0]
             if need_w:
                 gw = r[1]
-        return gx, gw, None, None
+        if galias is not None:
+            gx = galias if gx is None else gx + galias
+        return gx, gw, None, None, None
+
+
+def conv2d_shortcut(x, w, stride, pad):
+    """conv2d(x, w) and an alias of x for the residual path (see Conv2dFn.forward)."""
+    return Conv2dFn.apply(x, w, stride, pad, True)
 
 
 def conv2d(x, w, stride, pad):
-    return Conv2dFn.apply(x, w, stride, pad)
+    return Conv2dFn.apply(x, w, stride, pad, False)
