@@ -103,3 +103,48 @@ def test_state_dict_keys_match_reference_layout():
     m = TSN(101, 8, 'RGB', base_model='resnet50', tam=True)
     tmpl = cases.tanet_state_template(101, 8)
     assert list(m.state_dict().keys()) == list(tmpl.keys())
+
+
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """args.cuda_graph: after 3 eager steps the step is captured and replayed; losses, logits and weights must follow the
+    eager adapter exactly (same kernels in the same order; deterministic reductions)."""
+    import vitta_b200
+    from vitta_b200 import synth
+    from vitta_b200.corpus.basics import OnlineAdapter
+    from vitta_b200.models.tanet_models.tanet import TSN
+    from vitta_b200.utils import norm_stats_utils as nsu
+    from vitta_b200.utils.opts import default_args
+    vitta_b200.set_fp32_exact()
+    dev = cuda_device
+    cfg = cases.TANET_CASES["tanet_t8_r64_stats_mse"]
+    g = cases.load_golden("tanet_t8_r64_stats_mse")
+    src_m, src_v = cases.src_stats_from_golden(g)
+    outs = []
+    for use_graph in (False, True):
+        nsu.reset_arenas()
+        model = TSN(cfg["K"], cfg["T"], 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
+                    non_local=False, partial_bn=False)
+        model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=1), strict=True)
+        model.base_model.fc.p = 0.0
+        model = model.to(dev)
+        args = default_args(arch='tanet', clip_length=cfg["T"], batch_size=cfg["N"], n_augmented_views=1,
+                            if_pred_consistency=False, reg_type="l1_loss", lr=1e-3, num_classes=cfg["K"],
+                            input_size=cfg["res"], moving_avg=True, cuda_graph=use_graph)
+        ad = OnlineAdapter(model, args, (src_m, src_v))
+        rec = []
+        for s in range(7):
+            x = synth.tanet_loader_tensor(synth.synth_video(cfg["N"], 1, cfg["T"], cfg["res"], seed=500 + s, tag="tta")).to(dev)
+            r = ad.adapt(x)
+            rec.append((float(r["loss_reg"]), r["output"].clone().cpu()))
+        if use_graph:
+            assert ad._graph is not None, "the step was never captured"
+        ad.hooks_off()
+        ev = ad.evaluate(x).cpu()
+        outs.append((rec, ev, ad.model.new_fc.weight.detach().cpu().clone(),
+                     ad.model.base_model.layer3[2].net.conv2.weight.detach().cpu().clone()))
+    (re, eve, w1e, w2e), (rg, evg, w1g, w2g) = outs
+    for s, ((le, oe), (lg, og)) in enumerate(zip(re, rg)):
+        assert abs(le - lg) <= 1e-6 * abs(le) + 1e-9, (s, le, lg)
+        torch.testing.assert_close(og, oe, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(evg, eve, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(w2g, w2e, rtol=1e-5, atol=1e-9)

@@ -113,6 +113,14 @@ class OnlineAdapter:
     def __init__(self, model_origin, args, stats=None, process_group=None):
         self.args = args
         self.process_group = process_group
+        # CUDA-graph replay of the whole adaptation step (args.cuda_graph): the step has static shapes, so after a few
+        # eager steps it is captured once and replayed -- ~1.6k kernel launches collapse into one graph launch.
+        self._graph = None
+        self._graph_key = None
+        self._graph_in = None
+        self._graph_out = None
+        self._eager_steps = 0
+        self._side = None
         if args.arch == 'tanet':
             self.n_clips = int(args.sample_style.split("-")[-1])
         else:
@@ -191,6 +199,52 @@ class OnlineAdapter:
 
     # -- :606-677 -------------------------------------------------------------------------------
     def adapt(self, input, target=None, criterion=None):
+        """One adaptation step.  With ``args.cuda_graph`` (and no label-dependent logging) the step is captured into a
+        CUDA graph after 3 eager steps and replayed afterwards; results are identical (same kernels, same order)."""
+        args = self.args
+        graphable = (getattr(args, 'cuda_graph', False) and criterion is None and input.is_cuda
+                     and self.process_group is None and getattr(args, 'moving_avg', False)
+                     and not args.update_only_bn_affine and args.n_gradient_steps == 1)
+        if not graphable:
+            return self._adapt_eager(input, target, criterion)
+        key = (tuple(input.shape), input.dtype)
+        if self._graph is not None and self._graph_key == key:
+            return self._replay(input)
+        if self._eager_steps < 3 or self._graph_key not in (None, key):
+            # Warm-up steps run on a SIDE stream (PyTorch's rule for whole-step capture): autograd's AccumulateGrad nodes
+            # remember the stream they were created on, and nodes created on the legacy default stream would make the
+            # capture depend on it.
+            self._eager_steps += 1
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                out = self._adapt_eager(input, target, criterion)
+            cur.wait_stream(self._side)
+            return out
+        from .. import _lib
+        self._graph_in = input.clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count
+        with torch.cuda.graph(g):
+            out = self._adapt_eager(self._graph_in, None, None)
+        self._graph_launches = _lib.launch_count - l0     # kernels of ours inside one replay
+        _lib.launch_count = l0
+        self._graph, self._graph_key, self._graph_out = g, key, out
+        return self._replay(input)     # capture does not execute: replay once to actually take this step
+
+    def _replay(self, input):
+        from .. import _lib
+        if input.data_ptr() != self._graph_in.data_ptr():
+            self._graph_in.copy_(input, non_blocking=True)
+        self._graph.replay()
+        _lib.launch_count += self._graph_launches
+        ops.bump_weight_epoch()        # the replayed SGD step changed the weights behind the split cache's back
+        return dict(self._graph_out)
+
+    def _adapt_eager(self, input, target=None, criterion=None):
         args, model = self.args, self.model
         if not self._hooks_on:
             self.hooks_on()

@@ -71,6 +71,14 @@ def allreduce_grads(grads, group):
     return outs, flat
 
 
+def pinned_bytes(ctypes_array):
+    """uint8 tensor in pinned host memory holding a ctypes structure array (source of non-blocking H2D copies)."""
+    raw = bytes(ctypes_array)
+    t = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
+    t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    return t
+
+
 class StatsArena:
     """State shared by all alignment hooks attached to one model.
 
@@ -211,8 +219,7 @@ class StatsArena:
 
     @staticmethod
     def _upload(arr):
-        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-        return host
+        return pinned_bytes(arr)
 
     def finalize(self):
         if self.finalized:
@@ -225,10 +232,12 @@ class StatsArena:
         any_mean_meter = any(not ly.moving_avg for ly in active)
         ids = tuple(ly.idx for ly in active)
         if self.desc_dirty or ids != self._desc_active or any_mean_meter:
-            self._desc_dev = self._upload(self._build_descs(active)).to(dev)
+            self._desc_host = self._upload(self._build_descs(active))
+            self._desc_dev = self._desc_host.to(dev, non_blocking=True)
             if self.process_group is not None:
                 ws = torch.distributed.get_world_size(self.process_group)
-                self._desc_gath = self._upload(self._build_descs(active, (ws, len(active)))).to(dev)
+                self._desc_gath_host = self._upload(self._build_descs(active, (ws, len(active))))
+                self._desc_gath = self._desc_gath_host.to(dev, non_blocking=True)
             if ids != self._desc_active:
                 self.loss.zero_()       # the ticket slot moves with the number of active layers
             self._desc_active = ids
@@ -499,6 +508,8 @@ class FusedSGD:
         self.param_groups = [{"params": self.params, "lr": self.lr, "momentum": self.momentum,
                               "weight_decay": self.weight_decay}]
         self._block = None
+        self._pin = []
+        self._pin_next = 0
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -517,9 +528,19 @@ class FusedSGD:
             arr[i].p, arr[i].g, arr[i].buf, arr[i].n = p.data_ptr(), g.data_ptr(), buf.data_ptr(), p.numel()
             starts.append(blk)
             blk += (p.numel() + self._block - 1) // self._block
-        tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        st = torch.tensor(starts, dtype=torch.int32).to(dev)
-        return tab, st, n, blk
+        # Pinned staging buffers allocated ONCE (no host allocation may happen while a CUDA graph is being captured) and
+        # non-blocking copies (memcpy nodes inside a capture).  Alternating slots keep the previous tables' sources intact.
+        nbytes = C.sizeof(_lib.VittaSgdTensor) * len(self.params)
+        if not self._pin:
+            self._pin = [(torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
+                          torch.empty(len(self.params), dtype=torch.int32).pin_memory()) for _ in range(4)]
+        tab_h, st_h = self._pin[self._pin_next % 4]
+        self._pin_next += 1
+        raw = bytes(arr)
+        C.memmove(tab_h.data_ptr(), raw, len(raw))
+        st_np = (C.c_int32 * n)(*starts)
+        C.memmove(st_h.data_ptr(), st_np, 4 * n)
+        return (tab_h[:len(raw)].to(dev, non_blocking=True), st_h[:n].to(dev, non_blocking=True), n, blk)
 
     @torch.no_grad()
     def step(self):
