@@ -5,7 +5,8 @@ Workload (config.workload): configs[1] of BASELINE.json -- TANet-R50 ViTTA, synt
 16x224x224 clips, 8 videos per GPU (weak scaling), one view, statistics-alignment loss only (L1), SGD over all
 parameters.  A step = train-mode forward with the 47 alignment hooks + backward + SGD on one batch.
 
-  value      device-timed throughput with the batch already resident in HBM
+  value      device-timed throughput with the batch already resident in HBM (the step is replayed as one CUDA graph after
+             3 eager steps; --no-graph times eager launches)
   e2e        the same step through the public API (OnlineAdapter.adapt) from PINNED HOST input, with the H2D copy
              and a D2H read of the loss inside the timed region
   roofline   the statistics kernel (K1) over the 29 hooked layer shapes: algorithmic bytes / CUDA-event time
@@ -264,7 +265,10 @@ def run_ours(args):
     n = N_PER_GPU
     targs = default_args(arch='tanet', clip_length=T, batch_size=n, n_augmented_views=1, if_pred_consistency=False,
                          num_classes=K_CLASSES, input_size=RES)
-    targs.cuda_graph = not args.no_graph and not args.ncu_step and world == 1   # replay the step as one CUDA graph
+    targs.cuda_graph = not args.no_graph and not args.ncu_step   # replay the step as one CUDA graph
+    targs.cuda_graph_collectives = world > 1 and not args.no_graph_collectives   # NCCL all-gather / all-reduce captured too
+    if world > 1 and args.no_graph_collectives:
+        targs.cuda_graph = False
 
     # source statistics from a clean synthetic batch through our own compute_statistics (untimed set-up)
     class DS(torch.utils.data.Dataset):
@@ -344,10 +348,11 @@ def run_ours(args):
 
     # the instrumented step contains the step's collectives: every rank has to run it
     fam = attribute_step(adapter, resident)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _hard_exit()
     peak, peak_tf32, which = _peaks()
     gk = "gemm_tf32x3 (fwd+dgrad conv / linear)"
     g = fam[gk]
@@ -387,14 +392,22 @@ def run_ours(args):
             "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, batch 8 per GPU, 1 view, "
                                    "stats-align only (L1, 47 hooks), SGD all params (BASELINE.json configs[1])",
                        "clips_per_step": world * n, "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
-                       "conv_backend": "own tcgen05 3xTF32 implicit GEMM (stem conv + stride-2 dgrad: cuDNN fp32)", "with_eval_fwd_clips_per_s": world * n * 1000.0 / ms_eval},
+                       "conv_backend": "own tcgen05 3xTF32 implicit GEMM, fwd / dgrad (incl. strided) / wgrad (3-channel stem conv: cuDNN fp32)", "with_eval_fwd_clips_per_s": world * n * 1000.0 / ms_eval},
             "e2e": {"value": world * n * 1000.0 / ms_e2e, "unit": "clips/s",
                     "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "cuda_graph": bool(targs.cuda_graph), "clocks": sampler.summary(), "roofline": roof, "roofline_stats": roof_stats,
             "cpu_baseline": cpu, "kernels": step_table}
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _hard_exit()
+
+
+def _hard_exit():
+    """Multi-rank runs end without tearing NCCL down: destroying a communicator whose collectives live inside captured
+    CUDA graphs can block.  All results are printed and flushed at this point."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
@@ -405,6 +418,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-graph-collectives", dest="no_graph_collectives", action="store_true",
+                    help="multi-GPU: do not capture the NCCL collectives (falls back to eager steps)")
     ap.add_argument("--ncu-step", dest="ncu_step", action="store_true",
                     help="run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

@@ -203,7 +203,8 @@ class OnlineAdapter:
         CUDA graph after 3 eager steps and replayed afterwards; results are identical (same kernels, same order)."""
         args = self.args
         graphable = (getattr(args, 'cuda_graph', False) and criterion is None and input.is_cuda
-                     and self.process_group is None and getattr(args, 'moving_avg', False)
+                     and (self.process_group is None or getattr(args, 'cuda_graph_collectives', False))
+                     and getattr(args, 'moving_avg', False)
                      and not args.update_only_bn_affine and args.n_gradient_steps == 1)
         if not graphable:
             return self._adapt_eager(input, target, criterion)
