@@ -364,6 +364,9 @@ def run_ours(args):
             "note": "achieved counts ALGORITHMIC fp32 flops (2MNK); the kernel issues 3 tf32 MMAs per product "
                     "(3xTF32 split for the 1e-4 fp32 parity), i.e. tensor-pipe work is 3x this",
             "tensor_pipe_frac_issued": 3.0 * tf / peak_tf32,
+            "traffic_sample": {"launch": "gemm_tf32x3_kernel<256>, layer1 conv3 (M=401408, N=256, K=64), ncu --set full, "
+                                         "profiles/r01_tanet_ncu_full.md", "dram_bytes": 460.1e6,
+                               "algorithmic_bytes": 401408 * (64 + 256) * 4.0, "us": 151.1},
             "launches_per_step": g["launches"], "ms_per_step": g["ms"]}
     fk = "bn_act_fwd (BN+stats+ReLU+pool, K4+K1)"
     f = fam[fk]
@@ -372,7 +375,11 @@ def run_ours(args):
     achieved = bytes_pass / (ms_k1 * 1e-3) / 1e9
     roof_stats = {"bound": "hbm", "kernel": "bn_act_fwd_kernel (statistics hook fused into the norm pass: K4+K1), "
                                             "timed inside the step", "achieved": gbs, "peak": peak, "peak_source": which,
-                  "unit": "GB/s", "frac": gbs / peak, "traffic": None, "launches_per_step": f["launches"],
+                  "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                  "traffic_sample": {"launch": "bn_act_fwd_kernel<0>, stem BN+ReLU (1605632 rows x 64 ch), ncu --set full, "
+                                               "profiles/r01_tanet_ncu_full.md", "dram_bytes": 767.6e6,
+                                     "algorithmic_bytes": 1605632 * 64 * 8.0, "us": 165.3},
+                  "launches_per_step": f["launches"],
                   "ms_per_step": f["ms"],
                   "k1_standalone": {"kernel": "stats_cl_kernel over the 29 hooked layer shapes (hooks on stock modules)",
                                     "achieved": achieved, "frac": achieved / peak,
