@@ -119,14 +119,6 @@ __device__ __forceinline__ void umma_tf32_ts_p(uint32_t tmem_d, uint32_t tmem_a,
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t pe) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(pe)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -172,17 +164,6 @@ enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B
        B_S_FULL = B_V_FREE0 + kFwdVStages, B_S_FREE, B_P_READY, B_P_FREE, B_O_FULL, B_O_FREE, B_COUNT };
 
 constexpr int kFwdThreads = 320;   // warps 0-3 softmax, 4-7 loaders, 8 S issuer (+ TMEM owner), 9 PV issuer
-
-__device__ __forceinline__ void umma_tf32_p(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum,
-                                            uint32_t pe) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
-      : "memory");
-}
 
 __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
