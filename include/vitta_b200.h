@@ -324,6 +324,19 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
                      float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
                      const int* window_host, const int* shift_host, float scale, int impl, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * View gathering + normalisation (the step before the hot path).
+ *   replaces, for decoded frames at the target scale: container.get_batch(frame_indices) -> crop -> Stack ->
+ *             ToTorchFormatTensor (/255) -> GroupNormalize (models/tanet_models/video_dataset.py:318-345,
+ *             models/tanet_models/transforms.py:627-690) and the Swin pipeline's Normalize + FormatShape('NCTHW').
+ *   frames: (F, H, W, 3) uint8 device; idx: (n_idx = V*T) int32 device, clamped to [0, F-1];
+ *   mean3_host / std3_host: three HOST floats each on the [0, 1] scale (utils/opts.py:4-5);
+ *   layout 0: out (V*T*3, out_h, out_w) (TANet loader);  layout 1: out (V, 3, T, out_h, out_w) (Swin loader).
+ * ---------------------------------------------------------------------------------------------- */
+int vitta_gather_normalize_u8(const uint8_t* frames, int F, int H, int W, const int32_t* idx, int n_idx, int crop_y,
+                              int crop_x, int out_h, int out_w, const float* mean3_host, const float* std3_host, int layout,
+                              int T, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

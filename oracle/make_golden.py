@@ -392,10 +392,37 @@ def run_unit_case():
     print("wrote units", len(out), "arrays")
 
 
+def run_views_case():
+    """Frame indices of the reference's own view sampler (models/tanet_models/video_dataset.py:159-196) for the
+    deterministic styles, over a grid of video lengths / clip lengths / view counts."""
+    import importlib
+    ref_harness.load_reference()
+    vd = importlib.import_module("models.tanet_models.video_dataset")
+
+    class Rec:
+        def __init__(self, n):
+            self.num_frames = n
+    out = {}
+    for style in ("uniform", "dense", "uniform_equidist", "dense_equidist"):
+        for nf in (9, 16, 31, 64, 100, 177, 300):
+            for t in (8, 16, 32):
+                for views in (1, 2, 3):
+                    ds = object.__new__(vd.Video_TANetDataSet)
+                    ds.num_segments, ds.new_length, ds.n_tta_aug_views = t, 1, views
+                    idx = ds._sample_tta_augmented_views(Rec(nf), style)
+                    idx = np.minimum(np.asarray(idx), nf - 1)          # the clamp of get() (:328)
+                    out["%s/%d/%d/%d" % (style, nf, t, views)] = idx.astype(np.int64)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "views.npz"), **out)
+    print("wrote views", len(out), "index vectors")
+
+
 def main(argv):
     want = set(argv)
     if not want or "units" in want:
         run_unit_case()
+    if not want or "views" in want:
+        run_views_case()
     for name, cfg in TANET_CASES.items():
         if not want or name in want:
             run_model_case(name, cfg, "tanet")

@@ -215,6 +215,51 @@ def test_window_attention_fwd_bwd_vs_reference(cuda_device, b, d, h, w, heads, w
 
 
 # ----------------------------------------------------------------------------------------------
+# one whole block with live DropPath (per-sample factors in the GEMM epilogues, scaled gradients in the backward)
+# ----------------------------------------------------------------------------------------------
+def test_swin_block_with_drop_path_vs_float64(cuda_device):
+    """SwinTransformerBlock3D (shifted) with fixed per-sample DropPath factors against a float64 restatement of
+    swin_transformer.py:215-274 built from the oracle's pieces.  Covers row_scale in the proj / fc2 epilogues, the scaled
+    branch gradients, the GELU' epilogue and the shortcut-gradient fusion in the LayerNorm backward."""
+    from oracle import vitta_oracle as O
+    from vitta_b200.models.videoswintransformer_models.swin_transformer import SwinTransformerBlock3D
+    b, d, h, w, c, heads = 3, 8, 14, 14, 64, 2
+    window, shift = (8, 7, 7), (4, 3, 3)
+    torch.manual_seed(3)
+    blk = SwinTransformerBlock3D(c, heads, window, shift, drop_path=0.3).to(cuda_device)
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.copy_(torch.randn_like(p_) * (0.3 if p_.dim() == 1 else 0.08))
+        blk.norm1.weight.add_(1.0)
+        blk.norm2.weight.add_(1.0)
+    f1 = torch.tensor([0.0, 1.0 / 0.7, 1.0 / 0.7], device=cuda_device)
+    f2 = torch.tensor([1.0 / 0.7, 0.0, 1.0 / 0.7], device=cuda_device)
+    seq = iter([f1, f2])
+    blk._drop_factors = lambda n, dev: next(seq)          # deterministic DropPath draws
+    x = _rnd(b, d, h, w, c, seed=5).requires_grad_(True)
+    y = blk(x)
+    go = _rnd(*y.shape, seed=6)
+    y.backward(go)
+    # float64 reference
+    sd = {"blk." + k: v.detach().double().cpu().requires_grad_(v.dtype.is_floating_point) for k, v in blk.state_dict().items()
+          if "relative_position_index" not in k}
+    xd = x.detach().double().cpu().requires_grad_(True)
+    facs = iter([f1.double().cpu(), f2.double().cpu()])
+    gen = lambda shape, keep: next(facs).view(shape) * keep     # _drop_path multiplies by mask / keep
+    ws, ss = O.swin_window_and_shift((d, h, w), window, shift)
+    mask = O.swin_attn_mask(d, h, w, ws, ss).double()
+    ref = O.swin_block(xd, sd, "blk", heads, window, shift, mask, O.swin_rel_index(window), None, 0.3, gen)
+    ref.backward(go.double().cpu())
+    cases.assert_close(y.detach().cpu(), ref.detach(), 2e-5, 2e-5, "block output")
+    cases.assert_close(x.grad.cpu(), xd.grad, 1e-4, 2e-5 * float(xd.grad.abs().max()), "block input gradient")
+    for k in ("attn.qkv.weight", "attn.proj.bias", "mlp.fc1.weight", "mlp.fc2.bias", "norm2.weight",
+              "attn.relative_position_bias_table"):
+        gp = dict(blk.named_parameters())[k].grad.cpu()
+        gr = sd["blk." + k].grad
+        cases.assert_close(gp, gr, 2e-4, 3e-5 * float(gr.abs().max()), "grad " + k)
+
+
+# ----------------------------------------------------------------------------------------------
 # the whole Swin adaptation step vs the reference golden vectors
 # ----------------------------------------------------------------------------------------------
 def _build_swin(cfg, dev):

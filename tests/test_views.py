@@ -1,0 +1,47 @@
+"""View sampling: index rule against vectors recorded from the reference's own sampler (CPU),
+gather + normalise kernel against torch (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+
+def test_view_indices_match_reference_sampler():
+    from vitta_b200.corpus.views import sample_tta_view_indices
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "views.npz"))
+    assert len(g.files) == 4 * 7 * 3 * 3
+    for key in g.files:
+        style, nf, t, views = key.split("/")
+        got = sample_tta_view_indices(int(nf), int(t), int(views), style)
+        want = g[key]
+        assert got.shape == want.shape and (got == want).all(), (key, got, want)   # index work: bit exact
+
+
+def test_unknown_style_is_loud():
+    from vitta_b200.corpus.views import sample_tta_view_indices
+    with pytest.raises(NotImplementedError):
+        sample_tta_view_indices(100, 16, 2, "uniform_rand")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch", ["tanet", "videoswintransformer"])
+def test_views_to_device_vs_torch(cuda_device, arch):
+    from vitta_b200 import synth
+    from vitta_b200.corpus.views import sample_tta_view_indices, views_to_device
+    f, h, w, t, views = 37, 70, 90, 8, 2
+    rng = np.random.Generator(np.random.PCG64(5))
+    frames = torch.from_numpy(rng.integers(0, 256, (f, h, w, 3), dtype=np.uint8))
+    idx = sample_tta_view_indices(f, t, views)
+    crop = (3, 11, 64, 64)
+    out = views_to_device(frames.to(cuda_device), idx, t, arch, crop)
+    x = frames[torch.as_tensor(idx)][:, 3:67, 11:75, :].float() / 255.0           # (V*T, h, w, 3)
+    x = (x - torch.tensor(synth.INPUT_MEAN)) / torch.tensor(synth.INPUT_STD)
+    x = x.permute(0, 3, 1, 2)                                                      # (V*T, 3, h, w)
+    if arch == "tanet":
+        want = x.reshape(views * t * 3, 64, 64)
+    else:
+        want = x.reshape(views, t, 3, 64, 64).permute(0, 2, 1, 3, 4)
+    torch.testing.assert_close(out.cpu(), want.contiguous(), rtol=1e-6, atol=1e-6)
