@@ -208,9 +208,16 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
  *   of the data-gradient pass: transposed, filter rotated by 180 degrees).   hi = rna_tf32(x), lo = x - hi.
  * vitta_gemm_tf32x3: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) then act (0 none, 1 exact GELU) then (+ residual[M,N]).
  *   Row-major, leading dimensions in floats; lda, ldb multiples of 4; K tail and ragged M/N handled (TMA zero fill).
- *   force_bn: 0 = choose the N tile automatically, else 64 / 128 / 256.
+ *   force_bn: 0 = choose the N tile automatically, else 64 / 128 / 256; | VITTA_GEMM_FORCE_SS keeps the split A tile in
+ *   shared memory, | VITTA_GEMM_FORCE_TS holds it in tensor memory (N tiles of 64 / 128: `tcgen05.mma [d], [a_tmem], b`).
+ * vitta_gemm_set_operand_form: process-wide version of those flags (0 automatic, 1 shared memory, 2 tensor memory), also
+ *   honoured by the weight-gradient kernel; for timing / cross-checking the forms (they differ only in the fp32
+ *   summation order of the accumulator chains).
  * vitta_conv2d_tf32x3: Y[F,Ho,Wo,Cout] = conv2d(X[F,H,W,Cin], W[Cout][KH][KW][Cin], stride, pad) (+ bias), NHWC,
  *   Cin multiple of 4.  Padding comes from the TMA out-of-bounds zero fill; no im2col buffer exists. */
+#define VITTA_GEMM_FORCE_SS 0x1000
+#define VITTA_GEMM_FORCE_TS 0x2000
+int vitta_gemm_set_operand_form(int form);
 int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int Cc, int mode, void* stream);
 int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                       int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,

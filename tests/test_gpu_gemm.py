@@ -20,7 +20,7 @@ def _err_ok(got, ref64, absprod64, k=1024, tol=2e-6):
 
 @pytest.mark.parametrize("m,n,k", [(128, 64, 32), (128, 128, 64), (256, 256, 128), (200, 96, 100), (1000, 320, 256),
                                    (6272, 2048, 512), (25088, 64, 256), (392, 384, 128), (37, 5, 36)])
-@pytest.mark.parametrize("force_bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("force_bn", [0, 64, 128, 256, 64 | 0x2000, 128 | 0x2000])   # 0x2000: tensor-memory A operands
 def test_gemm_tf32x3_vs_float64(cuda_device, m, n, k, force_bn):
     from vitta_b200 import ops
     g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
@@ -34,6 +34,21 @@ def test_gemm_tf32x3_vs_float64(cuda_device, m, n, k, force_bn):
     rel = _err_ok(out, ref, absprod, k)
     # and it is an fp32-grade result, not a TF32 one
     assert rel < 2e-6
+
+
+@pytest.mark.parametrize("bn", [64, 128])
+def test_gemm_operand_forms_agree(cuda_device, bn):
+    """A from tensor memory and A from shared memory issue the same products on the same hi/lo values; only the number
+    of accumulator chains (= the fp32 summation order) differs, so the results agree to fp32 rounding."""
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(bn)
+    m, n, k = 3000, 192, 296
+    a = torch.randn(m, k, generator=g).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).to(cuda_device)
+    bh, bl = ops.split_tf32(b)
+    t = ops.gemm_tf32x3(a, bh, bl, n, force_bn=bn)
+    s = ops.gemm_tf32x3(a, bh, bl, n, force_bn=bn | 0x2000)
+    assert float((t - s).abs().max()) <= 4e-6 * float(s.abs().max())
 
 
 def test_gemm_epilogues(cuda_device):
@@ -118,6 +133,30 @@ def test_conv2d_wgrad_tf32x3_vs_float64(cuda_device, f, h, w, cin, cout, kh, str
     F.conv2d(x.double().abs(), wa, None, stride, pad).backward(gy.double().abs())
     assert gw.shape == wt.grad.shape and gw.is_contiguous()
     _err_ok(gw, wt.grad, wa.grad, f * ho * wo)
+
+
+@pytest.mark.parametrize("f,h,cin,cout,kh,stride,pad", [(6, 28, 128, 128, 3, 1, 1), (16, 14, 256, 64, 1, 1, 0),
+                                                        (3, 28, 64, 192, 3, 2, 1)])
+def test_conv_operand_forms_agree(cuda_device, f, h, cin, cout, kh, stride, pad):
+    """vitta_gemm_set_operand_form: shared-memory A operands (1) against tensor-memory A operands (2) for forward, data
+    gradient and weight gradient -- same products, different accumulator-chain count, so equal to fp32 rounding."""
+    from vitta_b200 import _lib, ops
+    g = torch.Generator().manual_seed(f + cin)
+    x = torch.randn(f, cin, h, h, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, kh, kh, generator=g) / (cin * kh * kh) ** 0.5).to(cuda_device)
+    res = []
+    try:
+        for form in (1, 2):
+            _lib.call("vitta_gemm_set_operand_form", form)
+            x1 = x.clone(memory_format=torch.channels_last).requires_grad_(True)
+            w1 = wt.clone().requires_grad_(True)
+            y = ops.conv2d(x1, w1, stride, pad)
+            y.backward(torch.ones_like(y) * 0.5)
+            res.append((y.detach(), x1.grad, w1.grad))
+    finally:
+        _lib.call("vitta_gemm_set_operand_form", 0)
+    for a, b in zip(*res):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
 
 
 def test_conv2d_autograd_matches_torch(cuda_device):

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "vitta_gemm_set_operand_form": (C.c_int, [C.c_int]),
     "vitta_split_tf32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_gemm_tf32x3": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
                                     C.c_int64, C.c_int, C.c_int, _P]),

@@ -12,15 +12,17 @@
 //   epilogue warps drain the other buffer (tcgen05.ld 32x32b) with the fused bias / GELU / residual epilogue.
 // * Persistent: grid = min(#tiles, #SMs); tiles are walked n-fastest so CTAs running together share an A panel in L2.
 //
-// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = operand split, 6-9 = epilogue.
+// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-9 = operand split, 10-13 = epilogue.
+// (Eight split warps: profiling showed the four-warp split ~80 % busy per stage at BN = 64 -- LDS latency under
+// tensor-core smem traffic, the rounding ALU work and the proxy fence -- i.e. it, not the tensor pipe, set the stage time.)
 #include "tc05.cuh"
 
 namespace vitta {
 
 constexpr int kBM = 128;         // UMMA M (one TMEM lane per accumulator row)
 constexpr int kBK = 32;          // fp32 elements per stage row = 128 B = one swizzle atom row
-constexpr int kGemmThreads = 320;
-constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
+constexpr int kGemmThreads = 448;
+constexpr int kSplitWarp0 = 2, kSplitWarps = 8, kEpiWarp0 = kSplitWarp0 + kSplitWarps;   // epilogue: warps 10-13
 
 struct GemmParams {
   float* C;
@@ -52,22 +54,40 @@ struct GemmParams {
 // ------------------------------------------------------------------------------------------------
 // shared memory plan
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// TS = true (BN <= 128): the split warps move the A tile into TENSOR MEMORY (hi | lo, thread = row, tcgen05.st) and the
+// MMAs take A from there ([d], [a_tmem], b_desc).  Shared memory then carries the raw A landing zone and the B tiles
+// only: per stage the smem port sees TMA writes + one A read + the B operand reads, instead of additionally the
+// hi/lo write-back and 12 A operand reads -- the SS form saturates the 128 B/clk shared-memory port long before the
+// tensor pipe (BN = 64: ~152 KB per 384 MMA cycles), which is what bounds the narrow-N tiles.
+template <int BN, bool TS>
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 128) ? 3 : 2;
+  static_assert(!TS || BN <= 128, "the TMEM-operand form needs 2*BN accumulator columns + 64 columns per stage");
+  static constexpr int kStages = TS ? 4 : ((BN <= 128) ? 3 : 2);
   static constexpr int kABytes = kBM * kBK * 4;   // 16 KB
   static constexpr int kBBytes = BN * kBK * 4;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBOff = TS ? kABytes : 2 * kABytes;   // B hi tile offset inside a stage (B lo follows)
+  static constexpr int kStageBytes = kBOff + 2 * kBBytes;
   static constexpr int kBarBytes = 1024;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // + alignment slack
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // kCat: the hi and lo tiles of B are adjacent in shared memory, so  a_hi x [b_hi ; b_lo]  is ONE MMA of N = 2*BN whose
+  // result lands in two column sets (hi*hi | hi*lo) that the epilogue adds; with a_lo x b_hi that is 2 MMAs per k-step
+  // instead of 3 for the same flops.  Profiling (profiles/r01_gemm_issue.md) shows the single issuing thread ~65 % busy
+  // at BN = 64 (~55 cycles per tcgen05.mma through the elect / uniform-register sequence), i.e. the instruction count,
+  // not the tensor pipe, bounds the narrow-N tiles.  Needs 2 x 2*BN accumulator columns (double-buffered).
+  static constexpr bool kCat = TS ? (BN == 64) : (BN <= 128);
+  static constexpr int kChains = kCat ? 2 : 1;    // accumulator column sets summed by the epilogue
+  static constexpr int kAccCols = kChains * BN;   // columns of one accumulator set
+  static constexpr int kATmem = 2 * kAccCols;     // TS: first TMEM column of the A stages (64 columns each: hi | lo)
+  static constexpr int kTmemNeed = TS ? (2 * kAccCols + kStages * 64) : 2 * kAccCols;
+  static constexpr int kTmemCols = (kTmemNeed <= 32) ? 32 : (kTmemNeed <= 64) ? 64 : (kTmemNeed <= 128) ? 128 : (kTmemNeed <= 256) ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
 
-template <int BN>
+template <int BN, bool TS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, TS>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -94,7 +114,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);    // one elected arrive per split warp
+      mbar_init(&split_bar[s], kSplitWarps);    // one elected arrive per split warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -142,8 +162,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* st = smem + stage * S::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           tma_load_4d(&tmA, &full_bar[stage], st, kc, w_in0 + tw, h_in0 + th, f0);
-          tma_load_2d(&tmBhi, &full_bar[stage], st + 2 * S::kABytes, wt * p.Kc + kc, n0);
-          tma_load_2d(&tmBlo, &full_bar[stage], st + 2 * S::kABytes + S::kBBytes, wt * p.Kc + kc, n0);
+          tma_load_2d(&tmBhi, &full_bar[stage], st + S::kBOff, wt * p.Kc + kc, n0);
+          tma_load_2d(&tmBlo, &full_bar[stage], st + S::kBOff + S::kBBytes, wt * p.Kc + kc, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -158,24 +178,48 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * S::kAccCols);
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);    // B tiles (and raw A) landed
         mbar_wait(&split_bar[stage], phase);   // a_hi / a_lo written
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
-          const uint64_t a_hi = umma_desc_sw128(st);
-          const uint64_t a_lo = umma_desc_sw128(st + S::kABytes);
-          const uint64_t b_hi = umma_desc_sw128(st + 2 * S::kABytes);
-          const uint64_t b_lo = umma_desc_sw128(st + 2 * S::kABytes + S::kBBytes);
+          const uint64_t b_hi = umma_desc_sw128(st + S::kBOff);
+          const uint64_t b_lo = umma_desc_sw128(st + S::kBOff + S::kBBytes);
+          constexpr uint32_t idesc_cat = umma_idesc_tf32(kBM, S::kCat ? 2 * BN : BN);   // B = [b_hi ; b_lo], N = 2*BN
+          if constexpr (TS) {
+            const uint32_t a_hi = tmem_base + (uint32_t)(S::kATmem + stage * 64);   // lane 0; 32 K columns
+            const uint32_t a_lo = a_hi + 32u;
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);   // 8 tf32 = 32 B = 2 x 16 B inside the swizzle atom row
-            // small terms first, the dominant hi*hi product last
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              const uint32_t ka = (uint32_t)(k * 8);   // 8 tf32 of A = 8 TMEM columns
+              if constexpr (S::kCat) {
+                umma_tf32_ts(d_tmem, a_hi + ka, b_hi + adv, idesc_cat, (it | k) != 0);
+                umma_tf32_ts(d_tmem, a_lo + ka, b_hi + adv, idesc, 1);
+              } else {
+                umma_tf32_ts(d_tmem, a_lo + ka, b_hi + adv, idesc, (it | k) != 0);
+                umma_tf32_ts(d_tmem, a_hi + ka, b_lo + adv, idesc, 1);
+                umma_tf32_ts(d_tmem, a_hi + ka, b_hi + adv, idesc, 1);
+              }
+            }
+          } else {
+            const uint64_t a_hi = umma_desc_sw128(st);
+            const uint64_t a_lo = umma_desc_sw128(st + S::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);   // 8 tf32 = 32 B = 2 x 16 B inside the swizzle atom row
+              if constexpr (S::kCat) {
+                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_cat, (it | k) != 0);
+                umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+              } else {
+                // small terms first, the dominant hi*hi product last
+                umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+                umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+              }
+            }
           }
           umma_commit(&empty_bar[stage]);                       // smem stage reusable once these MMAs retire
           if (it == k_iters - 1) umma_commit(&acc_full[acc]);   // accumulator complete
@@ -186,29 +230,64 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < kEpiWarp0) {
-    // ===================== operand split: raw A -> a_hi (in place) + a_lo =====================
-    const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127
+    // ===================== operand split: raw A -> a_hi + a_lo =====================
+    const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..255
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        float4* a = reinterpret_cast<float4*>(smem + stage * S::kStageBytes);
-        float4* lo = reinterpret_cast<float4*>(smem + stage * S::kStageBytes + S::kABytes);
+    if constexpr (TS) {
+      // thread = A row = TMEM lane (a warp may touch lanes 32*(warp%4) .. +31 only).  The row's eight 16-byte chunks
+      // sit at chunk ^ (row % 8) inside its 128-byte line (TMA SWIZZLE_128B; stage bases are 1024-aligned).
+      const int row = (warp & 3) * 32 + lane;
+      const int half = (warp - kSplitWarp0) >> 2;   // two warps per lane quadrant: K columns [0,16) and [16,32)
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(S::kATmem + half * 16);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t* arow = smem + stage * S::kStageBytes + row * 128;
+          float4 v[4];
 #pragma unroll
-        for (int j = 0; j < (kBM * kBK / 4) / 128; ++j) {
-          const int i = j * 128 + t;
-          const float4 v = a[i];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          a[i] = h;
-          lo[i] = l;
+          for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(arow + (((half * 4 + j) ^ (row & 7)) << 4));
+          tc_fence_after();   // the MMAs that read this TMEM stage last retired before full_bar could complete
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 x = v[u];
+            const float hx = tf32_rna_fast(x.x), hy = tf32_rna_fast(x.y), hz = tf32_rna_fast(x.z), hw = tf32_rna_fast(x.w);
+            hi[u * 4] = __float_as_uint(hx); hi[u * 4 + 1] = __float_as_uint(hy);
+            hi[u * 4 + 2] = __float_as_uint(hz); hi[u * 4 + 3] = __float_as_uint(hw);
+            lo[u * 4] = __float_as_uint(x.x - hx); lo[u * 4 + 1] = __float_as_uint(x.y - hy);
+            lo[u * 4 + 2] = __float_as_uint(x.z - hz); lo[u * 4 + 3] = __float_as_uint(x.w - hw);
+          }
+          tmem_st16(t_lane + (uint32_t)(stage * 64), hi);
+          tmem_st16(t_lane + (uint32_t)(stage * 64 + 32), lo);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          float4* a = reinterpret_cast<float4*>(smem + stage * S::kStageBytes);
+          float4* lo = reinterpret_cast<float4*>(smem + stage * S::kStageBytes + S::kABytes);
+#pragma unroll
+          for (int j = 0; j < (kBM * kBK / 4) / (kSplitWarps * 32); ++j) {
+            const int i = j * (kSplitWarps * 32) + t;
+            const float4 v = a[i];
+            float4 h, l;
+            h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            a[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -243,12 +322,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S::kAccCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
+#pragma unroll
+        for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
+          uint32_t r2[32];
+          tmem_ld32(t_addr + (uint32_t)(ch * BN + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         if (row_ok) {
           const int nbase = n0 + c0;
           if (nbase + 32 <= p.N && p.vec_ok == 2) {
@@ -414,13 +501,13 @@ int cached_sm_count() {
   return g_sms > 0 ? g_sms : 148;
 }
 
-template <int BN>
+template <int BN, bool TS>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, GemmParams p,
                        cudaStream_t st) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -434,7 +521,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
     return VITTA_E_BADARG;
   }
   const int grid = (int)(tiles < cached_sm_count() ? tiles : cached_sm_count());
-  gemm_tf32x3_kernel<BN><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
+  gemm_tf32x3_kernel<BN, TS><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm_tf32x3 launch: %s", cudaGetErrorString(e));
@@ -443,7 +530,12 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
   return 0;
 }
 
+// force_bn: 0 = automatic, 64 / 128 / 256 = that N tile; | kForceSS / kForceTS = shared-memory / tensor-memory A operands
+// (both forms stay selectable so that they are tested and timed against each other)
+constexpr int kForceSS = 0x1000, kForceTS = 0x2000;
+
 static int pick_bn(int N, int forced, int64_t tiles_m = 0) {
+  forced &= ~(kForceSS | kForceTS);
   if (forced == 64 || forced == 128 || forced == 256) return forced;
   if (N <= 64) return 64;
   if (N <= 128 || N % 256 != 0) return 128;
@@ -460,11 +552,17 @@ static int pick_bn(int N, int forced, int64_t tiles_m = 0) {
   return 256;
 }
 
+int g_gemm_operand_form = 0;   // vitta_gemm_set_operand_form: 0 automatic, 1 shared-memory A, 2 tensor-memory A
+
+// form: bits of force_bn (kForceSS / kForceTS), else the process-wide setting, else automatic
 static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, const GemmParams& p, int bn,
-                    cudaStream_t st) {
-  if (bn == 64) return launch_gemm<64>(a, bh, bl, p, st);
-  if (bn == 128) return launch_gemm<128>(a, bh, bl, p, st);
-  return launch_gemm<256>(a, bh, bl, p, st);
+                    cudaStream_t st, int force = 0) {
+  int form = (force & kForceSS) ? 1 : (force & kForceTS) ? 2 : g_gemm_operand_form;
+  if (form == 0) form = (bn == 64) ? 2 : 1;   // measured per tile width: profiles/r01_conv_shapes.md
+  const bool ss = form == 1;
+  if (bn == 64) return ss ? launch_gemm<64, false>(a, bh, bl, p, st) : launch_gemm<64, true>(a, bh, bl, p, st);
+  if (bn == 128) return ss ? launch_gemm<128, false>(a, bh, bl, p, st) : launch_gemm<128, true>(a, bh, bl, p, st);
+  return launch_gemm<256, false>(a, bh, bl, p, st);
 }
 
 static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const float* Bhi, const float* Blo, int64_t ldb, int N,
@@ -506,6 +604,13 @@ static void pick_boxes(int Wo, int Ho, int F, int* pBW, int* pBH, int* pBF) {
 using namespace vitta;
 
 extern "C" {
+
+int vitta_gemm_set_operand_form(int form) {
+  VITTA_CHECK_ARG(form >= 0 && form <= 2, VITTA_E_BADARG,
+                  "gemm_set_operand_form: 0 (automatic), 1 (shared-memory A) or 2 (tensor-memory A)");
+  g_gemm_operand_form = form;
+  return 0;
+}
 
 int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int Cc, int mode, void* stream) {
   VITTA_CHECK_ARG(src && hi && lo && R > 0 && T > 0 && Cc > 0 && (mode == 0 || mode == 1), VITTA_E_BADARG,
@@ -564,7 +669,7 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
   if (p.vec_ok && aligned32(C) && (ldc % 8 == 0) && (!residual || (aligned32(residual) && ldr % 8 == 0)) &&
       (!aux_out || aligned32(aux_out)))
     p.vec_ok = 2;
-  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
+  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream, force_bn);
 }
 
 int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
@@ -580,6 +685,13 @@ int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const f
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_tf32x3: bad filter");
   VITTA_CHECK_ARG(Cin % 4 == 0 && aligned16(X) && aligned16(Whi) && aligned16(Wlo), VITTA_E_ALIGN,
                   "conv2d_tf32x3: Cin must be a multiple of 4 and tensors 16-byte aligned");
+  if (KH == 1 && KW == 1 && stride == 1 && pad == 0 && (int64_t)F * H * W < (1ll << 31)) {
+    // pointwise convolution: the pixels form one dense row range, so M tiles need not respect the image geometry
+    // (a 14x14 or 7x7 map only fills 98 of the 128 rows of a {W, H, F} box)
+    W = F * H * W;
+    H = 1;
+    F = 1;
+  }
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   VITTA_CHECK_ARG(Ho > 0 && Wo > 0, VITTA_E_BADARG, "conv2d_tf32x3: empty output");
   int BW, BH, BF;
@@ -610,7 +722,7 @@ int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const f
   p.act = 0;
   p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias)) && (!residual || aligned16(residual));
   if (p.vec_ok && aligned32(Y) && (Cout % 8 == 0) && (!residual || aligned32(residual))) p.vec_ok = 2;
-  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream);
+  return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream, force_bn);
 }
 
 int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
@@ -685,7 +797,7 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
       p.out_sy = stride; p.out_sx = stride; p.out_oy = a; p.out_ox = b; p.out_H = H; p.out_W = W;
       p.vec_ok = aligned16(dX) && (Cin % 4 == 0);
       if (p.vec_ok && aligned32(dX) && (Cin % 8 == 0)) p.vec_ok = 2;
-      rc = dispatch(ta, tbh, tbl, p, bn, st);
+      rc = dispatch(ta, tbh, tbl, p, bn, st, 0);
       if (rc) return rc;
     }
   }

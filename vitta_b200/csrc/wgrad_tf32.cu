@@ -26,23 +26,37 @@ struct WgradParams {
   int boxes_w, boxes_h, boxes_f;
   int m_tiles, n_ctiles;   // Cout tiles, Cin tiles (per tap)
   int splits;
+  int box_base, box_rem;   // total_boxes = splits * box_base + box_rem: split sp covers box_base (+1 if sp < box_rem) boxes
 };
 
-template <int BN>
+// TS = true: the dY tile (A operand, M = output channel) is transposed into TENSOR MEMORY by four of the split warps
+// (thread = channel = TMEM lane, one conflict-free LDS.32 per pixel, hi | lo stored with tcgen05.st) and the MMAs read
+// it from there; shared memory keeps the raw dY landing zone and the X tile (hi in place + lo).  This takes the
+// 12 A-operand reads and the A hi/lo write-back per stage off the shared-memory port, which is what bounds the SS form
+// (224 KB of smem traffic per 768 MMA cycles at BN = 128), and the freed space buys a fourth stage.
+template <int BN, bool TS>
 struct WgSmem {
-  static constexpr int kStages = 3;
-  static constexpr int kABytes = 4 * kWgBoxBytes;            // 16 KB raw/hi, + same for lo
+  static constexpr int kStages = TS ? 4 : 3;
+  static constexpr int kABytes = 4 * kWgBoxBytes;            // 16 KB raw/hi (SS: + same for lo)
   static constexpr int kBBytes = (BN / 32) * kWgBoxBytes;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBOff = TS ? kABytes : 2 * kABytes;
+  static constexpr int kStageBytes = kBOff + 2 * kBBytes;
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // kCat (see GemmSmem in gemm_tf32.cu): a_hi x [b_hi ; b_lo] as one MMA of N = 2*BN into two column sets
+  static constexpr bool kCat = TS ? (BN == 64) : true;
+  static constexpr int kChains = kCat ? 2 : 1;
+  static constexpr int kAccCols = kChains * BN;
+  static constexpr int kATmem = 2 * kAccCols;
+  static constexpr int kTmemNeed = TS ? (2 * kAccCols + kStages * 64) : 2 * kAccCols;
+  static constexpr int kTmemCols = (kTmemNeed <= 128) ? 128 : (kTmemNeed <= 256) ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
 
-template <int BN>
+template <int BN, bool TS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                     const WgradParams p) {
-  using S = WgSmem<BN>;
+  using S = WgSmem<BN, TS>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
@@ -99,8 +113,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
     mt = r / p.splits;
     tap = nt / p.n_ctiles;
     ct = nt - tap * p.n_ctiles;
-    b0 = (int)(((int64_t)total_boxes * sp) / p.splits);
-    b1 = (int)(((int64_t)total_boxes * (sp + 1)) / p.splits);
+    // 32-bit arithmetic only: a 64-bit division is a subroutine call, behind which the compiler no longer treats the
+    // loop state as warp-uniform (descriptors then travel through per-MMA R2UR moves in the issuing thread)
+    b0 = sp * p.box_base + (sp < p.box_rem ? sp : p.box_rem);
+    b1 = b0 + p.box_base + (sp < p.box_rem ? 1 : 0);
   };
 
   if (warp == 0) {
@@ -123,7 +139,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           for (int g = 0; g < 4; ++g)
             tma_load_4d(&tmDY, &full_bar[stage], st + g * kWgBoxBytes, mt * kWgBM + g * 32, wb * p.BW, hb * p.BH,
                         fb * p.BF);
-          uint8_t* sb = st + 2 * S::kABytes;
+          uint8_t* sb = st + S::kBOff;
 #pragma unroll
           for (int g = 0; g < BN / 32; ++g)
             tma_load_4d(&tmX, &full_bar[stage], sb + g * kWgBoxBytes, ct * BN + g * 32,
@@ -143,23 +159,44 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       decode(item, mt, tap, ct, sp, b0, b1);
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * S::kAccCols);
       for (int b = b0; b < b1; ++b) {
         mbar_wait(&full_bar[stage], phase);
         mbar_wait(&split_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
-          const uint64_t a_hi = umma_desc_mn_sw128(st, kWgBoxBytes);
-          const uint64_t a_lo = umma_desc_mn_sw128(st + S::kABytes, kWgBoxBytes);
-          const uint64_t b_hi = umma_desc_mn_sw128(st + 2 * S::kABytes, kWgBoxBytes);
-          const uint64_t b_lo = umma_desc_mn_sw128(st + 2 * S::kABytes + S::kBBytes, kWgBoxBytes);
+          const uint64_t b_hi = umma_desc_mn_sw128(st + S::kBOff, kWgBoxBytes);
+          const uint64_t b_lo = umma_desc_mn_sw128(st + S::kBOff + S::kBBytes, kWgBoxBytes);
+          const uint32_t first = (uint32_t)(b != b0);
+          if constexpr (TS) {
+            constexpr uint32_t idesc_ts = umma_idesc_tf32(kWgBM, BN) | (1u << 16);   // A in TMEM, B MN-major
+            constexpr uint32_t idesc_ts_cat = umma_idesc_tf32(kWgBM, S::kCat ? 2 * BN : BN) | (1u << 16);
+            const uint32_t a_hi = tmem_base + (uint32_t)(S::kATmem + stage * 64);
+            const uint32_t a_lo = a_hi + 32u;
 #pragma unroll
-          for (int k = 0; k < kWgRows / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * (1024 >> 4));   // 8 pixels = 8 rows of 128 B (two 4-row swizzle atoms)
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (b != b0 || k != 0));
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            for (int k = 0; k < kWgRows / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * (1024 >> 4));
+              const uint32_t ka = (uint32_t)(k * 8);
+              if constexpr (S::kCat) {
+                umma_tf32_ts(d_tmem, a_hi + ka, b_hi + adv, idesc_ts_cat, first | (uint32_t)(k != 0));
+                umma_tf32_ts(d_tmem, a_lo + ka, b_hi + adv, idesc_ts, 1);
+              } else {
+                umma_tf32_ts(d_tmem, a_lo + ka, b_hi + adv, idesc_ts, first | (uint32_t)(k != 0));
+                umma_tf32_ts(d_tmem, a_hi + ka, b_lo + adv, idesc_ts, 1);
+                umma_tf32_ts(d_tmem, a_hi + ka, b_hi + adv, idesc_ts, 1);
+              }
+            }
+          } else {
+            constexpr uint32_t idesc_cat = umma_idesc_tf32_mn(kWgBM, 2 * BN);   // B = [x_hi ; x_lo]: N = 2*BN
+            const uint64_t a_hi = umma_desc_mn_sw128(st, kWgBoxBytes);
+            const uint64_t a_lo = umma_desc_mn_sw128(st + S::kABytes, kWgBoxBytes);
+#pragma unroll
+            for (int k = 0; k < kWgRows / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * (1024 >> 4));   // 8 pixels = 8 rows of 128 B (two 4-row swizzle atoms)
+              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_cat, first | (uint32_t)(k != 0));
+              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (b == b1 - 1) umma_commit(&acc_full[acc]);
@@ -181,32 +218,77 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       for (int b = b0; b < b1; ++b) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * S::kStageBytes;
-        {
-          float4* a = reinterpret_cast<float4*>(st);
-          float4* lo = reinterpret_cast<float4*>(st + S::kABytes);
+        if constexpr (TS) {
+          if (warp < 6) {
+            // warps 2-5: dY tile -> tensor memory, transposed.  thread = output channel m (TMEM lane): box m / 32,
+            // channel c = m % 32; pixel r of that box sits at r*128 + (((c >> 3) ^ (r & 3)) << 5) + (c & 7)*4
+            // (SWIZZLE_128B_ATOM_32B); the 32 lanes of a warp read one 128-byte line per pixel: no bank conflicts.
+            const int q = warp & 3;
+            const uint8_t* box = st + q * kWgBoxBytes + (lane & 7) * 4;
+            const int c8 = lane >> 3;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(S::kATmem + stage * 64);
+            tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < (S::kABytes / 16) / kWgSplitThreads; ++j) {
-            const int i = j * kWgSplitThreads + t;
-            const float4 v = a[i];
-            float4 h, l;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            a[i] = h;
-            lo[i] = l;
+            for (int half = 0; half < 2; ++half) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int r = half * 16 + u;
+                const float v = *reinterpret_cast<const float*>(box + r * 128 + ((c8 ^ (r & 3)) << 5));
+                const float h = tf32_rna_fast(v);
+                hi[u] = __float_as_uint(h);
+                lo[u] = __float_as_uint(v - h);
+              }
+              tmem_st16(t_lane + (uint32_t)(half * 16), hi);
+              tmem_st16(t_lane + (uint32_t)(32 + half * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            // warps 6-9: X tile, elementwise hi (in place) / lo
+            const int tb = threadIdx.x - 6 * 32;
+            float4* a = reinterpret_cast<float4*>(st + S::kBOff);
+            float4* lo = reinterpret_cast<float4*>(st + S::kBOff + S::kBBytes);
+#pragma unroll
+            for (int j = 0; j < (S::kBBytes / 16) / 128; ++j) {
+              const int i = j * 128 + tb;
+              const float4 v = a[i];
+              float4 h, l;
+              h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+              a[i] = h;
+              lo[i] = l;
+            }
           }
-        }
-        {
-          float4* a = reinterpret_cast<float4*>(st + 2 * S::kABytes);
-          float4* lo = reinterpret_cast<float4*>(st + 2 * S::kABytes + S::kBBytes);
+        } else {
+          // both tiles' loads are issued before the first use: one exposed shared-memory round trip per stage
+          constexpr int kA4 = (S::kABytes / 16) / kWgSplitThreads, kB4 = (S::kBBytes / 16) / kWgSplitThreads;
+          float4* a = reinterpret_cast<float4*>(st);
+          float4* alo = reinterpret_cast<float4*>(st + S::kABytes);
+          float4* x = reinterpret_cast<float4*>(st + S::kBOff);
+          float4* xlo = reinterpret_cast<float4*>(st + S::kBOff + S::kBBytes);
+          float4 va[kA4], vx[kB4];
 #pragma unroll
-          for (int j = 0; j < (S::kBBytes / 16) / kWgSplitThreads; ++j) {
-            const int i = j * kWgSplitThreads + t;
-            const float4 v = a[i];
+          for (int j = 0; j < kA4; ++j) va[j] = a[j * kWgSplitThreads + t];
+#pragma unroll
+          for (int j = 0; j < kB4; ++j) vx[j] = x[j * kWgSplitThreads + t];
+#pragma unroll
+          for (int j = 0; j < kA4; ++j) {
+            const float4 v = va[j];
             float4 h, l;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
             l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            a[i] = h;
-            lo[i] = l;
+            a[j * kWgSplitThreads + t] = h;
+            alo[j * kWgSplitThreads + t] = l;
+          }
+#pragma unroll
+          for (int j = 0; j < kB4; ++j) {
+            const float4 v = vx[j];
+            float4 h, l;
+            h.x = tf32_rna_fast(v.x); h.y = tf32_rna_fast(v.y); h.z = tf32_rna_fast(v.z); h.w = tf32_rna_fast(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            x[j * kWgSplitThreads + t] = h;
+            xlo[j * kWgSplitThreads + t] = l;
           }
         }
         fence_proxy_async();
@@ -234,12 +316,20 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S::kAccCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
+#pragma unroll
+        for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
+          uint32_t r2[32];
+          tmem_ld32(t_addr + (uint32_t)(ch * BN + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         if (co < p.Cout) {
           if (ct * BN + c0 + 32 <= p.Cin && (p.Cin & 3) == 0) {
 #pragma unroll
@@ -298,13 +388,27 @@ struct WgPlan {
   int bn;
 };
 
+// pointwise convolution: the pixels form one dense range, so a stage is simply 32 consecutive pixels (one 2-D TMA tile)
+// instead of a {BW, BH, BF} box that has to divide the image geometry
+static void flatten_pointwise(int& F, int& H, int& W, int KH, int KW, int stride, int pad) {
+  if (KH == 1 && KW == 1 && stride == 1 && pad == 0 && (int64_t)F * H * W < (1ll << 31)) {
+    W = F * H * W;
+    H = 1;
+    F = 1;
+  }
+}
+
 static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, WgPlan* out) {
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   if (Ho <= 0 || Wo <= 0) return VITTA_E_BADARG;
   WgradParams& p = out->p;
   p = WgradParams{};
   p.Cout = Cout; p.Cin = Cin; p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
-  wgrad_box(Wo, Ho, p.BW, p.BH, p.BF);
+  if (KH == 1 && KW == 1 && stride == 1 && pad == 0 && H == 1 && F == 1) {
+    p.BW = kWgRows; p.BH = 1; p.BF = 1;
+  } else {
+    wgrad_box(Wo, Ho, p.BW, p.BH, p.BF);
+  }
   p.boxes_w = (Wo + p.BW - 1) / p.BW; p.boxes_h = (Ho + p.BH - 1) / p.BH; p.boxes_f = (F + p.BF - 1) / p.BF;
   out->bn = (Cin <= 64) ? 64 : 128;
   p.m_tiles = (Cout + kWgBM - 1) / kWgBM;
@@ -317,15 +421,17 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
   if (splits < 1) splits = 1;
   if (splits > 1024) splits = 1024;
   p.splits = (int)splits;
+  p.box_base = (int)(boxes / splits);
+  p.box_rem = (int)(boxes % splits);
   return 0;
 }
 
-template <int BN>
+template <int BN, bool TS>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t st) {
-  using S = WgSmem<BN>;
+  using S = WgSmem<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("wgrad_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -334,7 +440,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
   }
   const int64_t items = (int64_t)p.m_tiles * p.taps_h * p.taps_w * p.n_ctiles * p.splits;
   const int grid = (int)(items < cached_sm_count() ? items : cached_sm_count());
-  wgrad_tf32x3_kernel<BN><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
+  wgrad_tf32x3_kernel<BN, TS><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("wgrad_tf32x3 launch: %s", cudaGetErrorString(e));
@@ -352,6 +458,7 @@ extern "C" {
 int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
   WgPlan pl;
   if (F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride < 1) return -1;
+  flatten_pointwise(F, H, W, KH, KW, stride, pad);
   if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl)) return -1;
   return (int64_t)pl.p.splits * Cout * KH * KW * Cin;
 }
@@ -363,6 +470,7 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_wgrad: bad filter");
   VITTA_CHECK_ARG(Cin % 4 == 0 && Cout % 4 == 0 && aligned16(X) && aligned16(dY) && aligned16(ws), VITTA_E_ALIGN,
                   "conv2d_wgrad: channel counts must be multiples of 4 and tensors 16-byte aligned");
+  flatten_pointwise(F, H, W, KH, KW, stride, pad);
   WgPlan pl;
   int rc = wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl);
   VITTA_CHECK_ARG(rc == 0, VITTA_E_BADARG, "conv2d_wgrad: empty output");
@@ -388,7 +496,10 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  rc = (pl.bn == 64) ? launch_wgrad<64>(tdy, tx, p, st) : launch_wgrad<128>(tdy, tx, p, st);
+  if (g_gemm_operand_form == 1)   // automatic = dY through tensor memory (12-15 % faster: profiles/r01_conv_shapes.md)
+    rc = (pl.bn == 64) ? launch_wgrad<64, false>(tdy, tx, p, st) : launch_wgrad<128, false>(tdy, tx, p, st);
+  else
+    rc = (pl.bn == 64) ? launch_wgrad<64, true>(tdy, tx, p, st) : launch_wgrad<128, true>(tdy, tx, p, st);
   if (rc) return rc;
   const int64_t n = (int64_t)Cout * KH * KW * Cin;
   int64_t blocks = (n + 255) / 256;

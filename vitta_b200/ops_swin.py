@@ -53,8 +53,7 @@ def linear_wgrad(x, gy):
     """dW (N, K) = gy[M, N]^T @ x[M, K] on the split-K tcgen05 weight-gradient kernel (a 1x1 'convolution' over M pixels)."""
     m, k = x.shape
     n = gy.shape[1]
-    wdt = 8 if m % 8 == 0 else 4 if m % 4 == 0 else 2 if m % 2 == 0 else 1
-    f = m // wdt
+    f, wdt = 1, m    # pointwise: the kernel walks the rows 32 at a time
     nws = _lib.load().vitta_conv2d_wgrad_ws_floats(f, 1, wdt, k, n, 1, 1, 1, 0)
     if nws <= 0:
         raise _lib.VittaError("linear_wgrad: bad geometry")
