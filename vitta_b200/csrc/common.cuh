@@ -57,14 +57,28 @@ static inline ClGeom cl_geom(int64_t frames, int64_t frame_rows, int C) {
   g.rs = kThreads / g.lpr;
   g.ctiles = (c4 + g.lpr - 1) / g.lpr;
   int64_t cap = (int64_t)g.rs * kMaxRowsPerThread;
-  g.cpf = (int)((frame_rows + cap - 1) / cap);
-  if (g.cpf < 1) g.cpf = 1;
-  g.rpt = (int)((frame_rows + (int64_t)g.cpf * g.rs - 1) / ((int64_t)g.cpf * g.rs));
-  if (g.rpt < 1) g.rpt = 1;
-  g.chunk_rows = g.rs * g.rpt;
-  // rounding rpt up can make the last chunks empty: recompute cpf for the final chunk size
-  g.cpf = (int)((frame_rows + g.chunk_rows - 1) / g.chunk_rows);
-  if (g.cpf < 1) g.cpf = 1;
+  int cpf0 = (int)((frame_rows + cap - 1) / cap);
+  if (cpf0 < 1) cpf0 = 1;
+  // A chunk is one CTA of the streaming kernels (K1 / K4 / K3), which run kClResident CTAs per SM: pick the chunks per
+  // frame (between the register-budget minimum and twice that) whose CTA count fills whole waves of the 148 SMs best --
+  // e.g. 64 channels at 56x56 x 128 frames: 7 chunks per frame = 896 CTAs = 1.51 waves, 9 chunks = 1152 = 1.95 waves.
+  constexpr int64_t kClResident = 4, kSlots = 148 * kClResident;
+  double best_eff = -1.0;
+  for (int cand = cpf0; cand <= 2 * cpf0 + 1; ++cand) {
+    int rpt = (int)((frame_rows + (int64_t)cand * g.rs - 1) / ((int64_t)cand * g.rs));
+    if (rpt < 1) rpt = 1;
+    if (cand > cpf0 && rpt < 4) break;   // keep at least 4 rows per thread: the per-CTA reduction epilogue is fixed cost
+    const int64_t chunk = (int64_t)g.rs * rpt;
+    const int64_t cpf = (frame_rows + chunk - 1) / chunk;
+    const int64_t n = frames * cpf * g.ctiles;
+    const double eff = (double)n / (double)(((n + kSlots - 1) / kSlots) * kSlots);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      g.rpt = rpt;
+      g.chunk_rows = (int)chunk;
+      g.cpf = (int)cpf;   // rounding rpt up can leave trailing chunks empty: cpf is recomputed from the chunk size
+    }
+  }
   g.frames = frames;
   g.frame_rows = frame_rows;
   return g;

@@ -43,7 +43,21 @@ __global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restri
   }
 }
 
-constexpr int kTamChunkRows = 64;
+constexpr int kTamChunkRows = 64;   // upper bound of the rows (pixels) one CTA of the backward walks
+
+// Rows per backward CTA: at most kTamChunkRows, fewer on the small late-stage maps so that a sample still yields ~74 CTAs
+// (592 = 148 SMs x 4 at the usual 8 samples) -- with 64-row chunks the 14x14 / 7x7 TAMs launched 32-64 CTAs in total.
+static inline int tam_chunk_rows(int64_t HW, int C) {
+  const int c4 = C / 4;
+  int lpr = 1;
+  while (lpr * 2 <= (c4 < 32 ? c4 : 32)) lpr *= 2;
+  const int ctiles = (c4 + lpr - 1) / lpr;
+  int64_t want = (74 + ctiles - 1) / ctiles;             // chunks per sample aimed at
+  int64_t rows = (HW + want - 1) / want;
+  if (rows < 4) rows = 4;                                // keep the per-CTA partial (3 x T x C floats) worth its rows
+  if (rows > kTamChunkRows) rows = kTamChunkRows;
+  return (int)rows;
+}
 
 // CTA = (n, row chunk, channel tile).  Thread = (float4 of channels, frame slot): owns frames t = slot, slot+rs, ...
 //   gx[t]    = act[t] * (k0*g[t+1] + k1*g[t] + k2*g[t-1])
@@ -51,7 +65,7 @@ constexpr int kTamChunkRows = 64;
 __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                                                           const float* __restrict__ kern, const float* __restrict__ act,
                                                           float* __restrict__ gx, float* __restrict__ dpart, int N, int T,
-                                                          int64_t HW, int C, int lpr, int rs, int nchunks) {
+                                                          int64_t HW, int C, int lpr, int rs, int nchunks, int chunk_rows) {
   const int tid = threadIdx.x;
   const int lane = tid % lpr;
   const int slot = tid / lpr;
@@ -60,9 +74,9 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
   const int c = col4 * 4;
   const int n = blockIdx.x / nchunks;
   const int ch = blockIdx.x % nchunks;
-  const int64_t p0 = (int64_t)ch * kTamChunkRows;
+  const int64_t p0 = (int64_t)ch * chunk_rows;
   const int64_t left = HW - p0;
-  const int np = (int)(left < kTamChunkRows ? left : kTamChunkRows);
+  const int np = (int)(left < chunk_rows ? left : chunk_rows);
   const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c);
   const float4 k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c);
   const float4 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
@@ -116,8 +130,9 @@ int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* ou
 }
 
 int vitta_tam_num_chunks(int64_t HW, int C) {
-  (void)C;
-  return (int)((HW + kTamChunkRows - 1) / kTamChunkRows);
+  if (HW <= 0 || C < 4) return 0;
+  const int rows = tam_chunk_rows(HW, C);
+  return (int)((HW + rows - 1) / rows);
 }
 
 int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
@@ -131,7 +146,7 @@ int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const fl
   const int nchunks = vitta_tam_num_chunks(HW, C);
   dim3 grid((unsigned)(N * nchunks), (unsigned)g.ctiles);
   tam_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(gout, x, kern, act, gx, dpart, N, T, HW, C, g.lpr, g.rs,
-                                                             nchunks);
+                                                             nchunks, tam_chunk_rows(HW, C));
   VITTA_CHECK_LAUNCH();
   return 0;
 }
