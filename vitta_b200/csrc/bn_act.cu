@@ -83,9 +83,12 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
   const int tid = threadIdx.x;
   const int lane = tid % lpr;
   const int slot = tid / lpr;
-  const int col4 = blockIdx.y * lpr + lane;
+  // 1-D grid, channel tile fastest: the CTAs that together cover the full rows of a chunk are scheduled side by side, so
+  // a DRAM page (a row is up to 8 KB) is swept once instead of once per channel tile
+  const int ctiles = (C / 4 + lpr - 1) / lpr;
+  const int col4 = (int)(blockIdx.x % ctiles) * lpr + lane;
   const bool active = col4 * 4 < C;
-  const int64_t e = blockIdx.x;
+  const int64_t e = blockIdx.x / ctiles;
   const int64_t frame = e / cpf;
   const int j = (int)(e % cpf);
   const int64_t row0 = frame * frame_rows + (int64_t)j * chunk_rows;
@@ -162,7 +165,7 @@ struct BwdArgs {
   float *gx, *gres, *gw, *gb, *gw2, *gb2;
   float* ws;
   int relu, C, lpr, rs, chunk_rows, cpf;
-  int64_t frame_rows, n_chunks;
+  int64_t frame_rows, n_chunks, ticket_off;   // tickets live at ws + ticket_off (fixed per shape, not per grid)
   float inv_frame_rows;
 };
 
@@ -179,8 +182,10 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
   const int tid = threadIdx.x;
   const int lane = tid % p.lpr;
   const int slot = tid / p.lpr;
-  const int col4 = blockIdx.y * p.lpr + lane;
   const int C = p.C;
+  const int ctiles = (C / 4 + p.lpr - 1) / p.lpr;   // 1-D grid, channel tile fastest (see the forward kernel)
+  const int by = (int)(blockIdx.x % ctiles), bx = (int)(blockIdx.x / ctiles), gdx = (int)(gridDim.x / ctiles);
+  const int col4 = by * p.lpr + lane;
   const bool active = col4 * 4 < C;
   const int c = col4 * 4;
   float4 agw = f4zero(), agb = f4zero(), agw2 = f4zero(), agb2 = f4zero();
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
       ca2 = ldg4(p.ca2 + c); cb2 = ldg4(p.cb2 + c); cm2 = ldg4(p.cm2 + c);
       ca2.x *= g; ca2.y *= g; ca2.z *= g; ca2.w *= g; cb2.x *= g; cb2.y *= g; cb2.z *= g; cb2.w *= g;
     }
-    for (int64_t e = blockIdx.x; e < p.n_chunks; e += gridDim.x) {
+    for (int64_t e = bx; e < p.n_chunks; e += gdx) {
       const int64_t frame = e / p.cpf;
       const int j = (int)(e % p.cpf);
       const int64_t row0 = frame * p.frame_rows + (int64_t)j * p.chunk_rows;
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
       }
     }
   }
-  // per-CTA partial parameter gradients -> ws[blockIdx.x][k][C], k in {gw, gb, gw2, gb2}
+  // per-CTA partial parameter gradients -> ws[bx][k][C], k in {gw, gb, gw2, gb2}
   const int nk = (RES == 2) ? 4 : 2;
   float4 red[4];
   red[0] = slot_reduce(agw, sm, tid, p.lpr, p.rs);
@@ -256,14 +261,14 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
     red[2] = slot_reduce(agw2, sm, tid, p.lpr, p.rs);
     red[3] = slot_reduce(agb2, sm, tid, p.lpr, p.rs);
   }
-  float* wsb = p.ws + (int64_t)blockIdx.x * 4 * C;
+  float* wsb = p.ws + (int64_t)bx * 4 * C;
   if (slot == 0 && active) {
     for (int k = 0; k < nk; ++k) st4(wsb + (int64_t)k * C + c, red[k]);
   }
   __threadfence();
   __syncthreads();
-  int* tickets = reinterpret_cast<int*>(p.ws + (int64_t)gridDim.x * 4 * C);
-  if (tid == 0) s_last = (atomicAdd(tickets + blockIdx.y, 1) == (int)gridDim.x - 1);
+  int* tickets = reinterpret_cast<int*>(p.ws + p.ticket_off);
+  if (tid == 0) s_last = (atomicAdd(tickets + by, 1) == gdx - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -271,21 +276,39 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
   const int nch = p.lpr * 4;
   for (int i = tid; i < nch * nk; i += kThreads) {
     const int k = i / nch;
-    const int cc = blockIdx.y * nch + (i % nch);
+    const int cc = by * nch + (i % nch);
     if (cc >= C) continue;
     float s = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(p.ws + ((int64_t)b * 4 + k) * C + cc);
+    for (int b = 0; b < gdx; ++b) s += __ldcg(p.ws + ((int64_t)b * 4 + k) * C + cc);
     float* dst = (k == 0) ? p.gw : (k == 1) ? p.gb : (k == 2) ? p.gw2 : p.gb2;
     if (dst) dst[cc] += s;
   }
-  if (tid == 0) tickets[blockIdx.y] = 0;
+  if (tid == 0) tickets[by] = 0;
 }
 
+// upper bound of the backward grid (per channel tile): sizes the workspace, fixed per shape
 static inline int bwd_grid_x(const ClGeom& g) {
   int64_t cap = (148 * 4 + g.ctiles - 1) / g.ctiles;
   if (cap < 1) cap = 1;
   int64_t n = g.n_chunks();
   return (int)(n < cap ? n : cap);
+}
+
+// The backward is a grid-stride (persistent) kernel: launch exactly one wave of what actually fits per SM for the
+// variant at hand (80 / 94 / 127 registers -> 3 / 2 / 2 CTAs), otherwise the surplus CTAs form a second, mostly empty wave.
+template <int RES>
+static int bwd_resident_ctas() {
+  static int cached = 0;
+  if (cached == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act_bwd_kernel<RES>, kThreads, 0) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 2;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = per_sm * (sms > 0 ? sms : 148);
+  }
+  return cached;
 }
 
 }  // namespace vitta
@@ -307,7 +330,8 @@ int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN
   VITTA_CHECK_ARG(!(res_bn && !res), VITTA_E_BADARG, "bn_act_fwd: res_bn without res");
   VITTA_CHECK_ARG((pool_part == nullptr) == (pool_out == nullptr), VITTA_E_BADARG, "bn_act_fwd: pool buffers");
   ClGeom g = cl_geom(frames, frame_rows, C);
-  dim3 grid((unsigned)g.n_chunks(), (unsigned)g.ctiles);
+  VITTA_CHECK_ARG(g.n_chunks() * g.ctiles < (1ll << 31), VITTA_E_UNSUPPORTED, "bn_act_fwd: grid too large");
+  dim3 grid((unsigned)(g.n_chunks() * g.ctiles));
   cudaStream_t st = (cudaStream_t)stream;
   BNDev b1 = to_dev(bn), b2 = res_bn ? to_dev(*res_bn) : b1;
   if (!res)
@@ -361,7 +385,12 @@ int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, Vitt
   p.gx = gx; p.gres = gres; p.gw = gw; p.gb = gb; p.gw2 = gw2; p.gb2 = gb2; p.ws = ws;
   p.relu = relu; p.C = C; p.lpr = g.lpr; p.rs = g.rs; p.chunk_rows = g.chunk_rows; p.cpf = g.cpf;
   p.frame_rows = g.frame_rows; p.n_chunks = g.n_chunks(); p.inv_frame_rows = 1.f / (float)frame_rows;
-  dim3 grid((unsigned)bwd_grid_x(g), (unsigned)g.ctiles);
+  p.ticket_off = (int64_t)bwd_grid_x(g) * 4 * C;
+  const int resident = !res ? bwd_resident_ctas<0>() : !res_bn ? bwd_resident_ctas<1>() : bwd_resident_ctas<2>();
+  int gx_ = resident / g.ctiles;
+  if (gx_ < 1) gx_ = 1;
+  if (gx_ > bwd_grid_x(g)) gx_ = bwd_grid_x(g);
+  dim3 grid((unsigned)(gx_ * g.ctiles));
   cudaStream_t st = (cudaStream_t)stream;
   if (!res)
     bn_act_bwd_kernel<0><<<grid, kThreads, 0, st>>>(p);

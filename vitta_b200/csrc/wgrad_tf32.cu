@@ -26,6 +26,7 @@ struct WgradParams {
   int boxes_w, boxes_h, boxes_f;
   int m_tiles, n_ctiles;   // Cout tiles, Cin tiles (per tap)
   int splits;
+  int tap_group;           // filter taps covered by one item (1, or 3 in the BN = 192 mode)
   int box_base, box_rem;   // total_boxes = splits * box_base + box_rem: split sp covers box_base (+1 if sp < box_rem) boxes
 };
 
@@ -34,20 +35,27 @@ struct WgradParams {
 // it from there; shared memory keeps the raw dY landing zone and the X tile (hi in place + lo).  This takes the
 // 12 A-operand reads and the A hi/lo write-back per stage off the shared-memory port, which is what bounds the SS form
 // (224 KB of smem traffic per 768 MMA cycles at BN = 128), and the freed space buys a fourth stage.
+// BN = 192 ("tap group" mode, TS only, Cin = 64): the B tile is the X boxes of THREE filter taps side by side
+// (3 x 64 channels), so one dY tile -- loaded, transposed and split once -- feeds three taps, and the 24 narrow MMAs per
+// pixel stage of three separate items become 12 MMAs of N = 192.  The accumulator is single-buffered there (192 columns +
+// 3 x 64 columns of A stages); an item runs for ~100 stages, so the unoverlapped epilogue is noise.
 template <int BN, bool TS>
 struct WgSmem {
-  static constexpr int kStages = TS ? 4 : 3;
+  static_assert(BN != 192 || TS, "the tap-group mode exists for the tensor-memory form only");
+  static constexpr int kGroup = (BN == 192) ? 3 : 1;
+  static constexpr int kStages = TS ? (BN == 192 ? 3 : 4) : 3;
   static constexpr int kABytes = 4 * kWgBoxBytes;            // 16 KB raw/hi (SS: + same for lo)
   static constexpr int kBBytes = (BN / 32) * kWgBoxBytes;
   static constexpr int kBOff = TS ? kABytes : 2 * kABytes;
   static constexpr int kStageBytes = kBOff + 2 * kBBytes;
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
   // kCat (see GemmSmem in gemm_tf32.cu): a_hi x [b_hi ; b_lo] as one MMA of N = 2*BN into two column sets
-  static constexpr bool kCat = TS ? (BN == 64) : true;
+  static constexpr bool kCat = (BN == 192) ? false : (TS ? (BN == 64) : true);
   static constexpr int kChains = kCat ? 2 : 1;
   static constexpr int kAccCols = kChains * BN;
-  static constexpr int kATmem = 2 * kAccCols;
-  static constexpr int kTmemNeed = TS ? (2 * kAccCols + kStages * 64) : 2 * kAccCols;
+  static constexpr int kAccBufs = (BN == 192) ? 1 : 2;
+  static constexpr int kATmem = kAccBufs * kAccCols;
+  static constexpr int kTmemNeed = TS ? (kAccBufs * kAccCols + kStages * 64) : kAccBufs * kAccCols;
   static constexpr int kTmemCols = (kTmemNeed <= 128) ? 128 : (kTmemNeed <= 256) ? 256 : 512;
   static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
@@ -72,9 +80,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int taps = p.taps_h * p.taps_w;
-  const int n_tiles = taps * p.n_ctiles;
+  const int n_tiles = (taps / p.tap_group) * p.n_ctiles;
   const int total_items = p.m_tiles * n_tiles * p.splits;
-  const int total_boxes = p.boxes_w * p.boxes_h * p.boxes_f;
   constexpr uint32_t stage_tx = (uint32_t)(S::kABytes + S::kBBytes);
 
   if (threadIdx.x == 0) {
@@ -113,6 +120,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
     mt = r / p.splits;
     tap = nt / p.n_ctiles;
     ct = nt - tap * p.n_ctiles;
+    tap *= p.tap_group;   // first tap of the item
     // 32-bit arithmetic only: a 64-bit division is a subroutine call, behind which the compiler no longer treats the
     // loop state as warp-uniform (descriptors then travel through per-MMA R2UR moves in the issuing thread)
     b0 = sp * p.box_base + (sp < p.box_rem ? sp : p.box_rem);
@@ -126,7 +134,6 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int mt, tap, ct, sp, b0, b1;
         decode(item, mt, tap, ct, sp, b0, b1);
-        const int th = tap / p.taps_w, tw = tap - th * p.taps_w;
         for (int b = b0; b < b1; ++b) {
           const int wb = b % p.boxes_w;
           const int r = b / p.boxes_w;
@@ -141,9 +148,13 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
                         fb * p.BF);
           uint8_t* sb = st + S::kBOff;
 #pragma unroll
-          for (int g = 0; g < BN / 32; ++g)
-            tma_load_4d(&tmX, &full_bar[stage], sb + g * kWgBoxBytes, ct * BN + g * 32,
+          for (int g = 0; g < BN / 32; ++g) {
+            constexpr int kBoxesPerTap = (BN / 32) / S::kGroup;
+            const int tapg = tap + g / kBoxesPerTap;
+            const int th = tapg / p.taps_w, tw = tapg - th * p.taps_w;
+            tma_load_4d(&tmX, &full_bar[stage], sb + g * kWgBoxBytes, ct * (BN / S::kGroup) + (g % kBoxesPerTap) * 32,
                         wb * p.BW * p.stride - p.pad + tw, hb * p.BH * p.stride - p.pad + th, fb * p.BF);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -205,7 +216,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (b1 > b0) {
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == S::kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 2 + kWgSplitThreads / 32) {
@@ -307,11 +318,13 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       int mt, tap, ct, sp, b0, b1;
       decode(item, mt, tap, ct, sp, b0, b1);
       const int co = mt * kWgBM + row;
-      float* dst = p.ws + ((int64_t)sp * p.Cout + co) * ktot + (int64_t)tap * p.Cin + ct * BN;
+      float* dst = p.ws + ((int64_t)sp * p.Cout + co) * ktot + (int64_t)tap * p.Cin + ct * (BN / S::kGroup);
+      // valid columns of this item: the rest of Cin, or (tap group) Cin == BN / 3 exactly and all three taps
+      const int ncols = (S::kGroup > 1) ? BN : (p.Cin - ct * BN);
       if (b1 <= b0) {   // empty K range (more splits than boxes): the partial is zero
         if (co < p.Cout)
           for (int j = 0; j < BN; ++j)
-            if (ct * BN + j < p.Cin) dst[j] = 0.f;
+            if (j < ncols) dst[j] = 0.f;
         continue;
       }
       mbar_wait(&acc_full[acc], acc_phase);
@@ -331,7 +344,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
         if (co < p.Cout) {
-          if (ct * BN + c0 + 32 <= p.Cin && (p.Cin & 3) == 0) {
+          if (c0 + 32 <= ncols && (p.Cin & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               st4(dst + c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -339,14 +352,14 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ct * BN + c0 + j < p.Cin) dst[c0 + j] = __uint_as_float(r[j]);
+              if (c0 + j < ncols) dst[c0 + j] = __uint_as_float(r[j]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == S::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -411,9 +424,14 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
   }
   p.boxes_w = (Wo + p.BW - 1) / p.BW; p.boxes_h = (Ho + p.BH - 1) / p.BH; p.boxes_f = (F + p.BF - 1) / p.BF;
   out->bn = (Cin <= 64) ? 64 : 128;
+  p.tap_group = 1;
+  if (Cin == 64 && (KH * KW) % 3 == 0 && g_gemm_operand_form != 1) {   // three taps per item (tensor-memory form only)
+    out->bn = 192;
+    p.tap_group = 3;
+  }
   p.m_tiles = (Cout + kWgBM - 1) / kWgBM;
-  p.n_ctiles = (Cin + out->bn - 1) / out->bn;
-  const int64_t base_items = (int64_t)p.m_tiles * KH * KW * p.n_ctiles;
+  p.n_ctiles = (p.tap_group > 1) ? 1 : (Cin + out->bn - 1) / out->bn;
+  const int64_t base_items = (int64_t)p.m_tiles * (KH * KW / p.tap_group) * p.n_ctiles;
   const int64_t boxes = (int64_t)p.boxes_w * p.boxes_h * p.boxes_f;
   int64_t splits = (2 * (int64_t)cached_sm_count() + base_items - 1) / base_items;
   const int64_t max_by_k = boxes / 8 > 0 ? boxes / 8 : 1;   // at least 8 stages of work per item
@@ -438,7 +456,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
     }
     attr_done = true;
   }
-  const int64_t items = (int64_t)p.m_tiles * p.taps_h * p.taps_w * p.n_ctiles * p.splits;
+  const int64_t items = (int64_t)p.m_tiles * (p.taps_h * p.taps_w / p.tap_group) * p.n_ctiles * p.splits;
   const int grid = (int)(items < cached_sm_count() ? items : cached_sm_count());
   wgrad_tf32x3_kernel<BN, TS><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
   cudaError_t e = cudaGetLastError();
@@ -499,7 +517,8 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
   if (g_gemm_operand_form == 1)   // automatic = dY through tensor memory (12-15 % faster: profiles/r01_conv_shapes.md)
     rc = (pl.bn == 64) ? launch_wgrad<64, false>(tdy, tx, p, st) : launch_wgrad<128, false>(tdy, tx, p, st);
   else
-    rc = (pl.bn == 64) ? launch_wgrad<64, true>(tdy, tx, p, st) : launch_wgrad<128, true>(tdy, tx, p, st);
+    rc = (pl.bn == 192) ? launch_wgrad<192, true>(tdy, tx, p, st)
+                        : (pl.bn == 64) ? launch_wgrad<64, true>(tdy, tx, p, st) : launch_wgrad<128, true>(tdy, tx, p, st);
   if (rc) return rc;
   const int64_t n = (int64_t)Cout * KH * KW * Cin;
   int64_t blocks = (n + 255) / 256;
