@@ -60,6 +60,37 @@ def test_chunk_counts_cover_every_row(lib):
         assert total == rows, (rows, c, frames, total)
 
 
+def test_chunking_fills_whole_waves(lib):
+    """The chunk count of the streaming kernels (one chunk = one CTA = one statistics entry) is picked against whole
+    waves of 148 SMs x 4 resident CTAs: the TANet layer shapes (128 frames) must not leave a half-empty last wave."""
+    from vitta_b200 import _lib
+    slots = 148 * 4
+    for rows_per_frame, c in [(3136, 64), (3136, 256), (3136, 128), (784, 128), (784, 512), (784, 256), (49, 2048)]:
+        ch = _lib.chunking(128 * rows_per_frame, c, 1, 128)
+        lanes = min(32, 1 << ((c // 4).bit_length() - 1))
+        ctas = ch.n_entries * ((c // 4 + lanes - 1) // lanes)
+        waves = -(-ctas // slots)
+        assert ctas / (waves * slots) >= 0.93, (rows_per_frame, c, ctas)
+        assert ch.chunk_rows * ch.chunks_per_frame >= rows_per_frame > ch.chunk_rows * (ch.chunks_per_frame - 1)
+
+
+def test_host_side_planners_without_gpu(lib):
+    """Workspace / chunk planners are pure host functions: sane, positive and consistent without a device."""
+    # TAM backward: at most 64 rows per chunk, small late-stage maps still yield >= 32 chunks per sample and channel tile
+    for hw, c in [(3136, 64), (784, 128), (196, 256), (49, 512), (5, 8)]:
+        n = lib.vitta_tam_num_chunks(hw, c)
+        assert n >= 1 and -(-hw // n) <= 64
+    assert lib.vitta_tam_num_chunks(196, 256) >= 30
+    # weight-gradient workspace: splits x Cout x KH*KW x Cin floats, also in the three-taps-per-item mode (Cin = 64, 3x3)
+    for f, h, cin, cout, k, s in [(128, 56, 64, 64, 3, 1), (128, 56, 64, 256, 1, 1), (128, 14, 256, 256, 3, 1),
+                                  (128, 28, 128, 128, 3, 2), (2, 9, 8, 24, 3, 1)]:
+        n = lib.vitta_conv2d_wgrad_ws_floats(f, h, h, cin, cout, k, k, s, k // 2)
+        assert n > 0 and n % (cout * k * k * cin) == 0
+    assert lib.vitta_conv2d_wgrad_ws_floats(0, 56, 56, 64, 64, 3, 3, 1, 1) == -1
+    assert lib.vitta_bn_act_bwd_ws_floats(128, 3136, 64) > 0
+    assert lib.vitta_gemm_set_operand_form(3) == -1 and lib.vitta_gemm_set_operand_form(0) == 0
+
+
 def test_missing_library_is_loud(monkeypatch, tmp_path):
     from vitta_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

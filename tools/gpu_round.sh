@@ -12,5 +12,6 @@ if [ "$1" == "ncu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python bench.py --ncu-step > gpurun_out/ncu_step.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_swin.csv python tools/swin_step.py --model tiny --ncu-step > gpurun_out/ncu_swin_step.log 2>&1; echo "ncu swin list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gemm_tf32x3_kernel|bn_act_fwd|wgrad_tf32x3" -c 12 -o gpurun_out/prof_tanet python bench.py --ncu-step > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"bn_act_bwd|wgrad_tf32x3" --launch-skip 88 -c 12 -o gpurun_out/prof_tanet_bwd python bench.py --ncu-step > gpurun_out/ncu_full_bwd.log 2>&1; echo "ncu full bwd rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"wmsa3d|ln_fwd|ln_bwd" -c 10 -o gpurun_out/prof_swin python tools/swin_step.py --model tiny --videos 2 --ncu-step > gpurun_out/ncu_full_swin.log 2>&1; echo "ncu full swin rc=$?"
 fi
