@@ -249,6 +249,33 @@ int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const f
 int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
                               int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream);
 
+/* ---- fp16 operand split (kind::f16) -- same contractions, same ~2^-21 per-product error, half the tensor-pipe work ----
+ * x*s = hi + lo with hi = fp16(x*s), lo = fp16(x*s - hi); s = the power of two that puts `amax` just below 2^14, where
+ * `amax` is a DEVICE scalar holding any upper bound of max|x| over the tensor (exact or up to ~2^10 too large: the
+ * residual keeps full precision for elements within 2^17 of the bound).  Results are rescaled by 1/(s_a*s_b) in the
+ * epilogue (exact).  Parity budget: tools/split_numerics.py emulates the scheme through forward, data and weight
+ * gradients of the whole adaptation step on the CPU; bf16 pieces fail the 1e-4 budget, these pass
+ * with the margin of the tf32 split.
+ *   vitta_amax_f32: *amax = max(*amax, max|x|) (integer atomic on the bit pattern; zero-initialise *amax first).
+ *   vitta_split_f16: weight preparation like vitta_split_tf32 (same modes) into two fp16 arrays, scaled by *amax's s.
+ *   vitta_gemm_f16x3_ex / vitta_conv2d_f16x3_ex / vitta_conv2d_dgrad_f16x3: the tf32 entry points with fp16 weight pieces
+ *     (ldb in fp16 elements, multiple of 8) and the two amax scalars.  Shared-memory A form; a stage holds 64 K elements.
+ * Round-1 status: compiled, exported and covered by opt-in GPU tests (VITTA_TEST_F16X3=1); the adaptation step still
+ * runs the tf32 kernels until the producers emit amax. */
+int vitta_amax_f32(const float* x, int64_t n, float* amax, void* stream);
+int vitta_split_f16(const float* src, void* hi, void* lo, const float* amax, int R, int T, int Cc, int mode,
+                    void* stream);
+int vitta_gemm_f16x3_ex(const float* A, int64_t lda, const float* a_amax, const void* Bhi, const void* Blo,
+                        const float* b_amax, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
+                        const float* bias, const float* residual, int64_t ldr, int act, float* aux_out,
+                        const float* row_scale, int64_t rows_per_group, int force_bn, void* stream);
+int vitta_conv2d_f16x3_ex(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
+                          const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad, float* Y,
+                          const float* bias, const float* residual, int force_bn, void* stream);
+int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int Ho, int Wo, int Cout, const void* Wthi,
+                             const void* Wtlo, const float* w_amax, int Cin, int KH, int KW, int stride, int pad, int H,
+                             int W, float* dX, void* stream);
+
 /* Weight gradient of the same convolution: dW[Cout][Cin][KH][KW] (contiguous NCHW, the layout of nn.Conv2d.weight)
  *   (+)= sum over output pixels of dY[F,Ho,Wo,Cout] (x) X[F,H,W,Cin] shifted by the filter tap.
  * Split-K over pixel ranges on the tcgen05 tensor cores (both operands MN-major, split hi/lo in-kernel); the K splits

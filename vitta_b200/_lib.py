@@ -71,6 +71,14 @@ _SIGNATURES = {
     "vitta_conv2d_wgrad_tf32x3": (C.c_int, [_P, _P] + [C.c_int] * 9 + [_P, C.c_int, _P, _P]),
     "vitta_gemm_tf32x3_ex": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
                                        C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int, _P]),
+    "vitta_amax_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "vitta_split_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_gemm_f16x3_ex": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                      _P, _P, C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int, _P]),
+    "vitta_conv2d_f16x3_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "vitta_conv2d_dgrad_f16x3": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_ln_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(VittaChunking)]),
     "vitta_ln_fwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P]),
     "vitta_ln_bwd_ws_floats": (C.c_int64, [C.c_int64, C.c_int]),

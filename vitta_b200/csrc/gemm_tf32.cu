@@ -15,6 +15,16 @@
 // Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-9 = operand split, 10-13 = epilogue.
 // (Eight split warps: profiling showed the four-warp split ~80 % busy per stage at BN = 64 -- LDS latency under
 // tensor-core smem traffic, the rounding ALU work and the proxy fence -- i.e. it, not the tensor pipe, set the stage time.)
+//
+// F16 = true (vitta_*_f16x3 entry points, DESIGN.md section 3 "fp16 split"): the same pipeline on kind::f16.  Operands are
+// split as x*s = hi + lo with hi = fp16(x*s), lo = fp16(x*s - hi), s a per-tensor power of two putting amax just below
+// 2^14 (the caller passes a device pointer to an upper bound of max|x|); hi*hi + hi*lo + lo*hi has the same ~2^-21 error
+// as the tf32 split at twice the tensor-pipe rate and half the weight bytes.  A stage carries 64 K elements: two raw
+// fp32 A boxes (32 channels each) that the split warps convert IN PLACE into the fp16 hi tile (first box area) and lo
+// tile (second box area), both [128][64] fp16 in exactly the SWIZZLE_128B K-major layout of the tf32 tiles, so shared
+// memory plan, descriptors, k-step advance and MMA count per stage are those of the shared-memory-A tf32 form.
+#include <cuda_fp16.h>
+
 #include "tc05.cuh"
 
 namespace vitta {
@@ -49,6 +59,8 @@ struct GemmParams {
   float* aux_out;          // optional second output: the pre-activation acc + bias (same indexing as C)
   const float* row_scale;  // optional per-row-group factor (DropPath): v *= row_scale[row / rows_per_group]
   int rows_per_group;
+  const float* a_amax;     // F16 kernels: device scalars >= max|A|, >= max|B| (f16_split_scale)
+  const float* b_amax;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -83,12 +95,14 @@ struct GemmSmem {
   static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
 
-template <int BN, bool TS>
+template <int BN, bool TS, bool F16 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+  static_assert(!(TS && F16), "the fp16 split uses the shared-memory A form");
   using S = GemmSmem<BN, TS>;
   constexpr int kStages = S::kStages;
+  constexpr int kStageK = F16 ? 2 * kBK : kBK;   // K elements per stage (fp16: two raw A boxes)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
@@ -109,7 +123,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int taps = p.ntaps ? p.ntaps : p.taps_h * p.taps_w;
   const int k_iters = taps * p.k_chunks;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BF) * kBK * 4;
-  const uint32_t stage_tx = a_box_bytes + 2u * S::kBBytes;
+  const uint32_t stage_tx = (F16 ? 2u : 1u) * a_box_bytes + 2u * S::kBBytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -155,13 +169,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int n0 = nt * BN;
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_chunks;
-          const int kc = (it - tap * p.k_chunks) * kBK;
+          const int kc = (it - tap * p.k_chunks) * kStageK;
           int th = tap / p.taps_w, tw = tap - th * p.taps_w, wt = tap;
           if (p.ntaps) { th = p.tap_dh[tap]; tw = p.tap_dw[tap]; wt = p.tap_wt[tap]; }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * S::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           tma_load_4d(&tmA, &full_bar[stage], st, kc, w_in0 + tw, h_in0 + th, f0);
+          if constexpr (F16)   // channels kc+32 .. kc+63 (zero fill past Kc)
+            tma_load_4d(&tmA, &full_bar[stage], st + S::kABytes, kc + kBK, w_in0 + tw, h_in0 + th, f0);
           tma_load_2d(&tmBhi, &full_bar[stage], st + S::kBOff, wt * p.Kc + kc, n0);
           tma_load_2d(&tmBlo, &full_bar[stage], st + S::kBOff + S::kBBytes, wt * p.Kc + kc, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -170,7 +186,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(kBM, BN) : umma_idesc_tf32(kBM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -187,7 +203,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
           const uint64_t b_hi = umma_desc_sw128(st + S::kBOff);
           const uint64_t b_lo = umma_desc_sw128(st + S::kBOff + S::kBBytes);
-          constexpr uint32_t idesc_cat = umma_idesc_tf32(kBM, S::kCat ? 2 * BN : BN);   // B = [b_hi ; b_lo], N = 2*BN
+          constexpr uint32_t idesc_cat = F16 ? umma_idesc_f16(kBM, S::kCat ? 2 * BN : BN)
+                                             : umma_idesc_tf32(kBM, S::kCat ? 2 * BN : BN);   // B = [b_hi ; b_lo], N = 2*BN
           if constexpr (TS) {
             const uint32_t a_hi = tmem_base + (uint32_t)(S::kATmem + stage * 64);   // lane 0; 32 K columns
             const uint32_t a_lo = a_hi + 32u;
@@ -207,8 +224,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           } else {
             const uint64_t a_hi = umma_desc_sw128(st);
             const uint64_t a_lo = umma_desc_sw128(st + S::kABytes);
+            if constexpr (F16) {
 #pragma unroll
-            for (int k = 0; k < kBK / 8; ++k) {
+              for (int k = 0; k < kBK / 8; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);   // 16 fp16 = 32 B = 2 x 16 B inside the swizzle atom row
+                if constexpr (S::kCat) {
+                  umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc_cat, (it | k) != 0);
+                  umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+                } else {
+                  umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+                  umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                  umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < (F16 ? 0 : kBK / 8); ++k) {
               const uint64_t adv = (uint64_t)(k * 2);   // 8 tf32 = 32 B = 2 x 16 B inside the swizzle atom row
               if constexpr (S::kCat) {
                 umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_cat, (it | k) != 0);
@@ -267,6 +298,51 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+    } else if constexpr (F16) {
+      // fp16 split, in place.  Lanes l and l+16 of a warp share A row (warp-2)*16 + (l & 15): lane l owns the raw box of
+      // channels [32*(l>>4), +32).  Both read their whole 128-byte line, __syncwarp, then each writes its four 16-byte
+      // chunks (8 fp16 = K 8j..8j+7, chunk j = 4*(l>>4) + 0..3) of the hi tile (first box area) and of the lo tile (second
+      // box area), at chunk ^ (row % 8) like every SWIZZLE_128B K-major row.  A line is only overwritten by the two lanes
+      // that read it, so no block-level barrier is needed; loads and stores are bank-conflict free (8 consecutive rows per
+      // quarter warp hit 8 distinct chunk positions).
+      const int row = (warp - kSplitWarp0) * 16 + (lane & 15);
+      const int half = lane >> 4;
+      const uint32_t sw = (uint32_t)(row & 7);
+      float sa, inv_unused;
+      f16_split_scale(__ldg(p.a_amax), sa, inv_unused);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          uint8_t* st = smem + stage * S::kStageBytes;
+          const uint8_t* src = st + half * S::kABytes + row * 128;
+          float4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w,
+                                v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = x[2 * e] * sa, x1 = x[2 * e + 1] * sa;
+              const __half2 h = __floats2half2_rn(x0, x1);            // .x (low half) = lower K index
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+              lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(half * 4 + j)) ^ sw) << 4);
+            *reinterpret_cast<uint4*>(st + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(st + S::kABytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
     } else {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int it = 0; it < k_iters; ++it) {
@@ -296,6 +372,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int row = q * 32 + lane;                // accumulator row == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
+    float inv_a = 1.f, inv_b = 1.f;   // F16: 1 / s_a, 1 / s_b -- exact powers of two, applied one after the other (their
+    if constexpr (F16) {              // product alone could leave the fp32 range for tiny gradient tensors)
+      float s_unused;
+      f16_split_scale(__ldg(p.a_amax), s_unused, inv_a);
+      f16_split_scale(__ldg(p.b_amax), s_unused, inv_b);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
@@ -335,6 +417,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
+        if constexpr (F16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_a * inv_b);
         }
         if (row_ok) {
           const int nbase = n0 + c0;
@@ -456,6 +542,46 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// max|x| over a tensor, accumulated into *amax with an integer atomic (non-negative floats order like their bit patterns);
+// the caller zero-initialises *amax.  NaN / Inf inputs propagate as a huge bound (garbage in, garbage out).
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ amax) {
+  uint32_t m = 0;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (n >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = __ldg(x4 + i);
+    m = max(max(m, __float_as_uint(fabsf(v.x))), __float_as_uint(fabsf(v.y)));
+    m = max(max(m, __float_as_uint(fabsf(v.z))), __float_as_uint(fabsf(v.w)));
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    m = max(m, __float_as_uint(fabsf(__ldg(x + i))));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(amax), m);
+}
+
+// fp16 weight preparation: same index modes as split_tf32_kernel; hi = fp16(x*s), lo = fp16(x*s - hi), s from *amax
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                                       __half* __restrict__ lo, const float* __restrict__ amax, int R,
+                                                       int T, int Cc, int mode) {
+  float sc, inv_unused;
+  f16_split_scale(__ldg(amax), sc, inv_unused);
+  const int64_t n = (int64_t)R * T * Cc;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t s = i;
+    if (mode == 1) {   // i indexes dst [c][t'][r]
+      const int r = (int)(i % R);
+      const int64_t q = i / R;
+      const int tp = (int)(q % T);
+      const int c = (int)(q / T);
+      s = ((int64_t)r * T + (T - 1 - tp)) * Cc + c;
+    }
+    const float v = __ldg(src + s) * sc;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -473,14 +599,30 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_tensor_map_typed(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank,
+                                 const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                 const uint32_t* estr, bool swizzle_atom_32b);
+
 int make_tensor_map_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, const uint32_t* estr, bool swizzle_atom_32b) {
+  return make_tensor_map_typed(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, estr,
+                               swizzle_atom_32b);
+}
+
+int make_tensor_map_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, const uint32_t* estr) {
+  return make_tensor_map_typed(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, estr, false);
+}
+
+static int make_tensor_map_typed(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank,
+                                 const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                 const uint32_t* estr, bool swizzle_atom_32b) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return VITTA_E_UNSUPPORTED;
   }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                    reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -501,13 +643,14 @@ int cached_sm_count() {
   return g_sms > 0 ? g_sms : 148;
 }
 
-template <int BN, bool TS>
+template <int BN, bool TS, bool F16 = false>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, GemmParams p,
                        cudaStream_t st) {
   using S = GemmSmem<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -521,7 +664,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
     return VITTA_E_BADARG;
   }
   const int grid = (int)(tiles < cached_sm_count() ? tiles : cached_sm_count());
-  gemm_tf32x3_kernel<BN, TS><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
+  gemm_tf32x3_kernel<BN, TS, F16><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm_tf32x3 launch: %s", cudaGetErrorString(e));
@@ -557,6 +700,11 @@ int g_gemm_operand_form = 0;   // vitta_gemm_set_operand_form: 0 automatic, 1 sh
 // form: bits of force_bn (kForceSS / kForceTS), else the process-wide setting, else automatic
 static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, const GemmParams& p, int bn,
                     cudaStream_t st, int force = 0) {
+  if (p.a_amax) {   // fp16 split: shared-memory A form only
+    if (bn == 64) return launch_gemm<64, false, true>(a, bh, bl, p, st);
+    if (bn == 128) return launch_gemm<128, false, true>(a, bh, bl, p, st);
+    return launch_gemm<256, false, true>(a, bh, bl, p, st);
+  }
   int form = (force & kForceSS) ? 1 : (force & kForceTS) ? 2 : g_gemm_operand_form;
   if (form == 0) form = (bn == 64) ? 2 : 1;   // measured per tile width: profiles/r01_conv_shapes.md
   const bool ss = form == 1;
@@ -565,12 +713,19 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorM
   return launch_gemm<256, false>(a, bh, bl, p, st);
 }
 
-static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const float* Bhi, const float* Blo, int64_t ldb, int N,
-                       int Ktot, int bn) {
+static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const void* Bhi, const void* Blo, int64_t ldb, int N,
+                       int Ktot, int bn, bool f16 = false) {
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
+  const uint32_t es[2] = {1, 1};
+  if (f16) {   // [N][Ktot] fp16, 64 K elements (128 B) per stage row
+    const uint64_t str[1] = {(uint64_t)ldb * 2};
+    const uint32_t box[2] = {(uint32_t)(2 * kBK), (uint32_t)bn};
+    int rc = make_tensor_map_f16(bh, Bhi, 2, dims, str, box, es);
+    if (rc) return rc;
+    return make_tensor_map_f16(bl, Blo, 2, dims, str, box, es);
+  }
   const uint64_t str[1] = {(uint64_t)ldb * 4};
   const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
-  const uint32_t es[2] = {1, 1};
   int rc = make_tensor_map_f32(bh, Bhi, 2, dims, str, box, es);
   if (rc) return rc;
   return make_tensor_map_f32(bl, Blo, 2, dims, str, box, es);
@@ -630,11 +785,16 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
                               force_bn, stream);
 }
 
-int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
-                         int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
-                         int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
-                         void* stream) {
+// shared by the tf32 (a_amax == null, B = fp32 hi/lo) and fp16 (a_amax / b_amax given, B = fp16 hi/lo) entry points
+static int gemm_impl(const float* A, int64_t lda, const void* Bhi, const void* Blo, int64_t ldb, float* C,
+                     int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                     int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
+                     void* stream, const float* a_amax, const float* b_amax) {
+  const bool f16 = a_amax != nullptr;
+  const int stage_k = f16 ? 2 * kBK : kBK;
   VITTA_CHECK_ARG(A && Bhi && Blo && C && M > 0 && N > 0 && K > 0, VITTA_E_BADARG, "gemm_tf32x3: bad arguments");
+  VITTA_CHECK_ARG(!f16 || (b_amax && ldb % 8 == 0), VITTA_E_BADARG,
+                  "gemm_f16x3: needs both amax scalars and fp16 weight rows that are multiples of 8 elements");
   VITTA_CHECK_ARG(act >= 0 && act <= 2 && !(act == 2 && !residual), VITTA_E_BADARG,
                   "gemm_tf32x3: act must be 0/1/2 and act 2 needs the pre-activation in `residual`");
   VITTA_CHECK_ARG(!row_scale || (rows_per_group > 0 && rows_per_group < (1ll << 31)), VITTA_E_BADARG,
@@ -653,11 +813,12 @@ int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const fl
     int rc = make_tensor_map_f32(&ta, A, 4, dims, str, box, es);
     if (rc) return rc;
   }
-  int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn);
+  int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn, f16);
   if (rc) return rc;
   GemmParams p{};
+  p.a_amax = a_amax; p.b_amax = b_amax;
   p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
-  p.M_total = (int)M; p.N = N; p.Kc = K; p.k_chunks = (K + kBK - 1) / kBK;
+  p.M_total = (int)M; p.N = N; p.Kc = K; p.k_chunks = (K + stage_k - 1) / stage_k;
   p.taps_h = p.taps_w = 1; p.stride = 1; p.pad = 0;
   p.Ho = 1; p.Wo = (int)M; p.F = 1;
   p.BW = kBM; p.BH = 1; p.BF = 1;
@@ -677,11 +838,15 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
   return vitta_conv2d_tf32x3_ex(X, F, H, W, Cin, Whi, Wlo, Cout, KH, KW, stride, pad, Y, bias, nullptr, force_bn, stream);
 }
 
-int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
-                           int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
-                           int force_bn, void* stream) {
+static int conv2d_impl(const float* X, int F, int H, int W, int Cin, const void* Whi, const void* Wlo, int Cout,
+                       int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
+                       int force_bn, void* stream, const float* a_amax, const float* b_amax) {
+  const bool f16 = a_amax != nullptr;
+  const int stage_k = f16 ? 2 * kBK : kBK;
   VITTA_CHECK_ARG(X && Whi && Wlo && Y && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
                   "conv2d_tf32x3: bad arguments");
+  VITTA_CHECK_ARG(!f16 || (b_amax && (KH * KW * Cin) % 8 == 0), VITTA_E_BADARG,
+                  "conv2d_f16x3: needs both amax scalars and KH*KW*Cin a multiple of 8");
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_tf32x3: bad filter");
   VITTA_CHECK_ARG(Cin % 4 == 0 && aligned16(X) && aligned16(Whi) && aligned16(Wlo), VITTA_E_ALIGN,
                   "conv2d_tf32x3: Cin must be a multiple of 4 and tensors 16-byte aligned");
@@ -710,11 +875,12 @@ int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const f
     if (rc) return rc;
   }
   const int Ktot = KH * KW * Cin;
-  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn);
+  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn, f16);
   if (rc) return rc;
   GemmParams p{};
+  p.a_amax = a_amax; p.b_amax = b_amax;
   p.C = Y; p.bias = bias; p.residual = residual; p.ldc = Cout; p.ldr = Cout;
-  p.M_total = 0; p.N = Cout; p.Kc = Cin; p.k_chunks = (Cin + kBK - 1) / kBK;
+  p.M_total = 0; p.N = Cout; p.Kc = Cin; p.k_chunks = (Cin + stage_k - 1) / stage_k;
   p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
   p.Ho = Ho; p.Wo = Wo; p.F = F;
   p.BW = BW; p.BH = BH; p.BF = BF;
@@ -725,8 +891,13 @@ int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const f
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream, force_bn);
 }
 
-int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
-                              int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream) {
+static int dgrad_impl(const float* dY, int F, int Ho, int Wo, int Cout, const void* Wthi, const void* Wtlo,
+                      int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream,
+                      const float* a_amax, const float* b_amax) {
+  const bool f16 = a_amax != nullptr;
+  const int stage_k = f16 ? 2 * kBK : kBK;
+  VITTA_CHECK_ARG(!f16 || (b_amax && (KH * KW * Cout) % 8 == 0), VITTA_E_BADARG,
+                  "conv2d_dgrad_f16x3: needs both amax scalars and KH*KW*Cout a multiple of 8");
   VITTA_CHECK_ARG(dY && Wthi && Wtlo && dX && F > 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0,
                   VITTA_E_BADARG, "conv2d_dgrad: bad arguments");
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && KH * KW <= 9 && stride >= 1 && stride <= 4 && pad >= 0, VITTA_E_UNSUPPORTED,
@@ -739,7 +910,7 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
   const int Ktot = KH * KW * Cout;
   const int bn = pick_bn(Cin, 0);
   CUtensorMap tbh, tbl;
-  int rc = make_b_maps(&tbh, &tbl, Wthi, Wtlo, Ktot, Cin, Ktot, bn);
+  int rc = make_b_maps(&tbh, &tbl, Wthi, Wtlo, Ktot, Cin, Ktot, bn, f16);
   if (rc) return rc;
   // residue classes no filter tap reaches (e.g. 1x1 stride 2) have zero gradient: clear dX first if there are any
   bool any_empty = false;
@@ -789,7 +960,8 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
         rc = make_tensor_map_f32(&ta, dY, 4, dims, str, box, es);
         if (rc) return rc;
       }
-      p.C = dX; p.ldc = Cin; p.N = Cin; p.Kc = Cout; p.k_chunks = (Cout + kBK - 1) / kBK;
+      p.a_amax = a_amax; p.b_amax = b_amax;
+      p.C = dX; p.ldc = Cin; p.N = Cin; p.Kc = Cout; p.k_chunks = (Cout + stage_k - 1) / stage_k;
       p.taps_h = p.taps_w = 1; p.stride = 1; p.pad = 0; p.ntaps = nt;
       p.Ho = Hc; p.Wo = Wc; p.F = F;
       p.BW = BW; p.BH = BH; p.BF = BF;
@@ -802,6 +974,74 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
     }
   }
   return 0;
+}
+
+int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
+                         int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
+                         int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
+                         void* stream) {
+  return gemm_impl(A, lda, Bhi, Blo, ldb, C, ldc, M, N, K, bias, residual, ldr, act, aux_out, row_scale, rows_per_group,
+                   force_bn, stream, nullptr, nullptr);
+}
+
+int vitta_conv2d_tf32x3_ex(const float* X, int F, int H, int W, int Cin, const float* Whi, const float* Wlo, int Cout,
+                           int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
+                           int force_bn, void* stream) {
+  return conv2d_impl(X, F, H, W, Cin, Whi, Wlo, Cout, KH, KW, stride, pad, Y, bias, residual, force_bn, stream, nullptr,
+                     nullptr);
+}
+
+int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, const float* Wthi, const float* Wtlo,
+                              int Cin, int KH, int KW, int stride, int pad, int H, int W, float* dX, void* stream) {
+  return dgrad_impl(dY, F, Ho, Wo, Cout, Wthi, Wtlo, Cin, KH, KW, stride, pad, H, W, dX, stream, nullptr, nullptr);
+}
+
+// ---- fp16 split (experimental in round 1: compiled and exported, not yet used by the step) ----
+int vitta_amax_f32(const float* x, int64_t n, float* amax, void* stream) {
+  VITTA_CHECK_ARG(x && amax && n > 0, VITTA_E_BADARG, "amax_f32: bad arguments");
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  amax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, amax);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_split_f16(const float* src, void* hi, void* lo, const float* amax, int R, int T, int Cc, int mode,
+                    void* stream) {
+  VITTA_CHECK_ARG(src && hi && lo && amax && R > 0 && T > 0 && Cc > 0 && (mode == 0 || mode == 1), VITTA_E_BADARG,
+                  "split_f16: bad arguments");
+  const int64_t n = (int64_t)R * T * Cc;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, static_cast<__half*>(hi),
+                                                                       static_cast<__half*>(lo), amax, R, T, Cc, mode);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_gemm_f16x3_ex(const float* A, int64_t lda, const float* a_amax, const void* Bhi, const void* Blo,
+                        const float* b_amax, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
+                        const float* bias, const float* residual, int64_t ldr, int act, float* aux_out,
+                        const float* row_scale, int64_t rows_per_group, int force_bn, void* stream) {
+  VITTA_CHECK_ARG(a_amax && b_amax, VITTA_E_BADARG, "gemm_f16x3: amax scalars are required");
+  return gemm_impl(A, lda, Bhi, Blo, ldb, C, ldc, M, N, K, bias, residual, ldr, act, aux_out, row_scale, rows_per_group,
+                   force_bn, stream, a_amax, b_amax);
+}
+
+int vitta_conv2d_f16x3_ex(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
+                          const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad, float* Y,
+                          const float* bias, const float* residual, int force_bn, void* stream) {
+  VITTA_CHECK_ARG(x_amax && w_amax, VITTA_E_BADARG, "conv2d_f16x3: amax scalars are required");
+  return conv2d_impl(X, F, H, W, Cin, Whi, Wlo, Cout, KH, KW, stride, pad, Y, bias, residual, force_bn, stream, x_amax,
+                     w_amax);
+}
+
+int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int Ho, int Wo, int Cout, const void* Wthi,
+                             const void* Wtlo, const float* w_amax, int Cin, int KH, int KW, int stride, int pad, int H,
+                             int W, float* dX, void* stream) {
+  VITTA_CHECK_ARG(dy_amax && w_amax, VITTA_E_BADARG, "conv2d_dgrad_f16x3: amax scalars are required");
+  return dgrad_impl(dY, F, Ho, Wo, Cout, Wthi, Wtlo, Cin, KH, KW, stride, pad, H, W, dX, stream, dy_amax, w_amax);
 }
 
 }  // extern "C"

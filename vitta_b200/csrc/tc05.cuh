@@ -81,6 +81,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
       : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulation): same descriptor layout, A/B format fields 0 = F16; K = 16 per MMA
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Per-tensor power-of-two scale of the fp16 operand split: amax < 2^(eb-126) for the biased
+// exponent eb of amax, so s = 2^(140-eb) puts every |x|*s below 2^14; inv = 1/s exactly (0 when the tensor is ~0).
+__device__ __forceinline__ void f16_split_scale(float amax, float& s, float& inv) {
+  int se = 267 - (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  s = __uint_as_float((uint32_t)se << 23);
+  inv = __uint_as_float((uint32_t)(254 - se) << 23);
+}
 // Lane-predicated variants: EVERY lane of the issuing warp runs the (warp-uniform) control flow and only the instruction
 // itself is predicated on one lane, so descriptors and addresses stay in uniform registers instead of being moved
 // there per MMA (R2UR + election loop) -- the serial issue chain of the single MMA thread is what bounds small-N tiles.
@@ -201,6 +221,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n) {   // b
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int make_tensor_map_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, const uint32_t* estr, bool swizzle_atom_32b = false);
+int make_tensor_map_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, const uint32_t* estr);
 int cached_sm_count();
 extern int g_gemm_operand_form;   // see vitta_gemm_set_operand_form (0 automatic, 1 shared-memory A, 2 tensor-memory A)
 

@@ -630,6 +630,81 @@ def conv2d_tf32x3(x, w_hi, w_lo, cout, kh, kw, stride, pad, bias=None, force_bn=
     return y
 
 
+# ---- fp16 operand split (kind::f16): experimental in round 1 -- exported, opt-in tested, not yet used by the step ----
+def amax_f32(x, out=None):
+    """Device scalar max|x| (vitta_amax_f32).  ``out``: an existing scalar to accumulate into (max), else a fresh zero."""
+    _require_cuda(x, "amax_f32")
+    if not x.is_contiguous() and not x.is_contiguous(memory_format=CL):
+        raise _lib.VittaError("amax_f32: x must be dense")
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    call("vitta_amax_f32", ptr(x), x.numel(), ptr(out), stream_ptr())
+    return out
+
+
+def split_f16(w, mode=0):
+    """fp16 weight preparation (vitta_split_f16): same shapes / modes as split_tf32.  Returns (hi, lo, amax): two flat
+    fp16 tensors holding w * s and the device scalar the scale s is derived from."""
+    _require_cuda(w, "split_f16")
+    if w.dim() == 2:
+        r, t, c = w.shape[0], 1, w.shape[1]
+        src = w.contiguous()
+    else:
+        r, c, kh, kw = w.shape
+        t = kh * kw
+        src = w.contiguous(memory_format=CL) if t > 1 else w.reshape(r, c).contiguous()
+    am = amax_f32(src)
+    hi = torch.empty(r * t * c, dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    call("vitta_split_f16", ptr(src), ptr(hi), ptr(lo), ptr(am), r, t, c, int(mode), stream_ptr())
+    return hi, lo, am
+
+
+def gemm_f16x3(a, b_hi, b_lo, b_amax, n, a_amax=None, bias=None, residual=None, act=0, out=None, force_bn=0):
+    """gemm_tf32x3 on the fp16 split; ``a_amax`` defaults to a fresh vitta_amax_f32 pass over ``a``."""
+    _require_cuda(a, "gemm_f16x3")
+    if a.dim() != 2 or a.stride(1) != 1:
+        raise _lib.VittaError("gemm_f16x3: A must be (M, K) with unit inner stride")
+    m, k = a.shape
+    if a_amax is None:
+        a_amax = amax_f32(a if a.is_contiguous() else a.contiguous())
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    call("vitta_gemm_f16x3_ex", ptr(a), a.stride(0), ptr(a_amax), ptr(b_hi), ptr(b_lo), ptr(b_amax), k, ptr(out),
+         out.stride(0), m, n, k, ptr(bias), ptr(residual), ldr, int(act), None, None, 1, int(force_bn), stream_ptr())
+    return out
+
+
+def conv2d_f16x3(x, w_hi, w_lo, w_amax, cout, kh, kw, stride, pad, x_amax=None, bias=None, force_bn=0, residual=None):
+    """conv2d_tf32x3 on the fp16 split (channels_last in, channels_last out)."""
+    _require_cuda(x, "conv2d_f16x3")
+    if not x.is_contiguous(memory_format=CL):
+        raise _lib.VittaError("conv2d_f16x3: x must be channels_last contiguous")
+    f, cin, h, w = x.shape
+    if x_amax is None:
+        x_amax = amax_f32(x)
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    y = torch.empty((f, cout, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
+    call("vitta_conv2d_f16x3_ex", ptr(x), ptr(x_amax), f, h, w, cin, ptr(w_hi), ptr(w_lo), ptr(w_amax), cout, kh, kw,
+         stride, pad, ptr(y), ptr(bias), ptr(residual), int(force_bn), stream_ptr())
+    return y
+
+
+def conv2d_dgrad_f16x3(gy, wt_hi, wt_lo, w_amax, x_shape, kh, kw, stride, pad, gy_amax=None):
+    """Data gradient of a (strided) convolution on the fp16 split; wt_* from split_f16(w, mode=1)."""
+    _require_cuda(gy, "conv2d_dgrad_f16x3")
+    f, cin, h, w = x_shape
+    cout = gy.shape[1]
+    if gy_amax is None:
+        gy_amax = amax_f32(gy)
+    gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device).contiguous(memory_format=CL)
+    call("vitta_conv2d_dgrad_f16x3", ptr(gy), ptr(gy_amax), f, gy.shape[2], gy.shape[3], cout, ptr(wt_hi), ptr(wt_lo),
+         ptr(w_amax), cin, kh, kw, stride, pad, h, w, ptr(gx), stream_ptr())
+    return gx
+
+
 # weight-split cache: the hi/lo operands of a weight are rebuilt only when the weight changed.  Keyed by the
 # storage address (autograd hands backward() re-wrapped tensor objects); validated by the autograd version counter
 # and emptied by every FusedSGD step (it updates parameters through raw pointers, invisible to the version counter).
