@@ -5,6 +5,7 @@ hot-path arithmetic below runs in libvitta_b200.so.  Nothing in this file falls 
 math when the library is missing -- ``_lib.load()`` raises.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -715,6 +716,35 @@ def bump_weight_epoch():
     _split_cache.clear()
 
 
+# Operand split of the dense contractions: "tf32x3" (default, hardware-validated) or "f16x3" (opt-in until validated on
+# hardware, DESIGN.md section 9: forward and data-gradient GEMMs / convolutions on kind::f16 with per-tensor amax scaling;
+# weight gradients stay on the tf32 kernel).  Also settable with VITTA_GEMM_PRECISION.
+_gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "tf32x3")
+
+
+def set_gemm_precision(name):
+    global _gemm_precision
+    if name not in ("tf32x3", "f16x3"):
+        raise _lib.VittaError("gemm precision must be 'tf32x3' or 'f16x3', got %r" % (name,))
+    _gemm_precision = name
+    bump_weight_epoch()
+
+
+def gemm_precision():
+    return _gemm_precision
+
+
+def weight_split_f16(w, mode):
+    """Cached fp16 pieces + amax scalar of a weight (same invalidation rules as weight_split)."""
+    key = (w.data_ptr(), mode, "f16")
+    ent = _split_cache.get(key)
+    if ent is None or ent[0] != (w._version, tuple(w.shape)):
+        with torch.no_grad():
+            ent = ((w._version, tuple(w.shape)), split_f16(w.detach(), mode))
+        _split_cache[key] = ent
+    return ent[1]
+
+
 def weight_split(w, mode):
     key = (w.data_ptr(), mode)
     ent = _split_cache.get(key)
@@ -758,8 +788,12 @@ class Conv2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, pad, want_alias=False):
         cout, cin, kh, kw = w.shape
-        whi, wlo = weight_split(w, 0)
-        y = conv2d_tf32x3(x, whi, wlo, cout, kh, kw, stride, pad)
+        if _gemm_precision == "f16x3" and (cin * kh * kw) % 8 == 0:
+            whi, wlo, wam = weight_split_f16(w, 0)
+            y = conv2d_f16x3(x, whi, wlo, wam, cout, kh, kw, stride, pad)
+        else:
+            whi, wlo = weight_split(w, 0)
+            y = conv2d_tf32x3(x, whi, wlo, cout, kh, kw, stride, pad)
         ctx.save_for_backward(x, w)
         ctx.geom = (stride, pad)
         if want_alias:
@@ -778,17 +812,27 @@ class Conv2dFn(torch.autograd.Function):
         gy = gy.contiguous(memory_format=CL)
         gx = gw = None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        f16 = _gemm_precision == "f16x3" and (cout * kh * kw) % 8 == 0
         if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
-            whi, wlo = weight_split(w, 1)
-            gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
+            if f16:
+                whi, wlo, wam = weight_split_f16(w, 1)
+                gx = conv2d_f16x3(gy, whi, wlo, wam, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
+            else:
+                whi, wlo = weight_split(w, 1)
+                gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
             galias = None
             need_x = False
         elif need_x and stride > 1 and kh * kw <= 9 and cout % 4 == 0:
-            whi, wlo = weight_split(w, 1)
             f, _, h, wd = x.shape
             gx = torch.empty_like(x)             # channels_last like x
-            call("vitta_conv2d_dgrad_tf32x3", ptr(gy), f, gy.shape[2], gy.shape[3], cout, ptr(whi), ptr(wlo), cin, kh, kw,
-                 stride, pad, h, wd, ptr(gx), stream_ptr())
+            if f16:
+                whi, wlo, wam = weight_split_f16(w, 1)
+                call("vitta_conv2d_dgrad_f16x3", ptr(gy), ptr(amax_f32(gy)), f, gy.shape[2], gy.shape[3], cout, ptr(whi),
+                     ptr(wlo), ptr(wam), cin, kh, kw, stride, pad, h, wd, ptr(gx), stream_ptr())
+            else:
+                whi, wlo = weight_split(w, 1)
+                call("vitta_conv2d_dgrad_tf32x3", ptr(gy), f, gy.shape[2], gy.shape[3], cout, ptr(whi), ptr(wlo), cin, kh,
+                     kw, stride, pad, h, wd, ptr(gx), stream_ptr())
             need_x = False
         if need_w and cout % 4 == 0:
             gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)

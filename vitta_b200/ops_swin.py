@@ -40,10 +40,17 @@ def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=No
     mode 0: w is (N, K) (forward of nn.Linear);  mode 1: w is (K, N) and its transpose is used (data gradient)."""
     m, k = a.shape
     n = w.shape[0] if mode == 0 else w.shape[1]
-    hi, lo = ops.weight_split(w, mode)
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=a.device)
     ldr = residual.stride(0) if residual is not None else 0
+    if ops.gemm_precision() == "f16x3" and k % 8 == 0 and a.is_contiguous():
+        # opt-in fp16 operand split (DESIGN.md section 9); the amax of the activation operand is a separate pass for now
+        hi, lo, wam = ops.weight_split_f16(w, mode)
+        call("vitta_gemm_f16x3_ex", ptr(a), a.stride(0), ptr(ops.amax_f32(a)), ptr(hi), ptr(lo), ptr(wam), k, ptr(out),
+             out.stride(0), m, n, k, ptr(bias), ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale),
+             int(rows_per_group), 0, stream_ptr())
+        return out
+    hi, lo = ops.weight_split(w, mode)
     call("vitta_gemm_tf32x3_ex", ptr(a), a.stride(0), ptr(hi), ptr(lo), k, ptr(out), out.stride(0), m, n, k, ptr(bias),
          ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale), int(rows_per_group), 0, stream_ptr())
     return out
