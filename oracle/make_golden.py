@@ -37,6 +37,12 @@ TANET_CASES = {
                                    lr=1e-3, moving_avg=True),
     "tanet_t16_r224_stats_l1": dict(K=101, T=16, N=1, M=1, res=224, reg_type="l1_loss", consis=False, steps=1,
                                     lr=1e-3, moving_avg=True),
+    # option rows of SURVEY 8(f) rank 4 at model level: KLD against running MEANS of the statistics (moving_avg=False,
+    # AverageMeterTensor), and --update_only_bn_affine (everything frozen except norm affine parameters, Adam)
+    "tanet_t8_r64_stats_kld_avg": dict(K=101, T=8, N=2, M=1, res=64, reg_type="kld", consis=False, steps=3,
+                                       lr=1e-6, moving_avg=False),   # KLD sums over channels: large gradients
+    "tanet_t8_r64_consis_l1_bnaffine": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
+                                            lr=1e-3, moving_avg=True, bn_affine=True),
 }
 
 SWIN_CASES = {
@@ -103,6 +109,7 @@ def _base_args(ref, cfg, arch):
     args.if_sample_tta_aug_views = cfg.get("sample_views", True)
     args.n_augmented_views = cfg["M"]
     args.lr = cfg["lr"]
+    args.update_only_bn_affine = cfg.get("bn_affine", False)
     args.momentum_mvg = cfg.get("momentum_mvg", 0.1)
     args.lambda_pred_consis = cfg.get("lambda_consis", 0.1)
     args.stat_type = ["spatiotemp"]

@@ -472,19 +472,31 @@ class TTAState:
 
     def __init__(self, sd, arch, clip_len, src_means, src_vars, chosen_blocks, reg_type="l1_loss",
                  moving_avg=True, momentum_mvg=0.1, lr=5e-5, momentum=0.9, weight_decay=5e-4,
-                 swin_cfg=None, name_prefix=""):
+                 swin_cfg=None, name_prefix="", update_only_bn_affine=False):
         self.arch, self.clip_len = arch, clip_len
         self.swin_cfg = swin_cfg or {}
         self.sd = {}
+        if update_only_bn_affine:
+            # corpus/basics.py:547-557 + utils/BNS_utils.py:262-288: everything frozen except the norm layers
+            # (TANet: BatchNorm1d/2d/3d, Swin: every LayerNorm incl. patch_embed.norm); Adam over their weight / bias
+            if arch == "tanet":
+                norm_names = [n for n, _ in tanet_norm_layers()]
+            else:
+                norm_names = swin_norm_layers((self.swin_cfg or {}).get("depths", (2, 2, 18, 2)))
+            trainable = {n + leaf for n in norm_names for leaf in (".weight", ".bias")}
         params = []
         for k, v in sd.items():
             v = v.detach().clone()
             if v.is_floating_point() and not (k.endswith("running_mean") or k.endswith("running_var")):
-                v.requires_grad_(True)
-                params.append(v)
+                if not update_only_bn_affine or k in trainable:
+                    v.requires_grad_(True)
+                    params.append(v)
             self.sd[k] = v
         self.params = params
-        self.opt = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        if update_only_bn_affine:
+            self.opt = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), weight_decay=0.)
+        else:
+            self.opt = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.taps = {}
         if arch == "tanet":
             layers = tanet_norm_layers()
