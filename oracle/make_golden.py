@@ -43,6 +43,10 @@ TANET_CASES = {
                                        lr=1e-6, moving_avg=False),   # KLD sums over channels: large gradients
     "tanet_t8_r64_consis_l1_bnaffine": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                             lr=1e-3, moving_avg=True, bn_affine=True),
+    # tta_standard mode (corpus/basics.py:414-419,519-530): a fresh model copy, optimiser and hooks for every batch,
+    # momentum_mvg = 1 (no accumulation of target statistics), several gradient steps on the same batch
+    "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
+                                     lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }
 
 SWIN_CASES = {
@@ -89,10 +93,14 @@ class _CopyProxy:
     def __getattr__(self, name):
         return getattr(copy, name)
 
+    on_model_copy = None   # callback: tta_standard mode re-creates model + hooks per batch
+
     def deepcopy(self, obj, *a):
         out = copy.deepcopy(obj, *a)
         if isinstance(obj, nn.Module):
             self._sink.append(out)
+            if self.on_model_copy is not None:
+                self.on_model_copy()
         return out
 
 
@@ -110,6 +118,8 @@ def _base_args(ref, cfg, arch):
     args.n_augmented_views = cfg["M"]
     args.lr = cfg["lr"]
     args.update_only_bn_affine = cfg.get("bn_affine", False)
+    args.if_tta_standard = cfg.get("mode", "tta_online")
+    args.n_gradient_steps = cfg.get("gsteps", 1)
     args.momentum_mvg = cfg.get("momentum_mvg", 0.1)
     args.lambda_pred_consis = cfg.get("lambda_consis", 0.1)
     args.stat_type = ["spatiotemp"]
@@ -231,6 +241,10 @@ def run_model_case(name, cfg, arch):
         return v
     basics.compute_pred_consis = consis_rec
     basics.cp = _CopyProxy(rec["models"])
+
+    def _new_model():
+        Recording._count = 0      # hooks are re-created for every model copy: index them per copy
+    basics.cp.on_model_copy = _new_model
     try:
         top1 = basics.tta_standard(model, nn.CrossEntropyLoss(), args=args, logger=logging.getLogger("golden"),
                                    writer=None)
@@ -239,35 +253,39 @@ def run_model_case(name, cfg, arch):
         basics.compute_pred_consis = orig_consis
         basics.cp = copy
 
-    adapted = rec["models"][0]
+    adapted = rec["models"][-1]   # tta_online: the one copy; tta_standard: the copy adapted on the last batch
     n_hooks = Recording._count
-    out = {"top1": np.float32(top1[0]), "n_hooks": np.int64(n_hooks), "steps": np.int64(steps)}
+    gsteps = cfg.get("gsteps", 1)
+    out = {"top1": np.float32(top1[0]), "n_hooks": np.int64(n_hooks), "steps": np.int64(steps),
+           "gsteps": np.int64(gsteps)}
     for i, (m, v) in enumerate(zip(src_mean, src_var)):
         out["src_mean/%d" % i] = m.astype(np.float32)
         out["src_var/%d" % i] = v.astype(np.float32)
-    assert len(rec["hooks"]) == n_hooks * steps, (len(rec["hooks"]), n_hooks, steps)
+    assert len(rec["hooks"]) == n_hooks * steps * gsteps, (len(rec["hooks"]), n_hooks, steps, gsteps)
+    assert len(rec["outputs"]) == steps * (gsteps + 1)
     for s in range(steps):
-        rsum = 0.0
-        # hooks fire in execution order (bn1, tam.G.1, tam.L.1, bn2, ...); index them by creation order
-        step_recs = sorted(rec["hooks"][s * n_hooks:(s + 1) * n_hooks], key=lambda t: t[0])
-        for h in range(n_hooks):
-            idx, em, ev, r = step_recs[h]
-            assert idx == h
-            if em is not None:
-                out["step%d/ema_mean/%d" % (s, h)] = em
-                out["step%d/ema_var/%d" % (s, h)] = ev
-            out["step%d/r_feature/%d" % (s, h)] = np.float32(r)
-            rsum += r
-        out["step%d/loss_reg" % s] = np.float32(rsum)
-        if cfg["consis"]:
-            out["step%d/loss_consis" % s] = np.float32(rec["consis"][s])
-        tr, ev_ = rec["outputs"][2 * s], rec["outputs"][2 * s + 1]
-        if arch == "tanet":
-            out["step%d/train_logits" % s] = tr.detach().numpy()
-            out["step%d/eval_logits" % s] = ev_.detach().numpy()
-        else:
-            out["step%d/train_logits" % s] = tr[1].detach().numpy()   # per-view scores (N, V, K)
-            out["step%d/eval_logits" % s] = ev_[0].detach().numpy()
+        for j in range(gsteps):
+            # key prefix: "step<s>" (one gradient step per batch) or "step<s>.<j>" (n_gradient_steps > 1)
+            pre = "step%d" % s if gsteps == 1 else "step%d.%d" % (s, j)
+            fw = s * gsteps + j          # index of this training forward
+            rsum = 0.0
+            # hooks fire in execution order (bn1, tam.G.1, tam.L.1, bn2, ...); index them by creation order
+            step_recs = sorted(rec["hooks"][fw * n_hooks:(fw + 1) * n_hooks], key=lambda t: t[0])
+            for h in range(n_hooks):
+                idx, em, ev, r = step_recs[h]
+                assert idx == h
+                if em is not None:
+                    out["%s/ema_mean/%d" % (pre, h)] = em
+                    out["%s/ema_var/%d" % (pre, h)] = ev
+                out["%s/r_feature/%d" % (pre, h)] = np.float32(r)
+                rsum += r
+            out["%s/loss_reg" % pre] = np.float32(rsum)
+            if cfg["consis"]:
+                out["%s/loss_consis" % pre] = np.float32(rec["consis"][fw])
+            tr = rec["outputs"][s * (gsteps + 1) + j]
+            out["%s/train_logits" % pre] = (tr if arch == "tanet" else tr[1]).detach().numpy()   # Swin: (N, V, K)
+        ev_ = rec["outputs"][s * (gsteps + 1) + gsteps]
+        out["step%d/eval_logits" % s] = (ev_ if arch == "tanet" else ev_[0]).detach().numpy()
     # weight movement after all steps: per-tensor delta norms + a few full deltas
     new_sd = adapted.state_dict()
     names, dn = [], []
@@ -293,7 +311,7 @@ def run_model_case(name, cfg, arch):
         out["delta/" + n] = d[:4096].numpy().copy()   # leading slice only: keeps the fixtures small
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
-    print("wrote", name, "hooks", n_hooks, "loss_reg", [float(out["step%d/loss_reg" % s]) for s in range(steps)],
+    print("wrote", name, "hooks", n_hooks, "loss_reg", [float(v) for k, v in sorted(out.items()) if k.endswith("/loss_reg")],
           "consis", rec["consis"], "top1", float(top1[0]))
 
 

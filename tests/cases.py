@@ -21,6 +21,10 @@ TANET_CASES = {
                                        lr=1e-6, moving_avg=False),   # KLD sums over channels: large gradients
     "tanet_t8_r64_consis_l1_bnaffine": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                             lr=1e-3, moving_avg=True, bn_affine=True),
+    # tta_standard mode (corpus/basics.py:414-419,519-530): a fresh model copy, optimiser and hooks for every batch,
+    # momentum_mvg = 1 (no accumulation of target statistics), several gradient steps on the same batch
+    "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
+                                     lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }
 
 SWIN_CASES = {
