@@ -45,6 +45,10 @@ TANET_CASES = {
                                             lr=1e-3, moving_avg=True, bn_affine=True),
     # tta_standard mode (corpus/basics.py:414-419,519-530): a fresh model copy, optimiser and hooks for every batch,
     # momentum_mvg = 1 (no accumulation of target statistics), several gradient steps on the same batch
+    # --stat_reg BNS (utils/BNS_utils.py:19-77): statistics of every BN *input* (BatchNorm1d of the TAM branches
+    # included) against that layer's running statistics, EMA from zeros (running_manner)
+    "tanet_t8_r64_bns_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
+                                lr=1e-3, moving_avg=True, stat_reg="BNS"),
     "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                      lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }
@@ -118,6 +122,7 @@ def _base_args(ref, cfg, arch):
     args.n_augmented_views = cfg["M"]
     args.lr = cfg["lr"]
     args.update_only_bn_affine = cfg.get("bn_affine", False)
+    args.stat_reg = cfg.get("stat_reg", "mean_var")
     args.if_tta_standard = cfg.get("mode", "tta_online")
     args.n_gradient_steps = cfg.get("gsteps", 1)
     args.momentum_mvg = cfg.get("momentum_mvg", 0.1)
@@ -229,6 +234,22 @@ def run_model_case(name, cfg, arch):
                                      float(self.r_feature.detach())))
     nsu.CombineNormStatsRegHook_onereg = Recording
 
+    base_bns = basics.BNFeatureHook
+
+    class RecordingBNS(base_bns):
+        """--stat_reg BNS: the hooks are BNFeatureHook (utils/BNS_utils.py:19-77), also on the TAM's BatchNorm1d."""
+
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.idx = Recording._count
+            Recording._count += 1
+
+        def hook_fn(self, module, inp, out):
+            super().hook_fn(module, inp, out)
+            rec["hooks"].append((self.idx, self.mean.detach().numpy().copy(), self.var.detach().numpy().copy(),
+                                 float(self.r_feature.detach())))
+    basics.BNFeatureHook = RecordingBNS
+
     def out_hook(m, i, o):
         rec["outputs"].append(o)
     top = model
@@ -249,6 +270,7 @@ def run_model_case(name, cfg, arch):
         top1 = basics.tta_standard(model, nn.CrossEntropyLoss(), args=args, logger=logging.getLogger("golden"),
                                    writer=None)
     finally:
+        basics.BNFeatureHook = base_bns
         nsu.CombineNormStatsRegHook_onereg = base_cls
         basics.compute_pred_consis = orig_consis
         basics.cp = copy

@@ -472,7 +472,8 @@ class TTAState:
 
     def __init__(self, sd, arch, clip_len, src_means, src_vars, chosen_blocks, reg_type="l1_loss",
                  moving_avg=True, momentum_mvg=0.1, lr=5e-5, momentum=0.9, weight_decay=5e-4,
-                 swin_cfg=None, name_prefix="", update_only_bn_affine=False):
+                 swin_cfg=None, name_prefix="", update_only_bn_affine=False, stat_reg="mean_var",
+                 running_manner=True, momentum_bns=0.1):
         self.arch, self.clip_len = arch, clip_len
         self.swin_cfg = swin_cfg or {}
         self.sd = {}
@@ -498,7 +499,16 @@ class TTAState:
         else:
             self.opt = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.taps = {}
-        if arch == "tanet":
+        if stat_reg == "BNS":
+            # corpus/basics.py:588-600: a BNFeatureHook on EVERY BatchNorm (1d/2d/3d) of the chosen blocks, target = the
+            # layer's own running statistics as they are when the hook is created
+            assert arch == "tanet", "BNS is defined on BatchNorm layers"
+            for name, kind in tanet_norm_layers():
+                if any(b in name_prefix + name for b in chosen_blocks):
+                    self.taps[name] = BnsTap(self.sd[name + ".running_mean"], self.sd[name + ".running_var"], reg_type,
+                                             running_manner, momentum_bns)
+                    self.taps[name].kind = "bns"
+        elif arch == "tanet":
             layers = tanet_norm_layers()
             it = iter(range(len(src_means)))
             for name, kind in layers:

@@ -23,6 +23,10 @@ TANET_CASES = {
                                             lr=1e-3, moving_avg=True, bn_affine=True),
     # tta_standard mode (corpus/basics.py:414-419,519-530): a fresh model copy, optimiser and hooks for every batch,
     # momentum_mvg = 1 (no accumulation of target statistics), several gradient steps on the same batch
+    # --stat_reg BNS (utils/BNS_utils.py:19-77): statistics of every BN *input* (BatchNorm1d of the TAM branches
+    # included) against that layer's running statistics, EMA from zeros (running_manner)
+    "tanet_t8_r64_bns_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
+                                lr=1e-3, moving_avg=True, stat_reg="BNS"),
     "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                      lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }
