@@ -182,6 +182,15 @@ class StatsArena:
         ly.fired = True
         return ly.part
 
+    def set_source(self, ly, mean, var):
+        """Replace the target statistics of one layer (BNFeatureHook with use_src_stat_in_reg=False: the target is the
+        layer's live running statistics at hook time, utils/BNS_utils.py:61-62)."""
+        if not self.frozen:
+            raise _lib.VittaError("set_source: the arena has no device buffers yet (call after the layer recorded)")
+        sl = slice(ly.ch_off, ly.ch_off + ly.C)
+        self.src_mean[sl].copy_(mean.detach().reshape(-1))
+        self.src_var[sl].copy_(var.detach().reshape(-1))
+
     def record(self, ly, feat, O, Cc, I, frames=1):
         """Standalone K1 launch on a feature tensor (hooks on stock torch modules)."""
         part = self.partial_buffer(ly, O, Cc, I, frames, feat.device)

@@ -45,8 +45,6 @@ class BNFeatureHook(nsu._TapBase):
     def __init__(self, module, reg_type='l2norm', running_manner=False, use_src_stat_in_reg=True, momentum=0.1):
         if not isinstance(module, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
             raise VittaError("BNFeatureHook needs a BatchNorm module")
-        if not use_src_stat_in_reg:
-            raise VittaError("use_src_stat_in_reg=False (live running stats as the target) is not supported")
         self.reg_type = reg_type
         self.running_manner = running_manner
         self.use_src_stat_in_reg = use_src_stat_in_reg
@@ -76,6 +74,10 @@ class BNFeatureHook(nsu._TapBase):
         else:
             ly.token = None
             arena.record(ly, x, O, c, I, 1)
+        if not self.use_src_stat_in_reg:
+            # reference :61-62: the target is the layer's running statistics as they are NOW (they move when the BN layer
+            # is in train mode, i.e. --fix_BNS False); with use_src_stat_in_reg they stay the construction-time snapshot
+            arena.set_source(ly, module.running_mean, module.running_var)
 
     @property
     def r_feature(self):
