@@ -83,6 +83,8 @@ def main():
                 prof, _lib.profile = _lib.profile, None
                 for i, (nm, e0, e1, _args) in enumerate(prof):
                     kind = "fwd" if i < fwd_n else ("wgrad" if "wgrad" in nm else "dgrad")
+                    if "amax" in nm:      # VITTA_GEMM_PRECISION=f16x3 bring-up: standalone amax passes, reported apart
+                        kind = "amax"
                     acc[kind] = acc.get(kind, 0.0) + e0.elapsed_time(e1) * 1e3 / a.reps
                 outs[form] = (y.detach().clone(), x.grad.clone(), w.grad.clone())
                 x.grad = w.grad = None
@@ -113,6 +115,9 @@ def main():
         totf += flops * mult
         print("| %s | %d→%d %d/%d @%d | %d | %s%s |" % (name, cin, cout, k, s, r, mult, " | ".join(cells), chk))
     print()
+    amax_us = sum(res[2].get("amax", 0.0) * mult for _n, _ci, _co, _k, _s, _r, mult, _f, res, _c in rows)
+    print("operand split: %s%s" % (ops.gemm_precision(), "   (standalone amax passes: %.2f ms per step, not in the "
+                                   "columns above)" % (amax_us / 1e3) if amax_us else ""))
     for kd in ("fwd", "dgrad", "wgrad"):
         print("total %-5s: tmem-A %.2f ms (%.0f TF/s)   smem-A %.2f ms (%.0f TF/s)" % (
             kd, tot[(kd, 2)] / 1e3, totf / tot[(kd, 2)] / 1e6, tot[(kd, 1)] / 1e3, totf / tot[(kd, 1)] / 1e6))

@@ -1,0 +1,15 @@
+#!/bin/bash
+# First gpurun call of round 2: validate what round 1 prepared without a GPU, then the usual round.
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_round2_first.sh'
+mkdir -p gpurun_out
+# 1. fp16-split GEMM / conv / dgrad kernels against float64 (and against the tf32 kernels)
+VITTA_TEST_F16X3=1 timeout 900 python -m pytest tests/test_gpu_gemm_f16.py -q -x > gpurun_out/f16_tests.log 2>&1; echo "f16 tests rc=$?"; tail -5 gpurun_out/f16_tests.log
+# 2. option-mode goldens and the live-target BNS test that round 1 could only pin on the CPU oracle
+VITTA_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_kernels.py -q -k "option_modes or live_running" > gpurun_out/unverified_tests.log 2>&1; echo "unverified rc=$?"; tail -5 gpurun_out/unverified_tests.log
+# 3. whole-model parity with the fp16 split routed in (forward + data gradient; weight gradient stays tf32)
+VITTA_GEMM_PRECISION=f16x3 timeout 1200 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_swin.py -q > gpurun_out/f16_models.log 2>&1; echo "f16 models rc=$?"; tail -5 gpurun_out/f16_models.log
+# 4. per-shape timing, both splits
+timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32.md 2>&1; tail -5 gpurun_out/conv_shapes_tf32.md
+VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16.md 2>&1; tail -5 gpurun_out/conv_shapes_f16.md
+# 5. the regular round (tests, bench, Swin tables)
+bash tools/gpu_round.sh
