@@ -218,6 +218,11 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
 #define VITTA_GEMM_FORCE_SS 0x1000
 #define VITTA_GEMM_FORCE_TS 0x2000
 int vitta_gemm_set_operand_form(int form);
+/* vitta_gemm_set_cta_pair(1): N tiles of 256 run as clusters of two CTAs issuing tcgen05.mma.cta_group::2 (M = 256 per
+ * pair; each CTA loads half of the weight tile, halving the L2 -> SM weight traffic that bounds the wide layers).
+ * Applies to the tf32 and fp16 kernels (forward, data gradient, Linear).  Default 0; opt-in until validated on hardware
+ * (round 1 wrote it after the GPU budget was spent -- DESIGN.md section 9). */
+int vitta_gemm_set_cta_pair(int on);
 int vitta_split_tf32(const float* src, float* hi, float* lo, int R, int T, int Cc, int mode, void* stream);
 int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                       int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,

@@ -105,3 +105,57 @@ def test_conv2d_dgrad_f16x3_vs_float64(cuda_device, f, h, cin, cout, kh, stride,
     gx = ops.conv2d_dgrad_f16x3(go, wh, wl, wam, tuple(x.shape), kh, kh, stride, pad)
     scale = float(x.grad.abs().max())
     assert float((gx.double() - x.grad).abs().max()) < 3e-6 * scale * (cout * kh * kh) ** 0.5
+
+
+# ---- CTA pairs (cta_group::2), tf32 and fp16 splits ------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (1000, 512, 256), (6272, 2048, 512), (128, 256, 128), (3000, 768, 96)])
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
+def test_gemm_cta_pairs_vs_single_cta_and_float64(cuda_device, m, n, k, prec):
+    """vitta_gemm_set_cta_pair(1): the N = 256 tiles run as cta_group::2 pairs (M = 256 per MMA).  Same products in the
+    same order per accumulator as the single-CTA kernel, so the two must agree to fp32 rounding; both against float64.
+    Odd numbers of M tiles (m = 1000, 3000) exercise the all-out-of-bounds tile of the second CTA."""
+    from vitta_b200 import _lib, ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).to(cuda_device)
+    if prec == "tf32":
+        bh, bl = ops.split_tf32(b)
+        run = lambda: ops.gemm_tf32x3(a, bh, bl, n, force_bn=256)
+    else:
+        bh, bl, bam = ops.split_f16(b)
+        aam = ops.amax_f32(a)
+        run = lambda: ops.gemm_f16x3(a, bh, bl, bam, n, a_amax=aam, force_bn=256)
+    single = run()
+    try:
+        _lib.call("vitta_gemm_set_cta_pair", 1)
+        pair = run()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("vitta_gemm_set_cta_pair", 0)
+    ref = a.double() @ b.double().t()
+    absprod = a.double().abs() @ b.double().abs().t()
+    _err_ok(pair, ref, absprod, k)
+    assert float((pair - single).abs().max()) <= 2e-6 * float(single.abs().max())
+
+
+@pytest.mark.parametrize("f,h,cin,cout,kh,stride,pad", [(8, 14, 256, 256, 3, 1, 1), (16, 14, 1024, 256, 1, 1, 0),
+                                                        (5, 28, 128, 512, 1, 1, 0), (4, 14, 512, 512, 3, 2, 1)])
+def test_conv_cta_pairs_match_single_cta(cuda_device, f, h, cin, cout, kh, stride, pad):
+    """Forward, data gradient and (unchanged) weight gradient of Conv2dFn with CTA pairs on against off, tf32 split."""
+    from vitta_b200 import _lib, ops
+    g = torch.Generator().manual_seed(f + cin)
+    x = torch.randn(f, cin, h, h, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, kh, kh, generator=g) / (cin * kh * kh) ** 0.5).to(cuda_device)
+    res = []
+    try:
+        for on in (0, 1):
+            _lib.call("vitta_gemm_set_cta_pair", on)
+            x1 = x.clone(memory_format=torch.channels_last).requires_grad_(True)
+            w1 = wt.clone().requires_grad_(True)
+            y = ops.conv2d(x1, w1, stride, pad)
+            y.backward(torch.ones_like(y) * 0.5)
+            res.append((y.detach(), x1.grad, w1.grad))
+    finally:
+        _lib.call("vitta_gemm_set_cta_pair", 0)
+    for a, b in zip(*res):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())

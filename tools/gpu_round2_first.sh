@@ -8,6 +8,8 @@ VITTA_TEST_F16X3=1 timeout 900 python -m pytest tests/test_gpu_gemm_f16.py -q -x
 VITTA_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_kernels.py -q -k "option_modes or live_running" > gpurun_out/unverified_tests.log 2>&1; echo "unverified rc=$?"; tail -5 gpurun_out/unverified_tests.log
 # 3. whole-model parity with the fp16 split routed in (forward + data gradient; weight gradient stays tf32)
 VITTA_GEMM_PRECISION=f16x3 timeout 1200 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_swin.py -q > gpurun_out/f16_models.log 2>&1; echo "f16 models rc=$?"; tail -5 gpurun_out/f16_models.log
+# 3b. CTA pairs on for the whole model (tf32 split), only if their unit tests passed above
+VITTA_GEMM_CTA_PAIR=1 timeout 900 python -m pytest tests/test_gpu_tanet.py -q -k "golden and not option" > gpurun_out/pair_models.log 2>&1; echo "pair models rc=$?"; tail -3 gpurun_out/pair_models.log
 # 4. per-shape timing, both splits
 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32.md 2>&1; tail -5 gpurun_out/conv_shapes_tf32.md
 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16.md 2>&1; tail -5 gpurun_out/conv_shapes_f16.md

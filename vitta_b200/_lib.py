@@ -58,6 +58,7 @@ _SIGNATURES = {
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vitta_gemm_set_operand_form": (C.c_int, [C.c_int]),
+    "vitta_gemm_set_cta_pair": (C.c_int, [C.c_int]),
     "vitta_split_tf32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_gemm_tf32x3": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
                                     C.c_int64, C.c_int, C.c_int, _P]),
@@ -126,6 +127,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    if os.environ.get("VITTA_GEMM_CTA_PAIR") == "1":      # opt-in cta_group::2 kernels
+        lib.vitta_gemm_set_cta_pair(1)
     return lib
 
 

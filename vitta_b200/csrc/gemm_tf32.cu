@@ -95,14 +95,23 @@ struct GemmSmem {
   static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
 
-template <int BN, bool TS, bool F16 = false>
+// PAIR = true (vitta_gemm_set_cta_pair(1), N tile 256 only): the kernel runs as clusters of two CTAs on one TPC and the
+// MMAs are tcgen05.mma.cta_group::2 of M = 256: CTA r of the pair owns M tile 2*pm + r (its own A stages, its own 128
+// accumulator lanes and epilogue) and loads rows [r*BN/2, +BN/2) of the B tile, so every weight byte is fetched from L2
+// once per 256 output rows instead of once per 128 -- the operand feed, not the tensor pipe, bounds the wide layers
+// (DESIGN.md section 9).  Only CTA 0 issues MMAs; the split warps and epilogue warps of CTA 1 arrive on CTA 0's
+// barriers through the cluster address space, and CTA 0's commits are multicast to the barriers of both CTAs.
+template <int BN, bool TS, bool F16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   static_assert(!(TS && F16), "the fp16 split uses the shared-memory A form");
+  static_assert(!PAIR || (!TS && BN == 256), "CTA pairs: shared-memory A form, N tile 256 (single accumulator chain)");
   using S = GemmSmem<BN, TS>;
   constexpr int kStages = S::kStages;
   constexpr int kStageK = F16 ? 2 * kBK : kBK;   // K elements per stage (fp16: two raw A boxes)
+  constexpr int kBRows = PAIR ? BN / 2 : BN;     // B rows this CTA loads per stage
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
@@ -119,21 +128,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_f;
-  const int total_tiles = tiles_m * p.tiles_n;
+  // PAIR: the tile loop runs over pair tiles (two consecutive M tiles x one N tile); `tile_step` pairs work in parallel
+  const int total_tiles = PAIR ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
+// tile loop of a role: CTAs (PAIR: CTA pairs) stride over the tiles.  Spelled with blockIdx / gridDim at every use so that
+// the compiler keeps the loop state warp-uniform (descriptors in uniform registers, see profiles/r01_gemm_issue.md).
+#define VITTA_TILE_LOOP \
+  for (int tile = PAIR ? (blockIdx.x >> 1) : blockIdx.x; tile < total_tiles; tile += PAIR ? (gridDim.x >> 1) : gridDim.x)
   const int taps = p.ntaps ? p.ntaps : p.taps_h * p.taps_w;
   const int k_iters = taps * p.k_chunks;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BF) * kBK * 4;
-  const uint32_t stage_tx = (F16 ? 2u : 1u) * a_box_bytes + 2u * S::kBBytes;
+  const uint32_t stage_tx = (F16 ? 2u : 1u) * a_box_bytes + 2u * (uint32_t)(kBRows * 128);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], kSplitWarps);    // one elected arrive per split warp
+      mbar_init(&split_bar[s], (PAIR ? 2 : 1) * kSplitWarps);    // one elected arrive per split warp (of both CTAs)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);    // one elected arrive per epilogue warp
+      mbar_init(&acc_empty[a], PAIR ? 8 : 4);    // one elected arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -143,30 +157,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmBlo);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(S::kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (PAIR) {   // one warp of EACH CTA of the pair performs the pair allocation
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(S::kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(S::kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anyone arrives remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      VITTA_TILE_LOOP {
         const int nt = tile % p.tiles_n;
         int mt = tile / p.tiles_n;
+        if constexpr (PAIR) mt = 2 * mt + (int)cta_rank;   // may equal tiles_m (odd count): an all-OOB tile, nothing stored
         const int wb = mt % p.tiles_w; mt /= p.tiles_w;
         const int hb = mt % p.tiles_h;
         const int fb = mt / p.tiles_h;
         const int w_in0 = wb * p.BW * p.stride - p.pad;
         const int h_in0 = hb * p.BH * p.stride - p.pad;
         const int f0 = fb * p.BF;
-        const int n0 = nt * BN;
+        const int n0 = nt * BN + (PAIR ? (int)cta_rank * kBRows : 0);   // PAIR: this CTA's half of the B tile
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_chunks;
           const int kc = (it - tap * p.k_chunks) * kStageK;
@@ -191,13 +214,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    VITTA_TILE_LOOP {
+      if constexpr (PAIR) {
+        if (cta_rank != 0) break;   // only the first CTA of a pair issues MMAs
+      }
+      if constexpr (PAIR) mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+      else mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * S::kAccCols);
       for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);    // B tiles (and raw A) landed
-        mbar_wait(&split_bar[stage], phase);   // a_hi / a_lo written
+        if constexpr (PAIR) {
+          // split done in BOTH CTAs; a CTA's split warps only start after its own TMA landed (A boxes and its B half)
+          mbar_wait_cluster(&split_bar[stage], phase);
+        } else {
+          mbar_wait(&full_bar[stage], phase);    // B tiles (and raw A) landed
+          mbar_wait(&split_bar[stage], phase);   // a_hi / a_lo written
+        }
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = smem_u32(smem + stage * S::kStageBytes);
@@ -224,7 +256,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           } else {
             const uint64_t a_hi = umma_desc_sw128(st);
             const uint64_t a_lo = umma_desc_sw128(st + S::kABytes);
-            if constexpr (F16) {
+            if constexpr (PAIR) {
+              // M = 256 over the pair, N = BN: the descriptors name this CTA's tiles, the peer uses the same offsets
+              constexpr uint32_t idesc2 = F16 ? umma_idesc_f16(2 * kBM, BN) : umma_idesc_tf32(2 * kBM, BN);
+#pragma unroll
+              for (int k = 0; k < kBK / 8; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                if constexpr (F16) {
+                  umma_f16_2cta(d_tmem, a_lo + adv, b_hi + adv, idesc2, (it | k) != 0);
+                  umma_f16_2cta(d_tmem, a_hi + adv, b_lo + adv, idesc2, 1);
+                  umma_f16_2cta(d_tmem, a_hi + adv, b_hi + adv, idesc2, 1);
+                } else {
+                  umma_tf32_2cta(d_tmem, a_lo + adv, b_hi + adv, idesc2, (it | k) != 0);
+                  umma_tf32_2cta(d_tmem, a_hi + adv, b_lo + adv, idesc2, 1);
+                  umma_tf32_2cta(d_tmem, a_hi + adv, b_hi + adv, idesc2, 1);
+                }
+              }
+            } else if constexpr (F16) {
 #pragma unroll
               for (int k = 0; k < kBK / 8; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);   // 16 fp16 = 32 B = 2 x 16 B inside the swizzle atom row
@@ -239,7 +287,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
 #pragma unroll
-            for (int k = 0; k < (F16 ? 0 : kBK / 8); ++k) {
+            for (int k = 0; k < ((F16 || PAIR) ? 0 : kBK / 8); ++k) {
               const uint64_t adv = (uint64_t)(k * 2);   // 8 tf32 = 32 B = 2 x 16 B inside the swizzle atom row
               if constexpr (S::kCat) {
                 umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_cat, (it | k) != 0);
@@ -252,8 +300,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
           }
-          umma_commit(&empty_bar[stage]);                       // smem stage reusable once these MMAs retire
-          if (it == k_iters - 1) umma_commit(&acc_full[acc]);   // accumulator complete
+          if constexpr (PAIR) {
+            umma_commit_2cta(&empty_bar[stage]);                       // both CTAs' producers may refill the stage
+            if (it == k_iters - 1) umma_commit_2cta(&acc_full[acc]);   // both CTAs' epilogues may drain their lanes
+          } else {
+            umma_commit(&empty_bar[stage]);                       // smem stage reusable once these MMAs retire
+            if (it == k_iters - 1) umma_commit(&acc_full[acc]);   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -310,7 +363,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t sw = (uint32_t)(row & 7);
       float sa, inv_unused;
       f16_split_scale(__ldg(p.a_amax), sa, inv_unused);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      VITTA_TILE_LOOP {
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           uint8_t* st = smem + stage * S::kStageBytes;
@@ -339,12 +392,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(&split_bar[stage], 0);   // the issuing CTA's barrier
+            else mbar_arrive(&split_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     } else {
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      VITTA_TILE_LOOP {
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           float4* a = reinterpret_cast<float4*>(smem + stage * S::kStageBytes);
@@ -361,7 +417,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(&split_bar[stage], 0);   // the issuing CTA's barrier
+            else mbar_arrive(&split_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -378,9 +437,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       f16_split_scale(__ldg(p.a_amax), s_unused, inv_a);
       f16_split_scale(__ldg(p.b_amax), s_unused, inv_b);
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    VITTA_TILE_LOOP {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
+      if constexpr (PAIR) mt = 2 * mt + (int)cta_rank;
       const int wb = mt % p.tiles_w; mt /= p.tiles_w;
       const int hb = mt % p.tiles_h;
       const int fb = mt / p.tiles_h;
@@ -506,16 +566,24 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(&acc_empty[acc], 0);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's shared and tensor memory are operands until the last MMA retired
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::kTmemCols));
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::kTmemCols));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::kTmemCols));
   }
+#undef VITTA_TILE_LOOP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -643,14 +711,14 @@ int cached_sm_count() {
   return g_sms > 0 ? g_sms : 148;
 }
 
-template <int BN, bool TS, bool F16 = false>
+template <int BN, bool TS, bool F16 = false, bool PAIR = false>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, GemmParams p,
                        cudaStream_t st) {
   using S = GemmSmem<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS, F16, PAIR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -663,9 +731,35 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
     set_error("gemm_tf32x3: bad tile count");
     return VITTA_E_BADARG;
   }
+  cudaError_t e;
+  if constexpr (PAIR) {
+    // clusters of two CTAs (one TPC); a pair works on two consecutive M tiles of one N tile
+    const int64_t tiles_m = (int64_t)p.tiles_w * p.tiles_h * p.tiles_f;
+    const int64_t pair_tiles = ((tiles_m + 1) / 2) * p.tiles_n;
+    const int64_t max_pairs = cached_sm_count() / 2;
+    const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, TS, F16, PAIR>, a, bh, bl, p);
+    if (e != cudaSuccess) {
+      set_error("gemm_tf32x3 (CTA pairs) launch: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    return 0;
+  }
   const int grid = (int)(tiles < cached_sm_count() ? tiles : cached_sm_count());
   gemm_tf32x3_kernel<BN, TS, F16><<<grid, kGemmThreads, S::kTotal, st>>>(a, bh, bl, p);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm_tf32x3 launch: %s", cudaGetErrorString(e));
     return (int)e;
@@ -696,6 +790,9 @@ static int pick_bn(int N, int forced, int64_t tiles_m = 0) {
 }
 
 int g_gemm_operand_form = 0;   // vitta_gemm_set_operand_form: 0 automatic, 1 shared-memory A, 2 tensor-memory A
+int g_gemm_cta_pair = 0;       // vitta_gemm_set_cta_pair: N = 256 tiles as cta_group::2 pairs (opt-in until validated on hardware)
+
+static bool use_pair(int bn, int force) { return g_gemm_cta_pair && bn == 256 && !(force & kForceTS); }
 
 // form: bits of force_bn (kForceSS / kForceTS), else the process-wide setting, else automatic
 static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, const GemmParams& p, int bn,
@@ -703,8 +800,10 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorM
   if (p.a_amax) {   // fp16 split: shared-memory A form only
     if (bn == 64) return launch_gemm<64, false, true>(a, bh, bl, p, st);
     if (bn == 128) return launch_gemm<128, false, true>(a, bh, bl, p, st);
+    if (use_pair(bn, force)) return launch_gemm<256, false, true, true>(a, bh, bl, p, st);
     return launch_gemm<256, false, true>(a, bh, bl, p, st);
   }
+  if (use_pair(bn, force)) return launch_gemm<256, false, false, true>(a, bh, bl, p, st);
   int form = (force & kForceSS) ? 1 : (force & kForceTS) ? 2 : g_gemm_operand_form;
   if (form == 0) form = (bn == 64) ? 2 : 1;   // measured per tile width: profiles/r01_conv_shapes.md
   const bool ss = form == 1;
@@ -714,7 +813,8 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorM
 }
 
 static int make_b_maps(CUtensorMap* bh, CUtensorMap* bl, const void* Bhi, const void* Blo, int64_t ldb, int N,
-                       int Ktot, int bn, bool f16 = false) {
+                       int Ktot, int bn, bool f16 = false, int force = 0) {
+  if (use_pair(bn, force)) bn /= 2;   // CTA pairs: each CTA loads half of the B tile's rows
   const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)N};
   const uint32_t es[2] = {1, 1};
   if (f16) {   // [N][Ktot] fp16, 64 K elements (128 B) per stage row
@@ -759,6 +859,11 @@ static void pick_boxes(int Wo, int Ho, int F, int* pBW, int* pBH, int* pBF) {
 using namespace vitta;
 
 extern "C" {
+
+int vitta_gemm_set_cta_pair(int on) {
+  g_gemm_cta_pair = on ? 1 : 0;
+  return 0;
+}
 
 int vitta_gemm_set_operand_form(int form) {
   VITTA_CHECK_ARG(form >= 0 && form <= 2, VITTA_E_BADARG,
@@ -813,7 +918,7 @@ static int gemm_impl(const float* A, int64_t lda, const void* Bhi, const void* B
     int rc = make_tensor_map_f32(&ta, A, 4, dims, str, box, es);
     if (rc) return rc;
   }
-  int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn, f16);
+  int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn, f16, force_bn);
   if (rc) return rc;
   GemmParams p{};
   p.a_amax = a_amax; p.b_amax = b_amax;
@@ -875,7 +980,7 @@ static int conv2d_impl(const float* X, int F, int H, int W, int Cin, const void*
     if (rc) return rc;
   }
   const int Ktot = KH * KW * Cin;
-  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn, f16);
+  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn, f16, force_bn);
   if (rc) return rc;
   GemmParams p{};
   p.a_amax = a_amax; p.b_amax = b_amax;
