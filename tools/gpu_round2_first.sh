@@ -13,5 +13,7 @@ VITTA_GEMM_CTA_PAIR=1 timeout 900 python -m pytest tests/test_gpu_tanet.py -q -k
 # 4. per-shape timing, both splits
 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32.md 2>&1; tail -5 gpurun_out/conv_shapes_tf32.md
 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16.md 2>&1; tail -5 gpurun_out/conv_shapes_f16.md
+VITTA_GEMM_CTA_PAIR=1 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32_pair.md 2>&1; tail -5 gpurun_out/conv_shapes_tf32_pair.md
+VITTA_GEMM_CTA_PAIR=1 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16_pair.md 2>&1; tail -5 gpurun_out/conv_shapes_f16_pair.md
 # 5. the regular round (tests, bench, Swin tables)
 bash tools/gpu_round.sh
