@@ -71,12 +71,13 @@ struct GemmParams {
 // only: per stage the smem port sees TMA writes + one A read + the B operand reads, instead of additionally the
 // hi/lo write-back and 12 A operand reads -- the SS form saturates the 128 B/clk shared-memory port long before the
 // tensor pipe (BN = 64: ~152 KB per 384 MMA cycles), which is what bounds the narrow-N tiles.
-template <int BN, bool TS>
+template <int BN, bool TS, bool PAIR = false>
 struct GemmSmem {
   static_assert(!TS || BN <= 128, "the TMEM-operand form needs 2*BN accumulator columns + 64 columns per stage");
-  static constexpr int kStages = TS ? 4 : ((BN <= 128) ? 3 : 2);
+  // PAIR (cta_group::2): a CTA stages only its half of the B tile's rows, which buys a third stage at BN = 256
+  static constexpr int kStages = TS ? 4 : ((BN <= 128 || PAIR) ? 3 : 2);
   static constexpr int kABytes = kBM * kBK * 4;   // 16 KB
-  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 4;
   static constexpr int kBOff = TS ? kABytes : 2 * kABytes;   // B hi tile offset inside a stage (B lo follows)
   static constexpr int kStageBytes = kBOff + 2 * kBBytes;
   static constexpr int kBarBytes = 1024;
@@ -107,7 +108,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   static_assert(!(TS && F16), "the fp16 split uses the shared-memory A form");
   static_assert(!PAIR || (!TS && BN == 256), "CTA pairs: shared-memory A form, N tile 256 (single accumulator chain)");
-  using S = GemmSmem<BN, TS>;
+  using S = GemmSmem<BN, TS, PAIR>;
   constexpr int kStages = S::kStages;
   constexpr int kStageK = F16 ? 2 * kBK : kBK;   // K elements per stage (fp16: two raw A boxes)
   constexpr int kBRows = PAIR ? BN / 2 : BN;     // B rows this CTA loads per stage
@@ -137,7 +138,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int taps = p.ntaps ? p.ntaps : p.taps_h * p.taps_w;
   const int k_iters = taps * p.k_chunks;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BF) * kBK * 4;
-  const uint32_t stage_tx = (F16 ? 2u : 1u) * a_box_bytes + 2u * (uint32_t)(kBRows * 128);
+  const uint32_t stage_tx = (F16 ? 2u : 1u) * a_box_bytes + 2u * S::kBBytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -714,7 +715,7 @@ int cached_sm_count() {
 template <int BN, bool TS, bool F16 = false, bool PAIR = false>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtensorMap& bl, GemmParams p,
                        cudaStream_t st) {
-  using S = GemmSmem<BN, TS>;
+  using S = GemmSmem<BN, TS, PAIR>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TS, F16, PAIR>,
