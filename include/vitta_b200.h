@@ -265,6 +265,8 @@ int vitta_conv2d_dgrad_tf32x3(const float* dY, int F, int Ho, int Wo, int Cout, 
  *   vitta_split_f16: weight preparation like vitta_split_tf32 (same modes) into two fp16 arrays, scaled by *amax's s.
  *   vitta_gemm_f16x3_ex / vitta_conv2d_f16x3_ex / vitta_conv2d_dgrad_f16x3: the tf32 entry points with fp16 weight pieces
  *     (ldb in fp16 elements, multiple of 8) and the two amax scalars.  Shared-memory A form; a stage holds 64 K elements.
+ *   vitta_conv2d_wgrad_f16x3: the weight gradient with both activations split in-kernel (dY^T as packed fp16 pairs in
+ *     tensor memory, X converted in place into 16-bit MN-major atoms); amax scalars of X and dY.
  * Round-1 status: compiled, exported and covered by opt-in GPU tests (VITTA_TEST_F16X3=1); the adaptation step still
  * runs the tf32 kernels until the producers emit amax. */
 int vitta_amax_f32(const float* x, int64_t n, float* amax, void* stream);
@@ -277,6 +279,9 @@ int vitta_gemm_f16x3_ex(const float* A, int64_t lda, const float* a_amax, const 
 int vitta_conv2d_f16x3_ex(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
                           const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad, float* Y,
                           const float* bias, const float* residual, int force_bn, void* stream);
+int vitta_conv2d_wgrad_f16x3(const float* X, const float* x_amax, const float* dY, const float* dy_amax, int F, int H,
+                             int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* dW, int accumulate,
+                             float* ws, void* stream);   /* same ws size and reduction as vitta_conv2d_wgrad_tf32x3 */
 int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int Ho, int Wo, int Cout, const void* Wthi,
                              const void* Wtlo, const float* w_amax, int Cin, int KH, int KW, int stride, int pad, int H,
                              int W, float* dX, void* stream);

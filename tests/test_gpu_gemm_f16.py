@@ -159,3 +159,26 @@ def test_conv_cta_pairs_match_single_cta(cuda_device, f, h, cin, cout, kh, strid
         _lib.call("vitta_gemm_set_cta_pair", 0)
     for a, b in zip(*res):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("f,h,w,cin,cout,kh,stride,pad", [
+    (4, 14, 14, 64, 128, 3, 1, 1), (32, 7, 7, 32, 64, 3, 1, 1), (2, 56, 56, 64, 64, 3, 1, 1), (6, 28, 28, 128, 128, 3, 1, 1),
+    (2, 56, 56, 64, 256, 1, 1, 0), (3, 28, 28, 128, 128, 3, 2, 1), (3, 14, 14, 256, 512, 1, 2, 0),
+    (16, 7, 7, 512, 512, 3, 1, 1), (64, 14, 14, 1024, 256, 1, 1, 0), (5, 14, 14, 36, 20, 1, 1, 0),
+])
+def test_conv2d_wgrad_f16x3_vs_float64(cuda_device, f, h, w, cin, cout, kh, stride, pad):
+    """Weight gradient on kind::f16 (dY^T packed in tensor memory, X converted in place to 16-bit MN-major atoms) with a
+    gradient-sized dY; same float64 bound as the tf32 kernel."""
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(f * 5 + h + cout)
+    x = torch.randn(f, cin, h, w, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kh) // stride + 1
+    gy = (torch.randn(f, cout, ho, wo, generator=g) * 1e-7).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    gw = ops.conv2d_wgrad_f16x3(x, gy, cout, kh, kh, stride, pad)
+    torch.cuda.synchronize()
+    wt = torch.zeros(cout, cin, kh, kh, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    F.conv2d(x.double(), wt, None, stride, pad).backward(gy.double())
+    wa = torch.zeros_like(wt, requires_grad=True)
+    F.conv2d(x.double().abs(), wa, None, stride, pad).backward(gy.double().abs())
+    assert gw.shape == wt.grad.shape and gw.is_contiguous()
+    _err_ok(gw, wt.grad, wa.grad, f * ho * wo)

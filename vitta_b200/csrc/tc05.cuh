@@ -272,6 +272,29 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int m, int n) {   // b
   return umma_idesc_tf32(m, n) | (1u << 15) | (1u << 16);
 }
 
+// 16-bit MN-major operand tile, SWIZZLE_128B: a 128-byte row = one K index holding 64 MN-contiguous fp16 (eight 16-byte
+// chunks XORed with row % 8), 8 rows = one 1024-byte swizzle atom.  Canonical form (CUTLASS make_umma_desc<Major::MN>,
+// in 16-byte units): ((8,n),(8,k)):((1,LBO),(8,SBO)) -- SBO = distance between 8-row K groups, LBO = distance between
+// successive 64-element MN atoms.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_f16(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// D[tmem] (+)= A[tmem, packed fp16 pairs along K] * B[smem], kind::f16
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int make_tensor_map_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, const uint32_t* estr, bool swizzle_atom_32b = false);

@@ -8,6 +8,15 @@
 // operands are activations, so both are split in-kernel (hi in place, lo beside it) by four warps.
 // Work item = (Cout tile, tap, Cin tile, K split); every item writes its fp32 partial [128 x BN] to a workspace and
 // wgrad_reduce_kernel sums the K splits in a fixed order (deterministic) straight into the NCHW weight gradient.
+//
+// F16 = true (vitta_conv2d_wgrad_f16x3, tensor-memory form only): the same pipeline on kind::f16 with the fp16 operand split
+// of gemm_tf32.cu (x*s = hi + lo, s a per-tensor power of two from a device amax scalar).  dY^T goes to tensor memory as
+// PACKED fp16 pairs (column j of a stage = pixels 2j, 2j+1: 16 hi + 16 lo columns per 32-pixel stage); the X boxes land
+// with the plain 128B swizzle and are converted IN PLACE into 16-bit MN-major SWIZZLE_128B atoms of 64 channels x 32
+// pixels: box pair (2g, 2g+1) -> hi atom in box area g, lo atom in box area BN/64 + g (hi atoms adjacent, then lo atoms,
+// so [x_hi ; x_lo] is again one descriptor).  K = 16 pixels per MMA: half the MMAs and half the tensor-pipe work.
+#include <cuda_fp16.h>
+
 #include "tc05.cuh"
 
 namespace vitta {
@@ -28,6 +37,8 @@ struct WgradParams {
   int splits;
   int tap_group;           // filter taps covered by one item (1, or 3 in the BN = 192 mode)
   int box_base, box_rem;   // total_boxes = splits * box_base + box_rem: split sp covers box_base (+1 if sp < box_rem) boxes
+  const float* a_amax;     // F16 kernels: device scalars >= max|dY|, >= max|X|
+  const float* b_amax;
 };
 
 // TS = true: the dY tile (A operand, M = output channel) is transposed into TENSOR MEMORY by four of the split warps
@@ -60,10 +71,11 @@ struct WgSmem {
   static_assert(kTmemNeed <= 512, "tensor memory budget");
 };
 
-template <int BN, bool TS>
+template <int BN, bool TS, bool F16 = false>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                     const WgradParams p) {
+  static_assert(!F16 || (TS && BN % 64 == 0), "the fp16 split exists for the tensor-memory form, N tiles of 64 channels");
   using S = WgSmem<BN, TS>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -180,7 +192,27 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           const uint64_t b_hi = umma_desc_mn_sw128(st + S::kBOff, kWgBoxBytes);
           const uint64_t b_lo = umma_desc_mn_sw128(st + S::kBOff + S::kBBytes, kWgBoxBytes);
           const uint32_t first = (uint32_t)(b != b0);
-          if constexpr (TS) {
+          if constexpr (F16) {
+            constexpr uint32_t id16 = umma_idesc_f16(kWgBM, BN) | (1u << 16);   // A in TMEM, B MN-major
+            constexpr uint32_t id16_cat = umma_idesc_f16(kWgBM, S::kCat ? 2 * BN : BN) | (1u << 16);
+            const uint64_t x_hi = umma_desc_mn_sw128_f16(st + S::kBOff, kWgBoxBytes);
+            const uint64_t x_lo = umma_desc_mn_sw128_f16(st + S::kBOff + (BN / 64) * kWgBoxBytes, kWgBoxBytes);
+            const uint32_t a_hi = tmem_base + (uint32_t)(S::kATmem + stage * 64);
+            const uint32_t a_lo = a_hi + 32u;
+#pragma unroll
+            for (int k = 0; k < kWgRows / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * (2048 >> 4));   // 16 pixels = two 8-row atoms of 1024 B
+              const uint32_t ka = (uint32_t)(k * 8);              // 16 fp16 of A = 8 TMEM columns
+              if constexpr (S::kCat) {
+                umma_f16_ts(d_tmem, a_hi + ka, x_hi + adv, id16_cat, first | (uint32_t)(k != 0));
+                umma_f16_ts(d_tmem, a_lo + ka, x_hi + adv, id16, 1);
+              } else {
+                umma_f16_ts(d_tmem, a_lo + ka, x_hi + adv, id16, first | (uint32_t)(k != 0));
+                umma_f16_ts(d_tmem, a_hi + ka, x_lo + adv, id16, 1);
+                umma_f16_ts(d_tmem, a_hi + ka, x_hi + adv, id16, 1);
+              }
+            }
+          } else if constexpr (TS) {
             constexpr uint32_t idesc_ts = umma_idesc_tf32(kWgBM, BN) | (1u << 16);   // A in TMEM, B MN-major
             constexpr uint32_t idesc_ts_cat = umma_idesc_tf32(kWgBM, S::kCat ? 2 * BN : BN) | (1u << 16);
             const uint32_t a_hi = tmem_base + (uint32_t)(S::kATmem + stage * 64);
@@ -229,7 +261,84 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
       for (int b = b0; b < b1; ++b) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * S::kStageBytes;
-        if constexpr (TS) {
+        if constexpr (F16) {
+          if (warp < 6) {
+            // warps 2-5: dY tile -> tensor memory, transposed and packed.  thread = output channel m (TMEM lane); column j
+            // of the stage holds pixels (2j, 2j+1) as an fp16 pair (lower K index in the low half), hi at +0, lo at +32.
+            const int q = warp & 3;
+            const uint8_t* box = st + q * kWgBoxBytes + (lane & 7) * 4;
+            const int c8 = lane >> 3;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(S::kATmem + stage * 64);
+            float sa, inv_unused;
+            f16_split_scale(__ldg(p.a_amax), sa, inv_unused);
+            tc_fence_after();
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int r0 = 2 * u, r1 = 2 * u + 1;
+              const float v0 = *reinterpret_cast<const float*>(box + r0 * 128 + ((c8 ^ (r0 & 3)) << 5)) * sa;
+              const float v1 = *reinterpret_cast<const float*>(box + r1 * 128 + ((c8 ^ (r1 & 3)) << 5)) * sa;
+              const __half2 h = __floats2half2_rn(v0, v1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+              hi[u] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[u] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            tmem_st16(t_lane, hi);
+            tmem_st16(t_lane + 32u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            // warps 6-9: X boxes (raw fp32, plain 128B swizzle) -> fp16 MN-major atoms, in place.  Work item = (box pair g,
+            // pixel row, half): lanes l and l+16 of a warp share a pixel row and own the two boxes of the pair; everybody
+            // reads its 128-byte line first, the four warps meet at a named barrier (a lo atom lands in a box another pair
+            // read from), then each lane writes its four 16-byte chunks of the hi atom (box area g) and of the lo atom
+            // (box area BN/64 + g) at chunk ^ (row % 8).
+            constexpr int kItems = (BN / 64) * 64;
+            constexpr int kIters = (kItems + 127) / 128;
+            const int tb = threadIdx.x - 6 * 32;
+            float sx, inv_unused;
+            f16_split_scale(__ldg(p.b_amax), sx, inv_unused);
+            uint8_t* xb = st + S::kBOff;
+            float4 v[kIters][8];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+              const int item = tb + i * 128;
+              if (item < kItems) {
+                const int g = item >> 6, row = ((item >> 5) & 1) * 16 + (item & 15), half = (item >> 4) & 1;
+                const uint8_t* src = xb + (2 * g + half) * kWgBoxBytes + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[i][c] = *reinterpret_cast<const float4*>(src + ((c ^ (row & 7)) << 4));
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+              const int item = tb + i * 128;
+              if (item < kItems) {
+                const int g = item >> 6, row = ((item >> 5) & 1) * 16 + (item & 15), half = (item >> 4) & 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float x[8] = {v[i][2 * j].x, v[i][2 * j].y, v[i][2 * j].z, v[i][2 * j].w,
+                                      v[i][2 * j + 1].x, v[i][2 * j + 1].y, v[i][2 * j + 1].z, v[i][2 * j + 1].w};
+                  uint32_t hw[4], lw[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float x0 = x[2 * e] * sx, x1 = x[2 * e + 1] * sx;
+                    const __half2 h = __floats2half2_rn(x0, x1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                    hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+                  }
+                  const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((half * 4 + j) ^ (row & 7)) << 4);
+                  *reinterpret_cast<uint4*>(xb + g * kWgBoxBytes + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                  *reinterpret_cast<uint4*>(xb + (BN / 64 + g) * kWgBoxBytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+              }
+            }
+          }
+        } else if constexpr (TS) {
           if (warp < 6) {
             // warps 2-5: dY tile -> tensor memory, transposed.  thread = output channel m (TMEM lane): box m / 32,
             // channel c = m % 32; pixel r of that box sits at r*128 + (((c >> 3) ^ (r & 3)) << 5) + (c & 7)*4
@@ -314,6 +423,12 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     const int64_t ktot = (int64_t)taps * p.Cin;
+    float inv_a = 1.f, inv_b = 1.f;   // F16: exact power-of-two rescale of the partial sums
+    if constexpr (F16) {
+      float s_unused;
+      f16_split_scale(__ldg(p.a_amax), s_unused, inv_a);
+      f16_split_scale(__ldg(p.b_amax), s_unused, inv_b);
+    }
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int mt, tap, ct, sp, b0, b1;
       decode(item, mt, tap, ct, sp, b0, b1);
@@ -342,6 +457,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
+        if constexpr (F16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_a * inv_b);
         }
         if (co < p.Cout) {
           if (c0 + 32 <= ncols && (p.Cin & 3) == 0) {
@@ -444,12 +563,13 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
   return 0;
 }
 
-template <int BN, bool TS>
+template <int BN, bool TS, bool F16 = false>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t st) {
   using S = WgSmem<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN, TS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotal);
     if (e != cudaSuccess) {
       set_error("wgrad_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -458,7 +578,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
   }
   const int64_t items = (int64_t)p.m_tiles * (p.taps_h * p.taps_w / p.tap_group) * p.n_ctiles * p.splits;
   const int grid = (int)(items < cached_sm_count() ? items : cached_sm_count());
-  wgrad_tf32x3_kernel<BN, TS><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
+  wgrad_tf32x3_kernel<BN, TS, F16><<<grid, kWgThreads, S::kTotal, st>>>(tdy, tx, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("wgrad_tf32x3 launch: %s", cudaGetErrorString(e));
@@ -481,8 +601,11 @@ int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int
   return (int64_t)pl.p.splits * Cout * KH * KW * Cin;
 }
 
-int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
-                              int stride, int pad, float* dW, int accumulate, float* ws, void* stream) {
+static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
+                      int stride, int pad, float* dW, int accumulate, float* ws, void* stream, const float* x_amax,
+                      const float* dy_amax) {
+  const bool f16 = x_amax != nullptr;
+  VITTA_CHECK_ARG(!f16 || dy_amax, VITTA_E_BADARG, "conv2d_wgrad_f16x3: both amax scalars are required");
   VITTA_CHECK_ARG(X && dY && dW && ws && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
                   "conv2d_wgrad: bad arguments");
   VITTA_CHECK_ARG(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad >= 0, VITTA_E_BADARG, "conv2d_wgrad: bad filter");
@@ -494,6 +617,8 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
   VITTA_CHECK_ARG(rc == 0, VITTA_E_BADARG, "conv2d_wgrad: empty output");
   WgradParams& p = pl.p;
   p.ws = ws;
+  p.a_amax = dy_amax; p.b_amax = x_amax;
+  if (f16 && pl.bn == 192 && p.tap_group != 3) return VITTA_E_BADARG;   // (cannot happen: 192 is the tap-group mode)
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   VITTA_CHECK_ARG(p.BW * stride <= 256 && p.BH * stride <= 256, VITTA_E_UNSUPPORTED, "conv2d_wgrad: box too large");
   CUtensorMap tdy, tx;
@@ -510,11 +635,15 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
     const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * 4 * W, (uint64_t)Cin * 4 * W * H};
     const uint32_t box[4] = {32, (uint32_t)(p.BW * stride), (uint32_t)(p.BH * stride), (uint32_t)p.BF};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-    rc = make_tensor_map_f32(&tx, X, 4, dims, str, box, es, true);
+    rc = make_tensor_map_f32(&tx, X, 4, dims, str, box, es, !f16);   // fp16 split: plain 128B swizzle (converted in place)
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_gemm_operand_form == 1)   // automatic = dY through tensor memory (12-15 % faster: profiles/r01_conv_shapes.md)
+  if (f16)
+    rc = (pl.bn == 192) ? launch_wgrad<192, true, true>(tdy, tx, p, st)
+                        : (pl.bn == 64) ? launch_wgrad<64, true, true>(tdy, tx, p, st)
+                                        : launch_wgrad<128, true, true>(tdy, tx, p, st);
+  else if (g_gemm_operand_form == 1)   // automatic = dY through tensor memory (12-15 % faster: profiles/r01_conv_shapes.md)
     rc = (pl.bn == 64) ? launch_wgrad<64, false>(tdy, tx, p, st) : launch_wgrad<128, false>(tdy, tx, p, st);
   else
     rc = (pl.bn == 192) ? launch_wgrad<192, true>(tdy, tx, p, st)
@@ -526,6 +655,18 @@ int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int
   wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
+                              int stride, int pad, float* dW, int accumulate, float* ws, void* stream) {
+  return wgrad_impl(X, dY, F, H, W, Cin, Cout, KH, KW, stride, pad, dW, accumulate, ws, stream, nullptr, nullptr);
+}
+
+int vitta_conv2d_wgrad_f16x3(const float* X, const float* x_amax, const float* dY, const float* dy_amax, int F, int H,
+                             int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* dW, int accumulate,
+                             float* ws, void* stream) {
+  VITTA_CHECK_ARG(x_amax && dy_amax, VITTA_E_BADARG, "conv2d_wgrad_f16x3: amax scalars are required");
+  return wgrad_impl(X, dY, F, H, W, Cin, Cout, KH, KW, stride, pad, dW, accumulate, ws, stream, x_amax, dy_amax);
 }
 
 }  // extern "C"

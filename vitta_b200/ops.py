@@ -726,8 +726,9 @@ def bump_weight_epoch():
 
 
 # Operand split of the dense contractions: "tf32x3" (default, hardware-validated) or "f16x3" (opt-in until validated on
-# hardware, DESIGN.md section 9: forward and data-gradient GEMMs / convolutions on kind::f16 with per-tensor amax scaling;
-# weight gradients stay on the tf32 kernel).  Also settable with VITTA_GEMM_PRECISION.
+# hardware, DESIGN.md section 9: forward, data-gradient and weight-gradient convolutions and the Swin forward / data-gradient
+# GEMMs on kind::f16 with per-tensor amax scaling; Swin Linear weight gradients stay on the tf32 kernel for now).
+# Also settable with VITTA_GEMM_PRECISION.
 _gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "tf32x3")
 
 
@@ -787,6 +788,29 @@ def conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad):
     return gw
 
 
+def conv2d_wgrad_f16x3(x, gy, cout, kh, kw, stride, pad, x_amax=None, gy_amax=None):
+    """conv2d_wgrad_tf32x3 on the fp16 split (opt-in)."""
+    _require_cuda(x, "conv2d_wgrad_f16x3")
+    if not (x.is_contiguous(memory_format=CL) and gy.is_contiguous(memory_format=CL)):
+        raise _lib.VittaError("conv2d_wgrad_f16x3: x and gy must be channels_last contiguous")
+    f, cin, h, w = x.shape
+    n = _lib.load().vitta_conv2d_wgrad_ws_floats(f, h, w, cin, cout, kh, kw, stride, pad)
+    if n <= 0:
+        raise _lib.VittaError("conv2d_wgrad_f16x3: bad geometry")
+    ws = _wgrad_ws.get(x.device)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(n, dtype=torch.float32, device=x.device)
+        _wgrad_ws[x.device] = ws
+    if x_amax is None:
+        x_amax = amax_f32(x)
+    if gy_amax is None:
+        gy_amax = amax_f32(gy)
+    gw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+    call("vitta_conv2d_wgrad_f16x3", ptr(x), ptr(x_amax), ptr(gy), ptr(gy_amax), f, h, w, cin, cout, kh, kw, stride, pad,
+         ptr(gw), 0, ptr(ws), stream_ptr())
+    return gw
+
+
 class Conv2dFn(torch.autograd.Function):
     """Bias-free 2-D convolution, channels-last, forward and data gradient on the tcgen05 3xTF32 kernel.
 
@@ -822,10 +846,11 @@ class Conv2dFn(torch.autograd.Function):
         gx = gw = None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         f16 = _gemm_precision == "f16x3" and (cout * kh * kw) % 8 == 0
+        gy_am = amax_f32(gy) if _gemm_precision == "f16x3" else None    # one pass, shared by dgrad and wgrad
         if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
             if f16:
                 whi, wlo, wam = weight_split_f16(w, 1)
-                gx = conv2d_f16x3(gy, whi, wlo, wam, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
+                gx = conv2d_f16x3(gy, whi, wlo, wam, cin, kh, kw, 1, kh - 1 - pad, x_amax=gy_am, residual=galias)
             else:
                 whi, wlo = weight_split(w, 1)
                 gx = conv2d_tf32x3(gy, whi, wlo, cin, kh, kw, 1, kh - 1 - pad, residual=galias)
@@ -836,7 +861,7 @@ class Conv2dFn(torch.autograd.Function):
             gx = torch.empty_like(x)             # channels_last like x
             if f16:
                 whi, wlo, wam = weight_split_f16(w, 1)
-                call("vitta_conv2d_dgrad_f16x3", ptr(gy), ptr(amax_f32(gy)), f, gy.shape[2], gy.shape[3], cout, ptr(whi),
+                call("vitta_conv2d_dgrad_f16x3", ptr(gy), ptr(gy_am), f, gy.shape[2], gy.shape[3], cout, ptr(whi),
                      ptr(wlo), ptr(wam), cin, kh, kw, stride, pad, h, wd, ptr(gx), stream_ptr())
             else:
                 whi, wlo = weight_split(w, 1)
@@ -844,7 +869,10 @@ class Conv2dFn(torch.autograd.Function):
                      kw, stride, pad, h, wd, ptr(gx), stream_ptr())
             need_x = False
         if need_w and cout % 4 == 0:
-            gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)
+            if gy_am is not None:
+                gw = conv2d_wgrad_f16x3(x, gy, cout, kh, kw, stride, pad, gy_amax=gy_am)
+            else:
+                gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)
             need_w = False
         if need_x or need_w:
             r = torch.ops.aten.convolution_backward(gy, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0],
