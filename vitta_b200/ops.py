@@ -726,9 +726,8 @@ def bump_weight_epoch():
 
 
 # Operand split of the dense contractions: "tf32x3" (default, hardware-validated) or "f16x3" (opt-in until validated on
-# hardware, DESIGN.md section 9: forward, data-gradient and weight-gradient convolutions and the Swin forward / data-gradient
-# GEMMs on kind::f16 with per-tensor amax scaling; Swin Linear weight gradients stay on the tf32 kernel for now).
-# Also settable with VITTA_GEMM_PRECISION.
+# hardware, DESIGN.md section 9: forward, data-gradient and weight-gradient convolutions / Linear layers on kind::f16 with
+# per-tensor amax scaling; the window-attention kernels keep the tf32 split).  Also settable with VITTA_GEMM_PRECISION.
 _gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "tf32x3")
 
 

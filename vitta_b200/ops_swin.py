@@ -66,6 +66,10 @@ def linear_wgrad(x, gy):
         raise _lib.VittaError("linear_wgrad: bad geometry")
     ws = _workspace("wgrad", nws, x.device, False)
     gw = torch.empty(n, k, dtype=torch.float32, device=x.device)
+    if ops.gemm_precision() == "f16x3" and x.is_contiguous() and gy.is_contiguous():
+        call("vitta_conv2d_wgrad_f16x3", ptr(x), ptr(ops.amax_f32(x)), ptr(gy), ptr(ops.amax_f32(gy)), f, 1, wdt, k, n, 1,
+             1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
+        return gw
     call("vitta_conv2d_wgrad_tf32x3", ptr(x), ptr(gy), f, 1, wdt, k, n, 1, 1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
     return gw
 
