@@ -15,5 +15,8 @@ timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32.m
 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16.md 2>&1; tail -5 gpurun_out/conv_shapes_f16.md
 VITTA_GEMM_CTA_PAIR=1 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_tf32_pair.md 2>&1; tail -5 gpurun_out/conv_shapes_tf32_pair.md
 VITTA_GEMM_CTA_PAIR=1 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_shapes.py --reps 4 > gpurun_out/conv_shapes_f16_pair.md 2>&1; tail -5 gpurun_out/conv_shapes_f16_pair.md
+# 4b. the step itself with the opt-in paths (only meaningful if the tests above passed)
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-precision f16x3 > gpurun_out/bench_f16.log 2> gpurun_out/bench_f16.err; echo "bench f16 rc=$?"; head -c 300 gpurun_out/bench_f16.log; echo
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-precision f16x3 --cta-pair > gpurun_out/bench_f16_pair.log 2> gpurun_out/bench_f16_pair.err; echo "bench f16+pair rc=$?"; head -c 300 gpurun_out/bench_f16_pair.log; echo
 # 5. the regular round (tests, bench, Swin tables)
 bash tools/gpu_round.sh
