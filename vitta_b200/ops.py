@@ -820,9 +820,11 @@ class Conv2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, pad, want_alias=False):
         cout, cin, kh, kw = w.shape
+        ctx.x_am = None
         if _gemm_precision == "f16x3" and (cin * kh * kw) % 8 == 0:
             whi, wlo, wam = weight_split_f16(w, 0)
-            y = conv2d_f16x3(x, whi, wlo, wam, cout, kh, kw, stride, pad)
+            ctx.x_am = amax_f32(x)          # reused by the weight gradient (same tensor)
+            y = conv2d_f16x3(x, whi, wlo, wam, cout, kh, kw, stride, pad, x_amax=ctx.x_am)
         else:
             whi, wlo = weight_split(w, 0)
             y = conv2d_tf32x3(x, whi, wlo, cout, kh, kw, stride, pad)
@@ -869,7 +871,7 @@ class Conv2dFn(torch.autograd.Function):
             need_x = False
         if need_w and cout % 4 == 0:
             if gy_am is not None:
-                gw = conv2d_wgrad_f16x3(x, gy, cout, kh, kw, stride, pad, gy_amax=gy_am)
+                gw = conv2d_wgrad_f16x3(x, gy, cout, kh, kw, stride, pad, x_amax=ctx.x_am, gy_amax=gy_am)
             else:
                 gw = conv2d_wgrad_tf32x3(x, gy, cout, kh, kw, stride, pad)
             need_w = False
