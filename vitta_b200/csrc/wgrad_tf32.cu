@@ -289,34 +289,36 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
             tmem_st_wait();
             tc_fence_before();
           } else {
-            // warps 6-9: X boxes (raw fp32, plain 128B swizzle) -> fp16 MN-major atoms, in place.  Work item = (box pair g,
-            // pixel row, half): lanes l and l+16 of a warp share a pixel row and own the two boxes of the pair; everybody
-            // reads its 128-byte line first, the four warps meet at a named barrier (a lo atom lands in a box another pair
-            // read from), then each lane writes its four 16-byte chunks of the hi atom (box area g) and of the lo atom
-            // (box area BN/64 + g) at chunk ^ (row % 8).
-            constexpr int kItems = (BN / 64) * 64;
-            constexpr int kIters = (kItems + 127) / 128;
-            const int tb = threadIdx.x - 6 * 32;
+            // warps 6-9: X boxes (raw fp32, plain 128B swizzle) -> fp16 MN-major atoms, in place.  A warp owns 8 pixel
+            // rows of EVERY box: lane = (pair slot, half, row): lanes 0-15 work on box pair 2i, lanes 16-31 on pair 2i+1;
+            // within 16 lanes, lane l and l+8 share a pixel row and own the two boxes of the pair.  All 128-byte lines of
+            // the warp's rows are read first, then __syncwarp, then every lane writes its four 16-byte chunks of the hi
+            // atom (box area g) and of the lo atom (box area BN/64 + g) at chunk ^ (row % 8).  Because a row of any box
+            // is only ever touched by one warp, no cross-warp barrier is needed (a named barrier here made the compiler
+            // drop warp-uniformity for the whole kernel: descriptors then travel through R2UR moves in the MMA warp).
+            constexpr int kPairs = BN / 64;
+            constexpr int kIters = (kPairs + 1) / 2;
+            const int row = (warp - 6) * 8 + (lane & 7);
+            const int half = (lane >> 3) & 1;
+            const uint32_t sw = (uint32_t)(row & 7);
             float sx, inv_unused;
             f16_split_scale(__ldg(p.b_amax), sx, inv_unused);
             uint8_t* xb = st + S::kBOff;
             float4 v[kIters][8];
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
-              const int item = tb + i * 128;
-              if (item < kItems) {
-                const int g = item >> 6, row = ((item >> 5) & 1) * 16 + (item & 15), half = (item >> 4) & 1;
+              const int g = 2 * i + (lane >> 4);
+              if (g < kPairs) {
                 const uint8_t* src = xb + (2 * g + half) * kWgBoxBytes + row * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[i][c] = *reinterpret_cast<const float4*>(src + ((c ^ (row & 7)) << 4));
+                for (int c = 0; c < 8; ++c) v[i][c] = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sw) << 4));
               }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
-              const int item = tb + i * 128;
-              if (item < kItems) {
-                const int g = item >> 6, row = ((item >> 5) & 1) * 16 + (item & 15), half = (item >> 4) & 1;
+              const int g = 2 * i + (lane >> 4);
+              if (g < kPairs) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float x[8] = {v[i][2 * j].x, v[i][2 * j].y, v[i][2 * j].z, v[i][2 * j].w,
@@ -331,9 +333,9 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
                     hw[e] = *reinterpret_cast<const uint32_t*>(&h);
                     lw[e] = *reinterpret_cast<const uint32_t*>(&l);
                   }
-                  const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((half * 4 + j) ^ (row & 7)) << 4);
+                  const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(half * 4 + j)) ^ sw) << 4);
                   *reinterpret_cast<uint4*>(xb + g * kWgBoxBytes + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                  *reinterpret_cast<uint4*>(xb + (BN / 64 + g) * kWgBoxBytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                  *reinterpret_cast<uint4*>(xb + (kPairs + g) * kWgBoxBytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
               }
             }
