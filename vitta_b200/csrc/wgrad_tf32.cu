@@ -50,21 +50,26 @@ struct WgradParams {
 // (3 x 64 channels), so one dY tile -- loaded, transposed and split once -- feeds three taps, and the 24 narrow MMAs per
 // pixel stage of three separate items become 12 MMAs of N = 192.  The accumulator is single-buffered there (192 columns +
 // 3 x 64 columns of A stages); an item runs for ~100 stages, so the unoverlapped epilogue is noise.
-template <int BN, bool TS>
+// F16 = true: the X tile is converted in place (hi atoms + lo atoms fill exactly the raw boxes), so a stage is the raw dY
+// landing zone + BN/32 X boxes -- which makes an N tile of 256 channels affordable (48 KB stages, 4 of them; accumulator
+// single-buffered like the tap-group mode).  At fp16 speed the 128x128 tile is bound by the L2 feed of its two fp32
+// operands (32 KB per 384 MMA cycles); 128x256 halves the dY bytes per flop.
+template <int BN, bool TS, bool F16 = false>
 struct WgSmem {
   static_assert(BN != 192 || TS, "the tap-group mode exists for the tensor-memory form only");
+  static_assert(BN != 256 || F16, "the 256-channel N tile exists for the fp16 split only");
   static constexpr int kGroup = (BN == 192) ? 3 : 1;
-  static constexpr int kStages = TS ? (BN == 192 ? 3 : 4) : 3;
+  static constexpr int kStages = TS ? ((BN == 192 && !F16) ? 3 : 4) : 3;
   static constexpr int kABytes = 4 * kWgBoxBytes;            // 16 KB raw/hi (SS: + same for lo)
   static constexpr int kBBytes = (BN / 32) * kWgBoxBytes;
   static constexpr int kBOff = TS ? kABytes : 2 * kABytes;
-  static constexpr int kStageBytes = kBOff + 2 * kBBytes;
+  static constexpr int kStageBytes = kBOff + (F16 ? 1 : 2) * kBBytes;
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
   // kCat (see GemmSmem in gemm_tf32.cu): a_hi x [b_hi ; b_lo] as one MMA of N = 2*BN into two column sets
-  static constexpr bool kCat = (BN == 192) ? false : (TS ? (BN == 64) : true);
+  static constexpr bool kCat = (BN >= 192) ? false : (TS ? (BN == 64) : true);
   static constexpr int kChains = kCat ? 2 : 1;
   static constexpr int kAccCols = kChains * BN;
-  static constexpr int kAccBufs = (BN == 192) ? 1 : 2;
+  static constexpr int kAccBufs = (BN >= 192) ? 1 : 2;
   static constexpr int kATmem = kAccBufs * kAccCols;
   static constexpr int kTmemNeed = TS ? (kAccBufs * kAccCols + kStages * 64) : kAccBufs * kAccCols;
   static constexpr int kTmemCols = (kTmemNeed <= 128) ? 128 : (kTmemNeed <= 256) ? 256 : 512;
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                     const WgradParams p) {
   static_assert(!F16 || (TS && BN % 64 == 0), "the fp16 split exists for the tensor-memory form, N tiles of 64 channels");
-  using S = WgSmem<BN, TS>;
+  using S = WgSmem<BN, TS, F16>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
@@ -532,7 +537,8 @@ static void flatten_pointwise(int& F, int& H, int& W, int KH, int KW, int stride
   }
 }
 
-static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, WgPlan* out) {
+static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, WgPlan* out,
+                      bool f16 = false) {
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   if (Ho <= 0 || Wo <= 0) return VITTA_E_BADARG;
   WgradParams& p = out->p;
@@ -545,6 +551,7 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
   }
   p.boxes_w = (Wo + p.BW - 1) / p.BW; p.boxes_h = (Ho + p.BH - 1) / p.BH; p.boxes_f = (F + p.BF - 1) / p.BF;
   out->bn = (Cin <= 64) ? 64 : 128;
+  if (f16 && Cin % 256 == 0) out->bn = 256;   // fp16 split: wider N tile (see WgSmem)
   p.tap_group = 1;
   if (Cin == 64 && (KH * KW) % 3 == 0 && g_gemm_operand_form != 1) {   // three taps per item (tensor-memory form only)
     out->bn = 192;
@@ -567,7 +574,7 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
 
 template <int BN, bool TS, bool F16 = false>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t st) {
-  using S = WgSmem<BN, TS>;
+  using S = WgSmem<BN, TS, F16>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN, TS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -600,7 +607,11 @@ int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int
   if (F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride < 1) return -1;
   flatten_pointwise(F, H, W, KH, KW, stride, pad);
   if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl)) return -1;
-  return (int64_t)pl.p.splits * Cout * KH * KW * Cin;
+  int splits = pl.p.splits;
+  // the fp16 kernel may pick a wider N tile and therefore more K splits: size the workspace for either plan
+  if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl, true)) return -1;
+  if (pl.p.splits > splits) splits = pl.p.splits;
+  return (int64_t)splits * Cout * KH * KW * Cin;
 }
 
 static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
@@ -615,7 +626,7 @@ static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int 
                   "conv2d_wgrad: channel counts must be multiples of 4 and tensors 16-byte aligned");
   flatten_pointwise(F, H, W, KH, KW, stride, pad);
   WgPlan pl;
-  int rc = wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl);
+  int rc = wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl, f16);
   VITTA_CHECK_ARG(rc == 0, VITTA_E_BADARG, "conv2d_wgrad: empty output");
   WgradParams& p = pl.p;
   p.ws = ws;
@@ -642,9 +653,10 @@ static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (f16)
-    rc = (pl.bn == 192) ? launch_wgrad<192, true, true>(tdy, tx, p, st)
-                        : (pl.bn == 64) ? launch_wgrad<64, true, true>(tdy, tx, p, st)
-                                        : launch_wgrad<128, true, true>(tdy, tx, p, st);
+    rc = (pl.bn == 256) ? launch_wgrad<256, true, true>(tdy, tx, p, st)
+         : (pl.bn == 192) ? launch_wgrad<192, true, true>(tdy, tx, p, st)
+         : (pl.bn == 64) ? launch_wgrad<64, true, true>(tdy, tx, p, st)
+                         : launch_wgrad<128, true, true>(tdy, tx, p, st);
   else if (g_gemm_operand_form == 1)   // automatic = dY through tensor memory (12-15 % faster: profiles/r01_conv_shapes.md)
     rc = (pl.bn == 64) ? launch_wgrad<64, false>(tdy, tx, p, st) : launch_wgrad<128, false>(tdy, tx, p, st);
   else
