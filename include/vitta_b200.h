@@ -168,6 +168,21 @@ int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, Vitt
 int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
                   void* stream);
 int vitta_tam_num_chunks(int64_t HW, int C);
+/* *_amax variants (opt-in f16x3 path): the same kernels, additionally *amax = max(*amax, max|tensor written|) for the
+ * tensors the next fp16-split GEMM / convolution consumes (out; gx and gres), through one integer atomic per warp --
+ * the producer touches every element anyway, so the separate vitta_amax_f32 pass over the operand disappears.
+ * The caller zero-initialises the scalars.  Default kernels are untouched (separate template instantiations). */
+int vitta_bn_act_fwd_amax(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                          float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                          int64_t frame_rows, int C, float* amax_out, void* stream);
+int vitta_bn_act_bwd_amax(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                          const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b,
+                          const float* mean_main, const float* gs_main, const float* coef_a2, const float* coef_b2,
+                          const float* mean_res, const float* gs_res, float* gx, float* gres, float* gw, float* gb,
+                          float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows, int C, float* amax_gx,
+                          float* amax_gres, void* stream);
+int vitta_tam_fwd_amax(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                       float* amax_out, void* stream);
 int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
                   int N, int T, int64_t HW, int C, void* stream);
 

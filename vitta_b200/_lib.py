@@ -54,6 +54,11 @@ _SIGNATURES = {
     "vitta_bn_act_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "vitta_tam_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "vitta_bn_act_fwd_amax": (C.c_int, [_P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, C.c_int64,
+                                        C.c_int64, C.c_int, _P, _P]),
+    "vitta_bn_act_bwd_amax": (C.c_int, [_P, _P, _P, VittaBN, _P, C.POINTER(VittaBN), C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
+    "vitta_tam_fwd_amax": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

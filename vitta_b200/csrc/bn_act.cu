@@ -71,14 +71,25 @@ __device__ __forceinline__ void write_part(float* part, int64_t e, int C, int co
   st4(o + 4, o1);
 }
 
+__device__ __forceinline__ float amax4(float m, float4 v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+// max over the warp, one integer atomic per warp (non-negative floats order like their bit patterns); all 32 lanes call it
+__device__ __forceinline__ void amax_commit(float m, float* slot) {
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(slot), w);
+}
+
 // RES: 0 none, 1 raw residual, 2 residual through its own BN
-template <int RES>
+// AMAX: also accumulate max|out| into *amax_out (the operand range the fp16-split GEMM that consumes `out` needs; the
+//       kernel touches every element anyway, so the extra HBM pass of vitta_amax_f32 disappears)
+template <int RES, bool AMAX = false>
 __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __restrict__ x, BNDev bn,
                                                              const float* __restrict__ res, BNDev bn2, int relu,
                                                              float* __restrict__ out, float* __restrict__ part_main,
                                                              float* __restrict__ part_res, float* __restrict__ pool_part,
                                                              int C, int lpr, int rs, int chunk_rows, int cpf,
-                                                             int64_t frame_rows) {
+                                                             int64_t frame_rows, float* __restrict__ amax_out = nullptr) {
   __shared__ float4 sm[kThreads];
   const int tid = threadIdx.x;
   const int lane = tid % lpr;
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
   const int nrows = (int)(rem < chunk_rows ? rem : chunk_rows);
 
   float4 s1 = f4zero(), s2 = f4zero(), r1 = f4zero(), r2 = f4zero(), pool = f4zero(), ky = f4zero(), kr = f4zero();
+  float am = 0.f;
   if (active) {
     const int c = col4 * 4;
     const Aff4 a = load_aff(bn, c);
@@ -121,9 +133,11 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
         y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
       }
       st4(out + off, y);
+      if constexpr (AMAX) am = amax4(am, y);
       pool.x += y.x; pool.y += y.y; pool.z += y.z; pool.w += y.w;
     }
   }
+  if constexpr (AMAX) amax_commit(am, amax_out);
   if (part_main) {
     float4 a = slot_reduce(s1, sm, tid, lpr, rs);
     float4 b = slot_reduce(s2, sm, tid, lpr, rs);
@@ -175,8 +189,11 @@ __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
 
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
-template <int RES>
-__global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
+// AMAX: max|gx| and max|gres| accumulate into *amax_gx / *amax_gres.  The body is shared; the two __global__ wrappers below
+// keep the default kernel's signature (and with it its code) exactly as it was.
+template <int RES, bool AMAX>
+__device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restrict__ amax_gx,
+                                                float* __restrict__ amax_gres) {
   __shared__ float4 sm[kThreads];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -189,6 +206,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
   const bool active = col4 * 4 < C;
   const int c = col4 * 4;
   float4 agw = f4zero(), agb = f4zero(), agw2 = f4zero(), agb2 = f4zero();
+  float amx = 0.f, amr = 0.f;
   if (active) {
     const Aff4 a = load_aff(p.bn, c);
     Aff4 a2;
@@ -236,21 +254,28 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
         float4 gy = f4fma(cb, f4sub(y, cm), ca);
         gy.x += g.x; gy.y += g.y; gy.z += g.z; gy.w += g.w;
         st4(p.gx + off, make_float4(gy.x * a.k.x, gy.y * a.k.y, gy.z * a.k.z, gy.w * a.k.w));
+        if constexpr (AMAX) amx = amax4(amx, make_float4(gy.x * a.k.x, gy.y * a.k.y, gy.z * a.k.z, gy.w * a.k.w));
         agb.x += gy.x; agb.y += gy.y; agb.z += gy.z; agb.w += gy.w;
         agw.x = fmaf(gy.x, (xv.x - a.rm.x) * a.istd.x, agw.x); agw.y = fmaf(gy.y, (xv.y - a.rm.y) * a.istd.y, agw.y);
         agw.z = fmaf(gy.z, (xv.z - a.rm.z) * a.istd.z, agw.z); agw.w = fmaf(gy.w, (xv.w - a.rm.w) * a.istd.w, agw.w);
         if (RES == 1) {
           st4(p.gres + off, g);
+          if constexpr (AMAX) amr = amax4(amr, g);
         } else if (RES == 2) {
           float4 gr = f4fma(cb2, f4sub(rr, cm2), ca2);
           gr.x += g.x; gr.y += g.y; gr.z += g.z; gr.w += g.w;
           st4(p.gres + off, make_float4(gr.x * a2.k.x, gr.y * a2.k.y, gr.z * a2.k.z, gr.w * a2.k.w));
+          if constexpr (AMAX) amr = amax4(amr, make_float4(gr.x * a2.k.x, gr.y * a2.k.y, gr.z * a2.k.z, gr.w * a2.k.w));
           agb2.x += gr.x; agb2.y += gr.y; agb2.z += gr.z; agb2.w += gr.w;
           agw2.x = fmaf(gr.x, (rx.x - a2.rm.x) * a2.istd.x, agw2.x); agw2.y = fmaf(gr.y, (rx.y - a2.rm.y) * a2.istd.y, agw2.y);
           agw2.z = fmaf(gr.z, (rx.z - a2.rm.z) * a2.istd.z, agw2.z); agw2.w = fmaf(gr.w, (rx.w - a2.rm.w) * a2.istd.w, agw2.w);
         }
       }
     }
+  }
+  if constexpr (AMAX) {
+    amax_commit(amx, amax_gx);
+    if (RES != 0) amax_commit(amr, amax_gres);
   }
   // per-CTA partial parameter gradients -> ws[bx][k][C], k in {gw, gb, gw2, gb2}
   const int nk = (RES == 2) ? 4 : 2;
@@ -286,6 +311,16 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
   if (tid == 0) tickets[by] = 0;
 }
 
+template <int RES, bool AMAX = false>
+__global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(BwdArgs p) {
+  bn_act_bwd_body<RES, false>(p, nullptr, nullptr);
+}
+template <int RES>
+__global__ void __launch_bounds__(kThreads) bn_act_bwd_amax_kernel(BwdArgs p, float* __restrict__ amax_gx,
+                                                                  float* __restrict__ amax_gres) {
+  bn_act_bwd_body<RES, true>(p, amax_gx, amax_gres);
+}
+
 // upper bound of the backward grid (per channel tile): sizes the workspace, fixed per shape
 static inline int bwd_grid_x(const ClGeom& g) {
   int64_t cap = (148 * 4 + g.ctiles - 1) / g.ctiles;
@@ -296,12 +331,16 @@ static inline int bwd_grid_x(const ClGeom& g) {
 
 // The backward is a grid-stride (persistent) kernel: launch exactly one wave of what actually fits per SM for the
 // variant at hand (80 / 94 / 127 registers -> 3 / 2 / 2 CTAs), otherwise the surplus CTAs form a second, mostly empty wave.
-template <int RES>
+template <int RES, bool AMAX = false>
 static int bwd_resident_ctas() {
   static int cached = 0;
   if (cached == 0) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act_bwd_kernel<RES>, kThreads, 0) != cudaSuccess ||
+    const cudaError_t e = AMAX ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act_bwd_amax_kernel<RES>,
+                                                                               kThreads, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act_bwd_kernel<RES>,
+                                                                               kThreads, 0);
+    if (e != cudaSuccess ||
         per_sm < 1)
       per_sm = 2;
     int dev = 0, sms = 148;
@@ -319,9 +358,9 @@ static BNDev to_dev(const VittaBN& b) { return BNDev{b.weight, b.bias, b.running
 
 extern "C" {
 
-int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
-                     float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
-                     int64_t frame_rows, int C, void* stream) {
+static int bn_act_fwd_impl(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                           float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                           int64_t frame_rows, int C, float* amax_out, void* stream) {
   VITTA_CHECK_ARG(x && out && bn.weight && bn.bias && bn.running_mean && bn.running_var, VITTA_E_BADARG,
                   "bn_act_fwd: null pointer");
   VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && frames > 0 && frame_rows > 0, VITTA_E_BADARG, "bn_act_fwd: bad shape");
@@ -334,7 +373,17 @@ int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN
   dim3 grid((unsigned)(g.n_chunks() * g.ctiles));
   cudaStream_t st = (cudaStream_t)stream;
   BNDev b1 = to_dev(bn), b2 = res_bn ? to_dev(*res_bn) : b1;
-  if (!res)
+  if (amax_out) {
+    if (!res)
+      bn_act_fwd_kernel<0, true><<<grid, kThreads, 0, st>>>(x, b1, nullptr, b2, relu, out, part_main, nullptr, pool_part,
+                                                           C, g.lpr, g.rs, g.chunk_rows, g.cpf, g.frame_rows, amax_out);
+    else if (!res_bn)
+      bn_act_fwd_kernel<1, true><<<grid, kThreads, 0, st>>>(x, b1, res, b2, relu, out, part_main, nullptr, pool_part, C,
+                                                           g.lpr, g.rs, g.chunk_rows, g.cpf, g.frame_rows, amax_out);
+    else
+      bn_act_fwd_kernel<2, true><<<grid, kThreads, 0, st>>>(x, b1, res, b2, relu, out, part_main, part_res, pool_part, C,
+                                                           g.lpr, g.rs, g.chunk_rows, g.cpf, g.frame_rows, amax_out);
+  } else if (!res)
     bn_act_fwd_kernel<0><<<grid, kThreads, 0, st>>>(x, b1, nullptr, b2, relu, out, part_main, nullptr, pool_part, C,
                                                    g.lpr, g.rs, g.chunk_rows, g.cpf, g.frame_rows);
   else if (!res_bn)
@@ -353,17 +402,33 @@ int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN
   return 0;
 }
 
+int vitta_bn_act_fwd(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                     float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                     int64_t frame_rows, int C, void* stream) {
+  return bn_act_fwd_impl(x, bn, res, res_bn, relu, out, part_main, part_res, pool_part, pool_out, frames, frame_rows, C,
+                         nullptr, stream);
+}
+
+int vitta_bn_act_fwd_amax(const float* x, VittaBN bn, const float* res, const VittaBN* res_bn, int relu, float* out,
+                          float* part_main, float* part_res, float* pool_part, float* pool_out, int64_t frames,
+                          int64_t frame_rows, int C, float* amax_out, void* stream) {
+  VITTA_CHECK_ARG(amax_out, VITTA_E_BADARG, "bn_act_fwd_amax: amax_out is required");
+  return bn_act_fwd_impl(x, bn, res, res_bn, relu, out, part_main, part_res, pool_part, pool_out, frames, frame_rows, C,
+                         amax_out, stream);
+}
+
 int64_t vitta_bn_act_bwd_ws_floats(int64_t frames, int64_t frame_rows, int C) {
   if (C <= 0 || C % 4 || frames <= 0 || frame_rows <= 0) return -1;
   ClGeom g = cl_geom(frames, frame_rows, C);
   return (int64_t)bwd_grid_x(g) * 4 * C + g.ctiles + 4;
 }
 
-int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
-                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* mean_main,
-                     const float* gs_main, const float* coef_a2, const float* coef_b2, const float* mean_res,
-                     const float* gs_res, float* gx, float* gres, float* gw, float* gb, float* gw2, float* gb2,
-                     float* ws, int64_t frames, int64_t frame_rows, int C, void* stream) {
+static int bn_act_bwd_impl(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                           const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b,
+                           const float* mean_main, const float* gs_main, const float* coef_a2, const float* coef_b2,
+                           const float* mean_res, const float* gs_res, float* gx, float* gres, float* gw, float* gb,
+                           float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows, int C, float* amax_gx,
+                           float* amax_gres, void* stream) {
   VITTA_CHECK_ARG(gout && x && gx && ws, VITTA_E_BADARG, "bn_act_bwd: null pointer");
   VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && frames > 0 && frame_rows > 0, VITTA_E_BADARG, "bn_act_bwd: bad shape");
   VITTA_CHECK_ARG(aligned16(gout) && aligned16(x) && aligned16(gx) && (!res || aligned16(res)) &&
@@ -386,13 +451,24 @@ int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, Vitt
   p.relu = relu; p.C = C; p.lpr = g.lpr; p.rs = g.rs; p.chunk_rows = g.chunk_rows; p.cpf = g.cpf;
   p.frame_rows = g.frame_rows; p.n_chunks = g.n_chunks(); p.inv_frame_rows = 1.f / (float)frame_rows;
   p.ticket_off = (int64_t)bwd_grid_x(g) * 4 * C;
-  const int resident = !res ? bwd_resident_ctas<0>() : !res_bn ? bwd_resident_ctas<1>() : bwd_resident_ctas<2>();
+  const bool am = amax_gx != nullptr;
+  VITTA_CHECK_ARG(!am || !res || amax_gres, VITTA_E_BADARG, "bn_act_bwd_amax: amax_gres is required with a residual");
+  const int resident = am ? (!res ? bwd_resident_ctas<0, true>() : !res_bn ? bwd_resident_ctas<1, true>()
+                                                                            : bwd_resident_ctas<2, true>())
+                          : (!res ? bwd_resident_ctas<0>() : !res_bn ? bwd_resident_ctas<1>() : bwd_resident_ctas<2>());
   int gx_ = resident / g.ctiles;
   if (gx_ < 1) gx_ = 1;
   if (gx_ > bwd_grid_x(g)) gx_ = bwd_grid_x(g);
   dim3 grid((unsigned)(gx_ * g.ctiles));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!res)
+  if (am) {
+    if (!res)
+      bn_act_bwd_amax_kernel<0><<<grid, kThreads, 0, st>>>(p, amax_gx, amax_gres);
+    else if (!res_bn)
+      bn_act_bwd_amax_kernel<1><<<grid, kThreads, 0, st>>>(p, amax_gx, amax_gres);
+    else
+      bn_act_bwd_amax_kernel<2><<<grid, kThreads, 0, st>>>(p, amax_gx, amax_gres);
+  } else if (!res)
     bn_act_bwd_kernel<0><<<grid, kThreads, 0, st>>>(p);
   else if (!res_bn)
     bn_act_bwd_kernel<1><<<grid, kThreads, 0, st>>>(p);
@@ -400,6 +476,27 @@ int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, Vitt
     bn_act_bwd_kernel<2><<<grid, kThreads, 0, st>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+int vitta_bn_act_bwd(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                     const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b, const float* mean_main,
+                     const float* gs_main, const float* coef_a2, const float* coef_b2, const float* mean_res,
+                     const float* gs_res, float* gx, float* gres, float* gw, float* gb, float* gw2, float* gb2,
+                     float* ws, int64_t frames, int64_t frame_rows, int C, void* stream) {
+  return bn_act_bwd_impl(gout, gpool, x, bn, res, res_bn, relu, coef_a, coef_b, mean_main, gs_main, coef_a2, coef_b2,
+                         mean_res, gs_res, gx, gres, gw, gb, gw2, gb2, ws, frames, frame_rows, C, nullptr, nullptr, stream);
+}
+
+int vitta_bn_act_bwd_amax(const float* gout, const float* gpool, const float* x, VittaBN bn, const float* res,
+                          const VittaBN* res_bn, int relu, const float* coef_a, const float* coef_b,
+                          const float* mean_main, const float* gs_main, const float* coef_a2, const float* coef_b2,
+                          const float* mean_res, const float* gs_res, float* gx, float* gres, float* gw, float* gb,
+                          float* gw2, float* gb2, float* ws, int64_t frames, int64_t frame_rows, int C, float* amax_gx,
+                          float* amax_gres, void* stream) {
+  VITTA_CHECK_ARG(amax_gx, VITTA_E_BADARG, "bn_act_bwd_amax: amax_gx is required");
+  return bn_act_bwd_impl(gout, gpool, x, bn, res, res_bn, relu, coef_a, coef_b, mean_main, gs_main, coef_a2, coef_b2,
+                         mean_res, gs_res, gx, gres, gw, gb, gw2, gb2, ws, frames, frame_rows, C, amax_gx, amax_gres,
+                         stream);
 }
 
 }  // extern "C"

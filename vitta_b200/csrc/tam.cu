@@ -11,9 +11,11 @@ __device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
 }
 
 // thread = one (n, p, 4 channels) column, marching through t with a 3-frame register window
+// AMAX: also accumulate max|out| into *amax_out (operand range for the fp16-split convolution that consumes `out`)
+template <bool AMAX = false>
 __global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restrict__ x, const float* __restrict__ kern,
                                                           const float* __restrict__ act, float* __restrict__ out, int N,
-                                                          int T, int64_t HW, int C4) {
+                                                          int T, int64_t HW, int C4, float* __restrict__ amax_out = nullptr) {
   const int64_t per_n = HW * C4;
   const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (idx >= (int64_t)N * per_n) return;
@@ -30,6 +32,7 @@ __global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restri
   const int64_t ts = per_n * 4;
   float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 cur = mul4(ldg4(ab), ld_stream4(xb));
+  float am = 0.f;
 #pragma unroll 4
   for (int t = 0; t < T; ++t) {
     float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -38,8 +41,14 @@ __global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restri
     o = fma4(k1, cur, o);
     o = fma4(k2, nxt, o);
     st4(ob + (int64_t)t * ts, o);
+    if constexpr (AMAX) am = fmaxf(fmaxf(am, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     prev = cur;
     cur = nxt;
+  }
+  if constexpr (AMAX) {   // threads past the end have returned: reduce over the lanes that are still here
+    const unsigned mask = __activemask();
+    const uint32_t w = __reduce_max_sync(mask, __float_as_uint(am));
+    if ((int)(threadIdx.x & 31) == __ffs(mask) - 1 && w) atomicMax(reinterpret_cast<unsigned int*>(amax_out), w);
   }
 }
 
@@ -115,8 +124,8 @@ using namespace vitta;
 
 extern "C" {
 
-int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
-                  void* stream) {
+static int tam_fwd_impl(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                        float* amax_out, void* stream) {
   VITTA_CHECK_ARG(x && kern && act && out, VITTA_E_BADARG, "tam_fwd: null pointer");
   VITTA_CHECK_ARG(N > 0 && T > 0 && HW > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_fwd: bad shape (C %% 4 != 0?)");
   VITTA_CHECK_ARG(aligned16(x) && aligned16(kern) && aligned16(act) && aligned16(out), VITTA_E_ALIGN,
@@ -124,9 +133,24 @@ int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* ou
   const int64_t total = (int64_t)N * HW * (C / 4);
   const int64_t blocks = (total + kThreads - 1) / kThreads;
   VITTA_CHECK_ARG(blocks < (1ll << 31), VITTA_E_UNSUPPORTED, "tam_fwd: grid too large");
-  tam_fwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, kern, act, out, N, T, HW, C / 4);
+  if (amax_out)
+    tam_fwd_kernel<true><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, kern, act, out, N, T, HW, C / 4,
+                                                                                 amax_out);
+  else
+    tam_fwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, kern, act, out, N, T, HW, C / 4);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+int vitta_tam_fwd(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                  void* stream) {
+  return tam_fwd_impl(x, kern, act, out, N, T, HW, C, nullptr, stream);
+}
+
+int vitta_tam_fwd_amax(const float* x, const float* kern, const float* act, float* out, int N, int T, int64_t HW, int C,
+                       float* amax_out, void* stream) {
+  VITTA_CHECK_ARG(amax_out, VITTA_E_BADARG, "tam_fwd_amax: amax_out is required");
+  return tam_fwd_impl(x, kern, act, out, N, T, HW, C, amax_out, stream);
 }
 
 int vitta_tam_num_chunks(int64_t HW, int C) {

@@ -22,6 +22,18 @@ def _require_cuda(t, what):
         raise _lib.VittaError("%s: fp32 only (got %s)" % (what, t.dtype))
 
 
+def _fused_amax():
+    """Producers emit the operand range of their outputs only on the opt-in fp16-split path."""
+    return _gemm_precision == "f16x3" and _FUSED_AMAX
+
+
+def operand_amax(t):
+    """max|t| as a device scalar: the value its producer kernel emitted (attached to the tensor object, so it can never
+    be stale), else a standalone vitta_amax_f32 pass."""
+    am = getattr(t, "_vitta_amax", None)
+    return am if am is not None else amax_f32(t)
+
+
 def as_rows_cl(x):
     """4-D logical (F, C, H, W) tensor in channels_last memory -> (frames, frame_rows, C) geometry."""
     f, c, h, w = x.shape
@@ -386,8 +398,15 @@ class BNActFn(torch.autograd.Function):
             pool_out = torch.empty(frames, Cc, dtype=torch.float32, device=dev)
         bn = _lib.make_bn(w, b, rm, rv, eps)
         bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
-        call("vitta_bn_act_fwd", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu), ptr(out),
-             ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, stream_ptr())
+        if _fused_amax():
+            # opt-in f16x3 path: the kernel also emits max|out| for the fp16-split convolution that consumes `out`
+            am = torch.zeros(1, dtype=torch.float32, device=dev)
+            call("vitta_bn_act_fwd_amax", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu),
+                 ptr(out), ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, ptr(am), stream_ptr())
+            out._vitta_amax = am
+        else:
+            call("vitta_bn_act_fwd", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu),
+                 ptr(out), ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, stream_ptr())
         ctx.save_for_backward(x, w, b, rm, rv, res, w2, b2, rm2, rv2)
         ctx.meta = (eps, eps2, bool(relu), arena, ly_main, ly_res, want_pool, kf, kr, Cc)
         tok_main = new_token(x) if ly_main is not None else None
@@ -421,9 +440,19 @@ class BNActFn(torch.autograd.Function):
         ws = _bwd_ws(kf, kr, Cc, dev)
         bn = _lib.make_bn(w, b, rm, rv, eps)
         bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
-        call("vitta_bn_act_bwd", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
-             C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx), ptr(gres),
-             ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, stream_ptr())
+        if _fused_amax():
+            amx = torch.zeros(1, dtype=torch.float32, device=dev)
+            amr = torch.zeros(1, dtype=torch.float32, device=dev) if has_res else None
+            call("vitta_bn_act_bwd_amax", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
+                 C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx),
+                 ptr(gres), ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, ptr(amx), ptr(amr), stream_ptr())
+            gx._vitta_amax = amx
+            if has_res:
+                gres._vitta_amax = amr
+        else:
+            call("vitta_bn_act_bwd", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
+                 C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx),
+                 ptr(gres), ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, stream_ptr())
         return (gx, gw, gb, None, None, None, gres, gw2, gb2, None, None, None, None, None, None, None, None, None)
 
 
@@ -457,7 +486,12 @@ class TamStencilFn(torch.autograd.Function):
         n = nt // T
         kern, act = kern.contiguous(), act.contiguous()
         out = torch.empty_like(x)
-        call("vitta_tam_fwd", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, stream_ptr())
+        if _fused_amax():
+            am = torch.zeros(1, dtype=torch.float32, device=x.device)
+            call("vitta_tam_fwd_amax", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, ptr(am), stream_ptr())
+            out._vitta_amax = am
+        else:
+            call("vitta_tam_fwd", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, stream_ptr())
         ctx.save_for_backward(x, kern, act)
         ctx.T = T
         return out
@@ -729,6 +763,7 @@ def bump_weight_epoch():
 # hardware, DESIGN.md section 9: forward, data-gradient and weight-gradient convolutions / Linear layers on kind::f16 with
 # per-tensor amax scaling; the window-attention kernels keep the tf32 split).  Also settable with VITTA_GEMM_PRECISION.
 _gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "tf32x3")
+_FUSED_AMAX = os.environ.get("VITTA_FUSED_AMAX", "1") == "1"    # f16x3 only: 0 = always use standalone amax passes
 
 
 def set_gemm_precision(name):
@@ -823,7 +858,7 @@ class Conv2dFn(torch.autograd.Function):
         ctx.x_am = None
         if _gemm_precision == "f16x3" and (cin * kh * kw) % 8 == 0:
             whi, wlo, wam = weight_split_f16(w, 0)
-            ctx.x_am = amax_f32(x)          # reused by the weight gradient (same tensor)
+            ctx.x_am = operand_amax(x)      # reused by the weight gradient (same tensor)
             y = conv2d_f16x3(x, whi, wlo, wam, cout, kh, kw, stride, pad, x_amax=ctx.x_am)
         else:
             whi, wlo = weight_split(w, 0)
@@ -847,7 +882,7 @@ class Conv2dFn(torch.autograd.Function):
         gx = gw = None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         f16 = _gemm_precision == "f16x3" and (cout * kh * kw) % 8 == 0
-        gy_am = amax_f32(gy) if _gemm_precision == "f16x3" else None    # one pass, shared by dgrad and wgrad
+        gy_am = operand_amax(gy) if _gemm_precision == "f16x3" else None    # shared by dgrad and wgrad
         if need_x and stride == 1 and kh == kw and x.shape[2:] == gy.shape[2:]:
             if f16:
                 whi, wlo, wam = weight_split_f16(w, 1)
