@@ -97,3 +97,36 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.VittaError):
         _lib.load()
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding in _lib._SIGNATURES has the arity and the argument classes (pointer / struct by value / int / int64 /
+    float) of its prototype in include/vitta_b200.h -- a drifted ctypes signature would corrupt the call silently."""
+    import ctypes as C
+    import re
+    from vitta_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vitta_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+
+    def klass_c(p):
+        p = p.strip()
+        if "*" in p:
+            return "ptr"
+        t = p.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "float": "f32", "VittaBN": "VittaBN"}.get(t, t)
+
+    def klass_py(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "i32", C.c_int32: "i32", C.c_int64: "i64", C.c_float: "f32"}.get(t, getattr(t, "__name__", str(t)))
+
+    for name, (res, args) in _lib._SIGNATURES.items():
+        m = re.search(r"^\s*(?:const\s+)?([\w]+\s*\*?)\s*" + name + r"\s*\(([^;{]*?)\)\s*;", hdr, re.S | re.M)
+        assert m, "no prototype for " + name
+        params = [p for p in m.group(2).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+        for i, (pc, pa) in enumerate(zip(params, args)):
+            assert klass_c(pc) == klass_py(pa), (name, i, pc.strip(), pa)
+        ret = m.group(1).replace(" ", "")
+        want = {"int": "i32", "int64_t": "i64", "char*": "ptr"}[ret]
+        assert klass_py(res) == want, (name, ret, res)
