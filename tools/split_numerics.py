@@ -144,20 +144,25 @@ class PatchedF:
 
     @staticmethod
     def linear(x, w, bias=None):
-        if SplitConv2d.scheme == "fp32" or x.shape[-1] < 64:
+        if SplitConv2d.scheme == "fp32" or x.shape[-1] < 32:
             return F.linear(x, w, bias)
         y = SplitLinear.apply(x, w)
         return y if bias is None else y + bias
 
 
-def run(scheme, sd, src, clip, steps, T, N, res, lr):
+def run(scheme, sd, src, clip, steps, T, N, res, lr, swin=None):
     SplitConv2d.scheme = scheme
     O.F = PatchedF()
     try:
-        st = O.TTAState(sd, "tanet", T, src[0], src[1], ["layer3", "layer4"], "l1_loss", True, 0.1, lr=lr)
+        if swin is None:
+            st = O.TTAState(sd, "tanet", T, src[0], src[1], ["layer3", "layer4"], "l1_loss", True, 0.1, lr=lr)
+        else:   # Video-Swin: the Linear layers (qkv / proj / fc1 / fc2 / reduction) go through the split; attention stays fp32
+            st = O.TTAState(sd, "swin", T, src[0], src[1], swin["chosen"], "l1_loss", True, 0.05, lr=lr,
+                            swin_cfg=dict(depths=tuple(swin["depths"]), heads=tuple(swin["heads"]),
+                                          window=tuple(swin["window"])), name_prefix="module.")
         out = []
         for s in range(steps):
-            r = st.adapt_step(clip[s], N, 1, False)
+            r = st.adapt_step(clip[s], N, 1 if swin is None else swin["M"], False)
             stats = {k: (t.mean_meter.avg.detach().clone(), t.var_meter.avg.detach().clone())
                      for k, t in st.taps.items() if t.kind != "bn1d"}
             out.append((float(r["loss_reg"]), r["logits"].clone(), stats))
@@ -174,25 +179,41 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--lr", type=float, default=1e-3)
     ap.add_argument("--schemes", default="tf32x3,bf16x3,bf16x4,bf16x6,fp16x3,tf32x1")
+    ap.add_argument("--arch", default="tanet", choices=["tanet", "swin"])
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    from vitta_b200.models.tanet_models.tanet import TSN
-    K, T, N, res = 11, a.frames, 1, a.res
-    model = TSN(K, T, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
-                non_local=False, partial_bn=False)
-    sd = synth.synth_state_dict(model.state_dict(), seed=1)
-    clean = synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=100, gauss_sigma=0.0, tag="clean"))
-    src = O.collect_source_stats(sd, "tanet", T, [clean.view(N, T, 3, res, res)])
-    clips = [synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=200 + s, tag="tta")).view(N, T, 3, res, res)
-             for s in range(a.steps)]
-    ref, wref = run("fp32", sd, src, clips, a.steps, T, N, res, a.lr)
+    swin = None
+    if a.arch == "tanet":
+        from vitta_b200.models.tanet_models.tanet import TSN
+        K, T, N, res = 11, a.frames, 1, a.res
+        model = TSN(K, T, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
+                    non_local=False, partial_bn=False)
+        sd = synth.synth_state_dict(model.state_dict(), seed=1)
+        clean = synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=100, gauss_sigma=0.0, tag="clean"))
+        src = O.collect_source_stats(sd, "tanet", T, [clean.view(N, T, 3, res, res)])
+        clips = [synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=200 + s, tag="tta")).view(N, T, 3, res, res)
+                 for s in range(a.steps)]
+        title = f"TANet-R50 {N}x{T}x{res}x{res}"
+    else:
+        import cases
+        swin = dict(cases.SWIN_CASES["swin_tiny_t32_r56_stats_l1"])
+        K, T, N, res = swin["K"], swin["T"], swin["N"], swin["res"]
+        swin["M"] = 1
+        sd = synth.synth_state_dict(cases.swin_state_template(K, swin["embed_dim"], swin["depths"], swin["heads"],
+                                                              swin["window"]), seed=1)
+        cfg = dict(depths=tuple(swin["depths"]), heads=tuple(swin["heads"]), window=tuple(swin["window"]))
+        clean = synth.swin_loader_tensor(synth.synth_video(N, 1, T, res, seed=100, gauss_sigma=0.0, tag="clean"))
+        src = O.collect_source_stats(sd, "swin", T, [clean], cfg)
+        clips = [synth.swin_loader_tensor(synth.synth_video(N, 1, T, res, seed=200 + s, tag="tta")) for s in range(a.steps)]
+        title = f"Video-Swin (embed {swin['embed_dim']}, depths {swin['depths']}) {N}x{T}x{res}x{res}"
+    ref, wref = run("fp32", sd, src, clips, a.steps, T, N, res, a.lr, swin)
     w0 = {k: v for k, v in sd.items() if k in wref}
-    print(f"TANet-R50 {N}x{T}x{res}x{res}, {a.steps} adaptation steps, lr {a.lr}; deviation from the fp32 oracle")
+    print(f"{title}, {a.steps} adaptation steps, lr {a.lr}; deviation from the fp32 oracle")
     print("| scheme | loss_reg rel | logits max rel (vs max|logit|) | EMA mean (max abs / layer scale) | EMA var max rel "
           "| weight-delta rel (l2, all tensors) |")
     print("|---|---|---|---|---|---|")
     for sch in a.schemes.split(","):
-        got, wg = run(sch, sd, src, clips, a.steps, T, N, res, a.lr)
+        got, wg = run(sch, sd, src, clips, a.steps, T, N, res, a.lr, swin)
         e_loss = max(abs(g[0] - r[0]) / abs(r[0]) for g, r in zip(got, ref))
         e_log = max(float((g[1] - r[1]).abs().max() / r[1].abs().max()) for g, r in zip(got, ref))
         e_mu = e_var = 0.0
