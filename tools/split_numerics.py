@@ -126,6 +126,33 @@ class SplitLinear(torch.autograd.Function):
         return dx, dw
 
 
+class SplitMatmul(torch.autograd.Function):
+    """a @ b for the attention products (q k^T, p v) with every operand -- gradients included -- split."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return contract(lambda x, y: torch.matmul(x, y), a, b, SplitConv2d.scheme)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        sch = SplitConv2d.scheme
+        ga = contract(lambda x, y: torch.matmul(x, y.transpose(-2, -1)), g, b, sch)
+        gb = contract(lambda x, y: torch.matmul(x.transpose(-2, -1), y), a, g, sch)
+        return ga, gb
+
+
+_ATTENTION = False       # --attention: also run the 4-D batched matmuls of window attention through the split
+_orig_matmul = torch.Tensor.__matmul__
+
+
+def _patched_matmul(self, other):
+    if _ATTENTION and SplitConv2d.scheme != "fp32" and self.dim() == 4 and other.dim() == 4:
+        return SplitMatmul.apply(self, other)
+    return _orig_matmul(self, other)
+
+
 class PatchedF:
     """Stand-in for torch.nn.functional inside the oracle: dense conv2d / linear go through the split emulation;
     the 3-channel stem, grouped convs and everything else stay plain fp32 (they are not on the tensor-core kernels)."""
@@ -153,6 +180,7 @@ class PatchedF:
 def run(scheme, sd, src, clip, steps, T, N, res, lr, swin=None):
     SplitConv2d.scheme = scheme
     O.F = PatchedF()
+    torch.Tensor.__matmul__ = _patched_matmul
     try:
         if swin is None:
             st = O.TTAState(sd, "tanet", T, src[0], src[1], ["layer3", "layer4"], "l1_loss", True, 0.1, lr=lr)
@@ -170,6 +198,7 @@ def run(scheme, sd, src, clip, steps, T, N, res, lr, swin=None):
         return out, w
     finally:
         O.F = F
+        torch.Tensor.__matmul__ = _orig_matmul
 
 
 def main():
@@ -180,7 +209,10 @@ def main():
     ap.add_argument("--lr", type=float, default=1e-3)
     ap.add_argument("--schemes", default="tf32x3,bf16x3,bf16x4,bf16x6,fp16x3,tf32x1")
     ap.add_argument("--arch", default="tanet", choices=["tanet", "swin"])
+    ap.add_argument("--attention", action="store_true", help="swin: split the q k^T and p v products (fwd + bwd) too")
     a = ap.parse_args()
+    global _ATTENTION
+    _ATTENTION = a.attention
     torch.set_num_threads(os.cpu_count())
     swin = None
     if a.arch == "tanet":
