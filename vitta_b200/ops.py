@@ -27,11 +27,22 @@ def _fused_amax():
     return _gemm_precision == "f16x3" and _FUSED_AMAX
 
 
+def _attach_amax(t, am):
+    """Remember max|t| on the tensor OBJECT together with its version counter: an attribute cannot outlive the tensor (no
+    stale pointer keys), and an in-place update of the tensor invalidates it."""
+    t._vitta_amax = (am, t._version)
+
+
 def operand_amax(t):
-    """max|t| as a device scalar: the value its producer kernel emitted (attached to the tensor object, so it can never
-    be stale), else a standalone vitta_amax_f32 pass."""
-    am = getattr(t, "_vitta_amax", None)
-    return am if am is not None else amax_f32(t)
+    """max|t| as a device scalar: the value its producer kernel emitted or an earlier call computed (attached to the
+    tensor object), else a standalone vitta_amax_f32 pass whose result is attached for the next consumer (a conv input is
+    also the operand of its weight gradient)."""
+    ent = getattr(t, "_vitta_amax", None)
+    if ent is not None and ent[1] == t._version:
+        return ent[0]
+    am = amax_f32(t)
+    _attach_amax(t, am)
+    return am
 
 
 def as_rows_cl(x):
@@ -403,7 +414,7 @@ class BNActFn(torch.autograd.Function):
             am = torch.zeros(1, dtype=torch.float32, device=dev)
             call("vitta_bn_act_fwd_amax", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu),
                  ptr(out), ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, ptr(am), stream_ptr())
-            out._vitta_amax = am
+            _attach_amax(out, am)
         else:
             call("vitta_bn_act_fwd", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu),
                  ptr(out), ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, stream_ptr())
@@ -446,9 +457,9 @@ class BNActFn(torch.autograd.Function):
             call("vitta_bn_act_bwd_amax", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
                  C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx),
                  ptr(gres), ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, ptr(amx), ptr(amr), stream_ptr())
-            gx._vitta_amax = amx
+            _attach_amax(gx, amx)
             if has_res:
-                gres._vitta_amax = amr
+                _attach_amax(gres, amr)
         else:
             call("vitta_bn_act_bwd", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
                  C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx),
@@ -489,7 +500,7 @@ class TamStencilFn(torch.autograd.Function):
         if _fused_amax():
             am = torch.zeros(1, dtype=torch.float32, device=x.device)
             call("vitta_tam_fwd_amax", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, ptr(am), stream_ptr())
-            out._vitta_amax = am
+            _attach_amax(out, am)
         else:
             call("vitta_tam_fwd", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, stream_ptr())
         ctx.save_for_backward(x, kern, act)

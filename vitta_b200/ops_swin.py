@@ -46,7 +46,7 @@ def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=No
     if ops.gemm_precision() == "f16x3" and k % 8 == 0 and a.is_contiguous():
         # opt-in fp16 operand split; the amax of the activation operand is a separate pass for now
         hi, lo, wam = ops.weight_split_f16(w, mode)
-        call("vitta_gemm_f16x3_ex", ptr(a), a.stride(0), ptr(ops.amax_f32(a)), ptr(hi), ptr(lo), ptr(wam), k, ptr(out),
+        call("vitta_gemm_f16x3_ex", ptr(a), a.stride(0), ptr(ops.operand_amax(a)), ptr(hi), ptr(lo), ptr(wam), k, ptr(out),
              out.stride(0), m, n, k, ptr(bias), ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale),
              int(rows_per_group), 0, stream_ptr())
         return out
@@ -67,7 +67,7 @@ def linear_wgrad(x, gy):
     ws = _workspace("wgrad", nws, x.device, False)
     gw = torch.empty(n, k, dtype=torch.float32, device=x.device)
     if ops.gemm_precision() == "f16x3" and x.is_contiguous() and gy.is_contiguous():
-        call("vitta_conv2d_wgrad_f16x3", ptr(x), ptr(ops.amax_f32(x)), ptr(gy), ptr(ops.amax_f32(gy)), f, 1, wdt, k, n, 1,
+        call("vitta_conv2d_wgrad_f16x3", ptr(x), ptr(ops.operand_amax(x)), ptr(gy), ptr(ops.operand_amax(gy)), f, 1, wdt, k, n, 1,
              1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
         return gw
     call("vitta_conv2d_wgrad_tf32x3", ptr(x), ptr(gy), f, 1, wdt, k, n, 1, 1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
