@@ -65,6 +65,16 @@ SWIN_CASES = {
                                        momentum_mvg=0.05, lambda_consis=0.05, sample_views=False),
 }
 
+# option rows at model level for Video-Swin; kept apart from SWIN_CASES so that the default GPU suite
+# (which iterates SWIN_CASES) only contains cases that have run on hardware
+SWIN_OPTION_CASES = {
+    # --update_only_bn_affine on Swin: everything frozen except the LayerNorm affine parameters, Adam (basics.py:552-557)
+    "swin_tiny_t16_r112_consis_l1_lnaffine": dict(K=101, T=16, N=1, M=2, res=112, embed_dim=64, depths=[2, 2], heads=[2, 4],
+                                                  window=(8, 7, 7), reg_type="l1_loss", consis=True, steps=2, lr=1e-3,
+                                                  chosen=["module.backbone.layers.1", "module.backbone.norm"],
+                                                  momentum_mvg=0.05, lambda_consis=0.05, bn_affine=True),
+}
+
 
 class _ListDataset(torch.utils.data.Dataset):
     def __init__(self, x, y):
@@ -473,7 +483,7 @@ def main(argv):
     for name, cfg in TANET_CASES.items():
         if not want or name in want:
             run_model_case(name, cfg, "tanet")
-    for name, cfg in SWIN_CASES.items():
+    for name, cfg in list(SWIN_CASES.items()) + list(SWIN_OPTION_CASES.items()):
         if not want or name in want:
             run_model_case(name, cfg, "videoswintransformer")
 
