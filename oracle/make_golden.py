@@ -73,6 +73,12 @@ SWIN_OPTION_CASES = {
                                                   window=(8, 7, 7), reg_type="l1_loss", consis=True, steps=2, lr=1e-3,
                                                   chosen=["module.backbone.layers.1", "module.backbone.norm"],
                                                   momentum_mvg=0.05, lambda_consis=0.05, bn_affine=True),
+    # MSE alignment against running MEANS of the statistics (moving_avg=False, AverageMeterTensor), one view, no consistency
+    "swin_tiny_t32_r56_stats_mse_avg": dict(K=101, T=32, N=2, M=1, res=56, embed_dim=32, depths=[2, 2, 2], heads=[1, 2, 4],
+                                            window=(8, 7, 7), reg_type="mse_loss", consis=False, steps=3, lr=1e-3,
+                                            chosen=["module.backbone.layers.1", "module.backbone.layers.2",
+                                                    "module.backbone.norm"],
+                                            momentum_mvg=0.05, lambda_consis=0.05, sample_views=False, moving_avg=False),
 }
 
 

@@ -286,7 +286,8 @@ def test_swin_tta_vs_reference_golden(cuda_device, name):
                            "tests/test_oracle_golden.py); set VITTA_TEST_UNVERIFIED=1 to run them")
 @pytest.mark.parametrize("name", list(cases.SWIN_OPTION_CASES))
 def test_swin_option_modes_vs_reference_golden(cuda_device, name):
-    """--update_only_bn_affine on Video-Swin (Adam over the LayerNorm affine parameters, everything else frozen)."""
+    """--update_only_bn_affine on Video-Swin (Adam over the LayerNorm affine parameters, everything else frozen); MSE
+    alignment with AverageMeterTensor statistics (moving_avg=False)."""
     _run_swin_case(cuda_device, name, cases.SWIN_OPTION_CASES[name])
 
 
@@ -324,7 +325,7 @@ def _run_swin_case(cuda_device, name, cfg):
         cases.assert_close(ov[i], src_v[i], 2e-4, 2e-5 * float(np.abs(src_v[i]).max()) + 1e-6, "src_var/%d" % i)
 
     args = default_args(n_augmented_views=cfg["M"], if_pred_consistency=cfg["consis"], reg_type=cfg["reg_type"],
-                        lr=cfg["lr"], moving_avg=True, momentum_mvg=cfg["momentum_mvg"],
+                        lr=cfg["lr"], moving_avg=cfg.get("moving_avg", True), momentum_mvg=cfg["momentum_mvg"],
                         lambda_pred_consis=cfg["lambda_consis"], chosen_blocks=cfg["chosen"],
                         if_sample_tta_aug_views=cfg.get("sample_views", True),
                         update_only_bn_affine=cfg.get("bn_affine", False), **common)
