@@ -49,6 +49,9 @@ TANET_CASES = {
     # included) against that layer's running statistics, EMA from zeros (running_manner)
     "tanet_t8_r64_bns_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                 lr=1e-3, moving_avg=True, stat_reg="BNS"),
+    # --before_norm: statistics (source and target) of the norm layers' INPUT instead of their output
+    "tanet_t8_r64_stats_l1_before_norm": dict(K=101, T=8, N=2, M=1, res=64, reg_type="l1_loss", consis=False, steps=2,
+                                              lr=1e-3, moving_avg=True, before_norm=True),
     "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                      lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }
@@ -139,6 +142,7 @@ def _base_args(ref, cfg, arch):
     args.lr = cfg["lr"]
     args.update_only_bn_affine = cfg.get("bn_affine", False)
     args.stat_reg = cfg.get("stat_reg", "mean_var")
+    args.before_norm = cfg.get("before_norm", False)
     args.if_tta_standard = cfg.get("mode", "tta_online")
     args.n_gradient_steps = cfg.get("gsteps", 1)
     args.momentum_mvg = cfg.get("momentum_mvg", 0.1)
@@ -201,7 +205,7 @@ def run_model_case(name, cfg, arch):
     basics.get_dataset_videoswin = lambda a, split=None, dataset_type=None: clean_ds
     a2 = copy.copy(args)
     a2.stat_type = "spatiotemp"
-    a2.before_norm = False
+    a2.before_norm = cfg.get("before_norm", False)
     basics.compute_statistics(model, args=a2, log_time="x")
     src_mean = saved["list_spatiotemp_mean_x.npy"]
     src_var = saved["list_spatiotemp_var_x.npy"]

@@ -473,7 +473,7 @@ class TTAState:
     def __init__(self, sd, arch, clip_len, src_means, src_vars, chosen_blocks, reg_type="l1_loss",
                  moving_avg=True, momentum_mvg=0.1, lr=5e-5, momentum=0.9, weight_decay=5e-4,
                  swin_cfg=None, name_prefix="", update_only_bn_affine=False, stat_reg="mean_var",
-                 running_manner=True, momentum_bns=0.1):
+                 running_manner=True, momentum_bns=0.1, before_norm=False):
         self.arch, self.clip_len = arch, clip_len
         self.swin_cfg = swin_cfg or {}
         self.sd = {}
@@ -517,7 +517,7 @@ class TTAState:
                 if any(b in full for b in chosen_blocks):
                     self.taps[name] = AlignTap(kind, clip_len, None if idx is None else src_means[idx],
                                                None if idx is None else src_vars[idx], reg_type, moving_avg,
-                                               momentum_mvg)
+                                               momentum_mvg, before_norm)
         else:
             names = swin_norm_layers(self.swin_cfg.get("depths", (2, 2, 18, 2)))[1:]
             assert len(names) == len(src_means)
@@ -525,7 +525,7 @@ class TTAState:
                 full = name_prefix + name
                 if any(b in full for b in chosen_blocks):
                     self.taps[name] = AlignTap("ln", clip_len, src_means[i], src_vars[i], reg_type, moving_avg,
-                                               momentum_mvg)
+                                               momentum_mvg, before_norm)
 
     def forward(self, inp, taps, dropout_p=0.0, drop_path_rate=0.0, dp_gen=None):
         if self.arch == "tanet":
@@ -568,7 +568,7 @@ class TTAState:
         return swin_forward(self.sd, inp, taps=None, **self.swin_cfg)[0]
 
 
-def collect_source_stats(sd, arch, clip_len, batches, swin_cfg=None):
+def collect_source_stats(sd, arch, clip_len, batches, swin_cfg=None, before_norm=False):
     """compute_statistics, corpus/basics.py:220-307: model.eval(), ComputeNormStatsHook on every
     BN2d/BN3d (TANet) or LN[1:] (Swin); the per-batch mean and *per-batch biased variance* are averaged
     with AverageMeter(n=batch) (:298-304) -- i.e. NOT a global variance."""
@@ -577,7 +577,7 @@ def collect_source_stats(sd, arch, clip_len, batches, swin_cfg=None):
         names = [(n, k) for n, k in tanet_norm_layers() if k != "bn1d"]
     else:
         names = [(n, "ln") for n in swin_norm_layers(swin_cfg.get("depths", (2, 2, 18, 2)))[1:]]
-    taps = {n: StatTap(k, clip_len) for n, k in names}
+    taps = {n: StatTap(k, clip_len, "spatiotemp", before_norm) for n, k in names}
     sm = [0.0] * len(names)
     sv = [0.0] * len(names)
     cnt = 0

@@ -27,6 +27,9 @@ TANET_CASES = {
     # included) against that layer's running statistics, EMA from zeros (running_manner)
     "tanet_t8_r64_bns_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                 lr=1e-3, moving_avg=True, stat_reg="BNS"),
+    # --before_norm: statistics (source and target) of the norm layers' INPUT instead of their output
+    "tanet_t8_r64_stats_l1_before_norm": dict(K=101, T=8, N=2, M=1, res=64, reg_type="l1_loss", consis=False, steps=2,
+                                              lr=1e-3, moving_avg=True, before_norm=True),
     "tanet_t8_r64_standard_l1": dict(K=101, T=8, N=2, M=2, res=64, reg_type="l1_loss", consis=True, steps=2,
                                      lr=1e-3, moving_avg=True, mode="tta_standard", momentum_mvg=1.0, gsteps=2),
 }

@@ -34,7 +34,7 @@ def _run_case(name, dev):
                         num_classes=cfg["K"], input_size=cfg["res"], moving_avg=cfg["moving_avg"],
                         update_only_bn_affine=cfg.get("bn_affine", False), momentum_mvg=cfg.get("momentum_mvg", 0.1),
                         if_tta_standard=cfg.get("mode", "tta_online"), n_gradient_steps=cfg.get("gsteps", 1),
-                        stat_reg=cfg.get("stat_reg", "mean_var"))
+                        stat_reg=cfg.get("stat_reg", "mean_var"), before_norm=cfg.get("before_norm", False))
     bns = cfg.get("stat_reg") == "BNS"
     # the source statistics: our compute_statistics must reproduce the reference's (fused stats kernels, eval fwd)
     from vitta_b200.corpus.basics import compute_statistics
@@ -50,7 +50,8 @@ def _run_case(name, dev):
         def __getitem__(self, i):
             return self.x[i], 0
     a2 = default_args(arch='tanet', clip_length=cfg["T"], batch_size=cfg["N"], num_classes=cfg["K"],
-                      input_size=cfg["res"], stat_type='spatiotemp', result_dir=None)
+                      input_size=cfg["res"], stat_type='spatiotemp', result_dir=None,
+                      before_norm=cfg.get("before_norm", False))
     a2.dataset_factory = lambda a, split, dataset_type: DS(torch.cat(clean, 0))
     om, ov = compute_statistics(model, a2)
     assert len(om) == len(src_m) == 53
@@ -113,10 +114,11 @@ def test_tanet_tta_vs_reference_golden(cuda_device, name):
                     reason="golden cases added after round 1's GPU budget was spent (oracle-pinned on CPU in "
                            "tests/test_oracle_golden.py); set VITTA_TEST_UNVERIFIED=1 to run them")
 @pytest.mark.parametrize("name", ["tanet_t8_r64_stats_kld_avg", "tanet_t8_r64_consis_l1_bnaffine",
-                                  "tanet_t8_r64_standard_l1", "tanet_t8_r64_bns_l1"])
+                                  "tanet_t8_r64_standard_l1", "tanet_t8_r64_bns_l1", "tanet_t8_r64_stats_l1_before_norm"])
 def test_tanet_option_modes_vs_reference_golden(cuda_device, name):
     """SURVEY 8(f) rank 4 at model level: KLD + AverageMeterTensor statistics; --update_only_bn_affine (Adam);
-    tta_standard mode (per-batch re-initialisation, momentum_mvg = 1, two gradient steps per batch); --stat_reg BNS."""
+    tta_standard mode (per-batch re-initialisation, momentum_mvg = 1, two gradient steps per batch); --stat_reg BNS;
+    --before_norm (statistics of the norm inputs, through the generic forward-hook path)."""
     _run_case(name, cuda_device)
 
 
