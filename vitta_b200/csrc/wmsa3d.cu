@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast from lane 0: the value is the same in every lane, but only a shuffle tells the compiler so -- without it
+  // everything derived from it travels through R2UR.BROADCAST + ELECT in front of every lane-predicated tcgen05.mma
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp >= 4 && warp < 8) {
     // =========================== loaders ===========================
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     for (int item = item0; item < item1; ++item) {
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = chunk_ctr & (kFwdVStages - 1);
+          const int st = __shfl_sync(0xffffffffu, chunk_ctr, 0) & (kFwdVStages - 1);   // uniform registers for the descriptors
           mbar_wait(&bar[B_P_READY], chunk_ctr & 1);
           mbar_wait(&bar[B_V_READY0 + st], (chunk_ctr / kFwdVStages) & 1);
           if (c == 0) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
@@ -780,7 +782,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast from lane 0: the value is the same in every lane, but only a shuffle tells the compiler so -- without it
+  // everything derived from it travels through R2UR.BROADCAST + ELECT in front of every lane-predicated tcgen05.mma
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp >= 8 && warp < 12) {
     // =========================== loaders ===========================
@@ -959,7 +963,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
     // Four independent issue streams (each MMA is only 128 x 32 x 8, so the serial issue chain of ONE thread would be
     // the bottleneck): warp 12: S / S^T, warp 13: dP / dP^T, warp 14: ACC1 (dQ | dK), warp 15: ACC2 (dV, MODE 1 only).
     // They touch disjoint accumulators; ordering against the other roles goes through the mbarriers.
-    const int which = warp & 1;
+    const int which = __shfl_sync(0xffffffffu, warp & 1, 0);   // warp-uniform by construction; the shuffle makes it provable
     const bool is_score = warp < 14;
     const uint32_t pe = (lane == 0) ? 1u : 0u;
     const uint32_t sbase = smem_u32(smem);
@@ -971,8 +975,12 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
           mbar_wait(&bar[C_ROWS_READY], tile_ctr & 1);
           for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-            const int st = chunk_ctr & (kB2Stages - 1);
-            const int sb = chunk_ctr & 1;
+            // the stage / buffer indices feed the descriptors of lane-predicated MMAs: take them from a lane-0 broadcast
+            // of the (already uniform) counter so that they live in uniform registers (profiles/r01_gemm_issue.md: the
+            // R2UR.BROADCAST + ELECT sequence costs ~3x the issue time of a uniform-register MMA)
+            const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);
+            const int st = ccu & (kB2Stages - 1);
+            const int sb = ccu & 1;
             mbar_wait(&bar[C_COL_READY0 + st], (chunk_ctr / kB2Stages) & 1);
             mbar_wait(&bar[C_SC_FREE0 + sb], ((chunk_ctr >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -999,7 +1007,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       for (int item = item0; item < item1; ++item) {
         for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
           for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-            const int st = chunk_ctr & (kB2Stages - 1);
+            const int st = __shfl_sync(0xffffffffu, chunk_ctr, 0) & (kB2Stages - 1);   // uniform (see the score issuers)
             mbar_wait(&bar[C_E_READY], chunk_ctr & 1);
             if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
             tc_fence_after();
