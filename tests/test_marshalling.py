@@ -1,0 +1,88 @@
+"""CPU: argument marshalling of the Python operators into the C ABI, without a GPU.
+
+With the device check patched out, every wrapper is driven with host tensors of realistic shapes: ctypes converts the
+arguments (a wrong arity or class raises ``ctypes.ArgumentError`` / ``TypeError`` right there), the C entry point validates
+them and then fails at the first CUDA call because there is no device -- which surfaces as ``VittaError``.  So "raises
+VittaError and nothing else" means the wrapper built a call the library accepts.  This covers the opt-in f16x3 operators,
+which have not run on hardware yet, and the default ones as a regression net.  Nothing is computed here."""
+import pytest
+import torch
+import torch.nn as nn
+
+CL = torch.channels_last
+
+
+@pytest.fixture
+def ops_nogpu(monkeypatch):
+    if torch.cuda.is_available():
+        pytest.skip("marshalling-only test: meant for the GPU-less container")
+    from vitta_b200 import _lib, ops
+    _lib.load()
+    monkeypatch.setattr(ops, "_require_cuda", lambda t, what: None)
+    # torch.cuda.current_stream() needs a device: hand the library the null stream instead
+    import ctypes
+    monkeypatch.setattr(ops, "stream_ptr", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: ctypes.c_void_p(0))
+    return ops
+
+
+def _expect_device_error(fn):
+    from vitta_b200._lib import VittaError
+    with pytest.raises(VittaError):
+        fn()
+
+
+def test_default_gemm_conv_wrappers_marshal(ops_nogpu):
+    ops = ops_nogpu
+    w = torch.randn(128, 64, 3, 3)
+    x = torch.randn(2, 64, 14, 14).contiguous(memory_format=CL)
+    gy = torch.randn(2, 128, 14, 14).contiguous(memory_format=CL)
+    hi, lo = torch.empty(128 * 9 * 64), torch.empty(128 * 9 * 64)
+    _expect_device_error(lambda: ops.split_tf32(w))
+    _expect_device_error(lambda: ops.conv2d_tf32x3(x, hi, lo, 128, 3, 3, 1, 1))
+    _expect_device_error(lambda: ops.gemm_tf32x3(torch.randn(256, 64), hi, lo, 128))
+    _expect_device_error(lambda: ops.conv2d_wgrad_tf32x3(x, gy, 128, 3, 3, 1, 1))
+
+
+def test_f16x3_wrappers_marshal(ops_nogpu):
+    ops = ops_nogpu
+    x = torch.randn(2, 64, 14, 14).contiguous(memory_format=CL)
+    gy = torch.randn(2, 128, 14, 14).contiguous(memory_format=CL)
+    w = torch.randn(128, 64, 3, 3)
+    am = torch.ones(1)
+    hi16 = torch.empty(128 * 9 * 64, dtype=torch.float16)
+    lo16 = torch.empty_like(hi16)
+    _expect_device_error(lambda: ops.amax_f32(x))
+    _expect_device_error(lambda: ops.split_f16(w))
+    _expect_device_error(lambda: ops.gemm_f16x3(torch.randn(256, 576), hi16, lo16, am, 128, a_amax=am))
+    _expect_device_error(lambda: ops.conv2d_f16x3(x, hi16, lo16, am, 128, 3, 3, 1, 1, x_amax=am))
+    _expect_device_error(lambda: ops.conv2d_dgrad_f16x3(gy, hi16, lo16, am, (2, 64, 28, 28), 3, 3, 2, 1, gy_amax=am))
+    _expect_device_error(lambda: ops.conv2d_wgrad_f16x3(x, gy, 128, 3, 3, 1, 1, x_amax=am, gy_amax=am))
+
+
+def test_producers_with_fused_ranges_marshal(ops_nogpu, monkeypatch):
+    ops = ops_nogpu
+    monkeypatch.setattr(ops, "_gemm_precision", "f16x3")
+    bn = nn.BatchNorm2d(64).eval()
+    x = torch.randn(8, 64, 7, 7).contiguous(memory_format=CL)
+    _expect_device_error(lambda: ops.bn_act(x, bn, True))                      # vitta_bn_act_fwd_amax
+    _expect_device_error(lambda: ops.bn_act(x, bn, True, res=x.clone(memory_format=CL), res_bn=bn))
+    kern, act = torch.rand(2, 3, 64), torch.rand(2, 4, 64)
+    _expect_device_error(lambda: ops.TamStencilFn.apply(x, kern, act, 4))       # vitta_tam_fwd_amax
+    monkeypatch.setattr(ops, "_gemm_precision", "tf32x3")
+    _expect_device_error(lambda: ops.bn_act(x, bn, True))                      # default entry point
+    _expect_device_error(lambda: ops.TamStencilFn.apply(x, kern, act, 4))
+
+
+def test_swin_gemm_wrappers_marshal(ops_nogpu, monkeypatch):
+    from vitta_b200 import ops_swin
+    import ctypes
+    ops = ops_nogpu
+    monkeypatch.setattr(ops_swin, "stream_ptr", lambda: ctypes.c_void_p(0))
+    a, w = torch.randn(392, 96), torch.randn(288, 96)
+    for prec in ("tf32x3", "f16x3"):
+        monkeypatch.setattr(ops, "_gemm_precision", prec)
+        ops.bump_weight_epoch()
+        _expect_device_error(lambda: ops_swin.gemm(a, w, 0, bias=torch.randn(288)))
+        _expect_device_error(lambda: ops_swin.gemm(torch.randn(392, 288), w, 1))
+        _expect_device_error(lambda: ops_swin.linear_wgrad(a, torch.randn(392, 288)))
