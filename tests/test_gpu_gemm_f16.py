@@ -1,7 +1,8 @@
 """GPU, opt-in (VITTA_TEST_F16X3=1): the fp16-split (kind::f16) variant of the tcgen05 GEMM / implicit-GEMM convolution.
 
-Round-1 status: the kernels are compiled and exported but have not run on hardware yet (the round's GPU budget was spent
-before they were written), so these tests are skipped unless asked for; the adaptation step does not use the path.
+Round-1 status: the GEMM / amax / split tests (test_amax_and_split, test_gemm_f16x3_vs_float64: 73 cases) passed on the
+first hardware run (profiles/r01_late_checks.md); the conv / dgrad / wgrad, CTA-pair and fused-range tests have not run
+yet (the round's GPU budget was spent), so the file stays opt-in; the adaptation step does not use the path.
 Same float64 references and the same error bound as tests/test_gpu_gemm.py: the split keeps ~22 mantissa bits per operand
 (hi = fp16(x*s), lo = fp16(x*s - hi)), i.e. |err| <= 2e-6 * sum_k |a||b|, also for operands far from unit scale
 (gradient-sized, 1e-9) because the scale is a per-tensor power of two taken from amax."""

@@ -4,7 +4,7 @@ With the device check patched out, every wrapper is driven with host tensors of 
 arguments (a wrong arity or class raises ``ctypes.ArgumentError`` / ``TypeError`` right there), the C entry point validates
 them and then fails at the first CUDA call because there is no device -- which surfaces as ``VittaError``.  So "raises
 VittaError and nothing else" means the wrapper built a call the library accepts.  This covers the opt-in f16x3 operators,
-which have not run on hardware yet, and the default ones as a regression net.  Nothing is computed here."""
+most of which have not run on hardware yet, and the default ones as a regression net.  Nothing is computed here."""
 import pytest
 import torch
 import torch.nn as nn
