@@ -18,5 +18,9 @@ VITTA_GEMM_CTA_PAIR=1 VITTA_GEMM_PRECISION=f16x3 timeout 600 python tools/conv_s
 # 4b. the step itself with the opt-in paths (only meaningful if the tests above passed)
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-precision f16x3 > gpurun_out/bench_f16.log 2> gpurun_out/bench_f16.err; echo "bench f16 rc=$?"; head -c 300 gpurun_out/bench_f16.log; echo
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-precision f16x3 --cta-pair > gpurun_out/bench_f16_pair.log 2> gpurun_out/bench_f16_pair.err; echo "bench f16+pair rc=$?"; head -c 300 gpurun_out/bench_f16_pair.log; echo
+# 4c. W-MSA backward: what the row warps wait on (round 1's last measurement rejected the issue-bound hypothesis,
+#     profiles/r01_late_checks.md) -- full capture with source-level warp-state samples of the attention kernels alone
+timeout 120 python tools/one_wmsa.py > gpurun_out/one_wmsa.log 2>&1; cat gpurun_out/one_wmsa.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"wmsa3d_fwd|wmsa3d_bwd2" --launch-skip 6 -c 3 -o gpurun_out/prof_wmsa python tools/one_wmsa.py > gpurun_out/ncu_wmsa.log 2>&1; echo "ncu wmsa rc=$?"
 # 5. the regular round (tests, bench, Swin tables)
 bash tools/gpu_round.sh
