@@ -396,6 +396,30 @@ int vitta_gather_normalize_u8(const uint8_t* frames, int F, int H, int W, const 
                               int crop_x, int out_h, int out_w, const float* mean3_host, const float* std3_host, int layout,
                               int T, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-view random multi-scale crop + bilinear resize + normalisation.
+ *   replaces: SubgroupWise_MultiScaleCrop_TANet.crop_scale_subgroup -- img.crop(box).resize((S, S), Image.BILINEAR) per
+ *             frame of a temporal view (models/tanet_models/transforms.py:312-323; selected by corpus/basics.py:1238-1245)
+ *             -> Stack -> ToTorchFormatTensor (/255) -> GroupNormalize (transforms.py:627-690).
+ *   The resize is Pillow's 8-bit two-pass fixed-point resampler (Pillow 8.4.0, requirements.txt:37, libImaging/Resample.c):
+ *   results are bit-exact with PIL before the float normalisation.
+ *
+ * vitta_resample_ksize / vitta_resample_coeffs_u8 are HOST-ONLY (no CUDA call): Pillow's precompute_coeffs +
+ *   normalize_coeffs_8bpc for one axis.  bounds_host: [out_size][2] = (first source index + in_offset, count);
+ *   kk_host: [out_size][slots] 22-bit fixed-point weights, zero padded; slots >= vitta_resample_ksize(in, out).
+ * vitta_gather_crop_resize_normalize_u8: frames (F, H, W, 3) uint8 device; idx (n_idx = n_views * T) int32 device;
+ *   boxes_host: n_views x (crop_w, crop_h, offset_w, offset_h) HOST ints, the tuple _sample_crop_size returns
+ *   (validated against the frame); hbounds / hk: device tables [n_views][out_w][2] / [n_views][out_w][slots] built with
+ *   in_offset = offset_w, vbounds / vk likewise for the rows; mean / std / layout / T / out as vitta_gather_normalize_u8.
+ * ---------------------------------------------------------------------------------------------- */
+int vitta_resample_ksize(int in_size, int out_size);
+int vitta_resample_coeffs_u8(int in_size, int out_size, int in_offset, int slots, int32_t* bounds_host, int32_t* kk_host);
+int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int F, int H, int W, const int32_t* idx, int n_idx,
+                                          const int32_t* boxes_host, int n_views, const int32_t* hbounds, const int32_t* hk,
+                                          const int32_t* vbounds, const int32_t* vk, int slots, int out_h, int out_w,
+                                          const float* mean3_host, const float* std3_host, int layout, int T, float* out,
+                                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -484,12 +484,49 @@ def run_views_case():
     print("wrote views", len(out), "index vectors")
 
 
+def run_crops_case():
+    """Per-view random multi-scale crops of the reference's own transform (models/tanet_models/transforms.py:277-384):
+    (a) crop boxes of ``_sample_crop_size`` for seeded ``random`` streams over a grid of frame / input sizes,
+    (b) the whole transform (``crop`` + ``resize(BILINEAR)`` through the installed Pillow) on seeded uint8 frames."""
+    import importlib
+    import random
+
+    from PIL import Image
+    ref_harness.load_reference()
+    tr = importlib.import_module("models.tanet_models.transforms")
+    out = {}
+    for iw, ih, inp in ((320, 240, 224), (340, 256, 224), (455, 256, 224), (171, 128, 112), (224, 224, 224),
+                        (256, 256, 224), (64, 48, 32), (398, 224, 224)):
+        op = tr.SubgroupWise_MultiScaleCrop_TANet(input_size=inp, n_temp_clips=2, clip_len=4)
+        random.seed(1000 + iw)
+        out["boxes/%d/%d/%d/%d" % (iw, ih, inp, 1000 + iw)] = np.asarray(
+            [op._sample_crop_size((iw, ih)) for _ in range(64)], np.int64)
+    rng = np.random.Generator(np.random.PCG64(11))
+    for name, (ih, iw, inp, views, t, seed) in {"a": (48, 64, 32, 2, 3, 5), "b": (60, 44, 32, 3, 2, 6),
+                                                "c": (33, 80, 24, 2, 2, 7)}.items():
+        frames = rng.integers(0, 256, (views * t, ih, iw, 3), dtype=np.uint8)
+        op = tr.SubgroupWise_MultiScaleCrop_TANet(input_size=inp, n_temp_clips=views, clip_len=t)
+        random.seed(seed)
+        imgs, _ = op(([Image.fromarray(f) for f in frames], 0))
+        random.seed(seed)
+        boxes = [op._sample_crop_size((iw, ih)) for _ in range(views)]      # the same draws, recorded
+        out["xf/%s/frames" % name] = frames
+        out["xf/%s/meta" % name] = np.asarray([inp, views, t, seed], np.int64)
+        out["xf/%s/boxes" % name] = np.asarray(boxes, np.int64)
+        out["xf/%s/out" % name] = np.stack([np.asarray(im) for im in imgs])
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "crops.npz"), **out)
+    print("wrote crops", len(out), "arrays")
+
+
 def main(argv):
     want = set(argv)
     if not want or "units" in want:
         run_unit_case()
     if not want or "views" in want:
         run_views_case()
+    if not want or "crops" in want:
+        run_crops_case()
     for name, cfg in TANET_CASES.items():
         if not want or name in want:
             run_model_case(name, cfg, "tanet")

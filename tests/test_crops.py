@@ -1,0 +1,157 @@
+"""Per-view random multi-scale crop + bilinear resize (reference:
+models/tanet_models/transforms.py:277-384, Pillow 8.4.0 Resample.c for the resize arithmetic).
+
+CPU: the crop-box sampler and the oracle's Pillow restatement against vectors recorded from the unmodified reference
+transform (tests/golden/crops.npz, oracle/make_golden.py::run_crops_case) and against the installed Pillow; the library's
+host-side coefficient tables against the oracle's.  GPU: the fused gather + crop + resize + normalise kernel against the
+oracle.  Everything up to the float normalisation is integer work: bit exact."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+GOLDEN = os.path.join(cases.GOLDEN_DIR, "crops.npz")
+
+
+def test_crop_boxes_match_reference_sampler():
+    from oracle import pil_resample as R
+    from vitta_b200.corpus.views import sample_multiscale_crop
+    g = np.load(GOLDEN)
+    keys = [k for k in g.files if k.startswith("boxes/")]
+    assert len(keys) == 8
+    for key in keys:
+        _, iw, ih, inp, seed = key.split("/")
+        want = g[key]
+        r1, r2 = random.Random(int(seed)), random.Random(int(seed))
+        got = np.asarray([sample_multiscale_crop(int(iw), int(ih), int(inp), r1) for _ in range(len(want))])
+        ora = np.asarray([R.sample_crop(int(iw), int(ih), int(inp), r2) for _ in range(len(want))])
+        assert (got == want).all(), key
+        assert (ora == want).all(), key
+        assert (got[:, 2] + got[:, 0] <= int(iw)).all() and (got[:, 3] + got[:, 1] <= int(ih)).all()
+
+
+def test_global_random_stream_is_the_default():
+    """Like the reference, the sampler draws from the ``random`` module unless told otherwise."""
+    from vitta_b200.corpus.views import sample_view_crops
+    random.seed(21)
+    a = sample_view_crops(320, 240, 224, 3)
+    b = sample_view_crops(320, 240, 224, 3, random.Random(21))
+    assert a == b and len(a) == 3
+
+
+def test_oracle_resize_matches_reference_transform_golden():
+    from oracle import pil_resample as R
+    g = np.load(GOLDEN)
+    for name in ("a", "b", "c"):
+        inp, views, t, _ = (int(v) for v in g["xf/%s/meta" % name])
+        frames, boxes, want = g["xf/%s/frames" % name], g["xf/%s/boxes" % name], g["xf/%s/out" % name]
+        got = R.crop_resize_views(frames, np.arange(views * t), t, [tuple(int(x) for x in b) for b in boxes], inp)
+        assert got.dtype == np.uint8 and got.shape == want.shape
+        assert (got == want).all(), name
+
+
+def test_oracle_resize_matches_installed_pillow():
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import pil_resample as R
+    rng = np.random.Generator(np.random.PCG64(3))
+    for h, w, oh, ow in [(240, 320, 224, 224), (180, 180, 224, 224), (158, 210, 224, 224), (256, 340, 224, 224),
+                         (37, 53, 16, 16), (20, 20, 64, 48), (224, 180, 224, 224), (300, 224, 224, 224), (9, 7, 23, 31),
+                         (1, 1, 4, 4), (64, 64, 1, 1)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        assert (R.resize_bilinear_u8(img, ow, oh) == want).all(), (h, w, oh, ow)
+    flat = np.full((30, 40, 3), 255, np.uint8)            # saturation: weights sum to one, no overflow past 255
+    assert (R.resize_bilinear_u8(flat, 17, 53) == 255).all()
+
+
+@pytest.mark.parametrize("offset", [0, 7])
+def test_library_coefficient_tables_match_oracle(offset):
+    from oracle import pil_resample as R
+    from vitta_b200.corpus.views import resample_tables
+    for i, o in [(240, 224), (180, 224), (158, 224), (210, 224), (224, 224), (256, 224), (512, 112), (7, 31), (1000, 33),
+                 (3, 3), (224, 112), (1, 5), (5, 1), (31, 32), (33, 32)]:
+        b, k = resample_tables(i, o, offset)
+        bw, kw = R.resample_coeffs(i, o)
+        assert k.shape[1] == R.resample_ksize(i, o)
+        assert (b[:, 0] == bw[:, 0] + offset).all() and (b[:, 1] == bw[:, 1]).all(), (i, o)
+        assert (k == kw).all(), (i, o)
+        b2, k2 = resample_tables(i, o, offset, slots=k.shape[1] + 2)     # padded slots stay zero
+        assert (b2 == b).all() and (k2[:, :k.shape[1]] == k).all() and (k2[:, k.shape[1]:] == 0).all()
+        assert (b[:, 0] - offset >= 0).all() and (b[:, 0] - offset + b[:, 1] <= i).all()
+
+
+def test_coefficient_tables_bad_arguments_are_loud():
+    from vitta_b200 import _lib
+    from vitta_b200.corpus.views import resample_tables
+    with pytest.raises(_lib.VittaError):
+        resample_tables(0, 5)
+    with pytest.raises(_lib.VittaError):
+        resample_tables(10, 5, slots=2)          # fewer slots than vitta_resample_ksize(10, 5) = 5
+    with pytest.raises(_lib.VittaError):
+        resample_tables(10, 5, in_offset=-1)
+
+
+def test_crop_resize_entry_validates_before_touching_the_device():
+    """No GPU here: a well-formed call gets as far as the launch (and fails there), a bad box is refused before that."""
+    if torch.cuda.is_available():
+        pytest.skip("marshalling-only test: meant for the GPU-less container")
+    from vitta_b200 import _lib
+    from vitta_b200.corpus.views import crop_resize_tables
+    f, h, w, t, v, s = 4, 48, 64, 2, 2, 32
+    frames = torch.zeros(f, h, w, 3, dtype=torch.uint8)
+    idx = torch.zeros(v * t, dtype=torch.int32)
+    out = torch.empty(v * t * 3, s, s)
+    m3, s3 = (C.c_float * 3)(0.4, 0.4, 0.4), (C.c_float * 3)(0.2, 0.2, 0.2)
+
+    def go(boxes):
+        hb, hk, vb, vk, slots = crop_resize_tables(boxes, s, s)
+        tabs = [torch.from_numpy(x) for x in (hb, hk, vb, vk)]
+        bx = (C.c_int32 * (4 * v))(*[int(x) for b in boxes for x in b])
+        _lib.call("vitta_gather_crop_resize_normalize_u8", _lib.ptr(frames), f, h, w, _lib.ptr(idx), v * t, bx, v,
+                  _lib.ptr(tabs[0]), _lib.ptr(tabs[1]), _lib.ptr(tabs[2]), _lib.ptr(tabs[3]), slots, s, s, m3, s3, 0, t,
+                  _lib.ptr(out), C.c_void_p(0))
+
+    with pytest.raises(_lib.VittaError) as e:
+        go([(48, 42, 16, 6), (36, 36, 0, 0)])
+    assert "outside the frame" not in str(e.value)
+    with pytest.raises(_lib.VittaError, match="outside the frame"):
+        go([(48, 42, 17, 6), (36, 36, 0, 0)])        # 17 + 48 > 64
+
+
+def test_views_to_device_has_no_cpu_path():
+    from vitta_b200 import _lib
+    from vitta_b200.corpus.views import views_to_device
+    with pytest.raises(_lib.VittaError):
+        views_to_device(torch.zeros(4, 48, 64, 3, dtype=torch.uint8), [0, 1], 2, boxes=[(32, 32, 0, 0)], out_size=32)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
+                    reason="kernel written after round 1's GPU budget was spent (oracle and host tables are pinned on the "
+                           "CPU above); set VITTA_TEST_UNVERIFIED=1 to run")
+@pytest.mark.parametrize("arch", ["tanet", "videoswintransformer"])
+def test_views_to_device_crop_resize_vs_oracle(cuda_device, arch):
+    from oracle import pil_resample as R
+    from vitta_b200 import synth
+    from vitta_b200.corpus.views import sample_tta_view_indices, sample_view_crops, views_to_device
+    f, h, w, t, views, s = 37, 120, 160, 8, 2, 112
+    rng = np.random.Generator(np.random.PCG64(5))
+    frames = rng.integers(0, 256, (f, h, w, 3), dtype=np.uint8)
+    idx = sample_tta_view_indices(f, t, views)
+    for seed in (0, 1, 2, 3):
+        boxes = sample_view_crops(w, h, s, views, random.Random(seed))
+        out = views_to_device(torch.from_numpy(frames).to(cuda_device), idx, t, arch, boxes=boxes, out_size=s)
+        u8 = R.crop_resize_views(frames, idx, t, boxes, s)                            # (V*T, s, s, 3) uint8, PIL-exact
+        x = torch.from_numpy(u8).float() / 255.0
+        x = ((x - torch.tensor(synth.INPUT_MEAN)) / torch.tensor(synth.INPUT_STD)).permute(0, 3, 1, 2)
+        if arch == "tanet":
+            want = x.reshape(views * t * 3, s, s)
+        else:
+            want = x.reshape(views, t, 3, s, s).permute(0, 2, 1, 3, 4)
+        # one uint8 step is 1/(255*0.225) = 1.7e-2 after normalisation: 1e-5 means every pixel has the exact PIL value
+        torch.testing.assert_close(out.cpu(), want.contiguous(), rtol=1e-6, atol=1e-5)

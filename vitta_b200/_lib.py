@@ -103,6 +103,12 @@ _SIGNATURES = {
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P]),
     "vitta_gather_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, _P, _P]),
+    "vitta_resample_ksize": (C.c_int, [C.c_int, C.c_int]),
+    "vitta_resample_coeffs_u8": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vitta_gather_crop_resize_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int32),
+                                                        C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                                        C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, _P,
+                                                        _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }

@@ -7,8 +7,14 @@ uses, utils/opts.py ``--tta_view_sample_style_list``) including the final ``+1``
 ``views_to_device`` turns decoded uint8 frames into the loader tensors of ``corpus.basics`` with one kernel
 (``vitta_gather_normalize_u8``) instead of the PIL / numpy pipeline.  Decoding and resizing stay outside (decord /
 PIL are out of scope): frames must already be at the target scale.
+
+Spatial side of the views: ``sample_multiscale_crop`` mirrors ``SubgroupWise_MultiScaleCrop_TANet._sample_crop_size``
+(models/tanet_models/transforms.py:325-385; one random multi-scale crop box per temporal view, the reference's default with
+``--if_spatial_rand_cropping``, utils/opts.py:85, corpus/basics.py:1238-1245) and ``views_to_device(..., boxes=...)`` crops
+and resizes on the GPU with Pillow's exact 8-bit bilinear arithmetic (``vitta_gather_crop_resize_normalize_u8``).
 """
 import ctypes as C
+import random as _random
 
 import numpy as np
 import torch
@@ -45,18 +51,106 @@ def sample_tta_view_indices(num_frames, num_segments, n_views=2, style="uniform_
     return np.minimum(idx, num_frames - 1)                      # ... used as 0-based indices, clamped (:328)
 
 
-def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD):
+# ----------------------------------------------------------------------------------------------
+# per-view random multi-scale crop (the reference's default spatial augmentation of the TTA views)
+# ----------------------------------------------------------------------------------------------
+MULTISCALE_SCALES = (1, .875, .75, .66)      # transforms.py:291
+
+
+def fill_fix_offset(image_w, image_h, crop_w, crop_h, more_fix_crop=True):
+    """Candidate (offset_w, offset_h) positions in the reference's order (transforms.py:361-385): 5 or 13 of them."""
+    ws, hs = (image_w - crop_w) // 4, (image_h - crop_h) // 4
+    ret = [(0, 0), (4 * ws, 0), (0, 4 * hs), (4 * ws, 4 * hs), (2 * ws, 2 * hs)]
+    if more_fix_crop:
+        ret += [(0, 2 * hs), (4 * ws, 2 * hs), (2 * ws, 4 * hs), (2 * ws, 0),
+                (ws, hs), (3 * ws, hs), (ws, 3 * hs), (3 * ws, 3 * hs)]
+    return ret
+
+
+def sample_multiscale_crop(image_w, image_h, input_size, rng=_random, scales=MULTISCALE_SCALES, max_distort=1,
+                           more_fix_crop=True):
+    """One draw of ``_sample_crop_size`` with fix_crop=True (transforms.py:325-354): (crop_w, crop_h, offset_w, offset_h).
+    ``rng`` is the ``random`` module or a ``random.Random``; like the reference it is asked for two ``choice`` draws --
+    first the (w, h) pair, then the position -- so the same seed gives the same boxes as the reference pipeline."""
+    iw, ih = (input_size, input_size) if isinstance(input_size, int) else input_size
+    base = min(image_w, image_h)
+    sizes = [int(base * x) for x in scales]
+    crop_h = [ih if abs(x - ih) < 3 else x for x in sizes]
+    crop_w = [iw if abs(x - iw) < 3 else x for x in sizes]
+    pairs = [(w, h) for i, h in enumerate(crop_h) for j, w in enumerate(crop_w) if abs(i - j) <= max_distort]
+    cw, ch = rng.choice(pairs)
+    ow, oh = rng.choice(fill_fix_offset(image_w, image_h, cw, ch, more_fix_crop))
+    return cw, ch, ow, oh
+
+
+def sample_view_crops(image_w, image_h, input_size, n_views, rng=_random):
+    """One box per temporal view, drawn view after view (SubgroupWise_MultiScaleCrop_TANet.__call__, transforms.py:301-310)."""
+    return [sample_multiscale_crop(image_w, image_h, input_size, rng) for _ in range(n_views)]
+
+
+def resample_tables(in_size, out_size, in_offset=0, slots=None):
+    """Pillow's 8-bit bilinear coefficient tables for one axis (host arithmetic in the library, no GPU involved):
+    (bounds (out, 2) int32 = (first source index + in_offset, count), kk (out, slots) int32, 22-bit fixed point)."""
+    lib = _lib.load()
+    ks = lib.vitta_resample_ksize(int(in_size), int(out_size))
+    if ks <= 0:
+        raise _lib.VittaError("resample_tables: bad sizes %r -> %r" % (in_size, out_size))
+    slots = ks if slots is None else int(slots)
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, slots), np.int32)
+    _lib.check(lib.vitta_resample_coeffs_u8(int(in_size), int(out_size), int(in_offset), slots,
+                                            bounds.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            kk.ctypes.data_as(C.POINTER(C.c_int32))), "vitta_resample_coeffs_u8")
+    return bounds, kk
+
+
+def crop_resize_tables(boxes, out_h, out_w):
+    """Stacked per-view tables for ``vitta_gather_crop_resize_normalize_u8``: (hb, hk, vb, vk, slots) numpy int32."""
+    lib = _lib.load()
+    slots = max(3, max(max(lib.vitta_resample_ksize(int(b[0]), out_w), lib.vitta_resample_ksize(int(b[1]), out_h))
+                       for b in boxes))
+    hb, hk, vb, vk = [], [], [], []
+    for cw, ch, ow, oh in boxes:
+        b, k = resample_tables(cw, out_w, ow, slots)
+        hb.append(b), hk.append(k)
+        b, k = resample_tables(ch, out_h, oh, slots)
+        vb.append(b), vk.append(k)
+    return np.stack(hb), np.stack(hk), np.stack(vb), np.stack(vk), slots
+
+
+def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD,
+                    boxes=None, out_size=None):
     """frames_u8: (F, H, W, 3) uint8 CUDA tensor; indices: (V*T,) ints.  Returns the loader tensor of ONE video:
-    TANet ``(V*T*3, h, w)`` or Swin ``(V, 3, T, h, w)``, normalised fp32.  crop = (y, x, h, w) or None (whole frame)."""
+    TANet ``(V*T*3, h, w)`` or Swin ``(V, 3, T, h, w)``, normalised fp32.  crop = (y, x, h, w) or None (whole frame).
+    boxes = one (crop_w, crop_h, offset_w, offset_h) per view (``sample_view_crops``) + out_size = S (or (h, w)): every
+    view is cropped with its own box and resized to S x S exactly as PIL's BILINEAR does (the reference's
+    SubgroupWise_MultiScaleCrop_TANet); ``crop`` must then be None."""
     if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
         raise _lib.VittaError("views_to_device: frames must be a (F, H, W, 3) uint8 CUDA tensor; there is no CPU path")
     frames_u8 = frames_u8.contiguous()
     f, h, w, _ = frames_u8.shape
-    y0, x0, oh, ow = crop if crop is not None else (0, 0, h, w)
     idx = torch.as_tensor(np.asarray(indices, dtype=np.int32)).to(frames_u8.device)
     n = idx.numel()
     v = n // clip_len
     layout = 0 if arch == "tanet" else 1
+    if boxes is not None:
+        if crop is not None or out_size is None:
+            raise _lib.VittaError("views_to_device: boxes need out_size and exclude crop")
+        if len(boxes) != v or n != v * clip_len:
+            raise _lib.VittaError("views_to_device: one crop box per view (%d views, %d boxes)" % (v, len(boxes)))
+        oh, ow = (out_size, out_size) if isinstance(out_size, int) else out_size
+        hb, hk, vb, vk, slots = crop_resize_tables(boxes, oh, ow)
+        dev = frames_u8.device
+        tabs = [torch.from_numpy(t).to(dev) for t in (hb, hk, vb, vk)]
+        out = torch.empty((n * 3, oh, ow) if layout == 0 else (v, 3, clip_len, oh, ow), dtype=torch.float32, device=dev)
+        bx = (C.c_int32 * (4 * v))(*[int(x) for b in boxes for x in b])
+        m3 = (C.c_float * 3)(*[float(x) for x in mean])
+        s3 = (C.c_float * 3)(*[float(x) for x in std])
+        call("vitta_gather_crop_resize_normalize_u8", ptr(frames_u8), f, h, w, ptr(idx), n, bx, v, ptr(tabs[0]),
+             ptr(tabs[1]), ptr(tabs[2]), ptr(tabs[3]), slots, int(oh), int(ow), m3, s3, layout, int(clip_len), ptr(out),
+             stream_ptr())
+        return out
+    y0, x0, oh, ow = crop if crop is not None else (0, 0, h, w)
     out = torch.empty((n * 3, oh, ow) if layout == 0 else (v, 3, clip_len, oh, ow), dtype=torch.float32,
                       device=frames_u8.device)
     m3 = (C.c_float * 3)(*[float(x) for x in mean])

@@ -42,6 +42,76 @@ __global__ void __launch_bounds__(256) gather_normalize_kernel(const uint8_t* __
   }
 }
 
+// ---- per-view crop + bilinear resize (SubgroupWise_MultiScaleCrop_TANet, transforms.py:277-384) ----
+// Bit-exact restatement of what the reference's PIL pipeline computes for 8-bit frames: img.crop(box).resize((S, S),
+// Image.BILINEAR) is Pillow's two-pass fixed-point resampler (Resample.c: 22-bit coefficients, horizontal pass rounded to
+// uint8 before the vertical pass).  The coefficient tables come from vitta_resample_coeffs_u8 (host, double precision like
+// Pillow's precompute_coeffs) with the crop offset already added to the window starts, one table set per view.
+// One thread per output pixel: for each of its <= ks source rows it forms the horizontally resampled uint8 value, then
+// combines the rows with the vertical coefficients.  Consecutive threads read consecutive source pixels.
+constexpr int kResampleBits = 32 - 8 - 2;
+
+__device__ __forceinline__ int clip8_fixed(int v) {
+  v >>= kResampleBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256) gather_crop_resize_kernel(
+    const uint8_t* __restrict__ frames, int F, int H, int W, const int32_t* __restrict__ idx, int n_idx,
+    const int32_t* __restrict__ hb, const int32_t* __restrict__ hk, const int32_t* __restrict__ vb,
+    const int32_t* __restrict__ vk, int ks, int out_h, int out_w, float3 scale, float3 shift, int layout, int T,
+    float* __restrict__ out) {
+  const int64_t plane = (int64_t)out_h * out_w;
+  const int64_t total = (int64_t)n_idx * plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int k = (int)(i / plane);          // which (view, frame)
+    const int64_t px = i - (int64_t)k * plane;
+    const int y = (int)(px / out_w), x = (int)(px - (int64_t)y * out_w);
+    const int v = k / T;
+    int f = __ldg(idx + k);
+    f = f < 0 ? 0 : (f >= F ? F - 1 : f);    // np.minimum(frame_indices, num_frames - 1) (video_dataset.py:328)
+    const int32_t* hbv = hb + ((int64_t)v * out_w + x) * 2;
+    const int32_t* vbv = vb + ((int64_t)v * out_h + y) * 2;
+    const int32_t* hkv = hk + ((int64_t)v * out_w + x) * ks;
+    const int32_t* vkv = vk + ((int64_t)v * out_h + y) * ks;
+    const int x0 = __ldg(hbv), nx = min(__ldg(hbv + 1), ks);
+    const int y0 = __ldg(vbv), ny = min(__ldg(vbv + 1), ks);
+    const uint8_t* fr = frames + (int64_t)f * H * W * 3;
+    int ar = 1 << (kResampleBits - 1), ag = ar, ab = ar;
+    for (int yy = 0; yy < ny; ++yy) {
+      const int sy = min(max(y0 + yy, 0), H - 1);          // tables built by the library never leave the frame;
+      const uint8_t* row = fr + (int64_t)sy * W * 3;        // the clamp only guards against foreign tables
+      int hr = 1 << (kResampleBits - 1), hg = hr, hbl = hr;
+      for (int xx = 0; xx < nx; ++xx) {
+        const int sx = min(max(x0 + xx, 0), W - 1);
+        const int c = __ldg(hkv + xx);
+        hr += (int)row[sx * 3] * c;
+        hg += (int)row[sx * 3 + 1] * c;
+        hbl += (int)row[sx * 3 + 2] * c;
+      }
+      const int c = __ldg(vkv + yy);
+      ar += clip8_fixed(hr) * c;
+      ag += clip8_fixed(hg) * c;
+      ab += clip8_fixed(hbl) * c;
+    }
+    const float r = (float)clip8_fixed(ar) * scale.x + shift.x;
+    const float g = (float)clip8_fixed(ag) * scale.y + shift.y;
+    const float b = (float)clip8_fixed(ab) * scale.z + shift.z;
+    if (layout == 0) {
+      float* o = out + (int64_t)k * 3 * plane + px;
+      o[0] = r;
+      o[plane] = g;
+      o[2 * plane] = b;
+    } else {
+      const int t = k - v * T;
+      float* o = out + (((int64_t)v * 3) * T + t) * plane + px;
+      o[0] = r;
+      o[(int64_t)T * plane] = g;
+      o[2 * (int64_t)T * plane] = b;
+    }
+  }
+}
+
 }  // namespace vitta
 
 using namespace vitta;
@@ -63,6 +133,83 @@ extern "C" int vitta_gather_normalize_u8(const uint8_t* frames, int F, int H, in
   if (blocks > 148 * 16) blocks = 148 * 16;
   gather_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, idx, n_idx, crop_y, crop_x,
                                                                              out_h, out_w, scale, shift, layout, T, out);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// ---- Pillow's bilinear coefficient tables (host only: no CUDA call) ----
+extern "C" int vitta_resample_ksize(int in_size, int out_size) {
+  if (in_size <= 0 || out_size <= 0) return -1;
+  double filterscale = (double)in_size / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  return (int)ceil(filterscale) * 2 + 1;
+}
+
+extern "C" int vitta_resample_coeffs_u8(int in_size, int out_size, int in_offset, int slots, int32_t* bounds_host,
+                                        int32_t* kk_host) {
+  const int ksize = vitta_resample_ksize(in_size, out_size);
+  VITTA_CHECK_ARG(ksize > 0 && bounds_host && kk_host && in_offset >= 0, VITTA_E_BADARG, "resample_coeffs: bad arguments");
+  VITTA_CHECK_ARG(slots >= ksize, VITTA_E_BADARG, "resample_coeffs: fewer coefficient slots than vitta_resample_ksize");
+  // Resample.c precompute_coeffs (bilinear: support 1.0) + normalize_coeffs_8bpc, in double precision like Pillow
+  const double scale = (double)in_size / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  const double ss = 1.0 / filterscale;
+  double w[64];
+  VITTA_CHECK_ARG(ksize <= 64, VITTA_E_UNSUPPORTED, "resample_coeffs: reduction factor above 31");
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      w[x] = a < 1.0 ? 1.0 - a : 0.0;
+      ww += w[x];
+    }
+    int32_t* k = kk_host + (int64_t)xx * slots;
+    for (int x = 0; x < slots; ++x) {
+      double c = 0.0;
+      if (x < xmax) c = (ww != 0.0) ? w[x] / ww : w[x];
+      k[x] = c < 0 ? (int32_t)(-0.5 + c * (1 << kResampleBits)) : (int32_t)(0.5 + c * (1 << kResampleBits));
+    }
+    bounds_host[xx * 2] = xmin + in_offset;     // window start in frame coordinates (crop offset folded in)
+    bounds_host[xx * 2 + 1] = xmax;
+  }
+  return 0;
+}
+
+extern "C" int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int F, int H, int W, const int32_t* idx,
+                                                     int n_idx, const int32_t* boxes_host, int n_views,
+                                                     const int32_t* hbounds, const int32_t* hk, const int32_t* vbounds,
+                                                     const int32_t* vk, int slots, int out_h, int out_w,
+                                                     const float* mean3_host, const float* std3_host, int layout, int T,
+                                                     float* out, void* stream) {
+  VITTA_CHECK_ARG(frames && idx && out && mean3_host && std3_host && boxes_host && hbounds && hk && vbounds && vk,
+                  VITTA_E_BADARG, "gather_crop_resize: null pointer");
+  VITTA_CHECK_ARG(F > 0 && H > 0 && W > 0 && n_idx > 0 && out_h > 0 && out_w > 0 && T > 0 && n_views > 0 &&
+                      n_idx == n_views * T && slots >= 3,
+                  VITTA_E_BADARG, "gather_crop_resize: bad shape (n_idx must be n_views * T)");
+  VITTA_CHECK_ARG(layout == 0 || layout == 1, VITTA_E_BADARG, "gather_crop_resize: layout must be 0 (TANet) or 1 (Swin)");
+  for (int v = 0; v < n_views; ++v) {   // (crop_w, crop_h, offset_w, offset_h) per view, as _sample_crop_size returns them
+    const int32_t* b = boxes_host + v * 4;
+    VITTA_CHECK_ARG(b[0] > 0 && b[1] > 0 && b[2] >= 0 && b[3] >= 0 && b[2] + b[0] <= W && b[3] + b[1] <= H, VITTA_E_BADARG,
+                    "gather_crop_resize: crop box outside the frame");
+    VITTA_CHECK_ARG(vitta_resample_ksize(b[0], out_w) <= slots && vitta_resample_ksize(b[1], out_h) <= slots,
+                    VITTA_E_BADARG, "gather_crop_resize: coefficient slots too small for this crop");
+  }
+  const float3 scale = make_float3(1.f / (255.f * std3_host[0]), 1.f / (255.f * std3_host[1]), 1.f / (255.f * std3_host[2]));
+  const float3 shift = make_float3(-mean3_host[0] / std3_host[0], -mean3_host[1] / std3_host[1], -mean3_host[2] / std3_host[2]);
+  const int64_t total = (int64_t)n_idx * out_h * out_w;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_crop_resize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      frames, F, H, W, idx, n_idx, hbounds, hk, vbounds, vk, slots, out_h, out_w, scale, shift, layout, T, out);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
