@@ -411,6 +411,10 @@ int vitta_gather_normalize_u8(const uint8_t* frames, int F, int H, int W, const 
  *   boxes_host: n_views x (crop_w, crop_h, offset_w, offset_h) HOST ints, the tuple _sample_crop_size returns
  *   (validated against the frame); hbounds / hk: device tables [n_views][out_w][2] / [n_views][out_w][slots] built with
  *   in_offset = offset_w, vbounds / vk likewise for the rows; mean / std / layout / T / out as vitta_gather_normalize_u8.
+ *   A table row describes ONE output position, so any subset of the rows of a resize is "resize, then crop": the
+ *   reference's GroupScale + GroupCenterCrop path (transforms.py:46-52,170-183) uses the same entry point with the rows
+ *   [left, left + S) of a whole-frame resize.  The kernel clamps every source coordinate into the frame, so foreign
+ *   tables cannot read outside it.
  * ---------------------------------------------------------------------------------------------- */
 int vitta_resample_ksize(int in_size, int out_size);
 int vitta_resample_coeffs_u8(int in_size, int out_size, int in_offset, int slots, int32_t* bounds_host, int32_t* kk_host);

@@ -514,6 +514,14 @@ def run_crops_case():
         out["xf/%s/meta" % name] = np.asarray([inp, views, t, seed], np.int64)
         out["xf/%s/boxes" % name] = np.asarray(boxes, np.int64)
         out["xf/%s/out" % name] = np.stack([np.asarray(im) for im in imgs])
+    # (c) the other spatial path: GroupScale_TANet + GroupCenterCrop_TANet (corpus/basics.py:1259-1263)
+    for name, (ih, iw, z, inp) in {"a": (48, 64, 40, 32), "b": (64, 48, 40, 32), "c": (40, 40, 40, 32),
+                                   "d": (51, 77, 36, 33), "e": (30, 100, 64, 48)}.items():
+        frames = rng.integers(0, 256, (2, ih, iw, 3), dtype=np.uint8)
+        imgs, _ = tr.GroupCenterCrop_TANet(inp)(tr.GroupScale_TANet(z)(([Image.fromarray(f) for f in frames], 0)))
+        out["sc/%s/frames" % name] = frames
+        out["sc/%s/meta" % name] = np.asarray([z, inp], np.int64)
+        out["sc/%s/out" % name] = np.stack([np.asarray(im) for im in imgs])
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "crops.npz"), **out)
     print("wrote crops", len(out), "arrays")

@@ -118,3 +118,19 @@ def crop_resize_views(frames, indices, clip_len, boxes, out_size):
         cw, ch, ow, oh = boxes[k // clip_len]
         out.append(resize_bilinear_u8(frames[int(f)][oh:oh + ch, ow:ow + cw], out_size, out_size))
     return np.stack(out)
+
+
+def scale_center_crop_u8(img, scale_size, input_size):
+    """GroupScale_TANet(scale_size) + GroupCenterCrop_TANet(input_size) on one (H, W, 3) uint8 frame (transforms.py:46-52,
+    170-183): torchvision 0.8.2 (requirements.txt:63) ``Resize(int)`` -- smaller edge to ``scale_size``,
+    ``int(size * long / short)`` for the other, untouched when it already matches -- then ``CenterCrop``:
+    ``int(round((extent - S) / 2.))``."""
+    h, w = img.shape[:2]
+    if not ((w <= h and w == scale_size) or (h <= w and h == scale_size)):
+        if w < h:
+            img = resize_bilinear_u8(img, scale_size, int(scale_size * h / w))
+        else:
+            img = resize_bilinear_u8(img, int(scale_size * w / h), scale_size)
+    h, w = img.shape[:2]
+    top, left = int(round((h - input_size) / 2.)), int(round((w - input_size) / 2.))
+    return img[top:top + input_size, left:left + input_size]

@@ -69,6 +69,33 @@ def test_oracle_resize_matches_installed_pillow():
     assert (R.resize_bilinear_u8(flat, 17, 53) == 255).all()
 
 
+def test_scale_center_crop_matches_reference_transform_golden():
+    """GroupScale_TANet + GroupCenterCrop_TANet recorded from the reference: the oracle's restatement, and the product's
+    table slicing (rows [left, left + S) of the whole-frame resize) applied with the oracle's pass -- both bit exact."""
+    from oracle import pil_resample as R
+    from vitta_b200.corpus.views import scale_center_crop_geometry, scale_center_crop_tables
+    g = np.load(GOLDEN)
+    for name in ("a", "b", "c", "d", "e"):
+        z, inp = (int(v) for v in g["sc/%s/meta" % name])
+        frames, want = g["sc/%s/frames" % name], g["sc/%s/out" % name]
+        h, w = frames.shape[1:3]
+        hb, hk, vb, vk, slots = scale_center_crop_tables(w, h, z, inp, n_views=2)
+        assert hb.shape == (2, inp, 2) and hk.shape == (2, inp, slots) and (hb[0] == hb[1]).all()
+        ow, oh, left, top = scale_center_crop_geometry(w, h, z, inp)
+        assert min(ow, oh) == z and 0 <= left <= ow - inp and 0 <= top <= oh - inp
+        for f, wf in zip(frames, want):
+            assert (R.scale_center_crop_u8(f, z, inp) == wf).all(), name
+            got = R._pass(R._pass(f, hb[0], hk[0], axis=1), vb[0], vk[0], axis=0)
+            assert (got == wf).all(), name
+
+
+def test_scale_center_crop_smaller_than_the_crop_is_loud():
+    from vitta_b200 import _lib
+    from vitta_b200.corpus.views import scale_center_crop_geometry
+    with pytest.raises(_lib.VittaError):
+        scale_center_crop_geometry(64, 48, 24, 32)
+
+
 @pytest.mark.parametrize("offset", [0, 7])
 def test_library_coefficient_tables_match_oracle(offset):
     from oracle import pil_resample as R
@@ -155,3 +182,21 @@ def test_views_to_device_crop_resize_vs_oracle(cuda_device, arch):
             want = x.reshape(views, t, 3, s, s).permute(0, 2, 1, 3, 4)
         # one uint8 step is 1/(255*0.225) = 1.7e-2 after normalisation: 1e-5 means every pixel has the exact PIL value
         torch.testing.assert_close(out.cpu(), want.contiguous(), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
+                    reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
+def test_views_to_device_scale_center_crop_vs_oracle(cuda_device):
+    from oracle import pil_resample as R
+    from vitta_b200 import synth
+    from vitta_b200.corpus.views import sample_tta_view_indices, views_to_device
+    f, h, w, t, views, z, s = 20, 96, 128, 4, 2, 80, 64
+    rng = np.random.Generator(np.random.PCG64(9))
+    frames = rng.integers(0, 256, (f, h, w, 3), dtype=np.uint8)
+    idx = sample_tta_view_indices(f, t, views)
+    out = views_to_device(torch.from_numpy(frames).to(cuda_device), idx, t, "tanet", scale_size=z, out_size=s)
+    u8 = np.stack([R.scale_center_crop_u8(frames[int(i)], z, s) for i in idx])
+    x = torch.from_numpy(u8).float() / 255.0
+    x = ((x - torch.tensor(synth.INPUT_MEAN)) / torch.tensor(synth.INPUT_STD)).permute(0, 3, 1, 2)
+    torch.testing.assert_close(out.cpu(), x.reshape(views * t * 3, s, s).contiguous(), rtol=1e-6, atol=1e-5)

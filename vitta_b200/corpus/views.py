@@ -118,13 +118,46 @@ def crop_resize_tables(boxes, out_h, out_w):
     return np.stack(hb), np.stack(hk), np.stack(vb), np.stack(vk), slots
 
 
+def scale_center_crop_geometry(image_w, image_h, scale_size, input_size):
+    """GroupScale_TANet(scale_size) + GroupCenterCrop_TANet(input_size) (transforms.py:46-52,170-183; torchvision 0.8.2
+    ``Resize(int)`` / ``CenterCrop``): smaller edge -> scale_size keeping the aspect ratio (``int(size * long / short)``,
+    untouched if it already matches), then the centred S x S window (``int(round((extent - S) / 2.))``).
+    Returns (resized_w, resized_h, left, top)."""
+    w, h, size = int(image_w), int(image_h), int(scale_size)
+    if (w <= h and w == size) or (h <= w and h == size):
+        ow, oh = w, h
+    elif w < h:
+        ow, oh = size, int(size * h / w)
+    else:
+        ow, oh = int(size * w / h), size
+    s = int(input_size)
+    if ow < s or oh < s:
+        raise _lib.VittaError("scale_center_crop: %dx%d scaled to %dx%d is smaller than the %d crop" % (w, h, ow, oh, s))
+    return ow, oh, int(round((ow - s) / 2.)), int(round((oh - s) / 2.))
+
+
+def scale_center_crop_tables(image_w, image_h, scale_size, input_size, n_views=1):
+    """Tables of ``vitta_gather_crop_resize_normalize_u8`` for the scale + centre-crop path: the rows [left, left + S) /
+    [top, top + S) of the whole-frame resize (resize-then-crop == computing only those output positions)."""
+    ow, oh, left, top = scale_center_crop_geometry(image_w, image_h, scale_size, input_size)
+    s = int(input_size)
+    hb, hk = resample_tables(image_w, ow)
+    vb, vk = resample_tables(image_h, oh)
+    slots = max(3, hk.shape[1], vk.shape[1])
+    pad = lambda k: np.pad(k, ((0, 0), (0, slots - k.shape[1])))
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a, (n_views,) + a.shape))
+    return (rep(hb[left:left + s]), rep(pad(hk)[left:left + s]), rep(vb[top:top + s]), rep(pad(vk)[top:top + s]), slots)
+
+
 def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD,
-                    boxes=None, out_size=None):
+                    boxes=None, out_size=None, scale_size=None):
     """frames_u8: (F, H, W, 3) uint8 CUDA tensor; indices: (V*T,) ints.  Returns the loader tensor of ONE video:
     TANet ``(V*T*3, h, w)`` or Swin ``(V, 3, T, h, w)``, normalised fp32.  crop = (y, x, h, w) or None (whole frame).
     boxes = one (crop_w, crop_h, offset_w, offset_h) per view (``sample_view_crops``) + out_size = S (or (h, w)): every
     view is cropped with its own box and resized to S x S exactly as PIL's BILINEAR does (the reference's
-    SubgroupWise_MultiScaleCrop_TANet); ``crop`` must then be None."""
+    SubgroupWise_MultiScaleCrop_TANet); ``crop`` must then be None.
+    scale_size = Z + out_size = S (no boxes): the reference's other spatial path, GroupScale(Z) + GroupCenterCrop(S)
+    (corpus/basics.py:1259-1263), same kernel, same PIL-exact arithmetic."""
     if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
         raise _lib.VittaError("views_to_device: frames must be a (F, H, W, 3) uint8 CUDA tensor; there is no CPU path")
     frames_u8 = frames_u8.contiguous()
@@ -133,13 +166,18 @@ def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=
     n = idx.numel()
     v = n // clip_len
     layout = 0 if arch == "tanet" else 1
-    if boxes is not None:
-        if crop is not None or out_size is None:
-            raise _lib.VittaError("views_to_device: boxes need out_size and exclude crop")
-        if len(boxes) != v or n != v * clip_len:
-            raise _lib.VittaError("views_to_device: one crop box per view (%d views, %d boxes)" % (v, len(boxes)))
-        oh, ow = (out_size, out_size) if isinstance(out_size, int) else out_size
-        hb, hk, vb, vk, slots = crop_resize_tables(boxes, oh, ow)
+    if boxes is not None or scale_size is not None:
+        if crop is not None or out_size is None or (boxes is not None and scale_size is not None):
+            raise _lib.VittaError("views_to_device: boxes / scale_size need out_size and exclude crop and each other")
+        if n != v * clip_len or (boxes is not None and len(boxes) != v):
+            raise _lib.VittaError("views_to_device: one crop box per view (%d indices, clip length %d)" % (n, clip_len))
+        if boxes is not None:
+            oh, ow = (out_size, out_size) if isinstance(out_size, int) else out_size
+            hb, hk, vb, vk, slots = crop_resize_tables(boxes, oh, ow)
+        else:
+            oh = ow = int(out_size)
+            hb, hk, vb, vk, slots = scale_center_crop_tables(w, h, scale_size, out_size, v)
+            boxes = [(w, h, 0, 0)] * v            # the tables address the whole frame
         dev = frames_u8.device
         tabs = [torch.from_numpy(t).to(dev) for t in (hb, hk, vb, vk)]
         out = torch.empty((n * 3, oh, ow) if layout == 0 else (v, 3, clip_len, oh, ow), dtype=torch.float32, device=dev)

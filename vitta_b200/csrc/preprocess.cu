@@ -196,12 +196,10 @@ extern "C" int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int 
                       n_idx == n_views * T && slots >= 3,
                   VITTA_E_BADARG, "gather_crop_resize: bad shape (n_idx must be n_views * T)");
   VITTA_CHECK_ARG(layout == 0 || layout == 1, VITTA_E_BADARG, "gather_crop_resize: layout must be 0 (TANet) or 1 (Swin)");
-  for (int v = 0; v < n_views; ++v) {   // (crop_w, crop_h, offset_w, offset_h) per view, as _sample_crop_size returns them
+  for (int v = 0; v < n_views; ++v) {   // source region of each view: (crop_w, crop_h, offset_w, offset_h), as _sample_crop_size returns it
     const int32_t* b = boxes_host + v * 4;
     VITTA_CHECK_ARG(b[0] > 0 && b[1] > 0 && b[2] >= 0 && b[3] >= 0 && b[2] + b[0] <= W && b[3] + b[1] <= H, VITTA_E_BADARG,
                     "gather_crop_resize: crop box outside the frame");
-    VITTA_CHECK_ARG(vitta_resample_ksize(b[0], out_w) <= slots && vitta_resample_ksize(b[1], out_h) <= slots,
-                    VITTA_E_BADARG, "gather_crop_resize: coefficient slots too small for this crop");
   }
   const float3 scale = make_float3(1.f / (255.f * std3_host[0]), 1.f / (255.f * std3_host[1]), 1.f / (255.f * std3_host[2]));
   const float3 shift = make_float3(-mean3_host[0] / std3_host[0], -mean3_host[1] / std3_host[1], -mean3_host[2] / std3_host[2]);
