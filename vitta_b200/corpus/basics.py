@@ -229,8 +229,22 @@ class OnlineAdapter:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count
-        with torch.cuda.graph(g):
-            out = self._adapt_eager(self._graph_in, None, None)
+        try:
+            with torch.cuda.graph(g):
+                out = self._adapt_eager(self._graph_in, None, None)
+        except _lib.VittaError:
+            raise                                         # our own kernels refusing a call is never a capture problem
+        except RuntimeError as e:
+            # e.g. a collective the installed NCCL cannot capture at this world size: keep adapting with eager launches
+            # (same kernels, same order, same results -- only the launch overhead returns) and say so loudly.
+            import sys
+            sys.stderr.write("vitta_b200: CUDA-graph capture of the adaptation step failed (%s); continuing with eager "
+                             "launches\n" % (str(e).splitlines()[0] if str(e) else type(e).__name__))
+            args.cuda_graph = False
+            self._graph = self._graph_in = None
+            _lib.launch_count = l0
+            torch.cuda.synchronize()
+            return self._adapt_eager(input, target, criterion)
         self._graph_launches = _lib.launch_count - l0     # kernels of ours inside one replay
         _lib.launch_count = l0
         self._graph, self._graph_key, self._graph_out = g, key, out
