@@ -22,5 +22,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --gemm-preci
 #     profiles/r01_late_checks.md) -- full capture with source-level warp-state samples of the attention kernels alone
 timeout 120 python tools/one_wmsa.py > gpurun_out/one_wmsa.log 2>&1; cat gpurun_out/one_wmsa.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"wmsa3d_fwd|wmsa3d_bwd2" --launch-skip 6 -c 3 -o gpurun_out/prof_wmsa python tools/one_wmsa.py > gpurun_out/ncu_wmsa.log 2>&1; echo "ncu wmsa rc=$?"
+# 4d. the reference step on torch's own CUDA kernels (the 'reference-on-GPU' bar), TF32 off and on
+timeout 600 python tools/reference_gpu_step.py > gpurun_out/reference_gpu_step.json 2> gpurun_out/reference_gpu_step.err; echo "reference-on-GPU rc=$?"; head -c 600 gpurun_out/reference_gpu_step.json; echo
 # 5. the regular round (tests, bench, Swin tables)
 bash tools/gpu_round.sh
