@@ -527,6 +527,66 @@ def run_crops_case():
     print("wrote crops", len(out), "arrays")
 
 
+def run_loader_case():
+    """Whole items of the reference's own TANet loader: ``corpus.basics.get_dataset_tanet`` -> ``Video_TANetDataSet.
+    __getitem__`` (index sampling, PIL conversion, per-view random multi-scale crop or scale + centre crop, Stack,
+    ToTorchFormatTensor, GroupNormalize), unmodified.  Only the decoder is replaced: ``decord.VideoReader`` is an
+    in-memory reader over seeded uint8 frames (decoding is out of scope)."""
+    import importlib
+    import random
+    import tempfile
+    ref = ref_harness.load_reference()
+    vd = importlib.import_module("models.tanet_models.video_dataset")
+    basics = importlib.import_module("corpus.basics")
+    rng = np.random.Generator(np.random.PCG64(23))
+    videos = {"v0": rng.integers(0, 256, (11, 48, 64, 3), dtype=np.uint8),
+              "v1": rng.integers(0, 256, (20, 60, 44, 3), dtype=np.uint8)}
+    labels = {"v0": 3, "v1": 7}
+
+    class Batch:
+        def __init__(self, a):
+            self.a = a
+
+        def asnumpy(self):
+            return self.a
+
+    class Reader:
+        def __init__(self, path):
+            self.frames = videos[os.path.basename(path)[:-4]]
+            self._num_frame = len(self.frames)
+
+        def get_batch(self, idx):
+            return Batch(self.frames[np.asarray(idx)])
+    vd.decord.VideoReader = Reader
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        lst = os.path.join(tmp, "list.txt")
+        with open(lst, "w") as f:
+            for k, v in videos.items():
+                f.write("%s %d %d\n" % (k, len(v), labels[k]))
+        for case, (kind, views, rand_crop, seed) in {"tta_randcrop": ("tta", 2, True, 31), "tta_center": ("tta", 2, False, 32),
+                                                    "eval": ("eval", 2, True, 33), "tta_3views": ("tta", 3, True, 34)}.items():
+            args = ref["utils.opts"].parser.parse_args([])
+            args.arch, args.modality, args.vid_format = "tanet", "RGB", ".mp4"
+            args.val_vid_list, args.video_data_dir = lst, tmp
+            args.clip_length, args.input_size, args.scale_size, args.full_res = 4, 32, 40, False
+            args.test_crops, args.sample_style, args.debug = 1, "uniform-1", False
+            args.if_sample_tta_aug_views, args.n_augmented_views = True, views
+            args.if_spatial_rand_cropping = rand_crop
+            args.tta_view_sample_style_list = ["uniform_equidist"]
+            ds = basics.get_dataset_tanet(args, split="val", dataset_type=kind)
+            random.seed(seed)
+            for i, name in enumerate(videos):
+                x, y = ds[i]
+                out["%s/%s/x" % (case, name)] = x.numpy().astype(np.float32)
+                out["%s/%s/y" % (case, name)] = np.asarray(y, np.int64)
+            out["%s/meta" % case] = np.asarray([1 if kind == "tta" else 0, views, int(rand_crop), seed], np.int64)
+    for k, v in videos.items():
+        out["video/%s" % k] = v
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "loader.npz"), **out)
+    print("wrote loader", len(out), "arrays")
+
+
 def main(argv):
     want = set(argv)
     if not want or "units" in want:
@@ -535,6 +595,8 @@ def main(argv):
         run_views_case()
     if not want or "crops" in want:
         run_crops_case()
+    if not want or "loader" in want:
+        run_loader_case()
     for name, cfg in TANET_CASES.items():
         if not want or name in want:
             run_model_case(name, cfg, "tanet")

@@ -157,6 +157,75 @@ def test_views_to_device_has_no_cpu_path():
         views_to_device(torch.zeros(4, 48, 64, 3, dtype=torch.uint8), [0, 1], 2, boxes=[(32, 32, 0, 0)], out_size=32)
 
 
+# ----------------------------------------------------------------------------------------------
+# whole loader items recorded from the unmodified reference (get_dataset_tanet -> Video_TANetDataSet.__getitem__ with an
+# in-memory decoder): tests/golden/loader.npz
+# ----------------------------------------------------------------------------------------------
+LOADER = os.path.join(cases.GOLDEN_DIR, "loader.npz")
+LOADER_CASES = ["tta_randcrop", "tta_center", "eval", "tta_3views"]
+
+
+def _loader_args(g, case):
+    from vitta_b200.utils.opts import default_args
+    is_tta, views, rand_crop, seed = (int(v) for v in g[case + "/meta"])
+    args = default_args(arch="tanet", clip_length=4, input_size=32, scale_size=40, n_augmented_views=views,
+                        if_sample_tta_aug_views=True, if_spatial_rand_cropping=bool(rand_crop), num_classes=11,
+                        batch_size=1)
+    return args, ("tta" if is_tta else "eval"), seed
+
+
+def _oracle_item(frames, idx, boxes, t, scale_size, input_size):
+    """uint8 frames -> the reference's loader tensor (V*T*3, S, S) through the oracle's spatial pipeline."""
+    from oracle import pil_resample as R
+    from vitta_b200 import synth
+    if boxes is not None:
+        u8 = R.crop_resize_views(frames, idx, t, boxes, input_size)
+    else:
+        u8 = np.stack([R.scale_center_crop_u8(frames[int(i)], scale_size, input_size) for i in idx])
+    x = torch.from_numpy(u8).permute(0, 3, 1, 2).float().div(255)                  # ToTorchFormatTensor(div=True)
+    x = x.reshape(-1, input_size, input_size)                                      # Stack: planes [view][frame][rgb]
+    mean = torch.tensor(synth.INPUT_MEAN).repeat(x.shape[0] // 3)[:, None, None]   # GroupNormalize (transforms.py:627-650)
+    std = torch.tensor(synth.INPUT_STD).repeat(x.shape[0] // 3)[:, None, None]
+    return (x - mean) / std
+
+
+@pytest.mark.parametrize("case", LOADER_CASES)
+def test_dataset_plan_and_oracle_pipeline_match_reference_loader(case):
+    """The product's host-side plan (frame indices + crop boxes, drawn in the reference's order from the same seed) fed
+    through the oracle's PIL-exact pipeline reproduces the items of the reference's own loader."""
+    from vitta_b200.corpus.views import DecodedVideoDataset
+    g = np.load(LOADER)
+    args, kind, seed = _loader_args(g, case)
+    videos = [torch.from_numpy(g["video/v0"]), torch.from_numpy(g["video/v1"])]
+    ds = DecodedVideoDataset(videos, [3, 7], args, kind, rng=random.Random(seed))
+    assert len(ds) == 2
+    for i, name in enumerate(("v0", "v1")):
+        idx, boxes = ds.plan(i)
+        want = g["%s/%s/x" % (case, name)]
+        assert (boxes is not None) == (kind == "tta" and args.if_spatial_rand_cropping)
+        got = _oracle_item(videos[i].numpy(), idx, boxes, args.clip_length, args.scale_size, args.input_size)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        # same uint8 pixels, then the same two float ops: differences are a float32 ulp at most
+        np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=2e-6)
+        assert int(g["%s/%s/y" % (case, name)]) == ds.labels[i]
+
+
+def test_dataset_refuses_what_it_does_not_mirror():
+    from vitta_b200 import _lib
+    from vitta_b200.corpus.views import DecodedVideoDataset
+    from vitta_b200.utils.opts import default_args
+    vids = [torch.zeros(8, 48, 64, 3, dtype=torch.uint8)]
+    with pytest.raises(NotImplementedError):
+        DecodedVideoDataset(vids, [0], default_args(arch="videoswintransformer"), "tta")
+    with pytest.raises(NotImplementedError):
+        DecodedVideoDataset(vids, [0], default_args(arch="tanet", test_crops=3), "tta")
+    with pytest.raises(_lib.VittaError):
+        DecodedVideoDataset(vids, [0, 1], default_args(arch="tanet"), "tta")
+    ds = DecodedVideoDataset(vids, [0], default_args(arch="tanet", sample_style="dense-1", clip_length=4), "eval")
+    with pytest.raises(NotImplementedError):
+        ds.plan(0)
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
                     reason="kernel written after round 1's GPU budget was spent (oracle and host tables are pinned on the "
@@ -200,3 +269,21 @@ def test_views_to_device_scale_center_crop_vs_oracle(cuda_device):
     x = torch.from_numpy(u8).float() / 255.0
     x = ((x - torch.tensor(synth.INPUT_MEAN)) / torch.tensor(synth.INPUT_STD)).permute(0, 3, 1, 2)
     torch.testing.assert_close(out.cpu(), x.reshape(views * t * 3, s, s).contiguous(), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
+                    reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
+@pytest.mark.parametrize("case", LOADER_CASES)
+def test_decoded_video_dataset_vs_reference_loader_golden(cuda_device, case):
+    """End to end on the GPU: DecodedVideoDataset items against the items of the unmodified reference loader."""
+    from vitta_b200.corpus.views import DecodedVideoDataset
+    g = np.load(LOADER)
+    args, kind, seed = _loader_args(g, case)
+    videos = [torch.from_numpy(g["video/v0"]).to(cuda_device), torch.from_numpy(g["video/v1"]).to(cuda_device)]
+    ds = DecodedVideoDataset(videos, [3, 7], args, kind, rng=random.Random(seed))
+    for i, name in enumerate(("v0", "v1")):
+        x, y = ds[i]
+        # x*(1/(255 s)) - m/s against (x/255 - m)/s: a few float32 ulps of values up to ~2.6; one uint8 step is 1.7e-2
+        np.testing.assert_allclose(x.cpu().numpy(), g["%s/%s/x" % (case, name)], rtol=0, atol=5e-6)
+        assert y == int(g["%s/%s/y" % (case, name)])

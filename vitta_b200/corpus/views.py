@@ -196,3 +196,68 @@ def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=
     call("vitta_gather_normalize_u8", ptr(frames_u8), f, h, w, ptr(idx), n, int(y0), int(x0), int(oh), int(ow), m3, s3,
          layout, int(clip_len), ptr(out), stream_ptr())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's TANet dataset item, from decoded frames that are already on the device
+# ----------------------------------------------------------------------------------------------
+class DecodedVideoDataset(torch.utils.data.Dataset):
+    """``Video_TANetDataSet.__getitem__`` + its transform (models/tanet_models/video_dataset.py:306-345,
+    corpus/basics.py:1221-1290) for videos whose decoded uint8 frames ``(F, H, W, 3)`` already sit in HBM: frame-index
+    sampling, per-view random multi-scale crop (``--if_spatial_rand_cropping``, TTA views only) or scale + centre crop,
+    resize, /255 and mean/std, as ONE kernel per item.  Decoding itself (decord) stays outside.
+
+    Use it through ``args.dataset_factory = lambda args, split, kind: DecodedVideoDataset(videos, labels, args, kind)``
+    with ``num_workers=0`` (the tensors live on the GPU).  TANet layouts and arithmetic only: the Video-Swin loader of the
+    reference resizes with mmcv / OpenCV, whose arithmetic differs (tools/cv2_linear_probe.py)."""
+
+    def __init__(self, videos, labels, args, dataset_type='tta', rng=_random):
+        if args.arch != 'tanet':
+            raise NotImplementedError("DecodedVideoDataset mirrors the TANet loader; the Swin loader's OpenCV resize is "
+                                      "not reproduced")
+        if len(videos) != len(labels):
+            raise _lib.VittaError("DecodedVideoDataset: %d videos, %d labels" % (len(videos), len(labels)))
+        if getattr(args, 'test_crops', 1) != 1:
+            raise NotImplementedError(f'{args.test_crops} spatial crops not implemented!')      # basics.py:1264-1267
+        self.videos, self.labels, self.args, self.rng = videos, labels, args, rng
+        self.sample_views = bool(args.if_sample_tta_aug_views) if dataset_type == 'tta' else False   # basics.py:1232-1238
+        self.rand_crop = bool(getattr(args, 'if_spatial_rand_cropping', True)) if self.sample_views else False
+        self.input_size = args.scale_size if getattr(args, 'full_res', False) else args.input_size  # basics.py:1230
+
+    def __len__(self):
+        return len(self.videos)
+
+    def plan(self, index):
+        """Host side of one item: (frame indices (V*T,), crop boxes or None).  Draw order as in the reference: the index
+        rule is deterministic, then one crop box per temporal view, view after view."""
+        a = self.args
+        f, h, w, _ = self.videos[index].shape
+        t = a.clip_length
+        if self.sample_views:
+            idx = np.concatenate([sample_tta_view_indices(f, t, a.n_augmented_views, style)
+                                  for style in a.tta_view_sample_style_list])
+        else:
+            kind, _, n = str(getattr(a, 'sample_style', 'uniform-1')).partition('-')       # video_dataset.py:270-303
+            if kind != 'uniform':
+                raise NotImplementedError("sample_style %r: only 'uniform-N' is mirrored" % (a.sample_style,))
+            n = int(n or 1)
+            idx = sample_tta_view_indices(f, t, n, 'uniform' if n == 1 else 'uniform_equidist')
+        boxes = None
+        if self.rand_crop:
+            if idx.size != a.n_augmented_views * t:        # the reference's transform asserts this (transforms.py:303)
+                raise _lib.VittaError("random cropping needs n_augmented_views * clip_length frames, got %d" % idx.size)
+            boxes = sample_view_crops(w, h, self.input_size, a.n_augmented_views, self.rng)
+        return idx, boxes
+
+    def __getitem__(self, index):
+        idx, boxes = self.plan(index)
+        a = self.args
+        mean = getattr(a, 'input_mean', synth.INPUT_MEAN)
+        std = getattr(a, 'input_std', synth.INPUT_STD)
+        if boxes is not None:
+            x = views_to_device(self.videos[index], idx, a.clip_length, 'tanet', mean=mean, std=std, boxes=boxes,
+                                out_size=self.input_size)
+        else:
+            x = views_to_device(self.videos[index], idx, a.clip_length, 'tanet', mean=mean, std=std,
+                                scale_size=a.scale_size, out_size=self.input_size)
+        return x, self.labels[index]
