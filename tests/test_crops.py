@@ -157,6 +157,56 @@ def test_views_to_device_has_no_cpu_path():
         views_to_device(torch.zeros(4, 48, 64, 3, dtype=torch.uint8), [0, 1], 2, boxes=[(32, 32, 0, 0)], out_size=32)
 
 
+def _emulate_kernel(frames, idx, t, hb, hk, vb, vk, slots, out_h, out_w, layout):
+    """numpy transcription of gather_crop_resize_kernel (preprocess.cu), index for index: per output pixel the <= slots
+    source rows are resampled horizontally to uint8, then combined vertically; planes ordered as the two loader layouts."""
+    f_total, h, w, _ = frames.shape
+    n = len(idx)
+    v_count = n // t
+    u8 = np.zeros((n, out_h, out_w, 3), np.int64)
+    for k in range(n):
+        v = k // t
+        f = min(max(int(idx[k]), 0), f_total - 1)
+        for y in range(out_h):
+            y0, ny = int(vb[v, y, 0]), min(int(vb[v, y, 1]), slots)
+            for x in range(out_w):
+                x0, nx = int(hb[v, x, 0]), min(int(hb[v, x, 1]), slots)
+                acc = np.full(3, 1 << 21, np.int64)
+                for yy in range(ny):
+                    sy = min(max(y0 + yy, 0), h - 1)
+                    hacc = np.full(3, 1 << 21, np.int64)
+                    for xx in range(nx):
+                        sx = min(max(x0 + xx, 0), w - 1)
+                        hacc += frames[f, sy, sx].astype(np.int64) * int(hk[v, x, xx])
+                    acc += np.clip(hacc >> 22, 0, 255) * int(vk[v, y, yy])
+                u8[k, y, x] = np.clip(acc >> 22, 0, 255)
+    if layout == 0:
+        return u8.transpose(0, 3, 1, 2).reshape(n * 3, out_h, out_w)                       # [view][frame][rgb] planes
+    return u8.reshape(v_count, t, out_h, out_w, 3).transpose(0, 4, 1, 2, 3)                # (V, 3, T, h, w)
+
+
+def test_kernel_index_arithmetic_emulated_against_oracle():
+    """The CUDA kernel cannot run here; its index arithmetic, transcribed to numpy, must reproduce the oracle through the
+    same tables the product uploads (crop offsets folded into the window starts, per-view table sets, both layouts)."""
+    from oracle import pil_resample as R
+    from vitta_b200.corpus.views import crop_resize_tables, scale_center_crop_tables
+    rng = np.random.Generator(np.random.PCG64(8))
+    frames = rng.integers(0, 256, (5, 30, 40, 3), dtype=np.uint8)
+    t, s = 2, 12
+    idx = np.asarray([0, 4, 2, 9])                                        # 9 is clamped to the last frame like the reference
+    boxes = [(26, 30, 12, 0), (19, 22, 3, 6)]
+    hb, hk, vb, vk, slots = crop_resize_tables(boxes, s, s)
+    want = R.crop_resize_views(frames, np.minimum(idx, 4), t, boxes, s)   # (V*T, s, s, 3)
+    got0 = _emulate_kernel(frames, idx, t, hb, hk, vb, vk, slots, s, s, 0)
+    assert (got0 == want.transpose(0, 3, 1, 2).reshape(-1, s, s)).all()
+    got1 = _emulate_kernel(frames, idx, t, hb, hk, vb, vk, slots, s, s, 1)
+    assert (got1 == want.reshape(2, t, s, s, 3).transpose(0, 4, 1, 2, 3)).all()
+    hb, hk, vb, vk, slots = scale_center_crop_tables(40, 30, 16, s, n_views=2)
+    want = np.stack([R.scale_center_crop_u8(frames[min(int(i), 4)], 16, s) for i in idx])
+    got = _emulate_kernel(frames, idx, t, hb, hk, vb, vk, slots, s, s, 0)
+    assert (got == want.transpose(0, 3, 1, 2).reshape(-1, s, s)).all()
+
+
 # ----------------------------------------------------------------------------------------------
 # whole loader items recorded from the unmodified reference (get_dataset_tanet -> Video_TANetDataSet.__getitem__ with an
 # in-memory decoder): tests/golden/loader.npz
