@@ -482,6 +482,16 @@ def run_views_case():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "views.npz"), **out)
     print("wrote views", len(out), "index vectors")
+    # the Video-Swin loader's clean evaluation clip (SampleFrames.get_seq_frames, test mode)
+    tb = importlib.import_module("models.videoswintransformer_models.transforms_backup")
+    seq = {}
+    for nf in (1, 2, 9, 16, 17, 31, 33, 64, 100, 177, 300):
+        for t in (8, 16, 32):
+            sf = object.__new__(tb.SampleFrames)
+            sf.clip_len, sf.test_mode = t, True
+            seq["%d/%d" % (nf, t)] = np.minimum(np.asarray(sf.get_seq_frames(nf)), nf - 1).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "swin_seq.npz"), **seq)
+    print("wrote swin_seq", len(seq), "index vectors")
 
 
 def run_crops_case():

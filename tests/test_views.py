@@ -20,6 +20,17 @@ def test_view_indices_match_reference_sampler():
         assert got.shape == want.shape and (got == want).all(), (key, got, want)   # index work: bit exact
 
 
+def test_swin_eval_clip_indices_match_reference_sampler():
+    """SampleFrames.get_seq_frames (test mode) of the reference's Video-Swin loader, 33 recorded vectors."""
+    from vitta_b200.corpus.views import swin_seq_frames
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "swin_seq.npz"))
+    assert len(g.files) == 33
+    for key in g.files:
+        nf, t = (int(v) for v in key.split("/"))
+        got = swin_seq_frames(nf, t)
+        assert got.shape == g[key].shape and (got == g[key]).all(), (key, got, g[key])
+
+
 def test_unknown_style_is_loud():
     from vitta_b200.corpus.views import sample_tta_view_indices
     with pytest.raises(NotImplementedError):

@@ -149,6 +149,16 @@ def scale_center_crop_tables(image_w, image_h, scale_size, input_size, n_views=1
     return (rep(hb[left:left + s]), rep(pad(hk)[left:left + s]), rep(vb[top:top + s]), rep(pad(vk)[top:top + s]), slots)
 
 
+def swin_seq_frames(num_frames, clip_len):
+    """Frame indices of the Video-Swin loader's clean evaluation clip (``SampleFrames.get_seq_frames`` in test mode,
+    models/videoswintransformer_models/transforms_backup.py:548-569; ``--frame_uniform``, its default): the middle frame of
+    each of ``clip_len`` segments of ``(num_frames - 1) / clip_len`` frames, segment borders rounded half to even
+    (``np.round``), then clamped to the last frame (:690)."""
+    seg = float(num_frames - 1) / clip_len
+    seq = [(int(np.round(seg * i)) + int(np.round(seg * (i + 1)))) // 2 for i in range(clip_len)]
+    return np.minimum(np.asarray(seq, dtype=np.int64), num_frames - 1)
+
+
 def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD,
                     boxes=None, out_size=None, scale_size=None):
     """frames_u8: (F, H, W, 3) uint8 CUDA tensor; indices: (V*T,) ints.  Returns the loader tensor of ONE video:
