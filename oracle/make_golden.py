@@ -575,12 +575,13 @@ def run_loader_case():
             for k, v in videos.items():
                 f.write("%s %d %d\n" % (k, len(v), labels[k]))
         for case, (kind, views, rand_crop, seed) in {"tta_randcrop": ("tta", 2, True, 31), "tta_center": ("tta", 2, False, 32),
-                                                    "eval": ("eval", 2, True, 33), "tta_3views": ("tta", 3, True, 34)}.items():
+                                                    "eval": ("eval", 2, True, 33), "tta_3views": ("tta", 3, True, 34),
+                                                    "tta_3crops": ("tta", 2, True, 35)}.items():
             args = ref["utils.opts"].parser.parse_args([])
             args.arch, args.modality, args.vid_format = "tanet", "RGB", ".mp4"
             args.val_vid_list, args.video_data_dir = lst, tmp
             args.clip_length, args.input_size, args.scale_size, args.full_res = 4, 32, 40, False
-            args.test_crops, args.sample_style, args.debug = 1, "uniform-1", False
+            args.test_crops, args.sample_style, args.debug = (3 if case == "tta_3crops" else 1), "uniform-1", False
             args.if_sample_tta_aug_views, args.n_augmented_views = True, views
             args.if_spatial_rand_cropping = rand_crop
             args.tta_view_sample_style_list = ["uniform_equidist"]
@@ -590,7 +591,8 @@ def run_loader_case():
                 x, y = ds[i]
                 out["%s/%s/x" % (case, name)] = x.numpy().astype(np.float32)
                 out["%s/%s/y" % (case, name)] = np.asarray(y, np.int64)
-            out["%s/meta" % case] = np.asarray([1 if kind == "tta" else 0, views, int(rand_crop), seed], np.int64)
+            out["%s/meta" % case] = np.asarray([1 if kind == "tta" else 0, views, int(rand_crop), seed, args.test_crops],
+                                               np.int64)
     for k, v in videos.items():
         out["video/%s" % k] = v
     np.savez_compressed(os.path.join(GOLDEN_DIR, "loader.npz"), **out)

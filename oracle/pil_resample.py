@@ -134,3 +134,18 @@ def scale_center_crop_u8(img, scale_size, input_size):
     h, w = img.shape[:2]
     top, left = int(round((h - input_size) / 2.)), int(round((w - input_size) / 2.))
     return img[top:top + input_size, left:left + input_size]
+
+
+def full_res_sample_u8(img, scale_size, input_size):
+    """GroupFullResSample_TANet(input_size, scale_size, flip=False) on one frame (transforms.py:227-272): the three crops
+    (left, right, centre) of the frame scaled to ``scale_size`` -> (3, S, S, 3) uint8."""
+    h, w = img.shape[:2]
+    if not ((w <= h and w == scale_size) or (h <= w and h == scale_size)):
+        if w < h:
+            img = resize_bilinear_u8(img, scale_size, int(scale_size * h / w))
+        else:
+            img = resize_bilinear_u8(img, int(scale_size * w / h), scale_size)
+    h, w = img.shape[:2]
+    ws, hs = (w - input_size) // 4, (h - input_size) // 4
+    return np.stack([img[oh:oh + input_size, ow:ow + input_size]
+                     for ow, oh in ((0, 2 * hs), (4 * ws, 2 * hs), (2 * ws, 2 * hs))])

@@ -205,6 +205,14 @@ def test_kernel_index_arithmetic_emulated_against_oracle():
     want = np.stack([R.scale_center_crop_u8(frames[min(int(i), 4)], 16, s) for i in idx])
     got = _emulate_kernel(frames, idx, t, hb, hk, vb, vk, slots, s, s, 0)
     assert (got == want.transpose(0, 3, 1, 2).reshape(-1, s, s)).all()
+    # --test_crops 3: every frame once per crop, tables as 3 * n_clips "views" (crop-major)
+    from vitta_b200.corpus.views import full_res_sample_tables
+    hb, hk, vb, vk, slots = full_res_sample_tables(40, 30, 16, s, n_clips=2)
+    assert hb.shape == (6, s, 2)
+    per = np.stack([R.full_res_sample_u8(frames[min(int(i), 4)], 16, s) for i in idx])     # (L, 3, s, s, 3)
+    want = per.transpose(1, 0, 2, 3, 4).reshape(-1, s, s, 3)
+    got = _emulate_kernel(frames, np.tile(idx, 3), t, hb, hk, vb, vk, slots, s, s, 0)
+    assert (got == want.transpose(0, 3, 1, 2).reshape(-1, s, s)).all()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -212,24 +220,27 @@ def test_kernel_index_arithmetic_emulated_against_oracle():
 # in-memory decoder): tests/golden/loader.npz
 # ----------------------------------------------------------------------------------------------
 LOADER = os.path.join(cases.GOLDEN_DIR, "loader.npz")
-LOADER_CASES = ["tta_randcrop", "tta_center", "eval", "tta_3views"]
+LOADER_CASES = ["tta_randcrop", "tta_center", "eval", "tta_3views", "tta_3crops"]
 
 
 def _loader_args(g, case):
     from vitta_b200.utils.opts import default_args
-    is_tta, views, rand_crop, seed = (int(v) for v in g[case + "/meta"])
+    is_tta, views, rand_crop, seed, test_crops = (int(v) for v in g[case + "/meta"])
     args = default_args(arch="tanet", clip_length=4, input_size=32, scale_size=40, n_augmented_views=views,
                         if_sample_tta_aug_views=True, if_spatial_rand_cropping=bool(rand_crop), num_classes=11,
-                        batch_size=1)
+                        batch_size=1, test_crops=test_crops)
     return args, ("tta" if is_tta else "eval"), seed
 
 
-def _oracle_item(frames, idx, boxes, t, scale_size, input_size):
+def _oracle_item(frames, idx, boxes, t, scale_size, input_size, three_crops=False):
     """uint8 frames -> the reference's loader tensor (V*T*3, S, S) through the oracle's spatial pipeline."""
     from oracle import pil_resample as R
     from vitta_b200 import synth
     if boxes is not None:
         u8 = R.crop_resize_views(frames, idx, t, boxes, input_size)
+    elif three_crops:         # [crop][frame]: all frames of the left crop, then right, then centre
+        per = np.stack([R.full_res_sample_u8(frames[int(i)], scale_size, input_size) for i in idx])    # (L, 3, S, S, 3)
+        u8 = per.transpose(1, 0, 2, 3, 4).reshape(-1, input_size, input_size, 3)
     else:
         u8 = np.stack([R.scale_center_crop_u8(frames[int(i)], scale_size, input_size) for i in idx])
     x = torch.from_numpy(u8).permute(0, 3, 1, 2).float().div(255)                  # ToTorchFormatTensor(div=True)
@@ -252,8 +263,9 @@ def test_dataset_plan_and_oracle_pipeline_match_reference_loader(case):
     for i, name in enumerate(("v0", "v1")):
         idx, boxes = ds.plan(i)
         want = g["%s/%s/x" % (case, name)]
-        assert (boxes is not None) == (kind == "tta" and args.if_spatial_rand_cropping)
-        got = _oracle_item(videos[i].numpy(), idx, boxes, args.clip_length, args.scale_size, args.input_size)
+        assert (boxes is not None) == (kind == "tta" and args.if_spatial_rand_cropping and args.test_crops == 1)
+        got = _oracle_item(videos[i].numpy(), idx, boxes, args.clip_length, args.scale_size, args.input_size,
+                           three_crops=args.test_crops == 3)
         assert got.shape == want.shape, (got.shape, want.shape)
         # same uint8 pixels, then the same two float ops: differences are a float32 ulp at most
         np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=2e-6)
@@ -268,7 +280,7 @@ def test_dataset_refuses_what_it_does_not_mirror():
     with pytest.raises(NotImplementedError):
         DecodedVideoDataset(vids, [0], default_args(arch="videoswintransformer"), "tta")
     with pytest.raises(NotImplementedError):
-        DecodedVideoDataset(vids, [0], default_args(arch="tanet", test_crops=3), "tta")
+        DecodedVideoDataset(vids, [0], default_args(arch="tanet", test_crops=5), "tta")
     with pytest.raises(_lib.VittaError):
         DecodedVideoDataset(vids, [0, 1], default_args(arch="tanet"), "tta")
     ds = DecodedVideoDataset(vids, [0], default_args(arch="tanet", sample_style="dense-1", clip_length=4), "eval")

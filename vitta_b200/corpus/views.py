@@ -149,6 +149,27 @@ def scale_center_crop_tables(image_w, image_h, scale_size, input_size, n_views=1
     return (rep(hb[left:left + s]), rep(pad(hk)[left:left + s]), rep(vb[top:top + s]), rep(pad(vk)[top:top + s]), slots)
 
 
+def full_res_sample_tables(image_w, image_h, scale_size, input_size, n_clips=1):
+    """GroupFullResSample_TANet(input_size, scale_size, flip=False) (transforms.py:227-272; ``--test_crops 3``,
+    corpus/basics.py:1264-1265): scale the smaller edge to scale_size, then THREE S x S crops at (0, 2h'), (4w', 2h'),
+    (2w', 2h') with w' = (W - S) // 4, h' = (H - S) // 4 -- left / right / centre.  The reference emits all frames of crop
+    0, then of crop 1, then of crop 2, so the tables come as 3 * n_clips "views": view j uses crop j // n_clips."""
+    ow, oh, _, _ = scale_center_crop_geometry(image_w, image_h, scale_size, input_size)
+    s = int(input_size)
+    ws, hs = (ow - s) // 4, (oh - s) // 4
+    hb, hk = resample_tables(image_w, ow)
+    vb, vk = resample_tables(image_h, oh)
+    slots = max(3, hk.shape[1], vk.shape[1])
+    pad = lambda k: np.pad(k, ((0, 0), (0, slots - k.shape[1])))
+    hk, vk = pad(hk), pad(vk)
+    out = [[], [], [], []]
+    for left, top in ((0, 2 * hs), (4 * ws, 2 * hs), (2 * ws, 2 * hs)):
+        for _ in range(n_clips):
+            for lst, a in zip(out, (hb[left:left + s], hk[left:left + s], vb[top:top + s], vk[top:top + s])):
+                lst.append(a)
+    return tuple(np.ascontiguousarray(np.stack(a)) for a in out) + (slots,)
+
+
 def swin_seq_frames(num_frames, clip_len):
     """Frame indices of the Video-Swin loader's clean evaluation clip (``SampleFrames.get_seq_frames`` in test mode,
     models/videoswintransformer_models/transforms_backup.py:548-569; ``--frame_uniform``, its default): the middle frame of
@@ -160,14 +181,15 @@ def swin_seq_frames(num_frames, clip_len):
 
 
 def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD,
-                    boxes=None, out_size=None, scale_size=None):
+                    boxes=None, out_size=None, scale_size=None, three_crops=False):
     """frames_u8: (F, H, W, 3) uint8 CUDA tensor; indices: (V*T,) ints.  Returns the loader tensor of ONE video:
     TANet ``(V*T*3, h, w)`` or Swin ``(V, 3, T, h, w)``, normalised fp32.  crop = (y, x, h, w) or None (whole frame).
     boxes = one (crop_w, crop_h, offset_w, offset_h) per view (``sample_view_crops``) + out_size = S (or (h, w)): every
     view is cropped with its own box and resized to S x S exactly as PIL's BILINEAR does (the reference's
     SubgroupWise_MultiScaleCrop_TANet); ``crop`` must then be None.
     scale_size = Z + out_size = S (no boxes): the reference's other spatial path, GroupScale(Z) + GroupCenterCrop(S)
-    (corpus/basics.py:1259-1263), same kernel, same PIL-exact arithmetic."""
+    (corpus/basics.py:1259-1263), same kernel, same PIL-exact arithmetic; with three_crops=True the reference's
+    ``--test_crops 3`` path (GroupFullResSample_TANet): output planes ordered [crop][clip][frame][rgb]."""
     if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
         raise _lib.VittaError("views_to_device: frames must be a (F, H, W, 3) uint8 CUDA tensor; there is no CPU path")
     frames_u8 = frames_u8.contiguous()
@@ -184,6 +206,12 @@ def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=
         if boxes is not None:
             oh, ow = (out_size, out_size) if isinstance(out_size, int) else out_size
             hb, hk, vb, vk, slots = crop_resize_tables(boxes, oh, ow)
+        elif three_crops:
+            oh = ow = int(out_size)
+            hb, hk, vb, vk, slots = full_res_sample_tables(w, h, scale_size, out_size, v)
+            idx = idx.repeat(3)                   # every frame once per crop: [crop][clip][frame]
+            n, v = 3 * n, 3 * v
+            boxes = [(w, h, 0, 0)] * v
         else:
             oh = ow = int(out_size)
             hb, hk, vb, vk, slots = scale_center_crop_tables(w, h, scale_size, out_size, v)
@@ -227,11 +255,13 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
                                       "not reproduced")
         if len(videos) != len(labels):
             raise _lib.VittaError("DecodedVideoDataset: %d videos, %d labels" % (len(videos), len(labels)))
-        if getattr(args, 'test_crops', 1) != 1:
+        if getattr(args, 'test_crops', 1) not in (1, 3):
             raise NotImplementedError(f'{args.test_crops} spatial crops not implemented!')      # basics.py:1264-1267
+        self.three_crops = getattr(args, 'test_crops', 1) == 3
         self.videos, self.labels, self.args, self.rng = videos, labels, args, rng
         self.sample_views = bool(args.if_sample_tta_aug_views) if dataset_type == 'tta' else False   # basics.py:1232-1238
-        self.rand_crop = bool(getattr(args, 'if_spatial_rand_cropping', True)) if self.sample_views else False
+        self.rand_crop = (bool(getattr(args, 'if_spatial_rand_cropping', True)) if self.sample_views else False) \
+            and not self.three_crops
         self.input_size = args.scale_size if getattr(args, 'full_res', False) else args.input_size  # basics.py:1230
 
     def __len__(self):
@@ -269,5 +299,5 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
                                 out_size=self.input_size)
         else:
             x = views_to_device(self.videos[index], idx, a.clip_length, 'tanet', mean=mean, std=std,
-                                scale_size=a.scale_size, out_size=self.input_size)
+                                scale_size=a.scale_size, out_size=self.input_size, three_crops=self.three_crops)
         return x, self.labels[index]
