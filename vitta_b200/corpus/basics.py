@@ -52,11 +52,15 @@ def _dataset(args, split, dataset_type):
                                  seed=getattr(args, 'synthetic_seed', 0), tag='tta')
 
 
-def get_dataset_tanet(args, split='val', dataset_type=None):
+def get_dataset_tanet(args, split='train', dataset_type=None):
+    if split == 'train':      # reference corpus/basics.py:1225-1226 (and its default): adaptation uses split='val' only
+        raise NotImplementedError('Training dataset processing for TANet to be added!')
     return _dataset(args, split, dataset_type)
 
 
-def get_dataset_videoswin(args, split='val', dataset_type=None):
+def get_dataset_videoswin(args, split='train', dataset_type=None):
+    if split == 'train':      # reference corpus/basics.py:1194-1195
+        raise NotImplementedError('Training dataset processing for Video Swin Transformer to be added!')
     return _dataset(args, split, dataset_type)
 
 
@@ -427,7 +431,7 @@ def compute_statistics(model=None, args=None, logger=None, log_time=None):
 
 
 @torch.no_grad()
-def validate(val_loader, model, criterion, iter=0, epoch=None, args=None, logger=None, writer=None):
+def validate(val_loader, model, criterion, iter=0, epoch=None, args=None, logger=None, writer=None, optimizer=None):
     """Source-only evaluation: model.eval() forward + accuracy (reference :149-217; config 1 of BASELINE.json)."""
     top1, top5, losses = AverageMeter(), AverageMeter(), AverageMeter()
     model.eval()
