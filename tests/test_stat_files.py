@@ -47,3 +47,26 @@ def test_in_memory_statistics_bypass_the_files():
     args = default_args(source_stats=(means, variances))
     got_m, got_v = basics.load_source_statistics(args)
     assert got_m[3] is means[3] and got_v[0] is variances[0]
+
+
+def test_all_result_file_has_the_reference_layout(tmp_path):
+    """utils/utils_.py:252-267 of the reference: path rule, 'name value' header of the public args, two separator lines,
+    two blank lines; accuracies are appended after that by the entry scripts."""
+    from vitta_b200.utils.opts import default_args
+    from vitta_b200.utils.utils_ import get_writer_to_all_result
+    args = default_args(arch="tanet", result_dir=str(tmp_path / "res" / "tta_gauss"))
+    f = get_writer_to_all_result(args)
+    f.write("12.5 13.0\n")
+    f.close()
+    import os
+    files = os.listdir(args.result_dir)
+    assert len(files) == 1 and files[0].endswith("_all_result") and len(files[0]) == len("20260101_000000_all_result")
+    lines = open(os.path.join(args.result_dir, files[0])).read().split("\n")
+    names = [a for a in dir(args) if a[0] != "_"]
+    assert [ln.split(" ")[0] for ln in lines[:len(names)]] == names
+    assert lines[names.index("arch")] == "arch tanet"
+    assert lines[len(names):len(names) + 5] == ["#" * 29, "#" * 29, "", "", "12.5 13.0"]
+    f = get_writer_to_all_result(args, custom_path=str(tmp_path / "custom"))
+    f.close()
+    (name,) = os.listdir(tmp_path / "custom")
+    assert name.startswith(str(args.baseline) + "_") and name.endswith("_all_result")

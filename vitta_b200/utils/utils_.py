@@ -89,8 +89,21 @@ def path_logger(result_dir, log_time):
 
 
 def get_writer_to_all_result(args, custom_path=None):
-    """One text line per corruption (reference :252-267)."""
+    """The per-run results file of the entry scripts (reference :252-267): ``<result_dir>/<time>_all_result`` (or
+    ``<custom_path>/<baseline>_<time>_all_result``) opened 'w+', a header with one ``name value`` line per public attribute
+    of ``args``, two separator lines and two blank lines; the caller then appends one line of accuracies per corruption."""
     log_time = time.strftime("%Y%m%d_%H%M%S")
-    base = custom_path if custom_path is not None else os.path.dirname(args.result_dir.rstrip("/"))
-    make_dir(base)
-    return open(os.path.join(base, f"{log_time}_all_result"), "w+")
+    if custom_path is None:
+        make_dir(args.result_dir)       # eval() normally created it already; the reference relies on that
+        f_write = open(os.path.join(args.result_dir, f'{log_time}_all_result'), 'w+')
+    else:
+        make_dir(custom_path)
+        f_write = open(os.path.join(custom_path, f'{args.baseline}_{log_time}_all_result'), 'w+')
+    for arg in dir(args):
+        if arg[0] != '_':
+            f_write.write(f'{arg} {getattr(args, arg)}\n')
+    f_write.write('#############################\n')
+    f_write.write('#############################\n')
+    f_write.write('\n')
+    f_write.write('\n')
+    return f_write
