@@ -97,6 +97,28 @@ def _worker(rank, world, port, out_dir):
     g_local, = torch.autograd.grad(yl, w, gy)
     (g_sum,), _ = ops.allreduce_grads([g_local], dist.group.WORLD)
     torch.testing.assert_close(g_sum, g_full, rtol=1e-4, atol=1e-7)
+    # ---- driver-level sharding (corpus.basics.tta_standard under torchrun): contiguous video blocks of every GLOBAL
+    #      batch, ragged tails split as evenly as possible, accuracy merged over all videos
+    from vitta_b200.corpus.basics import merge_meters, shard_batch
+    from vitta_b200.utils.utils_ import AverageMeter
+    meter = AverageMeter()
+    seen = []
+    for bz in (8, 5, 2, 3):
+        x = torch.arange(bz * 4.0).reshape(bz, 4)
+        y = torch.arange(bz)
+        xs, ys = shard_batch(x, y, rank, world)
+        assert xs.shape[0] == ys.shape[0] and (xs[:, 0] == ys * 4.0).all()          # videos stay with their labels
+        assert xs.shape[0] in (bz // world, bz // world + 1) and (rank != 0 or xs.shape[0] == (bz + 1) // world)
+        got = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(got, torch.tensor([xs.shape[0]]))
+        assert sum(int(g) for g in got) == bz                                        # every video exactly once
+        seen += ys.tolist()
+        # "accuracy" of the shard: share of even labels, weighted by the local video count like tta_standard does
+        if xs.shape[0]:
+            meter.update(100.0 * float((ys % 2 == 0).float().mean()), xs.shape[0])
+    (acc,) = merge_meters([meter], dist.group.WORLD)
+    want = 100.0 * sum(1 for bz in (8, 5, 2, 3) for v in range(bz) if v % 2 == 0) / 18
+    assert abs(acc - want) < 1e-5, (acc, want)       # shard accuracies are float32 means
     if rank == 0:
         open(os.path.join(out_dir, "ok"), "w").write("ok")
     dist.destroy_process_group()

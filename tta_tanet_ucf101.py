@@ -31,6 +31,8 @@ if __name__ == '__main__':
         args.val_vid_list = val_vid_list.format(args.corruptions)
         args.result_dir = result_dir.format(args.arch, args.dataset, args.corruptions)
         epoch_result_list, _ = eval(args=args)
+        if int(os.environ.get('RANK', '0')) != 0:
+            continue          # torchrun launch (videos sharded over the ranks): the merged accuracy is written once
         if corr_id == 0:
             f_write = get_writer_to_all_result(args)
         f_write.write(' '.join([str(round(float(xx), 3)) for xx in epoch_result_list]) + '\n')

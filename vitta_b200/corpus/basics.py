@@ -64,6 +64,31 @@ def get_dataset_videoswin(args, split='train', dataset_type=None):
     return _dataset(args, split, dataset_type)
 
 
+# ----------------------------------------------------------------------------------------------
+# video sharding across ranks (the reference itself is single-process)
+# ----------------------------------------------------------------------------------------------
+def shard_batch(input, target, rank, world):
+    """Rank r's videos of one GLOBAL loader batch: every rank iterates the same loader (same order, same batches as the
+    single-process run) and keeps a contiguous block of ``batch / world`` videos with all their views, so that the merged
+    statistics (collective C1) and summed gradients (C2) are those of the reference's full batch.  A ragged last batch is
+    split as evenly as possible (the first ``batch % world`` ranks take one more video); a rank may get none."""
+    bz = input.shape[0]
+    base, rem = divmod(bz, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return input[lo:hi], target[lo:hi]
+
+
+def merge_meters(meters, process_group):
+    """Global value of weighted-average meters whose per-rank weights are the local video counts: one all-reduce of
+    (sum, count) pairs.  Returns the list of global averages (identical on every rank)."""
+    import torch.distributed as dist
+    dev = 'cuda' if dist.get_backend(process_group) == 'nccl' else 'cpu'
+    buf = torch.tensor([[m.sum, m.count] for m in meters], dtype=torch.float64, device=dev)
+    dist.all_reduce(buf, group=process_group)
+    return [float(s / c) if c > 0 else 0.0 for s, c in buf.tolist()]
+
+
 def get_model(args, num_classes, logger=None):
     """reference :1447-1493 (only the two architectures ``--arch`` can select, utils/opts.py:43)."""
     if args.arch == 'tanet':
@@ -354,9 +379,18 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
     device = next(model_origin.parameters()).device
     adapter = None
     end = time.time()
+    pg = getattr(args, 'process_group', None)      # set by corpus.main_eval.eval under torchrun: shard the videos
+    if pg is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
     for batch_id, (input, target) in enumerate(tta_loader):
         if args.if_tta_standard == 'tta_standard' or batch_id == 0:
-            adapter = OnlineAdapter(model_origin, args, stats, getattr(args, 'process_group', None))
+            adapter = OnlineAdapter(model_origin, args, stats, pg)
+        if pg is not None:
+            if input.shape[0] < world:
+                raise RuntimeError("batch of %d videos cannot be sharded over %d ranks (every rank must take part in "
+                                   "the step's collectives)" % (input.shape[0], world))
+            input, target = shard_batch(input, target, rank, world)
         actual_bz = input.shape[0]
         input = input.to(device, non_blocking=True)
         target = target.to(device, non_blocking=True)
@@ -368,6 +402,8 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
             losses_consis.update(res['loss_consis'].item(), actual_bz)
         adapter.hooks_off()
         input, target = next(eval_iter)
+        if pg is not None:
+            input, target = shard_batch(input, target, rank, world)
         input, target = input.to(device, non_blocking=True), target.to(device, non_blocking=True)
         output = adapter.evaluate(input)
         prec1, prec5 = accuracy(output.data, target, topk=(1, 5))
@@ -384,6 +420,8 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
                          f'Loss consis {losses_consis.val:.4f} ({losses_consis.avg:.4f})\t'
                          f'Prec@1 {top1.val:.3f} ({top1.avg:.3f})\tPrec@5 {top5.val:.3f} ({top5.avg:.3f})')
     tta_standard.last_adapter = adapter
+    if pg is not None:       # accuracy over ALL videos, identical on every rank
+        return [merge_meters([top1], pg)[0]]
     return [top1.avg]
 
 

@@ -36,6 +36,23 @@ def load_checkpoint_into(model, args, logger=None):
     return model
 
 
+def _maybe_init_distributed(args):
+    """torchrun launch (WORLD_SIZE > 1): one process per GPU over NCCL; ``tta_standard`` then shards the videos of every
+    loader batch over the ranks and the step's two collectives keep statistics and weights identical everywhere
+    (DESIGN.md section 7).  The reference itself is single-process; without torchrun nothing here runs."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or getattr(args, 'process_group', None) is not None:
+        return
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args.process_group = dist.group.WORLD
+    args.gpus = [local]
+
+
 def eval(args=None, model=None):
     log_time = time.strftime("%Y%m%d_%H%M%S")
     make_dir(args.result_dir)
@@ -49,6 +66,7 @@ def eval(args=None, model=None):
     if not torch.cuda.is_available():
         raise RuntimeError("vitta_b200 needs a CUDA device (sm_100a); there is no CPU path")
     set_fp32_exact()
+    _maybe_init_distributed(args)
     if model is None:
         model = get_model(args, num_classes, logger)
         if getattr(args, 'model_path', None):
