@@ -482,6 +482,19 @@ def run_views_case():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "views.npz"), **out)
     print("wrote views", len(out), "index vectors")
+    # the random styles (one view per call) under a seeded numpy legacy generator
+    rnd = {}
+    for style in ("uniform_rand", "dense_rand", "random"):
+        for nf in (5, 9, 16, 31, 64, 100, 177, 300):
+            for t in (8, 16, 32):
+                ds = object.__new__(vd.Video_TANetDataSet)
+                ds.num_segments, ds.new_length, ds.n_tta_aug_views = t, 1, 1
+                np.random.seed(nf * 100 + t)
+                a = np.asarray(ds._sample_tta_augmented_views(Rec(nf), style))
+                b = np.asarray(ds._sample_tta_augmented_views(Rec(nf), style))       # second draw from the same stream
+                rnd["%s/%d/%d" % (style, nf, t)] = np.minimum(np.stack([a, b]), nf - 1).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "views_rand.npz"), **rnd)
+    print("wrote views_rand", len(rnd), "index arrays")
     # the Video-Swin loader's clean evaluation clip (SampleFrames.get_seq_frames, test mode)
     tb = importlib.import_module("models.videoswintransformer_models.transforms_backup")
     seq = {}

@@ -31,10 +31,27 @@ def test_swin_eval_clip_indices_match_reference_sampler():
         assert got.shape == g[key].shape and (got == g[key]).all(), (key, got, g[key])
 
 
+def test_random_view_styles_match_reference_sampler_under_the_same_seed():
+    """uniform_rand / dense_rand / random (video_dataset.py:197-229): same numpy legacy-generator calls in the same order,
+    so a seeded stream gives the reference's indices -- two consecutive draws per case, 72 cases."""
+    from vitta_b200.corpus.views import sample_tta_view_indices
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "views_rand.npz"))
+    assert len(g.files) == 3 * 8 * 3
+    for key in g.files:
+        style, nf, t = key.split("/")
+        rs = np.random.RandomState(int(nf) * 100 + int(t))
+        got = np.stack([sample_tta_view_indices(int(nf), int(t), 1, style, np_rng=rs) for _ in range(2)])
+        assert got.shape == g[key].shape and (got == g[key]).all(), (key, got, g[key])
+    np.random.seed(7)                                             # the module-level generator is the default, as in the reference
+    a = sample_tta_view_indices(100, 16, 1, "uniform_rand")
+    b = sample_tta_view_indices(100, 16, 1, "uniform_rand", np_rng=np.random.RandomState(7))
+    assert (a == b).all()
+
+
 def test_unknown_style_is_loud():
     from vitta_b200.corpus.views import sample_tta_view_indices
     with pytest.raises(NotImplementedError):
-        sample_tta_view_indices(100, 16, 2, "uniform_rand")
+        sample_tta_view_indices(100, 16, 2, "uniform_jitter")
 
 
 @pytest.mark.gpu

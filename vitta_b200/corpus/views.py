@@ -23,11 +23,36 @@ from .. import _lib, synth
 from .._lib import call, ptr, stream_ptr
 
 DETERMINISTIC_STYLES = ("uniform", "dense", "uniform_equidist", "dense_equidist")
+RANDOM_STYLES = ("uniform_rand", "dense_rand", "random")        # one view per call, drawn from numpy's legacy generator
 
 
-def sample_tta_view_indices(num_frames, num_segments, n_views=2, style="uniform_equidist", new_length=1):
-    """Frame indices (0-based into the decoded video) of all views, concatenated view after view: (n_views * T,)."""
+def sample_tta_view_indices(num_frames, num_segments, n_views=2, style="uniform_equidist", new_length=1, np_rng=np.random):
+    """Frame indices (0-based into the decoded video) of all views, concatenated view after view: (n_views * T,).
+    The random styles (video_dataset.py:197-229) give ONE view per call (the reference lists a style once per view) and
+    draw from ``np_rng`` -- the ``numpy.random`` module like the reference, or a ``RandomState`` -- with the same calls in
+    the same order, so ``np.random.seed(s)`` reproduces the reference's indices."""
     t = int(num_segments)
+    if style in RANDOM_STYLES:
+        if style == "uniform_rand":       # one random frame from each of T equal segments
+            avg = (num_frames - new_length + 1) // t
+            if avg > 0:
+                offs = np.multiply(list(range(t)), avg) + np_rng.randint(avg, size=t)
+            elif num_frames > t:          # too short to segment: T sorted draws with replacement
+                offs = np.sort(np_rng.randint(num_frames - new_length + 1, size=t))
+            else:
+                offs = np.zeros((t,))
+            idx = np.asarray(offs).astype(np.int64) + 1
+        elif style == "dense_rand":       # stride 64 // T from a random start
+            stride = 64 // t
+            pos = max(1, 1 + num_frames - stride * t)
+            start = 0 if pos == 1 else int(np_rng.randint(0, pos - 1))
+            idx = np.asarray([(i * stride + start) % num_frames for i in range(t)], dtype=np.int64) + 1
+        else:                             # 'random': T distinct frames, sorted -- and NO +1 in the reference (:221-229)
+            if num_frames >= t:
+                idx = np.sort(np_rng.choice(num_frames, size=t, replace=False)).astype(np.int64)
+            else:
+                idx = np.asarray(list(range(num_frames)) + [num_frames - 1] * (t - num_frames), dtype=np.int64)
+        return np.minimum(idx, num_frames - 1)
     if style == "uniform":            # middle frame of each of T equal segments, one view
         tick = (num_frames - new_length + 1) / float(t)
         offs = [int(tick / 2.0 + tick * x) for x in range(t)]
@@ -46,7 +71,7 @@ def sample_tta_view_indices(num_frames, num_segments, n_views=2, style="uniform_
         starts = np.linspace(0, pos - 1, num=n_views, dtype=int).tolist()
         offs = [(i * stride + s) % num_frames for s in starts for i in range(t)]
     else:
-        raise NotImplementedError("style %r: only the deterministic styles %s are mirrored" % (style, DETERMINISTIC_STYLES))
+        raise NotImplementedError("style %r: the reference defines %s" % (style, DETERMINISTIC_STYLES + RANDOM_STYLES))
     idx = np.asarray(offs, dtype=np.int64) + 1                  # the reference's 1-based offsets ...
     return np.minimum(idx, num_frames - 1)                      # ... used as 0-based indices, clamped (:328)
 
