@@ -482,6 +482,16 @@ def run_views_case():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "views.npz"), **out)
     print("wrote views", len(out), "index vectors")
+    # evaluation clips: _get_test_indices for --sample_style uniform-N / dense-N
+    tst = {}
+    for style in ("uniform-1", "uniform-3", "dense-1", "dense-2", "dense-4"):
+        for nf in (5, 9, 16, 31, 64, 100, 177, 300):
+            for t in (8, 16, 32):
+                ds = object.__new__(vd.Video_TANetDataSet)
+                ds.num_segments, ds.new_length, ds.test_sample = t, 1, style
+                tst["%s/%d/%d" % (style, nf, t)] = np.minimum(np.asarray(ds._get_test_indices(Rec(nf))), nf - 1).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "test_indices.npz"), **tst)
+    print("wrote test_indices", len(tst), "index vectors")
     # the random styles (one view per call) under a seeded numpy legacy generator
     rnd = {}
     for style in ("uniform_rand", "dense_rand", "random"):

@@ -283,7 +283,7 @@ def test_dataset_refuses_what_it_does_not_mirror():
         DecodedVideoDataset(vids, [0], default_args(arch="tanet", test_crops=5), "tta")
     with pytest.raises(_lib.VittaError):
         DecodedVideoDataset(vids, [0, 1], default_args(arch="tanet"), "tta")
-    ds = DecodedVideoDataset(vids, [0], default_args(arch="tanet", sample_style="dense-1", clip_length=4), "eval")
+    ds = DecodedVideoDataset(vids, [0], default_args(arch="tanet", sample_style="random-1", clip_length=4), "eval")
     with pytest.raises(NotImplementedError):
         ds.plan(0)
 

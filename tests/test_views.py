@@ -48,6 +48,19 @@ def test_random_view_styles_match_reference_sampler_under_the_same_seed():
     assert (a == b).all()
 
 
+def test_evaluation_clip_indices_match_reference():
+    """Video_TANetDataSet._get_test_indices for --sample_style uniform-N / dense-N: 120 recorded vectors."""
+    from vitta_b200.corpus.views import test_clip_indices
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "test_indices.npz"))
+    assert len(g.files) == 5 * 8 * 3
+    for key in g.files:
+        style, nf, t = key.split("/")
+        got = test_clip_indices(int(nf), int(t), style)
+        assert got.shape == g[key].shape and (got == g[key]).all(), (key, got, g[key])
+    with pytest.raises(NotImplementedError):
+        test_clip_indices(100, 16, "random-1")
+
+
 def test_unknown_style_is_loud():
     from vitta_b200.corpus.views import sample_tta_view_indices
     with pytest.raises(NotImplementedError):

@@ -195,6 +195,20 @@ def full_res_sample_tables(image_w, image_h, scale_size, input_size, n_clips=1):
     return tuple(np.ascontiguousarray(np.stack(a)) for a in out) + (slots,)
 
 
+def test_clip_indices(num_frames, num_segments, sample_style="uniform-1"):
+    """``Video_TANetDataSet._get_test_indices`` (video_dataset.py:270-303) for ``--sample_style`` 'uniform-N' / 'dense-N':
+    the same formulas as the deterministic TTA styles -- N = 1: 'uniform' / 'dense', N > 1: the equidistant variants with N
+    clips -- followed by the loader's clamp to the last frame (:328)."""
+    kind, _, n = str(sample_style).partition('-')
+    n = int(n or 1)
+    if kind not in ("uniform", "dense"):
+        raise NotImplementedError("{} not exist".format(sample_style))       # the reference's message (:303)
+    return sample_tta_view_indices(num_frames, num_segments, n, kind if n == 1 else kind + "_equidist")
+
+
+test_clip_indices.__test__ = False      # not a pytest test, whatever module imports it
+
+
 def swin_seq_frames(num_frames, clip_len):
     """Frame indices of the Video-Swin loader's clean evaluation clip (``SampleFrames.get_seq_frames`` in test mode,
     models/videoswintransformer_models/transforms_backup.py:548-569; ``--frame_uniform``, its default): the middle frame of
@@ -302,11 +316,7 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
             idx = np.concatenate([sample_tta_view_indices(f, t, a.n_augmented_views, style)
                                   for style in a.tta_view_sample_style_list])
         else:
-            kind, _, n = str(getattr(a, 'sample_style', 'uniform-1')).partition('-')       # video_dataset.py:270-303
-            if kind != 'uniform':
-                raise NotImplementedError("sample_style %r: only 'uniform-N' is mirrored" % (a.sample_style,))
-            n = int(n or 1)
-            idx = sample_tta_view_indices(f, t, n, 'uniform' if n == 1 else 'uniform_equidist')
+            idx = test_clip_indices(f, t, getattr(a, 'sample_style', 'uniform-1'))
         boxes = None
         if self.rand_crop:
             if idx.size != a.n_augmented_views * t:        # the reference's transform asserts this (transforms.py:303)
