@@ -513,6 +513,13 @@ def run_views_case():
             sf = object.__new__(tb.SampleFrames)
             sf.clip_len, sf.test_mode = t, True
             seq["%d/%d" % (nf, t)] = np.minimum(np.asarray(sf.get_seq_frames(nf)), nf - 1).astype(np.int64)
+    # RandomResizedCrop.get_crop_bbox under seeded numpy + random generators (8 consecutive boxes per frame size)
+    import random
+    for ih, iw in ((256, 341), (256, 455), (256, 256), (341, 256), (64, 85), (120, 30)):
+        np.random.seed(ih * 7 + iw)
+        random.seed(ih * 7 + iw)
+        seq["bbox/%d/%d" % (ih, iw)] = np.asarray(
+            [tb.RandomResizedCrop.get_crop_bbox((ih, iw), (0.08, 1.0), (3 / 4, 4 / 3)) for _ in range(8)], np.int64)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "swin_seq.npz"), **seq)
     print("wrote swin_seq", len(seq), "index vectors")
 

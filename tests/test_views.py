@@ -24,8 +24,9 @@ def test_swin_eval_clip_indices_match_reference_sampler():
     """SampleFrames.get_seq_frames (test mode) of the reference's Video-Swin loader, 33 recorded vectors."""
     from vitta_b200.corpus.views import swin_seq_frames
     g = np.load(os.path.join(cases.GOLDEN_DIR, "swin_seq.npz"))
-    assert len(g.files) == 33
-    for key in g.files:
+    keys = [k for k in g.files if not k.startswith("bbox/")]
+    assert len(keys) == 33
+    for key in keys:
         nf, t = (int(v) for v in key.split("/"))
         got = swin_seq_frames(nf, t)
         assert got.shape == g[key].shape and (got == g[key]).all(), (key, got, g[key])
@@ -46,6 +47,24 @@ def test_random_view_styles_match_reference_sampler_under_the_same_seed():
     a = sample_tta_view_indices(100, 16, 1, "uniform_rand")
     b = sample_tta_view_indices(100, 16, 1, "uniform_rand", np_rng=np.random.RandomState(7))
     assert (a == b).all()
+
+
+def test_swin_random_resized_crop_boxes_match_reference():
+    """RandomResizedCrop.get_crop_bbox of the Video-Swin loader: seeded numpy + random generators, 8 consecutive boxes for
+    each of 6 frame sizes (one of them so elongated that the centred-square fallback is hit)."""
+    import random
+    from vitta_b200.corpus.views import swin_center_crop_box, swin_random_resized_crop_bbox, swin_rescale_size
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "swin_seq.npz"))
+    keys = [k for k in g.files if k.startswith("bbox/")]
+    assert len(keys) == 6
+    for key in keys:
+        _, ih, iw = key.split("/")
+        ih, iw = int(ih), int(iw)
+        nrs, prs = np.random.RandomState(ih * 7 + iw), random.Random(ih * 7 + iw)
+        got = np.asarray([swin_random_resized_crop_bbox(ih, iw, np_rng=nrs, py_rng=prs) for _ in range(8)])
+        assert (got == g[key]).all(), (key, got, g[key])
+    assert swin_center_crop_box(341, 256, 224) == (58, 16, 282, 240)
+    assert swin_rescale_size(320, 240, 256) == (341, 256) and swin_rescale_size(240, 320, 256) == (256, 341)
 
 
 def test_evaluation_clip_indices_match_reference():

@@ -219,6 +219,45 @@ def swin_seq_frames(num_frames, clip_len):
     return np.minimum(np.asarray(seq, dtype=np.int64), num_frames - 1)
 
 
+# ---- host-side geometry of the Video-Swin loader (models/videoswintransformer_models/video_dataset.py:66-101): the boxes
+# ---- only -- its mmcv / OpenCV resize arithmetic is not on the device yet (tools/cv2_linear_probe.py)
+def swin_rescale_size(image_w, image_h, short_edge):
+    """``Resize(scale=(-1, short_edge))`` (transforms_backup.py:772-790,834-835): mmcv.rescale_size with the long edge
+    unbounded -- factor = short_edge / min(h, w), new size = int(x * factor + 0.5).  mmcv (pinned 1.3.12,
+    requirements.txt:25) is not under /root/reference and not installed: its published rule is restated, parity unpinned."""
+    factor = float(short_edge) / min(image_h, image_w)
+    return int(image_w * factor + 0.5), int(image_h * factor + 0.5)
+
+
+def swin_center_crop_box(image_w, image_h, crop_size):
+    """``CenterCrop`` (transforms_backup.py:897-915): (left, top, right, bottom) with floor-halved margins."""
+    left, top = (image_w - crop_size) // 2, (image_h - crop_size) // 2
+    return left, top, left + crop_size, top + crop_size
+
+
+def swin_random_resized_crop_bbox(image_h, image_w, area_range=(0.08, 1.0), aspect_ratio_range=(3 / 4, 4 / 3),
+                                  max_attempts=10, np_rng=np.random, py_rng=_random):
+    """``RandomResizedCrop.get_crop_bbox`` (transforms_backup.py:223-272): ten log-uniform aspect ratios and ten uniform
+    areas from numpy's generator, the first candidate that fits placed with two ``random.randint`` draws, else the centred
+    square.  One box per VIDEO (all frames of all views share it, :274-281).  Same calls in the same order as the reference,
+    so seeding both generators reproduces its boxes.  Returns (left, top, right, bottom)."""
+    area = image_h * image_w
+    min_ar, max_ar = aspect_ratio_range
+    ratios = np.exp(np_rng.uniform(np.log(min_ar), np.log(max_ar), size=max_attempts))
+    areas = np_rng.uniform(*area_range, size=max_attempts) * area
+    cand_w = np.round(np.sqrt(areas * ratios)).astype(np.int32)
+    cand_h = np.round(np.sqrt(areas / ratios)).astype(np.int32)
+    for i in range(max_attempts):
+        cw, ch = int(cand_w[i]), int(cand_h[i])
+        if ch <= image_h and cw <= image_w:
+            x = py_rng.randint(0, image_w - cw)
+            y = py_rng.randint(0, image_h - ch)
+            return x, y, x + cw, y + ch
+    size = min(image_h, image_w)
+    x, y = (image_w - size) // 2, (image_h - size) // 2
+    return x, y, x + size, y + size
+
+
 def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=synth.INPUT_MEAN, std=synth.INPUT_STD,
                     boxes=None, out_size=None, scale_size=None, three_crops=False):
     """frames_u8: (F, H, W, 3) uint8 CUDA tensor; indices: (V*T,) ints.  Returns the loader tensor of ONE video:
