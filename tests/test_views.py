@@ -51,7 +51,7 @@ def test_random_view_styles_match_reference_sampler_under_the_same_seed():
 
 def test_swin_random_resized_crop_boxes_match_reference():
     """RandomResizedCrop.get_crop_bbox of the Video-Swin loader: seeded numpy + random generators, 8 consecutive boxes for
-    each of 6 frame sizes (one of them so elongated that the centred-square fallback is hit)."""
+    each of 6 frame sizes (landscape, portrait, square, and a very elongated one where most candidates are rejected)."""
     import random
     from vitta_b200.corpus.views import swin_center_crop_box, swin_random_resized_crop_bbox, swin_rescale_size
     g = np.load(os.path.join(cases.GOLDEN_DIR, "swin_seq.npz"))
