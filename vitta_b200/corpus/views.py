@@ -224,7 +224,7 @@ def swin_seq_frames(num_frames, clip_len):
 def swin_rescale_size(image_w, image_h, short_edge):
     """``Resize(scale=(-1, short_edge))`` (transforms_backup.py:772-790,834-835): mmcv.rescale_size with the long edge
     unbounded -- factor = short_edge / min(h, w), new size = int(x * factor + 0.5).  mmcv (pinned 1.3.12,
-    requirements.txt:25) is not under /root/reference and not installed: its published rule is restated, parity unpinned."""
+    requirements.txt:25) is neither part of the reference tree nor installed: its published rule is restated, parity unpinned."""
     factor = float(short_edge) / min(image_h, image_w)
     return int(image_w * factor + 0.5), int(image_h * factor + 0.5)
 
