@@ -424,6 +424,27 @@ int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int F, int H, i
                                           const float* mean3_host, const float* std3_host, int layout, int T, float* out,
                                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The Video-Swin loader's resize: OpenCV's 8-bit INTER_LINEAR, bit exact (Swin side).
+ *   replaces: Resize._resize_imgs -> mmcv.imresize -> cv2.resize(INTER_LINEAR) (models/videoswintransformer_models/
+ *             transforms_backup.py:794-798, pipeline video_dataset.py:66-101) and Normalize -> mmcv.imnormalize_ (:1151-1166).
+ * vitta_cv_linear_tables is HOST-ONLY: per output position the first tap and the two 11-bit weights of one axis
+ *   (ofs_host [dst], w_host [dst][2]); horizontal != 0 applies OpenCV's left / right border rule, the vertical pass clips
+ *   row indices in the kernel instead.
+ * vitta_cv_resize_u8: region (x0, y0, cw, ch) of frame idx[k] (idx NULL: frame k) of src (F, H, W, 3) uint8 ->
+ *   out (n, out_h, out_w, 3) uint8; tables built for cw -> out_w and ch -> out_h.
+ * vitta_cv_resize_normalize_u8: the same resize, then (x - mean) * (1 / std) with HOST mean / std on the 0..255 scale
+ *   (utils/opts.py:8-9), written as layout 1 (V, 3, T, h, w) (FormatShape 'NCTHW') or layout 0 (TANet planes).
+ * ---------------------------------------------------------------------------------------------- */
+int vitta_cv_linear_tables(int src, int dst, int horizontal, int32_t* ofs_host, int32_t* w_host);
+int vitta_cv_resize_u8(const uint8_t* src, int F, int H, int W, const int32_t* idx, int n, int x0, int y0, int cw, int ch,
+                       const int32_t* xofs, const int32_t* xw, const int32_t* yofs, const int32_t* yw, int out_h, int out_w,
+                       uint8_t* out, void* stream);
+int vitta_cv_resize_normalize_u8(const uint8_t* src, int F, int H, int W, const int32_t* idx, int n, int x0, int y0, int cw,
+                                 int ch, const int32_t* xofs, const int32_t* xw, const int32_t* yofs, const int32_t* yw,
+                                 int out_h, int out_w, const float* mean3_host, const float* std3_host, int layout, int T,
+                                 float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

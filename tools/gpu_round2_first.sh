@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 # 1. fp16-split GEMM / conv / dgrad kernels against float64 (and against the tf32 kernels)
 VITTA_TEST_F16X3=1 timeout 900 python -m pytest tests/test_gpu_gemm_f16.py -q -x > gpurun_out/f16_tests.log 2>&1; echo "f16 tests rc=$?"; tail -5 gpurun_out/f16_tests.log
 # 2. option-mode goldens and the live-target BNS test that round 1 could only pin on the CPU oracle
-VITTA_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_kernels.py tests/test_gpu_swin.py tests/test_crops.py -q -k "option_modes or live_running or crop_resize_vs_oracle or scale_center_crop_vs_oracle or reference_loader_golden" > gpurun_out/unverified_tests.log 2>&1; echo "unverified rc=$?"; tail -5 gpurun_out/unverified_tests.log
+VITTA_TEST_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_kernels.py tests/test_gpu_swin.py tests/test_crops.py tests/test_swin_loader.py -q -k "swin_views_to_device or option_modes or live_running or crop_resize_vs_oracle or scale_center_crop_vs_oracle or reference_loader_golden" > gpurun_out/unverified_tests.log 2>&1; echo "unverified rc=$?"; tail -5 gpurun_out/unverified_tests.log
 # 3. whole-model parity with the fp16 split routed in (forward + data gradient; weight gradient stays tf32)
 VITTA_GEMM_PRECISION=f16x3 timeout 1200 python -m pytest tests/test_gpu_tanet.py tests/test_gpu_swin.py -q > gpurun_out/f16_models.log 2>&1; echo "f16 models rc=$?"; tail -5 gpurun_out/f16_models.log
 # 3b. CTA pairs on for the whole model (tf32 split), only if their unit tests passed above

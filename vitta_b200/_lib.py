@@ -109,6 +109,12 @@ _SIGNATURES = {
                                                         C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                                         C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, _P,
                                                         _P]),
+    "vitta_cv_linear_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vitta_cv_resize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
+                                     _P, _P, C.c_int, C.c_int, _P, _P]),
+    "vitta_cv_resize_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                               C.c_int, C.c_int, _P, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }

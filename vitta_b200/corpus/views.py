@@ -314,6 +314,62 @@ def views_to_device(frames_u8, indices, clip_len, arch="tanet", crop=None, mean=
     return out
 
 
+def cv_linear_tables(src, dst, horizontal):
+    """OpenCV INTER_LINEAR taps of one axis (host arithmetic in the library): (ofs (dst,) int32, w (dst, 2) int32)."""
+    ofs = np.zeros(dst, np.int32)
+    w = np.zeros((dst, 2), np.int32)
+    _lib.check(_lib.load().vitta_cv_linear_tables(int(src), int(dst), 1 if horizontal else 0,
+                                                  ofs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  w.ctypes.data_as(C.POINTER(C.c_int32))), "vitta_cv_linear_tables")
+    return ofs, w
+
+
+SWIN_MEAN_255 = (123.675, 116.28, 103.53)       # utils/opts.py:8-9 (img_norm_cfg, 0..255 scale)
+SWIN_STD_255 = (58.395, 57.12, 57.375)
+
+
+def swin_views_to_device(frames_u8, indices, clip_len, scale_size, input_size, bbox=None, mean=SWIN_MEAN_255,
+                         std=SWIN_STD_255):
+    """The Video-Swin loader's item from decoded frames on the device (video_dataset.py:66-101): frames[indices] ->
+    ``Resize(scale=(-1, scale_size))`` -> evaluation: ``CenterCrop(input_size)``; TTA views: crop ``bbox`` (left, top,
+    right, bottom in the resized frame; ``swin_random_resized_crop_bbox``) + ``Resize((S, S), keep_ratio=False)`` ->
+    ``Normalize`` -> ``FormatShape('NCTHW')``: (V, 3, T, S, S) fp32.  Resizes are OpenCV's INTER_LINEAR, bit exact."""
+    if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+        raise _lib.VittaError("swin_views_to_device: frames must be a (F, H, W, 3) uint8 CUDA tensor; there is no CPU path")
+    frames_u8 = frames_u8.contiguous()
+    dev = frames_u8.device
+    f, h, w, _ = frames_u8.shape
+    idx = torch.as_tensor(np.asarray(indices, dtype=np.int32)).to(dev)
+    n = idx.numel()
+    if n % clip_len:
+        raise _lib.VittaError("swin_views_to_device: %d indices are not a multiple of clip_len %d" % (n, clip_len))
+    v, s = n // clip_len, int(input_size)
+    nw, nh = swin_rescale_size(w, h, scale_size)
+    up = lambda a: torch.from_numpy(a).to(dev)
+    xo, xw = cv_linear_tables(w, nw, True)
+    yo, yw = cv_linear_tables(h, nh, False)
+    big = torch.empty((n, nh, nw, 3), dtype=torch.uint8, device=dev)
+    t1 = [up(a) for a in (xo, xw, yo, yw)]
+    call("vitta_cv_resize_u8", ptr(frames_u8), f, h, w, ptr(idx), n, 0, 0, w, h, ptr(t1[0]), ptr(t1[1]), ptr(t1[2]),
+         ptr(t1[3]), nh, nw, ptr(big), stream_ptr())
+    out = torch.empty((v, 3, clip_len, s, s), dtype=torch.float32, device=dev)
+    m3 = (C.c_float * 3)(*[float(x) for x in mean])
+    s3 = (C.c_float * 3)(*[float(x) for x in std])
+    if bbox is None:
+        left, top, right, bottom = swin_center_crop_box(nw, nh, s)
+        if left < 0 or top < 0:
+            raise _lib.VittaError("swin_views_to_device: %dx%d is smaller than the %d crop" % (nw, nh, s))
+    else:
+        left, top, right, bottom = (int(x) for x in bbox)
+    cw, ch = right - left, bottom - top
+    xo, xw = cv_linear_tables(cw, s, True)         # identity taps when the crop already has the target size
+    yo, yw = cv_linear_tables(ch, s, False)
+    t2 = [up(a) for a in (xo, xw, yo, yw)]
+    call("vitta_cv_resize_normalize_u8", ptr(big), n, nh, nw, None, n, left, top, cw, ch, ptr(t2[0]), ptr(t2[1]),
+         ptr(t2[2]), ptr(t2[3]), s, s, m3, s3, 1, int(clip_len), ptr(out), stream_ptr())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # the reference's TANet dataset item, from decoded frames that are already on the device
 # ----------------------------------------------------------------------------------------------

@@ -112,6 +112,63 @@ __global__ void __launch_bounds__(256) gather_crop_resize_kernel(
   }
 }
 
+// ---- OpenCV's 8-bit INTER_LINEAR (the Video-Swin loader's mmcv.imresize, transforms_backup.py:794-798) ----
+// Bit-exact restatement of resize.cpp's fixed-point path (oracle/cv2_resample.py has the derivation): 11-bit weights, the
+// horizontal pass keeps 32-bit sums, rows clipped (not re-weighted) at the top / bottom, and the vertical combine
+// ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  The source is the region (x0, y0, cw, ch) of frame
+// idx[k] (or frame k); tables from vitta_cv_linear_tables.  OUT_F32: normalise like mmcv.imnormalize_ ((x - mean) * 1/std
+// on the 0..255 scale) and write the Swin loader layout (V, 3, T, h, w) or the TANet one; else write uint8 (n, h, w, 3).
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) cv_resize_kernel(const uint8_t* __restrict__ src, int F, int H, int W,
+                                                       const int32_t* __restrict__ idx, int n, int x0, int y0, int cw, int ch,
+                                                       const int32_t* __restrict__ xofs, const int32_t* __restrict__ xw,
+                                                       const int32_t* __restrict__ yofs, const int32_t* __restrict__ yw,
+                                                       int out_h, int out_w, float3 mean, float3 stdinv, int layout, int T,
+                                                       void* __restrict__ out_) {
+  const int64_t plane = (int64_t)out_h * out_w;
+  const int64_t total = (int64_t)n * plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int k = (int)(i / plane);
+    const int64_t px = i - (int64_t)k * plane;
+    const int y = (int)(px / out_w), x = (int)(px - (int64_t)y * out_w);
+    int f = idx ? __ldg(idx + k) : k;
+    f = f < 0 ? 0 : (f >= F ? F - 1 : f);
+    const int sy = __ldg(yofs + y), sx = __ldg(xofs + x);
+    const int r0 = y0 + min(max(sy, 0), ch - 1), r1 = y0 + min(max(sy + 1, 0), ch - 1);
+    const int c0 = x0 + min(max(sx, 0), cw - 1), c1 = x0 + min(max(sx + 1, 0), cw - 1);
+    const int a0 = __ldg(xw + 2 * x), a1 = __ldg(xw + 2 * x + 1), b0 = __ldg(yw + 2 * y), b1 = __ldg(yw + 2 * y + 1);
+    const uint8_t* fr = src + (int64_t)f * H * W * 3;
+    const uint8_t* p00 = fr + ((int64_t)r0 * W + c0) * 3;
+    const uint8_t* p01 = fr + ((int64_t)r0 * W + c1) * 3;
+    const uint8_t* p10 = fr + ((int64_t)r1 * W + c0) * 3;
+    const uint8_t* p11 = fr + ((int64_t)r1 * W + c1) * 3;
+    int v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int s0 = (int)p00[c] * a0 + (int)p01[c] * a1;
+      const int s1 = (int)p10[c] * a0 + (int)p11[c] * a1;
+      const int o = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+      v[c] = o < 0 ? 0 : (o > 255 ? 255 : o);
+    }
+    if constexpr (OUT_F32) {
+      float* out = reinterpret_cast<float*>(out_);
+      const float r = ((float)v[0] - mean.x) * stdinv.x, g = ((float)v[1] - mean.y) * stdinv.y,
+                  b = ((float)v[2] - mean.z) * stdinv.z;
+      if (layout == 0) {
+        float* o = out + (int64_t)k * 3 * plane + px;
+        o[0] = r; o[plane] = g; o[2 * plane] = b;
+      } else {
+        const int vw = k / T, t = k - vw * T;
+        float* o = out + (((int64_t)vw * 3) * T + t) * plane + px;
+        o[0] = r; o[(int64_t)T * plane] = g; o[2 * (int64_t)T * plane] = b;
+      }
+    } else {
+      uint8_t* o = reinterpret_cast<uint8_t*>(out_) + i * 3;
+      o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+    }
+  }
+}
+
 }  // namespace vitta
 
 using namespace vitta;
@@ -210,4 +267,72 @@ extern "C" int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int 
       frames, F, H, W, idx, n_idx, hbounds, hk, vbounds, vk, slots, out_h, out_w, scale, shift, layout, T, out);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+
+// ---- OpenCV INTER_LINEAR tap tables (host only: no CUDA call) ----
+extern "C" int vitta_cv_linear_tables(int src, int dst, int horizontal, int32_t* ofs_host, int32_t* w_host) {
+  VITTA_CHECK_ARG(src > 0 && dst > 0 && ofs_host && w_host, VITTA_E_BADARG, "cv_linear_tables: bad arguments");
+  const double scale = 1.0 / ((double)dst / src);          // resize(): inv_scale = dst / src, scale = 1 / inv_scale
+  for (int d = 0; d < dst; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (horizontal) {                                      // the vertical pass clips the ROW INDICES instead
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    ofs_host[d] = s;
+    w_host[2 * d] = (int32_t)lrintf((1.f - f) * 2048.f);   // saturate_cast<short>(float): round half to even
+    w_host[2 * d + 1] = (int32_t)lrintf(f * 2048.f);
+  }
+  return 0;
+}
+
+static int cv_resize_impl(const uint8_t* src, int F, int H, int W, const int32_t* idx, int n, int x0, int y0, int cw, int ch,
+                          const int32_t* xofs, const int32_t* xw, const int32_t* yofs, const int32_t* yw, int out_h,
+                          int out_w, const float* mean3_host, const float* std3_host, int layout, int T, void* out,
+                          bool f32, void* stream) {
+  VITTA_CHECK_ARG(src && out && xofs && xw && yofs && yw, VITTA_E_BADARG, "cv_resize: null pointer");
+  VITTA_CHECK_ARG(F > 0 && H > 0 && W > 0 && n > 0 && out_h > 0 && out_w > 0, VITTA_E_BADARG, "cv_resize: bad shape");
+  VITTA_CHECK_ARG(cw > 0 && ch > 0 && x0 >= 0 && y0 >= 0 && x0 + cw <= W && y0 + ch <= H, VITTA_E_BADARG,
+                  "cv_resize: source region outside the frame");
+  VITTA_CHECK_ARG(idx || n <= F, VITTA_E_BADARG, "cv_resize: without an index vector n must not exceed the frame count");
+  float3 mean = make_float3(0.f, 0.f, 0.f), stdinv = make_float3(1.f, 1.f, 1.f);
+  if (f32) {
+    VITTA_CHECK_ARG(mean3_host && std3_host && T > 0 && n % T == 0 && (layout == 0 || layout == 1), VITTA_E_BADARG,
+                    "cv_resize_normalize: needs mean / std, layout 0 or 1 and n a multiple of T");
+    mean = make_float3(mean3_host[0], mean3_host[1], mean3_host[2]);
+    stdinv = make_float3((float)(1.0 / (double)std3_host[0]), (float)(1.0 / (double)std3_host[1]),
+                         (float)(1.0 / (double)std3_host[2]));
+  }
+  const int64_t total = (int64_t)n * out_h * out_w;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (f32)
+    cv_resize_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, F, H, W, idx, n, x0, y0, cw, ch, xofs, xw,
+                                                                              yofs, yw, out_h, out_w, mean, stdinv, layout,
+                                                                              T, out);
+  else
+    cv_resize_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, F, H, W, idx, n, x0, y0, cw, ch, xofs, xw,
+                                                                               yofs, yw, out_h, out_w, mean, stdinv, 0, 1,
+                                                                               out);
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vitta_cv_resize_u8(const uint8_t* src, int F, int H, int W, const int32_t* idx, int n, int x0, int y0, int cw,
+                                  int ch, const int32_t* xofs, const int32_t* xw, const int32_t* yofs, const int32_t* yw,
+                                  int out_h, int out_w, uint8_t* out, void* stream) {
+  return cv_resize_impl(src, F, H, W, idx, n, x0, y0, cw, ch, xofs, xw, yofs, yw, out_h, out_w, nullptr, nullptr, 0, 1, out,
+                        false, stream);
+}
+
+extern "C" int vitta_cv_resize_normalize_u8(const uint8_t* src, int F, int H, int W, const int32_t* idx, int n, int x0,
+                                            int y0, int cw, int ch, const int32_t* xofs, const int32_t* xw,
+                                            const int32_t* yofs, const int32_t* yw, int out_h, int out_w,
+                                            const float* mean3_host, const float* std3_host, int layout, int T, float* out,
+                                            void* stream) {
+  return cv_resize_impl(src, F, H, W, idx, n, x0, y0, cw, ch, xofs, xw, yofs, yw, out_h, out_w, mean3_host, std3_host, layout,
+                        T, out, true, stream);
 }
