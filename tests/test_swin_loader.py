@@ -121,6 +121,35 @@ def test_entry_points_validate_before_touching_the_device():
         swin_views_to_device(src, [0, 1], 2, 15, 8)          # host tensor: no CPU path
 
 
+def test_dataset_plan_draws_in_the_pipeline_order():
+    """SampleFrames (deterministic style) -> RandomResizedCrop (numpy uniform x 2, random.randint x 2) -> Flip (one numpy
+    draw per item): the plan of consecutive items equals the pinned pieces called in that order on the same generators."""
+    import random
+    from vitta_b200.corpus.views import (DecodedSwinVideoDataset, sample_tta_view_indices, swin_random_resized_crop_bbox,
+                                         swin_rescale_size, swin_seq_frames)
+    from vitta_b200.utils.opts import default_args
+    args = default_args(arch="videoswintransformer", clip_length=4, input_size=32, scale_size=40, n_augmented_views=2,
+                        if_sample_tta_aug_views=True)
+    vids = [torch.zeros(11, 48, 64, 3, dtype=torch.uint8), torch.zeros(20, 60, 44, 3, dtype=torch.uint8)]
+    ds = DecodedSwinVideoDataset(vids, [1, 2], args, "tta", np_rng=np.random.RandomState(3), py_rng=random.Random(3))
+    nrs, prs = np.random.RandomState(3), random.Random(3)
+    for i, v in enumerate(vids):
+        idx, bbox = ds.plan(i)
+        f, h, w, _ = v.shape
+        assert (idx == sample_tta_view_indices(f, 4, 2, "uniform_equidist")).all()
+        nw, nh = swin_rescale_size(w, h, 40)
+        assert bbox == swin_random_resized_crop_bbox(nh, nw, np_rng=nrs, py_rng=prs)
+        nrs.rand()
+        assert 0 <= bbox[0] < bbox[2] <= nw and 0 <= bbox[1] < bbox[3] <= nh
+    ev = DecodedSwinVideoDataset(vids, [1, 2], args, "eval", np_rng=np.random.RandomState(3), py_rng=random.Random(3))
+    idx, bbox = ev.plan(1)
+    assert bbox is None and (idx == swin_seq_frames(20, 4)).all()
+    with pytest.raises(NotImplementedError):
+        DecodedSwinVideoDataset(vids, [1, 2], default_args(arch="tanet"), "tta")
+    with pytest.raises(NotImplementedError):
+        DecodedSwinVideoDataset(vids, [1, 2], default_args(arch="videoswintransformer", flip_ratio=1), "tta")
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
                     reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")

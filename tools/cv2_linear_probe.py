@@ -10,7 +10,7 @@ on the cases below (up- and down-scaling, exact 2x, degenerate sizes):
   * VERTICAL taps: NO such border rule -- the row indices s, s + 1 are clipped to [0, src - 1] and the weights stay as
     computed, so the first / last rows mix the same row with two separately truncated products;
   * output = ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
-Not built into the product in round 1 (SURVEY.md section 8f rank 3 names the TANet transform only)."""
+This probe came first; the restatement now lives in oracle/cv2_resample.py and the device version in preprocess.cu (K14)."""
 import numpy as np, cv2, math
 def cv_round(x): return int(np.rint(x))
 def tabs(ssize, dsize, border_fix):

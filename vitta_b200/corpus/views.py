@@ -219,8 +219,8 @@ def swin_seq_frames(num_frames, clip_len):
     return np.minimum(np.asarray(seq, dtype=np.int64), num_frames - 1)
 
 
-# ---- host-side geometry of the Video-Swin loader (models/videoswintransformer_models/video_dataset.py:66-101): the boxes
-# ---- only -- its mmcv / OpenCV resize arithmetic is not on the device yet (tools/cv2_linear_probe.py)
+# ---- host-side geometry of the Video-Swin loader (models/videoswintransformer_models/video_dataset.py:66-101); its
+# ---- OpenCV resize runs on the device through swin_views_to_device below (K14)
 def swin_rescale_size(image_w, image_h, short_edge):
     """``Resize(scale=(-1, short_edge))`` (transforms_backup.py:772-790,834-835): mmcv.rescale_size with the long edge
     unbounded -- factor = short_edge / min(h, w), new size = int(x * factor + 0.5).  mmcv (pinned 1.3.12,
@@ -381,7 +381,7 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
 
     Use it through ``args.dataset_factory = lambda args, split, kind: DecodedVideoDataset(videos, labels, args, kind)``
     with ``num_workers=0`` (the tensors live on the GPU).  TANet layouts and arithmetic only: the Video-Swin loader of the
-    reference resizes with mmcv / OpenCV, whose arithmetic differs (tools/cv2_linear_probe.py)."""
+    reference resizes with mmcv / OpenCV, whose arithmetic differs -- see ``DecodedSwinVideoDataset``."""
 
     def __init__(self, videos, labels, args, dataset_type='tta', rng=_random):
         if args.arch != 'tanet':
@@ -430,4 +430,51 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
         else:
             x = views_to_device(self.videos[index], idx, a.clip_length, 'tanet', mean=mean, std=std,
                                 scale_size=a.scale_size, out_size=self.input_size, three_crops=self.three_crops)
+        return x, self.labels[index]
+
+
+class DecodedSwinVideoDataset(torch.utils.data.Dataset):
+    """``Video_SwinDataset.__getitem__`` (models/videoswintransformer_models/video_dataset.py:58-110) for decoded uint8
+    frames resident in HBM: SampleFrames -> Resize(-1, scale_size) -> [TTA views: RandomResizedCrop (ONE box per video) +
+    Resize(S, S)] or [CenterCrop(S)] -> Flip (``--flip_ratio 0``: never flips, but draws) -> Normalize -> NCTHW.
+    The random draws are made in the pipeline's order from ``np_rng`` / ``py_rng`` (numpy's legacy generator and
+    ``random``, like the reference).  Use through ``args.dataset_factory`` with ``num_workers=0``."""
+
+    def __init__(self, videos, labels, args, dataset_type='tta', np_rng=np.random, py_rng=_random):
+        if args.arch != 'videoswintransformer':
+            raise NotImplementedError("DecodedSwinVideoDataset mirrors the Video-Swin loader; use DecodedVideoDataset for TANet")
+        if len(videos) != len(labels):
+            raise _lib.VittaError("DecodedSwinVideoDataset: %d videos, %d labels" % (len(videos), len(labels)))
+        if getattr(args, 'flip_ratio', 0) != 0:
+            raise NotImplementedError("flip_ratio != 0: horizontal flips are not on the device")
+        self.videos, self.labels, self.args, self.np_rng, self.py_rng = videos, labels, args, np_rng, py_rng
+        self.sample_views = bool(args.if_sample_tta_aug_views) if dataset_type == 'tta' else False   # basics.py:1197-1201
+
+    def __len__(self):
+        return len(self.videos)
+
+    def plan(self, index):
+        """Host side of one item: (frame indices, crop box in the resized frame or None)."""
+        a = self.args
+        f, h, w, _ = self.videos[index].shape
+        t = a.clip_length
+        bbox = None
+        if self.sample_views:
+            idx = np.concatenate([sample_tta_view_indices(f, t, a.n_augmented_views, style, np_rng=self.np_rng)
+                                  for style in a.tta_view_sample_style_list])
+            nw, nh = swin_rescale_size(w, h, a.scale_size)
+            bbox = swin_random_resized_crop_bbox(nh, nw, np_rng=self.np_rng, py_rng=self.py_rng)
+        else:
+            if not getattr(a, 'frame_uniform', True) or getattr(a, 'num_clips', 1) != 1:
+                raise NotImplementedError("dense clip sampling (frame_uniform=False / num_clips > 1) is not mirrored")
+            idx = swin_seq_frames(f, t)
+        self.np_rng.rand()             # Flip.__call__ draws once per item even with flip_ratio 0 (transforms_backup.py:1073)
+        return idx, bbox
+
+    def __getitem__(self, index):
+        idx, bbox = self.plan(index)
+        a = self.args
+        cfg = getattr(a, 'img_norm_cfg', None) or {}
+        x = swin_views_to_device(self.videos[index], idx, a.clip_length, a.scale_size, a.input_size, bbox,
+                                 mean=cfg.get('mean', SWIN_MEAN_255), std=cfg.get('std', SWIN_STD_255))
         return x, self.labels[index]
