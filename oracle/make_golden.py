@@ -520,6 +520,23 @@ def run_views_case():
         random.seed(ih * 7 + iw)
         seq["bbox/%d/%d" % (ih, iw)] = np.asarray(
             [tb.RandomResizedCrop.get_crop_bbox((ih, iw), (0.08, 1.0), (3 / 4, 4 / 3)) for _ in range(8)], np.int64)
+    # draw ORDER of the TTA pipeline tail: RandomResizedCrop.__call__ then Flip.__call__ (flip_ratio 0) of the reference on
+    # two consecutive items; the generators' next values afterwards fix the stream positions.  (__init__ bypassed: it only
+    # validates with mmcv.is_tuple_of, and mmcv is absent.)
+    rrc = object.__new__(tb.RandomResizedCrop)
+    rrc.area_range, rrc.aspect_ratio_range, rrc.lazy = (0.08, 1.0), (3 / 4, 4 / 3), False
+    fl = object.__new__(tb.Flip)
+    fl.flip_ratio, fl.direction, fl.flip_label_map, fl.left_kp, fl.right_kp, fl.lazy = 0, 'horizontal', None, None, None, False
+    np.random.seed(3)
+    random.seed(3)
+    boxes = []
+    for h, w in ((40, 53), (55, 40)):                     # = swin_rescale_size of 64x48 and 44x60 frames to short edge 40
+        res = {"imgs": [np.zeros((h, w, 3), np.uint8)] * 2, "img_shape": (h, w), "modality": "RGB"}
+        res = fl(rrc(res))
+        assert not res["flip"]
+        boxes.append(res["crop_bbox"])
+    seq["pipeline/boxes"] = np.asarray(boxes, np.int64)
+    seq["pipeline/next"] = np.asarray([np.random.rand(), random.random()], np.float64)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "swin_seq.npz"), **seq)
     print("wrote swin_seq", len(seq), "index vectors")
 

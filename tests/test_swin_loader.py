@@ -150,6 +150,23 @@ def test_dataset_plan_draws_in_the_pipeline_order():
         DecodedSwinVideoDataset(vids, [1, 2], default_args(arch="videoswintransformer", flip_ratio=1), "tta")
 
 
+def test_dataset_plan_matches_reference_pipeline_draws():
+    """RandomResizedCrop.__call__ + Flip.__call__ of the UNMODIFIED reference on two consecutive items under seeded
+    generators (tests/golden/swin_seq.npz: pipeline/*): same boxes, and both generators end at the same position."""
+    import random
+    from vitta_b200.corpus.views import DecodedSwinVideoDataset
+    from vitta_b200.utils.opts import default_args
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "swin_seq.npz"))
+    args = default_args(arch="videoswintransformer", clip_length=4, input_size=32, scale_size=40, n_augmented_views=2,
+                        if_sample_tta_aug_views=True)
+    vids = [torch.zeros(11, 48, 64, 3, dtype=torch.uint8), torch.zeros(20, 60, 44, 3, dtype=torch.uint8)]
+    nrs, prs = np.random.RandomState(3), random.Random(3)
+    ds = DecodedSwinVideoDataset(vids, [1, 2], args, "tta", np_rng=nrs, py_rng=prs)
+    got = [ds.plan(i)[1] for i in range(2)]
+    assert (np.asarray(got) == g["pipeline/boxes"]).all(), (got, g["pipeline/boxes"])
+    assert [nrs.rand(), prs.random()] == g["pipeline/next"].tolist()
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
                     reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
