@@ -43,6 +43,20 @@ def test_oracle_item_pipeline_matches_opencv_composition():
     assert (R.swin_item_u8(frames, idx, z, s, bbox) == want).all()
 
 
+def test_normalisation_formula_matches_opencv_for_every_pixel_value():
+    """The kernel's normalisation -- float32 (x - mean), then the product with the float64 reciprocal of the float32 std
+    rounded once -- against mmcv.imnormalize_'s cv2.subtract / cv2.multiply, for all 256 values of every channel."""
+    cv2 = pytest.importorskip("cv2")
+    from vitta_b200.corpus.views import SWIN_MEAN_255, SWIN_STD_255
+    mean, std = np.array(SWIN_MEAN_255, np.float32), np.array(SWIN_STD_255, np.float32)        # Normalize.__init__ (:1146-1147)
+    img = np.stack([np.arange(256)] * 3, -1).astype(np.float32).reshape(16, 16, 3)
+    ref = img.copy()
+    cv2.subtract(ref, np.float64(mean.reshape(1, -1)), ref)
+    cv2.multiply(ref, 1 / np.float64(std.reshape(1, -1)), ref)
+    mine = ((img - mean).astype(np.float64) * (1.0 / std.astype(np.float64))).astype(np.float32)
+    assert np.array_equal(mine, ref)
+
+
 def test_library_tap_tables_match_oracle():
     from oracle import cv2_resample as R
     from vitta_b200.corpus.views import cv_linear_tables
@@ -180,6 +194,8 @@ def test_swin_views_to_device_vs_oracle(cuda_device, with_bbox):
     bbox = (11, 5, 83, 70) if with_bbox else None
     out = swin_views_to_device(torch.from_numpy(frames).to(cuda_device), idx, t, z, s, bbox)
     u8 = R.swin_item_u8(frames, np.minimum(idx, 8), z, s, bbox)                                 # (V*T, s, s, 3)
-    x = (torch.from_numpy(u8).float() - torch.tensor(SWIN_MEAN_255)) * (1.0 / torch.tensor(SWIN_STD_255, dtype=torch.float64)).float()
+    # mmcv.imnormalize_: float32 difference, product with the float64 reciprocal of the float32 std rounded once
+    mean32, std32 = torch.tensor(SWIN_MEAN_255, dtype=torch.float32), torch.tensor(SWIN_STD_255, dtype=torch.float32)
+    x = ((torch.from_numpy(u8).float() - mean32).double() * (1.0 / std32.double())).float()
     want = x.reshape(2, t, s, s, 3).permute(0, 4, 1, 2, 3).contiguous()
-    torch.testing.assert_close(out.cpu(), want, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out.cpu(), want, rtol=0, atol=0)             # bit exact, normalisation included

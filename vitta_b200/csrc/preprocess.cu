@@ -117,13 +117,13 @@ __global__ void __launch_bounds__(256) gather_crop_resize_kernel(
 // horizontal pass keeps 32-bit sums, rows clipped (not re-weighted) at the top / bottom, and the vertical combine
 // ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  The source is the region (x0, y0, cw, ch) of frame
 // idx[k] (or frame k); tables from vitta_cv_linear_tables.  OUT_F32: normalise like mmcv.imnormalize_ ((x - mean) * 1/std
-// on the 0..255 scale) and write the Swin loader layout (V, 3, T, h, w) or the TANet one; else write uint8 (n, h, w, 3).
+// on the 0..255 scale, float32 mean / std as mmcv's Normalize stores them) and write the Swin loader layout (V, 3, T, h, w) or the TANet one; else write uint8 (n, h, w, 3).
 template <bool OUT_F32>
 __global__ void __launch_bounds__(256) cv_resize_kernel(const uint8_t* __restrict__ src, int F, int H, int W,
                                                        const int32_t* __restrict__ idx, int n, int x0, int y0, int cw, int ch,
                                                        const int32_t* __restrict__ xofs, const int32_t* __restrict__ xw,
                                                        const int32_t* __restrict__ yofs, const int32_t* __restrict__ yw,
-                                                       int out_h, int out_w, float3 mean, float3 stdinv, int layout, int T,
+                                                       int out_h, int out_w, float3 mean, double3 stdinv, int layout, int T,
                                                        void* __restrict__ out_) {
   const int64_t plane = (int64_t)out_h * out_w;
   const int64_t total = (int64_t)n * plane;
@@ -152,8 +152,10 @@ __global__ void __launch_bounds__(256) cv_resize_kernel(const uint8_t* __restric
     }
     if constexpr (OUT_F32) {
       float* out = reinterpret_cast<float*>(out_);
-      const float r = ((float)v[0] - mean.x) * stdinv.x, g = ((float)v[1] - mean.y) * stdinv.y,
-                  b = ((float)v[2] - mean.z) * stdinv.z;
+      // mmcv.imnormalize_ = cv2.subtract then cv2.multiply with float64 scalars on a float32 image: the difference is
+      // rounded to float32, the product is formed in double and rounded once (checked against OpenCV for all 256 values)
+      const float r = (float)((double)((float)v[0] - mean.x) * stdinv.x), g = (float)((double)((float)v[1] - mean.y) * stdinv.y),
+                  b = (float)((double)((float)v[2] - mean.z) * stdinv.z);
       if (layout == 0) {
         float* o = out + (int64_t)k * 3 * plane + px;
         o[0] = r; o[plane] = g; o[2 * plane] = b;
@@ -298,13 +300,13 @@ static int cv_resize_impl(const uint8_t* src, int F, int H, int W, const int32_t
   VITTA_CHECK_ARG(cw > 0 && ch > 0 && x0 >= 0 && y0 >= 0 && x0 + cw <= W && y0 + ch <= H, VITTA_E_BADARG,
                   "cv_resize: source region outside the frame");
   VITTA_CHECK_ARG(idx || n <= F, VITTA_E_BADARG, "cv_resize: without an index vector n must not exceed the frame count");
-  float3 mean = make_float3(0.f, 0.f, 0.f), stdinv = make_float3(1.f, 1.f, 1.f);
+  float3 mean = make_float3(0.f, 0.f, 0.f);
+  double3 stdinv = make_double3(1.0, 1.0, 1.0);
   if (f32) {
     VITTA_CHECK_ARG(mean3_host && std3_host && T > 0 && n % T == 0 && (layout == 0 || layout == 1), VITTA_E_BADARG,
                     "cv_resize_normalize: needs mean / std, layout 0 or 1 and n a multiple of T");
     mean = make_float3(mean3_host[0], mean3_host[1], mean3_host[2]);
-    stdinv = make_float3((float)(1.0 / (double)std3_host[0]), (float)(1.0 / (double)std3_host[1]),
-                         (float)(1.0 / (double)std3_host[2]));
+    stdinv = make_double3(1.0 / (double)std3_host[0], 1.0 / (double)std3_host[1], 1.0 / (double)std3_host[2]);
   }
   const int64_t total = (int64_t)n * out_h * out_w;
   int64_t blocks = (total + 255) / 256;
