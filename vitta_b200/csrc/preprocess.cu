@@ -59,7 +59,7 @@ __device__ __forceinline__ int clip8_fixed(int v) {
 __global__ void __launch_bounds__(256) gather_crop_resize_kernel(
     const uint8_t* __restrict__ frames, int F, int H, int W, const int32_t* __restrict__ idx, int n_idx,
     const int32_t* __restrict__ hb, const int32_t* __restrict__ hk, const int32_t* __restrict__ vb,
-    const int32_t* __restrict__ vk, int ks, int out_h, int out_w, float3 scale, float3 shift, int layout, int T,
+    const int32_t* __restrict__ vk, int ks, int out_h, int out_w, float3 mean, float3 stdv, int layout, int T,
     float* __restrict__ out) {
   const int64_t plane = (int64_t)out_h * out_w;
   const int64_t total = (int64_t)n_idx * plane;
@@ -94,9 +94,12 @@ __global__ void __launch_bounds__(256) gather_crop_resize_kernel(
       ag += clip8_fixed(hg) * c;
       ab += clip8_fixed(hbl) * c;
     }
-    const float r = (float)clip8_fixed(ar) * scale.x + shift.x;
-    const float g = (float)clip8_fixed(ag) * scale.y + shift.y;
-    const float b = (float)clip8_fixed(ab) * scale.z + shift.z;
+    // ToTorchFormatTensor (img.float().div(255)) then GroupNormalize (t.sub_(m).div_(s)): three correctly rounded float32
+    // operations, spelled with intrinsics so that nothing is contracted or turned into a reciprocal multiply -- the result
+    // is bit-identical to the reference loader's tensor (tests/golden/loader.npz)
+    const float r = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8_fixed(ar), 255.f), mean.x), stdv.x);
+    const float g = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8_fixed(ag), 255.f), mean.y), stdv.y);
+    const float b = __fdiv_rn(__fsub_rn(__fdiv_rn((float)clip8_fixed(ab), 255.f), mean.z), stdv.z);
     if (layout == 0) {
       float* o = out + (int64_t)k * 3 * plane + px;
       o[0] = r;
@@ -260,13 +263,13 @@ extern "C" int vitta_gather_crop_resize_normalize_u8(const uint8_t* frames, int 
     VITTA_CHECK_ARG(b[0] > 0 && b[1] > 0 && b[2] >= 0 && b[3] >= 0 && b[2] + b[0] <= W && b[3] + b[1] <= H, VITTA_E_BADARG,
                     "gather_crop_resize: crop box outside the frame");
   }
-  const float3 scale = make_float3(1.f / (255.f * std3_host[0]), 1.f / (255.f * std3_host[1]), 1.f / (255.f * std3_host[2]));
-  const float3 shift = make_float3(-mean3_host[0] / std3_host[0], -mean3_host[1] / std3_host[1], -mean3_host[2] / std3_host[2]);
+  const float3 mean = make_float3(mean3_host[0], mean3_host[1], mean3_host[2]);
+  const float3 stdv = make_float3(std3_host[0], std3_host[1], std3_host[2]);
   const int64_t total = (int64_t)n_idx * out_h * out_w;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gather_crop_resize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      frames, F, H, W, idx, n_idx, hbounds, hk, vbounds, vk, slots, out_h, out_w, scale, shift, layout, T, out);
+      frames, F, H, W, idx, n_idx, hbounds, hk, vbounds, vk, slots, out_h, out_w, mean, stdv, layout, T, out);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
