@@ -128,3 +128,66 @@ def test_two_rank_gloo_statistics_and_gradients(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+class _LabelDataset(torch.utils.data.Dataset):
+    """Item i = a tensor filled with its label i (so a shard shows which videos it holds)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return torch.full((3, 2, 2), float(i)), i
+
+
+def _driver_worker(rank, world, port, out_dir):
+    """tta_standard's loop under a 2-rank group with the adapter replaced by a recorder: every rank must see exactly its
+    block of every global batch (adaptation AND evaluation loader) and return the accuracy over ALL videos."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vitta_b200.corpus import basics
+    from vitta_b200.utils.opts import default_args
+    seen = {"adapt": [], "eval": []}
+
+    class Recorder:
+        def __init__(self, model_origin, args, stats=None, process_group=None):
+            assert process_group is dist.group.WORLD
+
+        def adapt(self, input, target=None, criterion=None):
+            seen["adapt"].append(input[:, 0, 0, 0].tolist())
+            return {"loss_ce": None, "loss_reg": torch.tensor(1.0), "loss_consis": None}
+
+        def evaluate(self, input):
+            vid = input[:, 0, 0, 0].long()
+            seen["eval"].append(vid.tolist())
+            logits = torch.zeros(len(vid), 16)
+            logits[torch.arange(len(vid)), torch.where(vid % 3 == 0, vid, vid + 1) % 16] = 1.0      # right iff vid % 3 == 0
+            return logits
+
+        def hooks_off(self):
+            pass
+
+        def hooks_on(self):
+            pass
+    basics.OnlineAdapter = Recorder
+    n_videos = 11                                       # batches of 4, 4, 3: the last one is ragged
+    args = default_args(arch="tanet", batch_size=4, workers=0, num_classes=16, verbose=False, stat_reg="BNS")
+    args.process_group = dist.group.WORLD
+    args.dataset_factory = lambda a, split, kind: _LabelDataset(n_videos)
+    (acc,) = basics.tta_standard(torch.nn.Linear(2, 2), None, args=args)
+    want_blocks = {0: [[0.0, 1.0], [4.0, 5.0], [8.0, 9.0]], 1: [[2.0, 3.0], [6.0, 7.0], [10.0]]}[rank]
+    assert seen["adapt"] == want_blocks and seen["eval"] == [[int(v) for v in b] for b in want_blocks], seen
+    want_acc = 100.0 * sum(1 for v in range(n_videos) if v % 3 == 0) / n_videos
+    assert abs(acc - want_acc) < 1e-4, (acc, want_acc)
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_driver_shards_every_batch_and_merges_accuracy(tmp_path):
+    port = _free_port()
+    mp.spawn(_driver_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
