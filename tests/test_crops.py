@@ -349,3 +349,19 @@ def test_decoded_video_dataset_vs_reference_loader_golden(cuda_device, case):
         # K13 normalises with the reference's own three float32 operations: bit identical to the reference loader
         assert np.array_equal(x.cpu().numpy(), g["%s/%s/x" % (case, name)])
         assert y == int(g["%s/%s/y" % (case, name)])
+
+
+def test_driver_loader_does_not_pin_or_fork_for_device_resident_datasets():
+    """corpus.basics._loader keeps the reference's DataLoader settings, except that items already on the device
+    (Decoded*VideoDataset.on_device) are neither pinned (torch refuses to pin CUDA tensors) nor produced in workers."""
+    from vitta_b200.corpus.basics import _loader
+    from vitta_b200.corpus.views import DecodedSwinVideoDataset, DecodedVideoDataset
+    from vitta_b200.utils.opts import default_args
+    args = default_args(arch="tanet", batch_size=3, workers=4)
+    vids = [torch.zeros(8, 48, 64, 3, dtype=torch.uint8)] * 2
+    dl = _loader(DecodedVideoDataset(vids, [0, 1], args, "tta"), args)
+    assert dl.pin_memory is False and dl.num_workers == 0 and dl.batch_size == 3
+    sargs = default_args(arch="videoswintransformer", batch_size=2, workers=4)
+    assert _loader(DecodedSwinVideoDataset(vids, [0, 1], sargs, "eval"), sargs).num_workers == 0
+    plain = _loader(torch.utils.data.TensorDataset(torch.zeros(4, 2)), args)
+    assert plain.pin_memory is True and plain.num_workers == 4 and plain.batch_size == 3

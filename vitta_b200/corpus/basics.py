@@ -52,6 +52,14 @@ def _dataset(args, split, dataset_type):
                                  seed=getattr(args, 'synthetic_seed', 0), tag='tta')
 
 
+def _loader(dataset, args):
+    """The reference's DataLoader settings (shuffle off, pinned host batches); datasets whose items already live on the
+    device (``on_device``: vitta_b200.corpus.views.Decoded*VideoDataset) are iterated in-process and not pinned."""
+    on_device = getattr(dataset, 'on_device', False)
+    return torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, shuffle=False,
+                                       num_workers=0 if on_device else args.workers, pin_memory=not on_device)
+
+
 def get_dataset_tanet(args, split='train', dataset_type=None):
     if split == 'train':      # reference corpus/basics.py:1225-1226 (and its default): adaptation uses split='val' only
         raise NotImplementedError('Training dataset processing for TANet to be added!')
@@ -367,11 +375,8 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
         assert args.n_gradient_steps == 1
         assert args.n_epoch_adapat == 1
     make = get_dataset_tanet if args.arch == 'tanet' else get_dataset_videoswin
-    tta_loader = torch.utils.data.DataLoader(make(args, split='val', dataset_type='tta'), batch_size=args.batch_size,
-                                             shuffle=False, num_workers=args.workers, pin_memory=True)
-    eval_loader = torch.utils.data.DataLoader(make(args, split='val', dataset_type='eval'),
-                                              batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
-                                              pin_memory=True)
+    tta_loader = _loader(make(args, split='val', dataset_type='tta'), args)
+    eval_loader = _loader(make(args, split='val', dataset_type='eval'), args)
     stats = load_source_statistics(args) if args.stat_reg == 'mean_var' else None
     batch_time, losses_ce, losses_reg, losses_consis = AverageMeter(), AverageMeter(), AverageMeter(), AverageMeter()
     top1, top5 = AverageMeter(), AverageMeter()
@@ -442,8 +447,7 @@ def compute_statistics(model=None, args=None, logger=None, log_time=None):
         raise Exception(f'{args.arch} is not a valid model!')
     hooks = [ComputeNormStatsHook(layer, clip_len=args.clip_length, stat_type=args.stat_type,
                                   before_norm=args.before_norm, batch_size=args.batch_size) for _, layer in chosen]
-    loader = torch.utils.data.DataLoader(loader_ds, batch_size=args.batch_size, shuffle=False,
-                                         num_workers=args.workers, pin_memory=True)
+    loader = _loader(loader_ds, args)
     device = next(model.parameters()).device
     sum_mean = [None] * len(hooks)
     sum_var = [None] * len(hooks)

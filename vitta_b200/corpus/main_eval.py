@@ -14,7 +14,8 @@ import torch.backends.cudnn as cudnn
 
 from .. import set_fp32_exact
 from ..utils.utils_ import make_dir, path_logger
-from .basics import (compute_statistics, get_dataset_tanet, get_dataset_videoswin, get_model, tta_standard, validate)
+from .basics import (_loader, compute_statistics, get_dataset_tanet, get_dataset_videoswin, get_model, tta_standard,
+                     validate)
 
 NUM_CLASSES = {'ucf101': 101, 'hmdb51': 51, 'kinetics': 400, 'somethingv2': 174, 'kth': 6, 'u2h': 12, 'h2u': 12}
 
@@ -107,9 +108,7 @@ def eval(args=None, model=None):
         if args.baseline != 'source':
             raise NotImplementedError(f"baseline {args.baseline!r}: only source-only evaluation is on the hot path")
         make = get_dataset_tanet if args.arch == 'tanet' else get_dataset_videoswin
-        val_loader = torch.utils.data.DataLoader(make(args, split='val', dataset_type='eval'),
-                                                 batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
-                                                 pin_memory=True)
+        val_loader = _loader(make(args, split='val', dataset_type='eval'), args)
         top1_acc = validate(val_loader, model, criterion, 0, epoch=0, args=args, logger=logger)
         epoch_result_list = [top1_acc]
     return epoch_result_list, model

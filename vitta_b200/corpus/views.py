@@ -383,6 +383,8 @@ class DecodedVideoDataset(torch.utils.data.Dataset):
     with ``num_workers=0`` (the tensors live on the GPU).  TANet layouts and arithmetic only: the Video-Swin loader of the
     reference resizes with mmcv / OpenCV, whose arithmetic differs -- see ``DecodedSwinVideoDataset``."""
 
+    on_device = True      # corpus.basics._loader: iterate in-process, do not pin
+
     def __init__(self, videos, labels, args, dataset_type='tta', rng=_random):
         if args.arch != 'tanet':
             raise NotImplementedError("DecodedVideoDataset mirrors the TANet loader; the Swin loader's OpenCV resize is "
@@ -439,6 +441,8 @@ class DecodedSwinVideoDataset(torch.utils.data.Dataset):
     Resize(S, S)] or [CenterCrop(S)] -> Flip (``--flip_ratio 0``: never flips, but draws) -> Normalize -> NCTHW.
     The random draws are made in the pipeline's order from ``np_rng`` / ``py_rng`` (numpy's legacy generator and
     ``random``, like the reference).  Use through ``args.dataset_factory`` with ``num_workers=0``."""
+
+    on_device = True      # corpus.basics._loader: iterate in-process, do not pin
 
     def __init__(self, videos, labels, args, dataset_type='tta', np_rng=np.random, py_rng=_random):
         if args.arch != 'videoswintransformer':
