@@ -289,9 +289,6 @@ def test_dataset_refuses_what_it_does_not_mirror():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="kernel written after round 1's GPU budget was spent (oracle and host tables are pinned on the "
-                           "CPU above); set VITTA_TEST_UNVERIFIED=1 to run")
 @pytest.mark.parametrize("arch", ["tanet", "videoswintransformer"])
 def test_views_to_device_crop_resize_vs_oracle(cuda_device, arch):
     from oracle import pil_resample as R
@@ -316,8 +313,6 @@ def test_views_to_device_crop_resize_vs_oracle(cuda_device, arch):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
 def test_views_to_device_scale_center_crop_vs_oracle(cuda_device):
     from oracle import pil_resample as R
     from vitta_b200 import synth
@@ -334,8 +329,6 @@ def test_views_to_device_scale_center_crop_vs_oracle(cuda_device):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
 @pytest.mark.parametrize("case", LOADER_CASES)
 def test_decoded_video_dataset_vs_reference_loader_golden(cuda_device, case):
     """End to end on the GPU: DecodedVideoDataset items against the items of the unmodified reference loader."""

@@ -185,3 +185,28 @@ def test_conv2d_autograd_matches_torch(cuda_device):
             err = float((a.detach().double() - b.detach()).abs().max())
             # 3xTF32 drops the lo*lo term (2^-22 per product): the bound grows with sqrt(K); K = 4608 in the last case
             assert err < 5e-5 * scale, (nm, stride, kh, err, scale)
+
+
+def test_weight_split_cache_survives_address_reuse(cuda_device):
+    """Regression for the round-1 parity failure: allocate a weight, convolve, free it, allocate a DIFFERENT weight of
+    the same shape (the caching allocator returns the same address, version counter 0 again) and convolve: each result
+    must come from its own weight."""
+    import gc
+    import vitta_b200
+    from vitta_b200 import ops
+    vitta_b200.set_fp32_exact()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 128, 14, 14, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    ptrs, errs = [], []
+    for i in range(4):
+        wt = (torch.randn(128, 128, 3, 3, generator=g) / 34.0).to(cuda_device)
+        w1 = wt.clone().requires_grad_(True)
+        ptrs.append(w1.data_ptr())
+        y = ops.conv2d(x, w1, 1, 1)
+        y.sum().backward()
+        ref = F.conv2d(x.double(), wt.double(), None, 1, 1)
+        errs.append(float((y.detach().double() - ref).abs().max()) / float(ref.abs().max()))
+        del wt, w1, y, ref
+        gc.collect()
+    assert max(errs) < 5e-5, (errs, ptrs)
+    assert len(set(ptrs)) < len(ptrs), "the allocator never reused an address: the regression was not exercised"

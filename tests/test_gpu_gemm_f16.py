@@ -12,9 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VITTA_TEST_F16X3") != "1", reason="fp16-split kernels are opt-in until "
-                                 "validated on hardware (set VITTA_TEST_F16X3=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _err_ok(got, ref64, absprod64, k=1024, tol=2e-6):

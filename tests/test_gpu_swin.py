@@ -281,9 +281,6 @@ def test_swin_tta_vs_reference_golden(cuda_device, name):
     _run_swin_case(cuda_device, name, cases.SWIN_CASES[name])
 
 
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="golden cases added after round 1's GPU budget was spent (oracle-pinned on CPU in "
-                           "tests/test_oracle_golden.py); set VITTA_TEST_UNVERIFIED=1 to run them")
 @pytest.mark.parametrize("name", list(cases.SWIN_OPTION_CASES))
 def test_swin_option_modes_vs_reference_golden(cuda_device, name):
     """--update_only_bn_affine on Video-Swin (Adam over the LayerNorm affine parameters, everything else frozen); MSE

@@ -110,9 +110,6 @@ def test_tanet_tta_vs_reference_golden(cuda_device, name):
     _run_case(name, cuda_device)
 
 
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="golden cases added after round 1's GPU budget was spent (oracle-pinned on CPU in "
-                           "tests/test_oracle_golden.py); set VITTA_TEST_UNVERIFIED=1 to run them")
 @pytest.mark.parametrize("name", ["tanet_t8_r64_stats_kld_avg", "tanet_t8_r64_consis_l1_bnaffine",
                                   "tanet_t8_r64_standard_l1", "tanet_t8_r64_bns_l1", "tanet_t8_r64_stats_l1_before_norm"])
 def test_tanet_option_modes_vs_reference_golden(cuda_device, name):

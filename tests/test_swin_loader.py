@@ -182,8 +182,6 @@ def test_dataset_plan_matches_reference_pipeline_draws():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("VITTA_TEST_UNVERIFIED") != "1",
-                    reason="kernel written after round 1's GPU budget was spent; set VITTA_TEST_UNVERIFIED=1 to run")
 @pytest.mark.parametrize("with_bbox", [False, True])
 def test_swin_views_to_device_vs_oracle(cuda_device, with_bbox):
     from oracle import cv2_resample as R

@@ -1,40 +1,70 @@
-"""Build libvitta_b200.so in-tree with nvcc for sm_100a (no torch headers: the boundary is a plain C ABI)."""
+"""Build libvitta_b200.so in-tree with nvcc for sm_100a (no torch headers: the boundary is a plain C ABI).
+
+Every ``csrc/*.cu`` is compiled to its own object (in parallel, cached by modification time under ``csrc/_obj/``) and
+the objects are linked into one shared library; ``force=True`` recompiles everything."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libvitta_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-shared", "-cudart", "static"]
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+LFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC"]
 
 
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "vitta_b200.h"))
+    return hs
+
+
+def _obj_of(src):
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "vitta_b200.h"))
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def needs_build():
+    return _stale(LIB, sources() + headers())
+
+
+def _compile(src, verbose):
+    cmd = [NVCC] + CFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    flags = [f for f in FLAGS if f != "--use_fast_math=false"]
-    cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    hs = headers()
+    todo = [s for s in sources() if force or _stale(_obj_of(s), [s] + hs)]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 4))) as ex:
+        for src, r in ex.map(lambda s: _compile(s, verbose), todo):
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed compiling %s" % os.path.basename(src))
+            if verbose:
+                print(r.stderr)
+    r = subprocess.run([NVCC] + LFLAGS + ["-o", LIB] + [_obj_of(s) for s in sources()], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libvitta_b200.so")
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("nvcc failed linking libvitta_b200.so")
     return LIB
 
 

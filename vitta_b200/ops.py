@@ -760,14 +760,37 @@ def conv2d_dgrad_f16x3(gy, wt_hi, wt_lo, w_amax, x_shape, kh, kw, stride, pad, g
     return gx
 
 
-# weight-split cache: the hi/lo operands of a weight are rebuilt only when the weight changed.  Keyed by the
-# storage address (autograd hands backward() re-wrapped tensor objects); validated by the autograd version counter
-# and emptied by every FusedSGD step (it updates parameters through raw pointers, invisible to the version counter).
-_split_cache = {}
+# weight-split cache: the hi/lo operands of a weight are rebuilt only when the weight changed.  The entry lives ON the
+# weight tensor object (like _vitta_amax above), so it dies with the tensor: a freed weight whose address the caching
+# allocator hands to a new same-shape weight can never serve its stale split (round-1 bug: the cache was keyed by
+# data_ptr).  autograd returns saved INPUT tensors as the original objects, so backward() finds the forward's entry; a
+# re-wrapped tensor merely misses and splits again.  Validated by the autograd version counter (in-place updates,
+# load_state_dict) and by a global epoch that every FusedSGD step / graph replay bumps (they update parameters through
+# raw pointers, invisible to the version counter).
+_weight_epoch = 0
 
 
 def bump_weight_epoch():
-    _split_cache.clear()
+    global _weight_epoch
+    _weight_epoch += 1
+
+
+def _cached_split(w, mode, kind, make):
+    cache = getattr(w, "_vitta_split", None)
+    if cache is None:
+        cache = {}
+        try:
+            w._vitta_split = cache
+        except AttributeError:       # an object without a __dict__: no caching, always correct
+            cache = None
+    stamp = (w._version, _weight_epoch, w.data_ptr(), tuple(w.shape))
+    ent = cache.get((mode, kind)) if cache is not None else None
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, make(w.detach(), mode))
+        if cache is not None:
+            cache[(mode, kind)] = ent
+    return ent[1]
 
 
 # Operand split of the dense contractions: "tf32x3" (default, hardware-validated) or "f16x3" (opt-in until validated on
@@ -791,23 +814,12 @@ def gemm_precision():
 
 def weight_split_f16(w, mode):
     """Cached fp16 pieces + amax scalar of a weight (same invalidation rules as weight_split)."""
-    key = (w.data_ptr(), mode, "f16")
-    ent = _split_cache.get(key)
-    if ent is None or ent[0] != (w._version, tuple(w.shape)):
-        with torch.no_grad():
-            ent = ((w._version, tuple(w.shape)), split_f16(w.detach(), mode))
-        _split_cache[key] = ent
-    return ent[1]
+    return _cached_split(w, mode, "f16", split_f16)
 
 
 def weight_split(w, mode):
-    key = (w.data_ptr(), mode)
-    ent = _split_cache.get(key)
-    if ent is None or ent[0] != (w._version, tuple(w.shape)):
-        with torch.no_grad():
-            ent = ((w._version, tuple(w.shape)), split_tf32(w.detach(), mode))
-        _split_cache[key] = ent
-    return ent[1]
+    """Cached tf32 (hi, lo) operands of a weight; see the cache rules above."""
+    return _cached_split(w, mode, "tf32", split_tf32)
 
 
 _wgrad_ws = {}
