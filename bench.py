@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- clips/s per ViTTA adaptation step (BASELINE.json metric) on N B200s of one node.
 
-Workload (config.workload): configs[1] of BASELINE.json -- TANet-R50 ViTTA, synthetic gauss-corrupted
+Headline workload (config.workload): configs[1] of BASELINE.json -- TANet-R50 ViTTA, synthetic gauss-corrupted
 16x224x224 clips, 8 videos per GPU (weak scaling), one view, statistics-alignment loss only (L1), SGD over all
 parameters.  A step = train-mode forward with the 47 alignment hooks + backward + SGD on one batch.
 
-  value      device-timed throughput with the batch already resident in HBM (the step is replayed as one CUDA graph after
-             3 eager steps; --no-graph times eager launches)
-  e2e        the same step through the public API (OnlineAdapter.adapt) from PINNED HOST input, with the H2D copy
-             and a D2H read of the loss inside the timed region
-  roofline   the statistics kernel (K1) over the 29 hooked layer shapes: algorithmic bytes / CUDA-event time
-  cpu_baseline  the oracle port of the reference step timed on the host cores (bounded sample: 1 clip)
+  value         device-timed throughput with the batch already resident in HBM (the step is replayed as one CUDA graph
+                after 3 eager steps; --no-graph times eager launches)
+  e2e           the same step through the public API (OnlineAdapter.adapt) from PINNED HOST input, with the H2D copy
+                and a D2H read of the loss inside the timed region
+  roofline      the dominant kernel of the step (tcgen05 implicit-GEMM conv): algorithmic flops / CUDA-event time
+  roofline_stats   the HBM-bound fused norm + statistics kernel, and the standalone K1 over the 29 hooked shapes
+  cpu_baseline  the oracle port of the reference step timed on the host cores (bounded sample: 1 clip per step), plus
+                configs[0] (TANet source-only evaluation forward, 1 clip 8x224x224, batch 1, CPU)
+  gpu_reference the reference step (oracle port) on torch's own CUDA kernels (cuDNN / cuBLAS / ATen), TF32 off and on:
+                the bar a user of the reference on the same B200 sees
+  secondary     configs[2] (Video-Swin-T, 8 videos x 2 views x 32x224x224) and the per-GPU shard of configs[4]
+                (Video-Swin-B, 4 videos x 2 views x 32x224x224 per GPU, sharded over the N ranks)
+  parity_check  (N > 1) the sharded step against the same global batch on ONE rank: loss, EMA statistics, weights
 
 `--impl reference` times the CPU port alone (the reference is Python + torch-CPU and cannot travel to the GPU
 box; oracle/vitta_oracle.py is its pinned restatement).
@@ -28,28 +35,105 @@ sys.path.insert(0, ROOT)
 
 K_CLASSES, T, RES, N_PER_GPU = 101, 16, 224, 8
 HOOKED_ELEMS_PER_CLIP = 44556288          # SURVEY.md 8a row a2 (29 BN2d outputs of layer3+layer4, T=16)
+SWIN = {"tiny": dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24]),
+        "base": dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32])}
 
 
 def _peaks():
-    """(HBM GB/s, dense tf32 TFLOP/s, source).  The driver measures bf16 cuBLAS; kind::tf32 tcgen05.mma runs at half
-    the bf16 rate (nominal 1.1 vs 2.25 PFLOP/s), so the tensor denominator is bf16_sustained / 2 (the kernels are
-    timed inside a long step)."""
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  The driver measures bf16 cuBLAS; kind::f16 tcgen05.mma runs at
+    that rate, kind::tf32 at half of it (nominal 1.1 vs 2.25 PFLOP/s).  The kernels are timed inside a long step, so the
+    sustained figure is the denominator."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]) / 2.0, "measured"
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, 1400.0 / 2.0, "fallback"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture of this round (written by
+    tools/ncu_summary.py --traffic into profiles/r02_traffic.json); None when no capture of that kernel exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
 
 
 def _arg(v):
     return v.value if hasattr(v, "value") else v
 
 
+# algorithmic work of one C-ABI call: name -> function(args) -> (family, flops, bytes)
+def _conv_flops(f, h, w, cin, cout, kh, kw, st, pad):
+    ho, wo = (h + 2 * pad - kh) // st + 1, (w + 2 * pad - kw) // st + 1
+    return 2.0 * f * ho * wo * cout * cin * kh * kw
+
+
+GEMM_FAM = "conv/linear GEMM fwd+dgrad (tcgen05)"
+WGRAD_FAM = "conv/linear wgrad (tcgen05 split-K)"
+
+
+def _work(name, a):
+    g = lambda *idx: [_arg(a[i]) for i in idx]
+    if name in ("vitta_gemm_tf32x3", "vitta_gemm_tf32x3_ex"):
+        m, n, k = g(7, 8, 9)
+        return GEMM_FAM, 2.0 * m * n * k, 0.0
+    if name == "vitta_gemm_f16x3_ex":
+        m, n, k = g(9, 10, 11)
+        return GEMM_FAM, 2.0 * m * n * k, 0.0
+    if name in ("vitta_conv2d_tf32x3", "vitta_conv2d_tf32x3_ex"):
+        return GEMM_FAM, _conv_flops(*g(1, 2, 3, 4, 7, 8, 9, 10, 11)), 0.0
+    if name == "vitta_conv2d_f16x3_ex":
+        return GEMM_FAM, _conv_flops(*g(2, 3, 4, 5, 9, 10, 11, 12, 13)), 0.0
+    if name == "vitta_conv2d_dgrad_tf32x3":
+        f, ho, wo, cout, cin, kh, kw = g(1, 2, 3, 4, 7, 8, 9)
+        return GEMM_FAM, 2.0 * f * ho * wo * cout * cin * kh * kw, 0.0
+    if name == "vitta_conv2d_dgrad_f16x3":
+        f, ho, wo, cout, cin, kh, kw = g(2, 3, 4, 5, 9, 10, 11)
+        return GEMM_FAM, 2.0 * f * ho * wo * cout * cin * kh * kw, 0.0
+    if name == "vitta_conv2d_wgrad_tf32x3":
+        return WGRAD_FAM, _conv_flops(*g(*range(2, 11))), 0.0
+    if name == "vitta_conv2d_wgrad_f16x3":
+        return WGRAD_FAM, _conv_flops(*g(*range(4, 13))), 0.0
+    if name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd"):
+        fwd = name == "vitta_wmsa3d_fwd"
+        i0 = 4 if fwd else 8
+        b_, d_, h_, w_, heads = g(*range(i0, i0 + 5))
+        nwin = ntok = 1
+        for dim, wsz in zip((d_, h_, w_), a[i0 + 6]):
+            wsz = min(int(wsz), dim)
+            nwin *= dim // wsz
+            ntok *= wsz
+        return (("wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (tcgen05 window attention backward)"),
+                (4.0 if fwd else 10.0) * ntok * ntok * 32 * b_ * nwin * heads, 0.0)
+    if name in ("vitta_ln_fwd", "vitta_ln_bwd"):
+        fwd = name == "vitta_ln_fwd"
+        rows, c = g(8, 9) if fwd else g(15, 16)
+        return (("ln_fwd (LayerNorm + stats, K9)" if fwd else "ln_bwd (K9 backward + hook gradient)"), 0.0,
+                4.0 * rows * c * (2 if fwd else 3))
+    if name == "vitta_amax_f32":
+        return "amax_f32 (standalone operand-range pass)", 0.0, 4.0 * _arg(a[1])
+    if name in ("vitta_bn_act_fwd", "vitta_bn_act_fwd_amax"):
+        frames, rows, c = g(10, 11, 12)
+        has_res = a[2] is not None and _arg(a[2]) is not None
+        return "bn_act_fwd (BN+stats+ReLU+pool, K4+K1)", 0.0, 4.0 * frames * rows * c * (3 if has_res else 2)
+    if name in ("vitta_bn_act_bwd", "vitta_bn_act_bwd_amax"):
+        frames, rows, c = g(22, 23, 24)
+        has_res = a[4] is not None and _arg(a[4]) is not None
+        return "bn_act_bwd (K4+K3 backward)", 0.0, 4.0 * frames * rows * c * (5 if has_res else 3)
+    if name in ("vitta_tam_fwd", "vitta_tam_fwd_amax", "vitta_tam_bwd"):
+        i0 = 6 if name == "vitta_tam_bwd" else 4
+        n_, t_, hw, c = g(*range(i0, i0 + 4))
+        return name[6:], 0.0, 4.0 * n_ * t_ * hw * c * (3 if name == "vitta_tam_bwd" else 2)
+    return name[6:] if name.startswith("vitta_") else name, 0.0, 0.0
+
+
 def attribute_step(adapter, resident, step=None):
     """One extra, instrumented adaptation step: CUDA events around every launch of our library on the launching
     stream (torch's current stream).  Returns {kernel family: {"ms", "launches", "flops", "bytes"}} with ALGORITHMIC
-    flops (2*M*N*K of the fp32 product, not the 3 tf32 MMAs issued per product) and bytes."""
+    flops (2*M*N*K of the fp32 product, not the 3 MMAs issued per product) and bytes."""
     import torch
     from vitta_b200 import _lib
     _lib.profile = []
@@ -58,86 +142,20 @@ def attribute_step(adapter, resident, step=None):
     recs, _lib.profile = _lib.profile, None
     fam = {}
     for name, e0, e1, a in recs:
-        ms = e0.elapsed_time(e1)
-        flops = nbytes = 0.0
-        key = name
-        if name in ("vitta_gemm_tf32x3", "vitta_gemm_tf32x3_ex"):
-            m, n, k = _arg(a[7]), _arg(a[8]), _arg(a[9])
-            flops = 2.0 * m * n * k
-            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-        elif name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd"):
-            fwd = name == "vitta_wmsa3d_fwd"
-            i0 = 4 if fwd else 8
-            b_, d_, h_, w_, heads = (_arg(a[i0 + j]) for j in range(5))
-            win = a[i0 + 6]
-            nwin = 1
-            ntok = 1
-            for dim, wsz in zip((d_, h_, w_), win):
-                wsz = min(int(wsz), dim)
-                nwin *= dim // wsz
-                ntok *= wsz
-            flops = (4.0 if fwd else 10.0) * ntok * ntok * 32 * b_ * nwin * heads
-            key = "wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (tcgen05 window attention backward, 2 launches + dsum)"
-        elif name in ("vitta_ln_fwd", "vitta_ln_bwd"):
-            fwd = name == "vitta_ln_fwd"
-            rows, c = (_arg(a[8]), _arg(a[9])) if fwd else (_arg(a[15]), _arg(a[16]))
-            nbytes = 4.0 * rows * c * (2 if fwd else 3)
-            key = "ln_fwd (LayerNorm + stats, K9)" if fwd else "ln_bwd (K9 backward + hook gradient)"
-        elif name == "vitta_conv2d_dgrad_tf32x3":
-            f, ho, wo, cout, cin, kh, kw = (_arg(a[i]) for i in (1, 2, 3, 4, 7, 8, 9))
-            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
-            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-        elif name in ("vitta_conv2d_tf32x3", "vitta_conv2d_tf32x3_ex", "vitta_conv2d_wgrad_tf32x3"):
-            if name != "vitta_conv2d_wgrad_tf32x3":
-                f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in (1, 2, 3, 4, 7, 8, 9, 10, 11))
-                key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-            else:
-                f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in range(2, 11))
-                key = "wgrad_tf32x3"
-            ho, wo = (h + 2 * pad - kh) // st + 1, (w + 2 * pad - kw) // st + 1
-            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
-        # opt-in fp16 operand split (--gemm-precision f16x3): same families, amax scalars shift the argument positions
-        elif name == "vitta_gemm_f16x3_ex":
-            m, n, k = _arg(a[9]), _arg(a[10]), _arg(a[11])
-            flops = 2.0 * m * n * k
-            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-        elif name == "vitta_conv2d_f16x3_ex":
-            f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in (2, 3, 4, 5, 9, 10, 11, 12, 13))
-            ho, wo = (h + 2 * pad - kh) // st + 1, (w + 2 * pad - kw) // st + 1
-            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
-            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-        elif name == "vitta_conv2d_dgrad_f16x3":
-            f, ho, wo, cout, cin, kh, kw = (_arg(a[i]) for i in (2, 3, 4, 5, 9, 10, 11))
-            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
-            key = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-        elif name == "vitta_conv2d_wgrad_f16x3":
-            f, h, w, cin, cout, kh, kw, st, pad = (_arg(a[i]) for i in range(4, 13))
-            ho, wo = (h + 2 * pad - kh) // st + 1, (w + 2 * pad - kw) // st + 1
-            flops = 2.0 * f * ho * wo * cout * cin * kh * kw
-            key = "wgrad_tf32x3"
-        elif name == "vitta_amax_f32":
-            nbytes = 4.0 * _arg(a[1])
-            key = "amax_f32 (standalone operand-range pass of the f16x3 bring-up)"
-        elif name == "vitta_bn_act_fwd":
-            frames, rows, c = _arg(a[10]), _arg(a[11]), _arg(a[12])
-            has_res = a[2] is not None and _arg(a[2]) is not None
-            nbytes = 4.0 * frames * rows * c * (3 if has_res else 2)
-            key = "bn_act_fwd (BN+stats+ReLU+pool, K4+K1)"
-        elif name == "vitta_bn_act_bwd":
-            frames, rows, c = _arg(a[22]), _arg(a[23]), _arg(a[24])
-            has_res = a[4] is not None and _arg(a[4]) is not None
-            nbytes = 4.0 * frames * rows * c * (5 if has_res else 3)
-            key = "bn_act_bwd (K4+K3 backward)"
-        elif name in ("vitta_tam_fwd", "vitta_tam_bwd"):
-            i0 = 4 if name == "vitta_tam_fwd" else 6
-            n_, t_, hw, c = (_arg(a[i0 + j]) for j in range(4))
-            nbytes = 4.0 * n_ * t_ * hw * c * (2 if name == "vitta_tam_fwd" else 3)
+        key, flops, nbytes = _work(name, a)
         d = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
-        d["ms"] += ms
+        d["ms"] += e0.elapsed_time(e1)
         d["launches"] += 1
         d["flops"] += flops
         d["bytes"] += nbytes
     return fam
+
+
+def _table(fam):
+    return {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["flops"] else {}),
+                **({"gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} if v["bytes"] else {})}
+            for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
 
 
 class ClockSampler(threading.Thread):
@@ -170,22 +188,38 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-def cpu_port_clips_per_s(steps=2, warmup=1):
-    """The reference step (fwd with 47 hooks + bwd + SGD over all parameters) on the host cores, via the oracle
-    port, on a bounded sample: 1 video x 1 view x 16 x 224 x 224 per step."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_tanet_state(dev=None, t=T):
+    import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cases
     from oracle import vitta_oracle as O
     from vitta_b200 import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = synth.synth_state_dict(cases.tanet_state_template(K_CLASSES, T), seed=1)
+    sd = synth.synth_state_dict(cases.tanet_state_template(K_CLASSES, t), seed=1)
+    if dev is not None:
+        sd = {k: v.to(dev) for k, v in sd.items()}
     names = [n for n, k in O.tanet_norm_layers() if k != "bn1d"]
     # fabricated source statistics: zeros/ones are enough for timing (sign() of anything is as expensive)
-    import numpy as np
-    src_m = [np.zeros(sd[n + ".weight"].shape[0], np.float32) for n in names]
-    src_v = [np.ones(sd[n + ".weight"].shape[0], np.float32) for n in names]
+    if dev is None:
+        src_m = [np.zeros(sd[n + ".weight"].shape[0], np.float32) for n in names]
+        src_v = [np.ones(sd[n + ".weight"].shape[0], np.float32) for n in names]
+    else:
+        src_m = [torch.zeros(sd[n + ".weight"].shape[0], device=dev) for n in names]
+        src_v = [torch.ones(sd[n + ".weight"].shape[0], device=dev) for n in names]
+    return O, sd, src_m, src_v
+
+
+def cpu_port_clips_per_s(steps=2, warmup=1):
+    """The reference step (fwd with 47 hooks + bwd + SGD over all parameters) on the host cores, via the oracle
+    port, on a bounded sample: 1 video x 1 view x 16 x 224 x 224 per step."""
+    import torch
+    from vitta_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, sd, src_m, src_v = _oracle_tanet_state()
     st = O.TTAState(sd, "tanet", T, src_m, src_v, ["layer3", "layer4"], "l1_loss", True, 0.1, lr=5e-5)
     x = synth.synth_video(1, 1, T, RES, seed=200, tag="tta").view(1, T, 3, RES, RES)
     for _ in range(warmup):
@@ -197,26 +231,78 @@ def cpu_port_clips_per_s(steps=2, warmup=1):
     return 1.0 / dt, cores, dt
 
 
+def cpu_cfg1_eval_clips_per_s(reps=3):
+    """BASELINE.json configs[0]: TANet-R50 source-only evaluation forward (reference corpus/basics.py:149-217 ->
+    validate), 1 clip of 8 x 224 x 224, batch 1, torch-CPU fp32 on all host threads, via the oracle port."""
+    import torch
+    from vitta_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    O, sd, _, _ = _oracle_tanet_state(t=8)
+    x = synth.synth_video(1, 1, 8, RES, seed=300, gauss_sigma=0.0, tag="clean").view(1, 8, 3, RES, RES)
+    with torch.no_grad():
+        O.tanet_forward(sd, x, 8)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.tanet_forward(sd, x, 8)
+    return reps / (time.perf_counter() - t0)
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is Python and
+    needs mmcv / timm / decord, absent from the box) on all host threads; every step a bounded sample (1 clip)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     v, cores, dt = cpu_port_clips_per_s(steps, warm)
     sample = "1 video x 1 view x 16x224x224 per step, %d timed steps after %d warm-up (oracle port of the reference " \
              "step: fwd + 47 hooks + bwd + SGD), torch-CPU fp32, %d threads" % (steps, warm, cores)
     line = {"impl": "reference", "metric": "clips/sec per TTA step", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, stats-align only (L1), "
-                                   "SGD all params; CPU port on a bounded sample", "clips_per_step": 1},
+            "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, stats-align only (L1, 47 "
+                                   "hooks), SGD all params (BASELINE.json configs[1]); CPU port on a bounded sample of "
+                                   "1 clip per step (CPU throughput is flat in the batch size)", "clips_per_step": 1},
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+def gpu_reference_step(dev, n_videos=N_PER_GPU, steps=5, warmup=3):
+    """The reference step executed by PyTorch's own CUDA kernels (eager cuDNN / cuBLAS / ATen; oracle port with its
+    tensors on the device), fp32 with TF32 off (the reference's numerics) and on (torch's conv default)."""
+    import torch
+    from vitta_b200 import synth
+    out = []
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        O, sd, src_m, src_v = _oracle_tanet_state(dev)
+        st = O.TTAState(sd, "tanet", T, src_m, src_v, ["layer3", "layer4"], "l1_loss", True, 0.1, lr=5e-5)
+        x = synth.synth_video(n_videos, 1, T, RES, seed=200, tag="tta").view(n_videos, T, 3, RES, RES).to(dev)
+        for _ in range(warmup):
+            st.adapt_step(x, n_videos, 1, False, dropout_p=0.8)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            st.adapt_step(x, n_videos, 1, False, dropout_p=0.8)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out.append({"tf32": tf32, "ms_per_step": ms, "clips_per_s": n_videos * 1000.0 / ms})
+        del st, sd, x
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    return {"what": "reference step (oracle port) on torch-CUDA eager kernels (cuDNN/cuBLAS/ATen), same workload, "
+                    "%d timed steps after %d warm-up" % (steps, warmup), "runs": out}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ----------------------------------------------------------------------------------------------------------------------
 def stats_kernel_roofline(dev, n_clips, iters=20):
     """K1 over the 29 hooked (layer3 + layer4) BN output shapes of the workload, channels-last as the model
     stores them.  Buffers total 1.43 GB per pass (> 126 MB L2, and each tensor is read once)."""
@@ -240,6 +326,7 @@ def stats_kernel_roofline(dev, n_clips, iters=20):
         part = torch.empty(ch.n_entries * c * 2, device=dev)
         bufs.append((x, part, f * hw, c))
     st = stream_ptr()
+
     def one_pass():
         for x, part, rows, c in bufs:
             call("vitta_stats_partial", ptr(x), rows, c, 1, 1, ptr(part), st)
@@ -256,14 +343,66 @@ def stats_kernel_roofline(dev, n_clips, iters=20):
     return elems * 4, ms, len(bufs)
 
 
+class _DS:
+    def __init__(self, x):
+        self.x = x
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return self.x[i], 0
+
+
+def build_tanet(dev, pg, n, graph, t=T, res=RES, k=K_CLASSES, lr=None):
+    from vitta_b200 import synth
+    from vitta_b200.corpus.basics import OnlineAdapter, compute_statistics
+    from vitta_b200.models.tanet_models.tanet import TSN
+    from vitta_b200.utils.opts import default_args
+    model = TSN(k, t, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
+                non_local=False, partial_bn=False)
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=1))
+    model = model.to(dev)
+    extra = {} if lr is None else {"lr": lr}
+    targs = default_args(arch='tanet', clip_length=t, batch_size=n, n_augmented_views=1, if_pred_consistency=False,
+                         num_classes=k, input_size=res, **extra)
+    targs.cuda_graph = graph
+    targs.cuda_graph_collectives = graph and pg is not None
+    # source statistics from a clean synthetic batch through our own compute_statistics (untimed set-up)
+    clean = synth.tanet_loader_tensor(synth.synth_video(2, 1, t, res, seed=100, gauss_sigma=0.0, tag="clean"))
+    sargs = default_args(arch='tanet', clip_length=t, batch_size=2, num_classes=k, input_size=res,
+                         stat_type='spatiotemp', result_dir=None)
+    sargs.dataset_factory = lambda a, split, dataset_type: _DS(clean)
+    stats = compute_statistics(model, sargs)
+    return OnlineAdapter(model, targs, stats, pg), model, targs, stats
+
+
+def build_swin(dev, pg, which, videos, views=2, frames=32, k=K_CLASSES):
+    import numpy as np
+    import torch
+    from vitta_b200 import synth
+    from vitta_b200.corpus.basics import OnlineAdapter
+    from vitta_b200.models.videoswintransformer_models.recognizer3d import Recognizer3D
+    from vitta_b200.utils.opts import default_args
+    model = Recognizer3D(num_classes=k, patch_size=(2, 4, 4), window_size=(8, 7, 7), drop_path_rate=0.2, **SWIN[which])
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=1))
+    model = torch.nn.DataParallel(model.to(dev), device_ids=[dev.index])
+    lns = [m for _, m in model.named_modules() if isinstance(m, torch.nn.LayerNorm)][1:]
+    src_m = [np.zeros(m.normalized_shape[0], np.float32) for m in lns]
+    src_v = [np.ones(m.normalized_shape[0], np.float32) for m in lns]
+    args = default_args(arch='videoswintransformer', clip_length=frames, batch_size=videos, n_augmented_views=views,
+                        if_pred_consistency=views > 1, if_sample_tta_aug_views=views > 1, lr=1e-5, momentum_mvg=0.05,
+                        lambda_pred_consis=0.05,
+                        chosen_blocks=['module.backbone.layers.2', 'module.backbone.layers.3', 'module.backbone.norm'],
+                        num_classes=k, input_size=224, num_clips=1)
+    return OnlineAdapter(model, args, (src_m, src_v), pg)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import vitta_b200
-    from vitta_b200 import _lib, synth
-    from vitta_b200.corpus.basics import OnlineAdapter, compute_statistics
-    from vitta_b200.models.tanet_models.tanet import TSN
-    from vitta_b200.utils.opts import default_args
+    from vitta_b200 import _lib, ops, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -279,45 +418,11 @@ def run_ours(args):
     vitta_b200.set_fp32_exact()
     torch.backends.cudnn.benchmark = True          # reference corpus/main_eval.py:77
     _lib.load()
-    from vitta_b200 import ops
     if args.gemm_precision:
-        ops.set_gemm_precision(args.gemm_precision)      # opt-in: the default stays the validated tf32x3 split
+        ops.set_gemm_precision(args.gemm_precision)
     if args.cta_pair:
         _lib.call("vitta_gemm_set_cta_pair", 1)
     f16 = ops.gemm_precision() == "f16x3"
-
-    model = TSN(K_CLASSES, T, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True,
-                non_local=False, partial_bn=False)
-    model.load_state_dict(synth.synth_state_dict(model.state_dict(), seed=1))
-    model = model.to(dev)
-    n = N_PER_GPU
-    targs = default_args(arch='tanet', clip_length=T, batch_size=n, n_augmented_views=1, if_pred_consistency=False,
-                         num_classes=K_CLASSES, input_size=RES)
-    targs.cuda_graph = not args.no_graph and not args.ncu_step   # replay the step as one CUDA graph
-    targs.cuda_graph_collectives = world > 1 and not args.no_graph_collectives   # NCCL all-gather / all-reduce captured too
-    if world > 1 and args.no_graph_collectives:
-        targs.cuda_graph = False
-
-    # source statistics from a clean synthetic batch through our own compute_statistics (untimed set-up)
-    class DS(torch.utils.data.Dataset):
-        def __init__(self, x):
-            self.x = x
-
-        def __len__(self):
-            return self.x.shape[0]
-
-        def __getitem__(self, i):
-            return self.x[i], 0
-    clean = synth.tanet_loader_tensor(synth.synth_video(2, 1, T, RES, seed=100, gauss_sigma=0.0, tag="clean"))
-    sargs = default_args(arch='tanet', clip_length=T, batch_size=2, num_classes=K_CLASSES, input_size=RES,
-                         stat_type='spatiotemp', result_dir=None)
-    sargs.dataset_factory = lambda a, split, dataset_type: DS(clean)
-    stats = compute_statistics(model, sargs)
-    adapter = OnlineAdapter(model, targs, stats, pg)
-
-    host = synth.tanet_loader_tensor(synth.synth_video(n, 1, T, RES, seed=200 + rank, tag="tta")).pin_memory()
-    resident = host.to(dev)
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -337,7 +442,19 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    n_warm = max(args.warmup, 3) + (2 if targs.cuda_graph else 0)   # 3 eager steps, then capture + first replay
+    n = N_PER_GPU
+    graph = not args.no_graph and not args.ncu_step and not (world > 1 and args.no_graph_collectives)
+    adapter, model, targs, stats = build_tanet(dev, pg, n, graph)
+    host = synth.tanet_loader_tensor(synth.synth_video(n, 1, T, RES, seed=200 + rank, tag="tta")).pin_memory()
+    resident = host.to(dev)
+    torch.cuda.synchronize()
+
+    # set-up steps that are not warm-up of the timed thing: 3 eager steps (autograd / allocator steady state), then the
+    # capture + first replay; the W warm-up steps after that run exactly what is timed
+    setup_steps = 5 if targs.cuda_graph else 0
+    for _ in range(setup_steps):
+        adapter.adapt(resident)
+    n_warm = max(args.warmup, 3)
     for _ in range(n_warm):
         adapter.adapt(resident)
     if args.ncu_step:
@@ -376,72 +493,146 @@ def run_ours(args):
 
     # the instrumented step contains the step's collectives: every rank has to run it
     fam = attribute_step(adapter, resident)
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
+    barrier()
+
+    # ---- secondary workloads (every rank takes part: the Swin-B step is sharded over the ranks) ----
+    secondary = []
+    if not args.no_secondary:
+        del adapter
+        torch.cuda.empty_cache()
+        secondary = secondary_records(dev, pg, world, rank, timed, args)
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_check(dev, pg, world, rank)
     if rank != 0:
         _hard_exit()
-    peak, peak_tf32, which = _peaks()
-    gk = "gemm_tf32x3 (fwd+dgrad conv / linear)"
-    g = fam[gk]
+
+    peak_hbm, peak_bf16, which = _peaks()
+    kind_peak = peak_bf16 if f16 else peak_bf16 / 2.0
+    g = fam[GEMM_FAM]
     tf = g["flops"] / (g["ms"] * 1e-3) / 1e12
-    # dominant kernel of the step by device time: the tcgen05 implicit-GEMM conv (forward + data gradient)
-    if f16:      # kind::f16 runs at the bf16 rate
-        peak_tf32 *= 2.0
-    roof = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (tcgen05 %s implicit-GEMM conv, fwd + dgrad)"
-                                         % ("fp16 hi/lo split" if f16 else "3xTF32"),
-            "achieved": tf, "peak": peak_tf32,
-            "peak_source": which + (" bf16_tflops_sustained (kind::f16 rate)" if f16
-                                    else " bf16_tflops_sustained / 2 (kind::tf32 rate)"),
-            "unit": "TFLOP/s", "frac": tf / peak_tf32, "traffic": None,
-            "note": "achieved counts ALGORITHMIC fp32 flops (2MNK); the kernel issues 3 tf32 MMAs per product "
-                    "(3xTF32 split for the 1e-4 fp32 parity), i.e. tensor-pipe work is 3x this",
-            "tensor_pipe_frac_issued": 3.0 * tf / peak_tf32,
-            "traffic_sample": {"launch": "gemm_tf32x3_kernel<256>, layer1 conv3 (M=401408, N=256, K=64), ncu --set full, "
-                                         "profiles/r01_tanet_ncu_full.md", "dram_bytes": 460.1e6,
-                               "algorithmic_bytes": 401408 * (64 + 256) * 4.0, "us": 151.1},
+    split = "fp16 hi/lo split on kind::f16" if f16 else "3xTF32 on kind::tf32"
+    roof = {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad; %s)" % split,
+            "achieved": tf, "peak": kind_peak,
+            "peak_source": which + (": bf16_tflops_sustained (the kind::f16 rate)" if f16
+                                    else ": bf16_tflops_sustained / 2 (the kind::tf32 rate)"),
+            "unit": "TFLOP/s", "frac": tf / kind_peak, "traffic": _traffic("gemm_tf32x3_kernel"),
+            "note": "achieved counts ALGORITHMIC fp32 flops (2MNK); fp32-grade products need 3 MMAs each (hi*hi + hi*lo + "
+                    "lo*hi, DESIGN.md section 3), so the issued tensor-pipe work is 3x this and frac cannot exceed 1/3",
+            "tensor_pipe_frac_issued": 3.0 * tf / kind_peak,
             "launches_per_step": g["launches"], "ms_per_step": g["ms"]}
-    fk = "bn_act_fwd (BN+stats+ReLU+pool, K4+K1)"
-    f = fam[fk]
+    f = fam["bn_act_fwd (BN+stats+ReLU+pool, K4+K1)"]
     gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9
     bytes_pass, ms_k1, n_launch = stats_kernel_roofline(dev, n)
     achieved = bytes_pass / (ms_k1 * 1e-3) / 1e9
     roof_stats = {"bound": "hbm", "kernel": "bn_act_fwd_kernel (statistics hook fused into the norm pass: K4+K1), "
-                                            "timed inside the step", "achieved": gbs, "peak": peak, "peak_source": which,
-                  "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                  "traffic_sample": {"launch": "bn_act_fwd_kernel<0>, stem BN+ReLU (1605632 rows x 64 ch), ncu --set full, "
-                                               "profiles/r01_tanet_ncu_full.md", "dram_bytes": 767.6e6,
-                                     "algorithmic_bytes": 1605632 * 64 * 8.0, "us": 165.3},
-                  "launches_per_step": f["launches"],
-                  "ms_per_step": f["ms"],
+                                            "timed inside the step", "achieved": gbs, "peak": peak_hbm,
+                  "peak_source": which, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": _traffic("bn_act_fwd_kernel"),
+                  "launches_per_step": f["launches"], "ms_per_step": f["ms"],
                   "k1_standalone": {"kernel": "stats_cl_kernel over the 29 hooked layer shapes (hooks on stock modules)",
-                                    "achieved": achieved, "frac": achieved / peak,
+                                    "achieved": achieved, "frac": achieved / peak_hbm,
                                     "bytes_per_launch": bytes_pass / n_launch, "us_per_launch": ms_k1 * 1e3 / n_launch}}
-    step_table = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                      **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["flops"] else {}),
-                      **({"gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} if v["bytes"] else {})}
-                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-    cpu = None
+    cpu = gpu_ref = None
     if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_step(dev)
         v, cores, dt = cpu_port_clips_per_s(2, 1)
         cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-               "sample": "1 video x 1 view x 16x224x224 per step, 2 timed steps after 1 warm-up, torch-CPU fp32"}
+               "sample": "1 video x 1 view x 16x224x224 per step, 2 timed steps after 1 warm-up, torch-CPU fp32",
+               "configs0_eval_clips_per_s": cpu_cfg1_eval_clips_per_s(),
+               "configs0": "TANet-R50 source-only eval forward, 1 clip 8x224x224, batch 1, CPU (oracle port)"}
     line = {"metric": "clips/sec per TTA step", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "TANet-R50 ViTTA, synthetic gauss-corrupted 16x224x224, batch 8 per GPU, 1 view, "
                                    "stats-align only (L1, 47 hooks), SGD all params (BASELINE.json configs[1])",
                        "clips_per_step": world * n, "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
-                       "conv_backend": "own tcgen05 3xTF32 implicit GEMM, fwd / dgrad (incl. strided) / wgrad (3-channel stem conv: cuDNN fp32)", "with_eval_fwd_clips_per_s": world * n * 1000.0 / ms_eval,
-                       **({"operand_split": ops.gemm_precision(), "cta_pair": bool(args.cta_pair)}
-                          if (f16 or args.cta_pair) else {})},
+                       "operand_split": ops.gemm_precision(), "cta_pair": bool(args.cta_pair),
+                       "setup_steps_before_warmup": setup_steps,
+                       "with_eval_fwd_clips_per_s": world * n * 1000.0 / ms_eval},
             "e2e": {"value": world * n * 1000.0 / ms_e2e, "unit": "clips/s",
                     "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": launches, "cuda_graph": bool(targs.cuda_graph), "clocks": sampler.summary(), "roofline": roof, "roofline_stats": roof_stats,
-            "cpu_baseline": cpu, "kernels": step_table}
+            "gpu_launches": launches, "cuda_graph": bool(targs.cuda_graph), "clocks": sampler.summary(),
+            "roofline": roof, "roofline_stats": roof_stats, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
+            "secondary": secondary, "parity_check": parity, "kernels": _table(fam)}
     print(json.dumps(line))
     if world > 1:
         _hard_exit()
+
+
+def secondary_records(dev, pg, world, rank, timed, args):
+    """configs[2] (Swin-T, single GPU: rank-local, run by rank 0 only semantics -> every rank runs its own replica and
+    rank 0 reports, no collectives) and configs[4]'s shard (Swin-B, 4 videos x 2 views per GPU, sharded with C1 + C2)."""
+    import torch
+    from vitta_b200 import _lib, synth
+    out = []
+    steps = max(3, min(args.steps, 5))
+    for which, videos, tag, group in (("tiny", 8, "BASELINE.json configs[2]: Video-Swin-T ViTTA, 8 videos x 2 views x "
+                                       "32x224x224, stats-align + pred-consistency, 1 GPU (replica per rank, no "
+                                       "collectives)", None),
+                                      ("base", 4, "BASELINE.json configs[4] shard: Video-Swin-B ViTTA, 4 videos x 2 views "
+                                       "x 32x224x224 per GPU, stats-align + pred-consistency, sharded over the ranks "
+                                       "(C1 statistics all-gather + C2 gradient all-reduce)", pg)):
+        ad = build_swin(dev, group, which, videos)
+        x = synth.swin_loader_tensor(synth.synth_video(videos, 2, 32, 224, seed=200 + rank, tag="tta")).to(dev)
+        for _ in range(3):
+            ad.adapt(x)
+        l0 = _lib.launch_count
+        ms = timed(lambda: ad.adapt(x), steps) / steps
+        launches = (_lib.launch_count - l0) // steps
+        fam = attribute_step(ad, x)
+        mult = world if group is not None else 1
+        out.append({"workload": tag, "ms_per_step": ms, "videos_per_s": mult * videos * 1000.0 / ms,
+                    "clip_views_per_s": mult * videos * 2 * 1000.0 / ms, "n_gpus": mult, "steps": steps, "warmup": 3,
+                    "gpu_launches_per_step": launches, "hooks": len(ad.stat_reg_hooks), "kernels": _table(fam)})
+        del ad, x
+        torch.cuda.empty_cache()
+    return out
+
+
+def parity_check(dev, pg, world, rank):
+    """Multi-GPU parity on hardware: `world` ranks x 2 videos against ONE process holding the same 2*world videos --
+    loss, EMA statistics of every hooked layer and a slice of the updated weights -- over two full steps and one ragged
+    step with world-1 videos (the last rank idles through the collectives).  Small TANet (T=8, 64x64) so it costs ~1 s."""
+    import torch
+    import torch.distributed as dist
+    from vitta_b200 import synth
+    t, res, k = 8, 64, 11
+    ad_s, _, _, _ = build_tanet(dev, pg, 2 * world, False, t=t, res=res, k=k, lr=1e-3)
+    ad_1, _, _, _ = build_tanet(dev, None, 2 * world, False, t=t, res=res, k=k, lr=1e-3)
+    worst = {"loss_reg": 0.0, "ema_mean": 0.0, "ema_var": 0.0, "weights": 0.0}
+
+    def rel(a, b, floor):
+        return float(((a - b).abs() / (b.abs() + floor)).max())
+
+    for step, gv in enumerate((2 * world, 2 * world, world - 1)):
+        full = synth.tanet_loader_tensor(synth.synth_video(gv, 1, t, res, seed=400 + step, tag="tta")).to(dev)
+        base, rem = divmod(gv, world)
+        lo = rank * base + min(rank, rem)
+        hi = lo + base + (1 if rank < rem else 0)
+        r1 = ad_1.adapt(full)
+        if hi > lo:
+            rs = ad_s.adapt(full[lo:hi], global_videos=gv)
+            worst["loss_reg"] = max(worst["loss_reg"], rel(rs["loss_reg"], r1["loss_reg"], 1e-12))
+        else:
+            ad_s.adapt_idle(gv)
+        for hs, h1 in zip(ad_s.stat_reg_hooks, ad_1.stat_reg_hooks):
+            if getattr(hs, "_layer", None) is None:
+                continue
+            scale = float((h1.ema_mean.abs() + h1.ema_var.abs().sqrt()).max())
+            worst["ema_mean"] = max(worst["ema_mean"], rel(hs.ema_mean, h1.ema_mean, scale))
+            worst["ema_var"] = max(worst["ema_var"], rel(hs.ema_var, h1.ema_var, 1e-3 * float(h1.ema_var.max())))
+    sd_s, sd_1, sd_0 = ad_s.model.state_dict(), ad_1.model.state_dict(), None
+    for name in ("base_model.layer3.0.net.conv2.weight", "base_model.layer4.2.net.bn3.weight", "base_model.conv1.weight"):
+        worst["weights"] = max(worst["weights"], rel(sd_s[name], sd_1[name], 1e-3 * float(sd_1[name].abs().max())))
+    v = torch.tensor([worst[k_] for k_ in sorted(worst)], device=dev, dtype=torch.float64)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=pg)
+    out = dict(zip(sorted(worst), [float(x) for x in v.tolist()]))
+    out["tolerance"] = 1e-4
+    out["ok"] = all(x <= 1e-4 for x in v.tolist())
+    out["what"] = "%d ranks x 2 videos vs 1 process x %d videos (TANet T=8 64x64, 2 full steps + 1 ragged step with an " \
+                  "idle rank): max relative difference, max over ranks" % (world, 2 * world)
+    return out
 
 
 def _hard_exit():
@@ -458,12 +649,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true",
+                    help="skip the cpu_baseline and gpu_reference legs")
+    ap.add_argument("--no-secondary", dest="no_secondary", action="store_true", help="skip the Video-Swin records")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="N > 1: skip the sharded-vs-single check")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-graph-collectives", dest="no_graph_collectives", action="store_true",
                     help="multi-GPU: do not capture the NCCL collectives (falls back to eager steps)")
     ap.add_argument("--gemm-precision", dest="gemm_precision", default=None, choices=["tf32x3", "f16x3"],
-                    help="operand split of the dense contractions (default: the validated tf32x3; f16x3 is opt-in)")
+                    help="operand split of the dense contractions (default: the library default)")
     ap.add_argument("--cta-pair", dest="cta_pair", action="store_true",
                     help="opt-in: N = 256 tiles as cta_group::2 CTA pairs")
     ap.add_argument("--ncu-step", dest="ncu_step", action="store_true",

@@ -157,9 +157,13 @@ def _driver_worker(rank, world, port, out_dir):
         def __init__(self, model_origin, args, stats=None, process_group=None):
             assert process_group is dist.group.WORLD
 
-        def adapt(self, input, target=None, criterion=None):
+        def adapt(self, input, target=None, criterion=None, global_videos=None):
             seen["adapt"].append(input[:, 0, 0, 0].tolist())
+            seen.setdefault("global", []).append(global_videos)
             return {"loss_ce": None, "loss_reg": torch.tensor(1.0), "loss_consis": None}
+
+        def adapt_idle(self, global_videos):
+            seen.setdefault("idle", []).append(global_videos)
 
         def evaluate(self, input):
             vid = input[:, 0, 0, 0].long()
@@ -181,8 +185,27 @@ def _driver_worker(rank, world, port, out_dir):
     (acc,) = basics.tta_standard(torch.nn.Linear(2, 2), None, args=args)
     want_blocks = {0: [[0.0, 1.0], [4.0, 5.0], [8.0, 9.0]], 1: [[2.0, 3.0], [6.0, 7.0], [10.0]]}[rank]
     assert seen["adapt"] == want_blocks and seen["eval"] == [[int(v) for v in b] for b in want_blocks], seen
+    assert seen["global"] == [4, 4, 3] and "idle" not in seen          # every rank is told the GLOBAL batch size
     want_acc = 100.0 * sum(1 for v in range(n_videos) if v % 3 == 0) / n_videos
     assert abs(acc - want_acc) < 1e-4, (acc, want_acc)
+    # ragged tail with FEWER videos than ranks (used to raise after all the work was done): 5 videos in
+    # batches of 4 -> the last batch has 1 video; rank 1 idles through the step's collectives and skips the meters
+    for k in ("adapt", "eval", "global", "idle"):
+        seen[k] = []
+    args.dataset_factory = lambda a, split, kind: _LabelDataset(5)
+    (acc,) = basics.tta_standard(torch.nn.Linear(2, 2), None, args=args)
+    if rank == 0:
+        assert seen["adapt"] == [[0.0, 1.0], [4.0]] and seen["global"] == [4, 1] and seen["idle"] == [], seen
+    else:
+        assert seen["adapt"] == [[2.0, 3.0]] and seen["idle"] == [1] and seen["eval"] == [[2, 3]], seen
+    assert abs(acc - 100.0 * 2 / 5) < 1e-4, acc
+    # a batch size below the world size is refused up front, before any adaptation work
+    args.batch_size = 1
+    try:
+        basics.tta_standard(torch.nn.Linear(2, 2), None, args=args)
+        raise AssertionError("batch_size < world must be refused")
+    except ValueError as e:
+        assert "cannot be sharded" in str(e)
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 

@@ -69,12 +69,16 @@ def _run_case(name, dev):
         r = ad.adapt(tta_in[s].to(dev))
         # with n_gradient_steps > 1 the adapter reports the last gradient step of the batch
         pre = "step%d" % s if gsteps == 1 else "step%d.%d" % (s, gsteps - 1)
-        cases.assert_close(r["loss_reg"].cpu(), g[pre + "/loss_reg"], 1e-4, 1e-6, "loss_reg " + pre)
+        # KLD divides by the adapted variance: the loss is ill-conditioned in the statistics (tests/cases.py
+        # kld_loss_tolerance propagates the statistics' own tolerances through it); L1 / MSE are 1-Lipschitz-like
+        kld_tol = cases.kld_loss_tolerance(g, pre, src_m, src_v) if cfg["reg_type"] == "kld" else None
+        cases.assert_close(r["loss_reg"].cpu(), g[pre + "/loss_reg"], 1e-4,
+                           1e-6 + (sum(kld_tol.values()) if kld_tol else 0.0), "loss_reg " + pre)
         if cfg["consis"]:
             cases.assert_close(r["loss_consis"].cpu(), g[pre + "/loss_consis"], 1e-3, 1e-7, "loss_consis")
         for h, hook in enumerate(ad.stat_reg_hooks):
-            cases.assert_close(hook.r_feature.detach().cpu(), g["%s/r_feature/%d" % (pre, h)], 1e-4, 1e-6,
-                               "r_feature %d" % h)
+            cases.assert_close(hook.r_feature.detach().cpu(), g["%s/r_feature/%d" % (pre, h)], 1e-4,
+                               1e-6 + (kld_tol.get(h, 0.0) if kld_tol else 0.0), "r_feature %d" % h)
             k = "%s/ema_mean/%d" % (pre, h)
             if k in g:
                 em, ev = g[k], g["%s/ema_var/%d" % (pre, h)]
@@ -102,7 +106,10 @@ def _run_case(name, dev):
             scale = float(np.abs(g[k]).max()) + 1e-12
             # a delta is a difference of two fp32 weights: it is quantised to ulp(|w|) = 2^-23 |w|
             ulp = 1.2e-7 * float(sd0[n].abs().max())
-            cases.assert_close(d, g[k], 5e-3, 2e-3 * scale + ulp, k)
+            atol = 2e-3 * scale + ulp
+            if cfg.get("bn_affine"):
+                atol = cases.adam_delta_atol(g[k], cfg["lr"], cfg["steps"], atol)
+            cases.assert_close(d, g[k], 5e-3, atol, k)
 
 
 @pytest.mark.parametrize("name", ["tanet_t8_r64_consis_l1", "tanet_t8_r64_stats_mse", "tanet_t16_r224_stats_l1"])

@@ -35,7 +35,17 @@ def test_bench_touches_the_oracle_only_in_the_cpu_baseline_leg():
         uses = [n for n in ast.walk(fn) if isinstance(n, (ast.Import, ast.ImportFrom))
                 and any("oracle" in (getattr(n, "module", None) or "") or "oracle" in a.name for a in n.names)]
         if uses:
-            assert fn.name == "cpu_port_clips_per_s", fn.name
+            assert fn.name == "_oracle_tanet_state", fn.name
+    # ... and that loader is only called by the baseline legs (CPU port, configs[0] CPU forward, reference-on-GPU record:
+    # baselines measured BESIDE the product, never the product path)
+    callers = {fn.name for fn in ast.walk(tree) if isinstance(fn, ast.FunctionDef)
+               for n in ast.walk(fn) if isinstance(n, ast.Call) and getattr(n.func, "id", None) == "_oracle_tanet_state"}
+    assert callers == {"cpu_port_clips_per_s", "cpu_cfg1_eval_clips_per_s", "gpu_reference_step"}, callers
+    baseline_legs = callers | {"_oracle_tanet_state"}
+    product = {"build_tanet", "build_swin", "secondary_records", "parity_check", "attribute_step", "stats_kernel_roofline"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in product]:
+        names = {getattr(n.func, "id", None) for n in ast.walk(fn) if isinstance(n, ast.Call)}
+        assert not (names & baseline_legs), (fn.name, names & baseline_legs)
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     assert not any("oracle" in (getattr(n, "module", None) or "") for n in top)
 

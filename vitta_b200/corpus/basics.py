@@ -199,6 +199,7 @@ class OnlineAdapter:
             self.model = model = freeze_except_bn(model, bn_condidiate_layers=kinds)
             params, _ = collect_bn_params(model, bn_candidate_layers=kinds)
             self.optimizer = torch.optim.Adam(params, lr=args.lr, betas=(0.9, 0.999), weight_decay=0.)
+            self._adam_params = list(params)      # multi-GPU: their gradients are summed over ranks before Adam.step
         else:
             self.optimizer = ops.FusedSGD(model.parameters(), lr=args.lr, momentum=args.momentum,
                                           weight_decay=args.weight_decay, process_group=process_group)
@@ -206,6 +207,7 @@ class OnlineAdapter:
         # hooks (:564-601)
         from ..utils import norm_stats_utils as nsu
         nsu.set_process_group(process_group)
+        nsu.new_align_generation()          # this adapter's hooks share ONE arena, and only with each other
         self.stat_reg_hooks = []
         self.hooked_layers = []
         if args.stat_reg == 'mean_var':
@@ -235,11 +237,31 @@ class OnlineAdapter:
         self._hooks_on = True
 
     # -- :606-677 -------------------------------------------------------------------------------
-    def adapt(self, input, target=None, criterion=None):
+    def _arenas(self):
+        seen = []
+        for h in self.stat_reg_hooks:
+            a = getattr(h, '_arena', None)
+            if a is not None and all(a is not b for b in seen):
+                seen.append(a)
+        return seen
+
+    def adapt(self, input, target=None, criterion=None, global_videos=None):
         """One adaptation step.  With ``args.cuda_graph`` (and no label-dependent logging) the step is captured into a
-        CUDA graph after 3 eager steps and replayed afterwards; results are identical (same kernels, same order)."""
+        CUDA graph after 3 eager steps and replayed afterwards; results are identical (same kernels, same order).
+        ``global_videos`` (multi-GPU): videos of the whole loader batch this shard was cut from; defaults to
+        world x local.  A value below the world size marks a ragged step in which some ranks call :meth:`adapt_idle`."""
         args = self.args
-        graphable = (getattr(args, 'cuda_graph', False) and criterion is None and input.is_cuda
+        self._ragged = False
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+            gv = input.shape[0] * world if global_videos is None else int(global_videos)
+            n_views = args.n_augmented_views if args.if_sample_tta_aug_views else self.n_clips
+            per_video = n_views * (args.test_crops if args.arch == 'tanet' else 1)
+            for a in self._arenas():
+                a.global_clips = gv * per_video
+            self._ragged = gv < world
+        graphable = (getattr(args, 'cuda_graph', False) and criterion is None and input.is_cuda and not self._ragged
                      and (self.process_group is None or getattr(args, 'cuda_graph_collectives', False))
                      and getattr(args, 'moving_avg', False)
                      and not args.update_only_bn_affine and args.n_gradient_steps == 1)
@@ -335,9 +357,60 @@ class OnlineAdapter:
                 loss = loss_reg                                        # :667: lambda_feature_reg not applied
             self.optimizer.zero_grad()
             loss.backward()
+            if getattr(self, '_ragged', False):
+                self._live_mask = self._exchange_live_mask()     # idle ranks are waiting for it (adapt_idle)
+            self._sync_foreign_grads()
             self.optimizer.step()
         return {'output': output.detach(), 'loss_reg': loss_reg.detach(), 'loss': loss.detach(),
                 'loss_consis': None if loss_consis is None else loss_consis.detach(), 'loss_ce': loss_ce}
+
+    def _exchange_live_mask(self):
+        if isinstance(self.optimizer, ops.FusedSGD):
+            return self.optimizer.exchange_live_mask()
+        import torch.distributed as dist
+        dev = self._adam_params[0].device
+        mask = torch.tensor([1 if p.grad is not None else 0 for p in self._adam_params], dtype=torch.uint8, device=dev)
+        dist.broadcast(mask, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+        return [bool(v) for v in mask.tolist()]
+
+    def adapt_idle(self, global_videos):
+        """The step of a rank that holds NO video of a ragged global batch (fewer videos than ranks): zero-count
+        statistics into collective C1, zero gradients into C2, and the same optimiser update as everyone else --
+        otherwise meters and weights would diverge between ranks.  Same collective order as
+        :meth:`_adapt_eager`: C1 (one per arena), live-mask broadcast, C2."""
+        args = self.args
+        if self.process_group is None:
+            raise RuntimeError("adapt_idle: only meaningful under a process group")
+        dev = next(self.model.parameters()).device
+        n_views = args.n_augmented_views if args.if_sample_tta_aug_views else self.n_clips
+        per_video = n_views * (args.test_crops if args.arch == 'tanet' else 1)
+        for _ in range(args.n_gradient_steps):
+            for a in self._arenas():
+                a.global_clips = int(global_videos) * per_video
+                a.finalize_idle(dev)
+            if isinstance(self.optimizer, ops.FusedSGD):
+                self.optimizer.step_idle()
+            else:
+                live = self._exchange_live_mask()
+                self.optimizer.zero_grad()
+                for p, on in zip(self._adam_params, live):
+                    p.grad = torch.zeros_like(p) if on else None
+                self._sync_foreign_grads()
+                self.optimizer.step()
+                self.optimizer.zero_grad()
+
+    def _sync_foreign_grads(self):
+        """Collective C2 for the optimisers that are not ours: FusedSGD all-reduces inside step(); torch's Adam on the
+        norm-affine parameters (--update_only_bn_affine, reference :547-557) knows nothing about ranks, so the summed
+        full-batch gradient is formed here -- every rank then takes the single-process update."""
+        if self.process_group is None or isinstance(self.optimizer, ops.FusedSGD):
+            return
+        live = [p for p in self._adam_params if p.grad is not None]
+        if not live:
+            return
+        summed, _ = ops.allreduce_grads([p.grad for p in live], self.process_group)
+        for p, g in zip(live, summed):
+            p.grad.copy_(g)
 
     def hooks_off(self):
         for h in self.stat_reg_hooks:        # :682-684
@@ -388,18 +461,29 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
     if pg is not None:
         import torch.distributed as dist
         rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+        if args.batch_size < world:
+            # checked BEFORE any work: every full batch would leave ranks idle (a ragged tail alone is fine, below)
+            raise ValueError("--batch_size %d cannot be sharded over %d ranks: launch at most batch_size processes or "
+                             "raise the batch size (the global batch is split over the ranks)" % (args.batch_size, world))
     for batch_id, (input, target) in enumerate(tta_loader):
         if args.if_tta_standard == 'tta_standard' or batch_id == 0:
             adapter = OnlineAdapter(model_origin, args, stats, pg)
+        global_videos = input.shape[0]
         if pg is not None:
-            if input.shape[0] < world:
-                raise RuntimeError("batch of %d videos cannot be sharded over %d ranks (every rank must take part in "
-                                   "the step's collectives)" % (input.shape[0], world))
             input, target = shard_batch(input, target, rank, world)
         actual_bz = input.shape[0]
+        if actual_bz == 0:
+            # ragged tail with fewer videos than ranks: this rank has nothing to forward but still takes part in the
+            # step's collectives and applies the common update; it contributes nothing to the accuracy meters
+            adapter.adapt_idle(global_videos)
+            next(eval_iter)
+            continue
         input = input.to(device, non_blocking=True)
         target = target.to(device, non_blocking=True)
-        res = adapter.adapt(input, target, criterion)
+        if pg is not None:
+            res = adapter.adapt(input, target, criterion, global_videos=global_videos)
+        else:
+            res = adapter.adapt(input, target, criterion)
         if res['loss_ce'] is not None:
             losses_ce.update(res['loss_ce'].item(), actual_bz)
         losses_reg.update(res['loss_reg'].item(), actual_bz)

@@ -54,6 +54,48 @@ def _maybe_init_distributed(args):
     args.gpus = [local]
 
 
+def resolve_dataset_factory(args):
+    """``VITTA_DATASET_FACTORY=package.module:callable`` (or ``args.dataset_factory`` set by the caller) plugs a real
+    loader -- ``callable(args, split, dataset_type) -> torch Dataset`` in the reference's loader layout, e.g.
+    ``vitta_b200.corpus.views:DecodedVideoDataset.factory`` -- into the entry scripts."""
+    import importlib
+    import os
+    spec = os.environ.get("VITTA_DATASET_FACTORY")
+    if getattr(args, 'dataset_factory', None) is None and spec:
+        mod, _, attr = spec.partition(":")
+        obj = importlib.import_module(mod)
+        for part in attr.split("."):
+            obj = getattr(obj, part)
+        args.dataset_factory = obj
+    return getattr(args, 'dataset_factory', None)
+
+
+def check_inputs_or_synthetic(args, model_given):
+    """The run needs a checkpoint, a dataset and (for mean_var alignment) source statistics.  Anything missing is an
+    error unless the caller explicitly asks for the synthetic stand-ins (``args.synthetic`` / ``VITTA_SYNTHETIC=1``:
+    seeded random weights, synthetic videos, statistics fabricated from a synthetic clean set) -- a result file
+    written from stand-ins must never look like a measured accuracy."""
+    import os
+    import sys
+    missing = []
+    if not model_given and not getattr(args, 'model_path', None):
+        missing.append("model_path (checkpoint)")
+    if resolve_dataset_factory(args) is None:
+        missing.append("dataset (args.dataset_factory / VITTA_DATASET_FACTORY)")
+    if (args.tta and args.stat_reg == 'mean_var' and args.compute_stat in (False, 'False')
+            and getattr(args, 'source_stats', None) is None and not getattr(args, 'spatiotemp_mean_clean_file', None)):
+        missing.append("source statistics (spatiotemp_mean/var_clean_file)")
+    if not missing:
+        return []
+    if not (getattr(args, 'synthetic', False) or os.environ.get("VITTA_SYNTHETIC") == "1"):
+        raise RuntimeError("missing inputs: %s.  Provide them, or set VITTA_SYNTHETIC=1 (args.synthetic=True) to run on "
+                           "seeded random weights / synthetic videos / fabricated statistics on purpose."
+                           % "; ".join(missing))
+    sys.stderr.write("vitta_b200: SYNTHETIC RUN -- stand-ins used for: %s. Accuracies are meaningless.\n"
+                     % "; ".join(missing))
+    return missing
+
+
 def eval(args=None, model=None):
     log_time = time.strftime("%Y%m%d_%H%M%S")
     make_dir(args.result_dir)
@@ -67,6 +109,9 @@ def eval(args=None, model=None):
     if not torch.cuda.is_available():
         raise RuntimeError("vitta_b200 needs a CUDA device (sm_100a); there is no CPU path")
     set_fp32_exact()
+    args.synthetic_stand_ins = check_inputs_or_synthetic(args, model is not None)
+    if args.synthetic_stand_ins:
+        logger.debug('SYNTHETIC RUN, stand-ins for: ' + '; '.join(args.synthetic_stand_ins))
     _maybe_init_distributed(args)
     if model is None:
         model = get_model(args, num_classes, logger)

@@ -125,6 +125,10 @@ class StatsArena:
         self._base = None
         self.total_C = 0
         self.finalize_calls = 0
+        # multi-GPU: clips (videos x views) of the GLOBAL batch of the current step, set by the adaptation driver.  The
+        # AverageMeterTensor weights n / (count + n) use the reference's full-batch n (utils/utils_.py:198-202), which a
+        # rank cannot derive from its own shard when the batch is ragged.
+        self.global_clips = None
 
     # -- registration ---------------------------------------------------------------------------
     def add_layer(self, C_, src_mean, src_var, reg_type, moving_avg, momentum, name=""):
@@ -232,7 +236,7 @@ class StatsArena:
             if ly.moving_avg:
                 d.w_new, d.w_old = ly.momentum, 1.0 - ly.momentum
             else:
-                n = ly.n_batch
+                n = self._meter_n(ly)
                 d.w_new = n / float(ly.meter_count + n)
                 d.w_old = ly.meter_count / float(ly.meter_count + n)
             if gathered is None:
@@ -290,13 +294,45 @@ class StatsArena:
             call("vitta_stats_finalize", ptr(self._desc_gath), n, ptr(means), ptr(counts), ptr(self.src_mean),
                  ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
                  ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, self.max_C, st)
+        self._finish(active)
+
+    def _meter_n(self, ly):
+        return int(self.global_clips) if (self.process_group is not None and self.global_clips) else ly.n_batch
+
+    def _finish(self, active):
         for ly in active:
             if not ly.moving_avg:
-                ly.meter_count += ly.n_batch
+                ly.meter_count += self._meter_n(ly)
         self._loss_index = {ly.idx: i for i, ly in enumerate(active)}
-        self._n_active = n
+        self._n_active = len(active)
         self.finalized = True
         self.finalize_calls += 1
+
+    def finalize_idle(self, dev):
+        """This rank holds no video of the step's global batch (ragged tail with fewer videos than ranks): take part in
+        collective C1 with an all-zero payload (count 0 entries are skipped by the Chan merge) and run the same gathered
+        finalize as every other rank, so that meters, loss and coefficients stay identical everywhere."""
+        if self.process_group is None:
+            raise _lib.VittaError("finalize_idle: only meaningful with a process group")
+        self._freeze(dev)
+        active = list(self.layers)           # every registered layer fires in a forward pass
+        n = len(active)
+        ws = torch.distributed.get_world_size(self.process_group)
+        self._desc_gath_host = self._upload(self._build_descs(active, (ws, n)))
+        self._desc_gath = self._desc_gath_host.to(dev, non_blocking=True)
+        ids = tuple(ly.idx for ly in active)
+        if ids != self._desc_active:
+            self.loss.zero_()
+            self._desc_active = ids
+        self.desc_dirty = True               # the local (non-gathered) descriptors were not built
+        pay, merged, cnts = stats_payload(self.total_C, n, dev)
+        pay.zero_()
+        means, counts = gather_stats_payload(pay, self.total_C, self.process_group)
+        self._gath_keep = (means, counts)
+        call("vitta_stats_finalize", ptr(self._desc_gath), n, ptr(means), ptr(counts), ptr(self.src_mean),
+             ptr(self.src_var), ptr(self.ema_mean), ptr(self.ema_var), ptr(self.batch_mean), ptr(self.batch_var),
+             ptr(self.coef_a), ptr(self.coef_b), ptr(self.loss), 0, None, None, self.max_C, stream_ptr())
+        self._finish(active)
 
     def layer_loss(self, ly):
         """r_feature of one layer: differentiable w.r.t. the layer's token (see _RFeature)."""
@@ -565,6 +601,7 @@ class FusedSGD:
         self._block = None
         self._pin = []
         self._pin_next = 0
+        self._pin_cap = 0
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -584,18 +621,44 @@ class FusedSGD:
             starts.append(blk)
             blk += (p.numel() + self._block - 1) // self._block
         # Pinned staging buffers allocated ONCE (no host allocation may happen while a CUDA graph is being captured) and
-        # non-blocking copies (memcpy nodes inside a capture).  Alternating slots keep the previous tables' sources intact.
+        # non-blocking copies (memcpy nodes inside a capture).  Eager steps rotate through slots 0-3 so that the previous
+        # tables' sources stay intact; tables built DURING a capture use the reserved slots 4-5, which no eager step
+        # ever rewrites -- a graph replay re-reads its memcpy node's pinned source every time (after four
+        # eager steps a captured slot of the rotation would have held stale gradient pointers).
         nbytes = C.sizeof(_lib.VittaSgdTensor) * len(self.params)
         if not self._pin:
             self._pin = [(torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
-                          torch.empty(len(self.params), dtype=torch.int32).pin_memory()) for _ in range(4)]
-        tab_h, st_h = self._pin[self._pin_next % 4]
-        self._pin_next += 1
+                          torch.empty(len(self.params), dtype=torch.int32).pin_memory()) for _ in range(6)]
+        if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            tab_h, st_h = self._pin[4 + self._pin_cap % 2]
+            self._pin_cap += 1
+        else:
+            tab_h, st_h = self._pin[self._pin_next % 4]
+            self._pin_next += 1
         raw = bytes(arr)
         C.memmove(tab_h.data_ptr(), raw, len(raw))
         st_np = (C.c_int32 * n)(*starts)
         C.memmove(st_h.data_ptr(), st_np, 4 * n)
         return (tab_h[:len(raw)].to(dev, non_blocking=True), st_h[:n].to(dev, non_blocking=True), n, blk)
+
+    def exchange_live_mask(self):
+        """Ragged global batch (some rank holds no video): group rank 0 -- which always holds one -- tells every rank
+        which parameters received a gradient, so that idle ranks can contribute zeros of the right layout to C2."""
+        import torch.distributed as dist
+        dev = self.params[0].device
+        mask = torch.tensor([1 if p.grad is not None else 0 for p in self.params], dtype=torch.uint8, device=dev)
+        dist.broadcast(mask, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+        return [bool(v) for v in mask.tolist()]
+
+    @torch.no_grad()
+    def step_idle(self):
+        """The step of a rank without videos: zero gradients for rank 0's live set, then the common all-reduce + update
+        (the weights must move exactly as on the ranks that did the work)."""
+        live = self.exchange_live_mask()
+        for p, on in zip(self.params, live):
+            p.grad = torch.zeros_like(p) if on else None
+        self.step()
+        self.zero_grad()
 
     @torch.no_grad()
     def step(self):

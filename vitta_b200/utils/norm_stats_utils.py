@@ -54,6 +54,15 @@ def reset_arenas():
     _align_gen, _stat_gen = _Generation(), _Generation()
 
 
+def new_align_generation():
+    """The alignment hooks constructed from now on get an arena of their own.  ``OnlineAdapter`` calls this before it
+    builds its hooks, so that two adapters alive at the same time (bench.py runs several workloads in one process; a
+    sharded and an unsharded adapter are compared in the multi-GPU parity check) never share statistics buffers --
+    the implicit rule of :class:`_Generation` only separates generations whose hooks were closed."""
+    global _align_gen
+    _align_gen = _Generation()
+
+
 def _is_fused_module(module):
     return getattr(module, "_vitta_fused", False)
 
