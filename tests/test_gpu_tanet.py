@@ -177,3 +177,16 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         torch.testing.assert_close(og, oe, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(evg, eve, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(w2g, w2e, rtol=1e-5, atol=1e-9)
+
+
+def test_tanet_golden_under_both_operand_splits(cuda_device):
+    """The library default is the fp16 hi/lo split (f16x3); the tf32 split stays selectable.  The small reference golden
+    must hold under BOTH (the other goldens of this file run under the default)."""
+    from vitta_b200 import ops
+    before = ops.gemm_precision()
+    try:
+        for prec in ("tf32x3", "f16x3"):
+            ops.set_gemm_precision(prec)
+            _run_case("tanet_t8_r64_stats_mse", cuda_device)
+    finally:
+        ops.set_gemm_precision(before)

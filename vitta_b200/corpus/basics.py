@@ -348,9 +348,11 @@ class OnlineAdapter:
                     loss_consis = compute_pred_consis(view_cls_score)
             if criterion is not None and target is not None:
                 loss_ce = criterion(output.detach(), target)        # logging only (:657)
-            loss_reg = torch.zeros((), dtype=torch.float32, device=x.device)
-            for hook in self.stat_reg_hooks:
-                loss_reg = loss_reg + hook.r_feature
+            loss_reg = self._total_alignment_loss()
+            if loss_reg is None:
+                loss_reg = torch.zeros((), dtype=torch.float32, device=x.device)
+                for hook in self.stat_reg_hooks:
+                    loss_reg = loss_reg + hook.r_feature
             if self.if_pred_consistency:
                 loss = args.lambda_feature_reg * loss_reg + args.lambda_pred_consis * loss_consis
             else:
@@ -363,6 +365,24 @@ class OnlineAdapter:
             self.optimizer.step()
         return {'output': output.detach(), 'loss_reg': loss_reg.detach(), 'loss': loss.detach(),
                 'loss_consis': None if loss_consis is None else loss_consis.detach(), 'loss_ce': loss_ce}
+
+    def _total_alignment_loss(self):
+        """sum_h hook.r_feature in one autograd node when every contributing hook lives in this adapter's single arena
+        (the BatchNorm1d hooks contribute exact zeros, reference utils/norm_stats_utils.py:158-183)."""
+        arenas = self._arenas()
+        if len(arenas) != 1:
+            return None
+        layers = []
+        for h in self.stat_reg_hooks:
+            ly = getattr(h, '_layer', None)
+            if ly is None:
+                if not getattr(h, '_is_bn1d', False):
+                    return None
+                continue
+            if ly.geom_key is None or not ly.fired:
+                return None
+            layers.append(ly)
+        return arenas[0].total_loss(layers) if layers else None
 
     def _exchange_live_mask(self):
         if isinstance(self.optimizer, ops.FusedSGD):

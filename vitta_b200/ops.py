@@ -23,7 +23,7 @@ def _require_cuda(t, what):
 
 
 def _fused_amax():
-    """Producers emit the operand range of their outputs only on the opt-in fp16-split path."""
+    """Producers emit the operand range (max|out|) of their outputs when the consumers run the fp16 split."""
     return _gemm_precision == "f16x3" and _FUSED_AMAX
 
 
@@ -342,6 +342,21 @@ class StatsArena:
             return self.loss[i].clone()
         return _RFeature.apply(ly.token, self.loss, i)
 
+    def total_loss(self, layers):
+        """Sum of r_feature over ``layers`` when they are exactly the layers of this step, as ONE autograd node.
+
+        The finalize kernel already adds the per-layer losses in layer order (fp32, starting from 0) -- the arithmetic
+        of the driver's ``loss_reg += hook.r_feature`` loop (reference corpus/basics.py:659-661) -- so the 2 x 47 tiny
+        clone / add launches of that loop and their backward nodes collapse into one read.  Returns None when the layer
+        set does not match (the caller then sums the hooks one by one)."""
+        self.finalize()
+        if [ly.idx for ly in layers] != sorted(self._loss_index) or len(layers) != self._n_active:
+            return None
+        toks = [ly.token for ly in layers]
+        if any(t is None or not t.requires_grad for t in toks):
+            return None
+        return _RTotal.apply(self.loss, self._n_active, *toks)
+
     def vec(self, t, ly):
         return t[ly.ch_off:ly.ch_off + ly.C]
 
@@ -362,6 +377,19 @@ class _RFeature(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return g, None, None
+
+
+class _RTotal(torch.autograd.Function):
+    """Total alignment loss (slot n_layers of the finalize kernel's loss vector) tied to every layer's token."""
+
+    @staticmethod
+    def forward(ctx, loss, n, *tokens):
+        ctx.n_tok = len(tokens)
+        return loss[n].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + (g,) * ctx.n_tok
 
 
 def new_token(ref):
@@ -471,10 +499,9 @@ class BNActFn(torch.autograd.Function):
         has_res, has_res_bn = res is not None, w2 is not None
         gx = torch.empty_like(x)
         gres = torch.empty_like(res) if has_res else None
-        gw = torch.zeros(Cc, dtype=torch.float32, device=dev)
-        gb = torch.zeros(Cc, dtype=torch.float32, device=dev)
-        gw2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
-        gb2 = torch.zeros(Cc, dtype=torch.float32, device=dev) if has_res_bn else None
+        gparam = torch.zeros(4 if has_res_bn else 2, Cc, dtype=torch.float32, device=dev)     # one fill, not four
+        gw, gb = gparam[0], gparam[1]
+        gw2, gb2 = (gparam[2], gparam[3]) if has_res_bn else (None, None)
         ca = cb = cm = gs = ca2 = cb2 = cm2 = gs2 = None
         if ly_main is not None and gtok_main is not None:
             ca, cb, cm = arena.coef_ptrs(ly_main)
@@ -856,10 +883,12 @@ def _cached_split(w, mode, kind, make):
     return ent[1]
 
 
-# Operand split of the dense contractions: "tf32x3" (default, hardware-validated) or "f16x3" (opt-in until validated on
-# hardware, DESIGN.md section 9: forward, data-gradient and weight-gradient convolutions / Linear layers on kind::f16 with
-# per-tensor amax scaling; the window-attention kernels keep the tf32 split).  Also settable with VITTA_GEMM_PRECISION.
-_gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "tf32x3")
+# Operand split of the dense contractions: "f16x3" (default since round 2: fp16 hi/lo pieces on
+# kind::f16 with per-tensor power-of-two scales from amax -- the same ~2^-21 per-product error as the tf32 split at half
+# the tensor-pipe work and half the weight bytes; validated on hardware against float64 and the reference goldens) or
+# "tf32x3" (hi/lo tf32 pieces on kind::tf32).  Covers forward, data-gradient and weight-gradient convolutions / Linear
+# layers; the window-attention kernels keep the tf32 split.  Settable with VITTA_GEMM_PRECISION / set_gemm_precision().
+_gemm_precision = os.environ.get("VITTA_GEMM_PRECISION", "f16x3")
 _FUSED_AMAX = os.environ.get("VITTA_FUSED_AMAX", "1") == "1"    # f16x3 only: 0 = always use standalone amax passes
 
 
