@@ -116,13 +116,15 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
     const int64_t off0 = row0 * C + c;
     ky = apply_aff(a, ldg4(x + off0));
     if (RES == 2) kr = apply_aff(a2, ldg4(res + off0));
-#pragma unroll 8
-    for (int r = slot; r < nrows; r += rs) {
-      const int64_t off = off0 + (int64_t)r * C;
-      float4 y = apply_aff(a, ld_stream4(x + off));
+    // Rows are processed in batches whose loads are ALL issued before the first use: a plain `for (r < nrows)` loop,
+    // even unrolled, keeps one 16-byte load in flight per thread (the trip count is dynamic, so every copy of the body
+    // ends in an exit branch and ptxas will not hoist loads across it) -- 16 KB in flight per SM, which is what held
+    // this kernel at 0.6 of the copy bandwidth in round 1 (profiles/r01_tanet_ncu_full.md).
+    constexpr int kB = (RES == 0) ? 8 : 4;
+    auto body = [&](float4 xv, float4 rr, int64_t off) {
+      float4 y = apply_aff(a, xv);
       if (part_main) acc_shift(s1, s2, y, ky);
       if (RES != 0) {
-        float4 rr = ld_stream4(res + off);
         if (RES == 2) {
           rr = apply_aff(a2, rr);
           if (part_res) acc_shift(r1, r2, rr, kr);
@@ -135,6 +137,27 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const float* __res
       st4(out + off, y);
       if constexpr (AMAX) am = amax4(am, y);
       pool.x += y.x; pool.y += y.y; pool.z += y.z; pool.w += y.w;
+    };
+    const int64_t rstep = (int64_t)rs * C;
+    int r = slot;
+    for (; r + (kB - 1) * rs < nrows; r += kB * rs) {
+      const int64_t off = off0 + (int64_t)r * C;
+      float4 xv[kB], rv[kB];
+#pragma unroll
+      for (int j = 0; j < kB; ++j) xv[j] = ld_stream4(x + off + j * rstep);
+      if (RES != 0) {
+#pragma unroll
+        for (int j = 0; j < kB; ++j) rv[j] = ld_stream4(res + off + j * rstep);
+      }
+#pragma unroll
+      for (int j = 0; j < kB; ++j) body(xv[j], RES != 0 ? rv[j] : f4zero(), off + j * rstep);
+    }
+    for (; r < nrows; r += rs) {
+      const int64_t off = off0 + (int64_t)r * C;
+      const float4 xv = ld_stream4(x + off);
+      float4 rr = f4zero();
+      if (RES != 0) rr = ld_stream4(res + off);
+      body(xv, rr, off);
     }
   }
   if constexpr (AMAX) amax_commit(am, amax_out);
@@ -234,17 +257,12 @@ __device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restr
         gp.x *= p.inv_frame_rows; gp.y *= p.inv_frame_rows; gp.z *= p.inv_frame_rows; gp.w *= p.inv_frame_rows;
       }
       const int64_t off0 = row0 * C + c;
-#pragma unroll 2
-      for (int r = slot; r < nrows; r += p.rs) {
-        const int64_t off = off0 + (int64_t)r * C;
-        const float4 xv = ld_stream4(p.x + off);
-        float4 g = ld_stream4(p.gout + off);
+      // batched like the forward: all loads of kB rows are in flight before the first use
+      constexpr int kB = 4;
+      auto body = [&](float4 xv, float4 g, float4 rx, int64_t off) {
         const float4 y = apply_aff(a, xv);
-        float4 rr = f4zero(), rx = f4zero();
-        if (RES != 0) {
-          rx = ld_stream4(p.res + off);
-          rr = (RES == 2) ? apply_aff(a2, rx) : rx;
-        }
+        float4 rr = f4zero();
+        if (RES != 0) rr = (RES == 2) ? apply_aff(a2, rx) : rx;
         g.x += gp.x; g.y += gp.y; g.z += gp.z; g.w += gp.w;
         if (p.relu) {
           g.x = (y.x + rr.x > 0.f) ? g.x : 0.f; g.y = (y.y + rr.y > 0.f) ? g.y : 0.f;
@@ -270,6 +288,30 @@ __device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restr
           agw2.x = fmaf(gr.x, (rx.x - a2.rm.x) * a2.istd.x, agw2.x); agw2.y = fmaf(gr.y, (rx.y - a2.rm.y) * a2.istd.y, agw2.y);
           agw2.z = fmaf(gr.z, (rx.z - a2.rm.z) * a2.istd.z, agw2.z); agw2.w = fmaf(gr.w, (rx.w - a2.rm.w) * a2.istd.w, agw2.w);
         }
+      };
+      const int64_t rstep = (int64_t)p.rs * C;
+      int r = slot;
+      for (; r + (kB - 1) * p.rs < nrows; r += kB * p.rs) {
+        const int64_t off = off0 + (int64_t)r * C;
+        float4 xv[kB], gv[kB], rv[kB];
+#pragma unroll
+        for (int j = 0; j < kB; ++j) xv[j] = ld_stream4(p.x + off + j * rstep);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) gv[j] = ld_stream4(p.gout + off + j * rstep);
+        if (RES != 0) {
+#pragma unroll
+          for (int j = 0; j < kB; ++j) rv[j] = ld_stream4(p.res + off + j * rstep);
+        }
+#pragma unroll
+        for (int j = 0; j < kB; ++j) body(xv[j], gv[j], RES != 0 ? rv[j] : f4zero(), off + j * rstep);
+      }
+      for (; r < nrows; r += p.rs) {
+        const int64_t off = off0 + (int64_t)r * C;
+        const float4 xv = ld_stream4(p.x + off);
+        const float4 g = ld_stream4(p.gout + off);
+        float4 rx = f4zero();
+        if (RES != 0) rx = ld_stream4(p.res + off);
+        body(xv, g, rx, off);
       }
     }
   }

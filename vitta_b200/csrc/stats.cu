@@ -40,15 +40,27 @@ __global__ void __launch_bounds__(kThreads) stats_cl_kernel(const float* __restr
   if (active) {
     const float* base = x + row0 * C + (int64_t)col4 * 4;
     k = ldg4(base);
-#pragma unroll 8
-    for (int r = slot; r < nrows; r += rs) {
-      float4 v = ld_stream4(base + (int64_t)r * C);
+    auto acc = [&](float4 v) {
       float d;
       d = v.x - k.x; s1.x += d; s2.x = fmaf(d, d, s2.x);
       d = v.y - k.y; s1.y += d; s2.y = fmaf(d, d, s2.y);
       d = v.z - k.z; s1.z += d; s2.z = fmaf(d, d, s2.z);
       d = v.w - k.w; s1.w += d; s2.w = fmaf(d, d, s2.w);
+    };
+    // explicit batches of 8 rows: all eight 16-byte loads are issued before the first use (a dynamic-trip-count loop keeps
+    // one load in flight per thread, see bn_act.cu)
+    constexpr int kB = 8;
+    const int64_t rstep = (int64_t)rs * C;
+    int r = slot;
+    for (; r + (kB - 1) * rs < nrows; r += kB * rs) {
+      const float* q = base + (int64_t)r * C;
+      float4 v[kB];
+#pragma unroll
+      for (int j = 0; j < kB; ++j) v[j] = ld_stream4(q + j * rstep);
+#pragma unroll
+      for (int j = 0; j < kB; ++j) acc(v[j]);
     }
+    for (; r < nrows; r += rs) acc(ld_stream4(base + (int64_t)r * C));
   }
   sm1[tid] = s1;
   sm2[tid] = s2;
@@ -363,7 +375,7 @@ int vitta_stats_inject(const float* x, const float* yscale, const float* yshift,
   VITTA_CHECK_ARG(x && coef_a && coef_b && mean && gscale && gy, VITTA_E_BADARG, "stats_inject: null pointer");
   VITTA_CHECK_ARG((yscale == nullptr) == (yshift == nullptr), VITTA_E_BADARG, "stats_inject: scale/shift mismatch");
   const int64_t n = O * C * I;
-  const int sms = 148;
+  const int sms = vitta_sm_count() > 0 ? vitta_sm_count() : 148;
   if (I == 1 && C % 4 == 0 && aligned16(x) && aligned16(gy)) {
     int64_t n4 = n / 4;
     int64_t blocks = (n4 + kThreads - 1) / kThreads;

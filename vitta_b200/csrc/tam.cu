@@ -33,17 +33,35 @@ __global__ void __launch_bounds__(kThreads) tam_fwd_kernel(const float* __restri
   float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 cur = mul4(ldg4(ab), ld_stream4(xb));
   float am = 0.f;
-#pragma unroll 4
-  for (int t = 0; t < T; ++t) {
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t + 1 < T) nxt = mul4(ldg4(ab + (int64_t)(t + 1) * C), ld_stream4(xb + (int64_t)(t + 1) * ts));
-    float4 o = mul4(k0, prev);
-    o = fma4(k1, cur, o);
-    o = fma4(k2, nxt, o);
-    st4(ob + (int64_t)t * ts, o);
-    if constexpr (AMAX) am = fmaxf(fmaxf(am, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-    prev = cur;
-    cur = nxt;
+  // four frames per batch, their loads issued together (predicated past the clip's end): a frame-by-frame loop keeps a
+  // single 16-byte load in flight per thread
+  constexpr int kB = 4;
+  for (int t0 = 0; t0 < T; t0 += kB) {
+    float4 xn[kB], an[kB];
+#pragma unroll
+    for (int j = 0; j < kB; ++j) {
+      const int t = t0 + j + 1;
+      xn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      an[j] = xn[j];
+      if (t < T) {
+        xn[j] = ld_stream4(xb + (int64_t)t * ts);
+        an[j] = ldg4(ab + (int64_t)t * C);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kB; ++j) {
+      const int t = t0 + j;
+      if (t < T) {
+        const float4 nxt = mul4(an[j], xn[j]);
+        float4 o = mul4(k0, prev);
+        o = fma4(k1, cur, o);
+        o = fma4(k2, nxt, o);
+        st4(ob + (int64_t)t * ts, o);
+        if constexpr (AMAX) am = fmaxf(fmaxf(am, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        prev = cur;
+        cur = nxt;
+      }
+    }
   }
   if constexpr (AMAX) {   // threads past the end have returned: reduce over the lanes that are still here
     const unsigned mask = __activemask();
@@ -96,13 +114,7 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
     float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
     const int64_t base = nb + (int64_t)t * ts + p0 * C + c;
     const bool hp = t + 1 < T, hm = t > 0;
-#pragma unroll 2
-    for (int p = 0; p < np; ++p) {
-      const int64_t off = base + (int64_t)p * C;
-      const float4 g1 = ldg4(gout + off);
-      const float4 gp = hp ? ldg4(gout + off + ts) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 gm = hm ? ldg4(gout + off - ts) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 xv = ld_stream4(x + off);
+    auto body = [&](float4 g1, float4 gp, float4 gm, float4 xv, int64_t off) {
       float4 s = mul4(k0, gp);
       s = fma4(k1, g1, s);
       s = fma4(k2, gm, s);
@@ -110,6 +122,21 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
       d0 = fma4(gp, xv, d0);
       d1 = fma4(g1, xv, d1);
       d2 = fma4(gm, xv, d2);
+    };
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = 0;
+    for (; p + 1 < np; p += 2) {       // two rows per batch: eight loads in flight before the first use
+      const int64_t o0 = base + (int64_t)p * C, o1 = o0 + C;
+      const float4 g1a = ldg4(gout + o0), g1b = ldg4(gout + o1);
+      const float4 gpa = hp ? ldg4(gout + o0 + ts) : z, gpb = hp ? ldg4(gout + o1 + ts) : z;
+      const float4 gma = hm ? ldg4(gout + o0 - ts) : z, gmb = hm ? ldg4(gout + o1 - ts) : z;
+      const float4 xa = ld_stream4(x + o0), xb = ld_stream4(x + o1);
+      body(g1a, gpa, gma, xa, o0);
+      body(g1b, gpb, gmb, xb, o1);
+    }
+    if (p < np) {
+      const int64_t off = base + (int64_t)p * C;
+      body(ldg4(gout + off), hp ? ldg4(gout + off + ts) : z, hm ? ldg4(gout + off - ts) : z, ld_stream4(x + off), off);
     }
     float* dp = dpart + ((((int64_t)n * nchunks + ch) * T + t) * 3) * C + c;
     st4(dp, d0);
