@@ -211,6 +211,47 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
                    float lr, float momentum, float weight_decay, int first_step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stem of the ResNet-50 trunk (reference models/tanet_models/tanet.py:129: torchvision conv1 7x7/2 pad 3 on the 3-channel
+ * frames, bn1, relu, maxpool 3x3/2 pad 1) -- csrc/stem.cu, csrc/gemm_tf32.cu.
+ *   vitta_stem_pack: image X (F, 3, H, W) contiguous -> XP (F, H+6, W+6, 4): zero border of 3 pixels, 4th channel 0.
+ *   vitta_stem_pack_weight: conv1 weight (64, 3, 7, 7) -> tf32 hi / lo operands [64][7][8][4] (224 floats per filter).
+ *   vitta_stem_conv_tf32x3: Y (F, H/2, W/2, 64) channels-last = conv1(X) on the tcgen05 3xTF32 kernel; the A operand is
+ *     read straight from XP through a TMA tensor map with overlapping rows (no im2col buffer).  H, W even.
+ *   vitta_bn_relu_pool_fwd: out (F, Ho, Wo, C) = maxpool3x3s2p1(relu(BN_eval(x))), x (F, H, W, C) channels-last, plus one
+ *     byte per output element naming the window position (3*dh + dw) of the FIRST maximum in scan order (PyTorch's
+ *     max_pool2d_with_indices rule).  C % 4 == 0.
+ *   vitta_bn_relu_pool_bwd: gx = dL/dx given gpool = dL/dout; gw / gb = BN weight / bias gradients (assigned, reduced in a
+ *     fixed order).  ws: vitta_bn_relu_pool_bwd_ws_floats(C) floats, zero-initialised once by the caller. */
+int vitta_stem_pack(const float* x, float* xp, int F, int H, int W, void* stream);
+int vitta_stem_pack_weight(const float* w, float* hi, float* lo, void* stream);
+int vitta_stem_conv_tf32x3(const float* XP, int F, int H, int W, const float* Whi, const float* Wlo, float* Y,
+                           void* stream);
+int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
+                           void* stream);
+int64_t vitta_bn_relu_pool_bwd_ws_floats(int C);
+int vitta_bn_relu_pool_bwd(const float* gpool, const uint8_t* code, const float* x, VittaBN bn, float* gx, float* gw,
+                           float* gb, float* ws, int F, int H, int W, int C, void* stream);
+
+/* Multi-tensor weight preparation (once per optimizer step, all weights, both operand forms): the same hi/lo pieces as
+ * vitta_split_tf32 / vitta_split_f16 (bit-identical), in 1 (tf32) or 3 (fp16: zero + amax + split) launches.  tensors /
+ * block_start are device arrays; block_start[i] is the first CTA of tensor i when every CTA takes
+ * vitta_split_block_elems() destination elements, total_blocks the grid size.  src_tap_inner: the source is the
+ * contiguous conv weight [R][Cc][T] instead of [R][T][Cc].  f16: entries with compute_amax write *amax = max|src| first
+ * (entries of the same weight share the scalar; exactly one of them computes it); hi / lo are fp16 then, fp32 otherwise. */
+typedef struct VittaSplitTensor {
+  const float* src;
+  void* hi;
+  void* lo;
+  float* amax;
+  int32_t R, T, Cc, mode;
+  int32_t src_tap_inner, compute_amax;
+  int64_t n;
+} VittaSplitTensor;
+int vitta_split_block_elems(void);
+int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
+                      int f16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K6/K8  fp32-accurate GEMM and implicit-GEMM convolution on the tcgen05 tensor cores (3xTF32 split, fp32
  *        accumulation in TMEM, TMA-fed, persistent).  See csrc/gemm_tf32.cu.
  *   replaces: cuDNN / cuBLAS fp32 calls behind nn.Conv2d (torchvision Bottleneck convs inside TemporalBottleneck,

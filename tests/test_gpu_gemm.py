@@ -210,3 +210,38 @@ def test_weight_split_cache_survives_address_reuse(cuda_device):
         gc.collect()
     assert max(errs) < 5e-5, (errs, ptrs)
     assert len(set(ptrs)) < len(ptrs), "the allocator never reused an address: the regression was not exercised"
+
+
+@pytest.mark.parametrize("prec", ["f16x3", "tf32x3"])
+def test_multi_tensor_split_refresh_is_bit_identical_to_per_tensor_splits(cuda_device, prec):
+    """vitta_split_multi (all weights, both operand forms, one launch sequence after the SGD step) against the per-tensor
+    vitta_split_* path: same pieces bit for bit, written into the existing buffers, stamps valid afterwards."""
+    from vitta_b200 import ops
+    before = ops.gemm_precision()
+    ops.set_gemm_precision(prec)
+    try:
+        g = torch.Generator().manual_seed(11)
+        shapes = [(64, 64, 3, 3), (256, 64, 1, 1), (128, 128, 3, 3), (96, 288), (40, 24, 3, 3), (12, 8)]
+        ws = [torch.nn.Parameter((torch.randn(*sh, generator=g) * (10.0 ** -i)).to(cuda_device)) for i, sh in enumerate(shapes)]
+        split = ops.weight_split_f16 if prec == "f16x3" else ops.weight_split
+        first = [[tuple(t.clone() for t in split(w, m)) for m in (0, 1)] for w in ws]
+        ptrs = [[tuple(t.data_ptr() for t in split(w, m)) for m in (0, 1)] for w in ws]
+        # "optimizer step": change the weights through raw storage writes, announce it, refresh everything at once
+        with torch.no_grad():
+            for w in ws:
+                w.data.mul_(1.5).add_(0.01)
+        vers = [w._version for w in ws]
+        ops.bump_weight_epoch()
+        n = ops.refresh_weight_splits(ws)
+        assert n == 2 * len(ws)
+        for w, p0, f0 in zip(ws, ptrs, first):
+            for m in (0, 1):
+                got = split(w, m)                                  # cache hit: the refreshed buffers
+                assert tuple(t.data_ptr() for t in got) == p0[m]  # refreshed in place
+                make = ops.split_f16 if prec == "f16x3" else ops.split_tf32
+                want = make(w.detach(), m)                         # fresh per-tensor split of the NEW weight
+                for a, b, old in zip(got, want, f0[m]):
+                    assert torch.equal(a, b)
+                assert not torch.equal(got[0], f0[m][0])           # and really new
+    finally:
+        ops.set_gemm_precision(before)

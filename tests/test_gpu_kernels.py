@@ -338,3 +338,55 @@ def test_library_fails_loudly_without_cuda_tensor(cuda_device):
     from vitta_b200.utils.pred_consistency_utils import compute_pred_consis
     with pytest.raises(_lib.VittaError):
         compute_pred_consis(torch.randn(2, 2, 5))
+
+
+@pytest.mark.parametrize("f,h,w", [(3, 64, 64), (2, 224, 224), (5, 16, 40)])
+def test_stem_conv_on_tcgen05_vs_float64(cuda_device, f, h, w):
+    """conv1 (64x3x7x7, stride 2, pad 3) through vitta_stem_pack + the overlapping-row TMA operand of
+    vitta_stem_conv_tf32x3, against torch's float64 convolution; the weight gradient (library path) against autograd."""
+    import torch.nn.functional as F
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(f, 3, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) / 12.0).to(cuda_device).requires_grad_(True)
+    y = ops.StemConvFn.apply(x, wt)
+    assert y.shape == (f, 64, h // 2, w // 2) and y.is_contiguous(memory_format=torch.channels_last)
+    w64 = wt.detach().double().requires_grad_(True)
+    ref = F.conv2d(x.double(), w64, None, 2, 3)
+    scale = float(ref.abs().max())
+    assert float((y.detach().double() - ref).abs().max()) < 2e-6 * scale * 4
+    go = torch.randn(y.shape, generator=g).to(cuda_device)
+    y.backward(go)
+    ref.backward(go.double())
+    assert float((wt.grad.double() - w64.grad).abs().max()) < 1e-4 * float(w64.grad.abs().max())
+
+
+@pytest.mark.parametrize("f,c,h,w", [(2, 64, 16, 16), (3, 64, 15, 22), (4, 64, 112, 112), (2, 128, 9, 8)])
+def test_bn_relu_pool_one_pass_vs_torch(cuda_device, f, c, h, w):
+    """vitta_bn_relu_pool_fwd / _bwd against BatchNorm2d(eval) -> ReLU -> MaxPool2d(3, 2, 1) of torch: output, and the
+    gradients w.r.t. the input and the BN affine parameters (the argmax rule is PyTorch's: first maximum in scan order)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from vitta_b200 import ops
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(f, c, h, w, generator=g).to(cuda_device)
+    bn = nn.BatchNorm2d(c).to(cuda_device).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(c, generator=g) * 0.3)
+        bn.running_mean.copy_(torch.randn(c, generator=g) * 0.2)
+        bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    x1 = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = ops.BnReluPoolFn.apply(x1, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    x2 = x.clone().requires_grad_(True)
+    bn2 = nn.BatchNorm2d(c).to(cuda_device).eval()
+    bn2.load_state_dict(bn.state_dict())
+    ref = F.max_pool2d(F.relu(bn2(x2)), 3, 2, 1)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    go = torch.randn(ref.shape, generator=g).to(cuda_device)
+    out.backward(go)
+    ref.backward(go)
+    assert float((x1.grad - x2.grad).abs().max()) <= 1e-5 * float(x2.grad.abs().max())
+    for a, b in ((bn.weight.grad, bn2.weight.grad), (bn.bias.grad, bn2.bias.grad)):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-6

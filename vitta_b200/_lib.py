@@ -37,6 +37,12 @@ class VittaSgdTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("buf", C.c_void_p), ("n", C.c_int64)]
 
 
+class VittaSplitTensor(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("amax", C.c_void_p), ("R", C.c_int32),
+                ("T", C.c_int32), ("Cc", C.c_int32), ("mode", C.c_int32), ("src_tap_inner", C.c_int32),
+                ("compute_amax", C.c_int32), ("n", C.c_int64)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "vitta_version": (C.c_int, []),
@@ -115,6 +121,14 @@ _SIGNATURES = {
     "vitta_cv_resize_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                C.c_int, C.c_int, _P, _P]),
+    "vitta_stem_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_stem_pack_weight": (C.c_int, [_P, _P, _P, _P]),
+    "vitta_stem_conv_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "vitta_bn_relu_pool_fwd": (C.c_int, [_P, VittaBN, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_bn_relu_pool_bwd_ws_floats": (C.c_int64, [C.c_int]),
+    "vitta_bn_relu_pool_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_split_block_elems": (C.c_int, []),
+    "vitta_split_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),
     "vitta_sgd_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P]),
 }

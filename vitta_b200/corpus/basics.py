@@ -315,7 +315,11 @@ class OnlineAdapter:
             self._graph_in.copy_(input, non_blocking=True)
         self._graph.replay()
         _lib.launch_count += self._graph_launches
-        ops.bump_weight_epoch()        # the replayed SGD step changed the weights behind the split cache's back
+        # the replayed step changed the weights behind the split cache's back -- and, being a capture of FusedSGD.step,
+        # refreshed the registered splits in place: invalidate everything, then re-validate exactly those
+        ops.bump_weight_epoch()
+        if isinstance(self.optimizer, ops.FusedSGD):
+            ops.refresh_weight_splits(self.optimizer.params, launch=False)
         return dict(self._graph_out)
 
     def _adapt_eager(self, input, target=None, criterion=None):
@@ -333,6 +337,7 @@ class OnlineAdapter:
         loss_consis = None
         loss_ce = None
         for _ in range(args.n_gradient_steps):
+            ops.reset_amax_pool()           # one fill for all operand-range scalars of this pass
             if args.arch == 'tanet':
                 output = model(x)
                 if args.if_sample_tta_aug_views:
@@ -449,6 +454,7 @@ class OnlineAdapter:
         if self._hooks_on:
             self.hooks_off()
         model.eval()
+        ops.reset_amax_pool()
         x = _reshape_input(args, input, self.n_clips)
         if args.arch == 'tanet':
             out = model(x)

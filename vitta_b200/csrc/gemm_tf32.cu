@@ -45,6 +45,7 @@ struct GemmParams {
   int Kc;                  // channels (K extent per tap)
   int taps_h, taps_w;      // filter extent (1,1 for a plain GEMM)
   int stride, pad;
+  int stride_w;            // 0: same as stride; else the step of the TMA w coordinate per output column (stem: 1)
   int Ho, Wo, F;           // output geometry: rows of C = (f, ho, wo); plain GEMM: F = 1, Ho = 1, Wo = M
   int BW, BH, BF;          // output pixels covered by one M tile: BF frames x BH rows x BW cols  (BW*BH*BF <= 128)
   int tiles_w, tiles_h, tiles_f, tiles_n;
@@ -187,7 +188,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int wb = mt % p.tiles_w; mt /= p.tiles_w;
         const int hb = mt % p.tiles_h;
         const int fb = mt / p.tiles_h;
-        const int w_in0 = wb * p.BW * p.stride - p.pad;
+        const int w_in0 = wb * p.BW * (p.stride_w ? p.stride_w : p.stride) - p.pad;
         const int h_in0 = hb * p.BH * p.stride - p.pad;
         const int f0 = fb * p.BF;
         const int n0 = nt * BN + (PAIR ? (int)cta_rank * kBRows : 0);   // PAIR: this CTA's half of the B tile
@@ -652,6 +653,92 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-tensor weight preparation: every weight of the model, both operand forms, in 2-3 launches per optimizer step
+// (instead of one amax + one split launch per weight and form: 312 launches per TANet step).  Same arithmetic as
+// split_tf32_kernel / amax_kernel / split_f16_kernel, so the operands are bit-identical to the per-tensor path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSplitBlock = 4096;   // elements of one tensor handled by one CTA
+
+struct SplitEntry {
+  const float* src;
+  void* hi;
+  void* lo;
+  float* amax;
+  int32_t R, T, Cc, mode;
+  int32_t src_tap_inner, compute_amax;
+  int64_t n;
+};
+
+__device__ __forceinline__ int split_find(const int32_t* __restrict__ block_start, int n_tensors, int bid) {
+  int lo = 0, hi = n_tensors - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_start[mid] <= bid) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void split_multi_zero_kernel(const SplitEntry* __restrict__ t, int n_tensors) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tensors; i += gridDim.x * blockDim.x)
+    if (t[i].compute_amax) *t[i].amax = 0.f;
+}
+
+__global__ void __launch_bounds__(256) split_multi_amax_kernel(const SplitEntry* __restrict__ tensors,
+                                                              const int32_t* __restrict__ block_start, int n_tensors) {
+  const int ti = split_find(block_start, n_tensors, blockIdx.x);
+  const SplitEntry t = tensors[ti];
+  if (!t.compute_amax) return;
+  const int64_t e0 = (int64_t)(blockIdx.x - block_start[ti]) * kSplitBlock;
+  const int64_t rem = t.n - e0;
+  const int cnt = (int)(rem < kSplitBlock ? rem : kSplitBlock);
+  uint32_t m = 0;
+  for (int i = threadIdx.x; i < cnt; i += 256) m = max(m, __float_as_uint(fabsf(__ldg(t.src + e0 + i))));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(t.amax), m);
+}
+
+// dst index i -> source element; dst is [R][T][Cc] (mode 0) or [Cc][T'][R] with the taps reversed (mode 1); the source is
+// [R][T][Cc] or, for src_tap_inner, the contiguous conv weight [R][Cc][T] (no channels_last copy of the weight needed)
+template <bool F16>
+__global__ void __launch_bounds__(256) split_multi_kernel(const SplitEntry* __restrict__ tensors,
+                                                         const int32_t* __restrict__ block_start, int n_tensors) {
+  const int ti = split_find(block_start, n_tensors, blockIdx.x);
+  const SplitEntry t = tensors[ti];
+  const int64_t e0 = (int64_t)(blockIdx.x - block_start[ti]) * kSplitBlock;
+  const int64_t rem = t.n - e0;
+  const int cnt = (int)(rem < kSplitBlock ? rem : kSplitBlock);
+  float sc = 1.f, inv_unused;
+  if constexpr (F16) f16_split_scale(__ldcg(t.amax), sc, inv_unused);
+  for (int k = threadIdx.x; k < cnt; k += 256) {
+    const int64_t i = e0 + k;
+    int r, tp, c;
+    if (t.mode == 1) {   // i indexes dst [c][t'][r]
+      r = (int)(i % t.R);
+      const int64_t q = i / t.R;
+      tp = t.T - 1 - (int)(q % t.T);
+      c = (int)(q / t.T);
+    } else {             // i indexes dst [r][t][c]
+      c = (int)(i % t.Cc);
+      const int64_t q = i / t.Cc;
+      tp = (int)(q % t.T);
+      r = (int)(q / t.T);
+    }
+    const int64_t s = t.src_tap_inner ? ((int64_t)r * t.Cc + c) * t.T + tp : ((int64_t)r * t.T + tp) * t.Cc + c;
+    if constexpr (F16) {
+      const float v = __ldg(t.src + s) * sc;
+      const __half h = __float2half_rn(v);
+      static_cast<__half*>(t.hi)[i] = h;
+      static_cast<__half*>(t.lo)[i] = __float2half_rn(v - __half2float(h));
+    } else {
+      const float v = __ldg(t.src + s);
+      const float h = tf32_rna(v);
+      static_cast<float*>(t.hi)[i] = h;
+      static_cast<float*>(t.lo)[i] = v - h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1082,6 +1169,46 @@ static int dgrad_impl(const float* dY, int F, int Ho, int Wo, int Cout, const vo
   return 0;
 }
 
+// ResNet stem: 7x7 / stride 2 / pad 3 convolution of a 3-channel image, on the same kernel.  The image arrives
+// zero-padded and widened to 4 channels (vitta_stem_pack: XP[F][H+6][W+6][4]), so that the 8 pixels x 4 channels = 32
+// floats under one filter ROW of an output pixel are contiguous: the A operand of filter row kh is a [pixels x 32] matrix
+// whose rows OVERLAP in memory (row wo starts 2 pixels = 32 bytes after row wo-1).  TMA expresses that directly -- a
+// tensor map whose second dimension (the output column) has a 32-byte stride under a 128-byte inner extent -- so the
+// convolution is 7 "taps" of K = 32 (kw padded 7 -> 8, c padded 3 -> 4; the weight operand holds zeros there) with no
+// im2col buffer.  Replaces the cuDNN fp32 call for torchvision's conv1 (reference models/tanet_models/tanet.py:129).
+int vitta_stem_conv_tf32x3(const float* XP, int F, int H, int W, const float* Whi, const float* Wlo, float* Y,
+                           void* stream) {
+  VITTA_CHECK_ARG(XP && Whi && Wlo && Y && F > 0 && H >= 7 && W >= 7 && H % 2 == 0 && W % 2 == 0, VITTA_E_BADARG,
+                  "stem_conv: bad arguments (even H, W >= 7)");
+  VITTA_CHECK_ARG(aligned16(XP) && aligned16(Whi) && aligned16(Wlo) && aligned32(Y), VITTA_E_ALIGN,
+                  "stem_conv: tensors must be 16-byte aligned (output 32)");
+  const int Hp = H + 6, Wp = W + 6, Ho = H / 2, Wo = W / 2, Cout = 64;
+  int BW, BH, BF;
+  pick_boxes(Wo, Ho, F, &BW, &BH, &BF);
+  VITTA_CHECK_ARG(BH * 2 <= 256, VITTA_E_UNSUPPORTED, "stem_conv: box exceeds the TMA limit");
+  CUtensorMap ta, tbh, tbl;
+  {
+    // dims {32 floats of a window row, output column, padded input row, frame}
+    const uint64_t dims[4] = {32, (uint64_t)Wo, (uint64_t)Hp, (uint64_t)F};
+    const uint64_t str[3] = {32, (uint64_t)Wp * 16, (uint64_t)Wp * 16 * Hp};
+    const uint32_t box[4] = {32, (uint32_t)BW, (uint32_t)(BH * 2), (uint32_t)BF};
+    const uint32_t es[4] = {1, 1, 2, 1};
+    int rc = make_tensor_map_f32(&ta, XP, 4, dims, str, box, es);
+    if (rc) return rc;
+  }
+  int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, 224, Cout, 224, 64);
+  if (rc) return rc;
+  GemmParams p{};
+  p.C = Y; p.ldc = Cout; p.ldr = Cout;
+  p.N = Cout; p.Kc = 32; p.k_chunks = 1;
+  p.taps_h = 7; p.taps_w = 1; p.stride = 2; p.stride_w = 1; p.pad = 0;
+  p.Ho = Ho; p.Wo = Wo; p.F = F;
+  p.BW = BW; p.BH = BH; p.BF = BF;
+  p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
+  p.vec_ok = 2;
+  return dispatch(ta, tbh, tbl, p, 64, (cudaStream_t)stream, 0);
+}
+
 int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                          int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
                          int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
@@ -1148,6 +1275,28 @@ int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int H
                              int W, float* dX, void* stream) {
   VITTA_CHECK_ARG(dy_amax && w_amax, VITTA_E_BADARG, "conv2d_dgrad_f16x3: amax scalars are required");
   return dgrad_impl(dY, F, Ho, Wo, Cout, Wthi, Wtlo, Cin, KH, KW, stride, pad, H, W, dX, stream, dy_amax, w_amax);
+}
+
+int vitta_split_block_elems(void) { return kSplitBlock; }
+
+int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
+                      int f16, void* stream) {
+  VITTA_CHECK_ARG(tensors && block_start && n_tensors > 0 && total_blocks > 0, VITTA_E_BADARG,
+                  "split_multi: bad arguments");
+  static_assert(sizeof(SplitEntry) == sizeof(VittaSplitTensor), "layout");
+  const SplitEntry* t = reinterpret_cast<const SplitEntry*>(tensors);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f16) {
+    split_multi_zero_kernel<<<(n_tensors + 255) / 256, 256, 0, st>>>(t, n_tensors);
+    VITTA_CHECK_LAUNCH();
+    split_multi_amax_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(t, block_start, n_tensors);
+    VITTA_CHECK_LAUNCH();
+    split_multi_kernel<true><<<(unsigned)total_blocks, 256, 0, st>>>(t, block_start, n_tensors);
+  } else {
+    split_multi_kernel<false><<<(unsigned)total_blocks, 256, 0, st>>>(t, block_start, n_tensors);
+  }
+  VITTA_CHECK_LAUNCH();
+  return 0;
 }
 
 }  // extern "C"

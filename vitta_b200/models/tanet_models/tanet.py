@@ -8,7 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.init import constant_, normal_
 
-from ...nn import StatsBatchNorm2d, conv2d, norm_act
+from ...nn import StatsBatchNorm2d, conv2d, norm_act, stem
 from .basic_ops import ConsensusModule
 from .temporal_module import Bottleneck, TemporalBottleneck, make_temporal_modeling
 
@@ -46,10 +46,7 @@ class ResNet50Trunk(nn.Module):
 
     def forward(self, x):
         t = self.n_segment
-        x = x.contiguous(memory_format=torch.channels_last)
-        x = conv2d(self.conv1, x)
-        x, _ = norm_act(self.bn1, x, True, t)
-        x = self.maxpool(x)
+        x = stem(self.conv1, self.bn1, self.maxpool, x, t)
         pooled = None
         stages = (self.layer1, self.layer2, self.layer3, self.layer4)
         for si, stage in enumerate(stages):

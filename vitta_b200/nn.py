@@ -109,3 +109,22 @@ def conv2d(conv, x):
         x = x.contiguous(memory_format=torch.channels_last)
         return ops.conv2d(x, conv.weight, conv.stride[0], conv.padding[0])
     return conv(x)
+
+
+def stem(conv, bn, maxpool, x, clip_len):
+    """conv1 -> bn1 -> relu -> maxpool of the ResNet trunk.  Fast path: the 7x7/2 convolution on the tcgen05 kernel and
+    BN + ReLU + MaxPool(3, 2, 1) as ONE pass (no 411 MB un-pooled activation).  It is taken when the BatchNorm is in eval
+    mode without a statistics tap or foreign hooks (the default ViTTA configuration aligns layer3 / layer4 only); otherwise
+    the layers run one by one so that every hook observes the reference's tensors."""
+    if ops.stem_conv_supported(conv, x) and x.is_cuda:
+        y = ops.StemConvFn.apply(x, conv.weight)
+    else:
+        y = conv2d(conv, x.contiguous(memory_format=torch.channels_last))
+    if (_fusable(bn) and bn._vitta_tap is None and isinstance(maxpool, nn.MaxPool2d) and maxpool.kernel_size == 3
+            and maxpool.stride == 2 and maxpool.padding == 1 and maxpool.dilation == 1 and not maxpool.ceil_mode
+            and not maxpool.return_indices and not maxpool._forward_hooks and y.shape[1] % 4 == 0
+            and 256 % (y.shape[1] // 4) == 0 and y.is_cuda):
+        y = y.contiguous(memory_format=torch.channels_last)
+        return ops.BnReluPoolFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    y, _ = norm_act(bn, y, True, clip_len)
+    return maxpool(y)

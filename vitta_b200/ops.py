@@ -27,10 +27,41 @@ def _fused_amax():
     return _gemm_precision == "f16x3" and _FUSED_AMAX
 
 
+# Operand-range scalars live in a pre-zeroed pool: one fill per adaptation step instead of one torch.zeros(1) launch per
+# producer (~190 per TANet step).  reset_amax_pool() -- called at the start of every adaptation / evaluation pass --
+# re-zeroes the pool and starts handing out its slots again; scalars attached to tensors before a reset are disowned
+# through the generation number, so a long-lived tensor can never read a recycled slot.
+_AMAX_POOL = 4096
+_amax_pools = {}      # device -> [pool tensors], [next index]
+_amax_gen = 0
+
+
+def new_amax(dev):
+    """A zero-initialised device scalar (shape [1]) for a max|x| accumulation."""
+    ent = _amax_pools.get(dev)
+    if ent is None:
+        ent = _amax_pools[dev] = [[torch.zeros(_AMAX_POOL, dtype=torch.float32, device=dev)], 0]
+    pools, i = ent
+    if i >= _AMAX_POOL * len(pools):
+        pools.append(torch.zeros(_AMAX_POOL, dtype=torch.float32, device=dev))     # rare: a pass with > 4096 producers
+    ent[1] = i + 1
+    return pools[i // _AMAX_POOL][i % _AMAX_POOL:i % _AMAX_POOL + 1]
+
+
+def reset_amax_pool():
+    global _amax_gen
+    _amax_gen += 1
+    for ent in _amax_pools.values():
+        del ent[0][1:]
+        if ent[1]:
+            ent[0][0].zero_()
+        ent[1] = 0
+
+
 def _attach_amax(t, am):
     """Remember max|t| on the tensor OBJECT together with its version counter: an attribute cannot outlive the tensor (no
     stale pointer keys), and an in-place update of the tensor invalidates it."""
-    t._vitta_amax = (am, t._version)
+    t._vitta_amax = (am, t._version, _amax_gen)
 
 
 def operand_amax(t):
@@ -38,7 +69,7 @@ def operand_amax(t):
     tensor object), else a standalone vitta_amax_f32 pass whose result is attached for the next consumer (a conv input is
     also the operand of its weight gradient)."""
     ent = getattr(t, "_vitta_amax", None)
-    if ent is not None and ent[1] == t._version:
+    if ent is not None and ent[1] == t._version and ent[2] == _amax_gen:
         return ent[0]
     am = amax_f32(t)
     _attach_amax(t, am)
@@ -475,7 +506,7 @@ class BNActFn(torch.autograd.Function):
         bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
         if _fused_amax():
             # opt-in f16x3 path: the kernel also emits max|out| for the fp16-split convolution that consumes `out`
-            am = torch.zeros(1, dtype=torch.float32, device=dev)
+            am = new_amax(dev)
             call("vitta_bn_act_fwd_amax", ptr(x), bn, ptr(res), C.byref(bn2) if bn2 is not None else None, int(relu),
                  ptr(out), ptr(part_main), ptr(part_res), ptr(pool_part), ptr(pool_out), kf, kr, Cc, ptr(am), stream_ptr())
             _attach_amax(out, am)
@@ -515,8 +546,8 @@ class BNActFn(torch.autograd.Function):
         bn = _lib.make_bn(w, b, rm, rv, eps)
         bn2 = _lib.make_bn(w2, b2, rm2, rv2, eps2) if has_res_bn else None
         if _fused_amax():
-            amx = torch.zeros(1, dtype=torch.float32, device=dev)
-            amr = torch.zeros(1, dtype=torch.float32, device=dev) if has_res else None
+            amx = new_amax(dev)
+            amr = new_amax(dev) if has_res else None
             call("vitta_bn_act_bwd_amax", ptr(gout), ptr(gpool) if want_pool else None, ptr(x), bn, ptr(res),
                  C.byref(bn2) if bn2 is not None else None, int(relu), ca, cb, cm, gs, ca2, cb2, cm2, gs2, ptr(gx),
                  ptr(gres), ptr(gw), ptr(gb), ptr(gw2), ptr(gb2), ptr(ws), kf, kr, Cc, ptr(amx), ptr(amr), stream_ptr())
@@ -561,7 +592,7 @@ class TamStencilFn(torch.autograd.Function):
         kern, act = kern.contiguous(), act.contiguous()
         out = torch.empty_like(x)
         if _fused_amax():
-            am = torch.zeros(1, dtype=torch.float32, device=x.device)
+            am = new_amax(x.device)
             call("vitta_tam_fwd_amax", ptr(x), ptr(kern), ptr(act), ptr(out), n, T, h * w, Cc, ptr(am), stream_ptr())
             _attach_amax(out, am)
         else:
@@ -721,6 +752,7 @@ class FusedSGD:
             t, starts, n, blocks = tab
             call("vitta_sgd_step", ptr(t), ptr(starts), n, blocks, lr, self.momentum, self.weight_decay, is_first, 1.0, st)
         bump_weight_epoch()
+        refresh_weight_splits(self.params)       # all updated weights, both operand forms, one launch sequence
 
 
 # ----------------------------------------------------------------------------------------------
@@ -782,7 +814,7 @@ def amax_f32(x, out=None):
     if not x.is_contiguous() and not x.is_contiguous(memory_format=CL):
         raise _lib.VittaError("amax_f32: x must be dense")
     if out is None:
-        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+        out = new_amax(x.device)
     call("vitta_amax_f32", ptr(x), x.numel(), ptr(out), stream_ptr())
     return out
 
@@ -798,7 +830,8 @@ def split_f16(w, mode=0):
         r, c, kh, kw = w.shape
         t = kh * kw
         src = w.contiguous(memory_format=CL) if t > 1 else w.reshape(r, c).contiguous()
-    am = amax_f32(src)
+    # a weight's range scalar lives as long as the cached split: never a slot of the per-pass pool
+    am = amax_f32(src, out=torch.zeros(1, dtype=torch.float32, device=w.device))
     hi = torch.empty(r * t * c, dtype=torch.float16, device=w.device)
     lo = torch.empty_like(hi)
     call("vitta_split_f16", ptr(src), ptr(hi), ptr(lo), ptr(am), r, t, c, int(mode), stream_ptr())
@@ -858,11 +891,16 @@ def conv2d_dgrad_f16x3(gy, wt_hi, wt_lo, w_amax, x_shape, kh, kw, stride, pad, g
 # load_state_dict) and by a global epoch that every FusedSGD step / graph replay bumps (they update parameters through
 # raw pointers, invisible to the version counter).
 _weight_epoch = 0
+_split_registry = {}     # id(weight) -> weakref(weight): weights that carry cached splits (for the multi-tensor refresh)
 
 
 def bump_weight_epoch():
     global _weight_epoch
     _weight_epoch += 1
+
+
+def _stamp(w):
+    return (w._version, _weight_epoch, w.data_ptr(), tuple(w.shape))
 
 
 def _cached_split(w, mode, kind, make):
@@ -873,14 +911,97 @@ def _cached_split(w, mode, kind, make):
             w._vitta_split = cache
         except AttributeError:       # an object without a __dict__: no caching, always correct
             cache = None
-    stamp = (w._version, _weight_epoch, w.data_ptr(), tuple(w.shape))
+    stamp = _stamp(w)
     ent = cache.get((mode, kind)) if cache is not None else None
     if ent is None or ent[0] != stamp:
         with torch.no_grad():
-            ent = (stamp, make(w.detach(), mode))
+            ent = [stamp, make(w.detach(), mode)]
         if cache is not None:
             cache[(mode, kind)] = ent
+            if id(w) not in _split_registry:
+                import weakref
+                key = id(w)
+                _split_registry[key] = weakref.ref(w, lambda _r, k=key: _split_registry.pop(k, None))
     return ent[1]
+
+
+class _SplitTable:
+    """Device table of vitta_split_multi for one set of (weight, operand form) entries; rebuilt only when the set or any
+    buffer address changes (never inside a steady-state step, so it is CUDA-graph safe)."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+        self._keep = []      # superseded tables stay alive: a captured CUDA graph may still read them
+
+    def build(self, items, dev):
+        if self.dev is not None:
+            self._keep.append((self.dev, self._host))
+        blk = _lib.load().vitta_split_block_elems()
+        arr = (_lib.VittaSplitTensor * len(items))()
+        starts, b = [], 0
+        for i, (w, mode, bufs, geom) in enumerate(items):
+            r, t, c, tap_inner = geom
+            e = arr[i]
+            e.src, e.hi, e.lo = w.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr()
+            e.amax = bufs[2].data_ptr() if len(bufs) > 2 else None
+            e.R, e.T, e.Cc, e.mode, e.src_tap_inner = r, t, c, mode, tap_inner
+            e.compute_amax = 1 if len(bufs) > 2 else 0
+            e.n = r * t * c
+            starts.append(b)
+            b += (e.n + blk - 1) // blk
+        self._host = (pinned_bytes(arr), torch.tensor(starts, dtype=torch.int32).pin_memory())
+        self.dev = (self._host[0].to(dev, non_blocking=True), self._host[1].to(dev, non_blocking=True), len(items), b)
+
+
+_split_tables = {"f16": _SplitTable(), "tf32": _SplitTable()}
+
+
+def _split_geom(w):
+    """(R, T, Cc, src_tap_inner) of a weight the multi-tensor kernel can read in place, else None."""
+    if not w.is_contiguous():
+        return None
+    if w.dim() == 2:
+        return int(w.shape[0]), 1, int(w.shape[1]), 0
+    if w.dim() == 4:
+        r, c, kh, kw = (int(v) for v in w.shape)
+        return r, kh * kw, c, (1 if kh * kw > 1 else 0)
+    return None
+
+
+def refresh_weight_splits(params=None, launch=True):
+    """Bring the cached operand splits of all registered weights (restricted to ``params`` when given) up to date with
+    ONE multi-tensor launch sequence, writing into the existing buffers, and stamp them valid.  Called by FusedSGD.step
+    right after the update (so the next forward / backward finds every split ready), and with ``launch=False`` after a
+    CUDA-graph replay (the captured step already ran the refresh; only the stamps have to follow)."""
+    kind = "f16" if _gemm_precision == "f16x3" else "tf32"
+    allowed = None if params is None else {id(p) for p in params}
+    items, dev = [], None
+    for key, ref in list(_split_registry.items()):
+        w = ref()
+        if w is None or (allowed is not None and key not in allowed):
+            continue
+        geom = _split_geom(w)
+        cache = getattr(w, "_vitta_split", None)
+        if geom is None or not cache or not w.is_cuda:
+            continue
+        for (mode, k2), ent in cache.items():
+            if k2 == kind and mode in (0, 1):        # other forms (the stem's packed operand) re-split lazily
+                items.append((w, mode, ent[1], geom, ent))
+                dev = w.device
+    if not items:
+        return 0
+    if launch:
+        tab = _split_tables[kind]
+        key = tuple((id(w), mode, w.data_ptr()) + tuple(b.data_ptr() for b in bufs) for w, mode, bufs, _, _ in items)
+        if tab.key != key:
+            tab.build([it[:4] for it in items], dev)
+            tab.key = key
+        t, starts, n, blocks = tab.dev
+        call("vitta_split_multi", ptr(t), ptr(starts), n, blocks, 1 if kind == "f16" else 0, stream_ptr())
+    for w, mode, bufs, geom, ent in items:
+        ent[0] = _stamp(w)
+    return len(items)
 
 
 # Operand split of the dense contractions (DESIGN.md section 3): "f16x3" (default since round 2: fp16 hi/lo pieces on
@@ -1044,3 +1165,94 @@ def conv2d_shortcut(x, w, stride, pad):
 
 def conv2d(x, w, stride, pad):
     return Conv2dFn.apply(x, w, stride, pad, False)
+
+
+# ----------------------------------------------------------------------------------------------
+# ResNet stem: conv1 7x7/2 on tcgen05 (overlapping-row TMA operand), BN + ReLU + MaxPool in one pass
+# ----------------------------------------------------------------------------------------------
+def _stem_weight_split(w, mode):
+    hi = torch.empty(64 * 224, dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    call("vitta_stem_pack_weight", ptr(w.contiguous()), ptr(hi), ptr(lo), stream_ptr())
+    return hi, lo
+
+
+class StemConvFn(torch.autograd.Function):
+    """conv1 of the ResNet trunk (64 x 3 x 7 x 7, stride 2, padding 3) on the tcgen05 3xTF32 kernel.  x: (F, 3, H, W) in
+    ANY dense layout (read once by the packing kernel); result (F, 64, H/2, W/2) channels_last.  The weight gradient --
+    the only gradient the step needs here, the frames do not require one -- stays on the library (cuDNN) for now."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _require_cuda(x, "stem_conv")
+        f, c, h, wd = x.shape
+        xc = x if x.is_contiguous() else x.contiguous()
+        xp = torch.empty(f, h + 6, wd + 6, 4, dtype=torch.float32, device=x.device)
+        call("vitta_stem_pack", ptr(xc), ptr(xp), f, h, wd, stream_ptr())
+        whi, wlo = _cached_split(w, "stem", "tf32", _stem_weight_split)
+        y = torch.empty((f, 64, h // 2, wd // 2), dtype=torch.float32, device=x.device, memory_format=CL)
+        call("vitta_stem_conv_tf32x3", ptr(xp), f, h, wd, ptr(whi), ptr(wlo), ptr(y), stream_ptr())
+        ctx.save_for_backward(xc, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        need_x, need_w = ctx.needs_input_grad
+        if need_x or need_w:
+            # channels_last operands select cuDNN's NHWC kernels (no transposing copy of the 411 MB gradient)
+            r = torch.ops.aten.convolution_backward(gy.contiguous(memory_format=CL), x.contiguous(memory_format=CL), w,
+                                                    None, [2, 2], [3, 3], [1, 1], False, [0, 0], 1,
+                                                    [need_x, need_w, False])
+            gx, gw = r[0], r[1]
+        return gx, gw
+
+
+def stem_conv_supported(conv, x):
+    return (tuple(conv.weight.shape) == (64, 3, 7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.padding_mode == 'zeros'
+            and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and x.shape[2] >= 8
+            and x.shape[3] >= 8 and not conv._forward_hooks and not conv._forward_pre_hooks)
+
+
+_pool_ws = {}
+
+
+class BnReluPoolFn(torch.autograd.Function):
+    """maxpool3x3/2/1(relu(BN_eval(x))) in one pass (reference: torchvision bn1 -> relu -> maxpool inside
+    models/tanet_models/tanet.py's base_model); x (F, C, H, W) channels_last.  Saves x and one byte per pooled element
+    (the winner's window position); the backward is one pass as well."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rm, rv, eps):
+        _require_cuda(x, "bn_relu_pool")
+        if not x.is_contiguous(memory_format=CL):
+            raise _lib.VittaError("bn_relu_pool: x must be channels_last contiguous")
+        f, c, h, wd = x.shape
+        ho, wo = (h + 1) // 2, (wd + 1) // 2
+        out = torch.empty((f, c, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
+        code = torch.empty(f * ho * wo * c, dtype=torch.uint8, device=x.device)
+        call("vitta_bn_relu_pool_fwd", ptr(x), _lib.make_bn(w, b, rm, rv, eps), ptr(out), ptr(code), f, h, wd, c,
+             stream_ptr())
+        ctx.save_for_backward(x, w, b, rm, rv, code)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w, b, rm, rv, code = ctx.saved_tensors
+        f, c, h, wd = x.shape
+        gout = gout.contiguous(memory_format=CL)
+        key = (x.device, c)
+        ws = _pool_ws.get(key)
+        if ws is None:
+            ws = _pool_ws[key] = torch.zeros(_lib.load().vitta_bn_relu_pool_bwd_ws_floats(c), dtype=torch.float32,
+                                             device=x.device)
+        gx = torch.empty_like(x)
+        gparam = torch.empty(2, c, dtype=torch.float32, device=x.device)
+        call("vitta_bn_relu_pool_bwd", ptr(gout), ptr(code), ptr(x), _lib.make_bn(w, b, rm, rv, ctx.eps), ptr(gx),
+             ptr(gparam[0]), ptr(gparam[1]), ptr(ws), f, h, wd, c, stream_ptr())
+        if _fused_amax():
+            pass        # gx feeds only the stem convolution's weight gradient (library path): no operand range needed
+        return gx, gparam[0], gparam[1], None, None, None
