@@ -211,6 +211,25 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
                    float lr, float momentum, float weight_decay, int first_step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K5b  TAM gate networks (csrc/tam_gate.cu): the G and L branches of the Temporal Adaptive Module on the pooled
+ *      activation p (N, T, C), BatchNorm1d layers in eval mode -- replaces ~45 eager launches per TAM and direction
+ *      (reference models/tanet_models/temporal_module.py:27-41,49-55).
+ *   G: kern[n, :, c] = softmax(W2 . relu(BN1(W1 . p[n, :, c])))       W1 (2T, T), W2 (3, 2T)            -> (N, 3, C)
+ *   L: act[n, t, :]  = sigmoid(Wb . relu(BN2(conv1d_k3_pad1(Wa, p)[n, t, :])))   Wa (C/4, C, 3), Wb (C, C/4) -> (N, T, C)
+ *   fwd also writes pre (N*T, C/4), the L hidden layer before BN2 (saved for the backward).
+ *   bwd: given gkern, gact returns gp (N, T, C) and the gradients of W1, BN1 (w, b), W2, Wa, BN2 (w, b), Wb (assigned);
+ *        gz (N*T, C), gpre / ghm (N*T, C/4) are scratch; ws: vitta_tam_gate_bwd_ws_floats floats, zeroed once by the caller.
+ *   T <= 16, C % 4 == 0; every reduction runs in a fixed order. */
+int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
+                       const float* Wb, float* kern, float* act, float* pre, int N, int T, int C, void* stream);
+int64_t vitta_tam_gate_bwd_ws_floats(int N, int T, int C);
+int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
+                       const float* Wb, const float* act, const float* pre, const float* gkern, const float* gact,
+                       float* gp, float* gW1, float* gbn1w, float* gbn1b, float* gW2, float* gWa, float* gbn2w,
+                       float* gbn2b, float* gWb, float* gz, float* gpre, float* ghm, float* ws, int N, int T, int C,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stem of the ResNet-50 trunk (reference models/tanet_models/tanet.py:129: torchvision conv1 7x7/2 pad 3 on the 3-channel
  * frames, bn1, relu, maxpool 3x3/2 pad 1) -- csrc/stem.cu, csrc/gemm_tf32.cu.
  *   vitta_stem_pack: image X (F, 3, H, W) contiguous -> XP (F, H+6, W+6, 4): zero border of 3 pixels, 4th channel 0.

@@ -390,3 +390,40 @@ def test_bn_relu_pool_one_pass_vs_torch(cuda_device, f, c, h, w):
     assert float((x1.grad - x2.grad).abs().max()) <= 1e-5 * float(x2.grad.abs().max())
     for a, b in ((bn.weight.grad, bn2.weight.grad), (bn.bias.grad, bn2.bias.grad)):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("n,t,c,hw", [(2, 8, 64, 5), (3, 16, 128, 4), (1, 16, 512, 2), (2, 6, 24, 3)])
+def test_tam_gate_kernels_vs_torch_modules(cuda_device, n, t, c, hw):
+    """K5b (G and L branches of the TAM in 3 + 7 launches, eval-mode BatchNorm1d) against the same TAM evaluated through
+    its torch modules (a foreign forward hook forces that path): output and every gradient."""
+    import copy
+    from vitta_b200.models.tanet_models.temporal_module import TAM
+    g = torch.Generator().manual_seed(51)
+    tam = TAM(in_channels=c, n_segment=t).to(cuda_device)
+    with torch.no_grad():
+        for m in tam.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    tam.train()
+    for m in tam.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.eval()
+    ref = copy.deepcopy(tam)
+    ref.G[0].register_forward_hook(lambda *a: None)       # foreign hook -> module-by-module path
+    assert tam._gate_fusable(torch.empty(1, device=cuda_device), t, c) and not ref._gate_fusable(torch.empty(1, device=cuda_device), t, c)
+    x = torch.randn(n * t, c, hw, hw, generator=g).to(cuda_device)
+    x1 = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x2 = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y1, y2 = tam(x1), ref(x2)
+    assert float((y1 - y2).abs().max()) <= 2e-5 * float(y2.abs().max())
+    go = torch.randn(y2.shape, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    y1.backward(go)
+    y2.backward(go)
+    assert float((x1.grad - x2.grad).abs().max()) <= 5e-5 * float(x2.grad.abs().max())
+    for (k, p1), (_, p2) in zip(tam.named_parameters(), ref.named_parameters()):
+        assert p1.grad is not None and p2.grad is not None, k
+        err, scale = float((p1.grad - p2.grad).abs().max()), float(p2.grad.abs().max())
+        assert err <= 1e-4 * scale + 1e-7, (k, err, scale)

@@ -121,6 +121,9 @@ _SIGNATURES = {
     "vitta_cv_resize_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                C.c_int, C.c_int, _P, _P]),
+    "vitta_tam_gate_fwd": (C.c_int, [_P, _P, VittaBN, _P, _P, VittaBN, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_tam_gate_bwd_ws_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "vitta_tam_gate_bwd": (C.c_int, [_P, _P, VittaBN, _P, _P, VittaBN, _P] + [_P] * 17 + [C.c_int, C.c_int, C.c_int, _P]),
     "vitta_stem_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_stem_pack_weight": (C.c_int, [_P, _P, _P, _P]),
     "vitta_stem_conv_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -46,6 +46,19 @@ class TAM(nn.Module):
         n = nt // t
         if pooled is None:
             pooled = F.adaptive_avg_pool2d(x, 1).flatten(1)          # (N*T, C)
+        if self._gate_fusable(x, t, c):
+            # both gate networks in 3 launches (K5b); BatchNorm1d hooks of the alignment driver contribute exact zeros
+            # (reference utils/norm_stats_utils.py:158-183) and are marked as fired without running the modules
+            g_bn, l_bn = self.G[1], self.L[1]
+            for bn in (g_bn, l_bn):
+                for fn in bn._forward_hooks.values():
+                    fn.__self__.mark_bn1d_fired(x.device)
+            kern, act = ops.TamGateFn.apply(pooled, self.G[0].weight, g_bn.weight, g_bn.bias, g_bn.running_mean,
+                                            g_bn.running_var, self.G[3].weight, self.L[0].weight, l_bn.weight, l_bn.bias,
+                                            l_bn.running_mean, l_bn.running_var, self.L[3].weight.view(c, c // 4), t,
+                                            g_bn.eps, l_bn.eps)
+            x = x.contiguous(memory_format=torch.channels_last)
+            return ops.TamStencilFn.apply(x, kern, act, t)
         p_ntc = pooled.view(n, t, c)
         # G: per (video, channel) a softmax-normalised 3-tap kernel from the pooled T-vector
         kern = self.G(p_ntc.permute(0, 2, 1).reshape(n * c, t)).view(n, c, self.kernel_size)
@@ -53,6 +66,25 @@ class TAM(nn.Module):
         act = self._local_gate(p_ntc, n, t, c)                                                       # (N, T, C)
         x = x.contiguous(memory_format=torch.channels_last)
         return ops.TamStencilFn.apply(x, kern, act, t)
+
+    def _gate_fusable(self, x, t, c):
+        """K5b applies when both BatchNorm1d layers are in eval mode (``fix_BNS``, the ViTTA default), carry affine
+        parameters, and no module of the branches has hooks other than the alignment driver's no-op BatchNorm1d hooks."""
+        if not x.is_cuda or t > 16 or c % 4 != 0:
+            return False
+        from ...utils.norm_stats_utils import CombineNormStatsRegHook_onereg
+        for seq in (self.G, self.L):
+            for m in seq:
+                if m._forward_pre_hooks:
+                    return False
+                for fn in m._forward_hooks.values():
+                    owner = getattr(fn, '__self__', None)
+                    if not (isinstance(owner, CombineNormStatsRegHook_onereg) and owner._is_bn1d):
+                        return False
+        for bn in (self.G[1], self.L[1]):
+            if bn.training or not bn.affine or not bn.track_running_stats:
+                return False
+        return True
 
     def _local_gate(self, p_ntc, n, t, c):
         """L branch (reference :35-41,52-55) on the (N, T, C) pooled tensor.  The k=3 temporal Conv1d is evaluated as ONE

@@ -1256,3 +1256,55 @@ class BnReluPoolFn(torch.autograd.Function):
         if _fused_amax():
             pass        # gx feeds only the stem convolution's weight gradient (library path): no operand range needed
         return gx, gparam[0], gparam[1], None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# K5b: the TAM's G and L gate networks (eval-mode BatchNorm1d) in 3 launches forward / 7 backward
+# ----------------------------------------------------------------------------------------------
+_gate_ws = {}
+
+
+class TamGateFn(torch.autograd.Function):
+    """pooled (N*T, C) -> (kern (N, 3, C), act (N, T, C)): see include/vitta_b200.h K5b.  Parameters are passed as tensors
+    so autograd hands their gradients to the usual accumulation."""
+
+    @staticmethod
+    def forward(ctx, pooled, w1, g_w, g_b, g_rm, g_rv, w2, wa, l_w, l_b, l_rm, l_rv, wb, t, eps1, eps2):
+        _require_cuda(pooled, "tam_gate")
+        pooled = pooled.contiguous()
+        nt, c = pooled.shape
+        n = nt // t
+        dev = pooled.device
+        kern = torch.empty(n, 3, c, dtype=torch.float32, device=dev)
+        act = torch.empty(n, t, c, dtype=torch.float32, device=dev)
+        pre = torch.empty(nt, c // 4, dtype=torch.float32, device=dev)
+        w1c, w2c, wac, wbc = w1.contiguous(), w2.contiguous(), wa.contiguous(), wb.contiguous()
+        call("vitta_tam_gate_fwd", ptr(pooled), ptr(w1c), _lib.make_bn(g_w, g_b, g_rm, g_rv, eps1), ptr(w2c), ptr(wac),
+             _lib.make_bn(l_w, l_b, l_rm, l_rv, eps2), ptr(wbc), ptr(kern), ptr(act), ptr(pre), n, t, c, stream_ptr())
+        ctx.save_for_backward(pooled, w1c, g_w, g_b, g_rm, g_rv, w2c, wac, l_w, l_b, l_rm, l_rv, wbc, act, pre)
+        ctx.meta = (n, t, c, eps1, eps2)
+        return kern, act
+
+    @staticmethod
+    def backward(ctx, gkern, gact):
+        pooled, w1, g_w, g_b, g_rm, g_rv, w2, wa, l_w, l_b, l_rm, l_rv, wb, act, pre = ctx.saved_tensors
+        n, t, c, eps1, eps2 = ctx.meta
+        dev = pooled.device
+        z = lambda ref: torch.zeros_like(ref)
+        gkern = z(act.new_empty(n, 3, c)) if gkern is None else gkern.contiguous()
+        gact = z(act) if gact is None else gact.contiguous()
+        key = (dev, n, t, c)
+        ws = _gate_ws.get(key)
+        if ws is None:
+            ws = _gate_ws[key] = torch.zeros(_lib.load().vitta_tam_gate_bwd_ws_floats(n, t, c), dtype=torch.float32,
+                                             device=dev)
+        e = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+        gp, gw1, gw2, gwa, gwb = e(n * t, c), e(*w1.shape), e(*w2.shape), e(*wa.shape), e(*wb.shape)
+        gb1 = e(2, g_w.shape[0])
+        gb2 = e(2, l_w.shape[0])
+        gz, gpre, ghm = e(n * t, c), e(n * t, c // 4), e(n * t, c // 4)
+        call("vitta_tam_gate_bwd", ptr(pooled), ptr(w1), _lib.make_bn(g_w, g_b, g_rm, g_rv, eps1), ptr(w2), ptr(wa),
+             _lib.make_bn(l_w, l_b, l_rm, l_rv, eps2), ptr(wb), ptr(act), ptr(pre), ptr(gkern), ptr(gact), ptr(gp),
+             ptr(gw1), ptr(gb1[0]), ptr(gb1[1]), ptr(gw2), ptr(gwa), ptr(gb2[0]), ptr(gb2[1]), ptr(gwb), ptr(gz),
+             ptr(gpre), ptr(ghm), ptr(ws), n, t, c, stream_ptr())
+        return (gp, gw1, gb1[0], gb1[1], None, None, gw2, gwa, gb2[0], gb2[1], None, None, gwb, None, None, None)

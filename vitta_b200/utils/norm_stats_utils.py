@@ -39,6 +39,7 @@ class _Generation:
 
 
 _align_gen = _Generation()
+_zero_scalars = {}     # device -> shared constant 0-dim zero (never written)
 _stat_gen = _Generation()
 _process_group = None
 
@@ -166,6 +167,14 @@ class CombineNormStatsRegHook_onereg(_TapBase):
 
     def note_batch(self, n_clips):
         self._layer.n_batch = int(n_clips)
+
+    def mark_bn1d_fired(self, device):
+        """Called by the fused TAM gate kernels instead of running the BatchNorm1d module: this hook contributes an exact
+        zero for stat_type_list == ['spatiotemp'] (reference :158-183), so all it needs is to have 'seen' a forward."""
+        z = _zero_scalars.get(device)
+        if z is None:
+            z = _zero_scalars[device] = torch.zeros((), dtype=torch.float32, device=device)
+        self._zero = z
 
     def hook_fn(self, module, input, output):
         feature = input[0] if self.before_norm else output
