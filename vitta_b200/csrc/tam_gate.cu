@@ -266,24 +266,36 @@ __device__ __forceinline__ void gate_store(const GateArgs& a, int m, int n, floa
   }
 }
 
+// 32 x 32 output tile per CTA (16 x 16 threads, 2 x 2 outputs each), K walked in steps of kGateBK = 128: every thread has
+// 32 independent operand loads in flight per step -- the operands are L2-resident, so the kernel is bound by L2 latency
+// times the number of K steps (a 32-wide step made the K = 3C stage of a 512-channel TAM take ~50 us).
+constexpr int kGateBK = 128;
+
 template <int STAGE>
 __global__ void __launch_bounds__(256) tam_gate_gemm_kernel(GateArgs a, int M, int Nn, int K) {
-  __shared__ float As[32][33], Bs[32][33];
+  __shared__ float As[kGateBK][33], Bs[kGateBK][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  for (int k0 = 0; k0 < K; k0 += kGateBK) {
+    float av[kGateBK / 8], bv[kGateBK / 8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kGateBK / 8; ++i) {
       const int idx = threadIdx.x + i * 256;
-      const int kk = idx & 31, r = idx >> 5;
+      const int kk = idx % kGateBK, r = idx / kGateBK;
       const int k = k0 + kk;
-      As[kk][r] = (m0 + r < M && k < K) ? gate_A<STAGE>(a, m0 + r, k) : 0.f;
-      Bs[kk][r] = (n0 + r < Nn && k < K) ? gate_B<STAGE>(a, n0 + r, k) : 0.f;
+      av[i] = (m0 + r < M && k < K) ? gate_A<STAGE>(a, m0 + r, k) : 0.f;
+      bv[i] = (n0 + r < Nn && k < K) ? gate_B<STAGE>(a, n0 + r, k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kGateBK / 8; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      As[idx % kGateBK][idx / kGateBK] = av[i];
+      Bs[idx % kGateBK][idx / kGateBK] = bv[i];
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
+#pragma unroll 16
+    for (int kk = 0; kk < kGateBK; ++kk) {
       const float a0 = As[kk][ty], a1 = As[kk][ty + 16], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
