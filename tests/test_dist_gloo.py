@@ -214,3 +214,57 @@ def test_two_rank_driver_shards_every_batch_and_merges_accuracy(tmp_path):
     port = _free_port()
     mp.spawn(_driver_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    """GradBucketer (collective C2 overlapped with the backward): bucketed asynchronous all-reduces started from
+    post-accumulate-grad hooks must deliver exactly the summed gradients of a flat all-reduce, leave p.grad alone,
+    keep their flat-buffer addresses across steps, and stand down cleanly when disabled or when the live set changes."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vitta_b200 import ops
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(16, 16) for _ in range(6)])
+    params = list(net.parameters())
+    bk = ops.GradBucketer(params, dist.group.WORLD, n_buckets=3)
+    assert len(bk.buckets) == 3 and bk.buckets[0][0] is params[-1]          # reverse registration order
+    assert sum(len(b) for b in bk.buckets) == len(params)
+    ptrs = {p: bk.views[p].data_ptr() for p in params}
+    for step in range(3):
+        for p in params:
+            p.grad = None
+        x = torch.randn(4, 16, generator=torch.Generator().manual_seed(10 * step + rank))
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in params]
+        views = bk.finish(params)
+        assert views is not None
+        for p, g in zip(params, local):
+            want = g.clone()
+            dist.all_reduce(want)
+            assert torch.equal(p.grad, g)                                   # p.grad untouched
+            assert torch.allclose(views[p], want, rtol=0, atol=0)           # same sum (2 ranks: order-independent)
+            assert views[p].data_ptr() == ptrs[p]                           # stable addresses
+    # disabled (ragged step): hooks stand down, finish() says "flat path"
+    bk.enabled = False
+    for p in params:
+        p.grad = None
+    net(torch.randn(4, 16)).sum().backward()
+    assert bk.finish(params) is None
+    bk.enabled = True
+    # a parameter without gradient this step: its bucket never completes -> None, and no collective is left dangling
+    for p in params:
+        p.grad = None
+    net[3:](torch.randn(4, 16)).sum().backward()
+    live = [p for p in params if p.grad is not None]
+    assert len(live) == 6 and bk.finish(live) is None
+    dist.barrier()
+    bk.close()
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_allreduce(tmp_path):
+    port = _free_port()
+    mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -363,6 +363,8 @@ class OnlineAdapter:
             else:
                 loss = loss_reg                                        # :667: lambda_feature_reg not applied
             self.optimizer.zero_grad()
+            if isinstance(self.optimizer, ops.FusedSGD):
+                self.optimizer.set_overlap(not getattr(self, '_ragged', False))
             loss.backward()
             if getattr(self, '_ragged', False):
                 self._live_mask = self._exchange_live_mask()     # idle ranks are waiting for it (adapt_idle)
@@ -414,6 +416,7 @@ class OnlineAdapter:
                 a.global_clips = int(global_videos) * per_video
                 a.finalize_idle(dev)
             if isinstance(self.optimizer, ops.FusedSGD):
+                self.optimizer.set_overlap(False)
                 self.optimizer.step_idle()
             else:
                 live = self._exchange_live_mask()

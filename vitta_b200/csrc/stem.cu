@@ -129,25 +129,32 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __re
     const int64_t f = q / H;
     const float4 xv = ld_stream4(x + p * C + c);
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    // windows containing (h, ww): ho in {floor(h/2), and (h+1)/2 when h is odd}, likewise for the columns
+    // windows containing (h, ww): ho in {floor(h/2), and (h+1)/2 when h is odd}, likewise for the columns.  All (up to
+    // four) code / gradient loads are issued before the first use.
     const int ho0 = h >> 1, nho = (h & 1) ? 2 : 1;
     const int wo0 = ww >> 1, nwo = (ww & 1) ? 2 : 1;
-    for (int a = 0; a < nho; ++a) {
-      const int ho = ho0 + a;
-      if (ho >= Ho) continue;
-      const int dh = h - (2 * ho - 1);
-      for (int bb = 0; bb < nwo; ++bb) {
-        const int wo = wo0 + bb;
-        if (wo >= Wo) continue;
-        const uint32_t mine = (uint32_t)(3 * dh + (ww - (2 * wo - 1)));
+    uint32_t cd[4], mine[4];
+    float4 gp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = i >> 1, bb = i & 1;
+      const int ho = ho0 + a, wo = wo0 + bb;
+      const bool ok = a < nho && bb < nwo && ho < Ho && wo < Wo;
+      mine[i] = (uint32_t)(3 * (h - (2 * ho - 1)) + (ww - (2 * wo - 1)));
+      cd[i] = 0xffffffffu;                       // matches no window position
+      gp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
         const int64_t o = ((f * Ho + ho) * Wo + wo) * C4 + lane;
-        const uint32_t cd = __ldg(reinterpret_cast<const uint32_t*>(code) + o);
-        const float4 gp = ldg4(gpool + o * 4);
-        if ((cd & 0xffu) == mine) g.x += gp.x;
-        if (((cd >> 8) & 0xffu) == mine) g.y += gp.y;
-        if (((cd >> 16) & 0xffu) == mine) g.z += gp.z;
-        if ((cd >> 24) == mine) g.w += gp.w;
+        cd[i] = __ldg(reinterpret_cast<const uint32_t*>(code) + o);
+        gp[i] = ldg4(gpool + o * 4);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((cd[i] & 0xffu) == mine[i]) g.x += gp[i].x;
+      if (((cd[i] >> 8) & 0xffu) == mine[i]) g.y += gp[i].y;
+      if (((cd[i] >> 16) & 0xffu) == mine[i]) g.z += gp[i].z;
+      if ((cd[i] >> 24) == mine[i]) g.w += gp[i].w;
     }
     // ReLU mask on y = BN(x)
     const float yx = fmaf(xv.x - rm.x, k.x, b.x), yy = fmaf(xv.y - rm.y, k.y, b.y);

@@ -126,6 +126,80 @@ def allreduce_grads(grads, group):
     return outs, flat
 
 
+class GradBucketer:
+    """Collective C2 overlapped with the backward pass (device agnostic; exercised on CPU with gloo).
+
+    The parameters that receive gradients are cut into a few buckets in REVERSE registration order -- the order in which
+    the backward pass finishes them (layer4 first: 60 % of TANet's gradient bytes are complete when three quarters of
+    the backward are still to run).  A post-accumulate-grad hook on every parameter counts its bucket down; the last
+    one packs the bucket's gradients into its slice of ONE pre-allocated flat buffer (a single torch.cat(out=...)) and
+    starts an asynchronous all-reduce of that slice.  ``finish()`` waits for the collectives and returns views into the
+    flat buffer, which the optimiser reads in place (their addresses never change, so the fused-SGD pointer table and a
+    captured CUDA graph stay valid).  ``p.grad`` itself is never modified: if a step's live set differs from the one the
+    buckets were built for, ``finish()`` returns None and the caller falls back to the unbucketed all-reduce."""
+
+    def __init__(self, live_params, group, n_buckets=4):
+        import torch.distributed as dist
+        self.group = group
+        self.params = list(live_params)
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        order = list(reversed(self.params))
+        target = (total + n_buckets - 1) // n_buckets
+        self.buckets, cur, acc = [], [], 0
+        for p in order:
+            cur.append(p)
+            acc += p.numel()
+            if acc >= target and len(self.buckets) < n_buckets - 1:
+                self.buckets.append(cur)
+                cur, acc = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.slices, self.views, self.bucket_of, o = [], {}, {}, 0
+        for b, ps in enumerate(self.buckets):
+            start = o
+            for p in ps:
+                self.views[p] = self.flat[o:o + p.numel()].view(p.shape)
+                self.bucket_of[p] = b
+                o += p.numel()
+            self.slices.append(self.flat[start:o])
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._dist = dist
+        self.enabled = True       # False: hooks stand down and finish() reports "use the flat path" (ragged steps, where
+        self.arm()                # a rank without videos cannot run a backward pass and therefore no bucket hooks)
+
+    def arm(self):
+        self._pending = [len(ps) for ps in self.buckets]
+        self._works = [None] * len(self.buckets)
+
+    def _on_grad(self, p):
+        b = self.bucket_of.get(p)
+        if not self.enabled or b is None or self._works[b] is not None:
+            return
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            ps = self.buckets[b]
+            if all(q.grad is not None for q in ps):
+                torch.cat([q.grad.reshape(-1) for q in ps], out=self.slices[b])
+                self._works[b] = self._dist.all_reduce(self.slices[b], group=self.group, async_op=True)
+
+    def finish(self, live):
+        """-> {param: summed gradient view} when exactly the bucketed parameters had gradients this step, else None."""
+        ok = len(live) == len(self.params) and all(p in self.views for p in live) and all(w is not None for w in self._works)
+        for w in self._works:
+            if w is not None:
+                w.wait()
+        views = self.views if ok else None
+        self.arm()
+        return views
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def pinned_bytes(ctypes_array):
     """uint8 tensor in pinned host memory holding a ctypes structure array (source of non-blocking H2D copies)."""
     raw = bytes(ctypes_array)
@@ -659,7 +733,15 @@ class FusedSGD:
         self._block = None
         self._pin = []
         self._pin_next = 0
+        self._bucketer = None
+        self._bucket_live = None
+        self.overlap_allreduce = os.environ.get("VITTA_OVERLAP_ALLREDUCE", "1") == "1"
         self._pin_cap = 0
+
+    def set_overlap(self, on):
+        """Switch the bucketed all-reduce of this step on / off on EVERY rank alike (off for ragged steps)."""
+        if self._bucketer is not None:
+            self._bucketer.enabled = bool(on)
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -729,7 +811,17 @@ class FusedSGD:
         dev = live[0].device
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in live]
         if self.process_group is not None:
-            grads, self._flat_keep = allreduce_grads(grads, self.process_group)   # collective C2
+            views = self._bucketer.finish(live) if self._bucketer is not None else None
+            if views is not None:
+                grads = [views[p] for p in live]          # collective C2 ran in buckets DURING the backward pass
+            else:
+                grads, self._flat_keep = allreduce_grads(grads, self.process_group)   # collective C2, one flat buffer
+                if self.overlap_allreduce and self._bucket_live != [id(p) for p in live]:
+                    # (re)build the buckets for the live set just seen; they take over from the next step on
+                    if self._bucketer is not None:
+                        self._bucketer.close()
+                    self._bucketer = GradBucketer(live, self.process_group)
+                    self._bucket_live = [id(p) for p in live]
         first, rest = [], []
         for p, g in zip(live, grads):
             if not p.is_contiguous():
