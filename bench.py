@@ -136,6 +136,11 @@ def attribute_step(adapter, resident, step=None):
     flops (2*M*N*K of the fp32 product, not the 3 MMAs issued per product) and bytes."""
     import torch
     from vitta_b200 import _lib
+    # Eager launches are CPU-bound (~0.7 k launches at ~10 us of Python / ctypes each), so a GPU that has caught up with
+    # the CPU would add the launch latency to every event pair.  A spin kernel in front keeps the device busy while the
+    # whole step is enqueued behind it: the kernels then run back to back, as they do inside the replayed CUDA graph.
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(1.5e8))       # ~80 ms at 1.9 GHz
     _lib.profile = []
     (step or (lambda: adapter._adapt_eager(resident)))()
     torch.cuda.synchronize()

@@ -292,6 +292,9 @@ int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_star
  *   Cin multiple of 4.  Padding comes from the TMA out-of-bounds zero fill; no im2col buffer exists. */
 #define VITTA_GEMM_FORCE_SS 0x1000
 #define VITTA_GEMM_FORCE_TS 0x2000
+/* vitta_conv2d_*_ex only, or-ed into force_bn: the epilogue ends with ReLU, applied after bias and residual -- the
+ * BN-folded inference convolution  relu(conv(x, k*W) + b' [+ shortcut])  of the per-step evaluation forward. */
+#define VITTA_CONV_RELU 0x4000
 int vitta_gemm_set_operand_form(int form);
 /* vitta_gemm_set_cta_pair(1): N tiles of 256 run as clusters of two CTAs issuing tcgen05.mma.cta_group::2 (M = 256 per
  * pair; each CTA loads half of the weight tile, halving the L2 -> SM weight traffic that bounds the wide layers).

@@ -49,7 +49,8 @@ struct GemmParams {
   int Ho, Wo, F;           // output geometry: rows of C = (f, ho, wo); plain GEMM: F = 1, Ho = 1, Wo = M
   int BW, BH, BF;          // output pixels covered by one M tile: BF frames x BH rows x BW cols  (BW*BH*BF <= 128)
   int tiles_w, tiles_h, tiles_f, tiles_n;
-  int act;                 // 0 none, 1 exact GELU, 2 multiply by GELU'(residual[m, n]) (residual = saved pre-activation)
+  int act;                 // 0 none, 1 exact GELU, 2 multiply by GELU'(residual[m, n]) (residual = saved pre-activation),
+                           // 3 ReLU applied last, after bias and residual
   int vec_ok;              // C / bias / residual allow 128-bit accesses
   // optional tap table (strided data gradient): tap t reads the A box shifted by (tap_dh, tap_dw) and the B columns of
   // weight tap tap_wt; 0 taps = the plain taps_h x taps_w raster
@@ -522,6 +523,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v0.x *= rscale; v0.y *= rscale; v0.z *= rscale; v0.w *= rscale;
                 v1.x *= rscale; v1.y *= rscale; v1.z *= rscale; v1.w *= rscale;
               }
+              if (p.act == 3) {   // ReLU after bias and residual (BN-folded inference convolution)
+                v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v0.z = fmaxf(v0.z, 0.f); v0.w = fmaxf(v0.w, 0.f);
+                v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); v1.z = fmaxf(v1.z, 0.f); v1.w = fmaxf(v1.w, 0.f);
+              }
               st8(crow + nbase + j, v0, v1);
             }
           } else if (nbase + 32 <= p.N && p.vec_ok) {
@@ -547,6 +552,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               } else {
                 v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
               }
+              if (p.act == 3) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               st4(crow + nbase + j, v);
             }
           } else {
@@ -560,6 +566,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (p.act == 1) v = gelu_exact(v);
                 if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale : fmaf(v, rscale, rrow[n]);
                 else v *= rscale;
+                if (p.act == 3) v = fmaxf(v, 0.f);
                 crow[n] = v;
               }
             }
@@ -858,9 +865,10 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& bh, const CUtens
 // force_bn: 0 = automatic, 64 / 128 / 256 = that N tile; | kForceSS / kForceTS = shared-memory / tensor-memory A operands
 // (both forms stay selectable so that they are tested and timed against each other)
 constexpr int kForceSS = 0x1000, kForceTS = 0x2000;
+constexpr int kConvRelu = 0x4000;   // conv entry points: apply ReLU last (after bias and residual)
 
 static int pick_bn(int N, int forced, int64_t tiles_m = 0) {
-  forced &= ~(kForceSS | kForceTS);
+  forced &= ~(kForceSS | kForceTS | kConvRelu);
   if (forced == 64 || forced == 128 || forced == 256) return forced;
   if (N <= 64) return 64;
   if (N <= 128 || N % 256 != 0) return 128;
@@ -1078,7 +1086,7 @@ static int conv2d_impl(const float* X, int F, int H, int W, int Cin, const void*
   p.Ho = Ho; p.Wo = Wo; p.F = F;
   p.BW = BW; p.BH = BH; p.BF = BF;
   p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH; p.tiles_f = (F + BF - 1) / BF;
-  p.act = 0;
+  p.act = (force_bn & kConvRelu) ? 3 : 0;
   p.vec_ok = aligned16(Y) && (Cout % 4 == 0) && (!bias || aligned16(bias)) && (!residual || aligned16(residual));
   if (p.vec_ok && aligned32(Y) && (Cout % 8 == 0) && (!residual || aligned32(residual))) p.vec_ok = 2;
   return dispatch(ta, tbh, tbl, p, bn, (cudaStream_t)stream, force_bn);

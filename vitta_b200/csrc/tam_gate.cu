@@ -187,8 +187,16 @@ __global__ void __launch_bounds__(kGThreads) tam_g_bwd_kernel(GateArgs a, int n_
   if (!s_last) return;
   __threadfence();
   for (int o = tid; o < n_part; o += kGThreads) {
+    // CTA order is kept (deterministic), but the loads go out eight at a time: a plain `acc += load` loop pays one L2
+    // round trip per CTA and output (32 CTAs x 6 outputs per thread = ~60 us of pure latency on a 512-channel TAM)
     float acc = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(a.ws + (int64_t)b * n_part + o);
+    for (unsigned b0 = 0; b0 < gridDim.x; b0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (b0 + u < gridDim.x) ? __ldcg(a.ws + (int64_t)(b0 + u) * n_part + o) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
     if (o < H * T) a.gW1[o] = acc;
     else if (o < H * T + 3 * H) a.gW2[o - H * T] = acc;
     else if (o < H * T + 4 * H) a.gbn1w[o - H * T - 3 * H] = acc;
@@ -319,20 +327,85 @@ __global__ void __launch_bounds__(256) tam_gate_gz_kernel(GateArgs a, int64_t n)
   }
 }
 
-// BatchNorm1d (eval) parameter gradients of the L branch: one thread per hidden channel, rows in order
-__global__ void tam_gate_bn2_kernel(GateArgs a, int R) {
+// BatchNorm1d (eval) parameter gradients of the L branch.  CTA = 32 hidden channels x 8 row slices; a slice walks its
+// rows eight at a time (loads first), the slices are added in slice order through shared memory (deterministic).
+__global__ void __launch_bounds__(256) tam_gate_bn2_kernel(GateArgs a, int R) {
+  __shared__ float sgw[8][33], sgb[8][33];
   const int Hc = a.C / 4;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= Hc) return;
-  const float rm = __ldg(a.bn2.rm + o), istd = 1.f / sqrtf(__ldg(a.bn2.rv + o) + a.bn2.eps);
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
   float gw = 0.f, gb = 0.f;
-  for (int r = 0; r < R; ++r) {
-    const float g = a.ghm[(int64_t)r * Hc + o];
-    gb += g;
-    gw = fmaf(g, (__ldg(a.pre + (int64_t)r * Hc + o) - rm) * istd, gw);
+  if (o < Hc) {
+    const float rm = __ldg(a.bn2.rm + o), istd = 1.f / sqrtf(__ldg(a.bn2.rv + o) + a.bn2.eps);
+    const int per = (R + 7) / 8;
+    const int r0 = slice * per, r1 = min(R, r0 + per);
+    for (int rb = r0; rb < r1; rb += 8) {
+      float g[8], x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = rb + u < r1;
+        g[u] = ok ? a.ghm[(int64_t)(rb + u) * Hc + o] : 0.f;
+        x[u] = ok ? __ldg(a.pre + (int64_t)(rb + u) * Hc + o) : rm;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        gb += g[u];
+        gw = fmaf(g[u], (x[u] - rm) * istd, gw);
+      }
+    }
   }
-  a.gbn2w[o] = gw;
-  a.gbn2b[o] = gb;
+  sgw[slice][lane] = gw;
+  sgb[slice][lane] = gb;
+  __syncthreads();
+  if (slice == 0 && o < Hc) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { tw += sgw[q][lane]; tb += sgb[q][lane]; }
+    a.gbn2w[o] = tw;
+    a.gbn2b[o] = tb;
+  }
+}
+
+// L branch, hidden layer (the K = 3C stage): CTA = (slice of hidden channels, video).  The video's pooled rows
+// p[n] (T x C, plus a zero row on either side for the temporal padding) are staged in shared memory once; a warp owns
+// one hidden channel at a time, its lanes stride over the input channels of one temporal tap (conflict-free smem rows,
+// weights read once from L2) and keep T accumulators, reduced across the lanes at the end.
+constexpr int kL1Slices = 8;
+
+__global__ void __launch_bounds__(256) tam_l1_fwd_kernel(GateArgs a) {
+  extern __shared__ float sp[];   // [(T + 2)][C]
+  const int T = a.T, C = a.C, Hc = a.C / 4;
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (T + 2) * C; i += 256) {
+    const int t = i / C - 1;
+    sp[i] = (t >= 0 && t < T) ? __ldg(a.p + ((int64_t)n * T + t) * C + (i % C)) : 0.f;
+  }
+  __syncthreads();
+  const int per = (Hc + kL1Slices - 1) / kL1Slices;
+  const int o0 = blockIdx.x * per, o1 = min(Hc, o0 + per);
+  for (int o = o0 + warp; o < o1; o += 8) {
+    float acc[kGateMaxT];
+#pragma unroll
+    for (int t = 0; t < kGateMaxT; ++t) acc[t] = 0.f;
+    const float* wrow = a.Wa + (int64_t)o * 3 * C;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      for (int c = lane; c < C; c += 32) {
+        const float w = __ldg(wrow + c * 3 + j);
+#pragma unroll
+        for (int t = 0; t < kGateMaxT; ++t)
+          if (t < T) acc[t] = fmaf(w, sp[(t + j) * C + c], acc[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kGateMaxT; ++t) {
+      if (t < T) {
+        const float v = warp_sum(acc[t]);
+        if (lane == 0) a.pre[((int64_t)n * T + t) * Hc + o] = v;
+      }
+    }
+  }
 }
 
 template <int STAGE>
@@ -372,7 +445,20 @@ int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float
   cudaStream_t st = (cudaStream_t)stream;
   tam_g_fwd_kernel<<<(unsigned)((N * C + kGThreads - 1) / kGThreads), kGThreads, 0, st>>>(a);
   VITTA_CHECK_LAUNCH();
-  launch_stage<kL1Fwd>(a, N * T, C / 4, 3 * C, st);
+  {
+    const size_t smem = sizeof(float) * (size_t)(T + 2) * C;
+    VITTA_CHECK_ARG(smem <= 200 * 1024, VITTA_E_UNSUPPORTED, "tam_gate_fwd: (T + 2) * C floats exceed shared memory");
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(tam_l1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_error("tam_gate_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      attr_smem = smem;
+    }
+    tam_l1_fwd_kernel<<<dim3(kL1Slices, (unsigned)N), 256, smem, st>>>(a);
+  }
   VITTA_CHECK_LAUNCH();
   launch_stage<kL2Fwd>(a, N * T, C, C / 4, st);
   VITTA_CHECK_LAUNCH();
@@ -424,7 +510,7 @@ int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float
   VITTA_CHECK_LAUNCH();
   launch_stage<kGradHid>(a, R, Hc, C, st);
   VITTA_CHECK_LAUNCH();
-  tam_gate_bn2_kernel<<<(unsigned)((Hc + 127) / 128), 128, 0, st>>>(a, R);
+  tam_gate_bn2_kernel<<<(unsigned)((Hc + 31) / 32), 256, 0, st>>>(a, R);
   VITTA_CHECK_LAUNCH();
   launch_stage<kGradWa>(a, Hc, 3 * C, R, st);
   VITTA_CHECK_LAUNCH();
