@@ -185,6 +185,10 @@ int vitta_tam_fwd_amax(const float* x, const float* kern, const float* act, floa
                        float* amax_out, void* stream);
 int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
                   int N, int T, int64_t HW, int C, void* stream);
+/* After vitta_tam_bwd: sums dpart over its row chunks (fixed order) and contracts it with act / kern:
+ *   gkern[n,k,c] = sum_t act[n,t,c] * D[n,t,k,c],  gact[n,t,c] = sum_k kern[n,k,c] * D[n,t,k,c]. */
+int vitta_tam_bwd_finish(const float* dpart, const float* kern, const float* act, float* gkern, float* gact, int N, int T,
+                         int nch, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 prediction consistency, forward + gradient in one launch.  preds (B, V, K) logits.
@@ -265,7 +269,24 @@ typedef struct VittaSplitTensor {
   int32_t R, T, Cc, mode;
   int32_t src_tap_inner, compute_amax;
   int64_t n;
+  const float* fold_w;   /* optional eval-mode BatchNorm folded into the rows: row r scaled by fold_w[r] / sqrt(fold_rv[r] + */
+  const float* fold_rv;  /*   fold_eps) before the split (null: none) -- the weights of the BN-folded inference convolutions */
+  float fold_eps;
+  int32_t reserved;
 } VittaSplitTensor;
+typedef struct VittaFoldBias {
+  const float *w, *b, *rm, *rv;   /* BatchNorm weight, bias, running_mean, running_var */
+  float* out;                     /* out[c] = b[c] - rm[c] * w[c] / sqrt(rv[c] + eps) */
+  float eps;
+  int32_t C;
+} VittaFoldBias;
+/* folded biases of all eval-mode BatchNorm layers behind convolutions, one launch (table in device memory) */
+int vitta_bn_fold_bias_multi(const VittaFoldBias* table, int n, void* stream);
+/* BN-folded inference convolution (fp16 split): Y = [relu](conv(X, W') + bias [+ residual]); *y_amax (optional, zeroed by
+ * the caller) receives max|Y|.  Used by the per-step evaluation forward (reference corpus/basics.py:691-713). */
+int vitta_conv2d_f16x3_infer(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
+                             const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad,
+                             float* Y, const float* bias, const float* residual, int relu, float* y_amax, void* stream);
 int vitta_split_block_elems(void);
 int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
                       int f16, void* stream);

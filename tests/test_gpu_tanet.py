@@ -190,3 +190,40 @@ def test_tanet_golden_under_both_operand_splits(cuda_device):
             _run_case("tanet_t8_r64_stats_mse", cuda_device)
     finally:
         ops.set_gemm_precision(before)
+
+
+def test_bn_folded_inference_forward_matches_layerwise_forward(cuda_device, monkeypatch):
+    """The evaluation forward folds every eval-mode BatchNorm into its convolution (K6 epilogue: + bias, + shortcut, ReLU;
+    two multi-tensor launches refresh all folded operands after a weight update).  It must agree with the layer-by-layer
+    forward (VITTA_INFER_FOLD=0) to fp32 rounding, before and after an adaptation step changed the weights."""
+    import vitta_b200
+    from vitta_b200 import synth
+    from vitta_b200.corpus.basics import OnlineAdapter
+    from vitta_b200.models.tanet_models.tanet import TSN
+    from vitta_b200.utils import norm_stats_utils as nsu
+    from vitta_b200.utils.opts import default_args
+    from oracle import vitta_oracle as O
+    vitta_b200.set_fp32_exact()
+    nsu.reset_arenas()
+    K, T, N, res = 11, 8, 2, 64
+    model = TSN(K, T, 'RGB', base_model='resnet50', consensus_type='avg', img_feature_dim=256, tam=True, non_local=False,
+                partial_bn=False)
+    sd = synth.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model.base_model.fc.p = 0.0
+    model = model.to(cuda_device)
+    clean = synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=100, gauss_sigma=0.0, tag="clean"))
+    src_m, src_v = O.collect_source_stats(sd, "tanet", T, [clean.view(N, T, 3, res, res)])
+    args = default_args(arch='tanet', clip_length=T, batch_size=N, n_augmented_views=1, if_pred_consistency=False,
+                        lr=1e-3, num_classes=K, input_size=res)
+    ad = OnlineAdapter(model, args, (src_m, src_v))
+    x = synth.tanet_loader_tensor(synth.synth_video(N, 1, T, res, seed=200, tag="tta")).to(cuda_device)
+    for step in range(2):
+        monkeypatch.setenv("VITTA_INFER_FOLD", "1")
+        a = ad.evaluate(x)
+        assert getattr(ad.model.base_model, "_folds", None) is not None          # the folded path really ran
+        monkeypatch.setenv("VITTA_INFER_FOLD", "0")
+        b = ad.evaluate(x)
+        cases.assert_close(a.cpu(), b.cpu().numpy(), 1e-4, 1e-5 * float(b.abs().max()), "folded vs layerwise logits, step %d" % step)
+        ad.hooks_on()
+        ad.adapt(x)                                                               # weights move: folds must refresh

@@ -40,7 +40,13 @@ class VittaSgdTensor(C.Structure):
 class VittaSplitTensor(C.Structure):
     _fields_ = [("src", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("amax", C.c_void_p), ("R", C.c_int32),
                 ("T", C.c_int32), ("Cc", C.c_int32), ("mode", C.c_int32), ("src_tap_inner", C.c_int32),
-                ("compute_amax", C.c_int32), ("n", C.c_int64)]
+                ("compute_amax", C.c_int32), ("n", C.c_int64), ("fold_w", C.c_void_p), ("fold_rv", C.c_void_p),
+                ("fold_eps", C.c_float), ("reserved", C.c_int32)]
+
+
+class VittaFoldBias(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("rm", C.c_void_p), ("rv", C.c_void_p), ("out", C.c_void_p),
+                ("eps", C.c_float), ("C", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -67,6 +73,7 @@ _SIGNATURES = {
     "vitta_tam_fwd_amax": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
+    "vitta_tam_bwd_finish": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vitta_gemm_set_operand_form": (C.c_int, [C.c_int]),
     "vitta_gemm_set_cta_pair": (C.c_int, [C.c_int]),
@@ -130,6 +137,9 @@ _SIGNATURES = {
     "vitta_bn_relu_pool_fwd": (C.c_int, [_P, VittaBN, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_bn_relu_pool_bwd_ws_floats": (C.c_int64, [C.c_int]),
     "vitta_bn_relu_pool_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_bn_fold_bias_multi": (C.c_int, [_P, C.c_int, _P]),
+    "vitta_conv2d_f16x3_infer": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
     "vitta_split_block_elems": (C.c_int, []),
     "vitta_split_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),

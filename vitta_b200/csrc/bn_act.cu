@@ -265,7 +265,7 @@ __device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restr
       }
       const int64_t off0 = row0 * C + c;
       // batched like the forward: all loads of kB rows are in flight before the first use
-      constexpr int kB = 2;
+      constexpr int kB = 4;
       auto body = [&](float4 xv, float4 g, float4 rx, int64_t off) {
         const float4 y = apply_aff(a, xv);
         float4 rr = f4zero();
@@ -296,33 +296,29 @@ __device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restr
           agw2.z = fmaf(gr.z, (rx.z - a2.rm.z) * a2.istd.z, agw2.z); agw2.w = fmaf(gr.w, (rx.w - a2.rm.w) * a2.istd.w, agw2.w);
         }
       };
-      // software-pipelined like the forward: batch i+1 is in flight while batch i is processed
       const int64_t rstep = (int64_t)p.rs * C;
-      auto load = [&](int r0, float4* xb, float4* gb, float4* rb) {
+      int r = slot;
+      for (; r + (kB - 1) * p.rs < nrows; r += kB * p.rs) {
+        const int64_t off = off0 + (int64_t)r * C;
+        float4 xv[kB], gv[kB], rv[kB];
 #pragma unroll
-        for (int j = 0; j < kB; ++j) {
-          if (r0 + j * p.rs < nrows) {
-            const int64_t off = off0 + (int64_t)r0 * C + j * rstep;
-            xb[j] = ld_stream4(p.x + off);
-            gb[j] = ld_stream4(p.gout + off);
-            if (RES != 0) rb[j] = ld_stream4(p.res + off);
-          }
+        for (int j = 0; j < kB; ++j) xv[j] = ld_stream4(p.x + off + j * rstep);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) gv[j] = ld_stream4(p.gout + off + j * rstep);
+        if (RES != 0) {
+#pragma unroll
+          for (int j = 0; j < kB; ++j) rv[j] = ld_stream4(p.res + off + j * rstep);
         }
-      };
-      auto proc = [&](int r0, const float4* xb, const float4* gb, const float4* rb) {
 #pragma unroll
-        for (int j = 0; j < kB; ++j)
-          if (r0 + j * p.rs < nrows)
-            body(xb[j], gb[j], RES != 0 ? rb[j] : f4zero(), off0 + (int64_t)r0 * C + j * rstep);
-      };
-      float4 xa[kB], ga[kB], ra[kB], xb2[kB], gb2[kB], rb2[kB];
-      const int bstep = kB * p.rs;
-      load(slot, xa, ga, ra);
-      for (int r0 = slot; r0 < nrows; r0 += 2 * bstep) {
-        load(r0 + bstep, xb2, gb2, rb2);
-        proc(r0, xa, ga, ra);
-        load(r0 + 2 * bstep, xa, ga, ra);
-        proc(r0 + bstep, xb2, gb2, rb2);
+        for (int j = 0; j < kB; ++j) body(xv[j], gv[j], RES != 0 ? rv[j] : f4zero(), off + j * rstep);
+      }
+      for (; r < nrows; r += p.rs) {
+        const int64_t off = off0 + (int64_t)r * C;
+        const float4 xv = ld_stream4(p.x + off);
+        const float4 g = ld_stream4(p.gout + off);
+        float4 rx = f4zero();
+        if (RES != 0) rx = ld_stream4(p.res + off);
+        body(xv, g, rx, off);
       }
     }
   }

@@ -63,6 +63,7 @@ struct GemmParams {
   int rows_per_group;
   const float* a_amax;     // F16 kernels: device scalars >= max|A|, >= max|B| (f16_split_scale)
   const float* b_amax;
+  float* amax_out;         // optional: max|C| of everything this launch stores (operand range of the next fp16-split GEMM)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -434,6 +435,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int row = q * 32 + lane;                // accumulator row == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
+    float out_amax = 0.f;
     float inv_a = 1.f, inv_b = 1.f;   // F16: 1 / s_a, 1 / s_b -- exact powers of two, applied one after the other (their
     if constexpr (F16) {              // product alone could leave the fp32 range for tiny gradient tensors)
       float s_unused;
@@ -527,6 +529,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v0.z = fmaxf(v0.z, 0.f); v0.w = fmaxf(v0.w, 0.f);
                 v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); v1.z = fmaxf(v1.z, 0.f); v1.w = fmaxf(v1.w, 0.f);
               }
+              if (p.amax_out) {
+                out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+                out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+              }
               st8(crow + nbase + j, v0, v1);
             }
           } else if (nbase + 32 <= p.N && p.vec_ok) {
@@ -553,6 +559,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
               }
               if (p.act == 3) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (p.amax_out) out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
               st4(crow + nbase + j, v);
             }
           } else {
@@ -567,6 +574,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale : fmaf(v, rscale, rrow[n]);
                 else v *= rscale;
                 if (p.act == 3) v = fmaxf(v, 0.f);
+                if (p.amax_out) out_amax = fmaxf(out_amax, fabsf(v));
                 crow[n] = v;
               }
             }
@@ -580,6 +588,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         else mbar_arrive(&acc_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.amax_out) {   // one integer atomic per epilogue warp (non-negative floats order like their bit patterns)
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
+      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
     }
   }
 
@@ -674,7 +686,15 @@ struct SplitEntry {
   int32_t R, T, Cc, mode;
   int32_t src_tap_inner, compute_amax;
   int64_t n;
+  const float* fold_w;    // optional eval-mode BatchNorm folded into the rows: row r is scaled by
+  const float* fold_rv;   //   fold_w[r] * (1 / sqrt(fold_rv[r] + fold_eps))   (null: no scaling)
+  float fold_eps;
+  int32_t reserved;
 };
+
+__device__ __forceinline__ float split_row_scale(const SplitEntry& t, int r) {
+  return t.fold_w ? __ldg(t.fold_w + r) * (1.f / sqrtf(__ldg(t.fold_rv + r) + t.fold_eps)) : 1.f;
+}
 
 __device__ __forceinline__ int split_find(const int32_t* __restrict__ block_start, int n_tensors, int bid) {
   int lo = 0, hi = n_tensors - 1;
@@ -699,7 +719,12 @@ __global__ void __launch_bounds__(256) split_multi_amax_kernel(const SplitEntry*
   const int64_t rem = t.n - e0;
   const int cnt = (int)(rem < kSplitBlock ? rem : kSplitBlock);
   uint32_t m = 0;
-  for (int i = threadIdx.x; i < cnt; i += 256) m = max(m, __float_as_uint(fabsf(__ldg(t.src + e0 + i))));
+  const int64_t row_elems = (int64_t)t.T * t.Cc;   // both source layouts keep a row's elements together
+  for (int i = threadIdx.x; i < cnt; i += 256) {
+    float v = __ldg(t.src + e0 + i);
+    if (t.fold_w) v *= split_row_scale(t, (int)((e0 + i) / row_elems));
+    m = max(m, __float_as_uint(fabsf(v)));
+  }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(t.amax), m);
 }
@@ -731,17 +756,34 @@ __global__ void __launch_bounds__(256) split_multi_kernel(const SplitEntry* __re
       r = (int)(q / t.T);
     }
     const int64_t s = t.src_tap_inner ? ((int64_t)r * t.Cc + c) * t.T + tp : ((int64_t)r * t.T + tp) * t.Cc + c;
+    const float w = t.fold_w ? __ldg(t.src + s) * split_row_scale(t, r) : __ldg(t.src + s);
     if constexpr (F16) {
-      const float v = __ldg(t.src + s) * sc;
+      const float v = w * sc;
       const __half h = __float2half_rn(v);
       static_cast<__half*>(t.hi)[i] = h;
       static_cast<__half*>(t.lo)[i] = __float2half_rn(v - __half2float(h));
     } else {
-      const float v = __ldg(t.src + s);
+      const float v = w;
       const float h = tf32_rna(v);
       static_cast<float*>(t.hi)[i] = h;
       static_cast<float*>(t.lo)[i] = v - h;
     }
+  }
+}
+
+// folded bias of an eval-mode BatchNorm behind a convolution: b'[c] = beta[c] - running_mean[c] * k[c], all layers at once
+struct FoldBiasEntry {
+  const float *w, *b, *rm, *rv;
+  float* out;
+  float eps;
+  int32_t C;
+};
+
+__global__ void __launch_bounds__(256) bn_fold_bias_multi_kernel(const FoldBiasEntry* __restrict__ tab) {
+  const FoldBiasEntry e = tab[blockIdx.x];
+  for (int c = threadIdx.x; c < e.C; c += 256) {
+    const float k = __ldg(e.w + c) * (1.f / sqrtf(__ldg(e.rv + c) + e.eps));
+    e.out[c] = __ldg(e.b + c) - __ldg(e.rm + c) * k;
   }
 }
 
@@ -1041,7 +1083,7 @@ int vitta_conv2d_tf32x3(const float* X, int F, int H, int W, int Cin, const floa
 
 static int conv2d_impl(const float* X, int F, int H, int W, int Cin, const void* Whi, const void* Wlo, int Cout,
                        int KH, int KW, int stride, int pad, float* Y, const float* bias, const float* residual,
-                       int force_bn, void* stream, const float* a_amax, const float* b_amax) {
+                       int force_bn, void* stream, const float* a_amax, const float* b_amax, float* amax_out = nullptr) {
   const bool f16 = a_amax != nullptr;
   const int stage_k = f16 ? 2 * kBK : kBK;
   VITTA_CHECK_ARG(X && Whi && Wlo && Y && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
@@ -1079,7 +1121,7 @@ static int conv2d_impl(const float* X, int F, int H, int W, int Cin, const void*
   int rc = make_b_maps(&tbh, &tbl, Whi, Wlo, Ktot, Cout, Ktot, bn, f16, force_bn);
   if (rc) return rc;
   GemmParams p{};
-  p.a_amax = a_amax; p.b_amax = b_amax;
+  p.a_amax = a_amax; p.b_amax = b_amax; p.amax_out = amax_out;
   p.C = Y; p.bias = bias; p.residual = residual; p.ldc = Cout; p.ldr = Cout;
   p.M_total = 0; p.N = Cout; p.Kc = Cin; p.k_chunks = (Cin + stage_k - 1) / stage_k;
   p.taps_h = KH; p.taps_w = KW; p.stride = stride; p.pad = pad;
@@ -1303,6 +1345,25 @@ int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_star
   } else {
     split_multi_kernel<false><<<(unsigned)total_blocks, 256, 0, st>>>(t, block_start, n_tensors);
   }
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+// BN-folded inference convolution on the fp16 split (the per-step evaluation forward): Y = [relu](conv(X, W') + bias
+// [+ residual]) with W' = k * W and bias = beta - mean * k prepared by vitta_split_multi / vitta_bn_fold_bias_multi;
+// optionally accumulates max|Y| into *y_amax (zero-initialised by the caller) for the convolution that consumes Y.
+int vitta_conv2d_f16x3_infer(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
+                             const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad,
+                             float* Y, const float* bias, const float* residual, int relu, float* y_amax, void* stream) {
+  VITTA_CHECK_ARG(x_amax && w_amax, VITTA_E_BADARG, "conv2d_f16x3_infer: amax scalars are required");
+  return conv2d_impl(X, F, H, W, Cin, Whi, Wlo, Cout, KH, KW, stride, pad, Y, bias, residual, relu ? kConvRelu : 0, stream,
+                     x_amax, w_amax, y_amax);
+}
+
+int vitta_bn_fold_bias_multi(const VittaFoldBias* table, int n, void* stream) {
+  VITTA_CHECK_ARG(table && n > 0, VITTA_E_BADARG, "bn_fold_bias_multi: bad arguments");
+  static_assert(sizeof(FoldBiasEntry) == sizeof(VittaFoldBias), "layout");
+  bn_fold_bias_multi_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const FoldBiasEntry*>(table));
   VITTA_CHECK_LAUNCH();
   return 0;
 }

@@ -145,6 +145,51 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
   }
 }
 
+
+// After tam_bwd_kernel: D[n, t, k, c] = sum over the row chunks of dpart (fixed order), then
+//   gkern[n, k, c] = sum_t act[n, t, c] * D[n, t, k, c]        gact[n, t, c] = sum_k kern[n, k, c] * D[n, t, k, c]
+// (three eager reductions / products per TAM before).  Thread = (video, 4 channels).
+__global__ void __launch_bounds__(128) tam_bwd_finish_kernel(const float* __restrict__ dpart,
+                                                            const float* __restrict__ kern,
+                                                            const float* __restrict__ act, float* __restrict__ gkern,
+                                                            float* __restrict__ gact, int N, int T, int nch, int C4) {
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= N * C4) return;
+  const int n = idx / C4, c = (idx % C4) * 4;
+  const int C = C4 * 4;
+  const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c), k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c),
+               k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
+  float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+  for (int t = 0; t < T; ++t) {
+    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+    for (int ch0 = 0; ch0 < nch; ch0 += 4) {
+      float4 v[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = ch0 + u < nch;
+        const float* q = dpart + ((((int64_t)n * nch + (ok ? ch0 + u : 0)) * T + t) * 3) * C + c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[u][k] = ok ? ldg4(q + (int64_t)k * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        d0.x += v[u][0].x; d0.y += v[u][0].y; d0.z += v[u][0].z; d0.w += v[u][0].w;
+        d1.x += v[u][1].x; d1.y += v[u][1].y; d1.z += v[u][1].z; d1.w += v[u][1].w;
+        d2.x += v[u][2].x; d2.y += v[u][2].y; d2.z += v[u][2].z; d2.w += v[u][2].w;
+      }
+    }
+    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
+    g0 = fma4(a, d0, g0); g1 = fma4(a, d1, g1); g2 = fma4(a, d2, g2);
+    float4 ga = mul4(k0, d0);
+    ga = fma4(k1, d1, ga);
+    ga = fma4(k2, d2, ga);
+    st4(gact + ((int64_t)n * T + t) * C + c, ga);
+  }
+  st4(gkern + ((int64_t)n * 3 + 0) * C + c, g0);
+  st4(gkern + ((int64_t)n * 3 + 1) * C + c, g1);
+  st4(gkern + ((int64_t)n * 3 + 2) * C + c, g2);
+}
+
 }  // namespace vitta
 
 using namespace vitta;
@@ -198,6 +243,19 @@ int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const fl
   dim3 grid((unsigned)(N * nchunks), (unsigned)g.ctiles);
   tam_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(gout, x, kern, act, gx, dpart, N, T, HW, C, g.lpr, g.rs,
                                                              nchunks, tam_chunk_rows(HW, C));
+  VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+int vitta_tam_bwd_finish(const float* dpart, const float* kern, const float* act, float* gkern, float* gact, int N, int T,
+                         int nch, int C, void* stream) {
+  VITTA_CHECK_ARG(dpart && kern && act && gkern && gact, VITTA_E_BADARG, "tam_bwd_finish: null pointer");
+  VITTA_CHECK_ARG(N > 0 && T > 0 && nch > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_bwd_finish: bad shape");
+  VITTA_CHECK_ARG(aligned16(dpart) && aligned16(kern) && aligned16(act) && aligned16(gkern) && aligned16(gact), VITTA_E_ALIGN,
+                  "tam_bwd_finish: tensors must be 16-byte aligned");
+  const int total = N * (C / 4);
+  tam_bwd_finish_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dpart, kern, act, gkern, gact,
+                                                                                       N, T, nch, C / 4);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

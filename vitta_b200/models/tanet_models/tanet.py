@@ -3,6 +3,8 @@
 Same constructor arguments, attribute names and state-dict keys (``base_model.*``, ``new_fc.*``).  The ResNet-50
 trunk is built here (the reference pulls torchvision's and its ImageNet weights, tanet.py:129, which needs a
 network); activations are kept channels-last and every norm/activation/TAM step is a fused sm_100a kernel."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -44,17 +46,48 @@ class ResNet50Trunk(nn.Module):
         blks += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*blks)
 
+    def _inference_folds(self, x):
+        """The BN-folded operand set when this forward may use it: no autograd (the per-step evaluation / source-only
+        validation), the fp16 operand split, every BatchNorm2d of the residual stages in eval mode without statistics
+        taps or foreign hooks, and plain bias-free convolutions.  None otherwise (the layer-by-layer path runs)."""
+        from ... import ops
+        from ...nn import _fusable
+        if torch.is_grad_enabled() or not x.is_cuda or ops.gemm_precision() != "f16x3" or \
+                os.environ.get("VITTA_INFER_FOLD", "1") != "1":
+            return None
+        blocks = [b for st in (self.layer1, self.layer2, self.layer3, self.layer4) for b in st]
+        if not all(isinstance(b, TemporalBottleneck) for b in blocks):
+            return None
+        pairs = [p for b in blocks for p in b.infer_pairs()]
+        for conv, bn in pairs:
+            if not (_fusable(bn) and bn._vitta_tap is None and conv.bias is None and conv.groups == 1
+                    and conv.dilation == (1, 1) and conv.padding_mode == 'zeros' and not conv._forward_hooks
+                    and not conv._forward_pre_hooks and (conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1]) % 8 == 0
+                    and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+                    and conv.kernel_size[0] == conv.kernel_size[1] and conv.weight.is_contiguous()):
+                return None
+        f = getattr(self, "_folds", None)
+        if f is None or list(f.slot) != [id(c) for c, _ in pairs] or f.bias.device != x.device:   # (deepcopy keeps old ids)
+            f = ops.FoldedConvs(pairs)
+            object.__setattr__(self, "_folds", f)        # plain attribute: not a module / parameter / buffer
+        f.refresh()
+        return f
+
     def forward(self, x):
         t = self.n_segment
         x = stem(self.conv1, self.bn1, self.maxpool, x, t)
         pooled = None
         stages = (self.layer1, self.layer2, self.layer3, self.layer4)
+        folds = self._inference_folds(x)
         for si, stage in enumerate(stages):
             n = len(stage)
             for bi, blk in enumerate(stage):
                 last = si == len(stages) - 1 and bi == n - 1
                 if isinstance(blk, TemporalBottleneck):
-                    x, pooled = blk(x, want_pool=last)
+                    if folds is not None:
+                        x, pooled = blk.forward_infer(x, folds, want_pool=last)
+                    else:
+                        x, pooled = blk(x, want_pool=last)
                 else:
                     raise NotImplementedError("TSN(tam=False) trunk is not part of the ViTTA path")
         if pooled is None:

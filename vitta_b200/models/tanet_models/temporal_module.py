@@ -130,6 +130,26 @@ class TemporalBottleneck(nn.Module):
         self.tam = TAM(in_channels=net.conv1.out_channels, n_segment=n_segment, kernel_size=t_kernel_size,
                        stride=t_stride, padding=t_padding)
 
+    def infer_pairs(self):
+        """(convolution, BatchNorm) pairs of this block in the order the inference forward uses them."""
+        net = self.net
+        pairs = [(net.conv1, net.bn1), (net.conv2, net.bn2), (net.conv3, net.bn3)]
+        if net.downsample is not None:
+            pairs.append((net.downsample[0], net.downsample[1]))
+        return pairs
+
+    def forward_infer(self, x, folds, want_pool=False):
+        """Inference forward with every eval-mode BatchNorm folded into its convolution (K6 epilogue: + bias, + shortcut,
+        ReLU): no norm pass, no statistics, nothing saved for a backward.  Same arithmetic up to the association
+        conv(x, k*W) + b' vs (conv(x, W) - mean) * k + beta."""
+        net = self.net
+        out = ops.conv2d_folded(x, net.conv1, folds, True)
+        out = self.tam(out, ops.frame_mean_cl(out))
+        out = ops.conv2d_folded(out, net.conv2, folds, True)
+        idt = x if net.downsample is None else ops.conv2d_folded(x, net.downsample[0], folds, False)
+        out = ops.conv2d_folded(out, net.conv3, folds, True, residual=idt)
+        return out, (ops.frame_mean_cl(out) if want_pool else None)
+
     def forward(self, x, want_pool=False):
         net, t = self.net, self.n_segment
         out, x = conv2d_shortcut(net.conv1, x)                              # x: alias for the shortcut path

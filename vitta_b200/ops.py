@@ -686,9 +686,9 @@ class TamStencilFn(torch.autograd.Function):
         nch = _lib.load().vitta_tam_num_chunks(h * w, Cc)
         dpart = torch.empty(n, nch, T, 3, Cc, dtype=torch.float32, device=x.device)
         call("vitta_tam_bwd", ptr(gout), ptr(x), ptr(kern), ptr(act), ptr(gx), ptr(dpart), n, T, h * w, Cc, stream_ptr())
-        D = dpart.sum(1)                                   # (N, T, 3, C): tiny
-        gkern = (act.unsqueeze(2) * D).sum(1)              # (N, 3, C)
-        gact = (kern.unsqueeze(1) * D).sum(2)              # (N, T, C)
+        gkern = torch.empty_like(kern)                     # (N, 3, C)
+        gact = torch.empty_like(act)                       # (N, T, C)
+        call("vitta_tam_bwd_finish", ptr(dpart), ptr(kern), ptr(act), ptr(gkern), ptr(gact), n, T, nch, Cc, stream_ptr())
         return gx, gkern, gact, None
 
 
@@ -1400,3 +1400,100 @@ class TamGateFn(torch.autograd.Function):
              ptr(gw1), ptr(gb1[0]), ptr(gb1[1]), ptr(gw2), ptr(gwa), ptr(gb2[0]), ptr(gb2[1]), ptr(gwb), ptr(gz),
              ptr(gpre), ptr(ghm), ptr(ws), n, t, c, stream_ptr())
         return (gp, gw1, gb1[0], gb1[1], None, None, gw2, gwa, gb2[0], gb2[1], None, None, gwb, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# BN-folded inference forward (the per-step clean evaluation, reference corpus/basics.py:691-713)
+# ----------------------------------------------------------------------------------------------
+class FoldedConvs:
+    """Operands of the inference convolutions of one model: for every (convolution, eval-mode BatchNorm) pair the fp16
+    hi/lo pieces of W' = k * W (k = gamma / sqrt(running_var + eps), per output channel) and the bias
+    b' = beta - running_mean * k, so that  BN(conv(x, W)) = conv(x, W') + b'  costs no pass of its own: the GEMM epilogue
+    adds b' (and the shortcut) and applies ReLU.  All layers are refreshed by TWO launches (vitta_split_multi with the
+    fold pointers + vitta_bn_fold_bias_multi) whenever a weight, a BatchNorm parameter or a running statistic changed."""
+
+    def __init__(self, pairs):
+        self.pairs = list(pairs)
+        dev = self.pairs[0][0].weight.device
+        self.slot = {id(conv): i for i, (conv, _) in enumerate(self.pairs)}
+        self.bias = torch.empty(sum(bn.num_features for _, bn in self.pairs), dtype=torch.float32, device=dev)
+        self.ops_, o = [], 0
+        for conv, bn in self.pairs:
+            n = conv.weight.numel()
+            hi = torch.empty(n, dtype=torch.float16, device=dev)
+            self.ops_.append((hi, torch.empty_like(hi), torch.zeros(1, dtype=torch.float32, device=dev),
+                              self.bias[o:o + bn.num_features]))
+            o += bn.num_features
+        self._key = None
+        self._stamp = None
+        self._tables = None
+
+    def _build(self, dev):
+        blk = _lib.load().vitta_split_block_elems()
+        arr = (_lib.VittaSplitTensor * len(self.pairs))()
+        fb = (_lib.VittaFoldBias * len(self.pairs))()
+        starts, b = [], 0
+        for i, ((conv, bn), (hi, lo, am, bias)) in enumerate(zip(self.pairs, self.ops_)):
+            r, t, c, tap_inner = _split_geom(conv.weight)
+            e = arr[i]
+            e.src, e.hi, e.lo, e.amax = conv.weight.data_ptr(), hi.data_ptr(), lo.data_ptr(), am.data_ptr()
+            e.R, e.T, e.Cc, e.mode, e.src_tap_inner, e.compute_amax, e.n = r, t, c, 0, tap_inner, 1, r * t * c
+            e.fold_w, e.fold_rv, e.fold_eps = bn.weight.data_ptr(), bn.running_var.data_ptr(), float(bn.eps)
+            starts.append(b)
+            b += (e.n + blk - 1) // blk
+            f = fb[i]
+            f.w, f.b, f.rm, f.rv = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                    bn.running_var.data_ptr())
+            f.out, f.eps, f.C = bias.data_ptr(), float(bn.eps), bn.num_features
+        host = (pinned_bytes(arr), torch.tensor(starts, dtype=torch.int32).pin_memory(), pinned_bytes(fb))
+        self._tables = (host, tuple(h.to(dev, non_blocking=True) for h in host), len(self.pairs), b)
+
+    def refresh(self):
+        dev = self.bias.device
+        key = tuple((conv.weight.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                     bn.running_var.data_ptr()) for conv, bn in self.pairs)
+        stamp = (_weight_epoch,) + tuple((conv.weight._version, bn.weight._version, bn.bias._version,
+                                          bn.running_mean._version, bn.running_var._version) for conv, bn in self.pairs)
+        if key != self._key:
+            if any(_split_geom(conv.weight) is None for conv, _ in self.pairs):
+                raise _lib.VittaError("FoldedConvs: convolution weights must be contiguous")
+            self._build(dev)
+            self._key, self._stamp = key, None
+        if stamp == self._stamp:
+            return
+        _, (t, starts, fb), n, blocks = self._tables
+        call("vitta_split_multi", ptr(t), ptr(starts), n, blocks, 1, stream_ptr())
+        call("vitta_bn_fold_bias_multi", ptr(fb), n, stream_ptr())
+        self._stamp = stamp
+
+    def get(self, conv):
+        return self.ops_[self.slot[id(conv)]]
+
+
+def conv2d_folded(x, conv, folds, relu, residual=None):
+    """[relu](BN(conv(x)) [+ residual]) as ONE launch; x channels_last, inference only (no autograd)."""
+    _require_cuda(x, "conv2d_folded")
+    if not x.is_contiguous(memory_format=CL):
+        x = x.contiguous(memory_format=CL)
+    hi, lo, am, bias = folds.get(conv)
+    cout, cin, kh, kw = conv.weight.shape
+    stride, pad = conv.stride[0], conv.padding[0]
+    f, _, h, w = x.shape
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    y = torch.empty((f, cout, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
+    if residual is not None and not (residual.shape == y.shape and residual.is_contiguous(memory_format=CL)):
+        raise _lib.VittaError("conv2d_folded: residual must be channels_last with the shape of the result")
+    y_am = new_amax(x.device)
+    call("vitta_conv2d_f16x3_infer", ptr(x), ptr(operand_amax(x)), f, h, w, cin, ptr(hi), ptr(lo), ptr(am), cout, kh, kw,
+         stride, pad, ptr(y), ptr(bias), ptr(residual), 1 if relu else 0, ptr(y_am), stream_ptr())
+    _attach_amax(y, y_am)
+    return y
+
+
+def frame_mean_cl(x):
+    """(F, C, H, W) channels_last -> (F, C) spatial means (vitta_frame_mean), inference helper."""
+    f, c, h, w = x.shape
+    out = torch.empty(f, c, dtype=torch.float32, device=x.device)
+    call("vitta_frame_mean", ptr(x), f, h * w, c, ptr(out), stream_ptr())
+    return out
