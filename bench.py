@@ -87,6 +87,11 @@ def _work(name, a):
         return GEMM_FAM, _conv_flops(*g(1, 2, 3, 4, 7, 8, 9, 10, 11)), 0.0
     if name == "vitta_conv2d_f16x3_ex":
         return GEMM_FAM, _conv_flops(*g(2, 3, 4, 5, 9, 10, 11, 12, 13)), 0.0
+    if name == "vitta_conv2d_f16x3_infer":
+        return "conv + folded BN + ReLU/shortcut (tcgen05, inference)", _conv_flops(*g(2, 3, 4, 5, 9, 10, 11, 12, 13)), 0.0
+    if name == "vitta_frame_mean":
+        frames, rows, c = g(1, 2, 3)
+        return "frame_mean", 0.0, 4.0 * frames * rows * c
     if name == "vitta_conv2d_dgrad_tf32x3":
         f, ho, wo, cout, cin, kh, kw = g(1, 2, 3, 4, 7, 8, 9)
         return GEMM_FAM, 2.0 * f * ho * wo * cout * cin * kh * kw, 0.0
@@ -504,6 +509,12 @@ def run_ours(args):
 
     # the instrumented step contains the step's collectives: every rank has to run it
     fam = attribute_step(adapter, resident)
+
+    def eval_only():
+        adapter.hooks_off()
+        adapter.evaluate(resident)
+        adapter.hooks_on()
+    fam_eval = attribute_step(adapter, resident, step=eval_only)
     barrier()
 
     # ---- secondary workloads (every rank takes part: the Swin-B step is sharded over the ranks) ----
@@ -565,7 +576,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "cuda_graph": bool(targs.cuda_graph), "clocks": sampler.summary(),
             "roofline": roof, "roofline_stats": roof_stats, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
-            "secondary": secondary, "parity_check": parity, "kernels": _table(fam)}
+            "secondary": secondary, "parity_check": parity, "kernels": _table(fam), "kernels_eval_forward": _table(fam_eval)}
     print(json.dumps(line))
     if world > 1:
         _hard_exit()

@@ -27,3 +27,10 @@ for f in sys.argv[1:]:
         tot += v["ms"]
         print("   ", k, v)
     print("   sum of our kernels %.2f ms of %.2f" % (tot, d["ms_per_step"]))
+    if d.get("kernels_eval_forward"):
+        print("   -- evaluation forward:")
+        tot = 0.0
+        for k, v in d["kernels_eval_forward"].items():
+            tot += v["ms"]
+            print("    ", k, v)
+        print("     sum %.2f ms" % tot)

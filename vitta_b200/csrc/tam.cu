@@ -148,20 +148,22 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
 
 // After tam_bwd_kernel: D[n, t, k, c] = sum over the row chunks of dpart (fixed order), then
 //   gkern[n, k, c] = sum_t act[n, t, c] * D[n, t, k, c]        gact[n, t, c] = sum_k kern[n, k, c] * D[n, t, k, c]
-// (three eager reductions / products per TAM before).  Thread = (video, 4 channels).
-__global__ void __launch_bounds__(128) tam_bwd_finish_kernel(const float* __restrict__ dpart,
+// (three eager reductions / products per TAM before).  CTA = (video, tile of <= 32 channel quads) x T frames: thread
+// (t, quad) sums its chunks four at a time, writes gact and leaves act * D in shared memory; the threads of frame 0 add
+// those over t in frame order.
+constexpr int kTamFinMaxT = 16;
+
+__global__ void __launch_bounds__(512) tam_bwd_finish_kernel(const float* __restrict__ dpart,
                                                             const float* __restrict__ kern,
                                                             const float* __restrict__ act, float* __restrict__ gkern,
                                                             float* __restrict__ gact, int N, int T, int nch, int C4) {
-  const int idx = blockIdx.x * 128 + threadIdx.x;
-  if (idx >= N * C4) return;
-  const int n = idx / C4, c = (idx % C4) * 4;
-  const int C = C4 * 4;
-  const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c), k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c),
-               k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
-  float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
-  for (int t = 0; t < T; ++t) {
-    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+  __shared__ float4 sg[3][kTamFinMaxT][32];
+  const int lane = threadIdx.x, t = threadIdx.y;
+  const int n = blockIdx.x, c4 = blockIdx.y * 32 + lane;
+  const int C = C4 * 4, c = c4 * 4;
+  const bool on = c4 < C4;
+  float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+  if (on) {
     for (int ch0 = 0; ch0 < nch; ch0 += 4) {
       float4 v[4][3];
 #pragma unroll
@@ -178,16 +180,26 @@ __global__ void __launch_bounds__(128) tam_bwd_finish_kernel(const float* __rest
         d2.x += v[u][2].x; d2.y += v[u][2].y; d2.z += v[u][2].z; d2.w += v[u][2].w;
       }
     }
-    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
-    g0 = fma4(a, d0, g0); g1 = fma4(a, d1, g1); g2 = fma4(a, d2, g2);
+    const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c), k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c),
+                 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
     float4 ga = mul4(k0, d0);
     ga = fma4(k1, d1, ga);
     ga = fma4(k2, d2, ga);
     st4(gact + ((int64_t)n * T + t) * C + c, ga);
+    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
+    sg[0][t][lane] = mul4(a, d0);
+    sg[1][t][lane] = mul4(a, d1);
+    sg[2][t][lane] = mul4(a, d2);
   }
-  st4(gkern + ((int64_t)n * 3 + 0) * C + c, g0);
-  st4(gkern + ((int64_t)n * 3 + 1) * C + c, g1);
-  st4(gkern + ((int64_t)n * 3 + 2) * C + c, g2);
+  __syncthreads();
+  if (on && t < 3) {      // frame-threads 0..2 each own one tap k = t
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tt = 0; tt < T; ++tt) {
+      const float4 v = sg[t][tt][lane];
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    st4(gkern + ((int64_t)n * 3 + t) * C + c, g);
+  }
 }
 
 }  // namespace vitta
@@ -253,9 +265,10 @@ int vitta_tam_bwd_finish(const float* dpart, const float* kern, const float* act
   VITTA_CHECK_ARG(N > 0 && T > 0 && nch > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_bwd_finish: bad shape");
   VITTA_CHECK_ARG(aligned16(dpart) && aligned16(kern) && aligned16(act) && aligned16(gkern) && aligned16(gact), VITTA_E_ALIGN,
                   "tam_bwd_finish: tensors must be 16-byte aligned");
-  const int total = N * (C / 4);
-  tam_bwd_finish_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dpart, kern, act, gkern, gact,
-                                                                                       N, T, nch, C / 4);
+  VITTA_CHECK_ARG(T >= 3 && T <= kTamFinMaxT, VITTA_E_UNSUPPORTED, "tam_bwd_finish: 3 <= T <= 16");
+  const int C4 = C / 4;
+  dim3 block(32, (unsigned)T), grid((unsigned)N, (unsigned)((C4 + 31) / 32));
+  tam_bwd_finish_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dpart, kern, act, gkern, gact, N, T, nch, C4);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

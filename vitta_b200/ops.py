@@ -686,9 +686,15 @@ class TamStencilFn(torch.autograd.Function):
         nch = _lib.load().vitta_tam_num_chunks(h * w, Cc)
         dpart = torch.empty(n, nch, T, 3, Cc, dtype=torch.float32, device=x.device)
         call("vitta_tam_bwd", ptr(gout), ptr(x), ptr(kern), ptr(act), ptr(gx), ptr(dpart), n, T, h * w, Cc, stream_ptr())
-        gkern = torch.empty_like(kern)                     # (N, 3, C)
-        gact = torch.empty_like(act)                       # (N, T, C)
-        call("vitta_tam_bwd_finish", ptr(dpart), ptr(kern), ptr(act), ptr(gkern), ptr(gact), n, T, nch, Cc, stream_ptr())
+        if 3 <= T <= 16:
+            gkern = torch.empty_like(kern)                 # (N, 3, C)
+            gact = torch.empty_like(act)                   # (N, T, C)
+            call("vitta_tam_bwd_finish", ptr(dpart), ptr(kern), ptr(act), ptr(gkern), ptr(gact), n, T, nch, Cc,
+                 stream_ptr())
+        else:
+            D = dpart.sum(1)                               # (N, T, 3, C): tiny
+            gkern = (act.unsqueeze(2) * D).sum(1)
+            gact = (kern.unsqueeze(1) * D).sum(2)
         return gx, gkern, gact, None
 
 
