@@ -168,7 +168,12 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         if use_graph:
             assert ad._graph is not None, "the step was never captured"
         ad.hooks_off()
-        ev = ad.evaluate(x).cpu()
+        ev = ad.evaluate(x).clone().cpu()
+        if use_graph:      # the evaluation forward: eager pass, capture + first replay, replay -- all the same logits
+            for _ in range(2):
+                ev2 = ad.evaluate(x).clone().cpu()
+                torch.testing.assert_close(ev2, ev, rtol=1e-6, atol=1e-8)
+            assert getattr(ad, "_eval_graph", None) is not None, "the evaluation forward was never captured"
         outs.append((rec, ev, ad.model.new_fc.weight.detach().cpu().clone(),
                      ad.model.base_model.layer3[2].net.conv2.weight.detach().cpu().clone()))
     (re, eve, w1e, w2e), (rg, evg, w1g, w2g) = outs
