@@ -470,25 +470,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S::kAccCols);
-      // The residual (shortcut / shortcut gradient) of a chunk is fetched one chunk AHEAD: a load issued where it is
-      // used costs a full memory round trip per 32-byte sector and thread (4 per chunk, 8 chunks per 256-wide tile =
-      // ~16 us per tile against 1-3 us of MMA time -- profiles/r02: the BN-folded conv3 + shortcut layers ran at half the
-      // speed of the plain convolutions).
-      const bool res_fast = rrow != nullptr && row_ok && p.vec_ok == 2;
-      float4 rq[8];
-      if (res_fast && n0 + 32 <= p.N) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) ld8(rrow + n0 + u * 8, rq[2 * u], rq[2 * u + 1]);
-      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
-        float4 rn[8];
-        if (res_fast && c0 + 32 < BN && n0 + c0 + 64 <= p.N) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) ld8(rrow + n0 + c0 + 32 + u * 8, rn[2 * u], rn[2 * u + 1]);
-        }
         tmem_ld_wait();
 #pragma unroll
         for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
@@ -523,7 +508,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v1.x = gelu_exact(v1.x); v1.y = gelu_exact(v1.y); v1.z = gelu_exact(v1.z); v1.w = gelu_exact(v1.w);
               }
               if (rrow) {
-                const float4 r0 = rq[j / 4], r1 = rq[j / 4 + 1];    // prefetched (res_fast holds on this path)
+                float4 r0, r1;
+                ld8(rrow + nbase + j, r0, r1);
                 if (p.act == 2) {
                   v0.x *= gelu_grad(r0.x) * rscale; v0.y *= gelu_grad(r0.y) * rscale;
                   v0.z *= gelu_grad(r0.z) * rscale; v0.w *= gelu_grad(r0.w) * rscale;
@@ -594,8 +580,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) rq[u] = rn[u];
       }
       tc_fence_before();
       __syncwarp();

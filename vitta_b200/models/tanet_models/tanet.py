@@ -47,13 +47,16 @@ class ResNet50Trunk(nn.Module):
         return nn.Sequential(*blks)
 
     def _inference_folds(self, x):
-        """The BN-folded operand set when this forward may use it: no autograd (the per-step evaluation / source-only
+        """OPT-IN (VITTA_INFER_FOLD=1; measured on the B200 the folded forward is still 1.2 ms SLOWER than the layer-by-layer
+        one at the benchmark shape, 10.2 vs 9.0 ms: the bias / ReLU / range work it adds to the GEMM epilogue sits on the
+        critical path of the store-bound layer1 / layer2 convolutions -- DESIGN.md section 9).
+        The BN-folded operand set when this forward may use it: no autograd (the per-step evaluation / source-only
         validation), the fp16 operand split, every BatchNorm2d of the residual stages in eval mode without statistics
         taps or foreign hooks, and plain bias-free convolutions.  None otherwise (the layer-by-layer path runs)."""
         from ... import ops
         from ...nn import _fusable
         if torch.is_grad_enabled() or not x.is_cuda or ops.gemm_precision() != "f16x3" or \
-                os.environ.get("VITTA_INFER_FOLD", "1") != "1":
+                os.environ.get("VITTA_INFER_FOLD", "0") != "1":
             return None
         blocks = [b for st in (self.layer1, self.layer2, self.layer3, self.layer4) for b in st]
         if not all(isinstance(b, TemporalBottleneck) for b in blocks):
