@@ -114,6 +114,10 @@ def eval(args=None, model=None):
         logger.debug('SYNTHETIC RUN, stand-ins for: ' + '; '.join(args.synthetic_stand_ins))
     _maybe_init_distributed(args)
     if model is None:
+        if not getattr(args, 'model_path', None):
+            # synthetic stand-in for the checkpoint: the SAME seeded initialisation in every process and run (under
+            # torchrun all ranks must start from identical weights, as they would after loading one checkpoint)
+            torch.manual_seed(int(getattr(args, 'synthetic_seed', 0)))
         model = get_model(args, num_classes, logger)
         if getattr(args, 'model_path', None):
             model = load_checkpoint_into(model, args, logger)
