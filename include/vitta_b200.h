@@ -287,6 +287,11 @@ int vitta_bn_fold_bias_multi(const VittaFoldBias* table, int n, void* stream);
 int vitta_conv2d_f16x3_infer(const float* X, const float* x_amax, int F, int H, int W, int Cin, const void* Whi,
                              const void* Wlo, const float* w_amax, int Cout, int KH, int KW, int stride, int pad,
                              float* Y, const float* bias, const float* residual, int relu, float* y_amax, void* stream);
+/* vitta_gemm_f16x3_ex + max|C| accumulated into *c_amax (zeroed by the caller): the range of the next fp16-split GEMM. */
+int vitta_gemm_f16x3_amax(const float* A, int64_t lda, const float* a_amax, const void* Bhi, const void* Blo,
+                          const float* b_amax, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
+                          const float* bias, const float* residual, int64_t ldr, int act, float* aux_out,
+                          const float* row_scale, int64_t rows_per_group, float* c_amax, void* stream);
 int vitta_split_block_elems(void);
 int vitta_split_multi(const VittaSplitTensor* tensors, const int32_t* block_start, int n_tensors, int total_blocks,
                       int f16, void* stream);
@@ -422,6 +427,14 @@ int vitta_ln_bwd(const float* gy, const float* x, const float* gamma, const floa
                  const float* rstd, const float* gadd, const float* coef_a, const float* coef_b, const float* coef_mean,
                  const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws, int64_t rows, int C,
                  const VittaLnGather* gather, void* stream);
+/* The same two entry points with max|y| / max|gx| accumulated into a zero-initialised device scalar (null: off): the
+ * operand range of the fp16-split GEMMs that consume the LayerNorm output / the residual-stream gradient. */
+int vitta_ln_fwd_amax(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
+                      float* part, int64_t rows, int C, const VittaLnGather* gather, float* y_amax, void* stream);
+int vitta_ln_bwd_amax(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, const float* gadd, const float* coef_a, const float* coef_b,
+                      const float* coef_mean, const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws,
+                      int64_t rows, int C, const VittaLnGather* gather, float* gx_amax, void* stream);
 
 /* Small token-matrix helpers of the Swin path.
  *   vitta_colsum:      out[c] (+)= sum_r x[r, c]   (bias gradients of nn.Linear; deterministic two-stage sum;
@@ -439,6 +452,9 @@ int vitta_patchify3d(const float* video, int B, int T, int H, int W, int pt, int
  * weight-gradient GEMM (timm DropPath, call site swin_transformer.py:210). */
 int vitta_row_scale(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
                     void* stream);
+/* ... with max|out| accumulated into a zero-initialised device scalar (null: off) */
+int vitta_row_scale_amax(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
+                         float* out_amax, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K7  Video-Swin 3-D (shifted-)window multi-head self-attention, head_dim 32.
@@ -466,6 +482,14 @@ int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads);
 int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
                      float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
                      const int* window_host, const int* shift_host, float scale, int impl, void* stream);
+/* The attention entry points with max|out| / max|dqkv| accumulated into a zero-initialised device scalar (null: off). */
+int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
+                          void* stream);
+int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
+                          const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,
+                          int heads, int head_dim, const int* window, const int* shift, float scale, int impl,
+                          float* dqkv_amax, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * View gathering + normalisation (the step before the hot path).

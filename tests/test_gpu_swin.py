@@ -371,3 +371,42 @@ def test_swin_state_dict_keys_match_reference_layout():
     from oracle import vitta_oracle as O
     ln_names = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.LayerNorm)]
     assert ln_names == O.swin_norm_layers()
+
+
+def test_producers_emit_the_operand_range_of_their_outputs(cuda_device):
+    """Under the fp16 operand split every producer of a GEMM operand on the Swin path (LayerNorm forward / backward,
+    DropPath row scaling, the fc1 / GELU' GEMM epilogues, window attention forward / backward) emits max|output| into a
+    pooled device scalar attached to the output tensor: it must equal the true maximum (it is an exact max of the stored
+    fp32 values), so no consumer ever needs the standalone vitta_amax_f32 pass."""
+    from vitta_b200 import ops, ops_swin
+    before = ops.gemm_precision()
+    ops.set_gemm_precision("f16x3")
+    try:
+        ops.reset_amax_pool()
+
+        def check(t, what):
+            ent = getattr(t, "_vitta_amax", None)
+            assert ent is not None, what + ": no range attached"
+            assert float(ent[0]) == float(t.abs().max()), (what, float(ent[0]), float(t.abs().max()))
+        rows, c = 1500, 96
+        x = _rnd(rows, c, seed=1, scale=1.7) + 0.3
+        w, b = _rnd(c, seed=2) * 0.2 + 1.0, _rnd(c, seed=3) * 0.1
+        y, mean, rstd = ops_swin.ln_fwd(x, w, b, 1e-5, rows, c)
+        check(y, "ln_fwd")
+        gx, _, _ = ops_swin.ln_bwd(_rnd(rows, c, seed=4) * 1e-6, x, w, b, mean, rstd, rows, c, gadd=_rnd(rows, c, seed=5) * 1e-6)
+        check(gx, "ln_bwd")
+        sc = torch.tensor([0.0, 1.25, 1.25], device=cuda_device)
+        check(ops_swin.row_scale(x, sc, rows // 3), "row_scale")
+        w1 = torch.nn.Parameter(_rnd(4 * c, c, seed=6) * 0.1)
+        pre = torch.empty(rows, 4 * c, device=cuda_device)
+        act = ops_swin.gemm(y, w1, 0, bias=_rnd(4 * c, seed=7) * 0.1, act=1, aux_out=pre, want_amax=True)
+        check(act, "gemm epilogue (GELU)")
+        heads, dims, window = 3, (1, 4, 7, 7), (4, 7, 7)
+        qkv = _rnd(4 * 7 * 7, 3 * heads * 32, seed=8)
+        table = _rnd((2 * 4 - 1) * 13 * 13, heads, seed=9) * 0.2
+        out, lse = ops_swin.wmsa3d_fwd(qkv, table, dims, heads, window, (0, 0, 0), 32 ** -0.5)
+        check(out, "wmsa3d_fwd")
+        dqkv, _ = ops_swin.wmsa3d_bwd(qkv, table, out, _rnd(*out.shape, seed=10), lse, dims, heads, window, (0, 0, 0), 32 ** -0.5)
+        check(dqkv, "wmsa3d_bwd")
+    finally:
+        ops.set_gemm_precision(before)

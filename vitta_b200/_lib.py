@@ -101,6 +101,9 @@ _SIGNATURES = {
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_ln_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(VittaChunking)]),
     "vitta_ln_fwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P]),
+    "vitta_ln_fwd_amax": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P,
+                                    _P]),
+    "vitta_ln_bwd_amax": (C.c_int, [_P] * 15 + [C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P, _P]),
     "vitta_ln_bwd_ws_floats": (C.c_int64, [C.c_int64, C.c_int]),
     "vitta_ln_bwd": (C.c_int, [_P] * 15 + [C.c_int64, C.c_int, C.POINTER(VittaLnGather), _P]),
     "vitta_colsum_ws_floats": (C.c_int64, [C.c_int64, C.c_int]),
@@ -109,8 +112,13 @@ _SIGNATURES = {
     "vitta_frame_mean_bwd": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "vitta_patchify3d": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_row_scale": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "vitta_row_scale_amax": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
     "vitta_wmsa3d_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P]),
+    "vitta_wmsa3d_fwd_amax": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P, _P]),
+    "vitta_wmsa3d_bwd_amax": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P, _P]),
     "vitta_wmsa3d_bwd_ws_floats": (C.c_int64, [C.c_int] * 5),
     "vitta_wmsa3d_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P]),
@@ -140,6 +148,8 @@ _SIGNATURES = {
     "vitta_bn_fold_bias_multi": (C.c_int, [_P, C.c_int, _P]),
     "vitta_conv2d_f16x3_infer": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "vitta_gemm_f16x3_amax": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                        _P, _P, C.c_int64, C.c_int, _P, _P, C.c_int64, _P, _P]),
     "vitta_split_block_elems": (C.c_int, []),
     "vitta_split_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_sgd_block_elems": (C.c_int, []),

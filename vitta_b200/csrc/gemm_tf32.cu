@@ -1032,7 +1032,7 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
 static int gemm_impl(const float* A, int64_t lda, const void* Bhi, const void* Blo, int64_t ldb, float* C,
                      int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
                      int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,
-                     void* stream, const float* a_amax, const float* b_amax) {
+                     void* stream, const float* a_amax, const float* b_amax, float* c_amax = nullptr) {
   const bool f16 = a_amax != nullptr;
   const int stage_k = f16 ? 2 * kBK : kBK;
   VITTA_CHECK_ARG(A && Bhi && Blo && C && M > 0 && N > 0 && K > 0, VITTA_E_BADARG, "gemm_tf32x3: bad arguments");
@@ -1059,7 +1059,7 @@ static int gemm_impl(const float* A, int64_t lda, const void* Bhi, const void* B
   int rc = make_b_maps(&tbh, &tbl, Bhi, Blo, ldb, N, K, bn, f16, force_bn);
   if (rc) return rc;
   GemmParams p{};
-  p.a_amax = a_amax; p.b_amax = b_amax;
+  p.a_amax = a_amax; p.b_amax = b_amax; p.amax_out = c_amax;
   p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
   p.M_total = (int)M; p.N = N; p.Kc = K; p.k_chunks = (K + stage_k - 1) / stage_k;
   p.taps_h = p.taps_w = 1; p.stride = 1; p.pad = 0;
@@ -1366,6 +1366,17 @@ int vitta_bn_fold_bias_multi(const VittaFoldBias* table, int n, void* stream) {
   bn_fold_bias_multi_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const FoldBiasEntry*>(table));
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+// vitta_gemm_f16x3_ex that also accumulates max|C| into *c_amax (zero-initialised by the caller): the operand range of
+// the fp16-split GEMM that consumes C (fc1 -> GELU -> fc2, and the GELU' data gradient -> fc1's gradients), for free.
+int vitta_gemm_f16x3_amax(const float* A, int64_t lda, const float* a_amax, const void* Bhi, const void* Blo,
+                          const float* b_amax, int64_t ldb, float* C, int64_t ldc, int64_t M, int N, int K,
+                          const float* bias, const float* residual, int64_t ldr, int act, float* aux_out,
+                          const float* row_scale, int64_t rows_per_group, float* c_amax, void* stream) {
+  VITTA_CHECK_ARG(a_amax && b_amax && c_amax, VITTA_E_BADARG, "gemm_f16x3_amax: amax scalars are required");
+  return gemm_impl(A, lda, Bhi, Blo, ldb, C, ldc, M, N, K, bias, residual, ldr, act, aux_out, row_scale, rows_per_group, 0,
+                   stream, a_amax, b_amax, c_amax);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ struct LnFwdArgs {
   int rows_per_warp;
   float eps;
   LnGather g;
+  float* amax_y;   // optional: max|y| accumulated here (operand range of the fp16-split GEMM that consumes y)
 };
 
 __device__ __forceinline__ const float* ln_src_row(const float* x, int64_t r, int C, const LnGather& g, int64_t& base,
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
     for (int j = 0; j < VPL; ++j) wm[j] = w2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float nrow = 0.f;
+  float am = 0.f;
   for (int64_t r = r0; r < r1; ++r) {
     int64_t base;
     int h0 = 0, w0 = 0;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
         y.z = fmaf((v[j].z - mu) * rs, ga.z, be.z);
         y.w = fmaf((v[j].w - mu) * rs, ga.w, be.w);
         st4(p.y + r * p.C + (int64_t)i * 4, y);
+        am = fmaxf(am, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
         if (STATS) {
           float d;
           d = y.x - wm[j].x; wm[j].x = fmaf(d, inv_n, wm[j].x); w2[j].x = fmaf(d, y.x - wm[j].x, w2[j].x);
@@ -135,6 +138,10 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
         }
       }
     }
+  }
+  if (p.amax_y) {   // one integer atomic per warp (non-negative floats order like their bit patterns)
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_y), wmax);
   }
   if (STATS) {
     float* o = p.part + chunk * p.C * 2;
@@ -168,6 +175,7 @@ struct LnBwdArgs {
   int64_t rows;
   int C;
   LnGather g;
+  float* amax_gx;   // optional: max|gx| (plain mode), the range of the GEMMs that take gx as their gradient operand
 };
 
 template <int VPL>
@@ -195,6 +203,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
   float4 dg[VPL], db[VPL];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float am = 0.f;
 
   for (int64_t r = (int64_t)blockIdx.x * kLnWarps + warp; r < p.rows; r += (int64_t)gridDim.x * kLnWarps) {
     int64_t base;
@@ -249,11 +258,16 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
             o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
           }
           st4(p.gx + r * p.C + (int64_t)i * 4, o);
+          am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
         } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
           st4(p.gx + base + goff[j], o);
         }
       }
     }
+  }
+  if (p.amax_gx) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_gx), wmax);
   }
   // CTA reduction of d(gamma), d(beta): warps add in turn (fixed order), then one partial per CTA
   for (int w = 0; w < kLnWarps; ++w) {
@@ -405,11 +419,19 @@ __global__ void __launch_bounds__(256) frame_mean_bwd_kernel(const float* __rest
 
 // out[r, :] = x[r, :] * scale[r / rows_per_group]   (DropPath applied to a gradient before the weight-gradient GEMM)
 __global__ void __launch_bounds__(256) row_scale_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                       float* __restrict__ out, int64_t n4, int C4, int64_t rpg) {
+                                                       float* __restrict__ out, int64_t n4, int C4, int64_t rpg,
+                                                       float* __restrict__ amax_out) {
+  float am = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
     const float s = __ldg(scale + (i / C4) / rpg);
     const float4 v = ld_stream4(x + i * 4);
-    st4(out + i * 4, make_float4(v.x * s, v.y * s, v.z * s, v.w * s));
+    const float4 o = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+    st4(out + i * 4, o);
+    am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+  }
+  if (amax_out) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if ((threadIdx.x & 31) == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(amax_out), wmax);
   }
 }
 
@@ -470,6 +492,11 @@ static int ln_check_gather(const VittaLnGather* g, int C, int64_t rows, LnGather
 
 int vitta_ln_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
                  float* part, int64_t rows, int C, const VittaLnGather* gather, void* stream) {
+  return vitta_ln_fwd_amax(x, gamma, beta, eps, y, mean, rstd, part, rows, C, gather, nullptr, stream);
+}
+
+int vitta_ln_fwd_amax(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean, float* rstd,
+                      float* part, int64_t rows, int C, const VittaLnGather* gather, float* y_amax, void* stream) {
   VITTA_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows > 0, VITTA_E_BADARG, "ln_fwd: null pointer");
   VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 2048, VITTA_E_UNSUPPORTED, "ln_fwd: C must be a multiple of 4, <= 2048");
   VITTA_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!part || aligned16(part)),
@@ -480,7 +507,7 @@ int vitta_ln_fwd(const float* x, const float* gamma, const float* beta, float ep
   VittaChunking ch;
   rc = vitta_ln_chunking(rows, C, part != nullptr, &ch);
   if (rc) return rc;
-  p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.part = part;
+  p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.part = part; p.amax_y = y_amax;
   p.rows = rows; p.C = C; p.rows_per_warp = ch.chunk_rows; p.eps = eps;
   const unsigned grid = (unsigned)((ch.n_entries + kLnWarps - 1) / kLnWarps);
   cudaStream_t st = (cudaStream_t)stream;
@@ -509,6 +536,14 @@ int vitta_ln_bwd(const float* gy, const float* x, const float* gamma, const floa
                  const float* rstd, const float* gadd, const float* coef_a, const float* coef_b, const float* coef_mean,
                  const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws, int64_t rows, int C,
                  const VittaLnGather* gather, void* stream) {
+  return vitta_ln_bwd_amax(gy, x, gamma, beta, mean, rstd, gadd, coef_a, coef_b, coef_mean, gscale, gx, dgamma, dbeta, ws,
+                           rows, C, gather, nullptr, stream);
+}
+
+int vitta_ln_bwd_amax(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, const float* gadd, const float* coef_a, const float* coef_b,
+                      const float* coef_mean, const float* gscale, float* gx, float* dgamma, float* dbeta, float* ws,
+                      int64_t rows, int C, const VittaLnGather* gather, float* gx_amax, void* stream) {
   VITTA_CHECK_ARG(gy && x && gamma && beta && mean && rstd && gx && ws && rows > 0, VITTA_E_BADARG, "ln_bwd: null pointer");
   VITTA_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 2048, VITTA_E_UNSUPPORTED, "ln_bwd: C must be a multiple of 4, <= 2048");
   VITTA_CHECK_ARG((coef_a == nullptr) == (coef_b == nullptr) && (coef_a == nullptr) == (coef_mean == nullptr) &&
@@ -523,6 +558,7 @@ int vitta_ln_bwd(const float* gy, const float* x, const float* gamma, const floa
   p.gy = gy; p.x = x; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.gadd = gadd;
   p.ca = coef_a; p.cb = coef_b; p.cm = coef_mean; p.gs = gscale;
   p.gx = gx; p.dgamma = dgamma; p.dbeta = dbeta; p.ws = ws; p.rows = rows; p.C = C;
+  p.amax_gx = p.g.merge ? nullptr : gx_amax;
   cudaStream_t st = (cudaStream_t)stream;
   if (p.g.merge && ((p.g.H & 1) || (p.g.W & 1))) {
     // odd extents: every source element is still written exactly once (the padded ones do not exist)
@@ -580,12 +616,17 @@ int vitta_frame_mean_bwd(const float* g, int64_t frames, int rows, int C, float*
 
 int vitta_row_scale(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
                     void* stream) {
+  return vitta_row_scale_amax(x, scale, rows, rows_per_group, C, out, nullptr, stream);
+}
+
+int vitta_row_scale_amax(const float* x, const float* scale, int64_t rows, int64_t rows_per_group, int C, float* out,
+                         float* out_amax, void* stream) {
   VITTA_CHECK_ARG(x && scale && out && rows > 0 && rows_per_group > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG,
                   "row_scale: bad arguments");
   const int64_t n4 = rows * (C / 4);
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  row_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, scale, out, n4, C / 4, rows_per_group);
+  row_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, scale, out, n4, C / 4, rows_per_group, out_amax);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

@@ -114,6 +114,7 @@ struct WmsaFwdParams {
   float scale;
   int items, items_per_cta;
   WmsaGeom g;
+  float* amax_out;      // optional: max|out| (range of the fp16-split proj GEMM and its weight gradient)
 };
 
 enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages,
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kMask2 = -100.f * kLog2e;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    float out_amax = 0.f;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
@@ -443,12 +445,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
           const float inv = 1.f / l;
           float* dst = p.out + (int64_t)my_tok * C + head * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            st4(dst + q * 4, make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
-                                         __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv));
+          for (int q = 0; q < 8; ++q) {
+            const float4 ov = make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
+                                          __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv);
+            st4(dst + q * 4, ov);
+            out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(ov.x), fabsf(ov.y)), fmaxf(fabsf(ov.z), fabsf(ov.w))));
+          }
           p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2 + log2f(l)) * 0.6931471805599453f;
         }
       }
+    }
+    if (p.amax_out) {   // one integer atomic per softmax warp (non-negative floats order like their bit patterns)
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
+      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
     }
   }
 
@@ -693,6 +702,7 @@ struct WmsaBwd2Params {
   float scale;
   int items, items_per_cta;
   WmsaGeom g;
+  float* amax_out;      // optional: max|dqkv| over both launches (range of the qkv data / weight gradient GEMMs)
 };
 
 // dsum[token, head] = sum_d dout[token, head*32 + d] * out[token, head*32 + d]; one 8-lane group per (token, head)
@@ -1045,6 +1055,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
     const float* __restrict__ tab2 = tab;                        // bias table, pre-multiplied by log2(e) by the loaders
     float* __restrict__ mytab = dtab + warp * kAtMaxRel;         // this warp's private table gradient (no atomics)
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    float out_amax = 0.f;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       mbar_wait(&bar[C_ITEM_READY], it & 1);
@@ -1147,6 +1158,11 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[C_ACC_FREE]);
         if (valid) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            out_amax = fmaxf(out_amax, fabsf(__uint_as_float(a1[q])) * (MODE == 0 ? fabsf(p.scale) : 1.f));
+            if (MODE == 1) out_amax = fmaxf(out_amax, fabsf(__uint_as_float(a2[q])));
+          }
           if (MODE == 0) {
             float* dst = p.dqkv + (int64_t)my_tok * 3 * C + head * 32 + half * 16;
 #pragma unroll
@@ -1167,6 +1183,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[C_ITEM_FREE]);   // tab / dtab / info / tok / lse of this item no longer needed
+    }
+    if (p.amax_out) {
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
+      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
     }
   }
 
@@ -1215,13 +1235,19 @@ extern "C" {
 
 int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
                      int heads, int head_dim, const int* window, const int* shift, float scale, void* stream) {
+  return vitta_wmsa3d_fwd_amax(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr, stream);
+}
+
+int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
+                          void* stream) {
   VITTA_CHECK_ARG(qkv && bias_table && out && lse, VITTA_E_BADARG, "wmsa3d_fwd: null pointer");
   VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
   VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out), VITTA_E_ALIGN, "wmsa3d_fwd: tensors must be 16-byte aligned");
   WmsaFwdParams p;
   int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
   if (rc) return rc;
-  p.qkv = qkv; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale;
+  p.qkv = qkv; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale; p.amax_out = out_amax;
   p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1275,6 +1301,15 @@ int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads) {
 int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
                      float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
                      const int* window, const int* shift, float scale, int impl, void* stream) {
+  return vitta_wmsa3d_bwd_amax(qkv, bias_table, out, dout, lse, dqkv, dbias_table, ws, B, D, H, W, heads, head_dim, window,
+                               shift, scale, impl, nullptr, stream);
+}
+
+int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
+                          const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,
+                          int heads, int head_dim, const int* window, const int* shift, float scale, int impl,
+                          float* dqkv_amax, void* stream) {
+  VITTA_CHECK_ARG(!(impl == 1 && dqkv_amax), VITTA_E_UNSUPPORTED, "wmsa3d_bwd: the fp32 cross-check kernel emits no range");
   VITTA_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, VITTA_E_BADARG, "wmsa3d_bwd: null pointer");
   VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
   VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), VITTA_E_ALIGN,
@@ -1295,7 +1330,7 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
   WmsaBwd2Params p;
   p.g = g;
   p.qkv = qkv; p.table = bias_table; p.dout = dout; p.lse = lse; p.dsum = ws; p.dqkv = dqkv; p.dtable = dbias_table;
-  p.scale = scale;
+  p.scale = scale; p.amax_out = dqkv_amax;
   p.items = B * g.nw0 * g.nw1 * g.nw2 * heads;
   static bool attr_done = false;
   if (!attr_done) {

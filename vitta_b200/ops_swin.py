@@ -35,7 +35,8 @@ def _workspace(kind, n, dev, zero):
 # ----------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # ----------------------------------------------------------------------------------------------
-def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=None, rows_per_group=1, out=None):
+def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=None, rows_per_group=1, out=None,
+         want_amax=False):
     """out[M, N] = a[M, K] @ op(w)  with the fused epilogue of vitta_gemm_tf32x3_ex.
     mode 0: w is (N, K) (forward of nn.Linear);  mode 1: w is (K, N) and its transpose is used (data gradient)."""
     m, k = a.shape
@@ -46,6 +47,14 @@ def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=No
     if ops.gemm_precision() == "f16x3" and k % 8 == 0 and a.is_contiguous():
         # opt-in fp16 operand split; the amax of the activation operand is a separate pass for now
         hi, lo, wam = ops.weight_split_f16(w, mode)
+        if want_amax:
+            # the result feeds another fp16-split GEMM: its range comes out of this epilogue instead of an extra pass
+            am = ops.new_amax(a.device)
+            call("vitta_gemm_f16x3_amax", ptr(a), a.stride(0), ptr(ops.operand_amax(a)), ptr(hi), ptr(lo), ptr(wam), k,
+                 ptr(out), out.stride(0), m, n, k, ptr(bias), ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale),
+                 int(rows_per_group), ptr(am), stream_ptr())
+            ops._attach_amax(out, am)
+            return out
         call("vitta_gemm_f16x3_ex", ptr(a), a.stride(0), ptr(ops.operand_amax(a)), ptr(hi), ptr(lo), ptr(wam), k, ptr(out),
              out.stride(0), m, n, k, ptr(bias), ptr(residual), ldr, int(act), ptr(aux_out), ptr(row_scale),
              int(rows_per_group), 0, stream_ptr())
@@ -85,6 +94,12 @@ def colsum(g):
 
 def row_scale(x, scale, rows_per_group):
     out = torch.empty_like(x)
+    if ops.gemm_precision() == "f16x3":       # the scaled gradient is a GEMM operand: range for free
+        am = ops.new_amax(x.device)
+        call("vitta_row_scale_amax", ptr(x), ptr(scale), x.shape[0], int(rows_per_group), x.shape[1], ptr(out), ptr(am),
+             stream_ptr())
+        ops._attach_amax(out, am)
+        return out
     call("vitta_row_scale", ptr(x), ptr(scale), x.shape[0], int(rows_per_group), x.shape[1], ptr(out), stream_ptr())
     return out
 
@@ -101,6 +116,13 @@ def ln_fwd(x, weight, bias, eps, rows, c, part=None, gather=None):
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     keep, gp = _gather_struct(gather)
+    if ops.gemm_precision() == "f16x3":
+        # y feeds fp16-split GEMMs (qkv / fc1 / reduction): its range comes out of this pass
+        am = ops.new_amax(x.device)
+        call("vitta_ln_fwd_amax", ptr(x), ptr(weight), ptr(bias), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(part), rows,
+             c, gp, ptr(am), stream_ptr())
+        ops._attach_amax(y, am)
+        return y, mean, rstd
     call("vitta_ln_fwd", ptr(x), ptr(weight), ptr(bias), float(eps), ptr(y), ptr(mean), ptr(rstd), ptr(part), rows, c, gp,
          stream_ptr())
     return y, mean, rstd
@@ -118,6 +140,13 @@ def ln_bwd(gy, x, weight, bias, mean, rstd, rows, c, gadd=None, coef=None, gscal
         ca, cb, cm = coef
         gs = ptr(gscale)
     keep, gp = _gather_struct(gather)
+    if ops.gemm_precision() == "f16x3" and gather is None:
+        # gx is the residual-stream gradient the previous half-block's GEMMs (proj / fc2 data and weight gradients) take
+        am = ops.new_amax(dev)
+        call("vitta_ln_bwd_amax", ptr(gy), ptr(x), ptr(weight), ptr(bias), ptr(mean), ptr(rstd), ptr(gadd), ca, cb, cm, gs,
+             ptr(gx), ptr(dgamma), ptr(dbeta), ptr(ws), rows, c, gp, ptr(am), stream_ptr())
+        ops._attach_amax(gx, am)
+        return gx, dgamma, dbeta
     call("vitta_ln_bwd", ptr(gy), ptr(x), ptr(weight), ptr(bias), ptr(mean), ptr(rstd), ptr(gadd), ca, cb, cm, gs, ptr(gx),
          ptr(dgamma), ptr(dbeta), ptr(ws), rows, c, gp, stream_ptr())
     return gx, dgamma, dbeta
@@ -132,6 +161,12 @@ def wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale):
     c = heads * 32
     out = torch.empty(b * d * h * w, c, dtype=torch.float32, device=qkv.device)
     lse = torch.empty(b * d * h * w * heads, dtype=torch.float32, device=qkv.device)
+    if ops.gemm_precision() == "f16x3":       # out is the operand of the fp16-split proj GEMM and of its weight gradient
+        am = ops.new_amax(qkv.device)
+        call("vitta_wmsa3d_fwd_amax", ptr(qkv), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window),
+             _int3(shift), float(scale), ptr(am), stream_ptr())
+        ops._attach_amax(out, am)
+        return out, lse
     call("vitta_wmsa3d_fwd", ptr(qkv), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window), _int3(shift),
          float(scale), stream_ptr())
     return out, lse
@@ -143,6 +178,12 @@ def wmsa3d_bwd(qkv, table, out, dout, lse, dims, heads, window, shift, scale, im
     dqkv = torch.empty_like(qkv)
     dtable = torch.zeros_like(table)
     ws = _workspace("wmsa_bwd", b * d * h * w * heads, qkv.device, False)
+    if ops.gemm_precision() == "f16x3" and impl == 0:      # dqkv feeds the qkv data / weight gradient GEMMs
+        am = ops.new_amax(qkv.device)
+        call("vitta_wmsa3d_bwd_amax", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b,
+             d, h, w, heads, 32, _int3(window), _int3(shift), float(scale), int(impl), ptr(am), stream_ptr())
+        ops._attach_amax(dqkv, am)
+        return dqkv, dtable
     call("vitta_wmsa3d_bwd", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b, d, h, w,
          heads, 32, _int3(window), _int3(shift), float(scale), int(impl), stream_ptr())
     return dqkv, dtable
@@ -234,7 +275,7 @@ class SwinMlpFn(torch.autograd.Function):
         _chk(y, "swin_mlp")
         rows = y.shape[0]
         pre = torch.empty(rows, w1.shape[0], dtype=torch.float32, device=y.device)
-        act = gemm(y, w1, 0, bias=b1, act=1, aux_out=pre)
+        act = gemm(y, w1, 0, bias=b1, act=1, aux_out=pre, want_amax=True)
         out = gemm(act, w2, 0, bias=b2, residual=shortcut, row_scale=rscale, rows_per_group=rows // n_samples)
         ctx.save_for_backward(y, w1, w2, pre, act, rscale)
         ctx.meta = (n_samples, b1 is not None, b2 is not None)
@@ -247,7 +288,7 @@ class SwinMlpFn(torch.autograd.Function):
         g = g.contiguous()
         rpg = g.shape[0] // n_samples
         gs = row_scale(g, rscale, rpg) if rscale is not None else g
-        dpre = gemm(gs, w2, 1, residual=pre, act=2)                      # (g @ W2) * GELU'(pre) in the epilogue
+        dpre = gemm(gs, w2, 1, residual=pre, act=2, want_amax=True)      # (g @ W2) * GELU'(pre) in the epilogue
         dw2 = linear_wgrad(act, gs)
         db2 = colsum(gs) if has_b2 else None
         dy = gemm(dpre, w1, 1)
