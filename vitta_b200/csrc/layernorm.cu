@@ -178,6 +178,182 @@ struct LnBwdArgs {
   float* amax_gx;   // optional: max|gx| (plain mode), the range of the GEMMs that take gx as their gradient operand
 };
 
+// R rows per warp iteration: ALL their loads (x, gy, the shortcut gradient, mean / rstd) are issued before the first
+// use.  With one row at a time a warp of the narrow stages (C = 96 .. 384: one to three 16-byte loads per lane and operand)
+// kept ~3 loads in flight and the kernel streamed at 1.4-1.8 TB/s (profiles/r01, r02); the rows are still visited, and
+// their contributions to d(gamma) / d(beta) added, in the same order as before.
+template <int VPL>
+struct LnBwdRows { static constexpr int value = VPL <= 1 ? 4 : 2; };   // instantiated for VPL <= 2 (C <= 256) only
+
+template <int VPL>
+__global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_rows_kernel(const LnBwdArgs p) {
+  constexpr int R = LnBwdRows<VPL>::value;
+  __shared__ float4 s_red[2 * 512];   // [2][C/4], C <= 2048
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int C4 = p.C >> 2;
+  const float invC = 1.f / (float)p.C;
+  int goff[VPL];
+  int gdh[VPL], gdw[VPL];
+  if (p.g.merge) {
+    const int cin4 = p.g.Cin >> 2;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * 32 + lane;
+      const int q = i / cin4, ci = i - q * cin4;
+      gdh[j] = q & 1;
+      gdw[j] = q >> 1;
+      goff[j] = (gdh[j] * p.g.W + gdw[j]) * p.g.Cin + ci * 4;
+    }
+  }
+  const float gsc = p.ca ? __ldg(p.gs) : 0.f;
+  float4 dg[VPL], db[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float am = 0.f;
+
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  for (int64_t rb = (int64_t)blockIdx.x * kLnWarps + warp; rb < p.rows; rb += stride * R) {
+    float4 xv[R][VPL], gyv[R][VPL], gav[R][VPL];
+    float mu[R], rs[R];
+    int64_t base[R];
+    int h0[R], w0[R];
+    // ---- phase 1: every load of the R rows
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k * stride;
+      h0[k] = w0[k] = 0;
+      base[k] = 0;
+      mu[k] = 0.f; rs[k] = 0.f;
+      if (r < p.rows) {
+        const float* src = ln_src_row(p.x, r, p.C, p.g, base[k], h0[k], w0[k]);
+        mu[k] = __ldg(p.mean + r);
+        rs[k] = __ldg(p.rstd + r);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int i = j * 32 + lane;
+          xv[k][j] = gyv[k][j] = gav[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < C4) {
+            if (!p.g.merge) {
+              xv[k][j] = ld_stream4(src + base[k] + (int64_t)i * 4);
+              if (p.gadd) gav[k][j] = ld_stream4(p.gadd + r * p.C + (int64_t)i * 4);
+            } else if (h0[k] + gdh[j] < p.g.H && w0[k] + gdw[j] < p.g.W) {
+              xv[k][j] = ld_stream4(src + base[k] + goff[j]);
+            }
+            gyv[k][j] = ld_stream4(p.gy + r * p.C + (int64_t)i * 4);
+          }
+        }
+      }
+    }
+    // ---- phase 2: the rows one after the other (same arithmetic and order as a one-row-at-a-time loop)
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k * stride;
+      if (r >= p.rows) break;
+      float4 xh[VPL], g[VPL];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < C4) {
+          const float4 v = xv[k][j];
+          float4 gy = gyv[k][j];
+          const float4 ga = ldg4(p.gamma + i * 4);
+          xh[j] = make_float4((v.x - mu[k]) * rs[k], (v.y - mu[k]) * rs[k], (v.z - mu[k]) * rs[k], (v.w - mu[k]) * rs[k]);
+          if (p.ca) {
+            const float4 be = ldg4(p.beta + i * 4);
+            const float4 a = ldg4(p.ca + i * 4), b = ldg4(p.cb + i * 4), m = ldg4(p.cm + i * 4);
+            gy.x = fmaf(gsc, fmaf(b.x, fmaf(xh[j].x, ga.x, be.x) - m.x, a.x), gy.x);
+            gy.y = fmaf(gsc, fmaf(b.y, fmaf(xh[j].y, ga.y, be.y) - m.y, a.y), gy.y);
+            gy.z = fmaf(gsc, fmaf(b.z, fmaf(xh[j].z, ga.z, be.z) - m.z, a.z), gy.z);
+            gy.w = fmaf(gsc, fmaf(b.w, fmaf(xh[j].w, ga.w, be.w) - m.w, a.w), gy.w);
+          }
+          db[j].x += gy.x; db[j].y += gy.y; db[j].z += gy.z; db[j].w += gy.w;
+          dg[j].x = fmaf(gy.x, xh[j].x, dg[j].x); dg[j].y = fmaf(gy.y, xh[j].y, dg[j].y);
+          dg[j].z = fmaf(gy.z, xh[j].z, dg[j].z); dg[j].w = fmaf(gy.w, xh[j].w, dg[j].w);
+          g[j] = make_float4(gy.x * ga.x, gy.y * ga.y, gy.z * ga.z, gy.w * ga.w);
+          s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+          s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+        }
+      }
+      const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        if (i < C4) {
+          float4 o;
+          o.x = rs[k] * (g[j].x - c1 - xh[j].x * c2);
+          o.y = rs[k] * (g[j].y - c1 - xh[j].y * c2);
+          o.z = rs[k] * (g[j].z - c1 - xh[j].z * c2);
+          o.w = rs[k] * (g[j].w - c1 - xh[j].w * c2);
+          if (!p.g.merge) {
+            if (p.gadd) {
+              const float4 a = gav[k][j];
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            st4(p.gx + r * p.C + (int64_t)i * 4, o);
+            am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          } else if (h0[k] + gdh[j] < p.g.H && w0[k] + gdw[j] < p.g.W) {
+            st4(p.gx + base[k] + goff[j], o);
+          }
+        }
+      }
+    }
+  }
+  if (p.amax_gx) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_gx), wmax);
+  }
+  // CTA reduction of d(gamma), d(beta): warps add in turn (fixed order), then one partial per CTA
+  for (int w = 0; w < kLnWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        if (i < C4) {
+          if (w == 0) {
+            s_red[i] = dg[j];
+            s_red[512 + i] = db[j];
+          } else {
+            float4 a = s_red[i], b = s_red[512 + i];
+            a.x += dg[j].x; a.y += dg[j].y; a.z += dg[j].z; a.w += dg[j].w;
+            b.x += db[j].x; b.y += db[j].y; b.z += db[j].z; b.w += db[j].w;
+            s_red[i] = a;
+            s_red[512 + i] = b;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* wsp = p.ws + kWsHeader;   // ws = [ticket ints | per-CTA partials]
+  float* wsb = wsp + (int64_t)blockIdx.x * 2 * p.C;
+  for (int i = threadIdx.x; i < C4; i += kLnThreads) {
+    st4(wsb + (int64_t)i * 4, s_red[i]);
+    st4(wsb + p.C + (int64_t)i * 4, s_red[512 + i]);
+  }
+  __threadfence();
+  __syncthreads();
+  int* ticket = reinterpret_cast<int*>(p.ws);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
+    float s = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(wsp + (int64_t)b * 2 * p.C + i);
+    if (i < p.C) {
+      if (p.dgamma) p.dgamma[i] += s;
+    } else {
+      if (p.dbeta) p.dbeta[i - p.C] += s;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+// one row per warp iteration: the wide rows (C >= 384) already have 8+ loads per lane in flight
 template <int VPL>
 __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
   __shared__ float4 s_red[2 * 512];   // [2][C/4], C <= 2048
@@ -339,9 +515,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   const bool active = c4 * 4 < C;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
-    for (int64_t r = (int64_t)blockIdx.x * 8 + slot; r < rows; r += (int64_t)gridDim.x * 8) {
-      const float4 v = ld_stream4(x + r * C + (int64_t)c4 * 4);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // eight rows per batch, loads first (a one-load-per-iteration loop keeps a single 16-byte load in flight per thread)
+    const int64_t rstep = (int64_t)gridDim.x * 8;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + slot; r < rows; r += rstep * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r + u * rstep < rows) v[u] = ld_stream4(x + (r + u * rstep) * C + (int64_t)c4 * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
   }
   sm[threadIdx.x] = s;
@@ -565,8 +749,8 @@ int vitta_ln_bwd_amax(const float* gy, const float* x, const float* gamma, const
   }
   const unsigned grid = (unsigned)ln_bwd_grid(rows);
   switch (ln_vpl(C)) {
-    case 1: ln_bwd_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 2: ln_bwd_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 1: ln_bwd_rows_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 2: ln_bwd_rows_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
     case 4: ln_bwd_kernel<4><<<grid, kLnThreads, 0, st>>>(p); break;
     case 8: ln_bwd_kernel<8><<<grid, kLnThreads, 0, st>>>(p); break;
     default: ln_bwd_kernel<16><<<grid, kLnThreads, 0, st>>>(p); break;
