@@ -385,7 +385,11 @@ int vitta_conv2d_f16x3_ex(const float* X, const float* x_amax, int F, int H, int
                           const float* bias, const float* residual, int force_bn, void* stream);
 int vitta_conv2d_wgrad_f16x3(const float* X, const float* x_amax, const float* dY, const float* dy_amax, int F, int H,
                              int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* dW, int accumulate,
-                             float* ws, void* stream);   /* same ws size and reduction as vitta_conv2d_wgrad_tf32x3 */
+                             float* ws, void* stream);
+/* ... and with the bias gradient dbias[co] = sum_pixels dY[., co] as a by-product (no column-sum pass over dY) */
+int vitta_conv2d_wgrad_f16x3_bias(const float* X, const float* x_amax, const float* dY, const float* dy_amax, int F, int H,
+                                  int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* dW, float* dbias,
+                                  int accumulate, float* ws, void* stream);   /* same ws size and reduction as vitta_conv2d_wgrad_tf32x3 */
 int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int Ho, int Wo, int Cout, const void* Wthi,
                              const void* Wtlo, const float* w_amax, int Cin, int KH, int KW, int stride, int pad, int H,
                              int W, float* dX, void* stream);

@@ -81,11 +81,12 @@ def test_host_side_planners_without_gpu(lib):
         n = lib.vitta_tam_num_chunks(hw, c)
         assert n >= 1 and -(-hw // n) <= 64
     assert lib.vitta_tam_num_chunks(196, 256) >= 30
-    # weight-gradient workspace: splits x Cout x KH*KW x Cin floats, also in the three-taps-per-item mode (Cin = 64, 3x3)
+    # weight-gradient workspace: splits x (Cout x KH*KW x Cin weight partials + Cout bias partials) floats, also in the
+    # three-taps-per-item mode (Cin = 64, 3x3)
     for f, h, cin, cout, k, s in [(128, 56, 64, 64, 3, 1), (128, 56, 64, 256, 1, 1), (128, 14, 256, 256, 3, 1),
                                   (128, 28, 128, 128, 3, 2), (2, 9, 8, 24, 3, 1)]:
         n = lib.vitta_conv2d_wgrad_ws_floats(f, h, h, cin, cout, k, k, s, k // 2)
-        assert n > 0 and n % (cout * k * k * cin) == 0
+        assert n > 0 and n % (cout * k * k * cin + cout) == 0
     assert lib.vitta_conv2d_wgrad_ws_floats(0, 56, 56, 64, 64, 3, 3, 1, 1) == -1
     assert lib.vitta_bn_act_bwd_ws_floats(128, 3136, 64) > 0
     assert lib.vitta_gemm_set_operand_form(3) == -1 and lib.vitta_gemm_set_operand_form(0) == 0

@@ -410,3 +410,21 @@ def test_producers_emit_the_operand_range_of_their_outputs(cuda_device):
         check(dqkv, "wmsa3d_bwd")
     finally:
         ops.set_gemm_precision(before)
+
+
+@pytest.mark.parametrize("m,k,n", [(5000, 96, 288), (1568, 384, 96), (3136, 128, 512), (100, 64, 40)])
+def test_linear_wgrad_returns_the_bias_gradient(cuda_device, m, k, n):
+    """The fp16-split weight-gradient kernel adds up dY over the pixels while it transposes the dY tiles: db must equal
+    the column sums of gy (and dW is unchanged by the option)."""
+    from vitta_b200 import ops, ops_swin
+    before = ops.gemm_precision()
+    ops.set_gemm_precision("f16x3")
+    try:
+        x, gy = _rnd(m, k, seed=1), _rnd(m, n, seed=2) * 1e-3
+        gw0 = ops_swin.linear_wgrad(x, gy)
+        gw, db = ops_swin.linear_wgrad(x, gy, want_bias=True)
+        assert torch.equal(gw, gw0)
+        want = gy.double().sum(0)
+        cases.assert_close(db.cpu(), want.cpu(), 1e-5, 1e-6 * float(gy.abs().sum(0).max()), "bias gradient")
+    finally:
+        ops.set_gemm_precision(before)

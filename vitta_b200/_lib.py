@@ -97,6 +97,7 @@ _SIGNATURES = {
     "vitta_conv2d_f16x3_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "vitta_conv2d_wgrad_f16x3": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 9 + [_P, C.c_int, _P, _P]),
+    "vitta_conv2d_wgrad_f16x3_bias": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 9 + [_P, _P, C.c_int, _P, _P]),
     "vitta_conv2d_dgrad_f16x3": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_ln_chunking": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(VittaChunking)]),

@@ -39,6 +39,7 @@ struct WgradParams {
   int box_base, box_rem;   // total_boxes = splits * box_base + box_rem: split sp covers box_base (+1 if sp < box_rem) boxes
   const float* a_amax;     // F16 kernels: device scalars >= max|dY|, >= max|X|
   const float* b_amax;
+  float* bias_ws;          // optional (F16 kernels): [splits][Cout] partial sums of dY over the pixels = bias gradient
 };
 
 // TS = true: the dY tile (A operand, M = output channel) is transposed into TENSOR MEMORY by four of the split warps
@@ -263,6 +264,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int mt, tap, ct, sp, b0, b1;
       decode(item, mt, tap, ct, sp, b0, b1);
+      // bias gradient for free: the threads that transpose the dY tile (one output channel each) see every dY element of
+      // the item's pixel range; the items of the first tap / first Cin tile add them up (pixel order, then a fixed-order
+      // sum over the K splits in wgrad_reduce_kernel) -- no separate column-sum pass over dY
+      float bsum = 0.f;
+      const bool want_bias = F16 && p.bias_ws != nullptr && tap == 0 && ct == 0;
       for (int b = b0; b < b1; ++b) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * S::kStageBytes;
@@ -281,8 +287,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const int r0 = 2 * u, r1 = 2 * u + 1;
-              const float v0 = *reinterpret_cast<const float*>(box + r0 * 128 + ((c8 ^ (r0 & 3)) << 5)) * sa;
-              const float v1 = *reinterpret_cast<const float*>(box + r1 * 128 + ((c8 ^ (r1 & 3)) << 5)) * sa;
+              const float x0 = *reinterpret_cast<const float*>(box + r0 * 128 + ((c8 ^ (r0 & 3)) << 5));
+              const float x1 = *reinterpret_cast<const float*>(box + r1 * 128 + ((c8 ^ (r1 & 3)) << 5));
+              bsum += x0;
+              bsum += x1;
+              const float v0 = x0 * sa, v1 = x1 * sa;
               const __half2 h = __floats2half2_rn(v0, v1);
               const float2 hf = __half22float2(h);
               const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -423,6 +432,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         if (lane == 0) mbar_arrive(&split_bar[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (want_bias && warp < 6) {
+        const int ch = mt * kWgBM + (warp & 3) * 32 + lane;
+        if (ch < p.Cout) p.bias_ws[(int64_t)sp * p.Cout + ch] = bsum;
+      }
     }
   } else {
     const int q = warp & 3;
@@ -498,8 +511,16 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
 
 // dW (NCHW: [co][ci][tap]) (+)= sum_s ws[s][co][tap][ci], splits summed in order
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout,
-                                                          int Cin, int taps, int splits, int accumulate) {
+                                                          int Cin, int taps, int splits, int accumulate,
+                                                          const float* __restrict__ bias_ws, float* __restrict__ dbias) {
   const int64_t n = (int64_t)Cout * taps * Cin;
+  if (dbias) {   // bias gradient: the K-split partials of sum_pixels dY, in split order
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < Cout; c += gridDim.x * 256) {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += __ldg(bias_ws + (int64_t)k * Cout + c);
+      dbias[c] = s;
+    }
+  }
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += __ldg(ws + (int64_t)k * n + i);
@@ -611,12 +632,12 @@ int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int
   // the fp16 kernel may pick a wider N tile and therefore more K splits: size the workspace for either plan
   if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl, true)) return -1;
   if (pl.p.splits > splits) splits = pl.p.splits;
-  return (int64_t)splits * Cout * KH * KW * Cin;
+  return (int64_t)splits * Cout * KH * KW * Cin + (int64_t)splits * Cout;   // weight partials + bias partials
 }
 
 static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
                       int stride, int pad, float* dW, int accumulate, float* ws, void* stream, const float* x_amax,
-                      const float* dy_amax) {
+                      const float* dy_amax, float* dbias = nullptr) {
   const bool f16 = x_amax != nullptr;
   VITTA_CHECK_ARG(!f16 || dy_amax, VITTA_E_BADARG, "conv2d_wgrad_f16x3: both amax scalars are required");
   VITTA_CHECK_ARG(X && dY && dW && ws && F > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, VITTA_E_BADARG,
@@ -631,6 +652,9 @@ static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int 
   WgradParams& p = pl.p;
   p.ws = ws;
   p.a_amax = dy_amax; p.b_amax = x_amax;
+  VITTA_CHECK_ARG(!dbias || f16, VITTA_E_UNSUPPORTED, "conv2d_wgrad: the fused bias gradient exists for the fp16 split only");
+  // the bias partials live behind the weight partials of the workspace (vitta_conv2d_wgrad_ws_floats sizes both)
+  p.bias_ws = dbias ? ws + (int64_t)p.splits * Cout * KH * KW * Cin : nullptr;
   if (f16 && pl.bn == 192 && p.tap_group != 3) return VITTA_E_BADARG;   // (cannot happen: 192 is the tap-group mode)
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   VITTA_CHECK_ARG(p.BW * stride <= 256 && p.BH * stride <= 256, VITTA_E_UNSUPPORTED, "conv2d_wgrad: box too large");
@@ -666,7 +690,7 @@ static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int 
   const int64_t n = (int64_t)Cout * KH * KW * Cin;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate);
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate, p.bias_ws, dbias);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
@@ -681,6 +705,15 @@ int vitta_conv2d_wgrad_f16x3(const float* X, const float* x_amax, const float* d
                              float* ws, void* stream) {
   VITTA_CHECK_ARG(x_amax && dy_amax, VITTA_E_BADARG, "conv2d_wgrad_f16x3: amax scalars are required");
   return wgrad_impl(X, dY, F, H, W, Cin, Cout, KH, KW, stride, pad, dW, accumulate, ws, stream, x_amax, dy_amax);
+}
+
+// vitta_conv2d_wgrad_f16x3 that also returns the bias gradient dbias[co] = sum over the pixels of dY[., co] (nn.Linear /
+// nn.Conv2d with bias): the kernel's dY-transposing threads add it up on the way, so no column-sum pass over dY is needed.
+int vitta_conv2d_wgrad_f16x3_bias(const float* X, const float* x_amax, const float* dY, const float* dy_amax, int F, int H,
+                                  int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* dW, float* dbias,
+                                  int accumulate, float* ws, void* stream) {
+  VITTA_CHECK_ARG(x_amax && dy_amax && dbias, VITTA_E_BADARG, "conv2d_wgrad_f16x3_bias: amax scalars and dbias are required");
+  return wgrad_impl(X, dY, F, H, W, Cin, Cout, KH, KW, stride, pad, dW, accumulate, ws, stream, x_amax, dy_amax, dbias);
 }
 
 }  // extern "C"

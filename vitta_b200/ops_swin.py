@@ -65,8 +65,9 @@ def gemm(a, w, mode, bias=None, residual=None, act=0, aux_out=None, row_scale=No
     return out
 
 
-def linear_wgrad(x, gy):
-    """dW (N, K) = gy[M, N]^T @ x[M, K] on the split-K tcgen05 weight-gradient kernel (a 1x1 'convolution' over M pixels)."""
+def linear_wgrad(x, gy, want_bias=False):
+    """dW (N, K) = gy[M, N]^T @ x[M, K] on the split-K tcgen05 weight-gradient kernel (a 1x1 'convolution' over M pixels).
+    ``want_bias``: also return db (N,) = column sums of gy -- a by-product of the fp16-split kernel, else vitta_colsum."""
     m, k = x.shape
     n = gy.shape[1]
     f, wdt = 1, m    # pointwise: the kernel walks the rows 32 at a time
@@ -76,11 +77,16 @@ def linear_wgrad(x, gy):
     ws = _workspace("wgrad", nws, x.device, False)
     gw = torch.empty(n, k, dtype=torch.float32, device=x.device)
     if ops.gemm_precision() == "f16x3" and x.is_contiguous() and gy.is_contiguous():
+        if want_bias:
+            db = torch.empty(n, dtype=torch.float32, device=x.device)
+            call("vitta_conv2d_wgrad_f16x3_bias", ptr(x), ptr(ops.operand_amax(x)), ptr(gy), ptr(ops.operand_amax(gy)), f, 1,
+                 wdt, k, n, 1, 1, 1, 0, ptr(gw), ptr(db), 0, ptr(ws), stream_ptr())
+            return gw, db
         call("vitta_conv2d_wgrad_f16x3", ptr(x), ptr(ops.operand_amax(x)), ptr(gy), ptr(ops.operand_amax(gy)), f, 1, wdt, k, n, 1,
              1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
         return gw
     call("vitta_conv2d_wgrad_tf32x3", ptr(x), ptr(gy), f, 1, wdt, k, n, 1, 1, 1, 0, ptr(gw), 0, ptr(ws), stream_ptr())
-    return gw
+    return (gw, colsum(gy)) if want_bias else gw
 
 
 def colsum(g):
@@ -257,12 +263,16 @@ class SwinAttentionFn(torch.autograd.Function):
         rpg = g.shape[0] // b
         gs = row_scale(g, rscale, rpg) if rscale is not None else g      # gradient of the branch output
         dao = gemm(gs, wproj, 1)
-        dwproj = linear_wgrad(ao, gs)
-        dbproj = colsum(gs) if has_bproj else None
+        if has_bproj:
+            dwproj, dbproj = linear_wgrad(ao, gs, want_bias=True)
+        else:
+            dwproj, dbproj = linear_wgrad(ao, gs), None
         dqkv, dtable = wmsa3d_bwd(qkv, table, ao, dao, lse, dims, heads, window, shift, scale)
         dy = gemm(dqkv, wqkv, 1)
-        dwqkv = linear_wgrad(y, dqkv)
-        dbqkv = colsum(dqkv) if has_bqkv else None
+        if has_bqkv:
+            dwqkv, dbqkv = linear_wgrad(y, dqkv, want_bias=True)
+        else:
+            dwqkv, dbqkv = linear_wgrad(y, dqkv), None
         return dy, g, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None, None, None, None, None
 
 
@@ -289,11 +299,15 @@ class SwinMlpFn(torch.autograd.Function):
         rpg = g.shape[0] // n_samples
         gs = row_scale(g, rscale, rpg) if rscale is not None else g
         dpre = gemm(gs, w2, 1, residual=pre, act=2, want_amax=True)      # (g @ W2) * GELU'(pre) in the epilogue
-        dw2 = linear_wgrad(act, gs)
-        db2 = colsum(gs) if has_b2 else None
+        if has_b2:
+            dw2, db2 = linear_wgrad(act, gs, want_bias=True)
+        else:
+            dw2, db2 = linear_wgrad(act, gs), None
         dy = gemm(dpre, w1, 1)
-        dw1 = linear_wgrad(y, dpre)
-        db1 = colsum(dpre) if has_b1 else None
+        if has_b1:
+            dw1, db1 = linear_wgrad(y, dpre, want_bias=True)
+        else:
+            dw1, db1 = linear_wgrad(y, dpre), None
         return dy, g, dw1, db1, dw2, db2, None, None
 
 
