@@ -80,7 +80,7 @@ def _work(name, a):
     if name in ("vitta_gemm_tf32x3", "vitta_gemm_tf32x3_ex"):
         m, n, k = g(7, 8, 9)
         return GEMM_FAM, 2.0 * m * n * k, 0.0
-    if name == "vitta_gemm_f16x3_ex":
+    if name in ("vitta_gemm_f16x3_ex", "vitta_gemm_f16x3_amax"):
         m, n, k = g(9, 10, 11)
         return GEMM_FAM, 2.0 * m * n * k, 0.0
     if name in ("vitta_conv2d_tf32x3", "vitta_conv2d_tf32x3_ex"):
@@ -100,10 +100,10 @@ def _work(name, a):
         return GEMM_FAM, 2.0 * f * ho * wo * cout * cin * kh * kw, 0.0
     if name == "vitta_conv2d_wgrad_tf32x3":
         return WGRAD_FAM, _conv_flops(*g(*range(2, 11))), 0.0
-    if name == "vitta_conv2d_wgrad_f16x3":
+    if name in ("vitta_conv2d_wgrad_f16x3", "vitta_conv2d_wgrad_f16x3_bias"):
         return WGRAD_FAM, _conv_flops(*g(*range(4, 13))), 0.0
-    if name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd"):
-        fwd = name == "vitta_wmsa3d_fwd"
+    if name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd", "vitta_wmsa3d_fwd_amax", "vitta_wmsa3d_bwd_amax"):
+        fwd = name.startswith("vitta_wmsa3d_fwd")
         i0 = 4 if fwd else 8
         b_, d_, h_, w_, heads = g(*range(i0, i0 + 5))
         nwin = ntok = 1
@@ -113,8 +113,8 @@ def _work(name, a):
             ntok *= wsz
         return (("wmsa3d_fwd (tcgen05 window attention)" if fwd else "wmsa3d_bwd (tcgen05 window attention backward)"),
                 (4.0 if fwd else 10.0) * ntok * ntok * 32 * b_ * nwin * heads, 0.0)
-    if name in ("vitta_ln_fwd", "vitta_ln_bwd"):
-        fwd = name == "vitta_ln_fwd"
+    if name in ("vitta_ln_fwd", "vitta_ln_bwd", "vitta_ln_fwd_amax", "vitta_ln_bwd_amax"):
+        fwd = name.startswith("vitta_ln_fwd")
         rows, c = g(8, 9) if fwd else g(15, 16)
         return (("ln_fwd (LayerNorm + stats, K9)" if fwd else "ln_bwd (K9 backward + hook gradient)"), 0.0,
                 4.0 * rows * c * (2 if fwd else 3))
