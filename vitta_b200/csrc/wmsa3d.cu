@@ -384,32 +384,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         // ---- pass 1 (log2 domain): t = s*log2e + bias2 + mask2, in place; row maximum.  Padding columns carry region
         //      id 31 and are therefore always masked (their P is ~2^-144 and multiplies zero V rows).
         float m2 = -INFINITY;
-        {
-          // two register buffers: the tcgen05.ld of the next 16 columns is in flight while the current 16 are processed
-          // (one warp per scheduler runs this loop, so nothing else hides the TMEM round trip of a load-then-wait step)
-          auto pass1 = [&](uint32_t* r, int c0) {
+        for (int c0 = 0; c0 < g.NP; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_lane + (uint32_t)c0, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int fj = info[c0 + jj];
-              float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
-              t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
-              m2 = fmaxf(m2, t);
-              r[jj] = __float_as_uint(t);
-            }
-            tmem_st16(t_lane + (uint32_t)c0, r);
-          };
-          uint32_t ra[16], rb[16];
-          tmem_ld16(t_lane, ra);
-          for (int c0 = 0; c0 < g.NP; c0 += 32) {
-            tmem_ld_wait();                                                          // ra landed
-            if (c0 + 16 < g.NP) tmem_ld16(t_lane + (uint32_t)(c0 + 16), rb);
-            pass1(ra, c0);
-            if (c0 + 16 < g.NP) {
-              tmem_ld_wait();                                                        // rb landed
-              if (c0 + 32 < g.NP) tmem_ld16(t_lane + (uint32_t)(c0 + 32), ra);
-              pass1(rb, c0 + 16);
-            }
+          for (int jj = 0; jj < 16; ++jj) {
+            const int fj = info[c0 + jj];
+            float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
+            t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
+            m2 = fmaxf(m2, t);
+            r[jj] = __float_as_uint(t);
           }
+          tmem_st16(t_lane + (uint32_t)c0, r);
         }
         tmem_st_wait();
         if (tile == n_tiles - 1) {   // last use of tab / info by this warp for this item
