@@ -52,8 +52,9 @@ def _peaks():
 
 
 def _traffic(kernel_key):
-    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture of this round (written by
-    tools/ncu_summary.py --traffic into profiles/r02_traffic.json); None when no capture of that kernel exists."""
+    """DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture of this round (written by
+    tools/ncu_traffic.py into profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    captured launches); None when no capture of that kernel exists."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f).get(kernel_key)
@@ -541,7 +542,9 @@ def run_ours(args):
             "achieved": tf, "peak": kind_peak,
             "peak_source": which + (": bf16_tflops_sustained (the kind::f16 rate)" if f16
                                     else ": bf16_tflops_sustained / 2 (the kind::tf32 rate)"),
-            "unit": "TFLOP/s", "frac": tf / kind_peak, "traffic": _traffic("gemm_tf32x3_kernel"),
+            "unit": "TFLOP/s", "frac": tf / kind_peak, "frac_of_tf32_rate": tf / (peak_bf16 / 2.0),
+            "traffic": (_traffic("gemm_tf32x3_kernel") or {}).get("dram_bytes_per_launch"),
+            "traffic_detail": _traffic("gemm_tf32x3_kernel"),
             "note": "achieved counts ALGORITHMIC fp32 flops (2MNK); fp32-grade products need 3 MMAs each (hi*hi + hi*lo + "
                     "lo*hi, DESIGN.md section 3), so the issued tensor-pipe work is 3x this and frac cannot exceed 1/3",
             "tensor_pipe_frac_issued": 3.0 * tf / kind_peak,
@@ -552,7 +555,10 @@ def run_ours(args):
     achieved = bytes_pass / (ms_k1 * 1e-3) / 1e9
     roof_stats = {"bound": "hbm", "kernel": "bn_act_fwd_kernel (statistics hook fused into the norm pass: K4+K1), "
                                             "timed inside the step", "achieved": gbs, "peak": peak_hbm,
-                  "peak_source": which, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": _traffic("bn_act_fwd_kernel"),
+                  "peak_source": which, "unit": "GB/s", "frac": gbs / peak_hbm,
+                  "traffic": (_traffic("bn_act_fwd_kernel") or {}).get("dram_bytes_per_launch"),
+                  "traffic_detail": _traffic("bn_act_fwd_kernel"),
+                  "algorithmic_bytes_per_launch": f["bytes"] / max(f["launches"], 1),
                   "launches_per_step": f["launches"], "ms_per_step": f["ms"],
                   "k1_standalone": {"kernel": "stats_cl_kernel over the 29 hooked layer shapes (hooks on stock modules)",
                                     "achieved": achieved, "frac": achieved / peak_hbm,

@@ -13,4 +13,5 @@ prof bnfwd "bn_act_fwd_kernel" 3 6
 prof gemm "gemm_tf32x3_kernel" 4 24
 prof wgrad "wgrad_tf32x3_kernel" 0 10
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --ncu-step > gpurun_out/${TAG}_ncu_step.log 2>&1; echo "ncu list rc=$?"
+python tools/ncu_traffic.py gpurun_out/${TAG}_traffic.json gemm_tf32x3_kernel=/tmp/${TAG}_gemm.ncu-rep bn_act_fwd_kernel=/tmp/${TAG}_bnfwd.ncu-rep wgrad_tf32x3_kernel=/tmp/${TAG}_wgrad.ncu-rep > /dev/null
 du -sh gpurun_out
