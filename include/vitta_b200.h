@@ -249,6 +249,10 @@ int vitta_stem_pack(const float* x, float* xp, int F, int H, int W, void* stream
 int vitta_stem_pack_weight(const float* w, float* hi, float* lo, void* stream);
 int vitta_stem_conv_tf32x3(const float* XP, int F, int H, int W, const float* Whi, const float* Wlo, float* Y,
                            void* stream);
+/* weight gradient of the stem convolution: dW (64, 3, 7, 7) from the packed image XP and dY (F, H/2, W/2, 64) channels-last;
+ * exact fp32 FFMA (no operand split), per-CTA partials in ws (vitta_stem_wgrad_ws_floats floats), summed in a fixed order */
+int64_t vitta_stem_wgrad_ws_floats(void);
+int vitta_stem_wgrad(const float* XP, const float* dY, float* dW, float* ws, int F, int H, int W, void* stream);
 int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
                            void* stream);
 int64_t vitta_bn_relu_pool_bwd_ws_floats(int C);

@@ -358,7 +358,8 @@ def test_stem_conv_on_tcgen05_vs_float64(cuda_device, f, h, w):
     go = torch.randn(y.shape, generator=g).to(cuda_device)
     y.backward(go)
     ref.backward(go.double())
-    assert float((wt.grad.double() - w64.grad).abs().max()) < 1e-4 * float(w64.grad.abs().max())
+    # the weight gradient is our fp32 FFMA kernel (exact products): tight bound, relative to the largest entry
+    assert float((wt.grad.double() - w64.grad).abs().max()) < 2e-5 * float(w64.grad.abs().max())
 
 
 @pytest.mark.parametrize("f,c,h,w", [(2, 64, 16, 16), (3, 64, 15, 22), (4, 64, 112, 112), (2, 128, 9, 8)])

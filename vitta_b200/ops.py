@@ -1275,10 +1275,14 @@ def _stem_weight_split(w, mode):
     return hi, lo
 
 
+_stem_ws = {}
+
+
 class StemConvFn(torch.autograd.Function):
     """conv1 of the ResNet trunk (64 x 3 x 7 x 7, stride 2, padding 3) on the tcgen05 3xTF32 kernel.  x: (F, 3, H, W) in
     ANY dense layout (read once by the packing kernel); result (F, 64, H/2, W/2) channels_last.  The weight gradient --
-    the only gradient the step needs here, the frames do not require one -- stays on the library (cuDNN) for now."""
+    the only gradient the step needs here, the frames do not require one -- is the register-blocked fp32 kernel
+    vitta_stem_wgrad over the same packed image (the library convolution backward is used only for an input gradient)."""
 
     @staticmethod
     def forward(ctx, x, w):
@@ -1290,20 +1294,26 @@ class StemConvFn(torch.autograd.Function):
         whi, wlo = _cached_split(w, "stem", "tf32", _stem_weight_split)
         y = torch.empty((f, 64, h // 2, wd // 2), dtype=torch.float32, device=x.device, memory_format=CL)
         call("vitta_stem_conv_tf32x3", ptr(xp), f, h, wd, ptr(whi), ptr(wlo), ptr(y), stream_ptr())
-        ctx.save_for_backward(xc, w)
+        ctx.save_for_backward(xc, w, xp)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
+        x, w, xp = ctx.saved_tensors
+        f, _, h, wd = x.shape
         gx = gw = None
         need_x, need_w = ctx.needs_input_grad
-        if need_x or need_w:
-            # channels_last operands select cuDNN's NHWC kernels (no transposing copy of the 411 MB gradient)
-            r = torch.ops.aten.convolution_backward(gy.contiguous(memory_format=CL), x.contiguous(memory_format=CL), w,
-                                                    None, [2, 2], [3, 3], [1, 1], False, [0, 0], 1,
-                                                    [need_x, need_w, False])
-            gx, gw = r[0], r[1]
+        gy = gy.contiguous(memory_format=CL)
+        if need_w:
+            ws = _stem_ws.get(x.device)
+            if ws is None:
+                ws = _stem_ws[x.device] = torch.empty(_lib.load().vitta_stem_wgrad_ws_floats(), dtype=torch.float32,
+                                                      device=x.device)
+            gw = torch.empty(64, 3, 7, 7, dtype=torch.float32, device=x.device)
+            call("vitta_stem_wgrad", ptr(xp), ptr(gy), ptr(gw), ptr(ws), f, h, wd, stream_ptr())
+        if need_x:
+            gx = torch.ops.aten.convolution_backward(gy, x.contiguous(memory_format=CL), w, None, [2, 2], [3, 3], [1, 1],
+                                                     False, [0, 0], 1, [True, False, False])[0]
         return gx, gw
 
 
