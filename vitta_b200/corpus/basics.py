@@ -521,7 +521,7 @@ class OnlineAdapter:
                 if input.data_ptr() != eg['in'].data_ptr():
                     eg['in'].copy_(input, non_blocking=True)
                 eg['graph'].replay()
-                return eg['out']
+                return eg['out'].clone()        # the graph's output buffer is rewritten by the next replay
             if getattr(self, '_eval_eager_key', None) != key:
                 # first pass of this shape runs eagerly on a side stream (allocator / cuDNN warm-up before capture)
                 self._eval_eager_key = key
@@ -549,7 +549,7 @@ class OnlineAdapter:
                 return self._evaluate_eager(input)
             self._eval_graph = {'key': key, 'graph': g, 'in': static_in, 'out': out}
             g.replay()
-            return out
+            return out.clone()
         finally:
             self._release(slot)
 

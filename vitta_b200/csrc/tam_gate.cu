@@ -4,7 +4,7 @@
 //   L (local branch):  per (video, frame)     sigmoid( Wb . relu(BN1d( conv1d_k3(Wa, p)[n, t, :] )) )   -> act  (N, T, C)
 // with the BatchNorm1d layers in eval mode.  In eager PyTorch this is ~20 tiny kernels forward and ~25 backward per TAM
 // (cutlass simt sgemm, ATen batch-norm / elementwise / reduce kernels: 16 TAMs -> ~700 launches per step); here it is
-// 3 launches forward and 6 backward.  Everything is L2-resident (p is N*T*C <= 64 K floats, the largest weight 786 KB),
+// 3 launches forward and 8 backward (tam_bwd_finish of tam.cu included).  Everything is L2-resident (p is N*T*C <= 64 K floats, the largest weight 786 KB),
 // so the kernels are latency-bound; a generic 32x32-tile fp32 GEMM with stage-specific operand loaders and epilogues does
 // the L branch, one thread per (video, channel) does the G branch.  All reductions run in a fixed order (deterministic).
 #include "common.cuh"
@@ -208,16 +208,12 @@ __global__ void __launch_bounds__(kGThreads) tam_g_bwd_kernel(GateArgs a, int n_
 // ------------------------------------------------------------------------------------------------
 // L branch: generic 32x32-tile GEMM  D[m, n] = sum_k A(m, k) * B(n, k)  with stage-specific loaders / epilogues
 // ------------------------------------------------------------------------------------------------
-enum GateStage { kL1Fwd = 0, kL2Fwd, kGradWb, kGradHid, kGradWa, kGradP };
+enum GateStage { kL2Fwd = 1, kGradWb, kGradHid, kGradWa, kGradP };   // (the hidden layer has its own kernel, tam_l1_fwd_kernel)
 
 template <int STAGE>
 __device__ __forceinline__ float gate_A(const GateArgs& a, int m, int k) {
   const int T = a.T, C = a.C, Hc = a.C / 4;
-  if (STAGE == kL1Fwd) {            // m = (n, t), k = c*3 + j  ->  p[n, t + j - 1, c]
-    const int c = k / 3, j = k - 3 * c;
-    const int t = m % T + j - 1;
-    return (t >= 0 && t < T) ? __ldg(a.p + ((int64_t)(m - m % T + t)) * C + c) : 0.f;
-  } else if (STAGE == kL2Fwd) {     // hid[m, k] = relu(bn2(pre[m, k]))
+  if (STAGE == kL2Fwd) {            // hid[m, k] = relu(bn2(pre[m, k]))
     return fmaxf(gate_bn_apply(a.bn2, k, __ldg(a.pre + (int64_t)m * Hc + k)), 0.f);
   } else if (STAGE == kGradWb) {    // m = c, k = r  ->  gz[r, c]
     return a.gz[(int64_t)k * C + m];
@@ -235,9 +231,7 @@ __device__ __forceinline__ float gate_A(const GateArgs& a, int m, int k) {
 template <int STAGE>
 __device__ __forceinline__ float gate_B(const GateArgs& a, int n, int k) {
   const int T = a.T, C = a.C, Hc = a.C / 4;
-  if (STAGE == kL1Fwd) {            // n = o, k = c*3 + j  ->  Wa[o][c][j]
-    return __ldg(a.Wa + (int64_t)n * 3 * C + k);
-  } else if (STAGE == kL2Fwd) {     // n = c, k = o  ->  Wb[c][o]
+  if (STAGE == kL2Fwd) {            // n = c, k = o  ->  Wb[c][o]
     return __ldg(a.Wb + (int64_t)n * Hc + k);
   } else if (STAGE == kGradWb) {    // n = o, k = r  ->  hid[r, o]
     return fmaxf(gate_bn_apply(a.bn2, n, __ldg(a.pre + (int64_t)k * Hc + n)), 0.f);
@@ -256,9 +250,7 @@ __device__ __forceinline__ float gate_B(const GateArgs& a, int n, int k) {
 template <int STAGE>
 __device__ __forceinline__ void gate_store(const GateArgs& a, int m, int n, float acc) {
   const int C = a.C, Hc = a.C / 4;
-  if (STAGE == kL1Fwd) {
-    a.pre[(int64_t)m * Hc + n] = acc;
-  } else if (STAGE == kL2Fwd) {
+  if (STAGE == kL2Fwd) {
     a.act[(int64_t)m * C + n] = 1.f / (1.f + expf(-acc));
   } else if (STAGE == kGradWb) {
     a.gWb[(int64_t)m * Hc + n] = acc;

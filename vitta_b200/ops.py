@@ -1361,8 +1361,6 @@ class BnReluPoolFn(torch.autograd.Function):
         gparam = torch.empty(2, c, dtype=torch.float32, device=x.device)
         call("vitta_bn_relu_pool_bwd", ptr(gout), ptr(code), ptr(x), _lib.make_bn(w, b, rm, rv, ctx.eps), ptr(gx),
              ptr(gparam[0]), ptr(gparam[1]), ptr(ws), f, h, wd, c, stream_ptr())
-        if _fused_amax():
-            pass        # gx feeds only the stem convolution's weight gradient (library path): no operand range needed
         return gx, gparam[0], gparam[1], None, None, None
 
 
