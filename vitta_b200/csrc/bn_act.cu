@@ -352,8 +352,7 @@ __device__ __forceinline__ void bn_act_bwd_body(const BwdArgs& p, float* __restr
     const int k = i / nch;
     const int cc = by * nch + (i % nch);
     if (cc >= C) continue;
-    float s = 0.f;
-    for (int b = 0; b < gdx; ++b) s += __ldcg(p.ws + ((int64_t)b * 4 + k) * C + cc);
+    const float s = ordered_sum_strided(p.ws + (int64_t)k * C + cc, gdx, 4 * (int64_t)C);
     float* dst = (k == 0) ? p.gw : (k == 1) ? p.gb : (k == 2) ? p.gw2 : p.gb2;
     if (dst) dst[cc] += s;
   }

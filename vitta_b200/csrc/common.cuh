@@ -129,6 +129,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// sum_{b < n} p[b * stride] in index order (deterministic), with the loads issued sixteen at a time: the "last CTA adds the
+// per-CTA partials" epilogues walk up to ~600 partials per output, and a plain `s += load` loop pays one L2 round trip per
+// partial there (tens of microseconds at the tail of every launch).
+__device__ __forceinline__ float ordered_sum_strided(const float* p, int n, int64_t stride) {
+  float s = 0.f;
+  for (int b0 = 0; b0 < n; b0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (b0 + u < n) ? __ldcg(p + (int64_t)(b0 + u) * stride) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s += v[u];
+  }
+  return s;
+}
+
 // Chan et al. pairwise merge of (n, mean, M2)
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
   if (nb == 0.f) return;

@@ -342,8 +342,7 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_rows_kernel(const LnBwdA
   if (!s_last) return;
   __threadfence();
   for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
-    float s = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(wsp + (int64_t)b * 2 * p.C + i);
+    const float s = ordered_sum_strided(wsp + i, (int)gridDim.x, 2 * (int64_t)p.C);
     if (i < p.C) {
       if (p.dgamma) p.dgamma[i] += s;
     } else {
@@ -481,8 +480,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
   if (!s_last) return;
   __threadfence();
   for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
-    float s = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(wsp + (int64_t)b * 2 * p.C + i);
+    const float s = ordered_sum_strided(wsp + i, (int)gridDim.x, 2 * (int64_t)p.C);
     if (i < p.C) {
       if (p.dgamma) p.dgamma[i] += s;
     } else {
@@ -550,8 +548,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   for (int i = threadIdx.x; i < 128; i += 256) {
     const int c = blockIdx.y * 128 + i;
     if (c >= C) continue;
-    float t = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(wsp + (int64_t)b * C + c);
+    const float t = ordered_sum_strided(wsp + c, (int)gridDim.x, (int64_t)C);
     out[c] = accumulate ? out[c] + t : t;
   }
   if (threadIdx.x == 0) tickets[blockIdx.y] = 0;

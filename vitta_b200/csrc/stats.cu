@@ -47,20 +47,30 @@ __global__ void __launch_bounds__(kThreads) stats_cl_kernel(const float* __restr
       d = v.z - k.z; s1.z += d; s2.z = fmaf(d, d, s2.z);
       d = v.w - k.w; s1.w += d; s2.w = fmaf(d, d, s2.w);
     };
-    // explicit batches of 8 rows: all eight 16-byte loads are issued before the first use (a dynamic-trip-count loop keeps
-    // one load in flight per thread, see bn_act.cu)
-    constexpr int kB = 8;
+    // batches of 4 rows, software-pipelined over two register sets: the loads of batch i+1 are in flight while batch i is
+    // accumulated (a dynamic-trip-count loop keeps one load in flight per thread, see bn_act.cu); rows past the chunk's
+    // end are predicated off
+    constexpr int kB = 4;
     const int64_t rstep = (int64_t)rs * C;
-    int r = slot;
-    for (; r + (kB - 1) * rs < nrows; r += kB * rs) {
-      const float* q = base + (int64_t)r * C;
-      float4 v[kB];
+    auto load = [&](int r0, float4* v) {
 #pragma unroll
-      for (int j = 0; j < kB; ++j) v[j] = ld_stream4(q + j * rstep);
+      for (int j = 0; j < kB; ++j)
+        if (r0 + j * rs < nrows) v[j] = ld_stream4(base + (int64_t)r0 * C + j * rstep);
+    };
+    auto proc = [&](int r0, const float4* v) {
 #pragma unroll
-      for (int j = 0; j < kB; ++j) acc(v[j]);
+      for (int j = 0; j < kB; ++j)
+        if (r0 + j * rs < nrows) acc(v[j]);
+    };
+    float4 va[kB], vb[kB];
+    const int bstep = kB * rs;
+    load(slot, va);
+    for (int r0 = slot; r0 < nrows; r0 += 2 * bstep) {
+      load(r0 + bstep, vb);
+      proc(r0, va);
+      load(r0 + 2 * bstep, va);
+      proc(r0 + bstep, vb);
     }
-    for (; r < nrows; r += rs) acc(ld_stream4(base + (int64_t)r * C));
   }
   sm1[tid] = s1;
   sm2[tid] = s2;

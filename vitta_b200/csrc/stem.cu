@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __re
   __threadfence();
   for (int i = threadIdx.x; i < 2 * C; i += 256) {
     const int r = i / C, cc = i % C;
-    float s = 0.f;
-    for (unsigned bI = 0; bI < gridDim.x; ++bI) s += __ldcg(ws + ((int64_t)bI * 2 + r) * C + cc);
+    const float s = ordered_sum_strided(ws + (int64_t)r * C + cc, (int)gridDim.x, 2 * (int64_t)C);
     (r == 0 ? gw : gb)[cc] = s;
   }
   if (threadIdx.x == 0) *ticket = 0;
