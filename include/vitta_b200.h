@@ -186,9 +186,13 @@ int vitta_tam_fwd_amax(const float* x, const float* kern, const float* act, floa
 int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const float* act, float* gx, float* dpart,
                   int N, int T, int64_t HW, int C, void* stream);
 /* After vitta_tam_bwd: sums dpart over its row chunks (fixed order) and contracts it with act / kern:
- *   gkern[n,k,c] = sum_t act[n,t,c] * D[n,t,k,c],  gact[n,t,c] = sum_k kern[n,k,c] * D[n,t,k,c]. */
-int vitta_tam_bwd_finish(const float* dpart, const float* kern, const float* act, float* gkern, float* gact, int N, int T,
-                         int nch, int C, void* stream);
+ *   gkern[n,k,c] = sum_t act[n,t,c] * D[n,t,k,c],  gact[n,t,c] = sum_k kern[n,k,c] * D[n,t,k,c].
+ * One launch, parallel over (channel tile, frame, video) x 8 chunk slices; dpart is consumed (its chunk-0 slots are
+ * reused as scratch for act * D); tickets: vitta_tam_bwd_finish_tickets() ints, zeroed once by the caller (every launch
+ * leaves them at zero), one per (video, tile of 128 channels) -- the last frame-CTA of a pair adds over the frames. */
+int vitta_tam_bwd_finish_tickets(void);
+int vitta_tam_bwd_finish(float* dpart, const float* kern, const float* act, float* gkern, float* gact, int* tickets, int N,
+                         int T, int nch, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 prediction consistency, forward + gradient in one launch.  preds (B, V, K) logits.
@@ -222,16 +226,17 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
  *   L: act[n, t, :]  = sigmoid(Wb . relu(BN2(conv1d_k3_pad1(Wa, p)[n, t, :])))   Wa (C/4, C, 3), Wb (C, C/4) -> (N, T, C)
  *   fwd also writes pre (N*T, C/4), the L hidden layer before BN2 (saved for the backward).
  *   bwd: given gkern, gact returns gp (N, T, C) and the gradients of W1, BN1 (w, b), W2, Wa, BN2 (w, b), Wb (assigned);
- *        gz (N*T, C), gpre / ghm (N*T, C/4) are scratch; ws: vitta_tam_gate_bwd_ws_floats floats, zeroed once by the caller.
- *   T <= 16, C % 4 == 0; every reduction runs in a fixed order. */
+ *        gpre / ghm (N*T, C/4) are scratch; ws: vitta_tam_gate_bwd_ws_floats floats, zeroed once by the caller.
+ *   T <= 16, C % 4 == 0, p and Wa 16-byte aligned; every reduction runs in a fixed order.
+ *   Launches: 2 forward (L hidden layer | G branch;  L output layer) and 2 backward (G branch | dWb | hidden-layer
+ *   gradient;  dWa | gradient of p | BN2 gradients): stages whose inputs are ready run as CTA roles of one grid. */
 int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
                        const float* Wb, float* kern, float* act, float* pre, int N, int T, int C, void* stream);
 int64_t vitta_tam_gate_bwd_ws_floats(int N, int T, int C);
 int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
                        const float* Wb, const float* act, const float* pre, const float* gkern, const float* gact,
                        float* gp, float* gW1, float* gbn1w, float* gbn1b, float* gW2, float* gWa, float* gbn2w,
-                       float* gbn2b, float* gWb, float* gz, float* gpre, float* ghm, float* ws, int N, int T, int C,
-                       void* stream);
+                       float* gbn2b, float* gWb, float* gpre, float* ghm, float* ws, int N, int T, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stem of the ResNet-50 trunk (reference models/tanet_models/tanet.py:129: torchvision conv1 7x7/2 pad 3 on the 3-channel

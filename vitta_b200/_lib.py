@@ -73,7 +73,8 @@ _SIGNATURES = {
     "vitta_tam_fwd_amax": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "vitta_tam_num_chunks": (C.c_int, [C.c_int64, C.c_int]),
     "vitta_tam_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),
-    "vitta_tam_bwd_finish": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_tam_bwd_finish_tickets": (C.c_int, []),
+    "vitta_tam_bwd_finish": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_pred_consis": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vitta_gemm_set_operand_form": (C.c_int, [C.c_int]),
     "vitta_gemm_set_cta_pair": (C.c_int, [C.c_int]),
@@ -139,7 +140,7 @@ _SIGNATURES = {
                                                C.c_int, C.c_int, _P, _P]),
     "vitta_tam_gate_fwd": (C.c_int, [_P, _P, VittaBN, _P, _P, VittaBN, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_tam_gate_bwd_ws_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
-    "vitta_tam_gate_bwd": (C.c_int, [_P, _P, VittaBN, _P, _P, VittaBN, _P] + [_P] * 17 + [C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_tam_gate_bwd": (C.c_int, [_P, _P, VittaBN, _P, _P, VittaBN, _P] + [_P] * 16 + [C.c_int, C.c_int, C.c_int, _P]),
     "vitta_stem_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_stem_pack_weight": (C.c_int, [_P, _P, _P, _P]),
     "vitta_stem_conv_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -148,58 +148,90 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
 
 // After tam_bwd_kernel: D[n, t, k, c] = sum over the row chunks of dpart (fixed order), then
 //   gkern[n, k, c] = sum_t act[n, t, c] * D[n, t, k, c]        gact[n, t, c] = sum_k kern[n, k, c] * D[n, t, k, c]
-// (three eager reductions / products per TAM before).  CTA = (video, tile of <= 32 channel quads) x T frames: thread
-// (t, quad) sums its chunks four at a time, writes gact and leaves act * D in shared memory; the threads of frame 0 add
-// those over t in frame order.
+// (three eager reductions / products per TAM before).  CTA = (channel tile of <= 32 quads, frame, video) x 8 chunk
+// slices: a slice adds every 8th chunk, five chunks (15 x 16 bytes) in flight per thread; the slices are added in slice
+// order through shared memory; slice 0 writes gact and parks act * D in the frame's chunk-0 slot of dpart (already
+// consumed, and read by no other CTA).  The last CTA of a (video, channel tile) to arrive -- one ticket per pair, left
+// at zero again -- adds those over the frames in frame order.  (Round 2's first version walked all chunks of all frames
+// in ONE CTA per (video, tile): 8-32 CTAs, up to 19 dependent L2 round trips, 32 us per TAM.)
 constexpr int kTamFinMaxT = 16;
+constexpr int kTamFinSlices = 8;
 
-__global__ void __launch_bounds__(512) tam_bwd_finish_kernel(const float* __restrict__ dpart,
-                                                            const float* __restrict__ kern,
-                                                            const float* __restrict__ act, float* __restrict__ gkern,
-                                                            float* __restrict__ gact, int N, int T, int nch, int C4) {
-  __shared__ float4 sg[3][kTamFinMaxT][32];
-  const int lane = threadIdx.x, t = threadIdx.y;
-  const int n = blockIdx.x, c4 = blockIdx.y * 32 + lane;
+__global__ void __launch_bounds__(32 * kTamFinSlices) tam_bwd_finish_kernel(float* __restrict__ dpart,
+                                                                           const float* __restrict__ kern,
+                                                                           const float* __restrict__ act,
+                                                                           float* __restrict__ gkern,
+                                                                           float* __restrict__ gact, int* tickets, int N,
+                                                                           int T, int nch, int C4) {
+  __shared__ float4 sd[kTamFinSlices][3][32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x, s = threadIdx.y;
+  const int t = blockIdx.y, n = blockIdx.z, c4 = blockIdx.x * 32 + lane;
   const int C = C4 * 4, c = c4 * 4;
   const bool on = c4 < C4;
-  float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 d[3] = {z, z, z};
   if (on) {
-    for (int ch0 = 0; ch0 < nch; ch0 += 4) {
-      float4 v[4][3];
+    constexpr int kB = 5;
+    for (int ch0 = s; ch0 < nch; ch0 += kB * kTamFinSlices) {
+      float4 v[kB][3];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool ok = ch0 + u < nch;
-        const float* q = dpart + ((((int64_t)n * nch + (ok ? ch0 + u : 0)) * T + t) * 3) * C + c;
+      for (int u = 0; u < kB; ++u) {
+        const int ch = ch0 + u * kTamFinSlices;
+        const bool ok = ch < nch;
+        const float* q = dpart + ((((int64_t)n * nch + (ok ? ch : 0)) * T + t) * 3) * C + c;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) v[u][k] = ok ? ldg4(q + (int64_t)k * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) v[u][k] = ok ? __ldcg(reinterpret_cast<const float4*>(q + (int64_t)k * C)) : z;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        d0.x += v[u][0].x; d0.y += v[u][0].y; d0.z += v[u][0].z; d0.w += v[u][0].w;
-        d1.x += v[u][1].x; d1.y += v[u][1].y; d1.z += v[u][1].z; d1.w += v[u][1].w;
-        d2.x += v[u][2].x; d2.y += v[u][2].y; d2.z += v[u][2].z; d2.w += v[u][2].w;
-      }
+      for (int u = 0; u < kB; ++u)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          d[k].x += v[u][k].x; d[k].y += v[u][k].y; d[k].z += v[u][k].z; d[k].w += v[u][k].w;
+        }
     }
-    const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c), k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c),
-                 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
-    float4 ga = mul4(k0, d0);
-    ga = fma4(k1, d1, ga);
-    ga = fma4(k2, d2, ga);
-    st4(gact + ((int64_t)n * T + t) * C + c, ga);
-    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
-    sg[0][t][lane] = mul4(a, d0);
-    sg[1][t][lane] = mul4(a, d1);
-    sg[2][t][lane] = mul4(a, d2);
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sd[s][k][lane] = d[k];
   __syncthreads();
-  if (on && t < 3) {      // frame-threads 0..2 each own one tap k = t
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int tt = 0; tt < T; ++tt) {
-      const float4 v = sg[t][tt][lane];
+  if (on && s < 3) {      // slice-threads 0..2 each own one tap k = s: total over the slices, in slice order
+    float4 g = z;
+#pragma unroll
+    for (int q = 0; q < kTamFinSlices; ++q) {
+      const float4 v = sd[q][s][lane];
       g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
-    st4(gkern + ((int64_t)n * 3 + t) * C + c, g);
+    sd[0][s][lane] = g;       // only this thread reads sd[*][s][lane] in the loop above
+    const float4 a = ldg4(act + ((int64_t)n * T + t) * C + c);
+    st4(dpart + ((((int64_t)n * nch) * T + t) * 3 + s) * C + c, mul4(a, g));
   }
+  __syncthreads();
+  if (on && s == 0) {
+    const float4 k0 = ldg4(kern + ((int64_t)n * 3 + 0) * C + c), k1 = ldg4(kern + ((int64_t)n * 3 + 1) * C + c),
+                 k2 = ldg4(kern + ((int64_t)n * 3 + 2) * C + c);
+    float4 ga = mul4(k0, sd[0][0][lane]);
+    ga = fma4(k1, sd[0][1][lane], ga);
+    ga = fma4(k2, sd[0][2][lane], ga);
+    st4(gact + ((int64_t)n * T + t) * C + c, ga);
+  }
+  __threadfence();
+  __syncthreads();
+  int* ticket = tickets + n * gridDim.x + blockIdx.x;
+  if (lane == 0 && s == 0) s_last = (atomicAdd(ticket, 1) == T - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (on && s < 3) {
+    float4 v[kTamFinMaxT];
+#pragma unroll
+    for (int tt = 0; tt < kTamFinMaxT; ++tt)
+      v[tt] = tt < T ? __ldcg(reinterpret_cast<const float4*>(dpart + ((((int64_t)n * nch) * T + tt) * 3 + s) * C + c)) : z;
+    float4 g = z;
+#pragma unroll
+    for (int tt = 0; tt < kTamFinMaxT; ++tt) { g.x += v[tt].x; g.y += v[tt].y; g.z += v[tt].z; g.w += v[tt].w; }
+    st4(gkern + ((int64_t)n * 3 + s) * C + c, g);
+  }
+  if (lane == 0 && s == 0) *ticket = 0;
 }
 
 }  // namespace vitta
@@ -259,18 +291,24 @@ int vitta_tam_bwd(const float* gout, const float* x, const float* kern, const fl
   return 0;
 }
 
-int vitta_tam_bwd_finish(const float* dpart, const float* kern, const float* act, float* gkern, float* gact, int N, int T,
-                         int nch, int C, void* stream) {
-  VITTA_CHECK_ARG(dpart && kern && act && gkern && gact, VITTA_E_BADARG, "tam_bwd_finish: null pointer");
+int vitta_tam_bwd_finish(float* dpart, const float* kern, const float* act, float* gkern, float* gact, int* tickets, int N,
+                         int T, int nch, int C, void* stream) {
+  VITTA_CHECK_ARG(dpart && kern && act && gkern && gact && tickets, VITTA_E_BADARG, "tam_bwd_finish: null pointer");
   VITTA_CHECK_ARG(N > 0 && T > 0 && nch > 0 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "tam_bwd_finish: bad shape");
   VITTA_CHECK_ARG(aligned16(dpart) && aligned16(kern) && aligned16(act) && aligned16(gkern) && aligned16(gact), VITTA_E_ALIGN,
                   "tam_bwd_finish: tensors must be 16-byte aligned");
   VITTA_CHECK_ARG(T >= 3 && T <= kTamFinMaxT, VITTA_E_UNSUPPORTED, "tam_bwd_finish: 3 <= T <= 16");
   const int C4 = C / 4;
-  dim3 block(32, (unsigned)T), grid((unsigned)N, (unsigned)((C4 + 31) / 32));
-  tam_bwd_finish_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dpart, kern, act, gkern, gact, N, T, nch, C4);
+  const int ctiles = (C4 + 31) / 32;
+  VITTA_CHECK_ARG((int64_t)N * ctiles <= vitta_tam_bwd_finish_tickets(), VITTA_E_UNSUPPORTED,
+                  "tam_bwd_finish: more (video, channel tile) pairs than tickets");
+  VITTA_CHECK_ARG(N <= 65535, VITTA_E_UNSUPPORTED, "tam_bwd_finish: grid too large");
+  dim3 block(32, kTamFinSlices), grid((unsigned)ctiles, (unsigned)T, (unsigned)N);
+  tam_bwd_finish_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dpart, kern, act, gkern, gact, tickets, N, T, nch, C4);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
+
+int vitta_tam_bwd_finish_tickets(void) { return 4096; }
 
 }  // extern "C"

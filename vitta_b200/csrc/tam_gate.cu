@@ -3,25 +3,44 @@
 //   G (global branch): per (video, channel)   softmax( W2 . relu(BN1d( W1 . p[n, :, c] )) )            -> kern (N, 3, C)
 //   L (local branch):  per (video, frame)     sigmoid( Wb . relu(BN1d( conv1d_k3(Wa, p)[n, t, :] )) )   -> act  (N, T, C)
 // with the BatchNorm1d layers in eval mode.  In eager PyTorch this is ~20 tiny kernels forward and ~25 backward per TAM
-// (cutlass simt sgemm, ATen batch-norm / elementwise / reduce kernels: 16 TAMs -> ~700 launches per step); here it is
-// 3 launches forward and 8 backward (tam_bwd_finish of tam.cu included).  Everything is L2-resident (p is N*T*C <= 64 K floats, the largest weight 786 KB),
-// so the kernels are latency-bound; a generic 32x32-tile fp32 GEMM with stage-specific operand loaders and epilogues does
-// the L branch, one thread per (video, channel) does the G branch.  All reductions run in a fixed order (deterministic).
+// (cutlass simt sgemm, ATen batch-norm / elementwise / reduce kernels: 16 TAMs -> ~700 launches per step).
+//
+// Everything is L2-resident (p is N*T*C <= 64 K floats, the largest weight 786 KB), so the cost is the NUMBER of dependent
+// launches times their latency, not bytes or flops.  The work is therefore grouped by data dependence only -- every launch
+// runs all the stages whose inputs are ready as different CTA "roles" of one grid:
+//   forward   launch 1: L hidden layer (K = 3C)  |  G branch                              launch 2: L output layer
+//   backward  launch 1: G branch (+ its parameter gradients)  |  dWb  |  gradient at the hidden layer
+//             launch 2: dWa  |  gradient of p (L part, added to the G part)  |  BatchNorm1d(L) parameter gradients
+// (3 + 7 launches before: the ncu launch list of round 2 had 62 us forward and 134 us backward per TAM, with 8-64 CTAs
+// per launch.)  Inside the stages: the eval-mode BatchNorm constants are folded once per thread / CTA (an IEEE sqrt and
+// divide per element and hidden unit dominated the per-column G code), every operand tile is loaded along its contiguous
+// dimension, and the next K step's loads are in flight while the current one is multiplied.  All reductions run in a
+// fixed order (deterministic).
 #include "common.cuh"
 
 namespace vitta {
 
 constexpr int kGateMaxT = 16;
+constexpr int kGateThreads = 256;
 
 struct GateBN {
   const float *w, *b, *rm, *rv;
   float eps;
 };
 
-__device__ __forceinline__ float gate_bn_k(const GateBN& bn, int i) { return __ldg(bn.w + i) * (1.f / sqrtf(__ldg(bn.rv + i) + bn.eps)); }
-__device__ __forceinline__ float gate_bn_apply(const GateBN& bn, int i, float x) {
-  return fmaf(x - __ldg(bn.rm + i), gate_bn_k(bn, i), __ldg(bn.b + i));
+// folded eval-mode BatchNorm of unit i:  y = (x - rm) * k + b,  k = w / sqrt(rv + eps)
+struct BNc {
+  float rm, k, b, istd;
+};
+__device__ __forceinline__ BNc gate_bn_load(const GateBN& bn, int i) {
+  BNc c;
+  c.istd = 1.f / sqrtf(__ldg(bn.rv + i) + bn.eps);
+  c.rm = __ldg(bn.rm + i);
+  c.k = __ldg(bn.w + i) * c.istd;
+  c.b = __ldg(bn.b + i);
+  return c;
 }
+__device__ __forceinline__ float gate_bn_apply(const BNc& c, float x) { return fmaf(x - c.rm, c.k, c.b); }
 
 struct GateArgs {
   const float* p;        // (N, T, C)
@@ -32,7 +51,7 @@ struct GateArgs {
   float* pre;            // (N*T, C/4): L hidden layer before its BatchNorm
   // backward
   const float *gkern, *gact;
-  float *gz, *gpre, *ghm;     // (N*T, C), (N*T, C/4), (N*T, C/4)
+  float *gpre, *ghm;          // (N*T, C/4), (N*T, C/4)
   float *gp;                  // (N, T, C): gradient of p (G part written first, L part added)
   float *gW1, *gW2, *gbn1w, *gbn1b, *gWa, *gWb, *gbn2w, *gbn2b;
   float* ws;                  // G-branch per-CTA partials + ticket
@@ -42,26 +61,35 @@ struct GateArgs {
 // ------------------------------------------------------------------------------------------------
 // G branch
 // ------------------------------------------------------------------------------------------------
-constexpr int kGThreads = 128;
+// shared memory of the G roles (floats): W1 [2T*T] | W2 [3*2T] | BN1 rm, k, b, istd [4][2T]
+__device__ __forceinline__ void g_stage_params(const GateArgs& a, float* sW1, float* sW2, float* sbn) {
+  const int T = a.T, H = 2 * T;
+  for (int i = threadIdx.x; i < H * T; i += kGateThreads) sW1[i] = __ldg(a.W1 + i);
+  for (int i = threadIdx.x; i < 3 * H; i += kGateThreads) sW2[i] = __ldg(a.W2 + i);
+  if ((int)threadIdx.x < H) {
+    const BNc c = gate_bn_load(a.bn1, threadIdx.x);
+    sbn[threadIdx.x] = c.rm;
+    sbn[H + threadIdx.x] = c.k;
+    sbn[2 * H + threadIdx.x] = c.b;
+    sbn[3 * H + threadIdx.x] = c.istd;
+  }
+}
 
-// recompute the forward of one (n, c) column; returns softmax s[3]; fills v[T], hb[2T] (BN output, pre-ReLU)
-__device__ __forceinline__ void g_forward(const GateArgs& a, const float* sW1, const float* sW2, int n, int c, float* v,
-                                          float* hb, float* s) {
-  const int T = a.T, H = 2 * a.T;
-#pragma unroll
-  for (int t = 0; t < kGateMaxT; ++t) v[t] = (t < T) ? __ldg(a.p + ((int64_t)n * T + t) * a.C + c) : 0.f;
+// forward of one (n, c) column: hp[j] = W1[j] . v (pre-BN), softmax s[3]
+__device__ __forceinline__ void g_forward(int T, const float* sW1, const float* sW2, const float* sbn, const float* v,
+                                          float* hp, float* s) {
+  const int H = 2 * T;
   float z[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 2 * kGateMaxT; ++j) {
-    hb[j] = 0.f;
+    hp[j] = 0.f;
     if (j < H) {
       float h = 0.f;
 #pragma unroll
       for (int t = 0; t < kGateMaxT; ++t)
         if (t < T) h = fmaf(sW1[j * T + t], v[t], h);
-      h = gate_bn_apply(a.bn1, j, h);
-      hb[j] = h;
-      const float r = fmaxf(h, 0.f);
+      hp[j] = h;
+      const float r = fmaxf(fmaf(h - sbn[j], sbn[H + j], sbn[2 * H + j]), 0.f);
       z[0] = fmaf(sW2[j], r, z[0]);
       z[1] = fmaf(sW2[H + j], r, z[1]);
       z[2] = fmaf(sW2[2 * H + j], r, z[2]);
@@ -73,130 +101,120 @@ __device__ __forceinline__ void g_forward(const GateArgs& a, const float* sW1, c
   s[0] = e0 * inv; s[1] = e1 * inv; s[2] = e2 * inv;
 }
 
-__global__ void __launch_bounds__(kGThreads) tam_g_fwd_kernel(GateArgs a) {
-  __shared__ float sW1[2 * kGateMaxT * kGateMaxT], sW2[3 * 2 * kGateMaxT];
+__device__ __forceinline__ void g_load_column(const GateArgs& a, int n, int c, bool live, float* v) {
+#pragma unroll
+  for (int t = 0; t < kGateMaxT; ++t) v[t] = (live && t < a.T) ? __ldg(a.p + ((int64_t)n * a.T + t) * a.C + c) : 0.f;
+}
+
+// forward role: CTA = 256 columns
+__device__ __forceinline__ void g_fwd_role(const GateArgs& a, int cta, float* sm) {
   const int T = a.T, H = 2 * T;
-  for (int i = threadIdx.x; i < H * T; i += kGThreads) sW1[i] = __ldg(a.W1 + i);
-  for (int i = threadIdx.x; i < 3 * H; i += kGThreads) sW2[i] = __ldg(a.W2 + i);
+  float *sW1 = sm, *sW2 = sW1 + H * T, *sbn = sW2 + 3 * H;
+  g_stage_params(a, sW1, sW2, sbn);
   __syncthreads();
-  const int idx = blockIdx.x * kGThreads + threadIdx.x;
+  const int idx = cta * kGateThreads + threadIdx.x;
   if (idx >= a.N * a.C) return;
   const int n = idx / a.C, c = idx % a.C;
-  float v[kGateMaxT], hb[2 * kGateMaxT], s[3];
-  g_forward(a, sW1, sW2, n, c, v, hb, s);
+  float v[kGateMaxT], hp[2 * kGateMaxT], s[3];
+  g_load_column(a, n, c, true, v);
+  g_forward(T, sW1, sW2, sbn, v, hp, s);
   a.kern[((int64_t)n * 3 + 0) * a.C + c] = s[0];
   a.kern[((int64_t)n * 3 + 1) * a.C + c] = s[1];
   a.kern[((int64_t)n * 3 + 2) * a.C + c] = s[2];
 }
 
-// per-thread backward + CTA-level reduction of the parameter gradients through shared memory, per-CTA partials to the
-// workspace, the last CTA adds them in CTA order.  Partial layout per CTA: gW1 [2T*T] | gW2 [3*2T] | gbn_w [2T] | gbn_b [2T]
-__global__ void __launch_bounds__(kGThreads) tam_g_bwd_kernel(GateArgs a, int n_part) {
-  extern __shared__ float sm[];
+// backward role: CTA = kGCols columns (warps 0-3, one column per thread), all 8 warps reduce.
+// Partial layout per CTA: gW1 [2T*T] | gW2 [3*2T] | gbn_w [2T] | gbn_b [2T]; the last CTA adds the partials in CTA order.
+constexpr int kGCols = 128;
+__host__ __device__ constexpr int g_part_floats(int T) { return 2 * T * T + 3 * 2 * T + 2 * 2 * T; }
+__host__ __device__ constexpr int g_small_floats(int T) { return 3 * 2 * T + 2 * 2 * T; }
+__host__ __device__ constexpr int g_bwd_smem_floats(int T) {
+  return 2 * T * T + 3 * 2 * T + 4 * 2 * T + kGCols * (2 * T + 1) + kGCols * (T + 1) + 4 * g_small_floats(T);
+}
+
+__device__ __forceinline__ void g_bwd_role(const GateArgs& a, int cta, int n_ctas, float* sm) {
   __shared__ int s_last;
   const int T = a.T, H = 2 * T;
-  float* sW1 = sm;                         // H*T
-  float* sW2 = sW1 + H * T;                // 3*H
-  float* sv = sW2 + 3 * H;                 // [kGThreads][T]
-  float* sg = sv + kGThreads * T;          // [kGThreads][H]   gh_pre
-  float* sr = sg + kGThreads * H;          // [kGThreads][H]   relu(hb)
-  float* sb = sr + kGThreads * H;          // [kGThreads][H]   ghb (gradient at the BN output)
-  float* sx = sb + kGThreads * H;          // [kGThreads][H]   xhat
-  float* sz = sx + kGThreads * H;          // [kGThreads][3]   gz
-  for (int i = threadIdx.x; i < H * T; i += kGThreads) sW1[i] = __ldg(a.W1 + i);
-  for (int i = threadIdx.x; i < 3 * H; i += kGThreads) sW2[i] = __ldg(a.W2 + i);
+  const int n_part = g_part_floats(T), n_small = g_small_floats(T);
+  float* sW1 = sm;                          // H*T
+  float* sW2 = sW1 + H * T;                 // 3*H
+  float* sbn = sW2 + 3 * H;                 // 4*H
+  float* sg = sbn + 4 * H;                  // [kGCols][H + 1]   gradient at the hidden layer before its BatchNorm
+  float* sv = sg + kGCols * (H + 1);        // [kGCols][T + 1]   the column
+  float* sred = sv + kGCols * (T + 1);      // [4][n_small]      per-warp sums of the small parameter gradients
+  g_stage_params(a, sW1, sW2, sbn);
   __syncthreads();
-  const int idx = blockIdx.x * kGThreads + threadIdx.x;
-  const bool live = idx < a.N * a.C;
-  const int tid = threadIdx.x;
-  {
-    float v[kGateMaxT], hb[2 * kGateMaxT], s[3];
-    float gz[3] = {0.f, 0.f, 0.f};
-    int n = 0, c = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp < kGCols / 32) {
+    const int idx = cta * kGCols + tid;
+    const bool live = idx < a.N * a.C;
+    const int n = live ? idx / a.C : 0, c = live ? idx % a.C : 0;
+    float v[kGateMaxT], hp[2 * kGateMaxT], s[3], gz[3] = {0.f, 0.f, 0.f};
+    g_load_column(a, n, c, live, v);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (live) {
-      n = idx / a.C; c = idx % a.C;
-      g_forward(a, sW1, sW2, n, c, v, hb, s);
-      const float g0 = __ldg(a.gkern + ((int64_t)n * 3 + 0) * a.C + c), g1 = __ldg(a.gkern + ((int64_t)n * 3 + 1) * a.C + c),
-                  g2 = __ldg(a.gkern + ((int64_t)n * 3 + 2) * a.C + c);
+      g0 = __ldg(a.gkern + ((int64_t)n * 3 + 0) * a.C + c);
+      g1 = __ldg(a.gkern + ((int64_t)n * 3 + 1) * a.C + c);
+      g2 = __ldg(a.gkern + ((int64_t)n * 3 + 2) * a.C + c);
+    }
+    g_forward(T, sW1, sW2, sbn, v, hp, s);
+    if (live) {
       const float dot = g0 * s[0] + g1 * s[1] + g2 * s[2];
       gz[0] = s[0] * (g0 - dot); gz[1] = s[1] * (g1 - dot); gz[2] = s[2] * (g2 - dot);
-    } else {
-#pragma unroll
-      for (int t = 0; t < kGateMaxT; ++t) v[t] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 2 * kGateMaxT; ++j) hb[j] = 0.f;
     }
     float gv[kGateMaxT];
 #pragma unroll
     for (int t = 0; t < kGateMaxT; ++t) gv[t] = 0.f;
+    float* red = sred + warp * n_small;
 #pragma unroll
     for (int j = 0; j < 2 * kGateMaxT; ++j) {
       if (j < H) {
+        const float hb = fmaf(hp[j] - sbn[j], sbn[H + j], sbn[2 * H + j]);
+        const float r = fmaxf(hb, 0.f);
         const float ghr = sW2[j] * gz[0] + sW2[H + j] * gz[1] + sW2[2 * H + j] * gz[2];
-        const float ghb = (live && hb[j] > 0.f) ? ghr : 0.f;
-        const float k1 = gate_bn_k(a.bn1, j);
-        const float ghp = ghb * k1;
-        // xhat from the recomputed pre-BN value (dividing (hb - beta) by gamma would fail for gamma == 0)
-        float hp = 0.f;
-#pragma unroll
-        for (int t = 0; t < kGateMaxT; ++t)
-          if (t < T) hp = fmaf(sW1[j * T + t], v[t], hp);
-        const float xh = (hp - __ldg(a.bn1.rm + j)) * (1.f / sqrtf(__ldg(a.bn1.rv + j) + a.bn1.eps));
-        sg[tid * H + j] = ghp;
-        sr[tid * H + j] = live ? fmaxf(hb[j], 0.f) : 0.f;
-        sb[tid * H + j] = ghb;
-        sx[tid * H + j] = xh;
+        const float ghb = hb > 0.f ? ghr : 0.f;       // gz == 0 on dead columns
+        const float ghp = ghb * sbn[H + j];
+        const float xh = (hp[j] - sbn[j]) * sbn[3 * H + j];
+        sg[tid * (H + 1) + j] = ghp;
 #pragma unroll
         for (int t = 0; t < kGateMaxT; ++t)
           if (t < T) gv[t] = fmaf(sW1[j * T + t], ghp, gv[t]);
+        // small parameter gradients: sums over the warp's 32 columns (lane order of the butterfly is fixed)
+        const float w0 = warp_sum(gz[0] * r), w1 = warp_sum(gz[1] * r), w2 = warp_sum(gz[2] * r);
+        const float bw = warp_sum(ghb * xh), bb = warp_sum(ghb);
+        if (lane == 0) {
+          red[j] = w0; red[H + j] = w1; red[2 * H + j] = w2;
+          red[3 * H + j] = bw; red[4 * H + j] = bb;
+        }
       }
     }
 #pragma unroll
     for (int t = 0; t < kGateMaxT; ++t)
       if (t < T) {
-        sv[tid * T + t] = v[t];
+        sv[tid * (T + 1) + t] = v[t];
         if (live) a.gp[((int64_t)n * T + t) * a.C + c] = gv[t];
       }
-    sz[tid * 3 + 0] = gz[0]; sz[tid * 3 + 1] = gz[1]; sz[tid * 3 + 2] = gz[2];
   }
   __syncthreads();
-  // CTA partial of every parameter gradient: output o summed over the CTA's threads in thread order
-  float* part = a.ws + (int64_t)blockIdx.x * n_part;
-  for (int o = tid; o < n_part; o += kGThreads) {
+  // CTA partial of every parameter gradient
+  float* part = a.ws + (int64_t)cta * n_part;
+  for (int o = tid; o < H * T; o += kGateThreads) {      // gW1[j][t] = sum_q ghp[q][j] * v[q][t], q in column order
+    const int j = o / T, t = o - j * T;
     float acc = 0.f;
-    if (o < H * T) {
-      const int j = o / T, t = o % T;
-      for (int q = 0; q < kGThreads; ++q) acc = fmaf(sg[q * H + j], sv[q * T + t], acc);
-    } else if (o < H * T + 3 * H) {
-      const int k = (o - H * T) / H, j = (o - H * T) % H;
-      for (int q = 0; q < kGThreads; ++q) acc = fmaf(sz[q * 3 + k], sr[q * H + j], acc);
-    } else if (o < H * T + 4 * H) {
-      const int j = o - H * T - 3 * H;
-      for (int q = 0; q < kGThreads; ++q) acc = fmaf(sb[q * H + j], sx[q * H + j], acc);
-    } else {
-      const int j = o - H * T - 4 * H;
-      for (int q = 0; q < kGThreads; ++q) acc += sb[q * H + j];
-    }
+#pragma unroll 8
+    for (int q = 0; q < kGCols; ++q) acc = fmaf(sg[q * (H + 1) + j], sv[q * (T + 1) + t], acc);
     part[o] = acc;
   }
+  if (tid < n_small) part[H * T + tid] = (sred[tid] + sred[n_small + tid]) + (sred[2 * n_small + tid] + sred[3 * n_small + tid]);
   __threadfence();
   __syncthreads();
-  int* ticket = reinterpret_cast<int*>(a.ws + (int64_t)gridDim.x * n_part);
-  if (tid == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  int* ticket = reinterpret_cast<int*>(a.ws + (int64_t)n_ctas * n_part);
+  if (tid == 0) s_last = (atomicAdd(ticket, 1) == n_ctas - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int o = tid; o < n_part; o += kGThreads) {
-    // CTA order is kept (deterministic), but the loads go out eight at a time: a plain `acc += load` loop pays one L2
-    // round trip per CTA and output (32 CTAs x 6 outputs per thread = ~60 us of pure latency on a 512-channel TAM)
-    float acc = 0.f;
-    for (unsigned b0 = 0; b0 < gridDim.x; b0 += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (b0 + u < gridDim.x) ? __ldcg(a.ws + (int64_t)(b0 + u) * n_part + o) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc += v[u];
-    }
+  for (int o = tid; o < n_part; o += kGateThreads) {
+    const float acc = ordered_sum_strided(a.ws + o, n_ctas, n_part);
     if (o < H * T) a.gW1[o] = acc;
     else if (o < H * T + 3 * H) a.gW2[o - H * T] = acc;
     else if (o < H * T + 4 * H) a.gbn1w[o - H * T - 3 * H] = acc;
@@ -206,19 +224,118 @@ __global__ void __launch_bounds__(kGThreads) tam_g_bwd_kernel(GateArgs a, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// L branch: generic 32x32-tile GEMM  D[m, n] = sum_k A(m, k) * B(n, k)  with stage-specific loaders / epilogues
+// L branch, hidden layer (the K = 3C stage): CTA = (slice of hidden channels, video).  The video's pooled rows
+// p[n] (T x C, plus a zero row on either side for the temporal padding) are staged in shared memory once; a warp owns
+// TWO hidden channels at a time (one shared-memory read feeds both), its lanes walk the contiguous weight rows
+// Wa[o][c][j] with 128-bit loads (eight in flight per lane) and keep 2 x T accumulators, reduced across the lanes at the
+// end.  (Before: one 4-byte weight load per lane and iteration with nothing else in flight -- 35 us at C = 512.)
 // ------------------------------------------------------------------------------------------------
-enum GateStage { kL2Fwd = 1, kGradWb, kGradHid, kGradWa, kGradP };   // (the hidden layer has its own kernel, tam_l1_fwd_kernel)
+constexpr int kL1Slices = 8;
+
+__device__ __forceinline__ float f4c(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+__device__ __forceinline__ void l1_fwd_role(const GateArgs& a, int slice, int n, float* sp) {
+  const int T = a.T, C = a.C, Hc = a.C / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const int C4 = C / 4;
+    float4* sp4 = reinterpret_cast<float4*>(sp);
+    for (int i = threadIdx.x; i < (T + 2) * C4; i += kGateThreads) {
+      const int t = i / C4 - 1;
+      sp4[i] = (t >= 0 && t < T) ? ldg4(a.p + ((int64_t)n * T + t) * C + (i % C4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  const int per = (Hc + kL1Slices - 1) / kL1Slices;
+  const int o0 = slice * per, o1 = min(Hc, o0 + per);
+  const int n4 = 3 * C / 4;     // float4s per weight row
+  for (int o = o0 + 2 * warp; o < o1; o += 2 * (kGateThreads / 32)) {
+    const bool two = o + 1 < o1;
+    const float4* wr0 = reinterpret_cast<const float4*>(a.Wa + (int64_t)o * 3 * C);
+    const float4* wr1 = wr0 + (two ? n4 : 0);
+    float acc0[kGateMaxT], acc1[kGateMaxT];
+#pragma unroll
+    for (int t = 0; t < kGateMaxT; ++t) acc0[t] = acc1[t] = 0.f;
+    for (int b = 0; b < n4; b += 128) {
+      float4 wa[4], wb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = b + lane + 32 * u;
+        const bool ok = q < n4;
+        wa[u] = ok ? __ldg(wr0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wb[u] = (ok && two) ? __ldg(wr1 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e0 = 4 * (b + lane + 32 * u);
+        if (e0 < 3 * C) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = e0 + k;
+            const int c = e / 3, j = e - 3 * c;
+            const float* s = sp + j * C + c;
+            const float x0 = f4c(wa[u], k), x1 = f4c(wb[u], k);
+#pragma unroll
+            for (int t = 0; t < kGateMaxT; ++t)
+              if (t < T) {
+                const float pv = s[t * C];
+                acc0[t] = fmaf(x0, pv, acc0[t]);
+                acc1[t] = fmaf(x1, pv, acc1[t]);
+              }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kGateMaxT; ++t) {
+      if (t < T) {
+        const float v0 = warp_sum(acc0[t]), v1 = warp_sum(acc1[t]);
+        if (lane == 0) {
+          a.pre[((int64_t)n * T + t) * Hc + o] = v0;
+          if (two) a.pre[((int64_t)n * T + t) * Hc + o + 1] = v1;
+        }
+      }
+    }
+  }
+}
+
+// forward launch 1: blocks [0, kL1Slices * N) = L hidden layer, the rest = G branch
+__global__ void __launch_bounds__(kGateThreads) tam_gate_fwd1_kernel(GateArgs a) {
+  extern __shared__ __align__(16) float dsm[];
+  const int nl1 = kL1Slices * a.N;
+  if ((int)blockIdx.x < nl1) l1_fwd_role(a, blockIdx.x % kL1Slices, blockIdx.x / kL1Slices, dsm);
+  else g_fwd_role(a, blockIdx.x - nl1, dsm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// L branch: 32x32-tile GEMM  D[m, n] = sum_k A(m, k) * B(n, k)  with stage-specific loaders / epilogues
+// ------------------------------------------------------------------------------------------------
+enum GateStage { kL2Fwd = 1, kGradWb, kGradHid, kGradWa, kGradP };   // (the hidden layer has its own role, l1_fwd_role)
+
+// which index of an operand element is contiguous in memory: the K index (false) or the tile row (true).  The loader
+// threads walk that one, so a warp reads whole 128-byte lines either way.
+template <int STAGE> struct GateLayout;
+template <> struct GateLayout<kL2Fwd>   { static constexpr bool a_row = false, b_row = false; };
+template <> struct GateLayout<kGradWb>  { static constexpr bool a_row = true,  b_row = true;  };
+template <> struct GateLayout<kGradHid> { static constexpr bool a_row = false, b_row = true;  };
+template <> struct GateLayout<kGradWa>  { static constexpr bool a_row = true,  b_row = true;  };
+template <> struct GateLayout<kGradP>   { static constexpr bool a_row = false, b_row = true;  };
+
+// gradient at the output layer before the sigmoid: gz = gact * act * (1 - act) (formed on the fly: no gz pass / buffer)
+__device__ __forceinline__ float gate_gz(const GateArgs& a, int64_t i) {
+  const float s = __ldg(a.act + i);
+  return __ldg(a.gact + i) * s * (1.f - s);
+}
 
 template <int STAGE>
 __device__ __forceinline__ float gate_A(const GateArgs& a, int m, int k) {
   const int T = a.T, C = a.C, Hc = a.C / 4;
-  if (STAGE == kL2Fwd) {            // hid[m, k] = relu(bn2(pre[m, k]))
-    return fmaxf(gate_bn_apply(a.bn2, k, __ldg(a.pre + (int64_t)m * Hc + k)), 0.f);
+  if (STAGE == kL2Fwd) {            // pre[m, k]  (BatchNorm + ReLU applied by the loader: see gate_gemm_tile)
+    return __ldg(a.pre + (int64_t)m * Hc + k);
   } else if (STAGE == kGradWb) {    // m = c, k = r  ->  gz[r, c]
-    return a.gz[(int64_t)k * C + m];
+    return gate_gz(a, (int64_t)k * C + m);
   } else if (STAGE == kGradHid) {   // m = r, k = c  ->  gz[r, c]
-    return a.gz[(int64_t)m * C + k];
+    return gate_gz(a, (int64_t)m * C + k);
   } else if (STAGE == kGradWa) {    // m = o, k = r  ->  gpre[r, o]
     return a.gpre[(int64_t)k * Hc + m];
   } else {                          // kGradP: m = (n, t'), k = j*Hc + o  ->  gpre[n, t' - j + 1, o]
@@ -233,8 +350,8 @@ __device__ __forceinline__ float gate_B(const GateArgs& a, int n, int k) {
   const int T = a.T, C = a.C, Hc = a.C / 4;
   if (STAGE == kL2Fwd) {            // n = c, k = o  ->  Wb[c][o]
     return __ldg(a.Wb + (int64_t)n * Hc + k);
-  } else if (STAGE == kGradWb) {    // n = o, k = r  ->  hid[r, o]
-    return fmaxf(gate_bn_apply(a.bn2, n, __ldg(a.pre + (int64_t)k * Hc + n)), 0.f);
+  } else if (STAGE == kGradWb) {    // n = o, k = r  ->  pre[r, o]  (BatchNorm + ReLU applied by the loader)
+    return __ldg(a.pre + (int64_t)k * Hc + n);
   } else if (STAGE == kGradHid) {   // n = o, k = c  ->  Wb[c][o]
     return __ldg(a.Wb + (int64_t)k * Hc + n);
   } else if (STAGE == kGradWa) {    // n = c*3 + j, k = r = (n', t)  ->  p[n', t + j - 1, c]
@@ -254,46 +371,70 @@ __device__ __forceinline__ void gate_store(const GateArgs& a, int m, int n, floa
     a.act[(int64_t)m * C + n] = 1.f / (1.f + expf(-acc));
   } else if (STAGE == kGradWb) {
     a.gWb[(int64_t)m * Hc + n] = acc;
-  } else if (STAGE == kGradHid) {   // through ReLU and the eval-mode BatchNorm
-    const float hb = gate_bn_apply(a.bn2, n, __ldg(a.pre + (int64_t)m * Hc + n));
-    const float g = hb > 0.f ? acc : 0.f;
-    a.ghm[(int64_t)m * Hc + n] = g;
-    a.gpre[(int64_t)m * Hc + n] = g * gate_bn_k(a.bn2, n);
   } else if (STAGE == kGradWa) {
     a.gWa[(int64_t)m * 3 * C + n] = acc;
-  } else {
-    a.gp[(int64_t)m * C + n] += acc;      // the G branch wrote its part first (same stream)
+  } else if (STAGE == kGradP) {
+    a.gp[(int64_t)m * C + n] += acc;      // the G branch wrote its part first (previous launch, same stream)
   }
 }
 
-// 32 x 32 output tile per CTA (16 x 16 threads, 2 x 2 outputs each), K walked in steps of kGateBK = 128: every thread has
-// 32 independent operand loads in flight per step -- the operands are L2-resident, so the kernel is bound by L2 latency
-// times the number of K steps (a 32-wide step made the K = 3C stage of a 512-channel TAM take ~50 us).
+// 32 x 32 output tile (16 x 16 threads, 2 x 2 outputs each), K walked in steps of kGateBK = 128: every thread has 32
+// independent operand loads in flight per step, and the loads of step i+1 are issued before step i is multiplied.
 constexpr int kGateBK = 128;
+constexpr int kGateLd = kGateBK / 8;      // elements per thread, operand and step
+constexpr int kGemmSmemFloats = 2 * kGateBK * 33;
+
+template <bool ROW>
+__device__ __forceinline__ void gate_map(int i, int& kk, int& r) {
+  const int idx = threadIdx.x + i * kGateThreads;
+  if (ROW) { r = idx & 31; kk = idx >> 5; }             // thread's row fixed (tid & 31), kk = (tid >> 5) + 8 i
+  else { kk = idx % kGateBK; r = idx / kGateBK; }       // thread's kk fixed (tid & 127), r = (tid >> 7) + 2 i
+}
 
 template <int STAGE>
-__global__ void __launch_bounds__(256) tam_gate_gemm_kernel(GateArgs a, int M, int Nn, int K) {
-  __shared__ float As[kGateBK][33], Bs[kGateBK][33];
+__device__ __forceinline__ void gate_gemm_tile(const GateArgs& a, int m0, int n0, int M, int Nn, int K, float* sm) {
+  using L = GateLayout<STAGE>;
+  float (*As)[33] = reinterpret_cast<float (*)[33]>(sm);
+  float (*Bs)[33] = reinterpret_cast<float (*)[33]>(sm + kGateBK * 33);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int Hc = a.C / 4;
+  // folded BatchNorm(L) constants this thread needs: kL2Fwd -- of hidden unit k0 + (tid & 127) (reloaded per K step);
+  // kGradWb -- of hidden unit n0 + (tid & 31) (B operand rows); kGradHid -- of the two output columns of the epilogue
+  BNc bnc = {0.f, 0.f, 0.f, 0.f}, bnc2 = {0.f, 0.f, 0.f, 0.f};
+  if (STAGE == kGradWb) bnc = gate_bn_load(a.bn2, min(n0 + (int)(threadIdx.x & 31), Hc - 1));
+  if (STAGE == kGradHid) {
+    bnc = gate_bn_load(a.bn2, min(n0 + tx, Hc - 1));
+    bnc2 = gate_bn_load(a.bn2, min(n0 + tx + 16, Hc - 1));
+  }
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += kGateBK) {
-    float av[kGateBK / 8], bv[kGateBK / 8];
+  float av[kGateLd], bv[kGateLd];
+  auto load = [&](int k0) {
+    if (STAGE == kL2Fwd) bnc = gate_bn_load(a.bn2, min(k0 + (int)(threadIdx.x & 127), Hc - 1));
 #pragma unroll
-    for (int i = 0; i < kGateBK / 8; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      const int kk = idx % kGateBK, r = idx / kGateBK;
-      const int k = k0 + kk;
-      av[i] = (m0 + r < M && k < K) ? gate_A<STAGE>(a, m0 + r, k) : 0.f;
-      bv[i] = (n0 + r < Nn && k < K) ? gate_B<STAGE>(a, n0 + r, k) : 0.f;
+    for (int i = 0; i < kGateLd; ++i) {
+      int kk, r;
+      gate_map<L::a_row>(i, kk, r);
+      av[i] = (m0 + r < M && k0 + kk < K) ? gate_A<STAGE>(a, m0 + r, k0 + kk) : 0.f;
+      gate_map<L::b_row>(i, kk, r);
+      bv[i] = (n0 + r < Nn && k0 + kk < K) ? gate_B<STAGE>(a, n0 + r, k0 + kk) : 0.f;
     }
+  };
+  load(0);
+  for (int k0 = 0; k0 < K; k0 += kGateBK) {
 #pragma unroll
-    for (int i = 0; i < kGateBK / 8; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      As[idx % kGateBK][idx / kGateBK] = av[i];
-      Bs[idx % kGateBK][idx / kGateBK] = bv[i];
+    for (int i = 0; i < kGateLd; ++i) {
+      int kk, r;
+      gate_map<L::a_row>(i, kk, r);
+      float x = av[i];
+      if (STAGE == kL2Fwd) x = (m0 + r < M && k0 + kk < K) ? fmaxf(gate_bn_apply(bnc, x), 0.f) : 0.f;
+      As[kk][r] = x;
+      gate_map<L::b_row>(i, kk, r);
+      float y = bv[i];
+      if (STAGE == kGradWb) y = (n0 + r < Nn && k0 + kk < K) ? fmaxf(gate_bn_apply(bnc, y), 0.f) : 0.f;
+      Bs[kk][r] = y;
     }
     __syncthreads();
+    if (k0 + kGateBK < K) load(k0 + kGateBK);
 #pragma unroll 16
     for (int kk = 0; kk < kGateBK; ++kk) {
       const float a0 = As[kk][ty], a1 = As[kk][ty + 16], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
@@ -307,25 +448,43 @@ __global__ void __launch_bounds__(256) tam_gate_gemm_kernel(GateArgs a, int M, i
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
-      if (m < M && n < Nn) gate_store<STAGE>(a, m, n, acc[i][j]);
+      if (m < M && n < Nn) {
+        if (STAGE == kGradHid) {   // through ReLU and the eval-mode BatchNorm
+          const BNc& c = j ? bnc2 : bnc;
+          const float hb = gate_bn_apply(c, __ldg(a.pre + (int64_t)m * Hc + n));
+          const float g = hb > 0.f ? acc[i][j] : 0.f;
+          a.ghm[(int64_t)m * Hc + n] = g;
+          a.gpre[(int64_t)m * Hc + n] = g * c.k;
+        } else {
+          gate_store<STAGE>(a, m, n, acc[i][j]);
+        }
+      }
     }
 }
 
-// gz = gact * act * (1 - act)
-__global__ void __launch_bounds__(256) tam_gate_gz_kernel(GateArgs a, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const float s = __ldg(a.act + i);
-    a.gz[i] = __ldg(a.gact + i) * s * (1.f - s);
-  }
+__host__ __device__ inline int gate_tiles(int M, int Nn) { return ((M + 31) / 32) * ((Nn + 31) / 32); }
+
+// tile index -> (m0, n0), n fastest
+template <int STAGE>
+__device__ __forceinline__ void gate_gemm_role(const GateArgs& a, int tile, int M, int Nn, int K, float* sm) {
+  const int tn = (Nn + 31) / 32;
+  gate_gemm_tile<STAGE>(a, (tile / tn) * 32, (tile % tn) * 32, M, Nn, K, sm);
+}
+
+// forward launch 2: act = sigmoid(relu(BN2(pre)) . Wb^T)
+__global__ void __launch_bounds__(kGateThreads) tam_gate_fwd2_kernel(GateArgs a) {
+  __shared__ __align__(16) float sm[kGemmSmemFloats];
+  gate_gemm_role<kL2Fwd>(a, blockIdx.x, a.N * a.T, a.C, a.C / 4, sm);
 }
 
 // BatchNorm1d (eval) parameter gradients of the L branch.  CTA = 32 hidden channels x 8 row slices; a slice walks its
 // rows eight at a time (loads first), the slices are added in slice order through shared memory (deterministic).
-__global__ void __launch_bounds__(256) tam_gate_bn2_kernel(GateArgs a, int R) {
-  __shared__ float sgw[8][33], sgb[8][33];
-  const int Hc = a.C / 4;
+__device__ __forceinline__ void gate_bn2_role(const GateArgs& a, int cta, float* sm) {
+  float (*sgw)[33] = reinterpret_cast<float (*)[33]>(sm);
+  float (*sgb)[33] = reinterpret_cast<float (*)[33]>(sm + 8 * 33);
+  const int Hc = a.C / 4, R = a.N * a.T;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int o = blockIdx.x * 32 + lane;
+  const int o = cta * 32 + lane;
   float gw = 0.f, gb = 0.f;
   if (o < Hc) {
     const float rm = __ldg(a.bn2.rm + o), istd = 1.f / sqrtf(__ldg(a.bn2.rv + o) + a.bn2.eps);
@@ -358,58 +517,29 @@ __global__ void __launch_bounds__(256) tam_gate_bn2_kernel(GateArgs a, int R) {
   }
 }
 
-// L branch, hidden layer (the K = 3C stage): CTA = (slice of hidden channels, video).  The video's pooled rows
-// p[n] (T x C, plus a zero row on either side for the temporal padding) are staged in shared memory once; a warp owns
-// one hidden channel at a time, its lanes stride over the input channels of one temporal tap (conflict-free smem rows,
-// weights read once from L2) and keep T accumulators, reduced across the lanes at the end.
-constexpr int kL1Slices = 8;
-
-__global__ void __launch_bounds__(256) tam_l1_fwd_kernel(GateArgs a) {
-  extern __shared__ float sp[];   // [(T + 2)][C]
-  const int T = a.T, C = a.C, Hc = a.C / 4;
-  const int n = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (T + 2) * C; i += 256) {
-    const int t = i / C - 1;
-    sp[i] = (t >= 0 && t < T) ? __ldg(a.p + ((int64_t)n * T + t) * C + (i % C)) : 0.f;
-  }
-  __syncthreads();
-  const int per = (Hc + kL1Slices - 1) / kL1Slices;
-  const int o0 = blockIdx.x * per, o1 = min(Hc, o0 + per);
-  for (int o = o0 + warp; o < o1; o += 8) {
-    float acc[kGateMaxT];
-#pragma unroll
-    for (int t = 0; t < kGateMaxT; ++t) acc[t] = 0.f;
-    const float* wrow = a.Wa + (int64_t)o * 3 * C;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      for (int c = lane; c < C; c += 32) {
-        const float w = __ldg(wrow + c * 3 + j);
-#pragma unroll
-        for (int t = 0; t < kGateMaxT; ++t)
-          if (t < T) acc[t] = fmaf(w, sp[(t + j) * C + c], acc[t]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < kGateMaxT; ++t) {
-      if (t < T) {
-        const float v = warp_sum(acc[t]);
-        if (lane == 0) a.pre[((int64_t)n * T + t) * Hc + o] = v;
-      }
-    }
-  }
+// backward launch 1: [gradient at the hidden layer (K = C: the longest role first)] [G branch] [dWb]
+__global__ void __launch_bounds__(kGateThreads) tam_gate_bwd1_kernel(GateArgs a, int n_hid, int n_g) {
+  __shared__ __align__(16) float sm[kGemmSmemFloats];
+  static_assert(g_bwd_smem_floats(kGateMaxT) <= kGemmSmemFloats, "G backward role must fit the GEMM tile buffers");
+  const int R = a.N * a.T, Hc = a.C / 4;
+  int b = blockIdx.x;
+  if (b < n_hid) { gate_gemm_role<kGradHid>(a, b, R, Hc, a.C, sm); return; }
+  b -= n_hid;
+  if (b < n_g) { g_bwd_role(a, b, n_g, sm); return; }
+  b -= n_g;
+  gate_gemm_role<kGradWb>(a, b, a.C, Hc, R, sm);
 }
 
-template <int STAGE>
-static void launch_stage(const GateArgs& a, int M, int Nn, int K, cudaStream_t st) {
-  dim3 grid((unsigned)((Nn + 31) / 32), (unsigned)((M + 31) / 32));
-  tam_gate_gemm_kernel<STAGE><<<grid, 256, 0, st>>>(a, M, Nn, K);
-}
-
-static int g_part_floats(int T) { return 2 * T * T + 3 * 2 * T + 2 * 2 * T; }
-static size_t g_bwd_smem(int T) {
-  const int H = 2 * T;
-  return sizeof(float) * (size_t)(H * T + 3 * H + kGThreads * T + 4 * kGThreads * H + kGThreads * 3);
+// backward launch 2: [gradient of p, L part (K = 3C/4)] [dWa] [BatchNorm1d(L) parameter gradients]
+__global__ void __launch_bounds__(kGateThreads) tam_gate_bwd2_kernel(GateArgs a, int n_gp, int n_wa) {
+  __shared__ __align__(16) float sm[kGemmSmemFloats];
+  const int R = a.N * a.T, Hc = a.C / 4;
+  int b = blockIdx.x;
+  if (b < n_gp) { gate_gemm_role<kGradP>(a, b, R, a.C, 3 * Hc, sm); return; }
+  b -= n_gp;
+  if (b < n_wa) { gate_gemm_role<kGradWa>(a, b, Hc, 3 * a.C, R, sm); return; }
+  b -= n_wa;
+  gate_bn2_role(a, b, sm);
 }
 
 }  // namespace vitta
@@ -424,6 +554,8 @@ static int check_gate_shape(int N, int T, int C) {
   return 0;
 }
 
+static int g_bwd_ctas(int N, int C) { return (N * C + kGCols - 1) / kGCols; }
+
 extern "C" {
 
 int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
@@ -431,45 +563,47 @@ int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float
   VITTA_CHECK_ARG(p && W1 && W2 && Wa && Wb && kern && act && pre, VITTA_E_BADARG, "tam_gate_fwd: null pointer");
   int rc = check_gate_shape(N, T, C);
   if (rc) return rc;
+  VITTA_CHECK_ARG(aligned16(p) && aligned16(Wa), VITTA_E_ALIGN, "tam_gate_fwd: p and Wa must be 16-byte aligned");
   GateArgs a{};
   a.p = p; a.W1 = W1; a.W2 = W2; a.Wa = Wa; a.Wb = Wb; a.bn1 = to_gate_bn(bn1); a.bn2 = to_gate_bn(bn2);
   a.kern = kern; a.act = act; a.pre = pre; a.N = N; a.T = T; a.C = C;
   cudaStream_t st = (cudaStream_t)stream;
-  tam_g_fwd_kernel<<<(unsigned)((N * C + kGThreads - 1) / kGThreads), kGThreads, 0, st>>>(a);
-  VITTA_CHECK_LAUNCH();
   {
-    const size_t smem = sizeof(float) * (size_t)(T + 2) * C;
+    const int H = 2 * T;
+    size_t smem = sizeof(float) * (size_t)(T + 2) * C;
+    const size_t g_smem = sizeof(float) * (size_t)(H * T + 3 * H + 4 * H);
+    if (smem < g_smem) smem = g_smem;
     VITTA_CHECK_ARG(smem <= 200 * 1024, VITTA_E_UNSUPPORTED, "tam_gate_fwd: (T + 2) * C floats exceed shared memory");
     static size_t attr_smem = 48 * 1024;
     if (smem > attr_smem) {
-      cudaError_t e = cudaFuncSetAttribute(tam_l1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(tam_gate_fwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) {
         set_error("tam_gate_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
       }
       attr_smem = smem;
     }
-    tam_l1_fwd_kernel<<<dim3(kL1Slices, (unsigned)N), 256, smem, st>>>(a);
+    const unsigned n_g = (unsigned)((N * C + kGateThreads - 1) / kGateThreads);
+    tam_gate_fwd1_kernel<<<(unsigned)(kL1Slices * N) + n_g, kGateThreads, smem, st>>>(a);
   }
   VITTA_CHECK_LAUNCH();
-  launch_stage<kL2Fwd>(a, N * T, C, C / 4, st);
+  tam_gate_fwd2_kernel<<<(unsigned)gate_tiles(N * T, C), kGateThreads, 0, st>>>(a);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
 
 int64_t vitta_tam_gate_bwd_ws_floats(int N, int T, int C) {
   if (N <= 0 || T <= 0 || T > kGateMaxT || C <= 0) return -1;
-  const int64_t ctas = ((int64_t)N * C + kGThreads - 1) / kGThreads;
-  return ctas * g_part_floats(T) + 4;
+  return (int64_t)g_bwd_ctas(N, C) * g_part_floats(T) + 4;
 }
 
 int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,
                        const float* Wb, const float* act, const float* pre, const float* gkern, const float* gact,
                        float* gp, float* gW1, float* gbn1w, float* gbn1b, float* gW2, float* gWa, float* gbn2w,
-                       float* gbn2b, float* gWb, float* gz, float* gpre, float* ghm, float* ws, int N, int T, int C,
+                       float* gbn2b, float* gWb, float* gpre, float* ghm, float* ws, int N, int T, int C,
                        void* stream) {
   VITTA_CHECK_ARG(p && W1 && W2 && Wa && Wb && act && pre && gkern && gact && gp && gW1 && gbn1w && gbn1b && gW2 && gWa &&
-                      gbn2w && gbn2b && gWb && gz && gpre && ghm && ws,
+                      gbn2w && gbn2b && gWb && gpre && ghm && ws,
                   VITTA_E_BADARG, "tam_gate_bwd: null pointer");
   int rc = check_gate_shape(N, T, C);
   if (rc) return rc;
@@ -477,36 +611,16 @@ int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float
   a.p = p; a.W1 = W1; a.W2 = W2; a.Wa = Wa; a.Wb = Wb; a.bn1 = to_gate_bn(bn1); a.bn2 = to_gate_bn(bn2);
   a.act = const_cast<float*>(act); a.pre = const_cast<float*>(pre); a.gkern = gkern; a.gact = gact;
   a.gp = gp; a.gW1 = gW1; a.gbn1w = gbn1w; a.gbn1b = gbn1b; a.gW2 = gW2; a.gWa = gWa; a.gbn2w = gbn2w; a.gbn2b = gbn2b;
-  a.gWb = gWb; a.gz = gz; a.gpre = gpre; a.ghm = ghm; a.ws = ws; a.N = N; a.T = T; a.C = C;
+  a.gWb = gWb; a.gpre = gpre; a.ghm = ghm; a.ws = ws; a.N = N; a.T = T; a.C = C;
   cudaStream_t st = (cudaStream_t)stream;
   const int R = N * T, Hc = C / 4;
-  // G branch: writes gp (its part), gW1, gW2, gbn1w, gbn1b
-  static bool attr_done = false;
-  const size_t smem = g_bwd_smem(kGateMaxT);
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tam_g_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("tam_gate_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_done = true;
-  }
-  const unsigned g_ctas = (unsigned)((N * C + kGThreads - 1) / kGThreads);
-  tam_g_bwd_kernel<<<g_ctas, kGThreads, g_bwd_smem(T), st>>>(a, g_part_floats(T));
+  // launch 1 -- G branch: gp (its part), gW1, gW2, gbn1w, gbn1b;  L branch: gWb, ghm, gpre
+  const int n_hid = gate_tiles(R, Hc), n_g = g_bwd_ctas(N, C), n_wb = gate_tiles(C, Hc);
+  tam_gate_bwd1_kernel<<<(unsigned)(n_hid + n_g + n_wb), kGateThreads, 0, st>>>(a, n_hid, n_g);
   VITTA_CHECK_LAUNCH();
-  // L branch
-  const int64_t nz = (int64_t)R * C;
-  tam_gate_gz_kernel<<<(unsigned)((nz + 255) / 256 < 592 ? (nz + 255) / 256 : 592), 256, 0, st>>>(a, nz);
-  VITTA_CHECK_LAUNCH();
-  launch_stage<kGradWb>(a, C, Hc, R, st);
-  VITTA_CHECK_LAUNCH();
-  launch_stage<kGradHid>(a, R, Hc, C, st);
-  VITTA_CHECK_LAUNCH();
-  tam_gate_bn2_kernel<<<(unsigned)((Hc + 31) / 32), 256, 0, st>>>(a, R);
-  VITTA_CHECK_LAUNCH();
-  launch_stage<kGradWa>(a, Hc, 3 * C, R, st);
-  VITTA_CHECK_LAUNCH();
-  launch_stage<kGradP>(a, R, C, 3 * Hc, st);
+  // launch 2 -- L branch: gp += its part, gWa, gbn2w, gbn2b
+  const int n_gp = gate_tiles(R, C), n_wa = gate_tiles(Hc, 3 * C), n_bn = (Hc + 31) / 32;
+  tam_gate_bwd2_kernel<<<(unsigned)(n_gp + n_wa + n_bn), kGateThreads, 0, st>>>(a, n_gp, n_wa);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

@@ -509,27 +509,49 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   }
 }
 
-// dW (NCHW: [co][ci][tap]) (+)= sum_s ws[s][co][tap][ci], splits summed in order
+// dW (NCHW: [co][ci][tap]) (+)= sum_s ws[s][co][tap][ci], splits summed in a fixed order.
+// SLICED = false (few splits): thread = output, all its partials in flight at once (sixteen at a time).
+// SLICED = true (the small early layers have up to ~300 K splits for a few thousand outputs): CTA = 32 outputs x 8 slices;
+// a slice adds a contiguous range of splits, the slices are added in slice order through shared memory -- a thread per
+// output walking 296 partials was 19 dependent L2 round trips on 16 CTAs.
+__device__ __forceinline__ void wgrad_store(float* __restrict__ dw, int64_t i, int Cin, int taps, int accumulate, float s) {
+  const int ci = (int)(i % Cin);
+  const int64_t r = i / Cin;
+  const int tap = (int)(r % taps);
+  const int64_t co = r / taps;
+  float* d = dw + (co * Cin + ci) * taps + tap;
+  *d = accumulate ? *d + s : s;
+}
+
+template <bool SLICED>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout,
                                                           int Cin, int taps, int splits, int accumulate,
                                                           const float* __restrict__ bias_ws, float* __restrict__ dbias) {
   const int64_t n = (int64_t)Cout * taps * Cin;
   if (dbias) {   // bias gradient: the K-split partials of sum_pixels dY, in split order
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < Cout; c += gridDim.x * 256) {
-      float s = 0.f;
-      for (int k = 0; k < splits; ++k) s += __ldg(bias_ws + (int64_t)k * Cout + c);
-      dbias[c] = s;
-    }
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < Cout; c += gridDim.x * 256)
+      dbias[c] = ordered_sum_strided(bias_ws + c, splits, Cout);
   }
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += __ldg(ws + (int64_t)k * n + i);
-    const int ci = (int)(i % Cin);
-    const int64_t r = i / Cin;
-    const int tap = (int)(r % taps);
-    const int64_t co = r / taps;
-    float* d = dw + (co * Cin + ci) * taps + tap;
-    *d = accumulate ? *d + s : s;
+  if (!SLICED) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+      wgrad_store(dw, i, Cin, taps, accumulate, ordered_sum_strided(ws + i, splits, n));
+  } else {
+    __shared__ float sp[8][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int per = (splits + 7) / 8;
+    const int k0 = slice * per, k1 = min(splits, k0 + per);
+    for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < n; i0 += (int64_t)gridDim.x * 32) {
+      const int64_t i = i0 + lane;
+      sp[slice][lane] = (i < n && k1 > k0) ? ordered_sum_strided(ws + (int64_t)k0 * n + i, k1 - k0, n) : 0.f;
+      __syncthreads();
+      if (slice == 0 && i < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += sp[q][lane];
+        wgrad_store(dw, i, Cin, taps, accumulate, s);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -688,9 +710,17 @@ static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int 
                         : (pl.bn == 64) ? launch_wgrad<64, true>(tdy, tx, p, st) : launch_wgrad<128, true>(tdy, tx, p, st);
   if (rc) return rc;
   const int64_t n = (int64_t)Cout * KH * KW * Cin;
-  int64_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate, p.bias_ws, dbias);
+  if (p.splits >= 32 && n <= 148 * 8 * 256) {
+    int64_t blocks = (n + 31) / 32;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate, p.bias_ws,
+                                                                dbias);
+  } else {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(ws, dW, Cout, Cin, KH * KW, p.splits, accumulate, p.bias_ws,
+                                                                 dbias);
+  }
   VITTA_CHECK_LAUNCH();
   return 0;
 }

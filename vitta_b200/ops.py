@@ -653,6 +653,9 @@ def bn_act(x, bn, relu, res=None, res_bn=None, arena=None, ly_main=None, ly_res=
 # ----------------------------------------------------------------------------------------------
 # K5: TAM stencil
 # ----------------------------------------------------------------------------------------------
+_fin_tickets = {}      # per device: the zeroed ticket counters of vitta_tam_bwd_finish (left at zero by every launch)
+
+
 class TamStencilFn(torch.autograd.Function):
     """x (N*T, C, H, W) channels_last; kern (N, 3, C); act (N, T, C) -> out like x."""
 
@@ -689,7 +692,11 @@ class TamStencilFn(torch.autograd.Function):
         if 3 <= T <= 16:
             gkern = torch.empty_like(kern)                 # (N, 3, C)
             gact = torch.empty_like(act)                   # (N, T, C)
-            call("vitta_tam_bwd_finish", ptr(dpart), ptr(kern), ptr(act), ptr(gkern), ptr(gact), n, T, nch, Cc,
+            tk = _fin_tickets.get(x.device)
+            if tk is None:
+                tk = _fin_tickets[x.device] = torch.zeros(_lib.load().vitta_tam_bwd_finish_tickets(), dtype=torch.int32,
+                                                          device=x.device)
+            call("vitta_tam_bwd_finish", ptr(dpart), ptr(kern), ptr(act), ptr(gkern), ptr(gact), ptr(tk), n, T, nch, Cc,
                  stream_ptr())
         else:
             D = dpart.sum(1)                               # (N, T, 3, C): tiny
@@ -1365,7 +1372,7 @@ class BnReluPoolFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# K5b: the TAM's G and L gate networks (eval-mode BatchNorm1d) in 3 launches forward / 7 backward
+# K5b: the TAM's G and L gate networks (eval-mode BatchNorm1d) in 2 launches forward / 2 backward
 # ----------------------------------------------------------------------------------------------
 _gate_ws = {}
 
@@ -1408,11 +1415,11 @@ class TamGateFn(torch.autograd.Function):
         gp, gw1, gw2, gwa, gwb = e(n * t, c), e(*w1.shape), e(*w2.shape), e(*wa.shape), e(*wb.shape)
         gb1 = e(2, g_w.shape[0])
         gb2 = e(2, l_w.shape[0])
-        gz, gpre, ghm = e(n * t, c), e(n * t, c // 4), e(n * t, c // 4)
+        gpre, ghm = e(n * t, c // 4), e(n * t, c // 4)
         call("vitta_tam_gate_bwd", ptr(pooled), ptr(w1), _lib.make_bn(g_w, g_b, g_rm, g_rv, eps1), ptr(w2), ptr(wa),
              _lib.make_bn(l_w, l_b, l_rm, l_rv, eps2), ptr(wb), ptr(act), ptr(pre), ptr(gkern), ptr(gact), ptr(gp),
-             ptr(gw1), ptr(gb1[0]), ptr(gb1[1]), ptr(gw2), ptr(gwa), ptr(gb2[0]), ptr(gb2[1]), ptr(gwb), ptr(gz),
-             ptr(gpre), ptr(ghm), ptr(ws), n, t, c, stream_ptr())
+             ptr(gw1), ptr(gb1[0]), ptr(gb1[1]), ptr(gw2), ptr(gwa), ptr(gb2[0]), ptr(gb2[1]), ptr(gwb), ptr(gpre),
+             ptr(ghm), ptr(ws), n, t, c, stream_ptr())
         return (gp, gw1, gb1[0], gb1[1], None, None, gw2, gwa, gb2[0], gb2[1], None, None, gwb, None, None, None)
 
 
