@@ -227,7 +227,7 @@ int vitta_sgd_step(const VittaSgdTensor* tensors, const int32_t* block_start, in
  *   fwd also writes pre (N*T, C/4), the L hidden layer before BN2 (saved for the backward).
  *   bwd: given gkern, gact returns gp (N, T, C) and the gradients of W1, BN1 (w, b), W2, Wa, BN2 (w, b), Wb (assigned);
  *        gpre / ghm (N*T, C/4) are scratch; ws: vitta_tam_gate_bwd_ws_floats floats, zeroed once by the caller.
- *   T <= 16, C % 4 == 0, p and Wa 16-byte aligned; every reduction runs in a fixed order.
+ *   2 <= T <= 16, C % 4 == 0, p and Wa 16-byte aligned; every reduction runs in a fixed order.
  *   Launches: 2 forward (L hidden layer | G branch;  L output layer) and 2 backward (G branch | dWb | hidden-layer
  *   gradient;  dWa | gradient of p | BN2 gradients): stages whose inputs are ready run as CTA roles of one grid. */
 int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float* W2, const float* Wa, VittaBN bn2,

@@ -75,28 +75,35 @@ __device__ __forceinline__ void g_stage_params(const GateArgs& a, float* sW1, fl
   }
 }
 
-// forward of one (n, c) column: hp[j] = W1[j] . v (pre-BN), softmax s[3]
+// The per-column code keeps the loop over the 2T hidden units ROLLED (only the T-long dot products are unrolled): a CTA
+// runs it once, so fully unrolled it was ~270 KB of straight-line SASS whose instruction fetch, not its arithmetic, set
+// the 50 us floor of the first version of this file.
+// No `t < T` predicates on the unrolled T loops (here, in the gv update and in the L hidden layer): v is zero-filled past T
+// and w[t >= T] reads the next rows of the parameter block (finite), so the extra terms are exact zeros -- whereas the
+// compiler turns every predicate into a uniform BRANCH around its LDS + FFMA pair, which exposes the full shared-memory
+// latency 256 times per weight batch (the L hidden layer ran 12 us per batch that way).
+__device__ __forceinline__ float g_dot(const float* w, const float* v) {
+  float h = 0.f;
+#pragma unroll
+  for (int t = 0; t < kGateMaxT; ++t) h = fmaf(w[t], v[t], h);
+  return h;
+}
+
+// forward of one (n, c) column: softmax s[3] of W2 . relu(BN(W1 . v))
 __device__ __forceinline__ void g_forward(int T, const float* sW1, const float* sW2, const float* sbn, const float* v,
-                                          float* hp, float* s) {
+                                          float* s) {
   const int H = 2 * T;
-  float z[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 2 * kGateMaxT; ++j) {
-    hp[j] = 0.f;
-    if (j < H) {
-      float h = 0.f;
-#pragma unroll
-      for (int t = 0; t < kGateMaxT; ++t)
-        if (t < T) h = fmaf(sW1[j * T + t], v[t], h);
-      hp[j] = h;
-      const float r = fmaxf(fmaf(h - sbn[j], sbn[H + j], sbn[2 * H + j]), 0.f);
-      z[0] = fmaf(sW2[j], r, z[0]);
-      z[1] = fmaf(sW2[H + j], r, z[1]);
-      z[2] = fmaf(sW2[2 * H + j], r, z[2]);
-    }
+  float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < H; ++j) {
+    const float h = g_dot(sW1 + j * T, v);
+    const float r = fmaxf(fmaf(h - sbn[j], sbn[H + j], sbn[2 * H + j]), 0.f);
+    z0 = fmaf(sW2[j], r, z0);
+    z1 = fmaf(sW2[H + j], r, z1);
+    z2 = fmaf(sW2[2 * H + j], r, z2);
   }
-  const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
-  const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+  const float m = fmaxf(z0, fmaxf(z1, z2));
+  const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
   const float inv = 1.f / (e0 + e1 + e2);
   s[0] = e0 * inv; s[1] = e1 * inv; s[2] = e2 * inv;
 }
@@ -110,14 +117,15 @@ __device__ __forceinline__ void g_load_column(const GateArgs& a, int n, int c, b
 __device__ __forceinline__ void g_fwd_role(const GateArgs& a, int cta, float* sm) {
   const int T = a.T, H = 2 * T;
   float *sW1 = sm, *sW2 = sW1 + H * T, *sbn = sW2 + 3 * H;
+  const int idx = cta * kGateThreads + threadIdx.x;
+  const bool live = idx < a.N * a.C;
+  const int n = live ? idx / a.C : 0, c = live ? idx % a.C : 0;
+  float v[kGateMaxT], s[3];
+  g_load_column(a, n, c, live, v);          // in flight while the parameters are staged
   g_stage_params(a, sW1, sW2, sbn);
   __syncthreads();
-  const int idx = cta * kGateThreads + threadIdx.x;
-  if (idx >= a.N * a.C) return;
-  const int n = idx / a.C, c = idx % a.C;
-  float v[kGateMaxT], hp[2 * kGateMaxT], s[3];
-  g_load_column(a, n, c, true, v);
-  g_forward(T, sW1, sW2, sbn, v, hp, s);
+  if (!live) return;
+  g_forward(T, sW1, sW2, sbn, v, s);
   a.kern[((int64_t)n * 3 + 0) * a.C + c] = s[0];
   a.kern[((int64_t)n * 3 + 1) * a.C + c] = s[1];
   a.kern[((int64_t)n * 3 + 2) * a.C + c] = s[2];
@@ -125,68 +133,67 @@ __device__ __forceinline__ void g_fwd_role(const GateArgs& a, int cta, float* sm
 
 // backward role: CTA = kGCols columns (warps 0-3, one column per thread), all 8 warps reduce.
 // Partial layout per CTA: gW1 [2T*T] | gW2 [3*2T] | gbn_w [2T] | gbn_b [2T]; the last CTA adds the partials in CTA order.
+// The column threads leave their contributions to the parameter gradients in shared memory (ghp and the column for the
+// outer-product sum gW1, five more values per hidden unit for the small ones); the sums over the columns then run in
+// column order, one output per thread (no warp shuffles: inside a role branch the compiler brackets every shuffle with
+// WARPSYNC / ENDCOLLECTIVE, 800 of them in a row in the first version).
 constexpr int kGCols = 128;
 __host__ __device__ constexpr int g_part_floats(int T) { return 2 * T * T + 3 * 2 * T + 2 * 2 * T; }
 __host__ __device__ constexpr int g_small_floats(int T) { return 3 * 2 * T + 2 * 2 * T; }
 __host__ __device__ constexpr int g_bwd_smem_floats(int T) {
-  return 2 * T * T + 3 * 2 * T + 4 * 2 * T + kGCols * (2 * T + 1) + kGCols * (T + 1) + 4 * g_small_floats(T);
+  return 2 * T * T + 3 * 2 * T + 4 * 2 * T + kGCols * (2 * T + 1) + kGCols * (T + 1) + kGCols * (g_small_floats(T) + 1);
 }
 
 __device__ __forceinline__ void g_bwd_role(const GateArgs& a, int cta, int n_ctas, float* sm) {
   __shared__ int s_last;
   const int T = a.T, H = 2 * T;
-  const int n_part = g_part_floats(T), n_small = g_small_floats(T);
+  const int n_part = g_part_floats(T), n_small = g_small_floats(T), qs = n_small + 1;
   float* sW1 = sm;                          // H*T
   float* sW2 = sW1 + H * T;                 // 3*H
   float* sbn = sW2 + 3 * H;                 // 4*H
   float* sg = sbn + 4 * H;                  // [kGCols][H + 1]   gradient at the hidden layer before its BatchNorm
   float* sv = sg + kGCols * (H + 1);        // [kGCols][T + 1]   the column
-  float* sred = sv + kGCols * (T + 1);      // [4][n_small]      per-warp sums of the small parameter gradients
+  float* sq = sv + kGCols * (T + 1);        // [kGCols][5H + 1]  per-column terms of gW2 | gbn_w | gbn_b
+  const int tid = threadIdx.x;
+  const int idx = cta * kGCols + tid;
+  const bool col = tid < kGCols, live = col && idx < a.N * a.C;
+  const int n = live ? idx / a.C : 0, c = live ? idx % a.C : 0;
+  float v[kGateMaxT];
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  g_load_column(a, n, c, live, v);          // in flight while the parameters are staged
+  if (live) {
+    g0 = __ldg(a.gkern + ((int64_t)n * 3 + 0) * a.C + c);
+    g1 = __ldg(a.gkern + ((int64_t)n * 3 + 1) * a.C + c);
+    g2 = __ldg(a.gkern + ((int64_t)n * 3 + 2) * a.C + c);
+  }
   g_stage_params(a, sW1, sW2, sbn);
   __syncthreads();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp < kGCols / 32) {
-    const int idx = cta * kGCols + tid;
-    const bool live = idx < a.N * a.C;
-    const int n = live ? idx / a.C : 0, c = live ? idx % a.C : 0;
-    float v[kGateMaxT], hp[2 * kGateMaxT], s[3], gz[3] = {0.f, 0.f, 0.f};
-    g_load_column(a, n, c, live, v);
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (live) {
-      g0 = __ldg(a.gkern + ((int64_t)n * 3 + 0) * a.C + c);
-      g1 = __ldg(a.gkern + ((int64_t)n * 3 + 1) * a.C + c);
-      g2 = __ldg(a.gkern + ((int64_t)n * 3 + 2) * a.C + c);
-    }
-    g_forward(T, sW1, sW2, sbn, v, hp, s);
+  if (col) {
+    float s[3], gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+    g_forward(T, sW1, sW2, sbn, v, s);
     if (live) {
       const float dot = g0 * s[0] + g1 * s[1] + g2 * s[2];
-      gz[0] = s[0] * (g0 - dot); gz[1] = s[1] * (g1 - dot); gz[2] = s[2] * (g2 - dot);
+      gz0 = s[0] * (g0 - dot); gz1 = s[1] * (g1 - dot); gz2 = s[2] * (g2 - dot);
     }
     float gv[kGateMaxT];
 #pragma unroll
     for (int t = 0; t < kGateMaxT; ++t) gv[t] = 0.f;
-    float* red = sred + warp * n_small;
+    float* q = sq + tid * qs;
+#pragma unroll 1
+    for (int j = 0; j < H; ++j) {
+      const float* w = sW1 + j * T;
+      const float h = g_dot(w, v);
+      const float hb = fmaf(h - sbn[j], sbn[H + j], sbn[2 * H + j]);
+      const float r = fmaxf(hb, 0.f);
+      const float ghr = sW2[j] * gz0 + sW2[H + j] * gz1 + sW2[2 * H + j] * gz2;
+      const float ghb = hb > 0.f ? ghr : 0.f;       // gz == 0 on dead columns
+      const float ghp = ghb * sbn[H + j];
+      const float xh = (h - sbn[j]) * sbn[3 * H + j];
+      sg[tid * (H + 1) + j] = ghp;
+      q[j] = gz0 * r; q[H + j] = gz1 * r; q[2 * H + j] = gz2 * r;
+      q[3 * H + j] = ghb * xh; q[4 * H + j] = ghb;
 #pragma unroll
-    for (int j = 0; j < 2 * kGateMaxT; ++j) {
-      if (j < H) {
-        const float hb = fmaf(hp[j] - sbn[j], sbn[H + j], sbn[2 * H + j]);
-        const float r = fmaxf(hb, 0.f);
-        const float ghr = sW2[j] * gz[0] + sW2[H + j] * gz[1] + sW2[2 * H + j] * gz[2];
-        const float ghb = hb > 0.f ? ghr : 0.f;       // gz == 0 on dead columns
-        const float ghp = ghb * sbn[H + j];
-        const float xh = (hp[j] - sbn[j]) * sbn[3 * H + j];
-        sg[tid * (H + 1) + j] = ghp;
-#pragma unroll
-        for (int t = 0; t < kGateMaxT; ++t)
-          if (t < T) gv[t] = fmaf(sW1[j * T + t], ghp, gv[t]);
-        // small parameter gradients: sums over the warp's 32 columns (lane order of the butterfly is fixed)
-        const float w0 = warp_sum(gz[0] * r), w1 = warp_sum(gz[1] * r), w2 = warp_sum(gz[2] * r);
-        const float bw = warp_sum(ghb * xh), bb = warp_sum(ghb);
-        if (lane == 0) {
-          red[j] = w0; red[H + j] = w1; red[2 * H + j] = w2;
-          red[3 * H + j] = bw; red[4 * H + j] = bb;
-        }
-      }
+      for (int t = 0; t < kGateMaxT; ++t) gv[t] = fmaf(w[t], ghp, gv[t]);     // gv[t >= T] is never stored
     }
 #pragma unroll
     for (int t = 0; t < kGateMaxT; ++t)
@@ -196,16 +203,21 @@ __device__ __forceinline__ void g_bwd_role(const GateArgs& a, int cta, int n_cta
       }
   }
   __syncthreads();
-  // CTA partial of every parameter gradient
+  // CTA partial of every parameter gradient, columns added in column order
   float* part = a.ws + (int64_t)cta * n_part;
-  for (int o = tid; o < H * T; o += kGateThreads) {      // gW1[j][t] = sum_q ghp[q][j] * v[q][t], q in column order
+  for (int o = tid; o < H * T; o += kGateThreads) {      // gW1[j][t] = sum_q ghp[q][j] * v[q][t]
     const int j = o / T, t = o - j * T;
     float acc = 0.f;
 #pragma unroll 8
-    for (int q = 0; q < kGCols; ++q) acc = fmaf(sg[q * (H + 1) + j], sv[q * (T + 1) + t], acc);
+    for (int qq = 0; qq < kGCols; ++qq) acc = fmaf(sg[qq * (H + 1) + j], sv[qq * (T + 1) + t], acc);
     part[o] = acc;
   }
-  if (tid < n_small) part[H * T + tid] = (sred[tid] + sred[n_small + tid]) + (sred[2 * n_small + tid] + sred[3 * n_small + tid]);
+  if (tid < n_small) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int qq = 0; qq < kGCols; ++qq) acc += sq[qq * qs + tid];
+    part[H * T + tid] = acc;
+  }
   __threadfence();
   __syncthreads();
   int* ticket = reinterpret_cast<int*>(a.ws + (int64_t)n_ctas * n_part);
@@ -213,12 +225,32 @@ __device__ __forceinline__ void g_bwd_role(const GateArgs& a, int cta, int n_cta
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int o = tid; o < n_part; o += kGateThreads) {
-    const float acc = ordered_sum_strided(a.ws + o, n_ctas, n_part);
-    if (o < H * T) a.gW1[o] = acc;
-    else if (o < H * T + 3 * H) a.gW2[o - H * T] = acc;
-    else if (o < H * T + 4 * H) a.gbn1w[o - H * T - 3 * H] = acc;
-    else a.gbn1b[o - H * T - 4 * H] = acc;
+  // a thread owns outputs tid, tid + 256, tid + 512 (n_part <= 672): the partials of all three are loaded together, eight
+  // CTAs at a time, and added in CTA order
+  static_assert(g_part_floats(kGateMaxT) <= 3 * kGateThreads, "three outputs per thread cover the partial vector");
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int b0 = 0; b0 < n_ctas; b0 += 8) {
+    float pv[3][8];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int o = tid + i * kGateThreads;
+        pv[i][u] = (o < n_part && b0 + u < n_ctas) ? __ldcg(a.ws + (int64_t)(b0 + u) * n_part + o) : 0.f;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[i] += pv[i][u];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int o = tid + i * kGateThreads;
+    if (o >= n_part) continue;
+    if (o < H * T) a.gW1[o] = acc[i];
+    else if (o < H * T + 3 * H) a.gW2[o - H * T] = acc[i];
+    else if (o < H * T + 4 * H) a.gbn1w[o - H * T - 3 * H] = acc[i];
+    else a.gbn1b[o - H * T - 4 * H] = acc[i];
   }
   if (tid == 0) *ticket = 0;
 }
@@ -237,6 +269,7 @@ __device__ __forceinline__ float f4c(const float4& v, int k) { return k == 0 ? v
 __device__ __forceinline__ void l1_fwd_role(const GateArgs& a, int slice, int n, float* sp) {
   const int T = a.T, C = a.C, Hc = a.C / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* scr = sp + (kGateMaxT + 2) * C + warp * (32 * 33);     // per-warp reduction tile, behind the staged rows
   {
     const int C4 = C / 4;
     float4* sp4 = reinterpret_cast<float4*>(sp);
@@ -276,25 +309,29 @@ __device__ __forceinline__ void l1_fwd_role(const GateArgs& a, int slice, int n,
             const float* s = sp + j * C + c;
             const float x0 = f4c(wa[u], k), x1 = f4c(wb[u], k);
 #pragma unroll
-            for (int t = 0; t < kGateMaxT; ++t)
-              if (t < T) {
-                const float pv = s[t * C];
-                acc0[t] = fmaf(x0, pv, acc0[t]);
-                acc1[t] = fmaf(x1, pv, acc1[t]);
-              }
+            for (int t = 0; t < kGateMaxT; ++t) {     // rows past T + 1 are allocated but never written: acc[t >= T] is dropped
+              const float pv = s[t * C];
+              acc0[t] = fmaf(x0, pv, acc0[t]);
+              acc1[t] = fmaf(x1, pv, acc1[t]);
+            }
           }
         }
       }
     }
+    // sums over the lanes through the warp's scratch tile (lane m adds column m: 2 x T outputs), no shuffles
+    __syncwarp();
 #pragma unroll
     for (int t = 0; t < kGateMaxT; ++t) {
-      if (t < T) {
-        const float v0 = warp_sum(acc0[t]), v1 = warp_sum(acc1[t]);
-        if (lane == 0) {
-          a.pre[((int64_t)n * T + t) * Hc + o] = v0;
-          if (two) a.pre[((int64_t)n * T + t) * Hc + o + 1] = v1;
-        }
-      }
+      scr[lane * 33 + t] = acc0[t];
+      scr[lane * 33 + kGateMaxT + t] = acc1[t];
+    }
+    __syncwarp();
+    {
+      float tot = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) tot += scr[l * 33 + lane];
+      const int t = lane & (kGateMaxT - 1), second = lane >> 4;
+      if (t < T && (!second || two)) a.pre[((int64_t)n * T + t) * Hc + o + second] = tot;
     }
   }
 }
@@ -519,8 +556,7 @@ __device__ __forceinline__ void gate_bn2_role(const GateArgs& a, int cta, float*
 
 // backward launch 1: [gradient at the hidden layer (K = C: the longest role first)] [G branch] [dWb]
 __global__ void __launch_bounds__(kGateThreads) tam_gate_bwd1_kernel(GateArgs a, int n_hid, int n_g) {
-  __shared__ __align__(16) float sm[kGemmSmemFloats];
-  static_assert(g_bwd_smem_floats(kGateMaxT) <= kGemmSmemFloats, "G backward role must fit the GEMM tile buffers");
+  extern __shared__ __align__(16) float sm[];     // max(GEMM tile buffers, G backward role): see bwd1_smem_bytes
   const int R = a.N * a.T, Hc = a.C / 4;
   int b = blockIdx.x;
   if (b < n_hid) { gate_gemm_role<kGradHid>(a, b, R, Hc, a.C, sm); return; }
@@ -549,12 +585,17 @@ using namespace vitta;
 static GateBN to_gate_bn(const VittaBN& b) { return GateBN{b.weight, b.bias, b.running_mean, b.running_var, b.eps}; }
 
 static int check_gate_shape(int N, int T, int C) {
-  VITTA_CHECK_ARG(N > 0 && T > 0 && T <= kGateMaxT && C >= 4 && C % 4 == 0, VITTA_E_UNSUPPORTED,
-                  "tam_gate: needs T <= %d and C %% 4 == 0 (got T=%d C=%d)", kGateMaxT, T, C);
+  // T >= 2: the unpredicated T loops read up to 16 - T floats past a W1 row, which must stay inside W1 | W2 | BN1
+  VITTA_CHECK_ARG(N > 0 && T >= 2 && T <= kGateMaxT && C >= 4 && C % 4 == 0, VITTA_E_UNSUPPORTED,
+                  "tam_gate: needs 2 <= T <= %d and C %% 4 == 0 (got T=%d C=%d)", kGateMaxT, T, C);
   return 0;
 }
 
 static int g_bwd_ctas(int N, int C) { return (N * C + kGCols - 1) / kGCols; }
+static size_t bwd1_smem_bytes(int T) {
+  const int g = g_bwd_smem_floats(T);
+  return sizeof(float) * (size_t)(g > kGemmSmemFloats ? g : kGemmSmemFloats);
+}
 
 extern "C" {
 
@@ -570,10 +611,10 @@ int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float
   cudaStream_t st = (cudaStream_t)stream;
   {
     const int H = 2 * T;
-    size_t smem = sizeof(float) * (size_t)(T + 2) * C;
+    size_t smem = sizeof(float) * ((size_t)(kGateMaxT + 2) * C + (kGateThreads / 32) * 32 * 33);
     const size_t g_smem = sizeof(float) * (size_t)(H * T + 3 * H + 4 * H);
     if (smem < g_smem) smem = g_smem;
-    VITTA_CHECK_ARG(smem <= 200 * 1024, VITTA_E_UNSUPPORTED, "tam_gate_fwd: (T + 2) * C floats exceed shared memory");
+    VITTA_CHECK_ARG(smem <= 200 * 1024, VITTA_E_UNSUPPORTED, "tam_gate_fwd: 18 * C floats exceed shared memory");
     static size_t attr_smem = 48 * 1024;
     if (smem > attr_smem) {
       cudaError_t e = cudaFuncSetAttribute(tam_gate_fwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -593,7 +634,7 @@ int vitta_tam_gate_fwd(const float* p, const float* W1, VittaBN bn1, const float
 }
 
 int64_t vitta_tam_gate_bwd_ws_floats(int N, int T, int C) {
-  if (N <= 0 || T <= 0 || T > kGateMaxT || C <= 0) return -1;
+  if (N <= 0 || T < 2 || T > kGateMaxT || C <= 0) return -1;
   return (int64_t)g_bwd_ctas(N, C) * g_part_floats(T) + 4;
 }
 
@@ -616,7 +657,17 @@ int vitta_tam_gate_bwd(const float* p, const float* W1, VittaBN bn1, const float
   const int R = N * T, Hc = C / 4;
   // launch 1 -- G branch: gp (its part), gW1, gW2, gbn1w, gbn1b;  L branch: gWb, ghm, gpre
   const int n_hid = gate_tiles(R, Hc), n_g = g_bwd_ctas(N, C), n_wb = gate_tiles(C, Hc);
-  tam_gate_bwd1_kernel<<<(unsigned)(n_hid + n_g + n_wb), kGateThreads, 0, st>>>(a, n_hid, n_g);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tam_gate_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bwd1_smem_bytes(kGateMaxT));
+    if (e != cudaSuccess) {
+      set_error("tam_gate_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  tam_gate_bwd1_kernel<<<(unsigned)(n_hid + n_g + n_wb), kGateThreads, bwd1_smem_bytes(T), st>>>(a, n_hid, n_g);
   VITTA_CHECK_LAUNCH();
   // launch 2 -- L branch: gp += its part, gWa, gbn2w, gbn2b
   const int n_gp = gate_tiles(R, C), n_wa = gate_tiles(Hc, 3 * C), n_bn = (Hc + 31) / 32;

@@ -604,11 +604,25 @@ static int wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, in
   p.n_ctiles = (p.tap_group > 1) ? 1 : (Cin + out->bn - 1) / out->bn;
   const int64_t base_items = (int64_t)p.m_tiles * (KH * KW / p.tap_group) * p.n_ctiles;
   const int64_t boxes = (int64_t)p.boxes_w * p.boxes_h * p.boxes_f;
-  int64_t splits = (2 * (int64_t)cached_sm_count() + base_items - 1) / base_items;
+  // K splits: the persistent grid walks base_items * splits items round-robin, so the launch lasts
+  //   ceil(items / SMs) * (stages per item + fixed cost per item)
+  // -- minimised over the split count.  (Round 2 aimed at "about two items per SM", ceil(2 * SMs / base_items): 297, 304,
+  // 306, 320 or 360 items on 148 SMs for most of ResNet-50's layers, i.e. a THIRD pass in which 1-64 CTAs work and the
+  // others wait: +25 ... +50 % on those launches.)  The fixed cost stands for the pipeline fill and the un-overlapped
+  // part of the 128 x BN partial-tile store; fewer items also mean fewer partial bytes for wgrad_reduce_kernel.
   const int64_t max_by_k = boxes / 8 > 0 ? boxes / 8 : 1;   // at least 8 stages of work per item
-  if (splits > max_by_k) splits = max_by_k;
-  if (splits < 1) splits = 1;
-  if (splits > 1024) splits = 1024;
+  const int64_t sms = cached_sm_count();
+  const int64_t kItemCost = 6;
+  int64_t splits = 1, best = -1;
+  for (int64_t s = 1; s <= max_by_k && s <= 1024; ++s) {
+    const int64_t waves = (base_items * s + sms - 1) / sms;
+    const int64_t cost = waves * ((boxes + s - 1) / s + kItemCost);
+    if (best < 0 || cost < best) {
+      best = cost;
+      splits = s;
+    }
+    if (waves > 4) break;   // more passes only add per-item cost
+  }
   p.splits = (int)splits;
   p.box_base = (int)(boxes / splits);
   p.box_rem = (int)(boxes % splits);

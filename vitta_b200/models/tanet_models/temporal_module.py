@@ -47,7 +47,7 @@ class TAM(nn.Module):
         if pooled is None:
             pooled = F.adaptive_avg_pool2d(x, 1).flatten(1)          # (N*T, C)
         if self._gate_fusable(x, t, c):
-            # both gate networks in 3 launches (K5b); BatchNorm1d hooks of the alignment driver contribute exact zeros
+            # both gate networks in 2 launches (K5b); BatchNorm1d hooks of the alignment driver contribute exact zeros
             # (reference utils/norm_stats_utils.py:158-183) and are marked as fired without running the modules
             g_bn, l_bn = self.G[1], self.L[1]
             for bn in (g_bn, l_bn):
@@ -70,7 +70,7 @@ class TAM(nn.Module):
     def _gate_fusable(self, x, t, c):
         """K5b applies when both BatchNorm1d layers are in eval mode (``fix_BNS``, the ViTTA default), carry affine
         parameters, and no module of the branches has hooks other than the alignment driver's no-op BatchNorm1d hooks."""
-        if not x.is_cuda or t > 16 or c % 4 != 0:
+        if not x.is_cuda or t < 2 or t > 16 or c % 4 != 0:
             return False
         from ...utils.norm_stats_utils import CombineNormStatsRegHook_onereg
         for seq in (self.G, self.L):
