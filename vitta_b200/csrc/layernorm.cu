@@ -189,7 +189,6 @@ template <int VPL>
 __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_rows_kernel(const LnBwdArgs p) {
   constexpr int R = LnBwdRows<VPL>::value;
   __shared__ float4 s_red[2 * 512];   // [2][C/4], C <= 2048
-  __shared__ int s_last;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int C4 = p.C >> 2;
@@ -334,108 +333,170 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_rows_kernel(const LnBwdA
     st4(wsb + (int64_t)i * 4, s_red[i]);
     st4(wsb + p.C + (int64_t)i * 4, s_red[512 + i]);
   }
-  __threadfence();
-  __syncthreads();
-  int* ticket = reinterpret_cast<int*>(p.ws);
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
-    const float s = ordered_sum_strided(wsp + i, (int)gridDim.x, 2 * (int64_t)p.C);
-    if (i < p.C) {
-      if (p.dgamma) p.dgamma[i] += s;
-    } else {
-      if (p.dbeta) p.dbeta[i - p.C] += s;
-    }
-  }
-  if (threadIdx.x == 0) *ticket = 0;
+  // the per-CTA partials are added by ln_bwd_finish_kernel (next launch on the stream)
 }
 
-// one row per warp iteration: the wide rows (C >= 384) already have 8+ loads per lane in flight
-template <int VPL>
-__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
-  __shared__ float4 s_red[2 * 512];   // [2][C/4], C <= 2048
-  __shared__ int s_last;
+// Wide rows (C > 256): a row is split over K = 1, 2, 4 or 8 warps of the CTA, 96 float4 (three per lane) each, and every
+// warp iteration works on TWO rows with all their loads in flight.  The one-row-per-warp kernel above kept the whole row
+// plus its d(gamma) / d(beta) accumulators in one warp's registers: 136 registers at C = 384, 218 at C = 768, 255 + spills
+// at C = 1536 -- ONE resident CTA of 8 warps per SM, one row in flight per warp, 1.3-2.0 TB/s (tools/ln_probe.py).  Here
+// every thread carries 3 float4 of accumulators whatever C is; the K partial row sums meet in shared memory behind a
+// named barrier of the row's warps (double-buffered by iteration parity).  The reduction order of d(gamma) / d(beta) is
+// fixed (rows in visiting order per warp, then the row slots of the CTA in order, then the CTAs in order).
+constexpr int kLnSplitV = 3;                  // float4 per lane and warp
+constexpr int kLnSplitCols = 32 * kLnSplitV;  // float4 per warp = 384 channels
+
+template <int K>
+__global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_split_kernel(const LnBwdArgs p) {
+  constexpr int V = kLnSplitV, R = 2, kSlots = kLnWarps / K;
+  __shared__ float4 s_red[2 * 512];          // [2][C/4], C <= 2048
+  __shared__ float2 s_part[2][R][kLnWarps];  // [iteration parity][row][warp]: partial (sum g, sum g * xhat)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int slot = warp / K, part = warp % K;
   const int C4 = p.C >> 2;
   const float invC = 1.f / (float)p.C;
-  int goff[VPL];
-  int gdh[VPL], gdw[VPL];
-  if (p.g.merge) {
-    const int cin4 = p.g.Cin >> 2;
+  int col[V];        // float4 index of this lane's j-th vector within the row
+  int goff[V], gdh[V], gdw[V];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      const int q = i / cin4, ci = i - q * cin4;
+  for (int j = 0; j < V; ++j) {
+    col[j] = part * kLnSplitCols + j * 32 + lane;
+    goff[j] = gdh[j] = gdw[j] = 0;
+    if (p.g.merge && col[j] < C4) {
+      const int cin4 = p.g.Cin >> 2;
+      const int q = col[j] / cin4, ci = col[j] - q * cin4;
       gdh[j] = q & 1;
       gdw[j] = q >> 1;
       goff[j] = (gdh[j] * p.g.W + gdw[j]) * p.g.Cin + ci * 4;
     }
   }
   const float gsc = p.ca ? __ldg(p.gs) : 0.f;
-  float4 dg[VPL], db[VPL];
+  // gamma of this lane's columns stays in registers; the hook's per-channel constants are re-read where they are used
+  // (L1-resident) -- holding all five vectors cost 60 registers and spilled under the two-CTA bound
+  float4 ga[V];
 #pragma unroll
-  for (int j = 0; j < VPL; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < V; ++j) ga[j] = col[j] < C4 ? ldg4(p.gamma + col[j] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dg[V], db[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   float am = 0.f;
 
-  for (int64_t r = (int64_t)blockIdx.x * kLnWarps + warp; r < p.rows; r += (int64_t)gridDim.x * kLnWarps) {
-    int64_t base;
-    int h0 = 0, w0 = 0;
-    const float* src = ln_src_row(p.x, r, p.C, p.g, base, h0, w0);
-    const float mu = __ldg(p.mean + r), rs = __ldg(p.rstd + r);
-    float4 xh[VPL], g[VPL];
-    float s1 = 0.f, s2 = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * kSlots;
+  uint32_t iter = 0;
+  // every warp of a row slot runs the same number of iterations (rb depends on the slot only): the named barrier is safe
+  for (int64_t rb = (int64_t)blockIdx.x * kSlots + slot; rb < p.rows; rb += stride * R, ++iter) {
+    float4 xv[R][V], gyv[R][V];
+    float mu[R], rs[R];
+    int64_t base[R];
+    int h0[R], w0[R];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < C4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!p.g.merge) {
-          v = ld_stream4(src + base + (int64_t)i * 4);
-        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
-          v = ld_stream4(src + base + goff[j]);
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k * stride;
+      h0[k] = w0[k] = 0;
+      base[k] = 0;
+      mu[k] = rs[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) xv[k][j] = gyv[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.rows) {
+        const float* src = ln_src_row(p.x, r, p.C, p.g, base[k], h0[k], w0[k]);
+        mu[k] = __ldg(p.mean + r);
+        rs[k] = __ldg(p.rstd + r);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (col[j] < C4) {
+            if (!p.g.merge) {
+              xv[k][j] = ld_stream4(src + base[k] + (int64_t)col[j] * 4);
+            } else if (h0[k] + gdh[j] < p.g.H && w0[k] + gdw[j] < p.g.W) {
+              xv[k][j] = ld_stream4(src + base[k] + goff[j]);
+            }
+            gyv[k][j] = ld_stream4(p.gy + r * p.C + (int64_t)col[j] * 4);
+          }
         }
-        float4 gy = ld_stream4(p.gy + r * p.C + (int64_t)i * 4);
-        const float4 ga = ldg4(p.gamma + i * 4);
-        xh[j] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
-        if (p.ca) {
-          const float4 be = ldg4(p.beta + i * 4);
-          const float4 a = ldg4(p.ca + i * 4), b = ldg4(p.cb + i * 4), m = ldg4(p.cm + i * 4);
-          gy.x = fmaf(gsc, fmaf(b.x, fmaf(xh[j].x, ga.x, be.x) - m.x, a.x), gy.x);
-          gy.y = fmaf(gsc, fmaf(b.y, fmaf(xh[j].y, ga.y, be.y) - m.y, a.y), gy.y);
-          gy.z = fmaf(gsc, fmaf(b.z, fmaf(xh[j].z, ga.z, be.z) - m.z, a.z), gy.z);
-          gy.w = fmaf(gsc, fmaf(b.w, fmaf(xh[j].w, ga.w, be.w) - m.w, a.w), gy.w);
-        }
-        db[j].x += gy.x; db[j].y += gy.y; db[j].z += gy.z; db[j].w += gy.w;
-        dg[j].x = fmaf(gy.x, xh[j].x, dg[j].x); dg[j].y = fmaf(gy.y, xh[j].y, dg[j].y);
-        dg[j].z = fmaf(gy.z, xh[j].z, dg[j].z); dg[j].w = fmaf(gy.w, xh[j].w, dg[j].w);
-        g[j] = make_float4(gy.x * ga.x, gy.y * ga.y, gy.z * ga.z, gy.w * ga.w);
-        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
       }
     }
-    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+    float4 xh[R][V], g[R][V];
+    float s1[R], s2[R];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      if (i < C4) {
-        float4 o;
-        o.x = rs * (g[j].x - c1 - xh[j].x * c2);
-        o.y = rs * (g[j].y - c1 - xh[j].y * c2);
-        o.z = rs * (g[j].z - c1 - xh[j].z * c2);
-        o.w = rs * (g[j].w - c1 - xh[j].w * c2);
-        if (!p.g.merge) {
-          if (p.gadd) {
-            const float4 a = ld_stream4(p.gadd + r * p.C + (int64_t)i * 4);
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    for (int k = 0; k < R; ++k) {
+      s1[k] = s2[k] = 0.f;
+      const bool live = rb + k * stride < p.rows;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        xh[k][j] = g[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && col[j] < C4) {
+          const float4 v = xv[k][j];
+          float4 gy = gyv[k][j];
+          xh[k][j] = make_float4((v.x - mu[k]) * rs[k], (v.y - mu[k]) * rs[k], (v.z - mu[k]) * rs[k], (v.w - mu[k]) * rs[k]);
+          if (p.ca) {
+            const float4 be = ldg4(p.beta + col[j] * 4);
+            const float4 a = ldg4(p.ca + col[j] * 4), b = ldg4(p.cb + col[j] * 4), m = ldg4(p.cm + col[j] * 4);
+            gy.x = fmaf(gsc, fmaf(b.x, fmaf(xh[k][j].x, ga[j].x, be.x) - m.x, a.x), gy.x);
+            gy.y = fmaf(gsc, fmaf(b.y, fmaf(xh[k][j].y, ga[j].y, be.y) - m.y, a.y), gy.y);
+            gy.z = fmaf(gsc, fmaf(b.z, fmaf(xh[k][j].z, ga[j].z, be.z) - m.z, a.z), gy.z);
+            gy.w = fmaf(gsc, fmaf(b.w, fmaf(xh[k][j].w, ga[j].w, be.w) - m.w, a.w), gy.w);
           }
-          st4(p.gx + r * p.C + (int64_t)i * 4, o);
-          am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
-          st4(p.gx + base + goff[j], o);
+          db[j].x += gy.x; db[j].y += gy.y; db[j].z += gy.z; db[j].w += gy.w;
+          dg[j].x = fmaf(gy.x, xh[k][j].x, dg[j].x); dg[j].y = fmaf(gy.y, xh[k][j].y, dg[j].y);
+          dg[j].z = fmaf(gy.z, xh[k][j].z, dg[j].z); dg[j].w = fmaf(gy.w, xh[k][j].w, dg[j].w);
+          g[k][j] = make_float4(gy.x * ga[j].x, gy.y * ga[j].y, gy.z * ga[j].z, gy.w * ga[j].w);
+          s1[k] += (g[k][j].x + g[k][j].y) + (g[k][j].z + g[k][j].w);
+          s2[k] += (g[k][j].x * xh[k][j].x + g[k][j].y * xh[k][j].y) + (g[k][j].z * xh[k][j].z + g[k][j].w * xh[k][j].w);
+        }
+      }
+      s1[k] = warp_sum(s1[k]);
+      s2[k] = warp_sum(s2[k]);
+    }
+    if (K > 1) {
+      const int par = iter & 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) s_part[par][k][warp] = make_float2(s1[k], s2[k]);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(32 * K) : "memory");
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const float2 v = s_part[par][k][slot * K + q];
+          a += v.x;
+          b += v.y;
+        }
+        s1[k] = a;
+        s2[k] = b;
+      }
+    }
+    // the shortcut gradient is fetched only now (both rows' loads together): holding it from the first phase on cost 24
+    // registers and spilled under the two-CTA bound
+    float4 gav[R][V];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k * stride;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        gav[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gadd && r < p.rows && col[j] < C4) gav[k][j] = ld_stream4(p.gadd + r * p.C + (int64_t)col[j] * 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k * stride;
+      if (r >= p.rows) break;
+      const float c1 = s1[k] * invC, c2 = s2[k] * invC;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if (col[j] < C4) {
+          float4 o;
+          o.x = rs[k] * (g[k][j].x - c1 - xh[k][j].x * c2) + gav[k][j].x;
+          o.y = rs[k] * (g[k][j].y - c1 - xh[k][j].y * c2) + gav[k][j].y;
+          o.z = rs[k] * (g[k][j].z - c1 - xh[k][j].z * c2) + gav[k][j].z;
+          o.w = rs[k] * (g[k][j].w - c1 - xh[k][j].w * c2) + gav[k][j].w;
+          if (!p.g.merge) {
+            st4(p.gx + r * p.C + (int64_t)col[j] * 4, o);
+            am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          } else if (h0[k] + gdh[j] < p.g.H && w0[k] + gdw[j] < p.g.W) {
+            st4(p.gx + base[k] + goff[j], o);
+          }
         }
       }
     }
@@ -444,14 +505,14 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
     if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_gx), wmax);
   }
-  // CTA reduction of d(gamma), d(beta): warps add in turn (fixed order), then one partial per CTA
-  for (int w = 0; w < kLnWarps; ++w) {
-    if (warp == w) {
+  // CTA reduction of d(gamma), d(beta): the row slots add in turn (fixed order), then one partial per CTA
+  for (int sl = 0; sl < kSlots; ++sl) {
+    if (slot == sl) {
 #pragma unroll
-      for (int j = 0; j < VPL; ++j) {
-        const int i = j * 32 + lane;
+      for (int j = 0; j < V; ++j) {
+        const int i = col[j];
         if (i < C4) {
-          if (w == 0) {
+          if (sl == 0) {
             s_red[i] = dg[j];
             s_red[512 + i] = db[j];
           } else {
@@ -466,28 +527,37 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnBwdArgs p) {
     }
     __syncthreads();
   }
-  float* wsp = p.ws + kWsHeader;   // ws = [ticket ints | per-CTA partials]
-  float* wsb = wsp + (int64_t)blockIdx.x * 2 * p.C;
+  float* wsb = p.ws + kWsHeader + (int64_t)blockIdx.x * 2 * p.C;
   for (int i = threadIdx.x; i < C4; i += kLnThreads) {
     st4(wsb + (int64_t)i * 4, s_red[i]);
     st4(wsb + p.C + (int64_t)i * 4, s_red[512 + i]);
   }
-  __threadfence();
+  // the per-CTA partials are added by ln_bwd_finish_kernel (next launch on the stream)
+}
+
+// d(gamma)[c] += sum over the CTAs' partials, d(beta) likewise, in CTA order.  CTA = 32 columns x 8 slices of the CTA
+// range (sixteen loads in flight per thread), the slices added in slice order through shared memory.  (The backward
+// kernels used to elect their last CTA for this: 256 threads walking up to 592 partials of 2C columns one L2 round trip
+// after the other -- 100-400 us at the tail of every launch with C >= 384, several times the streaming part.)
+__global__ void __launch_bounds__(256) ln_bwd_finish_kernel(const float* __restrict__ wsp, int n_ctas, int C,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sp[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int per = (n_ctas + 7) / 8;
+  const int k0 = slice * per, k1 = min(n_ctas, k0 + per);
+  sp[slice][lane] = (i < 2 * C && k1 > k0) ? ordered_sum_strided(wsp + (int64_t)k0 * 2 * C + i, k1 - k0, 2 * (int64_t)C) : 0.f;
   __syncthreads();
-  int* ticket = reinterpret_cast<int*>(p.ws);
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = threadIdx.x; i < 2 * p.C; i += kLnThreads) {
-    const float s = ordered_sum_strided(wsp + i, (int)gridDim.x, 2 * (int64_t)p.C);
-    if (i < p.C) {
-      if (p.dgamma) p.dgamma[i] += s;
+  if (slice == 0 && i < 2 * C) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += sp[q][lane];
+    if (i < C) {
+      if (dgamma) dgamma[i] += s;
     } else {
-      if (p.dbeta) p.dbeta[i - p.C] += s;
+      if (dbeta) dbeta[i - C] += s;
     }
   }
-  if (threadIdx.x == 0) *ticket = 0;
 }
 
 static int ln_vpl(int C) {
@@ -744,15 +814,30 @@ int vitta_ln_bwd_amax(const float* gy, const float* x, const float* gamma, const
   if (p.g.merge && ((p.g.H & 1) || (p.g.W & 1))) {
     // odd extents: every source element is still written exactly once (the padded ones do not exist)
   }
-  const unsigned grid = (unsigned)ln_bwd_grid(rows);
-  switch (ln_vpl(C)) {
-    case 1: ln_bwd_rows_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 2: ln_bwd_rows_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 4: ln_bwd_kernel<4><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 8: ln_bwd_kernel<8><<<grid, kLnThreads, 0, st>>>(p); break;
-    default: ln_bwd_kernel<16><<<grid, kLnThreads, 0, st>>>(p); break;
+  unsigned grid = (unsigned)ln_bwd_grid(rows);
+  const int vpl = ln_vpl(C);
+  if (vpl <= 2) {
+    if (vpl == 1) ln_bwd_rows_kernel<1><<<grid, kLnThreads, 0, st>>>(p);
+    else ln_bwd_rows_kernel<2><<<grid, kLnThreads, 0, st>>>(p);
+  } else {
+    // wide rows: K warps per row, 8 / K row slots per CTA, two rows per slot and iteration
+    const int need = (C / 4 + kLnSplitCols - 1) / kLnSplitCols;
+    const int K = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : 8;
+    int64_t g = (rows + (kLnWarps / K) * 2 - 1) / ((kLnWarps / K) * 2);
+    if (g > 148 * 2) g = 148 * 2;     // two resident CTAs per SM (launch bounds), one wave
+    grid = (unsigned)g;
+    switch (K) {
+      case 1: ln_bwd_split_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
+      case 2: ln_bwd_split_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
+      case 4: ln_bwd_split_kernel<4><<<grid, kLnThreads, 0, st>>>(p); break;
+      default: ln_bwd_split_kernel<8><<<grid, kLnThreads, 0, st>>>(p); break;
+    }
   }
   VITTA_CHECK_LAUNCH();
+  if (dgamma || dbeta) {
+    ln_bwd_finish_kernel<<<(unsigned)((2 * C + 31) / 32), 256, 0, st>>>(p.ws + kWsHeader, (int)grid, C, dgamma, dbeta);
+    VITTA_CHECK_LAUNCH();
+  }
   return 0;
 }
 
