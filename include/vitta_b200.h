@@ -499,6 +499,12 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
 int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
                           int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
                           void* stream);
+/* Profiling aid: the forward kernel with time stamps.  trace = 14 x trace_cap records, zeroed by the caller: lane 0 of warp
+ * w of CTA 0 writes (clock << 16 | warp << 8 | event id) into trace[w * trace_cap ...] at the hand-over points of the
+ * pipeline (event ids: csrc/wmsa3d.cu, WMSA_TR; tools/wmsa_trace.py prints the timeline).  Results = vitta_wmsa3d_fwd. */
+int vitta_wmsa3d_fwd_trace(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                           int heads, int head_dim, const int* window, const int* shift, float scale,
+                           unsigned long long* trace, int trace_cap, void* stream);
 int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
                           const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,
                           int heads, int head_dim, const int* window, const int* shift, float scale, int impl,

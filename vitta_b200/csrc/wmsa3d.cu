@@ -7,9 +7,9 @@
 //   (B, D, H, W, 3, heads, 32) qkv tensor with the cyclic shift folded into the addresses, and the output rows are
 //   scattered back to their un-shifted token positions.
 //
-// Forward kernel (288 threads, 1 CTA / SM, persistent over a contiguous item range, head-major so the bias table of a
-// head is loaded once):
-//   warps 4-7  loaders: gather K (whole window), per 128-row tile Q (pre-scaled), per 32-key chunk V; split every value
+// Forward kernel (448 threads, 1 CTA / SM, persistent over a contiguous item range, head-major so the bias table of a
+// head is loaded once; warp numbering of the current kernel: see wmsa3d_fwd_kernel -- two softmax groups, warps 0-7):
+//   loaders: gather K (whole window), per 128-row tile Q (pre-scaled), per 32-key chunk V; split every value
 //              into tf32 hi / lo and store both in the UMMA shared-memory layouts (K-major SWIZZLE_128B for Q, K, P;
 //              MN-major SWIZZLE_128B_BASE32B for V)
 //   warp  8    one thread issues tcgen05.mma.kind::tf32:  S[128 x N] = Q K^T  (3 MMAs per k-step: lo*hi, hi*lo, hi*hi)
@@ -23,7 +23,6 @@
 
 namespace vitta {
 
-constexpr int kAtThreads = 288;   // (historic role layout: 4 softmax + 4 loader + 1 issuer warps)
 constexpr int kAtMaxKeys = 400;     // 392 padded to a multiple of 16 (UMMA N granularity)
 constexpr int kAtMaxRel = 2560;     // (2*8-1)*(2*7-1)*(2*7-1) = 2535 table rows
 
@@ -102,9 +101,11 @@ constexpr int kOffTab = kOffV + kFwdVStages * 8192;      // bias table of the cu
 constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;
 constexpr int kOffTok = kOffInfo + kAtColPad * 4;
 constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;
-constexpr int kAtSmemBytes = kOffBar + 256 + 1024;       // ~183 KB
-// TMEM columns of the forward kernel: S [0, 400), O [400, 432), P chunk hi [432, 464), lo [464, 496)
-constexpr uint32_t kFT_O = 400, kFT_Phi = 432, kFT_Plo = 464;
+constexpr int kOffXch = kOffBar + 256;                   // row maximum / row sum exchange between the two softmax groups
+constexpr int kAtSmemBytes = kOffXch + 2 * 2 * 128 * 4 + 1024;   // ~185 KB
+// TMEM columns of the forward kernel: S [0, 400) -- the hi part of P chunk c overwrites S columns [32c, 32c + 32) once the
+// softmax has consumed them --, O [400, 432), lo part of P: one 32-column buffer per softmax group at 432 / 464
+constexpr uint32_t kFT_O = 400, kFT_Plo = 432;
 
 struct WmsaFwdParams {
   const float* qkv;     // (B, D, H, W, 3, heads, 32)
@@ -115,13 +116,42 @@ struct WmsaFwdParams {
   int items, items_per_cta;
   WmsaGeom g;
   float* amax_out;      // optional: max|out| (range of the fp16-split proj GEMM and its weight gradient)
+  unsigned long long* trace;   // TRACE instantiation only: 14 warps x trace_cap records (0 = unused)
+  int trace_cap;
 };
 
 enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages,
-       B_S_FULL = B_V_FREE0 + kFwdVStages, B_S_FREE, B_P_READY, B_P_FREE, B_O_FULL, B_O_FREE, B_COUNT };
+       B_S_FULL = B_V_FREE0 + kFwdVStages, B_S_FREE, B_P_READY0, B_P_READY1, B_P_FREE0, B_P_FREE1, B_O_FULL, B_O_FREE,
+       B_COUNT };
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
-constexpr int kFwdThreads = 320;   // warps 0-3 softmax, 4-7 loaders, 8 S issuer (+ TMEM owner), 9 PV issuer
+// warps 0-3 softmax group A, 4-7 softmax group B (TMEM lane quadrant = warp & 3), 8-11 loaders, 12 S issuer (+ TMEM
+// owner), 13 PV issuer.
+//
+// Round 2 ran ONE softmax group (4 warps, one per scheduler, nothing to overlap their tcgen05.ld -> LDS -> EX2 -> tcgen05.st
+// chains with) and one P buffer: ~36 K cycles per 128-row tile against ~5 K cycles of tensor work.  Now the 32-column
+// chunks of a tile alternate between two groups (by the parity of a global chunk counter), in both passes:
+//   pass 1  adds bias + mask in place (log2 domain) and takes the partial row maximum of the group's chunks; the two
+//           partial maxima of a row meet in shared memory behind a 64-thread named barrier (warps q and q + 4);
+//   pass 2  exponentiates, splits P into tf32 hi / lo; hi goes back IN PLACE over the consumed S columns, lo into the
+//           group's own 32-column buffer -- so the P operand of chunk c + 1 (other group) is written while the PV MMAs of
+//           chunk c run, instead of store -> MMA -> "buffer free" -> store in one serial chain per chunk.
+// Because P lives in the S columns, S is released for the next tile's Q K^T by the PV issuer (commit after the last
+// chunk), not by the softmax warps.  The epilogue is split too: each group normalises and stores 16 of the 32 channels.
+constexpr int kFwdThreads = 448;
 
+// TRACE = true (vitta_wmsa3d_fwd_trace, a profiling aid): lane 0 of every warp of CTA 0 writes (clock << 16 | warp << 8 |
+// event id) records into its own slice of p.trace (plain stores, no atomics) at the hand-over points of the pipeline -- the timeline of one tile shows which role waits
+// for which (profiles/r02_wmsa_fwd_timeline.md); the production instantiation carries none of it.
+#define WMSA_TR(id)                                                                                              \
+  do {                                                                                                           \
+    if (TRACE && blockIdx.x == 0 && lane == 0 && tr_n < (uint32_t)p.trace_cap) {                                 \
+      p.trace[(size_t)warp * p.trace_cap + tr_n] = ((unsigned long long)clock64() << 16) | ((unsigned long long)warp << 8) | (id); \
+      ++tr_n;                                                                                                    \
+    }                                                                                                            \
+  } while (0)
+
+template <bool TRACE>
 __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the extern array (no integer round trip) keeps the shared address space: LDS/STS, not LD/ST
@@ -131,9 +161,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   float* tab = reinterpret_cast<float*>(smem + kOffTab);
   int* info = reinterpret_cast<int*>(smem + kOffInfo);
   int* tok = reinterpret_cast<int*>(smem + kOffTok);
+  float* xch_max = reinterpret_cast<float*>(smem + kOffXch);     // [2][128]
+  float* xch_sum = xch_max + 2 * 128;                            // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t tr_n = 0;
+  (void)tr_n;
   const WmsaGeom& g = p.g;
   const int C = g.heads * 32;
   const int nwin = g.nw0 * g.nw1 * g.nw2;
@@ -146,14 +180,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       int cnt = 1;   // tcgen05.commit barriers
-      if (i == B_KV_READY || i == B_TAB_FREE || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i == B_S_FREE ||
-          i == B_P_READY || i == B_O_FREE)
+      if (i == B_KV_READY || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i == B_P_READY0 || i == B_P_READY1)
         cnt = 4;     // one elected arrive per warp of a 4-warp role
+      if (i == B_TAB_FREE || i == B_O_FREE) cnt = 8;   // both softmax groups
       mbar_init(&bar[i], cnt);
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -164,9 +198,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   // everything derived from it travels through R2UR.BROADCAST + ELECT in front of every lane-predicated tcgen05.mma
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 12) {
     // =========================== loaders ===========================
-    const int lt = threadIdx.x - 128;
+    const int lt = threadIdx.x - 256;
     const int rslot = lt >> 3, q4 = lt & 7;
     int cur_head = -1;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
@@ -180,6 +214,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       const int wd = w / g.nw1;
       mbar_wait(&bar[B_KV_FREE], (it & 1) ^ 1);
       mbar_wait(&bar[B_TAB_FREE], (it & 1) ^ 1);
+      WMSA_TR(40);
       for (int i = lt; i < kAtColPad; i += 128) {
         int t = -1, f = 31 << 16;   // padding columns: region id 31 = always masked (and their V rows are zero)
         if (i < g.N) window_token(g, b, wd, wh, ww, i, t, f);
@@ -220,6 +255,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[B_KV_READY]);
+      WMSA_TR(41);
       // V chunks: groups of 4 chunks (8 float4 per thread), the next group in flight while the current one is stored
       auto v_issue = [&](float4 (&v)[8], int grp) {
 #pragma unroll
@@ -280,6 +316,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_Q_READY]);
+        WMSA_TR(42);
         for (int grp = 0; grp < n_groups; grp += 2) {
           if (grp + 1 < n_groups) v_issue(vb8, grp + 1);
           v_drain(va, grp);
@@ -288,7 +325,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // =========================== S issuer: S[128 x NP] = Q K^T ===========================
     // every lane runs the warp-uniform control flow, only the instruction is predicated on lane 0 (uniform operands)
     const uint32_t pe = (lane == 0) ? 1u : 0u;
@@ -303,8 +340,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         if (tile == 0) mbar_wait(&bar[B_KV_READY], it & 1);
         mbar_wait(&bar[B_Q_READY], tile_ctr & 1);
-        mbar_wait(&bar[B_S_FREE], (tile_ctr & 1) ^ 1);
+        mbar_wait(&bar[B_S_FREE], (tile_ctr & 1) ^ 1);   // the previous tile's PV MMAs (which read P from these columns) retired
         tc_fence_after();
+        WMSA_TR(30);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
           if (part == 1 && part1 == 0) break;
@@ -323,9 +361,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         umma_commit_p(&bar[B_Q_FREE], pe);
         if (tile == n_tiles - 1) umma_commit_p(&bar[B_KV_FREE], pe);
         umma_commit_p(&bar[B_S_FULL], pe);
+        WMSA_TR(31);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // =========================== PV issuer: O[128 x 32] += P_chunk V_chunk, P read from tensor memory ===============
     const uint32_t pe = (lane == 0) ? 1u : 0u;
     const uint32_t idesc_o = umma_idesc_tf32(128, 32) | (1u << 16);   // B (= V) is MN-major
@@ -334,35 +373,47 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     for (int item = item0; item < item1; ++item) {
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int st = __shfl_sync(0xffffffffu, chunk_ctr, 0) & (kFwdVStages - 1);   // uniform registers for the descriptors
-          mbar_wait(&bar[B_P_READY], chunk_ctr & 1);
+          const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);   // uniform registers for the descriptors / addresses
+          const int st = ccu & (kFwdVStages - 1);
+          const int grp = ccu & 1;
+          const uint32_t cu = __shfl_sync(0xffffffffu, (uint32_t)c, 0);
+          mbar_wait(&bar[B_P_READY0 + grp], (chunk_ctr >> 1) & 1);
+          WMSA_TR(20);
           mbar_wait(&bar[B_V_READY0 + st], (chunk_ctr / kFwdVStages) & 1);
           if (c == 0) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
           tc_fence_after();
+          WMSA_TR(21);
           const uint32_t vb = sbase + kOffV + st * 8192;
           const uint64_t v_hi = umma_desc_mn_sw128(vb, 4096), v_lo = umma_desc_mn_sw128(vb + 4096, 4096);
           const int left = g.N - c * 32;
           const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
           const uint32_t d = tmem_base + kFT_O;
+          const uint32_t p_hi = tmem_base + cu * 32u, p_lo = tmem_base + kFT_Plo + (uint32_t)grp * 32u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (k < ksteps) {
               const uint64_t advb = (uint64_t)(k * (1024 >> 4));
               const uint32_t ka = (uint32_t)(k * 8);
-              umma_tf32_ts_p(d, tmem_base + kFT_Plo + ka, v_hi + advb, idesc_o, (c | k) != 0, pe);
-              umma_tf32_ts_p(d, tmem_base + kFT_Phi + ka, v_lo + advb, idesc_o, 1, pe);
-              umma_tf32_ts_p(d, tmem_base + kFT_Phi + ka, v_hi + advb, idesc_o, 1, pe);
+              umma_tf32_ts_p(d, p_lo + ka, v_hi + advb, idesc_o, (c | k) != 0, pe);
+              umma_tf32_ts_p(d, p_hi + ka, v_lo + advb, idesc_o, 1, pe);
+              umma_tf32_ts_p(d, p_hi + ka, v_hi + advb, idesc_o, 1, pe);
             }
           }
-          umma_commit_p(&bar[B_P_FREE], pe);
+          umma_commit_p(&bar[B_P_FREE0 + grp], pe);
           umma_commit_p(&bar[B_V_FREE0 + st], pe);
-          if (c == n_chunks - 1) umma_commit_p(&bar[B_O_FULL], pe);
+          if (c == n_chunks - 1) {
+            umma_commit_p(&bar[B_O_FULL], pe);
+            umma_commit_p(&bar[B_S_FREE], pe);
+          }
+          WMSA_TR(22);
         }
       }
     }
   } else {
-    // =========================== softmax / epilogue (thread = query row = TMEM lane) ===========================
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // =========================== softmax / epilogue (thread = query row = TMEM lane, group = chunk parity) ===========
+    const int quad = warp & 3, grp = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int rel0 = rel_row_base(g);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kMask2 = -100.f * kLog2e;
@@ -373,86 +424,125 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       const int wg = item - head * nwin_total;
       mbar_wait(&bar[B_KV_READY], it & 1);   // tab / info / tok of this item are in place
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        const int i = tile * 128 + threadIdx.x;
+        const int i = tile * 128 + row;
         const bool valid = i < g.N;
+        // a warp whose 32 rows all lie past the window (last tile: 392 = 3 x 128 + 8) only keeps the handshakes going
+        const bool warp_live = tile * 128 + quad * 32 < g.N;
         const int fi = info[valid ? i : 0];
         const int a_i = (fi & 0xffff) + rel0;
         const int r_i = fi & 0x1f0000;
         const int my_tok = tok[valid ? i : 0];   // read before TAB_FREE is released (the loaders reuse tok[] / info[])
         mbar_wait(&bar[B_S_FULL], tile_ctr & 1);
         tc_fence_after();
-        // ---- pass 1 (log2 domain): t = s*log2e + bias2 + mask2, in place; row maximum.  Padding columns carry region
-        //      id 31 and are therefore always masked (their P is ~2^-144 and multiplies zero V rows).
+        WMSA_TR(1);
+        // ---- pass 1 (log2 domain): t = s*log2e + bias2 + mask2, in place; partial row maximum over this group's chunks.
+        //      Padding columns carry region id 31 and are therefore always masked (their P is ~2^-144 and multiplies
+        //      zero V rows).
         float m2 = -INFINITY;
-        for (int c0 = 0; c0 < g.NP; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_lane + (uint32_t)c0, r);
-          tmem_ld_wait();
+        if (warp_live) {
+          for (int c = 0; c < n_chunks; ++c) {
+            if (((chunk_ctr + c) & 1) != (uint32_t)grp) continue;
+            const int cols = min(32, g.NP - c * 32);
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int fj = info[c0 + jj];
-            float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
-            t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
-            m2 = fmaxf(m2, t);
-            r[jj] = __float_as_uint(t);
+            for (int hf = 0; hf < 2; ++hf) {
+              if (hf * 16 >= cols) break;
+              const int c0 = c * 32 + hf * 16;
+              uint32_t r[16];
+              tmem_ld16(t_lane + (uint32_t)c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                const int fj = info[c0 + jj];
+                float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
+                t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
+                m2 = fmaxf(m2, t);
+                r[jj] = __float_as_uint(t);
+              }
+              tmem_st16(t_lane + (uint32_t)c0, r);
+            }
           }
-          tmem_st16(t_lane + (uint32_t)c0, r);
+          tmem_st_wait();
         }
-        tmem_st_wait();
+        WMSA_TR(2);
+        // the two partial maxima of a row meet (warps quad and quad + 4)
+        xch_max[grp * 128 + row] = m2;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        m2 = fmaxf(m2, xch_max[(grp ^ 1) * 128 + row]);
+        WMSA_TR(3);
         if (tile == n_tiles - 1) {   // last use of tab / info by this warp for this item
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[B_TAB_FREE]);
         }
-        // ---- pass 2: p = 2^(t - m2), row sum; P chunks (tf32 hi / lo) go to tensor memory as the A operand of PV
+        // ---- pass 2: p = 2^(t - m2), partial row sum; P chunks (tf32 hi / lo) go to tensor memory as the A operand of PV
         float l = 0.f;
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          if ((chunk_ctr & 1) != (uint32_t)grp) continue;
           uint32_t r[32], lo[32];
           const int cols = min(32, g.NP - c * 32);
-          tmem_ld16(t_lane + (uint32_t)(c * 32), r);
-          if (cols > 16) tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
-          tmem_ld_wait();
+          if (warp_live) {
+            tmem_ld16(t_lane + (uint32_t)(c * 32), r);
+            if (cols > 16) tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
+            tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            float pij = 0.f;
-            if (jj < 16 || cols > 16) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(__uint_as_float(r[jj]) - m2));
-            l += pij;
-            const uint32_t h = (__float_as_uint(pij) + 0x1000u) & 0xffffe000u;   // tf32 round-to-nearest of a finite value
-            r[jj] = h;
-            lo[jj] = __float_as_uint(pij - __uint_as_float(h));
+            for (int jj = 0; jj < 32; ++jj) {
+              float pij = 0.f;
+              if (jj < 16 || cols > 16) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(__uint_as_float(r[jj]) - m2));
+              l += pij;
+              const uint32_t h = (__float_as_uint(pij) + 0x1000u) & 0xffffe000u;   // tf32 round-to-nearest of a finite value
+              r[jj] = h;
+              lo[jj] = __float_as_uint(pij - __uint_as_float(h));
+            }
           }
-          mbar_wait(&bar[B_P_FREE], (chunk_ctr & 1) ^ 1);
-          tc_fence_after();
-          tmem_st32(t_lane + kFT_Phi, r);
-          tmem_st32(t_lane + kFT_Plo, lo);
-          tmem_st_wait();
-          tc_fence_before();
+          WMSA_TR(10);
+          mbar_wait(&bar[B_P_FREE0 + grp], ((chunk_ctr >> 1) & 1) ^ 1);   // the group's lo buffer: MMAs of its previous chunk retired
+          WMSA_TR(11);
+          if (warp_live) {
+            tc_fence_after();
+            // hi: in place over the consumed S columns (a 16-column last chunk must not run into the O accumulator)
+            if (cols > 16) {
+              tmem_st32(t_lane + (uint32_t)(c * 32), r);
+              tmem_st32(t_lane + kFT_Plo + (uint32_t)(grp * 32), lo);
+            } else {
+              tmem_st16(t_lane + (uint32_t)(c * 32), r);
+              tmem_st16(t_lane + kFT_Plo + (uint32_t)(grp * 32), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_P_READY]);
+          if (lane == 0) mbar_arrive(&bar[B_P_READY0 + grp]);
+          WMSA_TR(12);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[B_S_FREE]);
-        // ---- O / l -> global
+        // the two partial sums of a row meet
+        xch_sum[grp * 128 + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        l += xch_sum[(grp ^ 1) * 128 + row];
+        WMSA_TR(5);
+        // ---- O / l -> global: this group's 16 of the 32 head channels
         mbar_wait(&bar[B_O_FULL], tile_ctr & 1);
         tc_fence_after();
-        uint32_t o[32];
-        tmem_ld32(t_lane + kFT_O, o);
-        tmem_ld_wait();
+        WMSA_TR(6);
+        uint32_t o[16];
+        if (warp_live) {
+          tmem_ld16(t_lane + kFT_O + (uint32_t)(grp * 16), o);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_O_FREE]);
         if (valid) {
           const float inv = 1.f / l;
-          float* dst = p.out + (int64_t)my_tok * C + head * 32;
+          float* dst = p.out + (int64_t)my_tok * C + head * 32 + grp * 16;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const float4 ov = make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
                                           __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv);
             st4(dst + q * 4, ov);
             out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(ov.x), fabsf(ov.y)), fmaxf(fabsf(ov.z), fabsf(ov.w))));
           }
-          p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2 + log2f(l)) * 0.6931471805599453f;
+          if (grp == 0) p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2 + log2f(l)) * 0.6931471805599453f;
         }
+        WMSA_TR(7);
       }
     }
     if (p.amax_out) {   // one integer atomic per softmax warp (non-negative floats order like their bit patterns)
@@ -463,7 +553,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
@@ -1238,9 +1328,9 @@ int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, floa
   return vitta_wmsa3d_fwd_amax(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr, stream);
 }
 
-int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
-                          void* stream) {
+static int wmsa3d_fwd_impl(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                           int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
+                           unsigned long long* trace, int trace_cap, void* stream) {
   VITTA_CHECK_ARG(qkv && bias_table && out && lse, VITTA_E_BADARG, "wmsa3d_fwd: null pointer");
   VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
   VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out), VITTA_E_ALIGN, "wmsa3d_fwd: tensors must be 16-byte aligned");
@@ -1248,10 +1338,13 @@ int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out,
   int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
   if (rc) return rc;
   p.qkv = qkv; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale; p.amax_out = out_amax;
+  p.trace = trace; p.trace_cap = trace_cap;
   p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wmsa3d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wmsa3d_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
     if (e != cudaSuccess) {
       set_error("wmsa3d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1262,9 +1355,27 @@ int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out,
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_fwd_kernel<<<grid, kFwdThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
+  if (trace)
+    wmsa3d_fwd_kernel<true><<<grid, kFwdThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
+  else
+    wmsa3d_fwd_kernel<false><<<grid, kFwdThreads, kAtSmemBytes, (cudaStream_t)stream>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
+                          void* stream) {
+  return wmsa3d_fwd_impl(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, out_amax, nullptr, 0,
+                         stream);
+}
+
+int vitta_wmsa3d_fwd_trace(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
+                           int heads, int head_dim, const int* window, const int* shift, float scale,
+                           unsigned long long* trace, int trace_cap, void* stream) {
+  VITTA_CHECK_ARG(trace && trace_cap > 1, VITTA_E_BADARG, "wmsa3d_fwd_trace: trace buffer required");
+  return wmsa3d_fwd_impl(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr, trace,
+                         trace_cap, stream);
 }
 
 static int wmsa3d_bwd_v0(const WmsaGeom& g, const float* qkv, const float* bias_table, const float* out,
