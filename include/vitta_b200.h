@@ -482,12 +482,15 @@ int vitta_row_scale_amax(const float* x, const float* scale, int64_t rows, int64
  *   as get_window_size (:71-84) does, and the bias index uses the configured window (relative_position_index[:N,:N]).
  *   D, H, W must be multiples of the clamped window (true for every 224x224 configuration; the zero-padding branch
  *   :222-227 returns VITTA_E_UNSUPPORTED).
- * Forward: tcgen05 (3xTF32) -- S = QK^T accumulates in TMEM, softmax in place, O += P V.
+ * Forward: tcgen05 -- S = QK^T (3xTF32) accumulates in TMEM, softmax in place, O += P V on kind::f16 with P and V as fp16
+ *   hi / lo pairs (22 mantissa bits; K = 16 per MMA halves the MMA issue count that bounds the kernel).  qkv_amax: device
+ *   scalar >= max|qkv| (as emitted by the qkv GEMM's epilogue, or vitta_amax_f32): the power-of-two scale of V's split.
  * Backward: dqkv has the layout of qkv (every element written once); dbias_table is ACCUMULATED into (zero it first).
  *   dS = P o (dO V^T - rowsum(dO o O)), dQ = scale dS K, dK = dS^T (scale Q), dV = P^T dO, dTable[rel(i,j)] += dS_ij.
  * ---------------------------------------------------------------------------------------------- */
-int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                     int heads, int head_dim, const int* window_host, const int* shift_host, float scale, void* stream);
+int vitta_wmsa3d_fwd(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B, int D,
+                     int H, int W, int heads, int head_dim, const int* window_host, const int* shift_host, float scale,
+                     void* stream);
 /* ws: vitta_wmsa3d_bwd_ws_floats() floats of scratch (D_i = dO_i . O_i per token and head; no init needed).
  * impl 0: tcgen05 (3xTF32) -- a query-outer launch (dQ, dTable) and a key-outer launch (dK, dV);
  * impl 1: the exact-fp32 FFMA2 kernel (one CTA per window and head), kept as an on-device cross-check. */
@@ -496,14 +499,14 @@ int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out
                      float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
                      const int* window_host, const int* shift_host, float scale, int impl, void* stream);
 /* The attention entry points with max|out| / max|dqkv| accumulated into a zero-initialised device scalar (null: off). */
-int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
-                          void* stream);
-/* Profiling aid: the forward kernel with time stamps.  trace = 14 x trace_cap records, zeroed by the caller: lane 0 of warp
+int vitta_wmsa3d_fwd_amax(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
+                          int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
+                          float* out_amax, void* stream);
+/* Profiling aid: the forward kernel with time stamps.  trace = 15 x trace_cap records, zeroed by the caller: lane 0 of warp
  * w of CTA 0 writes (clock << 16 | warp << 8 | event id) into trace[w * trace_cap ...] at the hand-over points of the
  * pipeline (event ids: csrc/wmsa3d.cu, WMSA_TR; tools/wmsa_trace.py prints the timeline).  Results = vitta_wmsa3d_fwd. */
-int vitta_wmsa3d_fwd_trace(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                           int heads, int head_dim, const int* window, const int* shift, float scale,
+int vitta_wmsa3d_fwd_trace(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
+                           int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
                            unsigned long long* trace, int trace_cap, void* stream);
 int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
                           const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,

@@ -26,14 +26,15 @@ def main():
     g = torch.Generator().manual_seed(0)
     qkv = (torch.randn(rows, 3 * c, generator=g) * 1.2).to(dev)
     table = (torch.randn((2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1), heads, generator=g) * 0.5).to(dev)
+    qam = qkv.abs().max().reshape(1).contiguous()
     out = torch.empty(rows, c, device=dev)
     nwin = rows // 392
     lse = torch.empty(nwin * heads * 392, device=dev)
     cap = 1 << 13
     i3 = lambda v: (C.c_int * 3)(*v)
     for rep in range(2):
-        trace = torch.zeros(14 * cap, dtype=torch.int64, device=dev)
-        call("vitta_wmsa3d_fwd_trace", ptr(qkv), ptr(table), ptr(out), ptr(lse), views, d, h, h, heads, 32, i3(window),
+        trace = torch.zeros(15 * cap, dtype=torch.int64, device=dev)
+        call("vitta_wmsa3d_fwd_trace", ptr(qkv), ptr(qam), ptr(table), ptr(out), ptr(lse), views, d, h, h, heads, 32, i3(window),
              i3(shift), float(32 ** -0.5), ptr(trace), cap, stream_ptr())
         torch.cuda.synchronize()
     t = trace.cpu().numpy().astype("uint64")
@@ -44,7 +45,7 @@ def main():
     starts = [r[0] for r in rec if r[1] == 0 and r[2] == 1]
     print("tile starts (warp 0), cycles between:", [starts[i + 1] - starts[i] for i in range(min(len(starts) - 1, 16))])
     lo, hi = starts[item * 4], starts[item * 4 + 5] if len(starts) > item * 4 + 5 else rec[-1][0]
-    keep = {0, 4, 8, 12, 13}
+    keep = {0, 4, 8, 12, 13, 14}
     for clk, w, e in rec:
         if lo - 3000 <= clk <= hi and w in keep:
             print("%8d  w%-2d %s" % (clk - lo, w, NAMES.get(e, str(e))))

@@ -115,11 +115,11 @@ _SIGNATURES = {
     "vitta_patchify3d": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_row_scale": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "vitta_row_scale_amax": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P]),
-    "vitta_wmsa3d_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "vitta_wmsa3d_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P]),
-    "vitta_wmsa3d_fwd_amax": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "vitta_wmsa3d_fwd_amax": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P, _P]),
-    "vitta_wmsa3d_fwd_trace": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "vitta_wmsa3d_fwd_trace": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, _P, C.c_int, _P]),
     "vitta_wmsa3d_bwd_amax": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P, _P]),

@@ -19,6 +19,8 @@
 //              writes P (hi / lo) chunk by chunk for the PV MMAs; finally O / rowsum is written out with log-sum-exp.
 //   The whole score row lives in TMEM, so there is no online-softmax rescaling and the N x N matrix never touches HBM.
 // Backward (v0): fp32 FFMA2 kernel, one CTA (384 threads) per item with Q, K, V, dO resident in shared memory (see wmsa3d_bwd_kernel).
+#include <cuda_fp16.h>
+
 #include "tc05.cuh"
 
 namespace vitta {
@@ -91,58 +93,81 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 // shared memory plan of the forward kernel (bytes from the 1024-aligned base)
 // ------------------------------------------------------------------------------------------------
 constexpr int kAtColPad = 416;                           // per-token arrays padded to a multiple of the 32-column chunk
-constexpr int kFwdVStages = 4;
+constexpr int kFwdVStages = 8;
 constexpr int kOffKhi = 0;
 constexpr int kOffKlo = kOffKhi + kAtMaxKeys * 128;      //  51200
 constexpr int kOffQhi = kOffKlo + kAtMaxKeys * 128;      // 102400
 constexpr int kOffQlo = kOffQhi + 128 * 128;             // 118784
-constexpr int kOffV = kOffQlo + 128 * 128;               // 135168: 4 stages x (hi 4 KB, lo 4 KB)
+constexpr int kOffV = kOffQlo + 128 * 128;               // 135168: 8 stages x (hi atom 4 KB, lo atom 4 KB)
 constexpr int kOffTab = kOffV + kFwdVStages * 8192;      // bias table of the current head (* log2 e)
 constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;
 constexpr int kOffTok = kOffInfo + kAtColPad * 4;
 constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;
-constexpr int kOffXch = kOffBar + 256;                   // row maximum / row sum exchange between the two softmax groups
-constexpr int kAtSmemBytes = kOffXch + 2 * 2 * 128 * 4 + 1024;   // ~185 KB
-// TMEM columns of the forward kernel: S [0, 400) -- the hi part of P chunk c overwrites S columns [32c, 32c + 32) once the
-// softmax has consumed them --, O [400, 432), lo part of P: one 32-column buffer per softmax group at 432 / 464
-constexpr uint32_t kFT_O = 400, kFT_Plo = 432;
+constexpr int kOffXch = kOffBar + 512;                   // row maximum / row sum exchange between the two softmax groups
+constexpr int kAtSmemBytes = kOffXch + 2 * 2 * 128 * 4 + 1024;   // ~218 KB
+// TMEM columns of the forward kernel: S [0, 400); the P chunk c (fp16 hi | lo, two keys per column) overwrites S columns
+// [32c, 32c + 32) once the softmax has consumed them; one O accumulator per softmax group / PV issuer at 400 and 432
+constexpr uint32_t kFT_O = 400;
 
 struct WmsaFwdParams {
   const float* qkv;     // (B, D, H, W, 3, heads, 32)
   const float* table;   // (nrel, heads)
+  const float* qkv_amax;   // device scalar >= max|qkv|: scale of V's fp16 operand split
   float* out;           // (B, D, H, W, heads*32)
   float* lse;           // ((b*nW + w)*heads + head)*N + i
   float scale;
   int items, items_per_cta;
   WmsaGeom g;
   float* amax_out;      // optional: max|out| (range of the fp16-split proj GEMM and its weight gradient)
-  unsigned long long* trace;   // TRACE instantiation only: 14 warps x trace_cap records (0 = unused)
+  unsigned long long* trace;   // TRACE instantiation only: 15 warps x trace_cap records (0 = unused)
   int trace_cap;
 };
 
-enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages,
-       B_S_FULL = B_V_FREE0 + kFwdVStages, B_S_FREE, B_P_READY0, B_P_READY1, B_P_FREE0, B_P_FREE1, B_O_FULL, B_O_FREE,
-       B_COUNT };
-static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
+constexpr int kPRing = 8;   // P_READY barriers per group: a group runs at most 7 chunks (one tile) ahead of its issuer
+enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_S_FULL, B_S_FREE, B_O_FULL, B_O_FREE,
+       B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages, B_P_READY0 = B_V_FREE0 + kFwdVStages,
+       B_COUNT = B_P_READY0 + 2 * kPRing };
+static_assert(B_COUNT * 8 + 8 <= 512, "barrier block");
+
+// D[tmem] (+)= A[tmem, packed fp16 pairs along K] * B[smem], kind::f16, issued by the lane with pe != 0
+__device__ __forceinline__ void umma_f16_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum,
+                                              uint32_t pe) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(pe)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 
 // warps 0-3 softmax group A, 4-7 softmax group B (TMEM lane quadrant = warp & 3), 8-11 loaders, 12 S issuer (+ TMEM
-// owner), 13 PV issuer.
+// owner), 13 PV issuer of group A, 14 PV issuer of group B.
 //
-// Round 2 ran ONE softmax group (4 warps, one per scheduler, nothing to overlap their tcgen05.ld -> LDS -> EX2 -> tcgen05.st
-// chains with) and one P buffer: ~36 K cycles per 128-row tile against ~5 K cycles of tensor work.  Now the 32-column
-// chunks of a tile alternate between two groups (by the parity of a global chunk counter), in both passes:
-//   pass 1  adds bias + mask in place (log2 domain) and takes the partial row maximum of the group's chunks; the two
-//           partial maxima of a row meet in shared memory behind a 64-thread named barrier (warps q and q + 4);
-//   pass 2  exponentiates, splits P into tf32 hi / lo; hi goes back IN PLACE over the consumed S columns, lo into the
-//           group's own 32-column buffer -- so the P operand of chunk c + 1 (other group) is written while the PV MMAs of
-//           chunk c run, instead of store -> MMA -> "buffer free" -> store in one serial chain per chunk.
-// Because P lives in the S columns, S is released for the next tile's Q K^T by the PV issuer (commit after the last
+// What bounds this kernel is the ISSUE of the P V MMAs, not the tensor pipe and not the softmax arithmetic (the kernel's
+// own time stamps: tools/wmsa_trace.py, profiles/r02_wmsa_fwd_timeline.md).  With tf32 operands a 32-key chunk is 4 K steps
+// x 3 split products = 12 MMAs of 128 x 32 x 8, each ~100 cycles of issue in one thread (~16 cycles of tensor work), plus
+// ~750 cycles of hand-over per chunk: 27 K of the 40 K cycles of a 128-row tile, during which eight softmax warps wait.
+// Hence:
+//   * P and V enter the P V product as fp16 hi / lo pairs (kind::f16, K = 16 per MMA: 6 MMAs per chunk).  P = 2^(t - m + 10)
+//     lies in [0, 1024]; V is scaled by the power of two that puts max|qkv| below 2^14 (the split
+//     the convolution GEMMs use; hi + lo carry 22 mantissa bits).  Output and log-sum-exp undo both scales exactly.
+//   * the 32-column chunks of a tile alternate between two softmax groups (parity of a global chunk counter), in both
+//     passes, and EACH GROUP HAS ITS OWN PV ISSUER AND ITS OWN O ACCUMULATOR: two independent issue streams; the epilogue
+//     adds the two accumulators.
+//   * a P chunk (16 packed hi + 16 packed lo columns) overwrites the S columns it was computed from, so there is no P
+//     buffer to hand back: a group writes all its chunks back to back, announcing each on a ring of mbarriers.
+//   pass 1 adds bias + mask in place (log2 domain) and takes the partial row maximum of the group's chunks; the two
+//   partial maxima (and later the partial sums) of a row meet in shared memory behind a 64-thread named barrier.
+// Because P lives in the S columns, S is released for the next tile's Q K^T by the PV issuers (commit after their last
 // chunk), not by the softmax warps.  The epilogue is split too: each group normalises and stores 16 of the 32 channels.
-constexpr int kFwdThreads = 448;
+constexpr int kFwdThreads = 480;
 
-// TRACE = true (vitta_wmsa3d_fwd_trace, a profiling aid): lane 0 of every warp of CTA 0 writes (clock << 16 | warp << 8 |
-// event id) records into its own slice of p.trace (plain stores, no atomics) at the hand-over points of the pipeline -- the timeline of one tile shows which role waits
-// for which (profiles/r02_wmsa_fwd_timeline.md); the production instantiation carries none of it.
 #define WMSA_TR(id)                                                                                              \
   do {                                                                                                           \
     if (TRACE && blockIdx.x == 0 && lane == 0 && tr_n < (uint32_t)p.trace_cap) {                                 \
@@ -180,9 +205,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       int cnt = 1;   // tcgen05.commit barriers
-      if (i == B_KV_READY || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i == B_P_READY0 || i == B_P_READY1)
+      if (i == B_KV_READY || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i >= B_P_READY0)
         cnt = 4;     // one elected arrive per warp of a 4-warp role
       if (i == B_TAB_FREE || i == B_O_FREE) cnt = 8;   // both softmax groups
+      if (i == B_S_FREE || i == B_O_FULL) cnt = 2;     // both PV issuers
       mbar_init(&bar[i], cnt);
     }
     fence_barrier_init();
@@ -204,6 +230,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     const int rslot = lt >> 3, q4 = lt & 7;
     int cur_head = -1;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    float sv, sv_inv_unused;
+    f16_split_scale(__ldg(p.qkv_amax), sv, sv_inv_unused);
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
@@ -266,6 +294,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
           if (t >= 0) v[u] = ldg4(qkv_h + ((int64_t)t * 3 + 2) * C);
         }
       };
+      // a V chunk in shared memory: two 16-bit MN-major SWIZZLE_128B atoms (hi, lo) of 32 keys x 128 bytes -- a row is one
+      // key holding its 32 channels as fp16 in the first four 16-byte chunks (chunk index XOR key % 8), the layout the
+      // weight-gradient kernel feeds its X operand with (wgrad_tf32.cu); the MMAs read N = 32 of the 64 columns
       auto v_drain = [&](float4 (&v)[8], int grp) {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -276,11 +307,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
             const int r = rslot + rr * 16;
-            float4 h, l;
-            split4(v[cc * 2 + rr], h, l);
-            const uint32_t o = mn32_off(r, q4);
-            *reinterpret_cast<float4*>(vb + o) = h;
-            *reinterpret_cast<float4*>(vb + 4096 + o) = l;
+            const float4 x = v[cc * 2 + rr];
+            const float x0 = x.x * sv, x1 = x.y * sv, x2 = x.z * sv, x3 = x.w * sv;
+            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+            const uint32_t o = (uint32_t)r * 128u + ((((uint32_t)q4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)q4 & 1u) * 8u;
+            *reinterpret_cast<uint2*>(vb + o) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(vb + 4096 + o) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
           fence_proxy_async();
           __syncwarp();
@@ -364,49 +400,52 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         WMSA_TR(31);
       }
     }
-  } else if (warp == 13) {
-    // =========================== PV issuer: O[128 x 32] += P_chunk V_chunk, P read from tensor memory ===============
+  } else if (warp == 13 || warp == 14) {
+    // =========================== PV issuers: O_grp[128 x 32] += P_chunk V_chunk over the group's chunks ===============
+    const int grp = __shfl_sync(0xffffffffu, warp - 13, 0);   // warp-uniform by construction; the shuffle makes it provable
     const uint32_t pe = (lane == 0) ? 1u : 0u;
-    const uint32_t idesc_o = umma_idesc_tf32(128, 32) | (1u << 16);   // B (= V) is MN-major
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 32) | (1u << 16);   // A in TMEM (packed fp16 pairs), B (= V) MN-major
     const uint32_t sbase = smem_u32(smem);
+    const uint32_t d = tmem_base + kFT_O + (uint32_t)grp * 32u;
     uint32_t tile_ctr = 0, chunk_ctr = 0;
     for (int item = item0; item < item1; ++item) {
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        uint32_t first = 1;
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
           const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);   // uniform registers for the descriptors / addresses
+          if ((ccu & 1u) != (uint32_t)grp) continue;
           const int st = ccu & (kFwdVStages - 1);
-          const int grp = ccu & 1;
+          const uint32_t own = ccu >> 1;                                  // index of this chunk among the group's chunks
           const uint32_t cu = __shfl_sync(0xffffffffu, (uint32_t)c, 0);
-          mbar_wait(&bar[B_P_READY0 + grp], (chunk_ctr >> 1) & 1);
+          mbar_wait(&bar[B_P_READY0 + grp * kPRing + (own & (kPRing - 1))], (own / kPRing) & 1);
           WMSA_TR(20);
           mbar_wait(&bar[B_V_READY0 + st], (chunk_ctr / kFwdVStages) & 1);
-          if (c == 0) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
+          if (first) mbar_wait(&bar[B_O_FREE], (tile_ctr & 1) ^ 1);
           tc_fence_after();
           WMSA_TR(21);
           const uint32_t vb = sbase + kOffV + st * 8192;
-          const uint64_t v_hi = umma_desc_mn_sw128(vb, 4096), v_lo = umma_desc_mn_sw128(vb + 4096, 4096);
+          const uint64_t v_hi = umma_desc_mn_sw128_f16(vb, 4096), v_lo = umma_desc_mn_sw128_f16(vb + 4096, 4096);
           const int left = g.N - c * 32;
-          const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
-          const uint32_t d = tmem_base + kFT_O;
-          const uint32_t p_hi = tmem_base + cu * 32u, p_lo = tmem_base + kFT_Plo + (uint32_t)grp * 32u;
+          const int ksteps = left >= 32 ? 2 : (left + 15) >> 4;
+          const int cols = min(32, g.NP - c * 32);
+          const uint32_t p_hi = tmem_base + cu * 32u, p_lo = p_hi + (uint32_t)(cols >> 1);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 2; ++k) {
             if (k < ksteps) {
-              const uint64_t advb = (uint64_t)(k * (1024 >> 4));
-              const uint32_t ka = (uint32_t)(k * 8);
-              umma_tf32_ts_p(d, p_lo + ka, v_hi + advb, idesc_o, (c | k) != 0, pe);
-              umma_tf32_ts_p(d, p_hi + ka, v_lo + advb, idesc_o, 1, pe);
-              umma_tf32_ts_p(d, p_hi + ka, v_hi + advb, idesc_o, 1, pe);
+              const uint64_t advb = (uint64_t)(k * (2048 >> 4));   // 16 keys = two 8-row atoms of 1024 B
+              const uint32_t ka = (uint32_t)(k * 8);               // 16 fp16 of P = 8 TMEM columns
+              umma_f16_ts_p(d, p_lo + ka, v_hi + advb, idesc_o, (first && k == 0) ? 0u : 1u, pe);
+              umma_f16_ts_p(d, p_hi + ka, v_lo + advb, idesc_o, 1, pe);
+              umma_f16_ts_p(d, p_hi + ka, v_hi + advb, idesc_o, 1, pe);
             }
           }
-          umma_commit_p(&bar[B_P_FREE0 + grp], pe);
+          first = 0;
           umma_commit_p(&bar[B_V_FREE0 + st], pe);
-          if (c == n_chunks - 1) {
-            umma_commit_p(&bar[B_O_FULL], pe);
-            umma_commit_p(&bar[B_S_FREE], pe);
-          }
           WMSA_TR(22);
         }
+        // (a group without a chunk in this tile -- single-chunk windows -- commits at once and its accumulator is not read)
+        umma_commit_p(&bar[B_O_FULL], pe);
+        umma_commit_p(&bar[B_S_FREE], pe);
       }
     }
   } else {
@@ -417,8 +456,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     const int rel0 = rel_row_base(g);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kMask2 = -100.f * kLog2e;
+    constexpr uint32_t kNegInf = 0xff800000u;
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     float out_amax = 0.f;
+    float sv_unused, sv_inv;
+    f16_split_scale(__ldg(p.qkv_amax), sv_unused, sv_inv);
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
@@ -436,30 +478,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         tc_fence_after();
         WMSA_TR(1);
         // ---- pass 1 (log2 domain): t = s*log2e + bias2 + mask2, in place; partial row maximum over this group's chunks.
-        //      Padding columns carry region id 31 and are therefore always masked (their P is ~2^-144 and multiplies
-        //      zero V rows).
+        //      Padding columns carry region id 31 and are therefore always masked; a 16-column last chunk is completed
+        //      with -inf in registers (no predicates inside the unrolled loops: they become branches around every
+        //      shared-memory load).
         float m2 = -INFINITY;
         if (warp_live) {
           for (int c = 0; c < n_chunks; ++c) {
             if (((chunk_ctr + c) & 1) != (uint32_t)grp) continue;
             const int cols = min(32, g.NP - c * 32);
+            uint32_t r[32];
+            tmem_ld16(t_lane + (uint32_t)(c * 32), r);
+            if (cols > 16) {
+              tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
+            } else {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              if (hf * 16 >= cols) break;
-              const int c0 = c * 32 + hf * 16;
-              uint32_t r[16];
-              tmem_ld16(t_lane + (uint32_t)c0, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                const int fj = info[c0 + jj];
-                float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
-                t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
-                m2 = fmaxf(m2, t);
-                r[jj] = __float_as_uint(t);
-              }
-              tmem_st16(t_lane + (uint32_t)c0, r);
+              for (int jj = 16; jj < 32; ++jj) r[jj] = kNegInf;
             }
+            tmem_ld_wait();
+            const int* ic = info + c * 32;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int fj = ic[jj];
+              float t = fmaf(__uint_as_float(r[jj]), kLog2e, tab[a_i - (fj & 0xffff)]);
+              t += ((fj & 0x1f0000) != r_i) ? kMask2 : 0.f;
+              m2 = fmaxf(m2, t);
+              r[jj] = __float_as_uint(t);
+            }
+            tmem_st16(t_lane + (uint32_t)(c * 32), r);
+            if (cols > 16) tmem_st16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
           }
           tmem_st_wait();
         }
@@ -473,44 +519,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[B_TAB_FREE]);
         }
-        // ---- pass 2: p = 2^(t - m2), partial row sum; P chunks (tf32 hi / lo) go to tensor memory as the A operand of PV
+        // ---- pass 2: p = 2^(t - m2 + 10), partial row sum; P chunks (fp16 hi / lo pairs) go back to tensor memory, over
+        //      the columns they came from, as the A operand of P V
         float l = 0.f;
+        const float m2s = m2 - 10.f;
         for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
           if ((chunk_ctr & 1) != (uint32_t)grp) continue;
-          uint32_t r[32], lo[32];
-          const int cols = min(32, g.NP - c * 32);
+          const uint32_t own = chunk_ctr >> 1;
           if (warp_live) {
+            const int cols = min(32, g.NP - c * 32);
+            uint32_t r[32], hi[16], lo[16];
             tmem_ld16(t_lane + (uint32_t)(c * 32), r);
-            if (cols > 16) tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
+            if (cols > 16) {
+              tmem_ld16(t_lane + (uint32_t)(c * 32 + 16), r + 16);
+            } else {
+#pragma unroll
+              for (int jj = 16; jj < 32; ++jj) r[jj] = kNegInf;
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              float pij = 0.f;
-              if (jj < 16 || cols > 16) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(__uint_as_float(r[jj]) - m2));
-              l += pij;
-              const uint32_t h = (__float_as_uint(pij) + 0x1000u) & 0xffffe000u;   // tf32 round-to-nearest of a finite value
-              r[jj] = h;
-              lo[jj] = __float_as_uint(pij - __uint_as_float(h));
+            for (int j = 0; j < 16; ++j) {
+              float p0, p1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(__uint_as_float(r[2 * j]) - m2s));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(__uint_as_float(r[2 * j + 1]) - m2s));
+              l += p0;
+              l += p1;
+              const __half2 h = __floats2half2_rn(p0, p1);          // key 2j in the low half (lower K index)
+              const float2 hf = __half22float2(h);
+              const __half2 lw = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
             }
-          }
-          WMSA_TR(10);
-          mbar_wait(&bar[B_P_FREE0 + grp], ((chunk_ctr >> 1) & 1) ^ 1);   // the group's lo buffer: MMAs of its previous chunk retired
-          WMSA_TR(11);
-          if (warp_live) {
-            tc_fence_after();
-            // hi: in place over the consumed S columns (a 16-column last chunk must not run into the O accumulator)
             if (cols > 16) {
-              tmem_st32(t_lane + (uint32_t)(c * 32), r);
-              tmem_st32(t_lane + kFT_Plo + (uint32_t)(grp * 32), lo);
-            } else {
-              tmem_st16(t_lane + (uint32_t)(c * 32), r);
-              tmem_st16(t_lane + kFT_Plo + (uint32_t)(grp * 32), lo);
+              tmem_st16(t_lane + (uint32_t)(c * 32), hi);
+              tmem_st16(t_lane + (uint32_t)(c * 32 + 16), lo);
+            } else {   // 16 keys: 8 + 8 columns
+              tmem_st8(t_lane + (uint32_t)(c * 32), hi);
+              tmem_st8(t_lane + (uint32_t)(c * 32 + 8), lo);
             }
             tmem_st_wait();
             tc_fence_before();
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_P_READY0 + grp]);
+          if (lane == 0) mbar_arrive(&bar[B_P_READY0 + grp * kPRing + (own & (kPRing - 1))]);
           WMSA_TR(12);
         }
         // the two partial sums of a row meet
@@ -518,29 +569,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
         l += xch_sum[(grp ^ 1) * 128 + row];
         WMSA_TR(5);
-        // ---- O / l -> global: this group's 16 of the 32 head channels
+        // ---- (O_A + O_B) / l -> global: this group's 16 of the 32 head channels
         mbar_wait(&bar[B_O_FULL], tile_ctr & 1);
         tc_fence_after();
         WMSA_TR(6);
-        uint32_t o[16];
+        uint32_t oa[16], ob[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) oa[q] = ob[q] = 0u;
         if (warp_live) {
-          tmem_ld16(t_lane + kFT_O + (uint32_t)(grp * 16), o);
+          // single-chunk windows: only the accumulator of the chunk's parity was written in this tile
+          const uint32_t first_par = (chunk_ctr - (uint32_t)n_chunks) & 1u;
+          if (n_chunks > 1 || first_par == 0u) tmem_ld16(t_lane + kFT_O + (uint32_t)(grp * 16), oa);
+          if (n_chunks > 1 || first_par == 1u) tmem_ld16(t_lane + kFT_O + 32u + (uint32_t)(grp * 16), ob);
           tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_O_FREE]);
         if (valid) {
-          const float inv = 1.f / l;
+          const float inv = sv_inv / l;    // l carries the factor 2^10 of P, the accumulators that factor and V's scale
           float* dst = p.out + (int64_t)my_tok * C + head * 32 + grp * 16;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 ov = make_float4(__uint_as_float(o[q * 4]) * inv, __uint_as_float(o[q * 4 + 1]) * inv,
-                                          __uint_as_float(o[q * 4 + 2]) * inv, __uint_as_float(o[q * 4 + 3]) * inv);
+            float4 ov;
+            ov.x = (__uint_as_float(oa[q * 4]) + __uint_as_float(ob[q * 4])) * inv;
+            ov.y = (__uint_as_float(oa[q * 4 + 1]) + __uint_as_float(ob[q * 4 + 1])) * inv;
+            ov.z = (__uint_as_float(oa[q * 4 + 2]) + __uint_as_float(ob[q * 4 + 2])) * inv;
+            ov.w = (__uint_as_float(oa[q * 4 + 3]) + __uint_as_float(ob[q * 4 + 3])) * inv;
             st4(dst + q * 4, ov);
             out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(ov.x), fabsf(ov.y)), fmaxf(fabsf(ov.z), fabsf(ov.w))));
           }
-          if (grp == 0) p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2 + log2f(l)) * 0.6931471805599453f;
+          if (grp == 0) p.lse[((int64_t)wg * g.heads + head) * g.N + i] = (m2s + log2f(l)) * 0.6931471805599453f;
         }
         WMSA_TR(7);
       }
@@ -1323,21 +1382,17 @@ using namespace vitta;
 
 extern "C" {
 
-int vitta_wmsa3d_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                     int heads, int head_dim, const int* window, const int* shift, float scale, void* stream) {
-  return vitta_wmsa3d_fwd_amax(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr, stream);
-}
 
-static int wmsa3d_fwd_impl(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                           int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
-                           unsigned long long* trace, int trace_cap, void* stream) {
-  VITTA_CHECK_ARG(qkv && bias_table && out && lse, VITTA_E_BADARG, "wmsa3d_fwd: null pointer");
+static int wmsa3d_fwd_impl(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
+                           int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
+                           float* out_amax, unsigned long long* trace, int trace_cap, void* stream) {
+  VITTA_CHECK_ARG(qkv && qkv_amax && bias_table && out && lse, VITTA_E_BADARG, "wmsa3d_fwd: null pointer");
   VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
   VITTA_CHECK_ARG(aligned16(qkv) && aligned16(out), VITTA_E_ALIGN, "wmsa3d_fwd: tensors must be 16-byte aligned");
   WmsaFwdParams p;
   int rc = wmsa_geom(B, D, H, W, heads, window, shift, &p.g);
   if (rc) return rc;
-  p.qkv = qkv; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale; p.amax_out = out_amax;
+  p.qkv = qkv; p.qkv_amax = qkv_amax; p.table = bias_table; p.out = out; p.lse = lse; p.scale = scale; p.amax_out = out_amax;
   p.trace = trace; p.trace_cap = trace_cap;
   p.items = B * p.g.nw0 * p.g.nw1 * p.g.nw2 * heads;
   static bool attr_done = false;
@@ -1363,19 +1418,25 @@ static int wmsa3d_fwd_impl(const float* qkv, const float* bias_table, float* out
   return 0;
 }
 
-int vitta_wmsa3d_fwd_amax(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                          int heads, int head_dim, const int* window, const int* shift, float scale, float* out_amax,
-                          void* stream) {
-  return wmsa3d_fwd_impl(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, out_amax, nullptr, 0,
-                         stream);
+int vitta_wmsa3d_fwd(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B, int D,
+                     int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale, void* stream) {
+  return wmsa3d_fwd_impl(qkv, qkv_amax, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr,
+                         nullptr, 0, stream);
 }
 
-int vitta_wmsa3d_fwd_trace(const float* qkv, const float* bias_table, float* out, float* lse, int B, int D, int H, int W,
-                           int heads, int head_dim, const int* window, const int* shift, float scale,
+int vitta_wmsa3d_fwd_amax(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
+                          int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
+                          float* out_amax, void* stream) {
+  return wmsa3d_fwd_impl(qkv, qkv_amax, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, out_amax,
+                         nullptr, 0, stream);
+}
+
+int vitta_wmsa3d_fwd_trace(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
+                           int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
                            unsigned long long* trace, int trace_cap, void* stream) {
   VITTA_CHECK_ARG(trace && trace_cap > 1, VITTA_E_BADARG, "wmsa3d_fwd_trace: trace buffer required");
-  return wmsa3d_fwd_impl(qkv, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr, trace,
-                         trace_cap, stream);
+  return wmsa3d_fwd_impl(qkv, qkv_amax, bias_table, out, lse, B, D, H, W, heads, head_dim, window, shift, scale, nullptr,
+                         trace, trace_cap, stream);
 }
 
 static int wmsa3d_bwd_v0(const WmsaGeom& g, const float* qkv, const float* bias_table, const float* out,

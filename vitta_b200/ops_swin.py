@@ -167,14 +167,15 @@ def wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale):
     c = heads * 32
     out = torch.empty(b * d * h * w, c, dtype=torch.float32, device=qkv.device)
     lse = torch.empty(b * d * h * w * heads, dtype=torch.float32, device=qkv.device)
+    qam = ops.operand_amax(qkv)     # range of V's fp16 operand split: emitted by the qkv GEMM's epilogue (else one amax pass)
     if ops.gemm_precision() == "f16x3":       # out is the operand of the fp16-split proj GEMM and of its weight gradient
         am = ops.new_amax(qkv.device)
-        call("vitta_wmsa3d_fwd_amax", ptr(qkv), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window),
-             _int3(shift), float(scale), ptr(am), stream_ptr())
+        call("vitta_wmsa3d_fwd_amax", ptr(qkv), ptr(qam), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32,
+             _int3(window), _int3(shift), float(scale), ptr(am), stream_ptr())
         ops._attach_amax(out, am)
         return out, lse
-    call("vitta_wmsa3d_fwd", ptr(qkv), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window), _int3(shift),
-         float(scale), stream_ptr())
+    call("vitta_wmsa3d_fwd", ptr(qkv), ptr(qam), ptr(table), ptr(out), ptr(lse), b, d, h, w, heads, 32, _int3(window),
+         _int3(shift), float(scale), stream_ptr())
     return out, lse
 
 
