@@ -480,8 +480,10 @@ int vitta_row_scale_amax(const float* x, const float* scale, int64_t rows, int64
  *   lse: (B*windows, heads, N) log-sum-exp per query row (saved for the backward);
  *   window / shift: the CONFIGURED 3-vectors (e.g. {8,7,7}, {4,3,3} or {0,0,0}); they are clamped per dimension exactly
  *   as get_window_size (:71-84) does, and the bias index uses the configured window (relative_position_index[:N,:N]).
- *   D, H, W must be multiples of the clamped window (true for every 224x224 configuration; the zero-padding branch
- *   :222-227 returns VITTA_E_UNSUPPORTED).
+ *   D, H, W must be multiples of the clamped window (true for every 224x224 configuration); other volumes are zero-padded
+ *   by the caller exactly as the reference pads them (:222-227: padding tokens carry the qkv bias, the shift mask is the
+ *   padded volume's, the result is cropped) -- vitta_b200.ops_swin.SwinAttentionFn does this; the raw entry points
+ *   return VITTA_E_UNSUPPORTED for a volume that is not a multiple.
  * Forward: tcgen05 -- S = QK^T (3xTF32) accumulates in TMEM, softmax in place, O += P V on kind::f16 with P and V as fp16
  *   hi / lo pairs (22 mantissa bits; K = 16 per MMA halves the MMA issue count that bounds the kernel).  qkv_amax: device
  *   scalar >= max|qkv| (as emitted by the qkv GEMM's epilogue, or vitta_amax_f32): the power-of-two scale of V's split.

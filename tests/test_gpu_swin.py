@@ -260,6 +260,45 @@ def test_swin_block_with_drop_path_vs_float64(cuda_device):
         cases.assert_close(gp, gr, 2e-4, 3e-5 * float(gr.abs().max()), "grad " + k)
 
 
+@pytest.mark.parametrize("d,h,w,shift", [(8, 10, 9, (4, 3, 3)), (12, 7, 16, (0, 0, 0)), (10, 14, 14, (4, 3, 3))])
+def test_swin_block_on_a_padded_token_volume_vs_float64(cuda_device, d, h, w, shift):
+    """Token volumes that are not multiples of the window: the reference zero-pads the normalised tokens
+    (swin_transformer.py:222-227), attends on the padded volume (padding tokens are keys with the qkv bias; the shift mask is
+    the padded volume's) and crops (:246-247).  Output, input gradient and every parameter gradient -- the qkv bias
+    receives the padding tokens' share -- against the float64 restatement."""
+    from oracle import vitta_oracle as O
+    from vitta_b200 import ops_swin
+    from vitta_b200.models.videoswintransformer_models.swin_transformer import SwinTransformerBlock3D
+    b, c, heads, window = 2, 64, 2, (8, 7, 7)
+    assert ops_swin.padded_token_dims((b, d, h, w), window) is not None
+    torch.manual_seed(11)
+    blk = SwinTransformerBlock3D(c, heads, window, shift, drop_path=0.0).to(cuda_device)
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.copy_(torch.randn_like(p_) * (0.3 if p_.dim() == 1 else 0.08))
+        blk.norm1.weight.add_(1.0)
+        blk.norm2.weight.add_(1.0)
+    x = _rnd(b, d, h, w, c, seed=7).requires_grad_(True)
+    y = blk(x)
+    go = _rnd(*y.shape, seed=8)
+    y.backward(go)
+    sd = {"blk." + k: v.detach().double().cpu().requires_grad_(v.dtype.is_floating_point) for k, v in blk.state_dict().items()
+          if "relative_position_index" not in k}
+    xd = x.detach().double().cpu().requires_grad_(True)
+    ws, ss = O.swin_window_and_shift((d, h, w), window, shift)
+    dp, hp, wp = (-(-e // s_) * s_ for e, s_ in zip((d, h, w), ws))
+    mask = O.swin_attn_mask(dp, hp, wp, ws, ss).double() if any(ss) else None
+    ref = O.swin_block(xd, sd, "blk", heads, window, shift, mask, O.swin_rel_index(window), None, 0.0, None)
+    ref.backward(go.double().cpu())
+    cases.assert_close(y.detach().cpu(), ref.detach(), 2e-5, 2e-5, "block output")
+    cases.assert_close(x.grad.cpu(), xd.grad, 1e-4, 2e-5 * float(xd.grad.abs().max()), "block input gradient")
+    for k in ("attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias", "norm1.weight",
+              "attn.relative_position_bias_table"):
+        gp = dict(blk.named_parameters())[k].grad.cpu()
+        gr = sd["blk." + k].grad
+        cases.assert_close(gp, gr, 2e-4, 3e-5 * float(gr.abs().max()), "grad " + k)
+
+
 # ----------------------------------------------------------------------------------------------
 # the whole Swin adaptation step vs the reference golden vectors
 # ----------------------------------------------------------------------------------------------

@@ -1359,8 +1359,8 @@ static int wmsa_geom(int B, int D, int H, int W, int heads, const int* window, c
       ss[i] = 0;
     }
     VITTA_CHECK_ARG(dims[i] % ws[i] == 0, VITTA_E_UNSUPPORTED,
-                    "wmsa3d: the token volume must be a multiple of the window (the zero-padding branch of "
-                    "swin_transformer.py:222-227 is not implemented)");
+                    "wmsa3d: the token volume must be a multiple of the window -- pad it first, as the reference does "
+                    "(swin_transformer.py:222-227; vitta_b200.ops_swin.SwinAttentionFn does so on the host side)");
   }
   g->B = B; g->D = D; g->H = H; g->W = W; g->heads = heads;
   g->ws0 = ws[0]; g->ws1 = ws[1]; g->ws2 = ws[2];

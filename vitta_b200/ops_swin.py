@@ -242,23 +242,64 @@ def layer_norm_rows(x, weight, bias, eps, arena=None, ly=None, want_alias=True):
 # ----------------------------------------------------------------------------------------------
 # K8 + K7: attention half-block   x + DropPath(proj(W-MSA(qkv(y))))
 # ----------------------------------------------------------------------------------------------
+def padded_token_dims(dims, window):
+    """(B, Dp, Hp, Wp) with every extent rounded up to a multiple of the clamped window (get_window_size,
+    swin_transformer.py:71-84, then the F.pad of :222-227), or None when the volume already is one."""
+    b, d, h, w = dims
+    ext = []
+    for x, wsz in zip((d, h, w), window):
+        ws = x if x <= wsz else wsz
+        ext.append(x + (-x) % ws)
+    return None if tuple(ext) == (d, h, w) else (b,) + tuple(ext)
+
+
+def _pad_tokens(t, dims, pdims, fill=None):
+    """(B*D*H*W, C) rows -> (B*Dp*Hp*Wp, C): the volume sits at the origin, the added tokens hold ``fill`` (a (C,) vector)
+    or zeros -- the reference pads the NORMALISED tokens with zeros (swin_transformer.py:227), so the padding tokens' qkv
+    row is the qkv bias."""
+    b, d, h, w = dims
+    _, dp, hp, wp = pdims
+    c = t.shape[1]
+    out = t.new_zeros(b, dp, hp, wp, c) if fill is None else fill.detach().to(t.dtype).expand(b, dp, hp, wp, c).contiguous()
+    out[:, :d, :h, :w] = t.view(b, d, h, w, c)
+    return out.view(-1, c)
+
+
+def _crop_tokens(t, pdims, dims):
+    b, d, h, w = dims
+    _, dp, hp, wp = pdims
+    return t.view(b, dp, hp, wp, t.shape[1])[:, :d, :h, :w].reshape(-1, t.shape[1])
+
+
 class SwinAttentionFn(torch.autograd.Function):
+    """A token volume that is not a multiple of the window (any resolution other than the 224 x 224 of the reference
+    configurations) is zero-padded the way the reference does (:222-227, :246-247): the attention kernels run on the padded
+    volume -- padding tokens take part as keys with q = k = v = the qkv bias, the shift mask is that of the padded
+    volume -- and the result is cropped.  The padding / cropping copies are torch ops: that path is correct, not tuned."""
+
     @staticmethod
     def forward(ctx, y, shortcut, wqkv, bqkv, table, wproj, bproj, dims, heads, window, shift, scale, rscale):
         _chk(y, "swin_attention")
         b, d, h, w = dims
         rows = b * d * h * w
-        qkv = gemm(y, wqkv, 0, bias=bqkv)
-        ao, lse = wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale)
+        pdims = padded_token_dims(dims, window)
+        qkv = gemm(y, wqkv, 0, bias=bqkv, want_amax=pdims is None)   # its range scales V's fp16 split in the attention kernel
+        if pdims is None:
+            ao, lse = wmsa3d_fwd(qkv, table, dims, heads, window, shift, scale)
+            ao_full = ao
+        else:
+            qkv = _pad_tokens(qkv, dims, pdims, fill=bqkv)
+            ao_full, lse = wmsa3d_fwd(qkv, table, pdims, heads, window, shift, scale)
+            ao = _crop_tokens(ao_full, pdims, dims)
         out = gemm(ao, wproj, 0, bias=bproj, residual=shortcut, row_scale=rscale, rows_per_group=rows // b)
-        ctx.save_for_backward(y, wqkv, table, wproj, qkv, ao, lse, rscale)
-        ctx.meta = (dims, heads, window, shift, scale, bqkv is not None, bproj is not None)
+        ctx.save_for_backward(y, wqkv, table, wproj, qkv, ao, lse, rscale, ao_full if pdims is not None else None)
+        ctx.meta = (dims, heads, window, shift, scale, bqkv is not None, bproj is not None, pdims)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        y, wqkv, table, wproj, qkv, ao, lse, rscale = ctx.saved_tensors
-        dims, heads, window, shift, scale, has_bqkv, has_bproj = ctx.meta
+        y, wqkv, table, wproj, qkv, ao, lse, rscale, ao_full = ctx.saved_tensors
+        dims, heads, window, shift, scale, has_bqkv, has_bproj, pdims = ctx.meta
         b = dims[0]
         g = g.contiguous()
         rpg = g.shape[0] // b
@@ -268,10 +309,20 @@ class SwinAttentionFn(torch.autograd.Function):
             dwproj, dbproj = linear_wgrad(ao, gs, want_bias=True)
         else:
             dwproj, dbproj = linear_wgrad(ao, gs), None
-        dqkv, dtable = wmsa3d_bwd(qkv, table, ao, dao, lse, dims, heads, window, shift, scale)
+        if pdims is None:
+            dqkv, dtable = wmsa3d_bwd(qkv, table, ao, dao, lse, dims, heads, window, shift, scale)
+            pad_bias = None
+        else:
+            # cropped outputs carry no gradient; the padding tokens' qkv rows are the bias, so their gradient joins d(bias)
+            dqkv_p, dtable = wmsa3d_bwd(qkv, table, ao_full, _pad_tokens(dao, dims, pdims), lse, pdims, heads, window, shift,
+                                        scale)
+            dqkv = _crop_tokens(dqkv_p, pdims, dims)
+            pad_bias = dqkv_p.sum(0) - dqkv.sum(0) if has_bqkv else None
         dy = gemm(dqkv, wqkv, 1)
         if has_bqkv:
             dwqkv, dbqkv = linear_wgrad(y, dqkv, want_bias=True)
+            if pad_bias is not None:
+                dbqkv = dbqkv + pad_bias
         else:
             dwqkv, dbqkv = linear_wgrad(y, dqkv), None
         return dy, g, dwqkv, dbqkv, dtable, dwproj, dbproj, None, None, None, None, None, None
