@@ -105,7 +105,7 @@ def _work(name, a):
         return WGRAD_FAM, _conv_flops(*g(*range(4, 13))), 0.0
     if name in ("vitta_wmsa3d_fwd", "vitta_wmsa3d_bwd", "vitta_wmsa3d_fwd_amax", "vitta_wmsa3d_bwd_amax"):
         fwd = name.startswith("vitta_wmsa3d_fwd")
-        i0 = 5 if fwd else 8     # (the forward takes qkv_amax after qkv)
+        i0 = 5 if fwd else 10    # (after the tensor arguments, which include the operand-range scalars)
         b_, d_, h_, w_, heads = g(*range(i0, i0 + 5))
         nwin = ntok = 1
         for dim, wsz in zip((d_, h_, w_), a[i0 + 6]):

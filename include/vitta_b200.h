@@ -494,12 +494,14 @@ int vitta_wmsa3d_fwd(const float* qkv, const float* qkv_amax, const float* bias_
                      int H, int W, int heads, int head_dim, const int* window_host, const int* shift_host, float scale,
                      void* stream);
 /* ws: vitta_wmsa3d_bwd_ws_floats() floats of scratch (D_i = dO_i . O_i per token and head; no init needed).
- * impl 0: tcgen05 (3xTF32) -- a query-outer launch (dQ, dTable) and a key-outer launch (dK, dV);
+ * impl 0: tcgen05, every product on kind::f16 with fp16 hi / lo operand pairs (qkv_amax, dout_amax: device scalars >= max|qkv|,
+ *         >= max|dout|: the power-of-two operand scales) -- a query-outer launch (dQ, dTable) and a key-outer launch (dK, dV);
  * impl 1: the exact-fp32 FFMA2 kernel (one CTA per window and head), kept as an on-device cross-check. */
 int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads);
-int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
-                     float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
-                     const int* window_host, const int* shift_host, float scale, int impl, void* stream);
+int vitta_wmsa3d_bwd(const float* qkv, const float* qkv_amax, const float* bias_table, const float* out, const float* dout,
+                     const float* dout_amax, const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H,
+                     int W, int heads, int head_dim, const int* window_host, const int* shift_host, float scale, int impl,
+                     void* stream);
 /* The attention entry points with max|out| / max|dqkv| accumulated into a zero-initialised device scalar (null: off). */
 int vitta_wmsa3d_fwd_amax(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
                           int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
@@ -510,10 +512,10 @@ int vitta_wmsa3d_fwd_amax(const float* qkv, const float* qkv_amax, const float* 
 int vitta_wmsa3d_fwd_trace(const float* qkv, const float* qkv_amax, const float* bias_table, float* out, float* lse, int B,
                            int D, int H, int W, int heads, int head_dim, const int* window, const int* shift, float scale,
                            unsigned long long* trace, int trace_cap, void* stream);
-int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
-                          const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,
-                          int heads, int head_dim, const int* window, const int* shift, float scale, int impl,
-                          float* dqkv_amax, void* stream);
+int vitta_wmsa3d_bwd_amax(const float* qkv, const float* qkv_amax, const float* bias_table, const float* out,
+                          const float* dout, const float* dout_amax, const float* lse, float* dqkv, float* dbias_table,
+                          float* ws, int B, int D, int H, int W, int heads, int head_dim, const int* window, const int* shift,
+                          float scale, int impl, float* dqkv_amax, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * View gathering + normalisation (the step before the hot path).

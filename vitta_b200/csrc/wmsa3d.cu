@@ -1346,6 +1346,494 @@ __global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBw
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward (v2): the skeleton of v1 (two launches: query-outer / key-outer) with EVERY product on kind::f16.
+//
+// What bounds these kernels is the number of dependent tcgen05.mma instructions and of hand-overs per 32-column chunk, not
+// tensor work (128 x 32 x 8 per MMA) or the row threads' arithmetic -- the forward kernel's time stamps show ~130 cycles
+// per dependent MMA and several hundred per mbarrier hand-over (profiles/r02_wmsa_fwd_timeline_*.txt).  v1 issued 12 tf32
+// MMAs per chunk and stream (4 K steps x 3 split products) and passed dS / P through ONE tensor-memory buffer
+// (store -> accumulate MMAs -> "buffer free" -> next store).  Here:
+//   * all operands are fp16 hi / lo pairs under per-tensor power-of-two scales (q, k, v: 2^14 / max|qkv|, dO: 2^14 /
+//     max|dO|; P * 2^10; dS * (those scales) * 2^-20 -- every factor is undone exactly in the epilogues): K = 16 per MMA,
+//     6 MMAs per chunk and stream;
+//   * dS (and P in the key-outer launch) are packed IN PLACE over the score columns they were computed from (each row
+//     thread owns 16 of a chunk's 32 columns: hi pairs in the first 8, lo pairs in the next 8), so there is no operand
+//     buffer to hand back: four score buffers rotate, released by the accumulate issuers' commits;
+//   * a column chunk is stored ONCE per tensor (fp16 hi + lo): 128-byte rows of 32 channels with the 16-byte chunk index
+//     XORed with row % 8 is at the same time the K-major SWIZZLE_128B operand of the score MMAs (row = N index) and the
+//     MN-major SWIZZLE_128B operand of the accumulate MMAs (row = K index); v1 wrote every chunk twice.
+// ------------------------------------------------------------------------------------------------
+struct WmsaBwd3Params {
+  const float* qkv;
+  const float* table;
+  const float* dout;
+  const float* lse;
+  const float* dsum;    // (tokens, heads)
+  const float* qkv_amax;
+  const float* dout_amax;
+  float* dqkv;
+  float* dtable;
+  float scale;
+  int items, items_per_cta;
+  WmsaGeom g;
+  float* amax_out;      // optional: max|dqkv| over both launches (range of the qkv data / weight gradient GEMMs)
+};
+
+constexpr int kB3Stages = 8;                        // column-chunk stages: C1 hi | lo, C2 hi | lo (4 KB each)
+constexpr int kB3StageBytes = 16384;
+constexpr int kB3Bufs = 4;                          // score buffers in tensor memory
+constexpr int kB3OffC = 0;
+constexpr int kB3OffDTab = kB3OffC + kB3Stages * kB3StageBytes;   // MODE 0: 8 warp-private table gradients
+constexpr int kB3OffTab = kB3OffDTab + 8 * kAtMaxRel * 4;         // bias table of the head (* log2 e)
+constexpr int kB3OffLse = kB3OffTab + kAtMaxRel * 4;              // float2 (lse * log2e, dsum * scales) per token
+constexpr int kB3OffInfo = kB3OffLse + kAtColPad * 8;
+constexpr int kB3OffTok = kB3OffInfo + kAtColPad * 4;
+constexpr int kB3OffBar = kB3OffTok + kAtColPad * 4;
+constexpr int kB3SmemBytes = kB3OffBar + 512 + 1024;              // 231424 <= 232448
+// TMEM columns: row tiles (packed fp16 pairs, 16 columns per 32 channels), score buffers b at 64 + 64 b (S | dP, 32 + 32),
+// accumulators
+constexpr uint32_t kT3R1hi = 0, kT3R1lo = 16, kT3R2hi = 32, kT3R2lo = 48, kT3SC = 64, kT3ACC1 = 320, kT3ACC2 = 352;
+
+enum { D_ITEM_READY = 0, D_ITEM_FREE, D_ROWS_READY, D_ROWS_FREE, D_ACC_FULL, D_ACC_FREE, D_COL_READY0,
+       D_COL_FREE0 = D_COL_READY0 + kB3Stages, D_SC_FULL0 = D_COL_FREE0 + kB3Stages, D_E_READY0 = D_SC_FULL0 + kB3Bufs,
+       D_SC_FREE0 = D_E_READY0 + kB3Bufs, D_COUNT = D_SC_FREE0 + kB3Bufs };
+static_assert(D_COUNT * 8 + 8 <= 512, "barrier block");
+
+// fp16 hi / lo pair words of (x0, x1): element 0 in the low half (lower K index)
+__device__ __forceinline__ void f16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int kB3Threads = 512;   // warps 0-7 row threads (TMEM lane quadrant = w & 3, column half = w >> 2), 8-11 loaders,
+                                  // 12-15 MMA issuers (S, dP, ACC1, ACC2)
+
+template <int MODE>
+__global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBwd3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kB3OffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + D_COUNT);
+  float* tab = reinterpret_cast<float*>(smem + kB3OffTab);
+  float* dtab = reinterpret_cast<float*>(smem + kB3OffDTab);
+  float2* sLD = reinterpret_cast<float2*>(smem + kB3OffLse);
+  int* info = reinterpret_cast<int*>(smem + kB3OffInfo);
+  int* tok = reinterpret_cast<int*>(smem + kB3OffTok);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const WmsaGeom& g = p.g;
+  const int C = g.heads * 32;
+  const int nwin = g.nw0 * g.nw1 * g.nw2;
+  const int nwin_total = g.B * nwin;
+  const int n_tiles = (g.N + 127) >> 7;
+  const int n_chunks = (g.N + 31) >> 5;
+  const int item0 = blockIdx.x * p.items_per_cta;
+  const int item1 = min(p.items, item0 + p.items_per_cta);
+  constexpr int kAccIssuers = MODE == 1 ? 2 : 1;
+  // operand scales (powers of two): q, k, v -> * sq;  dO -> * sd
+  float sq, inv_sq, sd, inv_sd;
+  f16_split_scale(__ldg(p.qkv_amax), sq, inv_sq);
+  f16_split_scale(__ldg(p.dout_amax), sd, inv_sd);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < D_COUNT; ++i) {
+      int cnt = kAccIssuers;   // COL_FREE, SC_FREE, ACC_FULL: one tcgen05.commit per accumulate issuer
+      if ((i >= D_SC_FULL0 && i < D_E_READY0) || i == D_ROWS_FREE) cnt = 2;   // one commit per score issuer
+      if (i == D_ITEM_READY || i == D_ROWS_READY || (i >= D_COL_READY0 && i < D_COL_FREE0))
+        cnt = 4;     // one elected arrive per loader warp
+      if (i == D_ITEM_FREE || (i >= D_E_READY0 && i < D_SC_FREE0) || i == D_ACC_FREE)
+        cnt = 8;     // one elected arrive per row warp
+      mbar_init(&bar[i], cnt);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // (uniform value made provably uniform)
+
+  if (warp >= 8 && warp < 12) {
+    // =========================== loaders ===========================
+    const int lt = threadIdx.x - 256;
+    const int rslot = lt >> 3, q4 = lt & 7;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 8) * 32) << 16);   // this warp's TMEM lane quadrant
+    int cur_head = -1;
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    // scale of the operand (which 0: R1 / C1, 1: R2 / C2) -- MODE 0 rows: Qs, dO; columns: K, V.  MODE 1 rows: K, V;
+    // columns: Qs, dO
+    const float s_r1 = (MODE == 0) ? p.scale * sq : sq, s_r2 = (MODE == 0) ? sd : sq;
+    const float s_c1 = (MODE == 0) ? sq : p.scale * sq, s_c2 = (MODE == 0) ? sq : sd;
+    auto flush_dtab = [&](int head) {
+      for (int i = lt; i < g.nrel; i += 128) {
+        float v = 0.f;
+#pragma unroll
+        for (int cpy = 0; cpy < 8; ++cpy) v += dtab[cpy * kAtMaxRel + i];
+        if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + head, v);
+      }
+    };
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      const int wg = item - head * nwin_total;
+      const int b = wg / nwin;
+      int w = wg - b * nwin;
+      const int ww = w % g.nw2; w /= g.nw2;
+      const int wh = w % g.nw1;
+      const int wd = w / g.nw1;
+      mbar_wait(&bar[D_ITEM_FREE], (it & 1) ^ 1);
+      if (head != cur_head) {
+        if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
+        for (int i = lt; i < g.nrel; i += 128) {
+          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
+          if (MODE == 0) {
+#pragma unroll
+            for (int cpy = 0; cpy < 8; ++cpy) dtab[cpy * kAtMaxRel + i] = 0.f;
+          }
+        }
+        cur_head = head;
+      }
+      for (int i = lt; i < kAtColPad; i += 128) {
+        int t = -1, f = 31 << 16;                 // padding columns: region id 31 = always masked
+        float2 q = make_float2(INFINITY, 0.f);    // ... and lse = +inf: p = 0 exactly when they are queries
+        if (i < g.N) {
+          window_token(g, b, wd, wh, ww, i, t, f);
+          q.x = __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) * 1.4426950408889634f;
+          q.y = (__ldg(p.dsum + (int64_t)t * g.heads + head) * sd) * sq;      // D_i in the units of the dP accumulator
+        }
+        tok[i] = t;
+        info[i] = f;
+        sLD[i] = q;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[D_ITEM_READY]);
+      const float* qkv_h = p.qkv + head * 32;
+      const float* do_h = p.dout + head * 32;
+      // row operand (which 0: R1, 1: R2) / column operand of token t; q = float4 index inside the 32-float head slice
+      auto load_row = [&](int which, int t, int q) -> float4 {
+        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 0) return which == 0 ? ldg4(qkv_h + (int64_t)t * 3 * C + q * 4) : ldg4(do_h + (int64_t)t * C + q * 4);
+        return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q * 4);
+      };
+      auto load_col = [&](int which, int t) -> float4 {
+        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 0) return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q4 * 4);
+        return which == 0 ? ldg4(qkv_h + (int64_t)t * 3 * C + q4 * 4) : ldg4(do_h + (int64_t)t * C + q4 * 4);
+      };
+      // column chunks: 2 chunks per group (2 tensors x 2 rows x 2 chunks = 8 float4 per thread)
+      auto c_issue = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cc = u >> 2, which = (u >> 1) & 1, rr = u & 1;
+          const int j = (grp * 2 + cc) * 32 + rslot + rr * 16;
+          const int t = (grp * 2 + cc < n_chunks) ? tok[j] : -1;
+          v[u] = load_col(which, t);
+        }
+      };
+      auto c_drain = [&](float4 (&v)[8], int grp) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (grp * 2 + cc >= n_chunks) break;
+          const int st = chunk_ctr & (kB3Stages - 1);
+          mbar_wait(&bar[D_COL_FREE0 + st], ((chunk_ctr / kB3Stages) & 1) ^ 1);
+          uint8_t* cb = smem + kB3OffC + st * kB3StageBytes;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            const float sc = which ? s_c2 : s_c1;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int r = rslot + rr * 16;
+              const float4 x = v[cc * 4 + which * 2 + rr];
+              uint32_t h0, l0, h1, l1;
+              f16_pair(x.x * sc, x.y * sc, h0, l0);
+              f16_pair(x.z * sc, x.w * sc, h1, l1);
+              const uint32_t o = (uint32_t)r * 128u + ((((uint32_t)q4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)q4 & 1u) * 8u;
+              uint8_t* base = cb + which * 8192;
+              *reinterpret_cast<uint2*>(base + o) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(base + 4096 + o) = make_uint2(l0, l1);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[D_COL_READY0 + st]);
+          ++chunk_ctr;
+        }
+      };
+      const int n_groups = (n_chunks + 1) >> 1;
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        // row tile: thread = row (TMEM lane); both rows' global loads are in flight before the wait
+        const int i = tile * 128 + (warp - 8) * 32 + lane;
+        const int trow = (i < g.N) ? tok[i] : -1;
+        float4 ra[8], rb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          ra[u] = load_row(0, trow, u);
+          rb[u] = load_row(1, trow, u);
+        }
+        mbar_wait(&bar[D_ROWS_FREE], (tile_ctr & 1) ^ 1);
+        tc_fence_after();
+        {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            f16_pair(ra[u].x * s_r1, ra[u].y * s_r1, hi[2 * u], lo[2 * u]);
+            f16_pair(ra[u].z * s_r1, ra[u].w * s_r1, hi[2 * u + 1], lo[2 * u + 1]);
+          }
+          tmem_st16(t_lane + kT3R1hi, hi);
+          tmem_st16(t_lane + kT3R1lo, lo);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            f16_pair(rb[u].x * s_r2, rb[u].y * s_r2, hi[2 * u], lo[2 * u]);
+            f16_pair(rb[u].z * s_r2, rb[u].w * s_r2, hi[2 * u + 1], lo[2 * u + 1]);
+          }
+          tmem_st16(t_lane + kT3R2hi, hi);
+          tmem_st16(t_lane + kT3R2lo, lo);
+        }
+        float4 va[8], vb8[8];
+        c_issue(va, 0);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[D_ROWS_READY]);
+        for (int grp = 0; grp < n_groups; grp += 2) {
+          if (grp + 1 < n_groups) c_issue(vb8, grp + 1);
+          c_drain(va, grp);
+          if (grp + 2 < n_groups) c_issue(va, grp + 2);
+          if (grp + 1 < n_groups) c_drain(vb8, grp + 1);
+        }
+      }
+    }
+    if (MODE == 0 && cur_head >= 0) {
+      mbar_wait(&bar[D_ITEM_FREE], (it & 1) ^ 1);   // the row threads finished the last item
+      flush_dtab(cur_head);
+    }
+  } else if (warp >= 12) {
+    // =========================== MMA issuers ===========================
+    // warp 12: S / S^T, warp 13: dP / dP^T, warp 14: ACC1 (dQ | dK), warp 15: ACC2 (dV, MODE 1 only).  They touch disjoint
+    // accumulators; ordering against the other roles goes through the mbarriers.
+    const int which = __shfl_sync(0xffffffffu, warp & 1, 0);   // warp-uniform by construction; the shuffle makes it provable
+    const bool is_score = warp < 14;
+    const uint32_t pe = (lane == 0) ? 1u : 0u;
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t tile_ctr = 0, chunk_ctr = 0;
+    if (is_score) {
+      constexpr uint32_t idesc_sc = umma_idesc_f16(128, 32);      // A in TMEM (packed pairs along the channels), B K-major
+      const uint32_t a_hi = tmem_base + (which ? kT3R2hi : kT3R1hi), a_lo = tmem_base + (which ? kT3R2lo : kT3R1lo);
+      for (int item = item0; item < item1; ++item) {
+        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+          mbar_wait(&bar[D_ROWS_READY], tile_ctr & 1);
+          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+            const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);   // uniform registers for descriptors / addresses
+            const int st = ccu & (kB3Stages - 1);
+            const int sb = ccu & (kB3Bufs - 1);
+            mbar_wait(&bar[D_COL_READY0 + st], (chunk_ctr / kB3Stages) & 1);
+            mbar_wait(&bar[D_SC_FREE0 + sb], ((chunk_ctr / kB3Bufs) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t cb = sbase + kB3OffC + st * kB3StageBytes + which * 8192;
+            const uint64_t c_hi = umma_desc_sw128(cb), c_lo = umma_desc_sw128(cb + 4096);
+            const uint32_t d = tmem_base + kT3SC + (uint32_t)(sb * 64 + which * 32);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);      // 16 channels = 32 bytes along the row
+              const uint32_t ka = (uint32_t)(k * 8);
+              umma_f16_ts_p(d, a_lo + ka, c_hi + adv, idesc_sc, k != 0, pe);
+              umma_f16_ts_p(d, a_hi + ka, c_lo + adv, idesc_sc, 1, pe);
+              umma_f16_ts_p(d, a_hi + ka, c_hi + adv, idesc_sc, 1, pe);
+            }
+            umma_commit_p(&bar[D_SC_FULL0 + sb], pe);
+            if (c == n_chunks - 1) umma_commit_p(&bar[D_ROWS_FREE], pe);   // the row tile is reusable when these retire
+          }
+        }
+      }
+    } else if (which == 0 || MODE == 1) {
+      constexpr uint32_t idesc_ac = umma_idesc_f16(128, 32) | (1u << 16);   // B MN-major
+      const uint32_t acc = tmem_base + (which ? kT3ACC2 : kT3ACC1);
+      for (int item = item0; item < item1; ++item) {
+        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+            const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);
+            const int st = ccu & (kB3Stages - 1);
+            const int sb = ccu & (kB3Bufs - 1);
+            mbar_wait(&bar[D_E_READY0 + sb], (chunk_ctr / kB3Bufs) & 1);
+            if (c == 0) mbar_wait(&bar[D_ACC_FREE], (tile_ctr & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t cb = sbase + kB3OffC + st * kB3StageBytes + which * 8192;
+            const uint64_t m_hi = umma_desc_mn_sw128_f16(cb, 4096), m_lo = umma_desc_mn_sw128_f16(cb + 4096, 4096);
+            // E operand of this stream: dS over the S columns (which 0), P over the dP columns (which 1); per 16-key K step
+            // the hi pairs sit in the first 8 of the step's 16 columns, the lo pairs in the next 8
+            const uint32_t e = tmem_base + kT3SC + (uint32_t)(sb * 64 + which * 32);
+            const int left = g.N - c * 32;
+            const int ksteps = left >= 32 ? 2 : (left + 15) >> 4;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (k < ksteps) {
+                const uint64_t advb = (uint64_t)(k * (2048 >> 4));   // 16 keys = two 8-row atoms of 1024 B
+                const uint32_t ka = (uint32_t)(k * 16);
+                umma_f16_ts_p(acc, e + ka + 8u, m_hi + advb, idesc_ac, (c | k) != 0, pe);
+                umma_f16_ts_p(acc, e + ka, m_lo + advb, idesc_ac, 1, pe);
+                umma_f16_ts_p(acc, e + ka, m_hi + advb, idesc_ac, 1, pe);
+              }
+            }
+            umma_commit_p(&bar[D_SC_FREE0 + sb], pe);
+            umma_commit_p(&bar[D_COL_FREE0 + st], pe);
+            if (c == n_chunks - 1) umma_commit_p(&bar[D_ACC_FULL], pe);
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== row threads ===========================
+    // thread = (row of the tile = TMEM lane, column half): warps w and w + 4 share a lane quadrant and split the 32 columns
+    // of every chunk, which doubles the warps available to hide the latency of the per-element chain.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int rel0 = rel_row_base(g);
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kMask2 = -100.f * kLog2e;
+    const float* __restrict__ tab2 = tab;                        // bias table, pre-multiplied by log2(e) by the loaders
+    float* __restrict__ mytab = dtab + warp * kAtMaxRel;         // this warp's private table gradient (no atomics)
+    const float c_s = (inv_sq * inv_sq) * kLog2e;                // score accumulator -> log2 domain
+    constexpr float kDsDown = 9.5367431640625e-07f;              // 2^-20: dS in the units of its fp16 operand
+    constexpr float kDsUp = 1048576.f;
+    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
+    float out_amax = 0.f;
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      mbar_wait(&bar[D_ITEM_READY], it & 1);
+      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
+        const int i = tile * 128 + row;
+        const bool valid = i < g.N;
+        const int ii = valid ? i : 0;
+        const int f_row = info[ii];
+        const int b_row = f_row & 0xffff;
+        const int r_row = f_row & 0x1f0000;
+        const int my_tok = tok[ii];
+        const float2 ld_row = sLD[ii];
+        const int kidx = (MODE == 0) ? (b_row + rel0) : (rel0 - b_row);
+        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
+          const int sb = chunk_ctr & (kB3Bufs - 1);
+          mbar_wait(&bar[D_SC_FULL0 + sb], (chunk_ctr / kB3Bufs) & 1);
+          tc_fence_after();
+          const uint32_t sc = t_lane + kT3SC + (uint32_t)(sb * 64 + half * 16);
+          uint32_t s[16], d[16];
+          tmem_ld16(sc, s);
+          tmem_ld16(sc + 32u, d);
+          tmem_ld_wait();
+          // per element: p = 2^(s*log2e + bias2 + mask2 - lse2), ds = p * (dp - dsum).  The per-token arrays are padded to
+          // a multiple of 32 columns: padding columns carry region id 31 (always masked: p flushes to 0) and, as
+          // queries (MODE 1), lse = +inf (p = 0 exactly), so no bounds selects are needed here.
+          const int col0 = c * 32 + half * 16;
+          const int* ic = info + col0;
+          float pv[16], dsv[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int fc = ic[jj];
+            const int idx = (MODE == 0) ? (kidx - (fc & 0xffff)) : (kidx + (fc & 0xffff));
+            float t = fmaf(__uint_as_float(s[jj]), c_s, tab2[idx]);
+            t += ((fc & 0x1f0000) != r_row) ? kMask2 : 0.f;
+            float lse2, dsum;
+            if (MODE == 0) {
+              lse2 = ld_row.x;
+              dsum = ld_row.y;
+            } else {
+              const float2 q = sLD[col0 + jj];
+              lse2 = q.x;
+              dsum = q.y;
+            }
+            float pij;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(t - lse2));
+            pv[jj] = pij;
+            dsv[jj] = pij * (__uint_as_float(d[jj]) - dsum) * kDsDown;     // dS * sd * sq * 2^-20
+          }
+          if (MODE == 0) {
+            // dTable[rel(i, j)] += dS_ij.  Lanes of a warp are distinct rows => distinct entries for one column, so a
+            // predicated straight-line LDS / FADD / STS on the warp-private copy is race free; program order keeps the
+            // successive columns of a thread coherent.
+            const float k_dt = (kDsUp * inv_sd) * inv_sq;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int fc = ic[jj];
+              const int idx = kidx - (fc & 0xffff);
+              const bool ok = valid && (col0 + jj < g.N);
+              const float o = mytab[ok ? idx : 0];
+              if (ok) mytab[idx] = fmaf(dsv[jj], k_dt, o);
+            }
+          }
+          // fp16 hi / lo pairs, straight back into tensor memory over this thread's 16 score columns: the A operand of the
+          // accumulate MMAs (key 2u in the low half of column u)
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f16_pair(dsv[2 * u], dsv[2 * u + 1], hi[u], lo[u]);
+          tmem_st8(sc, hi);
+          tmem_st8(sc + 8u, lo);
+          if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f16_pair(pv[2 * u] * 1024.f, pv[2 * u + 1] * 1024.f, hi[u], lo[u]);
+            tmem_st8(sc + 32u, hi);
+            tmem_st8(sc + 40u, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[D_E_READY0 + sb]);
+        }
+        // ---- accumulators -> global (this thread's 16 of the 32 head channels)
+        mbar_wait(&bar[D_ACC_FULL], tile_ctr & 1);
+        tc_fence_after();
+        uint32_t a1[16], a2[16];
+        tmem_ld16(t_lane + kT3ACC1 + (uint32_t)(half * 16), a1);
+        if (MODE == 1) tmem_ld16(t_lane + kT3ACC2 + (uint32_t)(half * 16), a2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[D_ACC_FREE]);
+        if (valid) {
+          // undo the operand scales (exact: powers of two, applied one after the other)
+          const float k1 = ((MODE == 0 ? p.scale : 1.f) * kDsUp * inv_sd) * inv_sq;      // (* inv_sq once more below)
+          const float k2 = 0.0009765625f * inv_sd;                                       // dV: P * 2^10, dO * sd
+          float* dst = p.dqkv + ((int64_t)my_tok * 3 + (MODE == 0 ? 0 : 1)) * C + head * 32 + half * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o1;
+            o1.x = (__uint_as_float(a1[q * 4]) * k1) * inv_sq; o1.y = (__uint_as_float(a1[q * 4 + 1]) * k1) * inv_sq;
+            o1.z = (__uint_as_float(a1[q * 4 + 2]) * k1) * inv_sq; o1.w = (__uint_as_float(a1[q * 4 + 3]) * k1) * inv_sq;
+            st4(dst + q * 4, o1);
+            out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(o1.x), fabsf(o1.y)), fmaxf(fabsf(o1.z), fabsf(o1.w))));
+            if (MODE == 1) {
+              float4 o2;
+              o2.x = __uint_as_float(a2[q * 4]) * k2; o2.y = __uint_as_float(a2[q * 4 + 1]) * k2;
+              o2.z = __uint_as_float(a2[q * 4 + 2]) * k2; o2.w = __uint_as_float(a2[q * 4 + 3]) * k2;
+              st4(dst + C + q * 4, o2);
+              out_amax = fmaxf(out_amax, fmaxf(fmaxf(fabsf(o2.x), fabsf(o2.y)), fmaxf(fabsf(o2.z), fabsf(o2.w))));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[D_ITEM_FREE]);   // tab / dtab / info / tok / lse of this item no longer needed
+    }
+    if (p.amax_out) {
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
+      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 static int wmsa_geom(int B, int D, int H, int W, int heads, const int* window, const int* shift, WmsaGeom* g) {
   VITTA_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && heads > 0 && window && shift, VITTA_E_BADARG, "wmsa3d: bad shape");
   const int dims[3] = {D, H, W};
@@ -1470,17 +1958,18 @@ int64_t vitta_wmsa3d_bwd_ws_floats(int B, int D, int H, int W, int heads) {
   return (int64_t)B * D * H * W * heads;
 }
 
-int vitta_wmsa3d_bwd(const float* qkv, const float* bias_table, const float* out, const float* dout, const float* lse,
-                     float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W, int heads, int head_dim,
-                     const int* window, const int* shift, float scale, int impl, void* stream) {
-  return vitta_wmsa3d_bwd_amax(qkv, bias_table, out, dout, lse, dqkv, dbias_table, ws, B, D, H, W, heads, head_dim, window,
-                               shift, scale, impl, nullptr, stream);
+int vitta_wmsa3d_bwd(const float* qkv, const float* qkv_amax, const float* bias_table, const float* out, const float* dout,
+                     const float* dout_amax, const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H,
+                     int W, int heads, int head_dim, const int* window, const int* shift, float scale, int impl,
+                     void* stream) {
+  return vitta_wmsa3d_bwd_amax(qkv, qkv_amax, bias_table, out, dout, dout_amax, lse, dqkv, dbias_table, ws, B, D, H, W, heads,
+                               head_dim, window, shift, scale, impl, nullptr, stream);
 }
 
-int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float* out, const float* dout,
-                          const float* lse, float* dqkv, float* dbias_table, float* ws, int B, int D, int H, int W,
-                          int heads, int head_dim, const int* window, const int* shift, float scale, int impl,
-                          float* dqkv_amax, void* stream) {
+int vitta_wmsa3d_bwd_amax(const float* qkv, const float* qkv_amax, const float* bias_table, const float* out,
+                          const float* dout, const float* dout_amax, const float* lse, float* dqkv, float* dbias_table,
+                          float* ws, int B, int D, int H, int W, int heads, int head_dim, const int* window, const int* shift,
+                          float scale, int impl, float* dqkv_amax, void* stream) {
   VITTA_CHECK_ARG(!(impl == 1 && dqkv_amax), VITTA_E_UNSUPPORTED, "wmsa3d_bwd: the fp32 cross-check kernel emits no range");
   VITTA_CHECK_ARG(qkv && bias_table && out && dout && lse && dqkv && dbias_table, VITTA_E_BADARG, "wmsa3d_bwd: null pointer");
   VITTA_CHECK_ARG(head_dim == 32, VITTA_E_UNSUPPORTED, "wmsa3d: head_dim must be 32 (every Video-Swin configuration)");
@@ -1492,6 +1981,7 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) return wmsa3d_bwd_v0(g, qkv, bias_table, out, dout, lse, dqkv, dbias_table, scale, st);
   VITTA_CHECK_ARG(ws, VITTA_E_BADARG, "wmsa3d_bwd: workspace of vitta_wmsa3d_bwd_ws_floats() floats required");
+  VITTA_CHECK_ARG(qkv_amax && dout_amax, VITTA_E_BADARG, "wmsa3d_bwd: the operand ranges (qkv_amax, dout_amax) are required");
   const int64_t n_pairs = (int64_t)B * D * H * W * heads;
   {
     int64_t blocks = (n_pairs + 31) / 32;
@@ -1499,16 +1989,17 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float
     wmsa3d_dsum_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, dout, ws, n_pairs);
     VITTA_CHECK_LAUNCH();
   }
-  WmsaBwd2Params p;
+  WmsaBwd3Params p;
   p.g = g;
   p.qkv = qkv; p.table = bias_table; p.dout = dout; p.lse = lse; p.dsum = ws; p.dqkv = dqkv; p.dtable = dbias_table;
+  p.qkv_amax = qkv_amax; p.dout_amax = dout_amax;
   p.scale = scale; p.amax_out = dqkv_amax;
   p.items = B * g.nw0 * g.nw1 * g.nw2 * heads;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(wmsa3d_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
+      e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
     if (e != cudaSuccess) {
       set_error("wmsa3d_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1519,9 +2010,9 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* bias_table, const float
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_bwd2_kernel<0><<<grid, kB2Threads, kB2SmemBytes, st>>>(p);
+  wmsa3d_bwd3_kernel<0><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
-  wmsa3d_bwd2_kernel<1><<<grid, kB2Threads, kB2SmemBytes, st>>>(p);
+  wmsa3d_bwd3_kernel<1><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
   return 0;
 }

@@ -185,14 +185,17 @@ def wmsa3d_bwd(qkv, table, out, dout, lse, dims, heads, window, shift, scale, im
     dqkv = torch.empty_like(qkv)
     dtable = torch.zeros_like(table)
     ws = _workspace("wmsa_bwd", b * d * h * w * heads, qkv.device, False)
+    # ranges of the fp16 operand splits (impl 0): emitted by the producing GEMM epilogues, else one amax pass each
+    qam = ptr(ops.operand_amax(qkv)) if impl == 0 else None
+    dam = ptr(ops.operand_amax(dout)) if impl == 0 else None
     if ops.gemm_precision() == "f16x3" and impl == 0:      # dqkv feeds the qkv data / weight gradient GEMMs
         am = ops.new_amax(qkv.device)
-        call("vitta_wmsa3d_bwd_amax", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b,
-             d, h, w, heads, 32, _int3(window), _int3(shift), float(scale), int(impl), ptr(am), stream_ptr())
+        call("vitta_wmsa3d_bwd_amax", ptr(qkv), qam, ptr(table), ptr(out), ptr(dout), dam, ptr(lse), ptr(dqkv), ptr(dtable),
+             ptr(ws), b, d, h, w, heads, 32, _int3(window), _int3(shift), float(scale), int(impl), ptr(am), stream_ptr())
         ops._attach_amax(dqkv, am)
         return dqkv, dtable
-    call("vitta_wmsa3d_bwd", ptr(qkv), ptr(table), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b, d, h, w,
-         heads, 32, _int3(window), _int3(shift), float(scale), int(impl), stream_ptr())
+    call("vitta_wmsa3d_bwd", ptr(qkv), qam, ptr(table), ptr(out), ptr(dout), dam, ptr(lse), ptr(dqkv), ptr(dtable), ptr(ws), b,
+         d, h, w, heads, 32, _int3(window), _int3(shift), float(scale), int(impl), stream_ptr())
     return dqkv, dtable
 
 
@@ -304,7 +307,7 @@ class SwinAttentionFn(torch.autograd.Function):
         g = g.contiguous()
         rpg = g.shape[0] // b
         gs = row_scale(g, rscale, rpg) if rscale is not None else g      # gradient of the branch output
-        dao = gemm(gs, wproj, 1)
+        dao = gemm(gs, wproj, 1, want_amax=True)       # its range scales dO's fp16 split in the attention backward
         if has_bproj:
             dwproj, dbproj = linear_wgrad(ao, gs, want_bias=True)
         else:
