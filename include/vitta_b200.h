@@ -516,6 +516,10 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* qkv_amax, const float* 
                           const float* dout, const float* dout_amax, const float* lse, float* dqkv, float* dbias_table,
                           float* ws, int B, int D, int H, int W, int heads, int head_dim, const int* window, const int* shift,
                           float scale, int impl, float* dqkv_amax, void* stream);
+/* Profiling aid for the backward: trace != null makes the following vitta_wmsa3d_bwd calls (impl 0) run their traced
+ * instantiation -- time stamps of CTA 0 as in vitta_wmsa3d_fwd_trace, 2 launches x 16 warps x trace_cap zeroed records
+ * (tools/wmsa_trace.py --bwd); null switches it off.  Results are unchanged. */
+int vitta_wmsa3d_bwd_set_trace(unsigned long long* trace, int trace_cap);
 
 /* ------------------------------------------------------------------------------------------------
  * View gathering + normalisation (the step before the hot path).

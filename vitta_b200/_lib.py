@@ -124,6 +124,7 @@ _SIGNATURES = {
     "vitta_wmsa3d_bwd_amax": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P, _P]),
     "vitta_wmsa3d_bwd_ws_floats": (C.c_int64, [C.c_int] * 5),
+    "vitta_wmsa3d_bwd_set_trace": (C.c_int, [_P, C.c_int]),
     "vitta_wmsa3d_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.c_int, _P]),
     "vitta_gather_normalize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

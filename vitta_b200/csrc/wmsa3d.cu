@@ -828,32 +828,6 @@ __global__ void __launch_bounds__(kAtBwdThreads, 1) wmsa3d_bwd_kernel(const Wmsa
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// backward (v1): tcgen05, 3xTF32.  Two launches of one skeleton (template MODE):
-//   MODE 0 "query-outer": thread = query row i.  Row operands (resident per 128-row tile, K-major A):  Qs_t, dO_t.
-//           per 32-key chunk c:  S = Qs_t K_c^T,  dP = dO_t V_c^T  (TMEM, double-buffered)
-//           dS = P o (dP - D_i), P = exp(S + bias + mask - lse_i);  dQ_t += dS K_c ;  dTable[rel(i,j)] += dS
-//   MODE 1 "key-outer":   thread = key row j.    Row operands: K_t, V_t.
-//           per 32-query chunk c:  S^T = K_t Qs_c^T,  dP^T = V_t dO_c^T
-//           P^T, dS^T with the per-column lse_i, D_i;  dV_t += P^T dO_c ;  dK_t += dS^T Qs_c
-// D_i = dO_i . O_i comes from wmsa3d_dsum_kernel.  Column chunks are stored twice: K-major (B operand of the score
-// MMAs) and MN-major (B operand of the accumulating MMAs); dS / P chunks are written by the row threads as K-major A
-// operands, exactly like P in the forward kernel.
-// ------------------------------------------------------------------------------------------------
-struct WmsaBwd2Params {
-  const float* qkv;
-  const float* table;
-  const float* dout;
-  const float* lse;
-  const float* dsum;    // (tokens, heads)
-  float* dqkv;
-  float* dtable;
-  float scale;
-  int items, items_per_cta;
-  WmsaGeom g;
-  float* amax_out;      // optional: max|dqkv| over both launches (range of the qkv data / weight gradient GEMMs)
-};
-
 // dsum[token, head] = sum_d dout[token, head*32 + d] * out[token, head*32 + d]; one 8-lane group per (token, head)
 __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restrict__ out, const float* __restrict__ dout,
                                                          float* __restrict__ dsum, int64_t n_pairs) {
@@ -872,485 +846,18 @@ __global__ void __launch_bounds__(256) wmsa3d_dsum_kernel(const float* __restric
   }
 }
 
-// Shared memory holds only the B operands (column chunks) and the tables: every A operand lives in TENSOR MEMORY --
-// the row tiles (written once per tile by the loader warps with tcgen05.st, thread = row) and the dS / P chunks (written
-// by the row threads, thread = row = TMEM lane, no swizzle / proxy fence needed).  With N = 32 per MMA an A operand in
-// shared memory would cost 4 KB of smem reads per 16 tensor cycles; from TMEM it is free.
-constexpr int kB2Stages = 4;
-constexpr int kB2OffC = 0;                          // 4 stages x 32 KB: C1k hi/lo, C1m hi/lo, C2k hi/lo, C2m hi/lo (4 KB each)
-constexpr int kB2OffDTab = kB2OffC + kB2Stages * 32768;     // MODE 0: 8 warp-private table gradients
-constexpr int kB2OffTab = kB2OffDTab + 8 * kAtMaxRel * 4;   // bias table of the head (* log2 e)
-constexpr int kB2OffLse = kB2OffTab + kAtMaxRel * 4;        // float2 (lse * log2e, dsum) per token
-constexpr int kB2OffInfo = kB2OffLse + kAtColPad * 8;
-constexpr int kB2OffTok = kB2OffInfo + kAtColPad * 4;
-constexpr int kB2OffBar = kB2OffTok + kAtColPad * 4;
-constexpr int kB2SmemBytes = kB2OffBar + 256 + 1024;        // 231168 <= 232448
-// TMEM columns
-constexpr uint32_t kTR1hi = 0, kTR1lo = 32, kTR2hi = 64, kTR2lo = 96;   // row tiles (A of the score MMAs)
-constexpr uint32_t kTSC = 128;                                          // scores: buffer b at 128 + 64 b: SC1, SC2
-constexpr uint32_t kTE1hi = 256, kTE1lo = 288, kTE2hi = 320, kTE2lo = 352;   // dS / P chunks (A of the accumulating MMAs)
-constexpr uint32_t kTACC1 = 384, kTACC2 = 416;
-
-enum { C_ITEM_READY = 0, C_ITEM_FREE, C_ROWS_READY, C_ROWS_FREE, C_COL_READY0, C_COL_FREE0 = C_COL_READY0 + kB2Stages,
-       C_SC_FULL0 = C_COL_FREE0 + kB2Stages, C_SC_FULL1, C_SC_FREE0, C_SC_FREE1, C_E_READY, C_E_FREE, C_ACC_FULL, C_ACC_FREE,
-       C_COUNT };
-
-constexpr int kB2Threads = 512;   // warps 0-7 row threads (TMEM lane quadrant = w & 3, column half = w >> 2), 8-11 loaders,
-                                  // 12-15 MMA issuers (SC1, SC2, ACC1, ACC2); 128 registers / thread
-
-template <int MODE>
-__global__ void __launch_bounds__(kB2Threads, 1) wmsa3d_bwd2_kernel(const WmsaBwd2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kB2OffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + C_COUNT);
-  float* tab = reinterpret_cast<float*>(smem + kB2OffTab);
-  float* dtab = reinterpret_cast<float*>(smem + kB2OffDTab);
-  float2* sLD = reinterpret_cast<float2*>(smem + kB2OffLse);
-  int* info = reinterpret_cast<int*>(smem + kB2OffInfo);
-  int* tok = reinterpret_cast<int*>(smem + kB2OffTok);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const WmsaGeom& g = p.g;
-  const int C = g.heads * 32;
-  const int nwin = g.nw0 * g.nw1 * g.nw2;
-  const int nwin_total = g.B * nwin;
-  const int n_tiles = (g.N + 127) >> 7;
-  const int n_chunks = (g.N + 31) >> 5;
-  const int item0 = blockIdx.x * p.items_per_cta;
-  const int item1 = min(p.items, item0 + p.items_per_cta);
-
-  if (threadIdx.x == 0) {
-    constexpr int kAccIssuers = MODE == 1 ? 2 : 1;
-    for (int i = 0; i < C_COUNT; ++i) {
-      int cnt = kAccIssuers;   // E_FREE, COL_FREE, ACC_FULL: one tcgen05.commit per accumulate issuer
-      if (i == C_SC_FULL0 || i == C_SC_FULL1 || i == C_ROWS_FREE) cnt = 2;   // one commit per score issuer
-      if (i == C_ITEM_READY || i == C_ROWS_READY || (i >= C_COL_READY0 && i < C_COL_FREE0))
-        cnt = 4;     // one elected arrive per loader warp
-      if (i == C_ITEM_FREE || i == C_SC_FREE0 || i == C_SC_FREE1 || i == C_E_READY || i == C_ACC_FREE)
-        cnt = 8;     // one elected arrive per row warp
-      mbar_init(&bar[i], cnt);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // broadcast from lane 0: the value is the same in every lane, but only a shuffle tells the compiler so -- without it
-  // everything derived from it travels through R2UR.BROADCAST + ELECT in front of every lane-predicated tcgen05.mma
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-  if (warp >= 8 && warp < 12) {
-    // =========================== loaders ===========================
-    const int lt = threadIdx.x - 256;
-    const int rslot = lt >> 3, q4 = lt & 7;
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 8) * 32) << 16);   // this warp's TMEM lane quadrant
-    int cur_head = -1;
-    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
-    auto flush_dtab = [&](int head) {
-      for (int i = lt; i < g.nrel; i += 128) {
-        float v = 0.f;
-#pragma unroll
-        for (int cpy = 0; cpy < 8; ++cpy) v += dtab[cpy * kAtMaxRel + i];
-        if (v != 0.f) atomicAdd(p.dtable + (int64_t)i * g.heads + head, v);
-      }
-    };
-    for (int item = item0; item < item1; ++item, ++it) {
-      const int head = item / nwin_total;
-      const int wg = item - head * nwin_total;
-      const int b = wg / nwin;
-      int w = wg - b * nwin;
-      const int ww = w % g.nw2; w /= g.nw2;
-      const int wh = w % g.nw1;
-      const int wd = w / g.nw1;
-      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);
-      if (head != cur_head) {
-        if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
-        for (int i = lt; i < g.nrel; i += 128) {
-          tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
-          if (MODE == 0) {
-#pragma unroll
-            for (int cpy = 0; cpy < 8; ++cpy) dtab[cpy * kAtMaxRel + i] = 0.f;
-          }
-        }
-        cur_head = head;
-      }
-      for (int i = lt; i < kAtColPad; i += 128) {
-        int t = -1, f = 31 << 16;                 // padding columns: region id 31 = always masked
-        float2 q = make_float2(INFINITY, 0.f);    // ... and lse = +inf: p = 0 exactly when they are queries
-        if (i < g.N) {
-          window_token(g, b, wd, wh, ww, i, t, f);
-          q.x = __ldg(p.lse + ((int64_t)wg * g.heads + head) * g.N + i) * 1.4426950408889634f;
-          q.y = __ldg(p.dsum + (int64_t)t * g.heads + head);
-        }
-        tok[i] = t;
-        info[i] = f;
-        sLD[i] = q;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[C_ITEM_READY]);
-      const float* qkv_h = p.qkv + head * 32;
-      const float* do_h = p.dout + head * 32;
-      // row operand (which 0: R1, 1: R2) / column operand of token t; q = float4 index inside the 32-float head slice
-      auto load_row = [&](int which, int t, int q) -> float4 {
-        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 0) {
-          if (which == 0) {
-            float4 v = ldg4(qkv_h + (int64_t)t * 3 * C + q * 4);
-            v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-            return v;
-          }
-          return ldg4(do_h + (int64_t)t * C + q * 4);
-        }
-        return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q * 4);
-      };
-      auto load_col = [&](int which, int t) -> float4 {
-        if (t < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 0) return ldg4(qkv_h + ((int64_t)t * 3 + 1 + which) * C + q4 * 4);
-        if (which == 0) {
-          float4 v = ldg4(qkv_h + (int64_t)t * 3 * C + q4 * 4);
-          v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-          return v;
-        }
-        return ldg4(do_h + (int64_t)t * C + q4 * 4);
-      };
-      // column chunks: 2 chunks per group (2 tensors x 2 rows x 2 chunks = 8 float4 per thread)
-      auto c_issue = [&](float4 (&v)[8], int grp) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int cc = u >> 2, which = (u >> 1) & 1, rr = u & 1;
-          const int j = (grp * 2 + cc) * 32 + rslot + rr * 16;
-          const int t = (grp * 2 + cc < n_chunks) ? tok[j] : -1;
-          v[u] = load_col(which, t);
-        }
-      };
-      auto c_drain = [&](float4 (&v)[8], int grp) {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (grp * 2 + cc >= n_chunks) break;
-          const int st = chunk_ctr & (kB2Stages - 1);
-          mbar_wait(&bar[C_COL_FREE0 + st], ((chunk_ctr / kB2Stages) & 1) ^ 1);
-          uint8_t* cb = smem + kB2OffC + st * 32768;
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const int r = rslot + rr * 16;
-              float4 h, l;
-              split4(v[cc * 4 + which * 2 + rr], h, l);
-              const uint32_t ok = sw128_off(r, q4), om = mn32_off(r, q4);
-              uint8_t* base = cb + which * 16384;
-              *reinterpret_cast<float4*>(base + ok) = h;
-              *reinterpret_cast<float4*>(base + 4096 + ok) = l;
-              if (MODE == 1 || which == 0) {
-                *reinterpret_cast<float4*>(base + 8192 + om) = h;
-                *reinterpret_cast<float4*>(base + 12288 + om) = l;
-              }
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_COL_READY0 + st]);
-          ++chunk_ctr;
-        }
-      };
-      const int n_groups = (n_chunks + 1) >> 1;
-      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        // row tile: thread = row (TMEM lane); both rows' global loads are in flight before the wait
-        const int i = tile * 128 + (warp - 8) * 32 + lane;
-        const int trow = (i < g.N) ? tok[i] : -1;
-        float4 ra[8], rb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          ra[u] = load_row(0, trow, u);
-          rb[u] = load_row(1, trow, u);
-        }
-        mbar_wait(&bar[C_ROWS_FREE], (tile_ctr & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float4 h, l;
-            split4(ra[half * 4 + u], h, l);
-            hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
-            hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
-            lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
-            lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
-          }
-          tmem_st16(t_lane + kTR1hi + half * 16, hi);
-          tmem_st16(t_lane + kTR1lo + half * 16, lo);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float4 h, l;
-            split4(rb[half * 4 + u], h, l);
-            hi[u * 4] = __float_as_uint(h.x); hi[u * 4 + 1] = __float_as_uint(h.y);
-            hi[u * 4 + 2] = __float_as_uint(h.z); hi[u * 4 + 3] = __float_as_uint(h.w);
-            lo[u * 4] = __float_as_uint(l.x); lo[u * 4 + 1] = __float_as_uint(l.y);
-            lo[u * 4 + 2] = __float_as_uint(l.z); lo[u * 4 + 3] = __float_as_uint(l.w);
-          }
-          tmem_st16(t_lane + kTR2hi + half * 16, hi);
-          tmem_st16(t_lane + kTR2lo + half * 16, lo);
-        }
-        float4 va[8], vb8[8];
-        c_issue(va, 0);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[C_ROWS_READY]);
-        for (int grp = 0; grp < n_groups; grp += 2) {
-          if (grp + 1 < n_groups) c_issue(vb8, grp + 1);
-          c_drain(va, grp);
-          if (grp + 2 < n_groups) c_issue(va, grp + 2);
-          if (grp + 1 < n_groups) c_drain(vb8, grp + 1);
-        }
-      }
-    }
-    if (MODE == 0 && cur_head >= 0) {
-      mbar_wait(&bar[C_ITEM_FREE], (it & 1) ^ 1);   // the row threads finished the last item
-      flush_dtab(cur_head);
-    }
-  } else if (warp >= 12) {
-    // =========================== MMA issuers ===========================
-    // Four independent issue streams (each MMA is only 128 x 32 x 8, so the serial issue chain of ONE thread would be
-    // the bottleneck): warp 12: S / S^T, warp 13: dP / dP^T, warp 14: ACC1 (dQ | dK), warp 15: ACC2 (dV, MODE 1 only).
-    // They touch disjoint accumulators; ordering against the other roles goes through the mbarriers.
-    const int which = __shfl_sync(0xffffffffu, warp & 1, 0);   // warp-uniform by construction; the shuffle makes it provable
-    const bool is_score = warp < 14;
-    const uint32_t pe = (lane == 0) ? 1u : 0u;
-    const uint32_t sbase = smem_u32(smem);
-    uint32_t tile_ctr = 0, chunk_ctr = 0;
-    if (is_score) {
-      const uint32_t idesc_sc = umma_idesc_tf32(128, 32);
-      const uint32_t a_hi = tmem_base + (which ? kTR2hi : kTR1hi), a_lo = tmem_base + (which ? kTR2lo : kTR1lo);
-      for (int item = item0; item < item1; ++item) {
-        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-          mbar_wait(&bar[C_ROWS_READY], tile_ctr & 1);
-          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-            // the stage / buffer indices feed the descriptors of lane-predicated MMAs: take them from a lane-0 broadcast
-            // of the (already uniform) counter so that they live in uniform registers (profiles/r01_gemm_issue.md: the
-            // R2UR.BROADCAST + ELECT sequence costs ~3x the issue time of a uniform-register MMA)
-            const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);
-            const int st = ccu & (kB2Stages - 1);
-            const int sb = ccu & 1;
-            mbar_wait(&bar[C_COL_READY0 + st], (chunk_ctr / kB2Stages) & 1);
-            mbar_wait(&bar[C_SC_FREE0 + sb], ((chunk_ctr >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t cb = sbase + kB2OffC + st * 32768 + which * 16384;
-            const uint64_t c_hi = umma_desc_sw128(cb), c_lo = umma_desc_sw128(cb + 4096);
-            const uint32_t d = tmem_base + kTSC + (uint32_t)(sb * 64 + which * 32);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              const uint32_t ka = (uint32_t)(k * 8);
-              umma_tf32_ts_p(d, a_lo + ka, c_hi + adv, idesc_sc, k != 0, pe);
-              umma_tf32_ts_p(d, a_hi + ka, c_lo + adv, idesc_sc, 1, pe);
-              umma_tf32_ts_p(d, a_hi + ka, c_hi + adv, idesc_sc, 1, pe);
-            }
-            umma_commit_p(&bar[C_SC_FULL0 + sb], pe);
-            if (c == n_chunks - 1) umma_commit_p(&bar[C_ROWS_FREE], pe);   // the row tile is reusable when these retire
-          }
-        }
-      }
-    } else if (which == 0 || MODE == 1) {
-      const uint32_t idesc_ac = umma_idesc_tf32(128, 32) | (1u << 16);   // B MN-major
-      const uint32_t e_hi = tmem_base + (which ? kTE2hi : kTE1hi), e_lo = tmem_base + (which ? kTE2lo : kTE1lo);
-      const uint32_t acc = tmem_base + (which ? kTACC2 : kTACC1);
-      for (int item = item0; item < item1; ++item) {
-        for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-          for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-            const int st = __shfl_sync(0xffffffffu, chunk_ctr, 0) & (kB2Stages - 1);   // uniform (see the score issuers)
-            mbar_wait(&bar[C_E_READY], chunk_ctr & 1);
-            if (c == 0) mbar_wait(&bar[C_ACC_FREE], (tile_ctr & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t cb = sbase + kB2OffC + st * 32768 + which * 16384;
-            const uint64_t m_hi = umma_desc_mn_sw128(cb + 8192, 4096), m_lo = umma_desc_mn_sw128(cb + 12288, 4096);
-            const int left = g.N - c * 32;
-            const int ksteps = left >= 32 ? 4 : (left + 7) >> 3;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                const uint64_t advb = (uint64_t)(k * (1024 >> 4));
-                const uint32_t ka = (uint32_t)(k * 8);
-                umma_tf32_ts_p(acc, e_lo + ka, m_hi + advb, idesc_ac, (c | k) != 0, pe);
-                umma_tf32_ts_p(acc, e_hi + ka, m_lo + advb, idesc_ac, 1, pe);
-                umma_tf32_ts_p(acc, e_hi + ka, m_hi + advb, idesc_ac, 1, pe);
-              }
-            }
-            umma_commit_p(&bar[C_E_FREE], pe);
-            umma_commit_p(&bar[C_COL_FREE0 + st], pe);
-            if (c == n_chunks - 1) umma_commit_p(&bar[C_ACC_FULL], pe);
-          }
-        }
-      }
-    }
-  } else {
-    // =========================== row threads ===========================
-    // thread = (row of the tile = TMEM lane, column half): warps w and w + 4 share a lane quadrant and split the 32 columns
-    // of every chunk, which doubles the warps available to hide the latency of the per-element chain.
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
-    const int rel0 = rel_row_base(g);
-    constexpr float kLog2e = 1.4426950408889634f;
-    constexpr float kMask2 = -100.f * kLog2e;
-    const float* __restrict__ tab2 = tab;                        // bias table, pre-multiplied by log2(e) by the loaders
-    float* __restrict__ mytab = dtab + warp * kAtMaxRel;         // this warp's private table gradient (no atomics)
-    uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
-    float out_amax = 0.f;
-    for (int item = item0; item < item1; ++item, ++it) {
-      const int head = item / nwin_total;
-      mbar_wait(&bar[C_ITEM_READY], it & 1);
-      for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
-        const int i = tile * 128 + row;
-        const bool valid = i < g.N;
-        const int ii = valid ? i : 0;
-        const int f_row = info[ii];
-        const int b_row = f_row & 0xffff;
-        const int r_row = f_row & 0x1f0000;
-        const int my_tok = tok[ii];
-        const float2 ld_row = sLD[ii];
-        const int kidx = (MODE == 0) ? (b_row + rel0) : (rel0 - b_row);
-        for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
-          const int sb = chunk_ctr & 1;
-          mbar_wait(&bar[C_SC_FULL0 + sb], (chunk_ctr >> 1) & 1);
-          tc_fence_after();
-          uint32_t s[16], d[16];
-          tmem_ld16(t_lane + kTSC + (uint32_t)(sb * 64), s);
-          tmem_ld16(t_lane + kTSC + (uint32_t)(sb * 64 + 32), d);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_SC_FREE0 + sb]);
-          // per element: p = 2^(s*log2e + bias2 + mask2 - lse2), ds = p * (dp - dsum).  The per-token arrays are padded to
-          // a multiple of 32 columns: padding columns carry region id 31 (always masked: p flushes to 0) and, as
-          // queries (MODE 1), lse = +inf (p = 0 exactly), so no bounds selects are needed here.
-          const int col0 = c * 32 + half * 16;
-          const int* ic = info + col0;
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int fc = ic[jj];
-            const int idx = (MODE == 0) ? (kidx - (fc & 0xffff)) : (kidx + (fc & 0xffff));
-            float t = fmaf(__uint_as_float(s[jj]), kLog2e, tab2[idx]);
-            t += ((fc & 0x1f0000) != r_row) ? kMask2 : 0.f;
-            float lse2, dsum;
-            if (MODE == 0) {
-              lse2 = ld_row.x;
-              dsum = ld_row.y;
-            } else {
-              const float2 q = sLD[col0 + jj];
-              lse2 = q.x;
-              dsum = q.y;
-            }
-            float pij;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pij) : "f"(t - lse2));
-            s[jj] = __float_as_uint(pij);                                          // P
-            d[jj] = __float_as_uint(pij * (__uint_as_float(d[jj]) - dsum));        // dS
-          }
-          if (MODE == 0) {
-            // dTable[rel(i, j)] += dS_ij.  Lanes of a warp are distinct rows => distinct entries for one column, so a
-            // predicated straight-line LDS / FADD / STS on the warp-private copy is race free; program order keeps the
-            // successive columns of a thread coherent.
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int fc = ic[jj];
-              const int idx = kidx - (fc & 0xffff);
-              const bool ok = valid && (col0 + jj < g.N);
-              const float o = mytab[ok ? idx : 0];
-              if (ok) mytab[idx] = o + __uint_as_float(d[jj]);
-            }
-          }
-          // hi / lo split (round-to-nearest tf32 of finite values), then straight into tensor memory as the A operand
-          uint32_t lo[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float x = __uint_as_float(d[jj]);
-            const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-            d[jj] = h;
-            lo[jj] = __float_as_uint(x - __uint_as_float(h));
-          }
-          mbar_wait(&bar[C_E_FREE], (chunk_ctr & 1) ^ 1);
-          tc_fence_after();
-          tmem_st16(t_lane + kTE1hi, d);
-          tmem_st16(t_lane + kTE1lo, lo);
-          if (MODE == 1) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const float x = __uint_as_float(s[jj]);
-              const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-              s[jj] = h;
-              lo[jj] = __float_as_uint(x - __uint_as_float(h));
-            }
-            tmem_st16(t_lane + kTE2hi, s);
-            tmem_st16(t_lane + kTE2lo, lo);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[C_E_READY]);
-        }
-        // ---- accumulators -> global (this thread's 16 of the 32 head channels)
-        mbar_wait(&bar[C_ACC_FULL], tile_ctr & 1);
-        tc_fence_after();
-        uint32_t a1[16], a2[16];
-        tmem_ld16(t_lane + kTACC1, a1);
-        if (MODE == 1) tmem_ld16(t_lane + kTACC2, a2);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[C_ACC_FREE]);
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            out_amax = fmaxf(out_amax, fabsf(__uint_as_float(a1[q])) * (MODE == 0 ? fabsf(p.scale) : 1.f));
-            if (MODE == 1) out_amax = fmaxf(out_amax, fabsf(__uint_as_float(a2[q])));
-          }
-          if (MODE == 0) {
-            float* dst = p.dqkv + (int64_t)my_tok * 3 * C + head * 32 + half * 16;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]) * p.scale, __uint_as_float(a1[q * 4 + 1]) * p.scale,
-                                           __uint_as_float(a1[q * 4 + 2]) * p.scale, __uint_as_float(a1[q * 4 + 3]) * p.scale));
-          } else {
-            float* dst = p.dqkv + ((int64_t)my_tok * 3 + 1) * C + head * 32 + half * 16;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              st4(dst + q * 4, make_float4(__uint_as_float(a1[q * 4]), __uint_as_float(a1[q * 4 + 1]),
-                                           __uint_as_float(a1[q * 4 + 2]), __uint_as_float(a1[q * 4 + 3])));
-              st4(dst + C + q * 4, make_float4(__uint_as_float(a2[q * 4]), __uint_as_float(a2[q * 4 + 1]),
-                                               __uint_as_float(a2[q * 4 + 2]), __uint_as_float(a2[q * 4 + 3])));
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[C_ITEM_FREE]);   // tab / dtab / info / tok / lse of this item no longer needed
-    }
-    if (p.amax_out) {
-      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
-      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), wmax);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 12) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// backward (v2): the skeleton of v1 (two launches: query-outer / key-outer) with EVERY product on kind::f16.
+// backward: tcgen05, two launches of one skeleton (template MODE), EVERY product on kind::f16.
+//   MODE 0 "query-outer": thread = query row i.  Row operands (resident per 128-row tile in tensor memory):  Qs_t, dO_t.
+//           per 32-key chunk c:  S = Qs_t K_c^T,  dP = dO_t V_c^T  (TMEM, four rotating buffers)
+//           dS = P o (dP - D_i), P = exp(S + bias + mask - lse_i);  dQ_t += dS K_c ;  dTable[rel(i,j)] += dS
+//   MODE 1 "key-outer":   thread = key row j.    Row operands: K_t, V_t.
+//           per 32-query chunk c:  S^T = K_t Qs_c^T,  dP^T = V_t dO_c^T
+//           P^T, dS^T with the per-column lse_i, D_i;  dV_t += P^T dO_c ;  dK_t += dS^T Qs_c
+// D_i = dO_i . O_i comes from wmsa3d_dsum_kernel.  (v1 of this kernel ran the same skeleton on 3xTF32.)
 //
 // What bounds these kernels is the number of dependent tcgen05.mma instructions and of hand-overs per 32-column chunk, not
-// tensor work (128 x 32 x 8 per MMA) or the row threads' arithmetic -- the forward kernel's time stamps show ~130 cycles
+// tensor work (128 x 32 x 16 per MMA) or the row threads' arithmetic -- the forward kernel's time stamps show ~130 cycles
 // per dependent MMA and several hundred per mbarrier hand-over (profiles/r02_wmsa_fwd_timeline_*.txt).  v1 issued 12 tf32
 // MMAs per chunk and stream (4 K steps x 3 split products) and passed dS / P through ONE tensor-memory buffer
 // (store -> accumulate MMAs -> "buffer free" -> next store).  Here:
@@ -1378,6 +885,8 @@ struct WmsaBwd3Params {
   int items, items_per_cta;
   WmsaGeom g;
   float* amax_out;      // optional: max|dqkv| over both launches (range of the qkv data / weight gradient GEMMs)
+  unsigned long long* trace;   // TRACE instantiation only: 16 warps x trace_cap records per launch (0 = unused)
+  int trace_cap;
 };
 
 constexpr int kB3Stages = 8;                        // column-chunk stages: C1 hi | lo, C2 hi | lo (4 KB each)
@@ -1412,7 +921,7 @@ __device__ __forceinline__ void f16_pair(float x0, float x1, uint32_t& hi, uint3
 constexpr int kB3Threads = 512;   // warps 0-7 row threads (TMEM lane quadrant = w & 3, column half = w >> 2), 8-11 loaders,
                                   // 12-15 MMA issuers (S, dP, ACC1, ACC2)
 
-template <int MODE>
+template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBwd3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1426,6 +935,8 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t tr_n = 0;     // WMSA_TR: time stamps of the TRACE instantiation (vitta_wmsa3d_bwd_trace)
+  (void)tr_n;
   const WmsaGeom& g = p.g;
   const int C = g.heads * 32;
   const int nwin = g.nw0 * g.nw1 * g.nw2;
@@ -1489,6 +1000,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
       const int wh = w % g.nw1;
       const int wd = w / g.nw1;
       mbar_wait(&bar[D_ITEM_FREE], (it & 1) ^ 1);
+      WMSA_TR(40);
       if (head != cur_head) {
         if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
         for (int i = lt; i < g.nrel; i += 128) {
@@ -1603,6 +1115,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[D_ROWS_READY]);
+        WMSA_TR(42);
         for (int grp = 0; grp < n_groups; grp += 2) {
           if (grp + 1 < n_groups) c_issue(vb8, grp + 1);
           c_drain(va, grp);
@@ -1635,8 +1148,10 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
             const int st = ccu & (kB3Stages - 1);
             const int sb = ccu & (kB3Bufs - 1);
             mbar_wait(&bar[D_COL_READY0 + st], (chunk_ctr / kB3Stages) & 1);
+            WMSA_TR(20);
             mbar_wait(&bar[D_SC_FREE0 + sb], ((chunk_ctr / kB3Bufs) & 1) ^ 1);
             tc_fence_after();
+            WMSA_TR(21);
             const uint32_t cb = sbase + kB3OffC + st * kB3StageBytes + which * 8192;
             const uint64_t c_hi = umma_desc_sw128(cb), c_lo = umma_desc_sw128(cb + 4096);
             const uint32_t d = tmem_base + kT3SC + (uint32_t)(sb * 64 + which * 32);
@@ -1650,6 +1165,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
             }
             umma_commit_p(&bar[D_SC_FULL0 + sb], pe);
             if (c == n_chunks - 1) umma_commit_p(&bar[D_ROWS_FREE], pe);   // the row tile is reusable when these retire
+            WMSA_TR(22);
           }
         }
       }
@@ -1665,6 +1181,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
             mbar_wait(&bar[D_E_READY0 + sb], (chunk_ctr / kB3Bufs) & 1);
             if (c == 0) mbar_wait(&bar[D_ACC_FREE], (tile_ctr & 1) ^ 1);
             tc_fence_after();
+            WMSA_TR(30);
             const uint32_t cb = sbase + kB3OffC + st * kB3StageBytes + which * 8192;
             const uint64_t m_hi = umma_desc_mn_sw128_f16(cb, 4096), m_lo = umma_desc_mn_sw128_f16(cb + 4096, 4096);
             // E operand of this stream: dS over the S columns (which 0), P over the dP columns (which 1); per 16-key K step
@@ -1685,6 +1202,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
             umma_commit_p(&bar[D_SC_FREE0 + sb], pe);
             umma_commit_p(&bar[D_COL_FREE0 + st], pe);
             if (c == n_chunks - 1) umma_commit_p(&bar[D_ACC_FULL], pe);
+            WMSA_TR(31);
           }
         }
       }
@@ -1723,6 +1241,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
           const int sb = chunk_ctr & (kB3Bufs - 1);
           mbar_wait(&bar[D_SC_FULL0 + sb], (chunk_ctr / kB3Bufs) & 1);
           tc_fence_after();
+          WMSA_TR(1);
           const uint32_t sc = t_lane + kT3SC + (uint32_t)(sb * 64 + half * 16);
           uint32_t s[16], d[16];
           tmem_ld16(sc, s);
@@ -1756,18 +1275,20 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
           }
           if (MODE == 0) {
             // dTable[rel(i, j)] += dS_ij.  Lanes of a warp are distinct rows => distinct entries for one column, so a
-            // predicated straight-line LDS / FADD / STS on the warp-private copy is race free; program order keeps the
-            // successive columns of a thread coherent.
+            // predicated straight-line LDS / FFMA / STS on the warp-private copy is race free; program order keeps the
+            // successive columns coherent -- (row, column) pairs of DIFFERENT columns do share entries (same relative
+            // position), which is why the 16 updates cannot be batched (all loads first loses updates: tried) and why this
+            // chain costs ~1000 cycles per chunk.  Shared-memory atomicAdd (a CAS loop for fp32) was slower still.
             const float k_dt = (kDsUp * inv_sd) * inv_sq;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-              const int fc = ic[jj];
-              const int idx = kidx - (fc & 0xffff);
+              const int idx = kidx - (ic[jj] & 0xffff);
               const bool ok = valid && (col0 + jj < g.N);
               const float o = mytab[ok ? idx : 0];
               if (ok) mytab[idx] = fmaf(dsv[jj], k_dt, o);
             }
           }
+          WMSA_TR(2);
           // fp16 hi / lo pairs, straight back into tensor memory over this thread's 16 score columns: the A operand of the
           // accumulate MMAs (key 2u in the low half of column u)
           uint32_t hi[8], lo[8];
@@ -1785,10 +1306,12 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[D_E_READY0 + sb]);
+          WMSA_TR(3);
         }
         // ---- accumulators -> global (this thread's 16 of the 32 head channels)
         mbar_wait(&bar[D_ACC_FULL], tile_ctr & 1);
         tc_fence_after();
+        WMSA_TR(6);
         uint32_t a1[16], a2[16];
         tmem_ld16(t_lane + kT3ACC1 + (uint32_t)(half * 16), a1);
         if (MODE == 1) tmem_ld16(t_lane + kT3ACC2 + (uint32_t)(half * 16), a2);
@@ -1833,6 +1356,9 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
+
+static unsigned long long* g_bwd_trace = nullptr;   // see vitta_wmsa3d_bwd_set_trace
+static int g_bwd_trace_cap = 0;
 
 static int wmsa_geom(int B, int D, int H, int W, int heads, const int* window, const int* shift, WmsaGeom* g) {
   VITTA_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && heads > 0 && window && shift, VITTA_E_BADARG, "wmsa3d: bad shape");
@@ -1994,12 +1520,17 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* qkv_amax, const float* 
   p.qkv = qkv; p.table = bias_table; p.dout = dout; p.lse = lse; p.dsum = ws; p.dqkv = dqkv; p.dtable = dbias_table;
   p.qkv_amax = qkv_amax; p.dout_amax = dout_amax;
   p.scale = scale; p.amax_out = dqkv_amax;
+  p.trace = g_bwd_trace; p.trace_cap = g_bwd_trace_cap;
   p.items = B * g.nw0 * g.nw1 * g.nw2 * heads;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
+      e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wmsa3d_bwd3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3SmemBytes);
     if (e != cudaSuccess) {
       set_error("wmsa3d_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -2010,10 +1541,26 @@ int vitta_wmsa3d_bwd_amax(const float* qkv, const float* qkv_amax, const float* 
   int grid = p.items < sms ? p.items : sms;
   p.items_per_cta = (p.items + grid - 1) / grid;
   grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
-  wmsa3d_bwd3_kernel<0><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
+  if (p.trace) {   // profiling aid (vitta_wmsa3d_bwd_set_trace): launch 0 writes the first 16 x cap records, launch 1 the next
+    wmsa3d_bwd3_kernel<0, true><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
+    VITTA_CHECK_LAUNCH();
+    p.trace += (size_t)16 * p.trace_cap;
+    wmsa3d_bwd3_kernel<1, true><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
+    VITTA_CHECK_LAUNCH();
+    return 0;
+  }
+  wmsa3d_bwd3_kernel<0, false><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
-  wmsa3d_bwd3_kernel<1><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
+  wmsa3d_bwd3_kernel<1, false><<<grid, kB3Threads, kB3SmemBytes, st>>>(p);
   VITTA_CHECK_LAUNCH();
+  return 0;
+}
+
+// Profiling aid: the next vitta_wmsa3d_bwd calls run the traced instantiation (time stamps of CTA 0, as in
+// vitta_wmsa3d_fwd_trace) into trace = 2 launches x 16 warps x trace_cap zeroed records; null switches it off again.
+int vitta_wmsa3d_bwd_set_trace(unsigned long long* trace, int trace_cap) {
+  g_bwd_trace = trace;
+  g_bwd_trace_cap = trace ? trace_cap : 0;
   return 0;
 }
 
