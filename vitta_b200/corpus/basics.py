@@ -615,7 +615,16 @@ def tta_standard(model_origin, criterion, args=None, logger=None, writer=None):
             losses_ce.update(res['loss_ce'].item(), actual_bz)
         losses_reg.update(res['loss_reg'].item(), actual_bz)
         if res['loss_consis'] is not None:
-            losses_consis.update(res['loss_consis'].item(), actual_bz)
+            lc = res['loss_consis']
+            if pg is not None:
+                # the consistency loss is a SUM over the videos of the batch (utils/pred_consistency_utils.py:15-31): a rank
+                # holds the share of its shard (the gradients are summed by C2); the meter shows the whole batch's value,
+                # as the single-process run does.  (Ranks without a video are in adapt_idle and do not reach this point:
+                # the collective is skipped on ragged steps.)
+                if global_videos >= world:
+                    lc = lc.clone()
+                    dist.all_reduce(lc, group=pg)
+            losses_consis.update(lc.item(), actual_bz)
         adapter.hooks_off()
         input, target = next(eval_iter)
         if pg is not None:

@@ -101,8 +101,8 @@ constexpr int kOffQlo = kOffQhi + 128 * 128;             // 118784
 constexpr int kOffV = kOffQlo + 128 * 128;               // 135168: 8 stages x (hi atom 4 KB, lo atom 4 KB)
 constexpr int kOffTab = kOffV + kFwdVStages * 8192;      // bias table of the current head (* log2 e)
 constexpr int kOffInfo = kOffTab + kAtMaxRel * 4;
-constexpr int kOffTok = kOffInfo + kAtColPad * 4;
-constexpr int kOffBar = kOffTok + kAtMaxKeys * 4;
+constexpr int kOffTok = kOffInfo + 2 * kAtColPad * 4;    // (info and tok: two buffers each, by item parity)
+constexpr int kOffBar = kOffTok + 2 * kAtMaxKeys * 4;
 constexpr int kOffXch = kOffBar + 512;                   // row maximum / row sum exchange between the two softmax groups
 constexpr int kAtSmemBytes = kOffXch + 2 * 2 * 128 * 4 + 1024;   // ~218 KB
 // TMEM columns of the forward kernel: S [0, 400); the P chunk c (fp16 hi | lo, two keys per column) overwrites S columns
@@ -124,7 +124,7 @@ struct WmsaFwdParams {
 };
 
 constexpr int kPRing = 8;   // P_READY barriers per group: a group runs at most 7 chunks (one tile) ahead of its issuer
-enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE, B_Q_READY, B_Q_FREE, B_S_FULL, B_S_FREE, B_O_FULL, B_O_FREE,
+enum { B_KV_READY = 0, B_KV_FREE, B_TAB_FREE0, B_TAB_FREE1, B_Q_READY, B_Q_FREE, B_S_FULL, B_S_FREE, B_O_FULL, B_O_FREE,
        B_V_READY0, B_V_FREE0 = B_V_READY0 + kFwdVStages, B_P_READY0 = B_V_FREE0 + kFwdVStages,
        B_COUNT = B_P_READY0 + 2 * kPRing };
 static_assert(B_COUNT * 8 + 8 <= 512, "barrier block");
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
   float* tab = reinterpret_cast<float*>(smem + kOffTab);
-  int* info = reinterpret_cast<int*>(smem + kOffInfo);
-  int* tok = reinterpret_cast<int*>(smem + kOffTok);
+  int* info_all = reinterpret_cast<int*>(smem + kOffInfo);   // [2][kAtColPad]: per-token arrays of the item, double-buffered
+  int* tok_all = reinterpret_cast<int*>(smem + kOffTok);     // [2][kAtMaxKeys]  by item parity
   float* xch_max = reinterpret_cast<float*>(smem + kOffXch);     // [2][128]
   float* xch_sum = xch_max + 2 * 128;                            // [2][128]
 
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       int cnt = 1;   // tcgen05.commit barriers
       if (i == B_KV_READY || i == B_Q_READY || (i >= B_V_READY0 && i < B_V_FREE0) || i >= B_P_READY0)
         cnt = 4;     // one elected arrive per warp of a 4-warp role
-      if (i == B_TAB_FREE || i == B_O_FREE) cnt = 8;   // both softmax groups
+      if (i == B_TAB_FREE0 || i == B_TAB_FREE0 + 1 || i == B_O_FREE) cnt = 8;   // both softmax groups
       if (i == B_S_FREE || i == B_O_FULL) cnt = 2;     // both PV issuers
       mbar_init(&bar[i], cnt);
     }
@@ -240,8 +240,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       const int ww = w % g.nw2; w /= g.nw2;
       const int wh = w % g.nw1;
       const int wd = w / g.nw1;
+      // tok[] / info[] are double-buffered by item parity, so the next item's K can be gathered as soon as the S MMAs of the
+      // current item's last tile have retired (KV_FREE) -- its softmax passes and PV products are still running; a single
+      // buffer made every item boundary wait for pass 1 of the last tile (+9.5 K cycles per item in the time stamps).
+      // The bias table is single: a change of head (once per ~100 items) waits for the previous item's TAB_FREE too.
+      int* info = info_all + (it & 1) * kAtColPad;
+      int* tok = tok_all + (it & 1) * kAtMaxKeys;
       mbar_wait(&bar[B_KV_FREE], (it & 1) ^ 1);
-      mbar_wait(&bar[B_TAB_FREE], (it & 1) ^ 1);
+      mbar_wait(&bar[B_TAB_FREE0 + (it & 1)], ((it >> 1) & 1) ^ 1);
+      if (head != cur_head && it > 0) mbar_wait(&bar[B_TAB_FREE0 + ((it - 1) & 1)], ((it - 1) >> 1) & 1);
       WMSA_TR(40);
       for (int i = lt; i < kAtColPad; i += 128) {
         int t = -1, f = 31 << 16;   // padding columns: region id 31 = always masked (and their V rows are zero)
@@ -465,6 +472,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
       mbar_wait(&bar[B_KV_READY], it & 1);   // tab / info / tok of this item are in place
+      const int* info = info_all + (it & 1) * kAtColPad;
+      const int* tok = tok_all + (it & 1) * kAtMaxKeys;
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         const int i = tile * 128 + row;
         const bool valid = i < g.N;
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
         WMSA_TR(3);
         if (tile == n_tiles - 1) {   // last use of tab / info by this warp for this item
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_TAB_FREE]);
+          if (lane == 0) mbar_arrive(&bar[B_TAB_FREE0 + (it & 1)]);
         }
         // ---- pass 2: p = 2^(t - m2 + 10), partial row sum; P chunks (fp16 hi / lo pairs) go back to tensor memory, over
         //      the columns they came from, as the A operand of P V
@@ -889,22 +898,22 @@ struct WmsaBwd3Params {
   int trace_cap;
 };
 
-constexpr int kB3Stages = 8;                        // column-chunk stages: C1 hi | lo, C2 hi | lo (4 KB each)
+constexpr int kB3Stages = 6;                        // column-chunk stages: C1 hi | lo, C2 hi | lo (4 KB each)
 constexpr int kB3StageBytes = 16384;
 constexpr int kB3Bufs = 4;                          // score buffers in tensor memory
 constexpr int kB3OffC = 0;
 constexpr int kB3OffDTab = kB3OffC + kB3Stages * kB3StageBytes;   // MODE 0: 8 warp-private table gradients
 constexpr int kB3OffTab = kB3OffDTab + 8 * kAtMaxRel * 4;         // bias table of the head (* log2 e)
 constexpr int kB3OffLse = kB3OffTab + kAtMaxRel * 4;              // float2 (lse * log2e, dsum * scales) per token
-constexpr int kB3OffInfo = kB3OffLse + kAtColPad * 8;
-constexpr int kB3OffTok = kB3OffInfo + kAtColPad * 4;
-constexpr int kB3OffBar = kB3OffTok + kAtColPad * 4;
-constexpr int kB3SmemBytes = kB3OffBar + 512 + 1024;              // 231424 <= 232448
+constexpr int kB3OffInfo = kB3OffLse + 2 * kAtColPad * 8;         // (lse / info / tok: two buffers each, by item parity)
+constexpr int kB3OffTok = kB3OffInfo + 2 * kAtColPad * 4;
+constexpr int kB3OffBar = kB3OffTok + 2 * kAtColPad * 4;
+constexpr int kB3SmemBytes = kB3OffBar + 512 + 1024;              // 205312 <= 232448
 // TMEM columns: row tiles (packed fp16 pairs, 16 columns per 32 channels), score buffers b at 64 + 64 b (S | dP, 32 + 32),
 // accumulators
 constexpr uint32_t kT3R1hi = 0, kT3R1lo = 16, kT3R2hi = 32, kT3R2lo = 48, kT3SC = 64, kT3ACC1 = 320, kT3ACC2 = 352;
 
-enum { D_ITEM_READY = 0, D_ITEM_FREE, D_ROWS_READY, D_ROWS_FREE, D_ACC_FULL, D_ACC_FREE, D_COL_READY0,
+enum { D_ITEM_READY0 = 0, D_ITEM_READY1, D_ITEM_FREE0, D_ITEM_FREE1, D_ROWS_READY, D_ROWS_FREE, D_ACC_FULL, D_ACC_FREE, D_COL_READY0,
        D_COL_FREE0 = D_COL_READY0 + kB3Stages, D_SC_FULL0 = D_COL_FREE0 + kB3Stages, D_E_READY0 = D_SC_FULL0 + kB3Bufs,
        D_SC_FREE0 = D_E_READY0 + kB3Bufs, D_COUNT = D_SC_FREE0 + kB3Bufs };
 static_assert(D_COUNT * 8 + 8 <= 512, "barrier block");
@@ -929,9 +938,9 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + D_COUNT);
   float* tab = reinterpret_cast<float*>(smem + kB3OffTab);
   float* dtab = reinterpret_cast<float*>(smem + kB3OffDTab);
-  float2* sLD = reinterpret_cast<float2*>(smem + kB3OffLse);
-  int* info = reinterpret_cast<int*>(smem + kB3OffInfo);
-  int* tok = reinterpret_cast<int*>(smem + kB3OffTok);
+  float2* sLD_all = reinterpret_cast<float2*>(smem + kB3OffLse);   // [2][kAtColPad]: per-token arrays of the item,
+  int* info_all = reinterpret_cast<int*>(smem + kB3OffInfo);       // double-buffered by item parity (the loaders start
+  int* tok_all = reinterpret_cast<int*>(smem + kB3OffTok);         // on the next item while the row threads finish this one)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -955,9 +964,9 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
     for (int i = 0; i < D_COUNT; ++i) {
       int cnt = kAccIssuers;   // COL_FREE, SC_FREE, ACC_FULL: one tcgen05.commit per accumulate issuer
       if ((i >= D_SC_FULL0 && i < D_E_READY0) || i == D_ROWS_FREE) cnt = 2;   // one commit per score issuer
-      if (i == D_ITEM_READY || i == D_ROWS_READY || (i >= D_COL_READY0 && i < D_COL_FREE0))
+      if (i == D_ITEM_READY0 || i == D_ITEM_READY1 || i == D_ROWS_READY || (i >= D_COL_READY0 && i < D_COL_FREE0))
         cnt = 4;     // one elected arrive per loader warp
-      if (i == D_ITEM_FREE || (i >= D_E_READY0 && i < D_SC_FREE0) || i == D_ACC_FREE)
+      if (i == D_ITEM_FREE0 || i == D_ITEM_FREE0 + 1 || (i >= D_E_READY0 && i < D_SC_FREE0) || i == D_ACC_FREE)
         cnt = 8;     // one elected arrive per row warp
       mbar_init(&bar[i], cnt);
     }
@@ -999,9 +1008,14 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
       const int ww = w % g.nw2; w /= g.nw2;
       const int wh = w % g.nw1;
       const int wd = w / g.nw1;
-      mbar_wait(&bar[D_ITEM_FREE], (it & 1) ^ 1);
+      float2* sLD = sLD_all + (it & 1) * kAtColPad;
+      int* info = info_all + (it & 1) * kAtColPad;
+      int* tok = tok_all + (it & 1) * kAtColPad;
+      mbar_wait(&bar[D_ITEM_FREE0 + (it & 1)], ((it >> 1) & 1) ^ 1);      // this buffer's previous item (it - 2) is done
       WMSA_TR(40);
       if (head != cur_head) {
+        // the bias table and the table gradients are single: a change of head waits for the previous item as well
+        if (it > 0) mbar_wait(&bar[D_ITEM_FREE0 + ((it - 1) & 1)], ((it - 1) >> 1) & 1);
         if (MODE == 0 && cur_head >= 0) flush_dtab(cur_head);
         for (int i = lt; i < g.nrel; i += 128) {
           tab[i] = __ldg(p.table + (int64_t)i * g.heads + head) * 1.4426950408889634f;   // bias * log2(e)
@@ -1026,7 +1040,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[D_ITEM_READY]);
+      if (lane == 0) mbar_arrive(&bar[D_ITEM_READY0 + (it & 1)]);   // (one barrier per buffer: the loaders run an item ahead)
       const float* qkv_h = p.qkv + head * 32;
       const float* do_h = p.dout + head * 32;
       // row operand (which 0: R1, 1: R2) / column operand of token t; q = float4 index inside the 32-float head slice
@@ -1054,7 +1068,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           if (grp * 2 + cc >= n_chunks) break;
-          const int st = chunk_ctr & (kB3Stages - 1);
+          const int st = chunk_ctr % kB3Stages;
           mbar_wait(&bar[D_COL_FREE0 + st], ((chunk_ctr / kB3Stages) & 1) ^ 1);
           uint8_t* cb = smem + kB3OffC + st * kB3StageBytes;
 #pragma unroll
@@ -1125,7 +1139,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
       }
     }
     if (MODE == 0 && cur_head >= 0) {
-      mbar_wait(&bar[D_ITEM_FREE], (it & 1) ^ 1);   // the row threads finished the last item
+      mbar_wait(&bar[D_ITEM_FREE0 + ((it - 1) & 1)], ((it - 1) >> 1) & 1);   // the row threads finished the last item
       flush_dtab(cur_head);
     }
   } else if (warp >= 12) {
@@ -1145,7 +1159,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
           mbar_wait(&bar[D_ROWS_READY], tile_ctr & 1);
           for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
             const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);   // uniform registers for descriptors / addresses
-            const int st = ccu & (kB3Stages - 1);
+            const int st = ccu % kB3Stages;
             const int sb = ccu & (kB3Bufs - 1);
             mbar_wait(&bar[D_COL_READY0 + st], (chunk_ctr / kB3Stages) & 1);
             WMSA_TR(20);
@@ -1176,7 +1190,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
         for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
           for (int c = 0; c < n_chunks; ++c, ++chunk_ctr) {
             const uint32_t ccu = __shfl_sync(0xffffffffu, chunk_ctr, 0);
-            const int st = ccu & (kB3Stages - 1);
+            const int st = ccu % kB3Stages;
             const int sb = ccu & (kB3Bufs - 1);
             mbar_wait(&bar[D_E_READY0 + sb], (chunk_ctr / kB3Bufs) & 1);
             if (c == 0) mbar_wait(&bar[D_ACC_FREE], (tile_ctr & 1) ^ 1);
@@ -1226,7 +1240,10 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
     float out_amax = 0.f;
     for (int item = item0; item < item1; ++item, ++it) {
       const int head = item / nwin_total;
-      mbar_wait(&bar[D_ITEM_READY], it & 1);
+      mbar_wait(&bar[D_ITEM_READY0 + (it & 1)], (it >> 1) & 1);
+      const float2* sLD = sLD_all + (it & 1) * kAtColPad;
+      const int* info = info_all + (it & 1) * kAtColPad;
+      const int* tok = tok_all + (it & 1) * kAtColPad;
       for (int tile = 0; tile < n_tiles; ++tile, ++tile_ctr) {
         const int i = tile * 128 + row;
         const bool valid = i < g.N;
@@ -1342,7 +1359,7 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[D_ITEM_FREE]);   // tab / dtab / info / tok / lse of this item no longer needed
+      if (lane == 0) mbar_arrive(&bar[D_ITEM_FREE0 + (it & 1)]);   // dtab / info / tok / lse of this item no longer needed
     }
     if (p.amax_out) {
       const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
