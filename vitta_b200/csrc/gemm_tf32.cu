@@ -83,7 +83,7 @@ struct GemmSmem {
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 4;
   static constexpr int kBOff = TS ? kABytes : 2 * kABytes;   // B hi tile offset inside a stage (B lo follows)
   static constexpr int kStageBytes = kBOff + 2 * kBBytes;
-  static constexpr int kBarBytes = 1024;
+  static constexpr int kBarBytes = 3072;          // barriers (first 256 bytes) + the epilogue's bias tile [2][BN <= 256] floats at +1024
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // + alignment slack
   // kCat: the hi and lo tiles of B are adjacent in shared memory, so  a_hi x [b_hi ; b_lo]  is ONE MMA of N = 2*BN whose
   // result lands in two column sets (hi*hi | hi*lo) that the epilogue adds; with a_lo x b_hi that is 2 MMAs per k-step
@@ -436,6 +436,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     float out_amax = 0.f;
+    // bias of the tile's BN columns, staged in shared memory once per tile (two buffers by tile parity, one named barrier
+    // of the four epilogue warps per tile).  Reading it with __ldg inside the store loop was the largest single stall of
+    // the narrow-K linear layers (Video-Swin stage 1, K = 96: every group of 8 columns waited for an L2 round trip --
+    // the streaming stores evict the 1 KB vector from L1 -- 16 times per row and tile: profiles/r02_swin_gemm_*.md).
+    float* sbias_all = reinterpret_cast<float*>(bars_mem + 1024);
+    uint32_t tile_par = 0;
+    const int et = threadIdx.x - (kGemmThreads - 128);     // 0..127 within the epilogue warps
     float inv_a = 1.f, inv_b = 1.f;   // F16: 1 / s_a, 1 / s_b -- exact powers of two, applied one after the other (their
     if constexpr (F16) {              // product alone could leave the fp32 range for tiny gradient tensors)
       float s_unused;
@@ -466,6 +473,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float* arow = p.aux_out ? p.aux_out + out_row * p.ldc : nullptr;
       const float rscale = (p.row_scale && row_ok) ? __ldg(p.row_scale + out_row / p.rows_per_group) : 1.f;
       const int n0 = nt * BN;
+      float* sbias = sbias_all + tile_par * BN;
+      if (p.bias) {
+#pragma unroll
+        for (int u = 0; u < BN / 128 + (BN < 128 ? 1 : 0); ++u) {
+          const int cidx = et + u * 128;
+          if (cidx < BN) sbias[cidx] = (n0 + cidx < p.N) ? __ldg(p.bias + n0 + cidx) : 0.f;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // (barrier 1 belongs to the split warps)
+      }
+      tile_par ^= 1u;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -474,6 +491,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
+        // the residual / pre-activation operand of this chunk: all four 32-byte loads of the row go out now, under the
+        // tensor-memory load, instead of one at a time right in front of their use (four DRAM round trips per chunk)
+        const bool res_pre = rrow != nullptr && row_ok && (n0 + c0 + 32 <= p.N) && p.vec_ok == 2;
+        float4 rq[8];
+        if (res_pre) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ld8(rrow + n0 + c0 + u * 8, rq[2 * u], rq[2 * u + 1]);
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
@@ -498,7 +523,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float4 v1 = make_float4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]),
                                       __uint_as_float(r[j + 7]));
               if (p.bias) {
-                const float4 b0 = ldg4(p.bias + nbase + j), b1 = ldg4(p.bias + nbase + j + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + j);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + j + 4);
                 v0.x += b0.x; v0.y += b0.y; v0.z += b0.z; v0.w += b0.w;
                 v1.x += b1.x; v1.y += b1.y; v1.z += b1.z; v1.w += b1.w;
               }
@@ -508,8 +534,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v1.x = gelu_exact(v1.x); v1.y = gelu_exact(v1.y); v1.z = gelu_exact(v1.z); v1.w = gelu_exact(v1.w);
               }
               if (rrow) {
-                float4 r0, r1;
-                ld8(rrow + nbase + j, r0, r1);
+                const float4 r0 = rq[j >> 2], r1 = rq[(j >> 2) + 1];
                 if (p.act == 2) {
                   v0.x *= gelu_grad(r0.x) * rscale; v0.y *= gelu_grad(r0.y) * rscale;
                   v0.z *= gelu_grad(r0.z) * rscale; v0.w *= gelu_grad(r0.w) * rscale;
@@ -541,7 +566,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                      __uint_as_float(r[j + 3]));
               if (p.bias) {
-                const float4 b = ldg4(p.bias + nbase + j);
+                const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + j);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
               }
               if (arow) st4(arow + nbase + j, v);
@@ -568,7 +593,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const int n = nbase + j;
               if (n < p.N) {
                 float v = __uint_as_float(r[j]);
-                if (p.bias) v += __ldg(p.bias + n);
+                if (p.bias) v += sbias[c0 + j];
                 if (arow) arow[n] = v;
                 if (p.act == 1) v = gelu_exact(v);
                 if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale : fmaf(v, rscale, rrow[n]);
