@@ -31,8 +31,9 @@ namespace vitta {
 
 constexpr int kBM = 128;         // UMMA M (one TMEM lane per accumulator row)
 constexpr int kBK = 32;          // fp32 elements per stage row = 128 B = one swizzle atom row
-constexpr int kGemmThreads = 448;
-constexpr int kSplitWarp0 = 2, kSplitWarps = 8, kEpiWarp0 = kSplitWarp0 + kSplitWarps;   // epilogue: warps 10-13
+constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant: warps q and q + 4 of the role split every 32-column chunk
+constexpr int kSplitWarp0 = 2, kSplitWarps = 8, kEpiWarp0 = kSplitWarp0 + kSplitWarps;   // epilogue: warps 10-17
+constexpr int kGemmThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 576
 
 struct GemmParams {
   float* C;
@@ -151,7 +152,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], PAIR ? 8 : 4);    // one elected arrive per epilogue warp (of both CTAs)
+      mbar_init(&acc_empty[a], (PAIR ? 2 : 1) * kEpiWarps);    // one elected arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -431,7 +432,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    // Eight warps: the narrow-K layers (layer-1 pointwise convolutions, the K = 96 ... 192 linear layers of Video-Swin) do
+    // ~1.2 K cycles of MMA work per tile against 6-9 K cycles of epilogue in four warps (GELU / GELU' per element, bias,
+    // residual, 64 KB of stores: profiles/r02_swin_gemm_*.md).  Warps w and w + 4 of the role share a lane quadrant and
+    // take the two 16-column halves of every 32-column chunk.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - kEpiWarp0) >> 2;     // 16-column half of every chunk
     const int row = q * 32 + lane;                // accumulator row == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -442,7 +448,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // the streaming stores evict the 1 KB vector from L1 -- 16 times per row and tile: profiles/r02_swin_gemm_*.md).
     float* sbias_all = reinterpret_cast<float*>(bars_mem + 1024);
     uint32_t tile_par = 0;
-    const int et = threadIdx.x - (kGemmThreads - 128);     // 0..127 within the epilogue warps
+    const int et = threadIdx.x - kEpiWarp0 * 32;           // 0..255 within the epilogue warps
     float inv_a = 1.f, inv_b = 1.f;   // F16: 1 / s_a, 1 / s_b -- exact powers of two, applied one after the other (their
     if constexpr (F16) {              // product alone could leave the fp32 range for tiny gradient tensors)
       float s_unused;
@@ -475,12 +481,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int n0 = nt * BN;
       float* sbias = sbias_all + tile_par * BN;
       if (p.bias) {
-#pragma unroll
-        for (int u = 0; u < BN / 128 + (BN < 128 ? 1 : 0); ++u) {
-          const int cidx = et + u * 128;
-          if (cidx < BN) sbias[cidx] = (n0 + cidx < p.N) ? __ldg(p.bias + n0 + cidx) : 0.f;
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");   // (barrier 1 belongs to the split warps)
+        if (et < BN) sbias[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // the eight epilogue warps
       }
       tile_par ^= 1u;
 
@@ -488,36 +490,37 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S::kAccCols);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
+      for (int c32 = 0; c32 < BN; c32 += 32) {
+        const int c0 = c32 + half * 16;           // this warp's 16 columns of the chunk
+        uint32_t r[16];
+        tmem_ld16(t_addr + (uint32_t)c0, r);
         // the residual / pre-activation operand of this chunk: all four 32-byte loads of the row go out now, under the
         // tensor-memory load, instead of one at a time right in front of their use (four DRAM round trips per chunk)
-        const bool res_pre = rrow != nullptr && row_ok && (n0 + c0 + 32 <= p.N) && p.vec_ok == 2;
-        float4 rq[8];
+        const bool res_pre = rrow != nullptr && row_ok && (n0 + c0 + 16 <= p.N) && p.vec_ok == 2;
+        float4 rq[4];
         if (res_pre) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) ld8(rrow + n0 + c0 + u * 8, rq[2 * u], rq[2 * u + 1]);
+          for (int u = 0; u < 2; ++u) ld8(rrow + n0 + c0 + u * 8, rq[2 * u], rq[2 * u + 1]);
         }
         tmem_ld_wait();
 #pragma unroll
         for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
-          uint32_t r2[32];
-          tmem_ld32(t_addr + (uint32_t)(ch * BN + c0), r2);
+          uint32_t r2[16];
+          tmem_ld16(t_addr + (uint32_t)(ch * BN + c0), r2);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
         if constexpr (F16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_a * inv_b);
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_a * inv_b);
         }
         if (row_ok) {
           const int nbase = n0 + c0;
-          if (nbase + 32 <= p.N && p.vec_ok == 2) {
+          if (nbase + 16 <= p.N && p.vec_ok == 2) {
             // 256-bit path: every store / load instruction moves one full 32-byte sector per thread
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 16; j += 8) {
               float4 v0 = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                       __uint_as_float(r[j + 3]));
               float4 v1 = make_float4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]),
@@ -560,9 +563,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
               st8(crow + nbase + j, v0, v1);
             }
-          } else if (nbase + 32 <= p.N && p.vec_ok) {
+          } else if (nbase + 16 <= p.N && p.vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 16; j += 4) {
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                      __uint_as_float(r[j + 3]));
               if (p.bias) {
@@ -589,7 +592,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const int n = nbase + j;
               if (n < p.N) {
                 float v = __uint_as_float(r[j]);
