@@ -491,11 +491,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S::kAccCols);
 #pragma unroll 1
       for (int c32 = 0; c32 < BN; c32 += 32) {
+        if (n0 + c32 >= p.N) break;               // columns past N (N = 288 on 128-wide tiles: three of four chunks of the last tile)
         const int c0 = c32 + half * 16;           // this warp's 16 columns of the chunk
-        uint32_t r[16];
+        uint32_t r[16], r2[16];
         tmem_ld16(t_addr + (uint32_t)c0, r);
-        // the residual / pre-activation operand of this chunk: all four 32-byte loads of the row go out now, under the
-        // tensor-memory load, instead of one at a time right in front of their use (four DRAM round trips per chunk)
+        if constexpr (S::kChains == 2) tmem_ld16(t_addr + (uint32_t)(BN + c0), r2);   // both accumulator chains under one wait
+        static_assert(S::kChains <= 2, "epilogue sums at most two accumulator chains");
+        // the residual / pre-activation operand of this chunk: both 32-byte loads of the row go out now, under the
+        // tensor-memory load, instead of one at a time right in front of their use (a DRAM round trip each)
         const bool res_pre = rrow != nullptr && row_ok && (n0 + c0 + 16 <= p.N) && p.vec_ok == 2;
         float4 rq[4];
         if (res_pre) {
@@ -503,11 +506,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int u = 0; u < 2; ++u) ld8(rrow + n0 + c0 + u * 8, rq[2 * u], rq[2 * u + 1]);
         }
         tmem_ld_wait();
-#pragma unroll
-        for (int ch = 1; ch < S::kChains; ++ch) {   // fixed summation order over the accumulator chains
-          uint32_t r2[16];
-          tmem_ld16(t_addr + (uint32_t)(ch * BN + c0), r2);
-          tmem_ld_wait();
+        if constexpr (S::kChains == 2) {   // fixed summation order over the accumulator chains
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
