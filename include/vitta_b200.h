@@ -343,8 +343,10 @@ int vitta_gemm_tf32x3(const float* A, int64_t lda, const float* Bhi, const float
 /* Extended epilogue (Swin MLP / attention projections):
  *   v = acc + bias;  aux_out[m,n] = v (optional: the pre-activation, leading dimension ldc);
  *   act 1: v = GELU(v);  act 2: v = v * GELU'(residual[m,n]) (residual = saved pre-activation; backward of fc1's GELU);
+ *   act 4: v = GELU(v) and aux_out[m,n] = GELU'(pre-activation) INSTEAD of the pre-activation (one erf serves both);
+ *   act 5: v = v * residual[m,n] (residual = the derivative saved by act 4: the backward multiplies, no erf / exp);
  *   v *= row_scale[m / rows_per_group] (optional: DropPath's per-sample factor, swin_transformer.py:210,246,252);
- *   act != 2: v += residual[m,n] (the block's shortcut, swin_transformer.py:266,272). */
+ *   act 0, 1, 4: v += residual[m,n] (the block's shortcut, swin_transformer.py:266,272). */
 int vitta_gemm_tf32x3_ex(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* C,
                          int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, int64_t ldr,
                          int act, float* aux_out, const float* row_scale, int64_t rows_per_group, int force_bn,

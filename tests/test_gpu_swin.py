@@ -122,6 +122,16 @@ def test_gemm_extended_epilogue(cuda_device):
     pk = prek.double().requires_grad_(True)
     F.gelu(pk).sum().backward()
     cases.assert_close(dx.cpu(), ((g.double() @ w.double()) * pk.grad).cpu(), 1e-5, 1e-5, "dgelu epilogue")
+    # GELU with its derivative from one erf (act 4: aux_out = GELU'(pre)), and the multiplying backward epilogue (act 5)
+    dg = torch.empty(m, n, device="cuda")
+    out4 = ops_swin.gemm(a, w, 0, bias=bias, residual=res, act=4, aux_out=dg, row_scale=rs, rows_per_group=250)
+    prg = pr.clone().requires_grad_(True)
+    F.gelu(prg).sum().backward()
+    cases.assert_close(out4.cpu(), ref.cpu(), 1e-5, 1e-5, "gelu (act 4)")
+    cases.assert_close(dg.cpu(), prg.grad.cpu(), 1e-5, 1e-5, "gelu derivative (act 4)")
+    dgk = _rnd(m, k, seed=7)
+    dx5 = ops_swin.gemm(g, w, 1, residual=dgk, act=5)
+    cases.assert_close(dx5.cpu(), ((g.double() @ w.double()) * dgk.double()).cpu(), 1e-5, 1e-5, "operand-multiply epilogue (act 5)")
     # weight gradient through the conv wgrad kernel and bias gradient
     dw = ops_swin.linear_wgrad(a, g)
     cases.assert_close(dw.cpu(), (g.double().t() @ a.double()).cpu(), 1e-5, 1e-4, "linear wgrad")

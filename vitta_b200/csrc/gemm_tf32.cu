@@ -530,7 +530,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v0.x += b0.x; v0.y += b0.y; v0.z += b0.z; v0.w += b0.w;
                 v1.x += b1.x; v1.y += b1.y; v1.z += b1.z; v1.w += b1.w;
               }
-              if (arow) st8(arow + nbase + j, v0, v1);
+              if (p.act == 4) {   // GELU, its derivative to aux_out (instead of the pre-activation)
+                float4 d0, d1;
+                v0.x = gelu_with_grad(v0.x, d0.x); v0.y = gelu_with_grad(v0.y, d0.y);
+                v0.z = gelu_with_grad(v0.z, d0.z); v0.w = gelu_with_grad(v0.w, d0.w);
+                v1.x = gelu_with_grad(v1.x, d1.x); v1.y = gelu_with_grad(v1.y, d1.y);
+                v1.z = gelu_with_grad(v1.z, d1.z); v1.w = gelu_with_grad(v1.w, d1.w);
+                if (arow) st8(arow + nbase + j, d0, d1);
+              } else if (arow) {
+                st8(arow + nbase + j, v0, v1);
+              }
               if (p.act == 1) {
                 v0.x = gelu_exact(v0.x); v0.y = gelu_exact(v0.y); v0.z = gelu_exact(v0.z); v0.w = gelu_exact(v0.w);
                 v1.x = gelu_exact(v1.x); v1.y = gelu_exact(v1.y); v1.z = gelu_exact(v1.z); v1.w = gelu_exact(v1.w);
@@ -542,6 +551,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   v0.z *= gelu_grad(r0.z) * rscale; v0.w *= gelu_grad(r0.w) * rscale;
                   v1.x *= gelu_grad(r1.x) * rscale; v1.y *= gelu_grad(r1.y) * rscale;
                   v1.z *= gelu_grad(r1.z) * rscale; v1.w *= gelu_grad(r1.w) * rscale;
+                } else if (p.act == 5) {   // multiply by the operand (the saved GELU derivative)
+                  v0.x *= r0.x * rscale; v0.y *= r0.y * rscale; v0.z *= r0.z * rscale; v0.w *= r0.w * rscale;
+                  v1.x *= r1.x * rscale; v1.y *= r1.y * rscale; v1.z *= r1.z * rscale; v1.w *= r1.w * rscale;
                 } else {
                   v0.x = fmaf(v0.x, rscale, r0.x); v0.y = fmaf(v0.y, rscale, r0.y);
                   v0.z = fmaf(v0.z, rscale, r0.z); v0.w = fmaf(v0.w, rscale, r0.w);
@@ -571,13 +583,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + j);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
               }
-              if (arow) st4(arow + nbase + j, v);
+              if (p.act == 4) {
+                float4 d;
+                v.x = gelu_with_grad(v.x, d.x); v.y = gelu_with_grad(v.y, d.y);
+                v.z = gelu_with_grad(v.z, d.z); v.w = gelu_with_grad(v.w, d.w);
+                if (arow) st4(arow + nbase + j, d);
+              } else if (arow) {
+                st4(arow + nbase + j, v);
+              }
               if (p.act == 1) { v.x = gelu_exact(v.x); v.y = gelu_exact(v.y); v.z = gelu_exact(v.z); v.w = gelu_exact(v.w); }
               if (rrow) {
                 const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
                 if (p.act == 2) {
                   v.x *= gelu_grad(rr.x); v.y *= gelu_grad(rr.y); v.z *= gelu_grad(rr.z); v.w *= gelu_grad(rr.w);
                   v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
+                } else if (p.act == 5) {
+                  v.x *= rr.x * rscale; v.y *= rr.y * rscale; v.z *= rr.z * rscale; v.w *= rr.w * rscale;
                 } else {
                   v.x = fmaf(v.x, rscale, rr.x); v.y = fmaf(v.y, rscale, rr.y);
                   v.z = fmaf(v.z, rscale, rr.z); v.w = fmaf(v.w, rscale, rr.w);
@@ -596,9 +617,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (n < p.N) {
                 float v = __uint_as_float(r[j]);
                 if (p.bias) v += sbias[c0 + j];
-                if (arow) arow[n] = v;
+                if (p.act == 4) {
+                  float d;
+                  v = gelu_with_grad(v, d);
+                  if (arow) arow[n] = d;
+                } else if (arow) {
+                  arow[n] = v;
+                }
                 if (p.act == 1) v = gelu_exact(v);
-                if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale : fmaf(v, rscale, rrow[n]);
+                if (rrow) v = (p.act == 2) ? v * gelu_grad(rrow[n]) * rscale
+                              : (p.act == 5) ? v * rrow[n] * rscale : fmaf(v, rscale, rrow[n]);
                 else v *= rscale;
                 if (p.act == 3) v = fmaxf(v, 0.f);
                 if (p.amax_out) out_amax = fmaxf(out_amax, fabsf(v));
@@ -1065,7 +1093,7 @@ static int gemm_impl(const float* A, int64_t lda, const void* Bhi, const void* B
   VITTA_CHECK_ARG(A && Bhi && Blo && C && M > 0 && N > 0 && K > 0, VITTA_E_BADARG, "gemm_tf32x3: bad arguments");
   VITTA_CHECK_ARG(!f16 || (b_amax && ldb % 8 == 0), VITTA_E_BADARG,
                   "gemm_f16x3: needs both amax scalars and fp16 weight rows that are multiples of 8 elements");
-  VITTA_CHECK_ARG(act >= 0 && act <= 2 && !(act == 2 && !residual), VITTA_E_BADARG,
+  VITTA_CHECK_ARG((act >= 0 && act <= 2 || act == 4 || act == 5) && !((act == 2 || act == 5) && !residual), VITTA_E_BADARG,
                   "gemm_tf32x3: act must be 0/1/2 and act 2 needs the pre-activation in `residual`");
   VITTA_CHECK_ARG(!row_scale || (rows_per_group > 0 && rows_per_group < (1ll << 31)), VITTA_E_BADARG,
                   "gemm_tf32x3: rows_per_group");

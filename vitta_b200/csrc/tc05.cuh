@@ -262,6 +262,13 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + 
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
+// gelu(x) and its derivative from ONE erf: the forward epilogue saves the derivative for the backward, which then only
+// multiplies (no erf / exp per element in the data-gradient GEMM's epilogue)
+__device__ __forceinline__ float gelu_with_grad(float x, float& d) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  d = fmaf(x * 0.3989422804014327f, expf(-0.5f * x * x), cdf);
+  return x * cdf;
+}
 
 
 // MN-major TF32 operand tile.  32-bit MN-major operands have exactly one legal shared-memory layout on sm_100:

@@ -339,21 +339,23 @@ class SwinMlpFn(torch.autograd.Function):
     def forward(ctx, y, shortcut, w1, b1, w2, b2, n_samples, rscale):
         _chk(y, "swin_mlp")
         rows = y.shape[0]
-        pre = torch.empty(rows, w1.shape[0], dtype=torch.float32, device=y.device)
-        act = gemm(y, w1, 0, bias=b1, act=1, aux_out=pre, want_amax=True)
+        # fc1's epilogue computes GELU and, from the same erf, GELU' -- saved in place of the pre-activation, so the backward's
+        # data-gradient epilogue only multiplies (an erf + exp per element in a GEMM epilogue bounds the K = 96 layers)
+        dgelu = torch.empty(rows, w1.shape[0], dtype=torch.float32, device=y.device)
+        act = gemm(y, w1, 0, bias=b1, act=4, aux_out=dgelu, want_amax=True)
         out = gemm(act, w2, 0, bias=b2, residual=shortcut, row_scale=rscale, rows_per_group=rows // n_samples)
-        ctx.save_for_backward(y, w1, w2, pre, act, rscale)
+        ctx.save_for_backward(y, w1, w2, dgelu, act, rscale)
         ctx.meta = (n_samples, b1 is not None, b2 is not None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        y, w1, w2, pre, act, rscale = ctx.saved_tensors
+        y, w1, w2, dgelu, act, rscale = ctx.saved_tensors
         n_samples, has_b1, has_b2 = ctx.meta
         g = g.contiguous()
         rpg = g.shape[0] // n_samples
         gs = row_scale(g, rscale, rpg) if rscale is not None else g
-        dpre = gemm(gs, w2, 1, residual=pre, act=2, want_amax=True)      # (g @ W2) * GELU'(pre) in the epilogue
+        dpre = gemm(gs, w2, 1, residual=dgelu, act=5, want_amax=True)    # (g @ W2) * GELU'(pre) in the epilogue
         if has_b2:
             dw2, db2 = linear_wgrad(act, gs, want_bias=True)
         else:
