@@ -411,6 +411,11 @@ int vitta_conv2d_dgrad_f16x3(const float* dY, const float* dy_amax, int F, int H
  * are summed in a fixed order (deterministic).  ws: vitta_conv2d_wgrad_ws_floats() floats of scratch (no init needed).
  *   replaces: autograd's convolution_backward weight branch (cuDNN wgrad) for the layers above. */
 int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+/* Host-only: the split-K plan (out[4] = N tile, base items, K splits, 32-pixel stages).  The persistent grid walks
+ * base items x splits work items round-robin over the SMs; the split count minimises ceil(items / SMs) * (stages per item +
+ * a fixed per-item cost) -- never a partial extra pass with most SMs idle. */
+int vitta_conv2d_wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int f16,
+                            int* out);
 int vitta_conv2d_wgrad_tf32x3(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
                               int stride, int pad, float* dW, int accumulate, float* ws, void* stream);
 

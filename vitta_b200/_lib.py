@@ -88,6 +88,7 @@ _SIGNATURES = {
     "vitta_conv2d_dgrad_tf32x3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_conv2d_wgrad_ws_floats": (C.c_int64, [C.c_int] * 9),
+    "vitta_conv2d_wgrad_plan": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int)]),
     "vitta_conv2d_wgrad_tf32x3": (C.c_int, [_P, _P] + [C.c_int] * 9 + [_P, C.c_int, _P, _P]),
     "vitta_gemm_tf32x3_ex": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, _P, _P,
                                        C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int, _P]),

@@ -671,6 +671,22 @@ int64_t vitta_conv2d_wgrad_ws_floats(int F, int H, int W, int Cin, int Cout, int
   return (int64_t)splits * Cout * KH * KW * Cin + (int64_t)splits * Cout;   // weight partials + bias partials
 }
 
+// Host-only: the split-K plan of a weight gradient (no device work; callable without a GPU, the SM count then defaults to
+// 148).  out = { N tile, base items (Cout tiles x taps x Cin tiles), K splits, 32-pixel stages in total }.
+int vitta_conv2d_wgrad_plan(int F, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int f16,
+                            int* out) {
+  if (!out || F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride < 1) return VITTA_E_BADARG;
+  flatten_pointwise(F, H, W, KH, KW, stride, pad);
+  WgPlan pl;
+  if (wgrad_plan(F, H, W, Cin, Cout, KH, KW, stride, pad, &pl, f16 != 0)) return VITTA_E_BADARG;
+  const WgradParams& p = pl.p;
+  out[0] = pl.bn;
+  out[1] = p.m_tiles * (KH * KW / p.tap_group) * p.n_ctiles;
+  out[2] = p.splits;
+  out[3] = p.boxes_w * p.boxes_h * p.boxes_f;
+  return 0;
+}
+
 static int wgrad_impl(const float* X, const float* dY, int F, int H, int W, int Cin, int Cout, int KH, int KW,
                       int stride, int pad, float* dW, int accumulate, float* ws, void* stream, const float* x_amax,
                       const float* dy_amax, float* dbias = nullptr) {
