@@ -223,7 +223,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
     uint32_t it = 0, tile_ctr = 0, chunk_ctr = 0;
     float sv, sv_inv_unused;
     f16_split_scale(__ldg(p.qkv_amax), sv, sv_inv_unused);
-    for (int item = item0; item < item1; ++item, ++it) {
+    // Set-up of one item: token maps, bias table on a change of head, the K gather.  tok[] / info[] are double-buffered by
+    // item parity and the set-up of item i + 1 runs INSIDE the last tile of item i, between its first eight V chunks (the
+    // ring is full then: the loaders would only wait) and the rest: it needs just the S MMAs of that tile to have retired
+    // (KV_FREE), while the softmax passes and PV products of the tile are still running.  Done at the item boundary it cost
+    // +9.5 K cycles per item (the K gather alone is four dependent batches of global loads): profiles/r02_wmsa_fwd_timeline_*.
+    // The bias table is single: a change of head (once per ~100 items) waits for the previous item's TAB_FREE too.
+    auto prepare_item = [&](int item, uint32_t it) {
       const int head = item / nwin_total;
       const int wg = item - head * nwin_total;
       const int b = wg / nwin;
@@ -231,10 +237,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       const int ww = w % g.nw2; w /= g.nw2;
       const int wh = w % g.nw1;
       const int wd = w / g.nw1;
-      // tok[] / info[] are double-buffered by item parity, so the next item's K can be gathered as soon as the S MMAs of the
-      // current item's last tile have retired (KV_FREE) -- its softmax passes and PV products are still running; a single
-      // buffer made every item boundary wait for pass 1 of the last tile (+9.5 K cycles per item in the time stamps).
-      // The bias table is single: a change of head (once per ~100 items) waits for the previous item's TAB_FREE too.
       int* info = info_all + (it & 1) * kAtColPad;
       int* tok = tok_all + (it & 1) * kAtMaxKeys;
       mbar_wait(&bar[B_KV_FREE], (it & 1) ^ 1);
@@ -282,6 +284,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[B_KV_READY]);
       WMSA_TR(41);
+    };
+    if (item0 < item1) prepare_item(item0, 0);
+    for (int item = item0; item < item1; ++item, ++it) {
+      const int head = item / nwin_total;
+      const int* tok = tok_all + (it & 1) * kAtMaxKeys;
+      const float* qkv_h = p.qkv + head * 32 + q4 * 4;
       // V chunks: groups of 4 chunks (8 float4 per thread), the next group in flight while the current one is stored
       auto v_issue = [&](float4 (&v)[8], int grp) {
 #pragma unroll
@@ -356,6 +364,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) wmsa3d_fwd_kernel(const WmsaFw
           v_drain(va, grp);
           if (grp + 2 < n_groups) v_issue(va, grp + 2);
           if (grp + 1 < n_groups) v_drain(vb8, grp + 1);
+          // the next item's set-up, once, after the first (up to) eight V chunks of this item's last tile
+          if (grp == 0 && tile == n_tiles - 1 && item + 1 < item1) prepare_item(item + 1, it + 1);
         }
       }
     }
