@@ -200,43 +200,51 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 // Stem weight gradient  dW[co][c][kh][kw] = sum over (f, ho, wo) of dY[f, ho, wo, co] * XP[f, 2ho + kh, 2wo + kw, c]
 // (cuDNN's NHWC wgrad engine before: 1.49 ms at the bench shape).  64 x 147 outputs reduced over 1.6 M pixels: a
-// register-blocked fp32 FFMA kernel -- exact fp32 products, no operand split needed.  CTA = 64 consecutive output pixels
-// per tile: the dY rows (64 x 64) and the compacted 7 x 7 x 3 input windows (64 x 147, padded to 156) are staged in
-// shared memory; thread (co-group of 4, k-group of 12) keeps a 4 x 12 accumulator block over all its tiles (one 128-bit
-// shared load of dY + three of the window per 48 FMAs).  Per-CTA partials go to a workspace and are summed in CTA order
+// register-blocked fp32 kernel -- exact fp32 products, no operand split needed.  CTA = 64 consecutive output pixels per
+// tile: the dY rows (64 x 64) and the compacted 7 x 7 x 3 input windows (64 x 147, padded to 156) are staged in shared
+// memory.  Thread (pixel half, co-group of 8, k-group of 10) keeps an 8 x 10 accumulator block over its 32 pixels of every
+// tile as 40 packed pairs and updates it with FFMA2 (fma.rn.f32x2): the three-register FFMA issues every other cycle per
+// scheduler on this part, so a scalar-FFMA kernel tops out at half the fp32 peak (the first version: 28 TFLOP/s, 1.08 ms);
+// two 128-bit loads of dY + five 64-bit loads of the window feed 40 FFMA2 (the loads are broadcast / conflict-free: dY is stored as
+// [pixel][half of the co-group][co-group][4]).  Per-CTA partials go to a workspace and are summed in CTA order
 // (deterministic).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSwP = 64;            // pixels per tile
-constexpr int kSwK = 156;           // 147 window values padded to 13 groups of 12
-constexpr int kSwThreads = 256;     // 16 co-groups x 13 k-groups = 208 compute threads; all 256 stage
+constexpr int kSwKG = 10;           // window values per k-group (five packed pairs)
+constexpr int kSwGroups = 15;       // 147 window values in 15 groups of 10
+constexpr int kSwK = 152;           // row length of the window buffer / the partials: 150 used + 2 (16-byte rows)
+constexpr int kSwThreads = 256;     // 2 pixel halves x 8 co-groups x 15 k-groups = 240 compute threads; all 256 stage
+constexpr int kSwCompute = 8 * kSwGroups;     // compute threads per pixel half
 
 __global__ void __launch_bounds__(kSwThreads, 2) stem_wgrad_kernel(const float4* __restrict__ xp,
                                                                   const float* __restrict__ gy, float* __restrict__ ws,
                                                                   int F, int H, int W) {
   extern __shared__ __align__(16) float stem_smem[];
-  float (*sA)[64] = reinterpret_cast<float (*)[64]>(stem_smem);
+  float* sA = stem_smem;                                                 // [64 pixels][2][8][4]
   float (*sB)[kSwK] = reinterpret_cast<float (*)[kSwK]>(stem_smem + kSwP * 64);
   const int Hp = H + 6, Wp = W + 6, Ho = H / 2, Wo = W / 2;
   const int64_t npix = (int64_t)F * Ho * Wo;
   const int64_t ntiles = (npix + kSwP - 1) / kSwP;
   const int tid = threadIdx.x;
-  const int cg = tid & 15, kg = tid >> 4;          // co-group (4 channels), k-group (12 window values); kg < 13 computes
-  float acc[4][12];
+  const bool compute = tid < 2 * kSwCompute;
+  const int ph = tid / kSwCompute, t = tid - ph * kSwCompute;
+  const int cg = t & 7, kg = t >> 3;               // co-group (8 channels), k-group (10 window values)
+  float2 acc[8][kSwKG / 2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 12; ++j) acc[i][j] = 0.f;
-  // zero the padding columns once (147..155)
+    for (int j = 0; j < kSwKG / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  // zero the padding columns once (147..151)
   for (int i = tid; i < kSwP * (kSwK - 147); i += kSwThreads) sB[i / (kSwK - 147)][147 + i % (kSwK - 147)] = 0.f;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t p0 = tile * kSwP;
     __syncthreads();                               // the previous tile has been consumed
-    // dY rows: 64 pixels x 16 float4
+    // dY rows: 64 pixels x 16 float4; float4 q of a row (channels 4q .. 4q+3) goes to [half = q & 1][co-group = q >> 1]
     for (int i = tid; i < kSwP * 16; i += kSwThreads) {
       const int p = i >> 4, q = i & 15;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p0 + p < npix) v = ld_stream4(gy + (p0 + p) * 64 + q * 4);
-      *reinterpret_cast<float4*>(&sA[p][q * 4]) = v;
+      *reinterpret_cast<float4*>(sA + p * 64 + (q & 1) * 32 + (q >> 1) * 4) = v;
     }
     // input windows: (pixel, filter row) pairs, seven 4-channel pixels each, compacted to 3 channels
     for (int i = tid; i < kSwP * 7; i += kSwThreads) {
@@ -245,9 +253,9 @@ __global__ void __launch_bounds__(kSwThreads, 2) stem_wgrad_kernel(const float4*
       float* dst = &sB[p][kh * 21];
       if (pix < npix) {
         const int wo = (int)(pix % Wo);
-        const int64_t t = pix / Wo;
-        const int ho = (int)(t % Ho);
-        const int64_t f = t / Ho;
+        const int64_t tt = pix / Wo;
+        const int ho = (int)(tt % Ho);
+        const int64_t f = tt / Ho;
         const float4* src = xp + (f * Hp + 2 * ho + kh) * Wp + 2 * wo;
 #pragma unroll
         for (int kw = 0; kw < 7; ++kw) {
@@ -260,29 +268,49 @@ __global__ void __launch_bounds__(kSwThreads, 2) stem_wgrad_kernel(const float4*
       }
     }
     __syncthreads();
-    if (kg < 13) {
-#pragma unroll 4
-      for (int p = 0; p < kSwP; ++p) {
-        const float4 a = *reinterpret_cast<const float4*>(&sA[p][cg * 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&sB[p][kg * 12]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&sB[p][kg * 12 + 4]);
-        const float4 b2 = *reinterpret_cast<const float4*>(&sB[p][kg * 12 + 8]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+    if (compute) {
+      const float* pa = sA + ph * 32 * 64 + cg * 4;
+      const float* pb = &sB[ph * 32][kg * kSwKG];
+#pragma unroll 2
+      for (int p = 0; p < kSwP / 2; ++p) {
+        const float4 a0 = *reinterpret_cast<const float4*>(pa + p * 64);
+        const float4 a1 = *reinterpret_cast<const float4*>(pa + p * 64 + 32);
+        float2 bp[kSwKG / 2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < kSwKG / 2; ++j) bp[j] = *reinterpret_cast<const float2*>(pb + p * kSwK + 2 * j);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int j = 0; j < 12; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int i = 0; i < 8; ++i) {
+          const float2 a2 = make_float2(av[i], av[i]);
+#pragma unroll
+          for (int j = 0; j < kSwKG / 2; ++j) acc[i][j] = __ffma2_rn(a2, bp[j], acc[i][j]);
+        }
       }
     }
   }
-  if (kg < 13) {
+  // the two pixel halves of a (co-group, k-group) are added: half 1 parks its block in shared memory (the window buffer),
+  // half 0 adds it to its own in a fixed order
+  __syncthreads();
+  float* park = stem_smem + kSwP * 64;
+  static_assert(kSwCompute * 8 * kSwKG <= kSwP * kSwK, "parked accumulators fit the window buffer");
+  if (compute && ph == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < kSwKG / 2; ++j)
+        *reinterpret_cast<float2*>(park + (i * (kSwKG / 2) + j) * 2 * kSwCompute + t * 2) = acc[i][j];
+  }
+  __syncthreads();
+  if (compute && ph == 0) {
     float* o = ws + (int64_t)blockIdx.x * 64 * kSwK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 12; j += 4)
-        st4(o + (cg * 4 + i) * kSwK + kg * 12 + j, make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]));
+      for (int j = 0; j < kSwKG / 2; ++j) {
+        const float2 other = *reinterpret_cast<const float2*>(park + (i * (kSwKG / 2) + j) * 2 * kSwCompute + t * 2);
+        *reinterpret_cast<float2*>(o + (cg * 8 + i) * kSwK + kg * kSwKG + 2 * j) =
+            make_float2(acc[i][j].x + other.x, acc[i][j].y + other.y);
+      }
   }
 }
 
