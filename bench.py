@@ -136,30 +136,38 @@ def _work(name, a):
     return name[6:] if name.startswith("vitta_") else name, 0.0, 0.0
 
 
-def attribute_step(adapter, resident, step=None):
-    """One extra, instrumented adaptation step: CUDA events around every launch of our library on the launching
+def attribute_step(adapter, resident, step=None, repeats=3):
+    """Extra, instrumented adaptation steps: CUDA events around every launch of our library on the launching
     stream (torch's current stream).  Returns {kernel family: {"ms", "launches", "flops", "bytes"}} with ALGORITHMIC
-    flops (2*M*N*K of the fp32 product, not the 3 MMAs issued per product) and bytes."""
+    flops (2*M*N*K of the fp32 product, not the 3 MMAs issued per product) and bytes.  ``repeats`` passes are taken and
+    every family keeps its FASTEST pass: when the enqueuing CPU falls behind, the device catches up and the launch latency
+    lands between an event and its kernel (one slow pass moved the GEMM family from 10.8 to 12.3 ms between two runs of
+    the same build)."""
     import torch
     from vitta_b200 import _lib
-    # Eager launches are CPU-bound (~0.7 k launches at ~10 us of Python / ctypes each), so a GPU that has caught up with
+    # Eager launches are CPU-bound (~0.5 k launches at ~10 us of Python / ctypes each), so a GPU that has caught up with
     # the CPU would add the launch latency to every event pair.  A spin kernel in front keeps the device busy while the
     # whole step is enqueued behind it: the kernels then run back to back, as they do inside the replayed CUDA graph.
-    torch.cuda.synchronize()
-    torch.cuda._sleep(int(1.5e8))       # ~80 ms at 1.9 GHz
-    _lib.profile = []
-    (step or (lambda: adapter._adapt_eager(resident)))()
-    torch.cuda.synchronize()
-    recs, _lib.profile = _lib.profile, None
-    fam = {}
-    for name, e0, e1, a in recs:
-        key, flops, nbytes = _work(name, a)
-        d = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
-        d["ms"] += e0.elapsed_time(e1)
-        d["launches"] += 1
-        d["flops"] += flops
-        d["bytes"] += nbytes
-    return fam
+    best = {}
+    for _ in range(max(1, int(repeats))):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(2.5e8))       # ~130 ms at 1.9 GHz
+        _lib.profile = []
+        (step or (lambda: adapter._adapt_eager(resident)))()
+        torch.cuda.synchronize()
+        recs, _lib.profile = _lib.profile, None
+        fam = {}
+        for name, e0, e1, a in recs:
+            key, flops, nbytes = _work(name, a)
+            d = fam.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        for key, d in fam.items():
+            if key not in best or d["ms"] < best[key]["ms"]:
+                best[key] = d
+    return best
 
 
 def _table(fam):
