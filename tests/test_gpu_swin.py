@@ -199,6 +199,9 @@ ATTN_CASES = [
     (1, 16, 7, 7, 4, (8, 7, 7), (4, 3, 3)),      # temporal-only shift (H, W clamp the shift to 0)
     (2, 4, 7, 7, 1, (8, 7, 7), (4, 3, 3)),       # clamped window (4,7,7): N = 196, relative_position_index[:N,:N] quirk
     (3, 8, 4, 4, 2, (8, 7, 7), (0, 0, 0)),       # clamped window (8,4,4): N = 128
+    (2, 2, 4, 4, 2, (8, 7, 7), (0, 0, 0)),       # clamped window (2,4,4): N = 32 = a single 32-key chunk (one PV issuer idle)
+    (5, 1, 4, 4, 1, (8, 7, 7), (0, 0, 0)),       # clamped window (1,4,4): N = 16, items alternate the chunk parity
+    (2, 8, 7, 14, 3, (8, 7, 7), (4, 3, 3)),      # two windows along W only, three heads (odd number of items per CTA)
 ]
 
 
