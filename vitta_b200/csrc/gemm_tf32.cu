@@ -12,7 +12,7 @@
 //   epilogue warps drain the other buffer (tcgen05.ld 32x32b) with the fused bias / GELU / residual epilogue.
 // * Persistent: grid = min(#tiles, #SMs); tiles are walked n-fastest so CTAs running together share an A panel in L2.
 //
-// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-9 = operand split, 10-13 = epilogue.
+// Warp roles (576 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-9 = operand split, 10-17 = epilogue.
 // (Eight split warps: profiling showed the four-warp split ~80 % busy per stage at BN = 64 -- LDS latency under
 // tensor-core smem traffic, the rounding ALU work and the proxy fence -- i.e. it, not the tensor pipe, set the stage time.)
 //

@@ -7,18 +7,20 @@
 //   (B, D, H, W, 3, heads, 32) qkv tensor with the cyclic shift folded into the addresses, and the output rows are
 //   scattered back to their un-shifted token positions.
 //
-// Forward kernel (448 threads, 1 CTA / SM, persistent over a contiguous item range, head-major so the bias table of a
-// head is loaded once; warp numbering of the current kernel: see wmsa3d_fwd_kernel -- two softmax groups, warps 0-7):
-//   loaders: gather K (whole window), per 128-row tile Q (pre-scaled), per 32-key chunk V; split every value
-//              into tf32 hi / lo and store both in the UMMA shared-memory layouts (K-major SWIZZLE_128B for Q, K, P;
-//              MN-major SWIZZLE_128B_BASE32B for V)
-//   warp  8    one thread issues tcgen05.mma.kind::tf32:  S[128 x N] = Q K^T  (3 MMAs per k-step: lo*hi, hi*lo, hi*hi)
-//              into TMEM columns [0, 400), then per key chunk  O[128 x 32] += P_chunk V_chunk  into columns [400, 432)
-//   warps 0-3  softmax: thread = query row = TMEM lane.  pass 1 adds bias[rel(i, j)] and the shift mask to S in place
-//              (tcgen05.ld / tcgen05.st) and finds the row maximum; pass 2 exponentiates, accumulates the row sum and
-//              writes P (hi / lo) chunk by chunk for the PV MMAs; finally O / rowsum is written out with log-sum-exp.
+// Forward kernel (480 threads, 1 CTA / SM, persistent over a contiguous item range, head-major so the bias table of a
+// head is loaded once; details at wmsa3d_fwd_kernel):
+//   warps 8-11 loaders: gather K (whole window), per 128-row tile Q (pre-scaled), per 32-key chunk V; Q and K are split
+//              into tf32 hi / lo in the K-major SWIZZLE_128B layout, V into fp16 hi / lo (16-bit MN-major SWIZZLE_128B)
+//   warp  12   issues tcgen05.mma.kind::tf32:  S[128 x N] = Q K^T  (3 MMAs per k-step: lo*hi, hi*lo, hi*hi) into TMEM
+//              columns [0, 400)
+//   warps 0-7  two softmax groups (thread = query row = TMEM lane) taking the 32-column chunks alternately: pass 1 adds
+//              bias[rel(i, j)] and the shift mask to S in place and finds the row maximum; pass 2 exponentiates,
+//              accumulates the row sum and writes P (fp16 hi / lo pairs) in place over the S columns
+//   warps 13, 14  one PV issuer per group: O_g[128 x 32] += P_chunk V_chunk on kind::f16 (columns [400, 432), [432, 464));
+//              the epilogue adds the two accumulators and writes O / rowsum with the log-sum-exp
 //   The whole score row lives in TMEM, so there is no online-softmax rescaling and the N x N matrix never touches HBM.
-// Backward (v0): fp32 FFMA2 kernel, one CTA (384 threads) per item with Q, K, V, dO resident in shared memory (see wmsa3d_bwd_kernel).
+// Backward: wmsa3d_bwd3_kernel<MODE> (tcgen05, kind::f16 operand pairs; two launches); wmsa3d_bwd_kernel is an exact fp32
+// FFMA2 kernel (one CTA per item with Q, K, V, dO resident in shared memory) kept as an on-device cross-check.
 #include <cuda_fp16.h>
 
 #include "tc05.cuh"
