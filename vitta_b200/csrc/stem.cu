@@ -59,18 +59,21 @@ struct StemBN {
 
 // thread = (pooled pixel, 4 channels).  Window rows 2ho-1 .. 2ho+1, cols 2wo-1 .. 2wo+1, scanned h-major like PyTorch;
 // the first maximum wins (strict >).  code = 3*dh + dw of the winner.
+// I = uint32_t when the flat index fits (the index decomposition is three divisions per thread and iteration, and 64-bit
+// ones cost more issue slots than the nine loads they address).
+template <typename I>
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ x, StemBN bn,
                                                               float* __restrict__ out, uint8_t* __restrict__ code,
                                                               int F, int H, int W, int C4) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const int64_t total = (int64_t)F * Ho * Wo * C4;
+  const I total = (I)F * Ho * Wo * C4;
   const int C = C4 * 4;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int c = (int)(i % C4) * 4;
-    int64_t q = i / C4;
-    const int wo = (int)(q % Wo); q /= Wo;
-    const int ho = (int)(q % Ho);
-    const int64_t f = q / Ho;
+  for (I i = (I)blockIdx.x * 256 + threadIdx.x; i < total; i += (I)gridDim.x * 256) {
+    const int c = (int)(i % (I)C4) * 4;
+    I q = i / (I)C4;
+    const int wo = (int)(q % (I)Wo); q /= (I)Wo;
+    const int ho = (int)(q % (I)Ho);
+    const int64_t f = (int64_t)(q / (I)Ho);
     const float4 w = ldg4(bn.w + c), b = ldg4(bn.b + c), rm = ldg4(bn.rm + c), rv = ldg4(bn.rv + c);
     float4 k;
     k.x = w.x * (1.f / sqrtf(rv.x + bn.eps)); k.y = w.y * (1.f / sqrtf(rv.y + bn.eps));
@@ -89,20 +92,28 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __re
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       if (!ok[t]) continue;
-      const float yx = fmaxf(fmaf(v[t].x - rm.x, k.x, b.x), 0.f), yy = fmaxf(fmaf(v[t].y - rm.y, k.y, b.y), 0.f);
-      const float yz = fmaxf(fmaf(v[t].z - rm.z, k.z, b.z), 0.f), yw = fmaxf(fmaf(v[t].w - rm.w, k.w, b.w), 0.f);
+      // The ReLU is applied to the maximum, not to the nine candidates: when the largest y is positive the first maximum
+      // of y and of relu(y) coincide; when it is not, the output is 0 either way and the recorded position is irrelevant
+      // -- the backward masks that pixel's gradient with y > 0.
+      const float yx = fmaf(v[t].x - rm.x, k.x, b.x), yy = fmaf(v[t].y - rm.y, k.y, b.y);
+      const float yz = fmaf(v[t].z - rm.z, k.z, b.z), yw = fmaf(v[t].w - rm.w, k.w, b.w);
       if (yx > m.x) { m.x = yx; cx = t; }
       if (yy > m.y) { m.y = yy; cy = t; }
       if (yz > m.z) { m.z = yz; cz = t; }
       if (yw > m.w) { m.w = yw; cw = t; }
     }
-    st4(out + i * 4, m);
+    m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f);
+    st4(out + (int64_t)i * 4, m);
     reinterpret_cast<uint32_t*>(code)[i] = cx | (cy << 8) | (cz << 16) | (cw << 24);
   }
 }
 
-// CTA = 256 threads = 16 pixel slots x 16 channel quads (C = 64); grid-stride over blocks of pixels.  Per input pixel:
-// gather the pooled gradients of the <= 4 windows whose recorded winner it is, apply the ReLU mask and the BN map.
+// CTA = 256 threads = 16 column slots x 16 channel quads (C = 64).  A thread handles a 2 x 2 block of input pixels
+// (rows 2i, 2i+1; columns 2j, 2j+1): the block lies inside the four windows (i..i+1) x (j..j+1) and no other, so four
+// pooled-gradient / code loads serve four pixels (a pixel on its own needs 1, 2, 2 or 4 of them: nine per block), and
+// every window position is a compile-time constant.  A CTA owns a contiguous range of row pairs (the pooled row i+1 it
+// gathers from is in its L1 again for the next pair); all twelve loads of a block are issued before the first use.
+// Per pixel: sum the pooled gradients of the windows whose recorded winner it is, apply the ReLU mask and the BN map.
 __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __restrict__ gpool,
                                                               const uint8_t* __restrict__ code,
                                                               const float* __restrict__ x, StemBN bn,
@@ -121,49 +132,67 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __re
   istd.z = 1.f / sqrtf(rv.z + bn.eps); istd.w = 1.f / sqrtf(rv.w + bn.eps);
   k.x = w.x * istd.x; k.y = w.y * istd.y; k.z = w.z * istd.z; k.w = w.w * istd.w;
   float4 agw = make_float4(0.f, 0.f, 0.f, 0.f), agb = agw;
-  const int64_t npix = (int64_t)F * H * W;
-  for (int64_t p = (int64_t)blockIdx.x * slots + slot; p < npix; p += (int64_t)gridDim.x * slots) {
-    const int ww = (int)(p % W);
-    const int64_t q = p / W;
-    const int h = (int)(q % H);
-    const int64_t f = q / H;
-    const float4 xv = ld_stream4(x + p * C + c);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    // windows containing (h, ww): ho in {floor(h/2), and (h+1)/2 when h is odd}, likewise for the columns.  All (up to
-    // four) code / gradient loads are issued before the first use.
-    const int ho0 = h >> 1, nho = (h & 1) ? 2 : 1;
-    const int wo0 = ww >> 1, nwo = (ww & 1) ? 2 : 1;
-    uint32_t cd[4], mine[4];
-    float4 gp[4];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t npairs = (int64_t)F * Ho;
+  const int64_t ppc = (npairs + gridDim.x - 1) / gridDim.x;
+  const int64_t pr0 = (int64_t)blockIdx.x * ppc, pr1 = pr0 + ppc < npairs ? pr0 + ppc : npairs;
+  for (int64_t pr = pr0; pr < pr1; ++pr) {
+    const int i = (int)(pr % Ho);
+    const int64_t f = pr / Ho;
+    const bool row1 = 2 * i + 1 < H, win1 = i + 1 < Ho;        // second pixel row / second window row exist
+    const float* xr = x + ((f * H + 2 * i) * W) * C + c;
+    float* gr = gx + ((f * H + 2 * i) * W) * C + c;
+    const int64_t o0 = ((f * Ho + i) * Wo) * C4 + lane;         // quad index of window (i, 0); + Wo*C4 for row i+1
+    for (int j = slot; j < Wo; j += slots) {
+      const bool col1 = 2 * j + 1 < W, wcol1 = j + 1 < Wo;
+      // pixel (dy, dx) -> xv[2*dy + dx]; window (a, bb) -> gp / cd[2*a + bb]
+      float4 xv[4], gp[4];
+      uint32_t cd[4];
+      const int64_t xo = (int64_t)(2 * j) * C;
+      xv[0] = ld_stream4(xr + xo);
+      xv[1] = col1 ? ld_stream4(xr + xo + C) : z4;
+      xv[2] = row1 ? ld_stream4(xr + xo + (int64_t)W * C) : z4;
+      xv[3] = (row1 && col1) ? ld_stream4(xr + xo + (int64_t)W * C + C) : z4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int a = i >> 1, bb = i & 1;
-      const int ho = ho0 + a, wo = wo0 + bb;
-      const bool ok = a < nho && bb < nwo && ho < Ho && wo < Wo;
-      mine[i] = (uint32_t)(3 * (h - (2 * ho - 1)) + (ww - (2 * wo - 1)));
-      cd[i] = 0xffffffffu;                       // matches no window position
-      gp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-        const int64_t o = ((f * Ho + ho) * Wo + wo) * C4 + lane;
-        cd[i] = __ldg(reinterpret_cast<const uint32_t*>(code) + o);
-        gp[i] = ldg4(gpool + o * 4);
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = ((q >> 1) == 0 || win1) && ((q & 1) == 0 || wcol1);
+        const int64_t o = o0 + (int64_t)(q >> 1) * Wo * C4 + (int64_t)(j + (q & 1)) * C4;
+        cd[q] = 0xffffffffu;                     // matches no window position
+        gp[q] = z4;
+        if (ok) {
+          cd[q] = __ldg(reinterpret_cast<const uint32_t*>(code) + o);
+          gp[q] = ldg4(gpool + o * 4);
+        }
+      }
+      // position of pixel (dy, dx) inside window (a, bb): 3 * (dy - 2a + 1) + (dx - 2bb + 1); outside it when negative
+      float4 g[4] = {z4, z4, z4, z4};
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ry = (px >> 1) - 2 * (q >> 1) + 1, rx = (px & 1) - 2 * (q & 1) + 1;
+          if (ry < 0 || rx < 0) continue;
+          const uint32_t mine = (uint32_t)(3 * ry + rx);
+          if ((cd[q] & 0xffu) == mine) g[px].x += gp[q].x;
+          if (((cd[q] >> 8) & 0xffu) == mine) g[px].y += gp[q].y;
+          if (((cd[q] >> 16) & 0xffu) == mine) g[px].z += gp[q].z;
+          if ((cd[q] >> 24) == mine) g[px].w += gp[q].w;
+        }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        if (((px >> 1) && !row1) || ((px & 1) && !col1)) continue;
+        const float4 v = xv[px];
+        float4 gg = g[px];
+        // ReLU mask on y = BN(x)
+        const float yx = fmaf(v.x - rm.x, k.x, b.x), yy = fmaf(v.y - rm.y, k.y, b.y);
+        const float yz = fmaf(v.z - rm.z, k.z, b.z), yw = fmaf(v.w - rm.w, k.w, b.w);
+        gg.x = yx > 0.f ? gg.x : 0.f; gg.y = yy > 0.f ? gg.y : 0.f; gg.z = yz > 0.f ? gg.z : 0.f; gg.w = yw > 0.f ? gg.w : 0.f;
+        st4(gr + xo + (int64_t)(px >> 1) * W * C + (px & 1) * C, make_float4(gg.x * k.x, gg.y * k.y, gg.z * k.z, gg.w * k.w));
+        agb.x += gg.x; agb.y += gg.y; agb.z += gg.z; agb.w += gg.w;
+        agw.x = fmaf(gg.x, (v.x - rm.x) * istd.x, agw.x); agw.y = fmaf(gg.y, (v.y - rm.y) * istd.y, agw.y);
+        agw.z = fmaf(gg.z, (v.z - rm.z) * istd.z, agw.z); agw.w = fmaf(gg.w, (v.w - rm.w) * istd.w, agw.w);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if ((cd[i] & 0xffu) == mine[i]) g.x += gp[i].x;
-      if (((cd[i] >> 8) & 0xffu) == mine[i]) g.y += gp[i].y;
-      if (((cd[i] >> 16) & 0xffu) == mine[i]) g.z += gp[i].z;
-      if ((cd[i] >> 24) == mine[i]) g.w += gp[i].w;
-    }
-    // ReLU mask on y = BN(x)
-    const float yx = fmaf(xv.x - rm.x, k.x, b.x), yy = fmaf(xv.y - rm.y, k.y, b.y);
-    const float yz = fmaf(xv.z - rm.z, k.z, b.z), yw = fmaf(xv.w - rm.w, k.w, b.w);
-    g.x = yx > 0.f ? g.x : 0.f; g.y = yy > 0.f ? g.y : 0.f; g.z = yz > 0.f ? g.z : 0.f; g.w = yw > 0.f ? g.w : 0.f;
-    st4(gx + p * C + c, make_float4(g.x * k.x, g.y * k.y, g.z * k.z, g.w * k.w));
-    agb.x += g.x; agb.y += g.y; agb.z += g.z; agb.w += g.w;
-    agw.x = fmaf(g.x, (xv.x - rm.x) * istd.x, agw.x); agw.y = fmaf(g.y, (xv.y - rm.y) * istd.y, agw.y);
-    agw.z = fmaf(g.z, (xv.z - rm.z) * istd.z, agw.z); agw.w = fmaf(g.w, (xv.w - rm.w) * istd.w, agw.w);
   }
   // per-CTA partials -> ws[cta][2][C]; the last CTA sums them in CTA order (deterministic)
   float4 red[2] = {agw, agb};
@@ -372,7 +401,10 @@ int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code
   int64_t blocks = (total + 255) / 256;
   if (blocks > stem_grid() * 4) blocks = stem_grid() * 4;
   StemBN b{bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps};
-  bn_relu_pool_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4);
+  if (total + (int64_t)blocks * 256 < (int64_t)1 << 32)
+    bn_relu_pool_fwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4);
+  else
+    bn_relu_pool_fwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4);
   VITTA_CHECK_LAUNCH();
   return 0;
 }
@@ -390,9 +422,17 @@ int vitta_bn_relu_pool_bwd(const float* gpool, const uint8_t* code, const float*
   VITTA_CHECK_ARG(aligned16(gpool) && aligned16(x) && aligned16(gx) && aligned16(ws), VITTA_E_ALIGN,
                   "bn_relu_pool_bwd: alignment");
   StemBN b{bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps};
-  const int slots = 256 / (C / 4);
-  const int64_t npix = (int64_t)F * H * W;
-  int64_t blocks = (npix + slots - 1) / slots;
+  // Row pairs in contiguous ranges; exactly the CTAs that are resident at once (the register count decides: a grid of
+  // 4 per SM with 3 resident ran a second, one-third-full wave), never more than the workspace has partial slots for.
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_relu_pool_bwd_kernel, 256, 0) != cudaSuccess || n < 1) n = 1;
+    per_sm = n;
+  }
+  int64_t blocks = (int64_t)F * ((H + 1) / 2);
+  const int64_t resident = (int64_t)per_sm * (stem_grid() / 4);
+  if (blocks > resident) blocks = resident;
   if (blocks > stem_grid()) blocks = stem_grid();
   bn_relu_pool_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gpool, code, x, b, gx, ws, gw, gb, F, H, W,
                                                                             C / 4, stem_grid() * 2 * C);

@@ -89,7 +89,7 @@ static inline int tam_chunk_rows(int64_t HW, int C) {
 // CTA = (n, row chunk, channel tile).  Thread = (float4 of channels, frame slot): owns frames t = slot, slot+rs, ...
 //   gx[t]    = act[t] * (k0*g[t+1] + k1*g[t] + k2*g[t-1])
 //   D[t][k]  = sum_p g[t-k+1][p] * x[t][p]                 (partial over the chunk's rows)
-__global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 2) tam_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                                                           const float* __restrict__ kern, const float* __restrict__ act,
                                                           float* __restrict__ gx, float* __restrict__ dpart, int N, int T,
                                                           int64_t HW, int C, int lpr, int rs, int nchunks, int chunk_rows) {
@@ -124,15 +124,28 @@ __global__ void __launch_bounds__(kThreads) tam_bwd_kernel(const float* __restri
       d2 = fma4(gm, xv, d2);
     };
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Two rows per batch.  The loads that go to HBM (this frame's g and x) are issued one batch AHEAD of their use, so
+    // they stay in flight across the arithmetic and the stores of the current batch; the neighbour frames' g rows are
+    // being fetched by the adjacent frame slots of this CTA at the same moment (L1 / L2 hits) and are loaded in place.
     int p = 0;
-    for (; p + 1 < np; p += 2) {       // two rows per batch: eight loads in flight before the first use
+    float4 g1a = z, g1b = z, xa = z, xb = z;
+    if (np >= 2) {
+      g1a = ldg4(gout + base); g1b = ldg4(gout + base + C);
+      xa = ld_stream4(x + base); xb = ld_stream4(x + base + C);
+    }
+    for (; p + 1 < np; p += 2) {
       const int64_t o0 = base + (int64_t)p * C, o1 = o0 + C;
-      const float4 g1a = ldg4(gout + o0), g1b = ldg4(gout + o1);
       const float4 gpa = hp ? ldg4(gout + o0 + ts) : z, gpb = hp ? ldg4(gout + o1 + ts) : z;
       const float4 gma = hm ? ldg4(gout + o0 - ts) : z, gmb = hm ? ldg4(gout + o1 - ts) : z;
-      const float4 xa = ld_stream4(x + o0), xb = ld_stream4(x + o1);
+      float4 ng1a = z, ng1b = z, nxa = z, nxb = z;
+      if (p + 3 < np) {
+        const int64_t n0 = o0 + 2 * (int64_t)C, n1 = n0 + C;
+        ng1a = ldg4(gout + n0); ng1b = ldg4(gout + n1);
+        nxa = ld_stream4(x + n0); nxb = ld_stream4(x + n1);
+      }
       body(g1a, gpa, gma, xa, o0);
       body(g1b, gpb, gmb, xb, o1);
+      g1a = ng1a; g1b = ng1b; xa = nxa; xb = nxb;
     }
     if (p < np) {
       const int64_t off = base + (int64_t)p * C;

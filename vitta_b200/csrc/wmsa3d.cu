@@ -1298,7 +1298,10 @@ __global__ void __launch_bounds__(kB3Threads, 1) wmsa3d_bwd3_kernel(const WmsaBw
             // predicated straight-line LDS / FFMA / STS on the warp-private copy is race free; program order keeps the
             // successive columns coherent -- (row, column) pairs of DIFFERENT columns do share entries (same relative
             // position), which is why the 16 updates cannot be batched (all loads first loses updates: tried) and why this
-            // chain costs ~1000 cycles per chunk.  Shared-memory atomicAdd (a CAS loop for fp32) was slower still.
+            // chain costs ~1000 cycles per chunk.  Shared-memory atomicAdd (a CAS loop for fp32) was slower still, and so
+            // was a fixed-point variant on the native 32-bit integer atomics (two digits per element, drained into a 64-bit
+            // sum by the loaders once per item: exact and order independent, but 32 ATOMS per thread and chunk cost more
+            // than the chain -- 1.77 ms against 1.60 ms for the stage-1 geometry of tools/one_wmsa.py).
             const float k_dt = (kDsUp * inv_sd) * inv_sq;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
