@@ -260,6 +260,10 @@ int64_t vitta_stem_wgrad_ws_floats(void);
 int vitta_stem_wgrad(const float* XP, const float* dY, float* dW, float* ws, int F, int H, int W, void* stream);
 int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
                            void* stream);
+/* ... that also accumulates max|out| into the device scalar *amax_out (zeroed by the caller): the operand range of the
+ * fp16-split convolutions that consume `out` (layer1.0's conv1 and downsample), so no separate range pass reads it again */
+int vitta_bn_relu_pool_fwd_amax(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
+                                float* amax_out, void* stream);
 int64_t vitta_bn_relu_pool_bwd_ws_floats(int C);
 int vitta_bn_relu_pool_bwd(const float* gpool, const uint8_t* code, const float* x, VittaBN bn, float* gx, float* gw,
                            float* gb, float* ws, int F, int H, int W, int C, void* stream);

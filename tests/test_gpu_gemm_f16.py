@@ -229,6 +229,42 @@ def test_tam_emits_the_range_of_its_output(cuda_device, f16_precision):
     assert float(out._vitta_amax[0]) == float(out.abs().max())
 
 
+def test_stem_pool_emits_the_range_of_its_output(cuda_device, f16_precision):
+    """vitta_bn_relu_pool_fwd_amax: the scalar attached to the pooled map equals its maximum exactly (out >= 0)."""
+    ops = f16_precision
+    g = torch.Generator().manual_seed(4)
+    f, c, h, w = 3, 64, 30, 26
+    x = (torch.randn(f, c, h, w, generator=g) * 2.0).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    wgt, b = (torch.rand(c, generator=g) + 0.5).to(cuda_device), (torch.randn(c, generator=g) * 0.3).to(cuda_device)
+    rm, rv = (torch.randn(c, generator=g) * 0.2).to(cuda_device), (torch.rand(c, generator=g) + 0.5).to(cuda_device)
+    out = ops.BnReluPoolFn.apply(x, wgt, b, rm, rv, 1e-5)
+    assert float(out._vitta_amax[0]) == float(out.max()) and float(out.min()) >= 0.0
+
+
+def test_shortcut_alias_inherits_the_range_of_the_block_input(cuda_device, f16_precision):
+    """conv2d_shortcut hands out an alias of the block input for the residual path: it is a new tensor object, and the
+    downsample convolution that consumes it must find the range the input already carries (no standalone pass)."""
+    import torch.nn as nn
+    ops = f16_precision
+    g = torch.Generator().manual_seed(6)
+    f, c, h = 4, 64, 14
+    bn = nn.BatchNorm2d(c).to(cuda_device).eval()
+    x0 = torch.randn(f, c, h, h, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x, _ = ops.bn_act(x0, bn, True)
+    wt = (torch.randn(32, c, 1, 1, generator=g) / 8).to(cuda_device).requires_grad_(True)
+    y, alias = ops.conv2d_shortcut(x, wt, 1, 0)
+    assert alias is not x and alias._vitta_amax[0] is x._vitta_amax[0]
+    calls = []
+    real = ops.amax_f32
+    ops.amax_f32 = lambda t, out=None: (calls.append(tuple(t.shape)), real(t, out))[1]
+    try:
+        wd = (torch.randn(128, c, 1, 1, generator=g) / 8).to(cuda_device).requires_grad_(True)
+        ops.conv2d(alias, wd, 2, 0)
+    finally:
+        ops.amax_f32 = real
+    assert (f, c, h, h) not in calls          # (the new weight's own range pass, shape (128, 64), is expected)
+
+
 @pytest.mark.parametrize("f,h,cin,cout,kh,stride,pad", [(4, 14, 64, 128, 3, 1, 1), (4, 28, 128, 256, 1, 2, 0)])
 def test_conv_with_fused_ranges_equals_standalone_ranges(cuda_device, f16_precision, f, h, cin, cout, kh, stride, pad):
     """bn_act -> conv -> bn_act under f16x3: with the ranges taken from the producers the results are bit-identical to

@@ -151,6 +151,7 @@ _SIGNATURES = {
     "vitta_stem_wgrad_ws_floats": (C.c_int64, []),
     "vitta_stem_wgrad": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_bn_relu_pool_fwd": (C.c_int, [_P, VittaBN, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitta_bn_relu_pool_fwd_amax": (C.c_int, [_P, VittaBN, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vitta_bn_relu_pool_bwd_ws_floats": (C.c_int64, [C.c_int]),
     "vitta_bn_relu_pool_bwd": (C.c_int, [_P, _P, _P, VittaBN, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitta_bn_fold_bias_multi": (C.c_int, [_P, C.c_int, _P]),

@@ -796,6 +796,72 @@ __global__ void __launch_bounds__(256) split_multi_kernel(const SplitEntry* __re
   const int cnt = (int)(rem < kSplitBlock ? rem : kSplitBlock);
   float sc = 1.f, inv_unused;
   if constexpr (F16) f16_split_scale(__ldcg(t.amax), sc, inv_unused);
+  // Fast path: the innermost destination extent (R in mode 1, Cc in mode 0) is a multiple of 8, so 8 consecutive
+  // destination elements share their outer indices: one index decomposition (32-bit) and one 16-byte store per operand
+  // half instead of eight of each; the source is read with stride 1 (two 16-byte loads), T (tap-inner conv weights) or
+  // Cc * T (transposed form; the eight neighbours of a sector are fetched by adjacent threads' groups -> L1).  Same
+  // arithmetic per element as the loop below: bit-identical operands.
+  const int inner = (t.mode == 1) ? t.R : t.Cc;
+  if ((inner & 7) == 0 && t.n < ((int64_t)1 << 31) && (reinterpret_cast<uintptr_t>(t.hi) & 15u) == 0 &&
+      (reinterpret_cast<uintptr_t>(t.lo) & 15u) == 0) {
+    for (int k = threadIdx.x * 8; k < cnt; k += 256 * 8) {
+      const uint32_t i = (uint32_t)e0 + (uint32_t)k;
+      uint32_t s0, stride;
+      int r0, rstep;
+      if (t.mode == 1) {   // dst [c][t'][r], r = r0 .. r0 + 7
+        const uint32_t r = i % (uint32_t)t.R, q = i / (uint32_t)t.R;
+        const uint32_t tp = (uint32_t)t.T - 1u - q % (uint32_t)t.T, c = q / (uint32_t)t.T;
+        s0 = t.src_tap_inner ? (r * (uint32_t)t.Cc + c) * (uint32_t)t.T + tp : (r * (uint32_t)t.T + tp) * (uint32_t)t.Cc + c;
+        stride = (uint32_t)t.Cc * (uint32_t)t.T;
+        r0 = (int)r; rstep = 1;
+      } else {             // dst [r][t][c], c = c0 .. c0 + 7
+        const uint32_t c = i % (uint32_t)t.Cc, q = i / (uint32_t)t.Cc;
+        const uint32_t tp = q % (uint32_t)t.T, r = q / (uint32_t)t.T;
+        s0 = t.src_tap_inner ? (r * (uint32_t)t.Cc + c) * (uint32_t)t.T + tp : (r * (uint32_t)t.T + tp) * (uint32_t)t.Cc + c;
+        stride = t.src_tap_inner ? (uint32_t)t.T : 1u;
+        r0 = (int)r; rstep = 0;
+      }
+      float w[8];
+      if (stride == 1u && (reinterpret_cast<uintptr_t>(t.src) & 15u) == 0) {
+        const float4 a = ldg4(t.src + s0), b = ldg4(t.src + s0 + 4);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __ldg(t.src + s0 + (uint32_t)j * stride);
+      }
+      if (t.fold_w) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = w[j] * split_row_scale(t, r0 + j * rstep);
+      }
+      if constexpr (F16) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = w[2 * j] * sc, v1 = w[2 * j + 1] * sc;
+          const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+          const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+          h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(static_cast<__half*>(t.hi) + i) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(static_cast<__half*>(t.lo) + i) = make_uint4(l[0], l[1], l[2], l[3]);
+      } else {
+        float hh[8], ll[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hh[j] = tf32_rna(w[j]);
+          ll[j] = w[j] - hh[j];
+        }
+        float* ph = static_cast<float*>(t.hi) + i;
+        float* pl = static_cast<float*>(t.lo) + i;
+        st4(ph, make_float4(hh[0], hh[1], hh[2], hh[3]));
+        st4(ph + 4, make_float4(hh[4], hh[5], hh[6], hh[7]));
+        st4(pl, make_float4(ll[0], ll[1], ll[2], ll[3]));
+        st4(pl + 4, make_float4(ll[4], ll[5], ll[6], ll[7]));
+      }
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < cnt; k += 256) {
     const int64_t i = e0 + k;
     int r, tp, c;

@@ -61,10 +61,13 @@ struct StemBN {
 // the first maximum wins (strict >).  code = 3*dh + dw of the winner.
 // I = uint32_t when the flat index fits (the index decomposition is three divisions per thread and iteration, and 64-bit
 // ones cost more issue slots than the nine loads they address).
+// amax_out (optional): max|out| accumulates there -- the operand range the fp16-split convolutions of layer1.0 need.
 template <typename I>
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ x, StemBN bn,
                                                               float* __restrict__ out, uint8_t* __restrict__ code,
-                                                              int F, int H, int W, int C4) {
+                                                              int F, int H, int W, int C4,
+                                                              float* __restrict__ amax_out) {
+  float am = 0.f;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const I total = (I)F * Ho * Wo * C4;
   const int C = C4 * 4;
@@ -105,6 +108,11 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __re
     m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f);
     st4(out + (int64_t)i * 4, m);
     reinterpret_cast<uint32_t*>(code)[i] = cx | (cy << 8) | (cz << 16) | (cw << 24);
+    am = fmaxf(fmaxf(am, fmaxf(m.x, m.y)), fmaxf(m.z, m.w));      // out >= 0
+  }
+  if (amax_out) {   // non-negative floats order like their bit patterns; the loop above has re-converged the warp
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if ((threadIdx.x & 31) == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(amax_out), wmax);
   }
 }
 
@@ -390,8 +398,8 @@ int vitta_stem_pack_weight(const float* w, float* hi, float* lo, void* stream) {
   return 0;
 }
 
-int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
-                           void* stream) {
+static int bn_relu_pool_fwd_impl(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
+                                 float* amax_out, void* stream) {
   VITTA_CHECK_ARG(x && out && code && bn.weight && bn.bias && bn.running_mean && bn.running_var, VITTA_E_BADARG,
                   "bn_relu_pool_fwd: null pointer");
   VITTA_CHECK_ARG(F > 0 && H > 1 && W > 1 && C > 0 && C % 4 == 0, VITTA_E_BADARG, "bn_relu_pool_fwd: bad shape");
@@ -402,11 +410,25 @@ int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code
   if (blocks > stem_grid() * 4) blocks = stem_grid() * 4;
   StemBN b{bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps};
   if (total + (int64_t)blocks * 256 < (int64_t)1 << 32)
-    bn_relu_pool_fwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4);
+    bn_relu_pool_fwd_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4,
+                                                                                        amax_out);
   else
-    bn_relu_pool_fwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4);
+    bn_relu_pool_fwd_kernel<int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, b, out, code, F, H, W, C / 4,
+                                                                                       amax_out);
   VITTA_CHECK_LAUNCH();
   return 0;
+}
+
+int vitta_bn_relu_pool_fwd(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
+                           void* stream) {
+  return bn_relu_pool_fwd_impl(x, bn, out, code, F, H, W, C, nullptr, stream);
+}
+
+// ... and max|out| accumulated into *amax_out (a device scalar the caller zeroed)
+int vitta_bn_relu_pool_fwd_amax(const float* x, VittaBN bn, float* out, uint8_t* code, int F, int H, int W, int C,
+                                float* amax_out, void* stream) {
+  VITTA_CHECK_ARG(amax_out, VITTA_E_BADARG, "bn_relu_pool_fwd_amax: amax_out is required");
+  return bn_relu_pool_fwd_impl(x, bn, out, code, F, H, W, C, amax_out, stream);
 }
 
 int64_t vitta_bn_relu_pool_bwd_ws_floats(int C) {

@@ -1265,7 +1265,13 @@ class Conv2dFn(torch.autograd.Function):
 
 def conv2d_shortcut(x, w, stride, pad):
     """conv2d(x, w) and an alias of x for the residual path (see Conv2dFn.forward)."""
-    return Conv2dFn.apply(x, w, stride, pad, True)
+    y, alias = Conv2dFn.apply(x, w, stride, pad, True)
+    # the alias is a new tensor object over the same values: hand the operand range on, or the block's downsample
+    # convolution pays a standalone range pass over a tensor whose range is already known
+    ent = getattr(x, "_vitta_amax", None)
+    if ent is not None and ent[1] == x._version and ent[2] == _amax_gen:
+        _attach_amax(alias, ent[0])
+    return y, alias
 
 
 def conv2d(x, w, stride, pad):
@@ -1348,8 +1354,14 @@ class BnReluPoolFn(torch.autograd.Function):
         ho, wo = (h + 1) // 2, (wd + 1) // 2
         out = torch.empty((f, c, ho, wo), dtype=torch.float32, device=x.device, memory_format=CL)
         code = torch.empty(f * ho * wo * c, dtype=torch.uint8, device=x.device)
-        call("vitta_bn_relu_pool_fwd", ptr(x), _lib.make_bn(w, b, rm, rv, eps), ptr(out), ptr(code), f, h, wd, c,
-             stream_ptr())
+        if _fused_amax():
+            am = new_amax(x.device)
+            call("vitta_bn_relu_pool_fwd_amax", ptr(x), _lib.make_bn(w, b, rm, rv, eps), ptr(out), ptr(code), f, h, wd, c,
+                 ptr(am), stream_ptr())
+            _attach_amax(out, am)
+        else:
+            call("vitta_bn_relu_pool_fwd", ptr(x), _lib.make_bn(w, b, rm, rv, eps), ptr(out), ptr(code), f, h, wd, c,
+                 stream_ptr())
         ctx.save_for_backward(x, w, b, rm, rv, code)
         ctx.eps = eps
         return out
