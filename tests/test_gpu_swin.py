@@ -22,7 +22,8 @@ def _rnd(*shape, seed=0, scale=1.0, dev="cuda"):
 # ----------------------------------------------------------------------------------------------
 # K9 LayerNorm
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,c", [(300, 32), (1000, 96), (777, 512), (260, 1024), (130, 1536), (64, 2048)])
+@pytest.mark.parametrize("rows,c", [(300, 32), (1000, 96), (1003, 128), (2049, 192), (515, 256), (777, 512), (260, 1024),
+                                    (130, 1536), (64, 2048)])
 def test_layernorm_fwd_bwd_vs_float64(cuda_device, rows, c):
     from vitta_b200 import ops_swin
     x = _rnd(rows, c, seed=1, scale=1.7) + 0.3
@@ -42,7 +43,7 @@ def test_layernorm_fwd_bwd_vs_float64(cuda_device, rows, c):
     cases.assert_close(db.cpu(), bd.grad.cpu(), 1e-4, 1e-4, "ln dbeta")
 
 
-@pytest.mark.parametrize("rows,c", [(5000, 64), (12544, 512), (3136, 1024)])
+@pytest.mark.parametrize("rows,c", [(5000, 64), (5003, 96), (4097, 192), (12544, 512), (3136, 1024)])
 def test_layernorm_fused_statistics_and_hook_gradient(cuda_device, rows, c):
     """LN forward emits the hook's per-channel statistics; LN backward adds the closed-form hook gradient."""
     from vitta_b200 import ops, ops_swin

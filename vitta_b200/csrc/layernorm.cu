@@ -81,60 +81,96 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
   }
   float nrow = 0.f;
   float am = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    int64_t base;
-    int h0 = 0, w0 = 0;
-    const float* src = ln_src_row(p.x, r, p.C, p.g, base, h0, w0);
-    float4 v[VPL];
-    float s = 0.f;
+  // R rows per pass, stage by stage over all of them: loads, row sums, the two shuffle reductions, then the per-row
+  // epilogue.  A row's critical path (load -> 5 shuffles -> 5 shuffles -> rsqrt -> store) is ~400 cycles; one row per pass
+  // left the narrow stages (C = 96: 384 bytes per row and warp) bound by that chain at half of the copy bandwidth, whatever
+  // the number of loads in flight.  Rows past the end are predicated (zero data), never branched around, so the R
+  // reduction chains of a pass interleave.
+  constexpr int R = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);
+  for (int64_t rb = r0; rb < r1; rb += R) {
+    float4 v[R][VPL];
+    float s[R], q[R], mu[R], rs[R];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < C4) {
-        if (!p.g.merge) {
-          v[j] = ld_stream4(src + base + (int64_t)i * 4);
-        } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
-          v[j] = ld_stream4(src + base + goff[j]);
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k;
+      const bool live = r < r1;
+      int64_t base = 0;
+      int h0 = 0, w0 = 0;
+      const float* src = ln_src_row(p.x, live ? r : r0, p.C, p.g, base, h0, w0);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        v[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < C4 && live) {
+          if (!p.g.merge) {
+            v[k][j] = ld_stream4(src + base + (int64_t)i * 4);
+          } else if (h0 + gdh[j] < p.g.H && w0 + gdw[j] < p.g.W) {
+            v[k][j] = ld_stream4(src + base + goff[j]);
+          }
         }
       }
-      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
-    const float mu = warp_sum(s) * invC;
-    float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      if (i < C4) {
-        const float a = v[j].x - mu, b = v[j].y - mu, c = v[j].z - mu, d = v[j].w - mu;
-        q += (a * a + b * b) + (c * c + d * d);
+    for (int k = 0; k < R; ++k) {
+      s[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) s[k] += (v[k][j].x + v[k][j].y) + (v[k][j].z + v[k][j].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      mu[k] = s[k] * invC;
+      q[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * 32 + lane;
+        if (i < C4) {
+          const float a = v[k][j].x - mu[k], b = v[k][j].y - mu[k], c = v[k][j].z - mu[k], d = v[k][j].w - mu[k];
+          q[k] += (a * a + b * b) + (c * c + d * d);
+        }
       }
     }
-    const float rs = 1.f / sqrtf(warp_sum(q) * invC + p.eps);
-    if (lane == 0) {
-      p.mean[r] = mu;
-      p.rstd[r] = rs;
-    }
-    nrow += 1.f;
-    const float inv_n = 1.f / nrow;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = j * 32 + lane;
-      if (i < C4) {
-        const float4 ga = ldg4(p.gamma + i * 4), be = ldg4(p.beta + i * 4);
-        float4 y;
-        y.x = fmaf((v[j].x - mu) * rs, ga.x, be.x);
-        y.y = fmaf((v[j].y - mu) * rs, ga.y, be.y);
-        y.z = fmaf((v[j].z - mu) * rs, ga.z, be.z);
-        y.w = fmaf((v[j].w - mu) * rs, ga.w, be.w);
-        st4(p.y + r * p.C + (int64_t)i * 4, y);
-        am = fmaxf(am, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
-        if (STATS) {
-          float d;
-          d = y.x - wm[j].x; wm[j].x = fmaf(d, inv_n, wm[j].x); w2[j].x = fmaf(d, y.x - wm[j].x, w2[j].x);
-          d = y.y - wm[j].y; wm[j].y = fmaf(d, inv_n, wm[j].y); w2[j].y = fmaf(d, y.y - wm[j].y, w2[j].y);
-          d = y.z - wm[j].z; wm[j].z = fmaf(d, inv_n, wm[j].z); w2[j].z = fmaf(d, y.z - wm[j].z, w2[j].z);
-          d = y.w - wm[j].w; wm[j].w = fmaf(d, inv_n, wm[j].w); w2[j].w = fmaf(d, y.w - wm[j].w, w2[j].w);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) rs[k] = 1.f / sqrtf(q[k] * invC + p.eps);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = rb + k;
+      if (r < r1) {
+        if (lane == 0) {
+          p.mean[r] = mu[k];
+          p.rstd[r] = rs[k];
+        }
+        nrow += 1.f;
+        const float inv_n = 1.f / nrow;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int i = j * 32 + lane;
+          if (i < C4) {
+            const float4 ga = ldg4(p.gamma + i * 4), be = ldg4(p.beta + i * 4);
+            float4 y;
+            y.x = fmaf((v[k][j].x - mu[k]) * rs[k], ga.x, be.x);
+            y.y = fmaf((v[k][j].y - mu[k]) * rs[k], ga.y, be.y);
+            y.z = fmaf((v[k][j].z - mu[k]) * rs[k], ga.z, be.z);
+            y.w = fmaf((v[k][j].w - mu[k]) * rs[k], ga.w, be.w);
+            st4(p.y + r * p.C + (int64_t)i * 4, y);
+            am = fmaxf(am, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+            if (STATS) {
+              float d;
+              d = y.x - wm[j].x; wm[j].x = fmaf(d, inv_n, wm[j].x); w2[j].x = fmaf(d, y.x - wm[j].x, w2[j].x);
+              d = y.y - wm[j].y; wm[j].y = fmaf(d, inv_n, wm[j].y); w2[j].y = fmaf(d, y.y - wm[j].y, w2[j].y);
+              d = y.z - wm[j].z; wm[j].z = fmaf(d, inv_n, wm[j].z); w2[j].z = fmaf(d, y.z - wm[j].z, w2[j].z);
+              d = y.w - wm[j].w; wm[j].w = fmaf(d, inv_n, wm[j].w); w2[j].w = fmaf(d, y.w - wm[j].w, w2[j].w);
+            }
+          }
         }
       }
     }
@@ -151,6 +187,133 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnFwdArgs p) {
       if (i < C4) {
         st4(o + (int64_t)i * 8, make_float4(wm[j].x, w2[j].x, wm[j].y, w2[j].y));
         st4(o + (int64_t)i * 8 + 4, make_float4(wm[j].z, w2[j].z, wm[j].w, w2[j].w));
+      }
+    }
+  }
+}
+
+// Narrow rows (C <= 256, plain mode): LPR lanes per row, 32 / LPR rows per warp pass.  ncu on the one-warp-per-row kernel at
+// C = 96 (Video-Swin-T stage 1, 308 MB per tensor): 63 % issue-slot utilisation at a third of the warp slots and 41 % of
+// the DRAM bandwidth -- ~150 warp instructions per 384-byte row, so the kernel is bound by instruction issue, not by loads
+// in flight.  Here one instruction stream serves 4 (C <= 128) or 2 rows, all 32 lanes hold data (24 of 32 did at C = 96),
+// and the row reductions take log2(LPR) shuffle steps.  Per-column Welford statistics are kept per lane over the rows of
+// its group and merged across the groups (Chan) once per chunk.
+template <int LPR, int VPL, bool STATS>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_narrow_kernel(const LnFwdArgs p) {
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int64_t chunk = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int64_t r0 = chunk * p.rows_per_warp;
+  if (r0 >= p.rows) return;
+  const int64_t r1 = (r0 + p.rows_per_warp < p.rows) ? r0 + p.rows_per_warp : p.rows;
+  const int C4 = p.C >> 2;
+  const float invC = 1.f / (float)p.C;
+  float4 ga[VPL], be[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int i = j * LPR + sub;
+    ga[j] = be[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < C4) {
+      ga[j] = ldg4(p.gamma + i * 4);
+      be[j] = ldg4(p.beta + i * 4);
+    }
+  }
+  float4 wm[VPL], w2[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) wm[j] = w2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nrow = 0.f, am = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += G) {      // warp-uniform trip count: the shuffles below see all 32 lanes
+    const int64_t r = rb + grp;
+    const bool live = r < r1;
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * LPR + sub;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C4 && live) v[j] = ld_stream4(p.x + r * p.C + (int64_t)i * 4);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = j * LPR + sub;
+      if (i < C4) {
+        const float a = v[j].x - mu, b = v[j].y - mu, c = v[j].z - mu, d = v[j].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = 1.f / sqrtf(q * invC + p.eps);
+    if (live) {
+      if (sub == 0) {
+        p.mean[r] = mu;
+        p.rstd[r] = rs;
+      }
+      nrow += 1.f;
+      const float inv_n = 1.f / nrow;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        if (i < C4) {
+          float4 y;
+          y.x = fmaf((v[j].x - mu) * rs, ga[j].x, be[j].x);
+          y.y = fmaf((v[j].y - mu) * rs, ga[j].y, be[j].y);
+          y.z = fmaf((v[j].z - mu) * rs, ga[j].z, be[j].z);
+          y.w = fmaf((v[j].w - mu) * rs, ga[j].w, be[j].w);
+          st4(p.y + r * p.C + (int64_t)i * 4, y);
+          am = fmaxf(am, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+          if (STATS) {
+            float d;
+            d = y.x - wm[j].x; wm[j].x = fmaf(d, inv_n, wm[j].x); w2[j].x = fmaf(d, y.x - wm[j].x, w2[j].x);
+            d = y.y - wm[j].y; wm[j].y = fmaf(d, inv_n, wm[j].y); w2[j].y = fmaf(d, y.y - wm[j].y, w2[j].y);
+            d = y.z - wm[j].z; wm[j].z = fmaf(d, inv_n, wm[j].z); w2[j].z = fmaf(d, y.z - wm[j].z, w2[j].z);
+            d = y.w - wm[j].w; wm[j].w = fmaf(d, inv_n, wm[j].w); w2[j].w = fmaf(d, y.w - wm[j].w, w2[j].w);
+          }
+        }
+      }
+    }
+  }
+  if (p.amax_y) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_y), wmax);
+  }
+  if (STATS) {
+    // the G groups' (n, mean, M2) per column -> one: pairwise Chan merges in a fixed order
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      const float nb = __shfl_xor_sync(0xffffffffu, nrow, o);
+      const float nt = nrow + nb;
+      const float f = nt > 0.f ? nb / nt : 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        float* m = reinterpret_cast<float*>(&wm[j]);
+        float* m2 = reinterpret_cast<float*>(&w2[j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float mb = __shfl_xor_sync(0xffffffffu, m[e], o);
+          const float m2b = __shfl_xor_sync(0xffffffffu, m2[e], o);
+          const float d = mb - m[e];
+          m2[e] = m2[e] + m2b + d * d * nrow * f;
+          m[e] = fmaf(d, f, m[e]);
+        }
+      }
+      nrow = nt;
+    }
+    if (grp == 0) {
+      float* o = p.part + chunk * p.C * 2;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        if (i < C4) {
+          st4(o + (int64_t)i * 8, make_float4(wm[j].x, w2[j].x, wm[j].y, w2[j].y));
+          st4(o + (int64_t)i * 8 + 4, make_float4(wm[j].z, w2[j].z, wm[j].w, w2[j].w));
+        }
       }
     }
   }
@@ -763,6 +926,29 @@ int vitta_ln_fwd_amax(const float* x, const float* gamma, const float* beta, flo
   const unsigned grid = (unsigned)((ch.n_entries + kLnWarps - 1) / kLnWarps);
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = ln_vpl(C);
+  const int c4 = C / 4;
+  if (!p.g.merge && c4 > 16 && c4 <= 64 && ch.chunk_rows % 4 == 0) {
+    unsigned grid = (unsigned)((ch.n_entries + kLnWarps - 1) / kLnWarps);
+    if (!part) {
+      // no statistics entry to respect: 32 rows per warp (8 passes of 4 rows) amortise the per-warp prologue -- with the
+      // 8-row chunks of vitta_ln_chunking a warp ran two passes and the kernel was bound by its fixed part
+      int rpw = 32;
+      while (rpw > 8 && (rows + rpw - 1) / rpw < (int64_t)148 * 16 * kLnWarps) rpw >>= 1;
+      p.rows_per_warp = rpw;
+      const int64_t n = (rows + rpw - 1) / rpw;
+      grid = (unsigned)((n + kLnWarps - 1) / kLnWarps);
+    }
+#define VITTA_LN_NARROW(L, V)                                                            \
+  if (part) ln_fwd_narrow_kernel<L, V, true><<<grid, kLnThreads, 0, st>>>(p);            \
+  else ln_fwd_narrow_kernel<L, V, false><<<grid, kLnThreads, 0, st>>>(p)
+    if (c4 <= 24) { VITTA_LN_NARROW(8, 3); }
+    else if (c4 <= 32) { VITTA_LN_NARROW(8, 4); }
+    else if (c4 <= 48) { VITTA_LN_NARROW(16, 3); }
+    else { VITTA_LN_NARROW(16, 4); }
+#undef VITTA_LN_NARROW
+    VITTA_CHECK_LAUNCH();
+    return 0;
+  }
 #define VITTA_LN_FWD(V)                                                        \
   if (part) ln_fwd_kernel<V, true><<<grid, kLnThreads, 0, st>>>(p);            \
   else ln_fwd_kernel<V, false><<<grid, kLnThreads, 0, st>>>(p)
