@@ -499,6 +499,156 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_rows_kernel(const LnBwdA
   // the per-CTA partials are added by ln_bwd_finish_kernel (next launch on the stream)
 }
 
+// Narrow rows (64 < C <= 192, plain mode), the backward counterpart of ln_fwd_narrow_kernel: LPR lanes per row, G = 32 / LPR
+// rows per warp pass, all loads of a pass issued before the first use.  Same issue-bound picture as the forward: the
+// one-warp-per-row kernel spends a full instruction stream (and two 5-step shuffle reductions) on a 384-byte row.  gamma
+// stays in registers; the hook coefficients (rare on these stages) are read on use.  d(gamma) / d(beta): per lane over its
+// rows, then across the warp's row groups by shuffles, then the warps of the CTA in turn -- a fixed order.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_narrow_kernel(const LnBwdArgs p) {
+  constexpr int G = 32 / LPR, R = 1;   // (two passes in flight spill at the 128 registers two resident CTAs allow; one
+                                       //  pass is 9-12 loads of 16 bytes per lane: ~70 KB in flight per SM)
+  __shared__ float4 s_red[2 * 64];   // [2][C/4], C <= 192
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int C4 = p.C >> 2;
+  const float invC = 1.f / (float)p.C;
+  const float gsc = p.ca ? __ldg(p.gs) : 0.f;
+  float4 ga[VPL], dg[VPL], db[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int i = j * LPR + sub;
+    dg[j] = db[j] = ga[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < C4) ga[j] = ldg4(p.gamma + i * 4);
+  }
+  float am = 0.f;
+  const int64_t nquads = (p.rows + G - 1) / G;
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  for (int64_t qb = (int64_t)blockIdx.x * kLnWarps + warp; qb < nquads; qb += stride * R) {   // warp-uniform trip count
+    float4 xv[R][VPL], gyv[R][VPL], gav[R][VPL];
+    float mu[R], rs[R];
+    // ---- every load of the pass
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = (qb + k * stride) * G + grp;
+      const bool live = (qb + k * stride) < nquads && r < p.rows;
+      mu[k] = 0.f; rs[k] = 0.f;
+      if (live) {
+        mu[k] = __ldg(p.mean + r);
+        rs[k] = __ldg(p.rstd + r);
+      }
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        xv[k][j] = gyv[k][j] = gav[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < C4 && live) {
+          xv[k][j] = ld_stream4(p.x + r * p.C + (int64_t)i * 4);
+          if (p.gadd) gav[k][j] = ld_stream4(p.gadd + r * p.C + (int64_t)i * 4);
+          gyv[k][j] = ld_stream4(p.gy + r * p.C + (int64_t)i * 4);
+        }
+      }
+    }
+    // ---- dead rows carry zeros (gy = 0: no contribution) and store nothing
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t r = (qb + k * stride) * G + grp;
+      const bool live = (qb + k * stride) < nquads && r < p.rows;
+      float4 xh[VPL], g[VPL];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < C4 && live) {
+          const float4 v = xv[k][j];
+          float4 gy = gyv[k][j];
+          xh[j] = make_float4((v.x - mu[k]) * rs[k], (v.y - mu[k]) * rs[k], (v.z - mu[k]) * rs[k], (v.w - mu[k]) * rs[k]);
+          if (p.ca) {
+            const float4 be = ldg4(p.beta + i * 4);
+            const float4 a = ldg4(p.ca + i * 4), b = ldg4(p.cb + i * 4), m = ldg4(p.cm + i * 4);
+            gy.x = fmaf(gsc, fmaf(b.x, fmaf(xh[j].x, ga[j].x, be.x) - m.x, a.x), gy.x);
+            gy.y = fmaf(gsc, fmaf(b.y, fmaf(xh[j].y, ga[j].y, be.y) - m.y, a.y), gy.y);
+            gy.z = fmaf(gsc, fmaf(b.z, fmaf(xh[j].z, ga[j].z, be.z) - m.z, a.z), gy.z);
+            gy.w = fmaf(gsc, fmaf(b.w, fmaf(xh[j].w, ga[j].w, be.w) - m.w, a.w), gy.w);
+          }
+          db[j].x += gy.x; db[j].y += gy.y; db[j].z += gy.z; db[j].w += gy.w;
+          dg[j].x = fmaf(gy.x, xh[j].x, dg[j].x); dg[j].y = fmaf(gy.y, xh[j].y, dg[j].y);
+          dg[j].z = fmaf(gy.z, xh[j].z, dg[j].z); dg[j].w = fmaf(gy.w, xh[j].w, dg[j].w);
+          g[j] = make_float4(gy.x * ga[j].x, gy.y * ga[j].y, gy.z * ga[j].z, gy.w * ga[j].w);
+          s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+          s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float c1 = s1 * invC, c2 = s2 * invC;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        if (i < C4 && live) {
+          float4 o;
+          o.x = rs[k] * (g[j].x - c1 - xh[j].x * c2);
+          o.y = rs[k] * (g[j].y - c1 - xh[j].y * c2);
+          o.z = rs[k] * (g[j].z - c1 - xh[j].z * c2);
+          o.w = rs[k] * (g[j].w - c1 - xh[j].w * c2);
+          if (p.gadd) {
+            const float4 a = gav[k][j];
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          st4(p.gx + r * p.C + (int64_t)i * 4, o);
+          am = fmaxf(am, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+        }
+      }
+    }
+  }
+  if (p.amax_gx) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+    if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(p.amax_gx), wmax);
+  }
+  // the warp's row groups -> group 0 (fixed order), then the warps of the CTA in turn, then one partial per CTA
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      dg[j].x += __shfl_xor_sync(0xffffffffu, dg[j].x, o); dg[j].y += __shfl_xor_sync(0xffffffffu, dg[j].y, o);
+      dg[j].z += __shfl_xor_sync(0xffffffffu, dg[j].z, o); dg[j].w += __shfl_xor_sync(0xffffffffu, dg[j].w, o);
+      db[j].x += __shfl_xor_sync(0xffffffffu, db[j].x, o); db[j].y += __shfl_xor_sync(0xffffffffu, db[j].y, o);
+      db[j].z += __shfl_xor_sync(0xffffffffu, db[j].z, o); db[j].w += __shfl_xor_sync(0xffffffffu, db[j].w, o);
+    }
+  }
+  for (int w = 0; w < kLnWarps; ++w) {
+    if (warp == w && grp == 0) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = j * LPR + sub;
+        if (i < C4) {
+          if (w == 0) {
+            s_red[i] = dg[j];
+            s_red[64 + i] = db[j];
+          } else {
+            float4 a = s_red[i], b = s_red[64 + i];
+            a.x += dg[j].x; a.y += dg[j].y; a.z += dg[j].z; a.w += dg[j].w;
+            b.x += db[j].x; b.y += db[j].y; b.z += db[j].z; b.w += db[j].w;
+            s_red[i] = a;
+            s_red[64 + i] = b;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* wsb = p.ws + kWsHeader + (int64_t)blockIdx.x * 2 * p.C;
+  for (int i = threadIdx.x; i < C4; i += kLnThreads) {
+    st4(wsb + (int64_t)i * 4, s_red[i]);
+    st4(wsb + p.C + (int64_t)i * 4, s_red[64 + i]);
+  }
+  // the per-CTA partials are added by ln_bwd_finish_kernel (next launch on the stream)
+}
+
 // Wide rows (C > 256): a row is split over K = 1, 2, 4 or 8 warps of the CTA, 96 float4 (three per lane) each, and every
 // warp iteration works on TWO rows with all their loads in flight.  The one-row-per-warp kernel above kept the whole row
 // plus its d(gamma) / d(beta) accumulators in one warp's registers: 136 registers at C = 384, 218 at C = 768, 255 + spills
@@ -1002,7 +1152,14 @@ int vitta_ln_bwd_amax(const float* gy, const float* x, const float* gamma, const
   }
   unsigned grid = (unsigned)ln_bwd_grid(rows);
   const int vpl = ln_vpl(C);
-  if (vpl <= 2) {
+  const int c4 = C / 4;
+  if (!p.g.merge && c4 > 16 && c4 <= 48) {
+    // (four float4 per lane spill at the 128 registers two resident CTAs allow: C = 128 takes 16 lanes x 2, C = 256 stays
+    //  on the one-warp-per-row kernel)
+    if (c4 <= 24) ln_bwd_narrow_kernel<8, 3><<<grid, kLnThreads, 0, st>>>(p);
+    else if (c4 <= 32) ln_bwd_narrow_kernel<16, 2><<<grid, kLnThreads, 0, st>>>(p);
+    else ln_bwd_narrow_kernel<16, 3><<<grid, kLnThreads, 0, st>>>(p);
+  } else if (vpl <= 2) {
     if (vpl == 1) ln_bwd_rows_kernel<1><<<grid, kLnThreads, 0, st>>>(p);
     else ln_bwd_rows_kernel<2><<<grid, kLnThreads, 0, st>>>(p);
   } else {
