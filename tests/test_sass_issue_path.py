@@ -35,3 +35,32 @@ def test_tensor_core_kernels_issue_from_uniform_registers():
         # a handful of moves (predicates of ragged k-steps in the attention backward) are tolerated; the pathological
         # state is ~3 per MMA
         assert c.get("R2UR.BROADCAST", 0) <= 8, (name, mma, c.get("R2UR.BROADCAST", 0))
+
+
+@pytest.mark.skipif(not os.path.exists(CUOBJDUMP) or not os.path.exists(LIB), reason="needs cuobjdump and the built library")
+def test_streaming_kernels_fit_their_register_budget_without_spills():
+    """The HBM-bound kernels are sized for a fixed number of resident CTAs per SM (their grids and the loads they keep in
+    flight assume it): the default-path instantiations must not spill to local memory, and the sub-warp LayerNorm kernels
+    must stay inside the 128 registers two resident CTAs allow."""
+    out = subprocess.run([CUOBJDUMP, "-res-usage", LIB], capture_output=True, text=True, timeout=600).stdout
+    usage, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and cur:
+            usage[cur] = (int(m.group(1)), int(m.group(2)))
+            cur = None
+    assert len(usage) > 100
+    want = ["bn_relu_pool_bwd_kernel", "bn_relu_pool_fwd_kernelIj", "tam_bwd_kernel", "tam_fwd_kernel", "ln_fwd_narrow_kernel",
+            "ln_bwd_narrow_kernel", "stats_cl_kernel", "bn_act_fwd_kernel", "bn_act_bwd_amax_kernel"]
+    # (ln_bwd_split_kernel<8> is known to keep 32 bytes of stack at C > 1536 and is not listed)
+    for key in want:
+        hits = {k: v for k, v in usage.items() if key in k}
+        assert hits, key
+        for name, (regs, stack) in hits.items():
+            assert stack == 0, (name, regs, stack)
+            if "narrow" in name:
+                assert regs <= 128, (name, regs)
